@@ -1,0 +1,166 @@
+/*
+ * bdepth.h -- C ABI of libbdepth.so, the B200-native engine behind `sambamba depth`.
+ *
+ * The reference has NO foreign-function boundary on this path: `depth` is D
+ * ranges composed in one function, sambamba/depth.d:1211-1232.  This header therefore DEFINES
+ * the drop-in boundary at the seam where the reference hands data between layers:
+ *
+ *   reference seam (what each entry point replaces)                      entry point
+ *   -------------------------------------------------------------------  ----------------------
+ *   new MultiBamReader(files)            sambamba/depth.d:1163,          bdepth_open /
+ *     BamReader.this                     BioD/bio/std/hts/bam/reader.d:101-125   bdepth_open_memory
+ *   bam.header.sorting_order, has_index  depth.d:1164-1166               bdepth_is_coordinate_sorted,
+ *                                                                        bdepth_has_index
+ *   bam.reference_sequences[i].name/.length  reader.d:588-598            bdepth_n_ref/_ref_name/_ref_length
+ *   bam.header.read_groups -> sample table   depth.d:1170-1181           bdepth_n_samples/_sample_name
+ *   createFilterFromQuery(default)       depth.d:1159, filtering.d:40-51 bdepth_set_filter
+ *   printer.min_base_quality             depth.d:280,1129                bdepth_set_min_baseq
+ *   bam.getReadsOverlapping(bed)         depth.d:1211, multireader.d:357 bdepth_set_regions
+ *   foreach (column; pileupColumns(..)) printer.push(column)             bdepth_run_base   (PerBasePrinter,  depth.d:402-607)
+ *     BGZF inflate   BioD/bio/core/bgzf/block.d:127-216                  bdepth_run_windows(PerWindowPrinter, depth.d:933-1077)
+ *     record walk    BioD/bio/std/hts/bam/readrange.d:118-173            bdepth_run_regions(PerBedRegionPrinter, depth.d:879-931)
+ *     column sweep   BioD/bio/std/hts/bam/pileup.d:345-424
+ *
+ * Conventions: every entry returns 0 on success or a negative bdepth_status; the message is
+ * available through bdepth_last_error().  No exception crosses the boundary.  There is no CPU
+ * fallback: a missing GPU or a CUDA failure is BDEPTH_ERR_CUDA.  The library owns all device and
+ * pinned memory; pointers handed to callbacks are valid only during the callback (like the
+ * reference's transient Column, pileup.d:660-664).  Callbacks run on the calling thread, in
+ * (ref_id, position) order, never concurrently.  The caller owns path strings and region arrays
+ * for the duration of the call that receives them.
+ */
+#ifndef BDEPTH_H
+#define BDEPTH_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct bdepth bdepth_t;
+
+typedef enum {
+    BDEPTH_OK = 0,
+    BDEPTH_ERR_IO = -1,        /* cannot open / read / mmap                                  */
+    BDEPTH_ERR_FORMAT = -2,    /* BGZF / BAM / BAI / DEFLATE format error                    */
+    BDEPTH_ERR_UNSORTED = -3,  /* header does not say SO:coordinate  (depth.d:1164)          */
+    BDEPTH_ERR_NOINDEX = -4,   /* no .bai next to the file           (depth.d:1166)          */
+    BDEPTH_ERR_CUDA = -5,      /* no device, CUDA error, out of device memory                */
+    BDEPTH_ERR_NCCL = -6,
+    BDEPTH_ERR_ARG = -7,       /* bad argument / unsupported combination                     */
+    BDEPTH_ERR_CALLBACK = -8   /* a callback returned non-zero                               */
+} bdepth_status;
+
+/* 0-based half-open interval on a reference, same meaning as BamRegion
+ * (BioD/bio/std/hts/bam/region.d:28-31). */
+typedef struct { uint32_t ref_id, start, end; } bdepth_region;
+
+/* One position-ordered tile of per-base counters.  counts is SoA: plane p (A,C,G,T,N,DEL,REFSKIP
+ * = the seven counters of PerBasePrinter.writeColumn, depth.d:495-556) occupies
+ * counts[p * stride .. p * stride + len).  COV of the reference = sum of the 7 planes. */
+typedef struct {
+    int32_t  ref_id;
+    uint32_t start;      /* first position of the tile on ref_id          */
+    uint32_t len;        /* number of positions                           */
+    uint32_t stride;     /* elements between planes                       */
+    const uint32_t* counts;
+} bdepth_tile;
+enum { BDEPTH_PLANE_A = 0, BDEPTH_PLANE_C, BDEPTH_PLANE_G, BDEPTH_PLANE_T, BDEPTH_PLANE_N, BDEPTH_PLANE_DEL, BDEPTH_PLANE_REFSKIP, BDEPTH_N_PLANES };
+
+typedef int (*bdepth_tile_cb)(void* user, const bdepth_tile* tile);
+
+/* Per-window / per-region statistics = PerSampleRegionData (depth.d:609-635):
+ * n_reads, n_bases and, for every -T threshold, the number of positions with coverage >= it. */
+typedef struct {
+    int32_t  ref_id;
+    uint32_t start, end;
+    uint32_t n_reads;
+    uint32_t n_bases;
+    const uint32_t* cov_ge;   /* n_thresholds entries */
+} bdepth_region_stat;
+typedef int (*bdepth_stat_cb)(void* user, const bdepth_region_stat* stat, uint64_t index);
+
+/* Counters and device timings of the last run (all times in milliseconds, CUDA events). */
+typedef struct {
+    uint64_t file_bytes;          /* compressed .bam bytes consumed (this shard)                    */
+    uint64_t n_blocks;            /* BGZF data blocks inflated                                      */
+    uint64_t cdata_bytes;         /* C: sum of raw deflate payload bytes                            */
+    uint64_t inflated_bytes;      /* U: sum of ISIZE                                                */
+    uint64_t n_records;           /* R: alignment records scanned                                   */
+    uint64_t n_records_pass;      /* records passing filter with basesCovered() > 0                 */
+    uint64_t n_cigar_ops;         /* K: sum of n_cigar over scanned records                         */
+    uint64_t seq_bytes;           /* Q: sum of ceil(l_seq/2) over passing records                   */
+    uint64_t positions;           /* T: positions of the counter tiles processed                    */
+    uint64_t covered_positions;   /* positions with >=1 passing read (rows of default `depth base`) */
+    uint64_t long_reads;          /* passing reads routed to the atomic scatter path                */
+    uint64_t chain_fixups;        /* record-chain entry guesses corrected by verification           */
+    uint32_t gpu_launches;        /* kernels launched by the library in the run                     */
+    uint32_t n_batches;
+    float ms_h2d, ms_inflate, ms_scan, ms_coverage, ms_reduce, ms_d2h, ms_total_device;
+    double host_wall_ms;          /* wall clock of the whole call, host side                        */
+} bdepth_stats;
+
+/* ------------------------------------------------------------------ lifecycle */
+int  bdepth_device_count(void);
+/* Open a BAM by path (mmap) -- also looks for <path>.bai / <path minus ext>.bai. */
+int  bdepth_open(const char* bam_path, int device, bdepth_t** out);
+/* Open a BAM image held in host memory (pinned memory gives full-rate H2D).  bai may be NULL. */
+int  bdepth_open_memory(const void* bam, size_t bam_len, const void* bai, size_t bai_len, int device, bdepth_t** out);
+void bdepth_close(bdepth_t* h);
+/* h == NULL returns the message of the last failed open on this thread. */
+const char* bdepth_last_error(const bdepth_t* h);
+
+/* ------------------------------------------------------------------ header */
+int         bdepth_n_ref(const bdepth_t* h);
+const char* bdepth_ref_name(const bdepth_t* h, int i);
+uint32_t    bdepth_ref_length(const bdepth_t* h, int i);
+const char* bdepth_header_text(const bdepth_t* h, size_t* len);
+int         bdepth_is_coordinate_sorted(const bdepth_t* h);
+int         bdepth_has_index(const bdepth_t* h);
+int         bdepth_n_samples(const bdepth_t* h);                 /* >= 1; "*" when there is no @RG */
+const char* bdepth_sample_name(const bdepth_t* h, int i);
+
+/* ------------------------------------------------------------------ configuration */
+/* keep a read iff mapq > mapq_gt && (flag & flag_reject_mask) == 0.
+ * default (depth.d:1159): mapq_gt = 0, mask = 0x400 | 0x200.  -F "" : mapq_gt = -1, mask = 0. */
+int bdepth_set_filter(bdepth_t* h, int mapq_gt, uint32_t flag_reject_mask);
+int bdepth_set_min_baseq(bdepth_t* h, uint32_t min_base_quality);
+/* Restrict runs to reads overlapping these regions (any order; merged internally).  n = 0 clears. */
+int bdepth_set_regions(bdepth_t* h, const bdepth_region* regions, size_t n);
+/* Multi-GPU: this process handles shard `rank` of `world` (BGZF virtual-offset ranges cut at BAI
+ * linear-index record starts).  nccl_unique_id (128 bytes, identical on all ranks, from
+ * bdepth_nccl_unique_id on rank 0) enables the boundary-counter exchange over NCCL; NULL with
+ * world > 1 processes the shard without exchange (tiles then carry only this shard's reads). */
+int bdepth_set_shard(bdepth_t* h, int rank, int world, const void* nccl_unique_id);
+int bdepth_nccl_unique_id(void* out128);
+/* Tuning knobs (0 = default): uncompressed bytes per batch, positions in the counter window. */
+int bdepth_set_tuning(bdepth_t* h, uint64_t batch_inflated_bytes, uint64_t window_positions);
+
+/* ------------------------------------------------------------------ runs */
+/* Stage the (shard of the) compressed file into HBM ahead of time; later runs then start with
+ * inputs resident on the device (kernel-only timing).  Without it every run streams H2D itself. */
+int bdepth_stage(bdepth_t* h);
+/* depth base: deliver every tile of the processed range in order.  cb may be NULL (benchmark). */
+int bdepth_run_base(bdepth_t* h, bdepth_tile_cb cb, void* user);
+/* depth window -w W --overlap O -T t...: stats for every window slot the reference would print
+ * (all full windows of every reference, in order; depth.d:1051-1076).  O must satisfy
+ * (W - O) divides W for GPU evaluation. */
+int bdepth_run_windows(bdepth_t* h, uint32_t window, uint32_t overlap, const uint32_t* thresholds, size_t n_thresholds, bdepth_stat_cb cb, void* user);
+/* depth region: stats for the given regions, delivered in the given order. */
+int bdepth_run_regions(bdepth_t* h, const bdepth_region* regions, size_t n, const uint32_t* thresholds, size_t n_thresholds, bdepth_stat_cb cb, void* user);
+
+int bdepth_get_stats(const bdepth_t* h, bdepth_stats* out);
+
+/* ------------------------------------------------------------------ kernel-level entry points
+ * (used by the parity tests and the roofline bench; same kernels as the runs above) */
+/* Inflate the whole (shard of the) file on the GPU and copy the concatenated payload to dst. */
+int64_t bdepth_inflate_to_host(bdepth_t* h, void* dst, uint64_t cap);
+/* Scan records on the GPU; copy out up to cap rows of the columnar SoA (any pointer may be NULL). */
+int64_t bdepth_scan_to_host(bdepth_t* h, uint64_t cap, int32_t* ref_id, int32_t* pos, uint32_t* span, uint16_t* flag, uint8_t* mapq, uint16_t* n_cigar, uint64_t* rec_off);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BDEPTH_H */

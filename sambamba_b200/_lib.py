@@ -1,0 +1,238 @@
+"""ctypes binding of libbdepth.so.  Fails loudly if the CUDA library is missing: there is no
+CPU fallback anywhere in the product path."""
+import ctypes as C
+import os
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def lib_path():
+    return os.path.join(_HERE, "_build", "libbdepth.so")
+
+
+class BDepthError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"bdepth error {code}: {msg}")
+        self.code = code
+        self.msg = msg
+
+
+class Region(C.Structure):
+    _fields_ = [("ref_id", C.c_uint32), ("start", C.c_uint32), ("end", C.c_uint32)]
+
+
+class Tile(C.Structure):
+    _fields_ = [("ref_id", C.c_int32), ("start", C.c_uint32), ("len", C.c_uint32), ("stride", C.c_uint32),
+                ("counts", C.POINTER(C.c_uint32))]
+
+
+class RegionStat(C.Structure):
+    _fields_ = [("ref_id", C.c_int32), ("start", C.c_uint32), ("end", C.c_uint32), ("n_reads", C.c_uint32),
+                ("n_bases", C.c_uint32), ("cov_ge", C.POINTER(C.c_uint32))]
+
+
+class Stats(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("file_bytes", "n_blocks", "cdata_bytes", "inflated_bytes", "n_records",
+                                          "n_records_pass", "n_cigar_ops", "seq_bytes", "positions",
+                                          "covered_positions", "long_reads", "chain_fixups")] + \
+               [("gpu_launches", C.c_uint32), ("n_batches", C.c_uint32)] + \
+               [(n, C.c_float) for n in ("ms_h2d", "ms_inflate", "ms_scan", "ms_coverage", "ms_reduce", "ms_d2h",
+                                         "ms_total_device")] + [("host_wall_ms", C.c_double)]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+TILE_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(Tile))
+STAT_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(RegionStat), C.c_uint64)
+
+_lib = None
+
+
+def load_library():
+    global _lib
+    if _lib is not None:
+        return _lib
+    p = lib_path()
+    if not os.path.exists(p):
+        raise ImportError(f"{p} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(there is no CPU fallback)")
+    L = C.CDLL(p)
+    vp = C.c_void_p
+    L.bdepth_device_count.restype = C.c_int
+    L.bdepth_open.argtypes = [C.c_char_p, C.c_int, C.POINTER(vp)]
+    L.bdepth_open_memory.argtypes = [vp, C.c_size_t, vp, C.c_size_t, C.c_int, C.POINTER(vp)]
+    L.bdepth_close.argtypes = [vp]
+    L.bdepth_close.restype = None
+    L.bdepth_last_error.argtypes = [vp]
+    L.bdepth_last_error.restype = C.c_char_p
+    L.bdepth_n_ref.argtypes = [vp]
+    L.bdepth_ref_name.argtypes = [vp, C.c_int]
+    L.bdepth_ref_name.restype = C.c_char_p
+    L.bdepth_ref_length.argtypes = [vp, C.c_int]
+    L.bdepth_ref_length.restype = C.c_uint32
+    L.bdepth_header_text.argtypes = [vp, C.POINTER(C.c_size_t)]
+    L.bdepth_header_text.restype = C.c_char_p
+    L.bdepth_is_coordinate_sorted.argtypes = [vp]
+    L.bdepth_has_index.argtypes = [vp]
+    L.bdepth_n_samples.argtypes = [vp]
+    L.bdepth_sample_name.argtypes = [vp, C.c_int]
+    L.bdepth_sample_name.restype = C.c_char_p
+    L.bdepth_set_filter.argtypes = [vp, C.c_int, C.c_uint32]
+    L.bdepth_set_min_baseq.argtypes = [vp, C.c_uint32]
+    L.bdepth_set_regions.argtypes = [vp, C.POINTER(Region), C.c_size_t]
+    L.bdepth_set_shard.argtypes = [vp, C.c_int, C.c_int, vp]
+    L.bdepth_nccl_unique_id.argtypes = [vp]
+    L.bdepth_set_tuning.argtypes = [vp, C.c_uint64, C.c_uint64]
+    L.bdepth_stage.argtypes = [vp]
+    L.bdepth_run_base.argtypes = [vp, TILE_CB, vp]
+    L.bdepth_run_windows.argtypes = [vp, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32), C.c_size_t, STAT_CB, vp]
+    L.bdepth_run_regions.argtypes = [vp, C.POINTER(Region), C.c_size_t, C.POINTER(C.c_uint32), C.c_size_t, STAT_CB, vp]
+    L.bdepth_get_stats.argtypes = [vp, C.POINTER(Stats)]
+    L.bdepth_inflate_to_host.argtypes = [vp, vp, C.c_uint64]
+    L.bdepth_inflate_to_host.restype = C.c_int64
+    L.bdepth_scan_to_host.argtypes = [vp, C.c_uint64] + [vp] * 7
+    L.bdepth_scan_to_host.restype = C.c_int64
+    _lib = L
+    return L
+
+
+EXPORTED_SYMBOLS = [
+    "bdepth_device_count", "bdepth_open", "bdepth_open_memory", "bdepth_close", "bdepth_last_error", "bdepth_n_ref",
+    "bdepth_ref_name", "bdepth_ref_length", "bdepth_header_text", "bdepth_is_coordinate_sorted", "bdepth_has_index",
+    "bdepth_n_samples", "bdepth_sample_name", "bdepth_set_filter", "bdepth_set_min_baseq", "bdepth_set_regions",
+    "bdepth_set_shard", "bdepth_nccl_unique_id", "bdepth_set_tuning", "bdepth_stage", "bdepth_run_base",
+    "bdepth_run_windows", "bdepth_run_regions", "bdepth_get_stats", "bdepth_inflate_to_host", "bdepth_scan_to_host",
+]
+
+
+class BDepth:
+    """Thin object wrapper over the C ABI (mirrors what the CLI host does)."""
+
+    def __init__(self, path=None, device=0, memory=None, bai=None):
+        self.L = load_library()
+        self.h = C.c_void_p()
+        if memory is not None:
+            self._keep = (memory, bai)
+            mp = memory.ctypes.data_as(C.c_void_p)
+            bp = bai.ctypes.data_as(C.c_void_p) if bai is not None else None
+            rc = self.L.bdepth_open_memory(mp, memory.size, bp, 0 if bai is None else bai.size, device, C.byref(self.h))
+        else:
+            rc = self.L.bdepth_open(os.fsencode(path), device, C.byref(self.h))
+        if rc:
+            raise BDepthError(rc, self.L.bdepth_last_error(None).decode())
+
+    def _ck(self, rc):
+        if rc < 0:
+            raise BDepthError(rc, self.L.bdepth_last_error(self.h).decode())
+        return rc
+
+    def close(self):
+        if self.h:
+            self.L.bdepth_close(self.h)
+            self.h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # header
+    @property
+    def refs(self):
+        return [(self.L.bdepth_ref_name(self.h, i).decode(), self.L.bdepth_ref_length(self.h, i))
+                for i in range(self.L.bdepth_n_ref(self.h))]
+
+    @property
+    def samples(self):
+        return [self.L.bdepth_sample_name(self.h, i).decode() for i in range(self.L.bdepth_n_samples(self.h))]
+
+    @property
+    def coordinate_sorted(self):
+        return bool(self.L.bdepth_is_coordinate_sorted(self.h))
+
+    @property
+    def has_index(self):
+        return bool(self.L.bdepth_has_index(self.h))
+
+    # config
+    def set_filter(self, mapq_gt=0, flag_reject=0x600):
+        self._ck(self.L.bdepth_set_filter(self.h, mapq_gt, flag_reject))
+
+    def set_min_baseq(self, q):
+        self._ck(self.L.bdepth_set_min_baseq(self.h, q))
+
+    def set_regions(self, regions):
+        arr = (Region * max(1, len(regions)))(*[Region(*r) for r in regions])
+        self._ck(self.L.bdepth_set_regions(self.h, arr, len(regions)))
+
+    def set_shard(self, rank, world, uid=None):
+        self._ck(self.L.bdepth_set_shard(self.h, rank, world, uid))
+
+    def set_tuning(self, batch_bytes=0, window_positions=0):
+        self._ck(self.L.bdepth_set_tuning(self.h, batch_bytes, window_positions))
+
+    def stage(self):
+        self._ck(self.L.bdepth_stage(self.h))
+
+    def stats(self):
+        s = Stats()
+        self.L.bdepth_get_stats(self.h, C.byref(s))
+        return s.as_dict()
+
+    # runs
+    def run_base(self, collect=True):
+        """Returns counts[7, total_len] over the concatenated references when collect=True."""
+        refs = self.refs
+        lin0 = np.concatenate([[0], np.cumsum([l for _, l in refs])]).astype(np.int64)
+        out = np.zeros((7, int(lin0[-1])), np.uint32) if collect else None
+
+        def cb(_user, tp):
+            t = tp.contents
+            a = int(lin0[t.ref_id]) + t.start
+            src = np.ctypeslib.as_array(t.counts, shape=(6 * t.stride + t.len,))
+            for p in range(7):
+                out[p, a:a + t.len] = src[p * t.stride:p * t.stride + t.len]
+            return 0
+
+        cbf = TILE_CB(cb) if collect else C.cast(None, TILE_CB)
+        self._ck(self.L.bdepth_run_base(self.h, cbf, None))
+        return out
+
+    def _run_stats(self, fn):
+        rows = []
+        nthr = self._nthr
+
+        def cb(_user, sp, idx):
+            s = sp.contents
+            rows.append((s.ref_id, s.start, s.end, s.n_reads, s.n_bases, [s.cov_ge[i] for i in range(nthr)]))
+            return 0
+        self._ck(fn(STAT_CB(cb)))
+        return rows
+
+    def run_windows(self, window, overlap=0, thresholds=()):
+        thr = (C.c_uint32 * max(1, len(thresholds)))(*thresholds)
+        self._nthr = len(thresholds)
+        return self._run_stats(lambda cb: self.L.bdepth_run_windows(self.h, window, overlap, thr, len(thresholds), cb, None))
+
+    def run_regions(self, regions, thresholds=()):
+        thr = (C.c_uint32 * max(1, len(thresholds)))(*thresholds)
+        arr = (Region * max(1, len(regions)))(*[Region(*r) for r in regions])
+        self._nthr = len(thresholds)
+        return self._run_stats(lambda cb: self.L.bdepth_run_regions(self.h, arr, len(regions), thr, len(thresholds), cb, None))
+
+    def inflate(self):
+        n = self._ck(self.L.bdepth_inflate_to_host(self.h, None, 0))
+        buf = np.zeros(max(1, n), np.uint8)
+        n2 = self._ck(self.L.bdepth_inflate_to_host(self.h, buf.ctypes.data_as(C.c_void_p), n))
+        assert n2 == n
+        return buf[:n]
+
+    def scan(self, cap):
+        cols = dict(ref_id=np.zeros(cap, np.int32), pos=np.zeros(cap, np.int32), span=np.zeros(cap, np.uint32),
+                    flag=np.zeros(cap, np.uint16), mapq=np.zeros(cap, np.uint8), n_cigar=np.zeros(cap, np.uint16),
+                    rec_off=np.zeros(cap, np.uint64))
+        n = self._ck(self.L.bdepth_scan_to_host(self.h, cap, *[c.ctypes.data_as(C.c_void_p) for c in cols.values()]))
+        return n, {k: v[:min(n, cap)] for k, v in cols.items()}

@@ -1,0 +1,611 @@
+// bdepth.cu -- host pipeline and C ABI of libbdepth.so (see include/bdepth.h for the contract and
+// the reference seams each entry point replaces).
+//
+// Pipeline per batch of BGZF blocks (all on one CUDA stream; a second stream feeds H2D):
+//   H2D (pinned or pageable)  ->  K1 inflate  ->  K2 guess/walk (+ host chain verification)
+//   ->  K2 decode (SoA)  ->  K3 tile index / long-read scatter / per-position gather
+// then reducers + D2H for the chosen front end (base tiles, window stats, region stats).
+// There is no CPU fallback anywhere: if CUDA is unavailable every run returns BDEPTH_ERR_CUDA.
+#include <cuda_runtime.h>
+#include <fcntl.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+#include <algorithm>
+#include <chrono>
+#include <string>
+#include <vector>
+
+#include "../../include/bdepth.h"
+#include "host_bam.hpp"
+#include "kernels.cuh"
+
+using namespace bdk;
+
+namespace {
+
+thread_local std::string g_open_error;
+
+struct DevBuf {
+    void* p = nullptr; size_t cap = 0;
+    cudaError_t ensure(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) { cudaFree(p); p = nullptr; cap = 0; }
+        size_t want = n + n / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T* as() const { return (T*)p; }
+};
+
+constexpr size_t CARRY_MAX = 64ull << 20;
+constexpr size_t EMIT_CHUNK = 4ull << 20;     // positions per D2H chunk
+constexpr uint32_t SHARD_EXTRA_BLOCKS = 8;
+
+enum RunMode { RUN_FULL = 0, RUN_INFLATE_ONLY = 1, RUN_SCAN_ONLY = 2 };
+
+}  // namespace
+
+struct bdepth {
+    // ---- input
+    const uint8_t* file = nullptr; size_t file_len = 0; bool mapped = false; int fd = -1;
+    std::vector<HostBlock> blocks; uint64_t total_u = 0;
+    BamHeader hdr; BaiIndex bai; bool has_index = false;
+    int device = 0;
+    // ---- config
+    int mapq_gt = 0; uint32_t flag_reject = 0x600; uint32_t minq = 0;
+    std::vector<bdepth_region> regions;   // merged, sorted
+    int rank = 0, world = 1;
+    uint64_t batch_u = 6ull << 30;
+    uint64_t window_positions = 0;
+    // ---- shard (resolved lazily)
+    bool shard_ready = false;
+    size_t blk_lo = 0, blk_hi = 0; int64_t entry0 = 0; uint64_t limit_abs_u = 0;
+    // ---- device state
+    cudaStream_t s_main = nullptr, s_copy = nullptr;
+    cudaEvent_t ev[16] = {};
+    bool staged = false; uint64_t staged_file_off = 0;
+    DevBuf comp, descs, status, ubuf, chunk_start, entry, exitb, count, slot_base, slots, rec_base, walk_list;
+    DevBuf soa_start, soa_span, soa_meta, soa_off, soa_ncl, soa_lseq, long_list, tile_first, tile_lo, counts, ref_len_d, ref_lin0_d, scan_stats, ref_has, misc;
+    uint64_t cnt_base = 0, win_len = 0;
+    void* pinned = nullptr; size_t pinned_cap = 0;
+    std::vector<uint32_t> ref_has_host;
+    // ---- results
+    bdepth_stats st{}; std::string err;
+};
+
+namespace {
+
+int fail(bdepth* h, int code, const char* fmt, ...) {
+    char buf[1024]; va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+    if (h) h->err = buf; else g_open_error = buf;
+    return code;
+}
+#define CK(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return fail(h, BDEPTH_ERR_CUDA, "CUDA error %s at %s:%d: %s", cudaGetErrorName(e__), __FILE__, __LINE__, cudaGetErrorString(e__)); } while (0)
+
+int ensure_pinned(bdepth* h, size_t n) {
+    if (n <= h->pinned_cap) return 0;
+    if (h->pinned) cudaFreeHost(h->pinned);
+    h->pinned = nullptr; h->pinned_cap = 0;
+    CK(cudaMallocHost(&h->pinned, n));
+    h->pinned_cap = n;
+    return 0;
+}
+
+int init_device(bdepth* h) {
+    int n = 0; cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) return fail(h, BDEPTH_ERR_CUDA, "no CUDA device available (%s); libbdepth has no CPU fallback", cudaGetErrorString(e));
+    if (h->device < 0 || h->device >= n) return fail(h, BDEPTH_ERR_ARG, "device %d out of range (%d devices)", h->device, n);
+    CK(cudaSetDevice(h->device));
+    if (!h->s_main) { CK(cudaStreamCreateWithFlags(&h->s_main, cudaStreamNonBlocking)); CK(cudaStreamCreateWithFlags(&h->s_copy, cudaStreamNonBlocking)); for (auto& e2 : h->ev) CK(cudaEventCreate(&e2)); }
+    CK(cudaFuncSetAttribute(k1_inflate, cudaFuncAttributeMaxDynamicSharedMemorySize, T_WORDS * 32 * 4));
+    return 0;
+}
+
+// Inflate blocks [b0, b1) into a host vector (used for the header only: a few blocks).
+int inflate_blocks_to_host(bdepth* h, size_t b0, size_t b1, std::vector<uint8_t>& out) {
+    size_t nb = b1 - b0; if (!nb) { out.clear(); return 0; }
+    uint64_t f0 = h->blocks[b0].coff & ~3ull, f1 = h->blocks[b1 - 1].coff + h->blocks[b1 - 1].bsize;
+    uint64_t ulen = h->blocks[b1 - 1].uoff + h->blocks[b1 - 1].isize - h->blocks[b0].uoff;
+    CK(h->comp.ensure(f1 - f0 + 256)); CK(h->descs.ensure(nb * sizeof(BlockDesc))); CK(h->status.ensure(nb * sizeof(int))); CK(h->ubuf.ensure(CARRY_MAX + ulen + 256));
+    std::vector<BlockDesc> d(nb);
+    for (size_t i = 0; i < nb; i++) { const HostBlock& b = h->blocks[b0 + i]; d[i] = BlockDesc{b.coff + b.cdata_off - f0, b.uoff - h->blocks[b0].uoff, b.csize, b.isize}; }
+    CK(cudaMemcpyAsync(h->comp.p, h->file + f0, f1 - f0, cudaMemcpyHostToDevice, h->s_main));
+    CK(cudaMemsetAsync((uint8_t*)h->comp.p + (f1 - f0), 0, 128, h->s_main));
+    CK(cudaMemcpyAsync(h->descs.p, d.data(), nb * sizeof(BlockDesc), cudaMemcpyHostToDevice, h->s_main));
+    k1_inflate<<<(unsigned)((nb + 31) / 32), 32, T_WORDS * 32 * 4, h->s_main>>>(h->comp.as<uint32_t>(), h->descs.as<BlockDesc>(), (uint32_t)nb, h->ubuf.as<uint8_t>() + CARRY_MAX, h->status.as<int>());
+    CK(cudaGetLastError());
+    std::vector<int> stt(nb); out.resize(ulen);
+    CK(cudaMemcpyAsync(stt.data(), h->status.p, nb * sizeof(int), cudaMemcpyDeviceToHost, h->s_main));
+    CK(cudaMemcpyAsync(out.data(), h->ubuf.as<uint8_t>() + CARRY_MAX, ulen, cudaMemcpyDeviceToHost, h->s_main));
+    CK(cudaStreamSynchronize(h->s_main));
+    h->st.gpu_launches += 1;
+    for (size_t i = 0; i < nb; i++) if (stt[i]) return fail(h, BDEPTH_ERR_FORMAT, "DEFLATE error %d in BGZF block at offset %llu", stt[i], (unsigned long long)h->blocks[b0 + i].coff);
+    return 0;
+}
+
+int finish_open(bdepth* h) {
+    std::string e = index_bgzf(h->file, h->file_len, h->blocks, &h->total_u);
+    if (!e.empty()) return fail(h, BDEPTH_ERR_FORMAT, "%s", e.c_str());
+    if (h->blocks.empty()) return fail(h, BDEPTH_ERR_FORMAT, "Invalid file format: expected BAM\\1");
+    int rc = init_device(h); if (rc) return rc;
+    // header: inflate a growing prefix of blocks on the GPU until it parses
+    size_t nb = std::min<size_t>(4, h->blocks.size());
+    for (;;) {
+        std::vector<uint8_t> u; rc = inflate_blocks_to_host(h, 0, nb, u); if (rc) return rc;
+        std::string perr; int pr = parse_bam_header(u.data(), u.size(), h->hdr, perr);
+        if (pr == 0) break;
+        if (pr < 0) return fail(h, BDEPTH_ERR_FORMAT, "%s", perr.c_str());
+        if (nb == h->blocks.size()) return fail(h, BDEPTH_ERR_FORMAT, "truncated BAM header");
+        nb = std::min(h->blocks.size(), nb * 4);
+    }
+    size_t nref = h->hdr.ref_len.size();
+    CK(h->ref_len_d.ensure((nref + 1) * 4)); CK(h->ref_lin0_d.ensure((nref + 1) * 8));
+    if (nref) { CK(cudaMemcpy(h->ref_len_d.p, h->hdr.ref_len.data(), nref * 4, cudaMemcpyHostToDevice)); CK(cudaMemcpy(h->ref_lin0_d.p, h->hdr.ref_lin0.data(), nref * 8, cudaMemcpyHostToDevice)); }
+    return 0;
+}
+
+// Resolve the block range / entry / limit of this rank's shard.
+int prepare_shard(bdepth* h) {
+    if (h->shard_ready) return 0;
+    const auto& B = h->blocks;
+    auto block_of_u = [&](uint64_t u) { size_t lo = 0, hi = B.size(); while (lo + 1 < hi) { size_t m = (lo + hi) / 2; if (B[m].uoff <= u) lo = m; else hi = m; } return lo; };
+    auto block_of_c = [&](uint64_t c) { size_t lo = 0, hi = B.size(); while (lo + 1 < hi) { size_t m = (lo + hi) / 2; if (B[m].coff <= c) lo = m; else hi = m; } return lo; };
+    uint64_t start_u = h->hdr.first_rec_off, end_u = h->total_u;
+    if (h->world > 1) {
+        if (!h->bai.valid) return fail(h, BDEPTH_ERR_NOINDEX, "sharding needs the BAI linear index");
+        std::vector<uint64_t> vos;
+        for (auto& v : h->bai.ioffsets) for (uint64_t x : v) if (x) vos.push_back(x);
+        std::sort(vos.begin(), vos.end()); vos.erase(std::unique(vos.begin(), vos.end()), vos.end());
+        auto cut = [&](int k) -> uint64_t {   // absolute inflated offset of the k-th shard boundary
+            if (k <= 0) return h->hdr.first_rec_off;
+            if (k >= h->world) return h->total_u;
+            uint64_t target = (uint64_t)((__uint128_t)h->file_len * (unsigned)k / (unsigned)h->world);
+            auto it = std::lower_bound(vos.begin(), vos.end(), target << 16);
+            if (it == vos.end()) return h->total_u;
+            uint64_t vo = *it; size_t b = block_of_c(vo >> 16);
+            if (B[b].coff != (vo >> 16)) return h->total_u;      // index does not match the file
+            uint64_t u = B[b].uoff + (vo & 0xFFFF);
+            return u < h->hdr.first_rec_off ? h->hdr.first_rec_off : u;
+        };
+        start_u = cut(h->rank); end_u = cut(h->rank + 1);
+        if (end_u < start_u) end_u = start_u;
+    }
+    if (start_u >= h->total_u) { h->blk_lo = h->blk_hi = B.size(); h->entry0 = 0; h->limit_abs_u = h->total_u; h->shard_ready = true; return 0; }
+    h->blk_lo = block_of_u(start_u); h->entry0 = (int64_t)(start_u - B[h->blk_lo].uoff);
+    h->limit_abs_u = end_u;
+    if (end_u >= h->total_u) h->blk_hi = B.size();
+    else h->blk_hi = std::min(B.size(), block_of_u(end_u) + 1 + SHARD_EXTRA_BLOCKS);
+    h->shard_ready = true;
+    return 0;
+}
+
+struct RunOut {                    // optional sinks for the kernel-level entry points
+    uint8_t* inflate_dst = nullptr; uint64_t inflate_cap = 0; uint64_t inflate_len = 0;
+    uint64_t scan_cap = 0; uint64_t scan_n = 0;
+    int32_t* ref_id = nullptr; int32_t* pos = nullptr; uint32_t* span = nullptr; uint16_t* flag = nullptr; uint8_t* mapq = nullptr; uint16_t* n_cigar = nullptr; uint64_t* rec_off = nullptr;
+};
+
+__global__ void k_fill_u32(uint32_t* p, uint32_t v, uint64_t n) { uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; if (i < n) p[i] = v; }
+
+// The pipeline: leaves the per-position counters of the whole shard in h->counts (RUN_FULL).
+int run_pipeline(bdepth* h, RunMode mode, RunOut* ro) {
+    int rc = init_device(h); if (rc) return rc;
+    rc = prepare_shard(h); if (rc) return rc;
+    auto t_host0 = std::chrono::steady_clock::now();
+    bdepth_stats& st = h->st; uint32_t launches0 = 0;
+    st = bdepth_stats{}; st.gpu_launches = launches0;
+    const auto& B = h->blocks;
+    const size_t nref = h->hdr.ref_len.size();
+    cudaStream_t sm = h->s_main;
+
+    // ---- counter window: the whole linear genome (SURVEY 7 "Memory": 28 B/position; 87 GB for GRCh38 fits 180 GB HBM)
+    if (mode == RUN_FULL) {
+        h->cnt_base = 0;
+        h->win_len = ((h->hdr.total_len + TILE_POS - 1) / TILE_POS + 1) * TILE_POS;
+        size_t need = (size_t)h->win_len * N_PLANES * 4;
+        size_t free_b = 0, tot_b = 0; CK(cudaMemGetInfo(&free_b, &tot_b));
+        if (need > h->counts.cap && need > free_b + h->counts.cap) return fail(h, BDEPTH_ERR_CUDA, "counter window needs %zu bytes of HBM, %zu free", need, free_b);
+        CK(h->counts.ensure(need));
+        CK(cudaMemsetAsync(h->counts.p, 0, need, sm));
+        CK(h->ref_has.ensure((nref / 32 + 2) * 4)); CK(cudaMemsetAsync(h->ref_has.p, 0, (nref / 32 + 2) * 4, sm));
+    }
+    CK(h->scan_stats.ensure(sizeof(ScanStats)));
+    { uint64_t shard_u = h->blk_hi > h->blk_lo ? B[h->blk_hi - 1].uoff + B[h->blk_hi - 1].isize - B[h->blk_lo].uoff : 0; CK(h->ubuf.ensure(CARRY_MAX + std::min<uint64_t>(h->batch_u + 65536, shard_u) + 256)); }
+    CK(h->misc.ensure(64));
+
+    float ms_h2d = 0, ms_k1 = 0, ms_k2 = 0, ms_k3 = 0;
+    uint64_t carry_len = 0; bool first_batch = true;
+    size_t b = h->blk_lo;
+    if (ro) { ro->inflate_len = 0; ro->scan_n = 0; }
+    while (b < h->blk_hi) {
+        // ---- batch extent
+        size_t b1 = b; uint64_t ub = 0;
+        while (b1 < h->blk_hi && (b1 == b || ub + B[b1].isize <= h->batch_u)) { ub += B[b1].isize; b1++; }
+        const size_t nb = b1 - b; const bool last_batch = b1 == h->blk_hi;
+        const uint64_t batch_u0 = B[b].uoff;               // absolute inflated offset of the batch start
+        st.n_batches++; st.n_blocks += nb; st.inflated_bytes += ub;
+        // ---- compressed bytes on the device
+        uint64_t f0 = B[b].coff & ~3ull, f1 = B[b1 - 1].coff + B[b1 - 1].bsize;
+        const uint32_t* d_comp; uint64_t comp_base_off;
+        cudaEvent_t e0 = h->ev[0], e1 = h->ev[1], e2 = h->ev[2], e3 = h->ev[3], e4 = h->ev[4];
+        CK(cudaEventRecord(e0, sm));
+        if (h->staged) { d_comp = h->comp.as<uint32_t>(); comp_base_off = h->staged_file_off; }
+        else {
+            CK(h->comp.ensure(f1 - f0 + 256));
+            CK(cudaMemcpyAsync(h->comp.p, h->file + f0, f1 - f0, cudaMemcpyHostToDevice, sm));
+            CK(cudaMemsetAsync((uint8_t*)h->comp.p + (f1 - f0), 0, 128, sm));
+            d_comp = h->comp.as<uint32_t>(); comp_base_off = f0;
+        }
+        st.file_bytes += f1 - B[b].coff;
+        // ---- descriptors
+        std::vector<BlockDesc> d(nb); uint64_t csum = 0;
+        for (size_t i = 0; i < nb; i++) { const HostBlock& hb = B[b + i]; d[i] = BlockDesc{hb.coff + hb.cdata_off - comp_base_off, hb.uoff - batch_u0, hb.csize, hb.isize}; csum += hb.csize; }
+        st.cdata_bytes += csum;
+        CK(h->descs.ensure(nb * sizeof(BlockDesc))); CK(h->status.ensure(nb * sizeof(int))); CK(h->ubuf.ensure(CARRY_MAX + ub + 256));
+        CK(cudaMemcpyAsync(h->descs.p, d.data(), nb * sizeof(BlockDesc), cudaMemcpyHostToDevice, sm));
+        uint8_t* u0 = h->ubuf.as<uint8_t>() + CARRY_MAX;     // offset 0 of this batch's inflated bytes
+        CK(cudaEventRecord(e1, sm));
+        // ---- K1
+        k1_inflate<<<(unsigned)((nb + 31) / 32), 32, T_WORDS * 32 * 4, sm>>>(d_comp, h->descs.as<BlockDesc>(), (uint32_t)nb, u0, h->status.as<int>());
+        CK(cudaGetLastError()); st.gpu_launches++;
+        CK(cudaEventRecord(e2, sm));
+        std::vector<int> stt(nb);
+        CK(cudaMemcpyAsync(stt.data(), h->status.p, nb * sizeof(int), cudaMemcpyDeviceToHost, sm));
+        if (mode == RUN_INFLATE_ONLY) {
+            CK(cudaStreamSynchronize(sm));
+            for (size_t i = 0; i < nb; i++) if (stt[i]) return fail(h, BDEPTH_ERR_FORMAT, "DEFLATE error %d in BGZF block at offset %llu", stt[i], (unsigned long long)B[b + i].coff);
+            if (ro && ro->inflate_dst) {
+                if (ro->inflate_len + ub > ro->inflate_cap) return fail(h, BDEPTH_ERR_ARG, "inflate buffer too small");
+                CK(cudaMemcpy(ro->inflate_dst + ro->inflate_len, u0, ub, cudaMemcpyDeviceToHost));
+            }
+            if (ro) ro->inflate_len += ub;
+            float t; CK(cudaEventElapsedTime(&t, e0, e1)); ms_h2d += t; CK(cudaEventElapsedTime(&t, e1, e2)); ms_k1 += t;
+            b = b1; continue;
+        }
+        // ---- K2: chunk table
+        std::vector<int64_t> cstart(nb + 1); std::vector<uint32_t> sbase(nb + 1);
+        { uint64_t acc = 0; for (size_t i = 0; i < nb; i++) { cstart[i] = (int64_t)d[i].uoff; sbase[i] = (uint32_t)acc; uint64_t sz = d[i].isize + (i == 0 ? carry_len : 0); acc += sz / 36 + 2; } cstart[nb] = (int64_t)ub; sbase[nb] = (uint32_t)acc; cstart[0] = -(int64_t)carry_len;
+          if (acc > 0xFFFFFFFFull) return fail(h, BDEPTH_ERR_ARG, "batch too large"); }
+        const uint64_t n_slots = sbase[nb];
+        CK(h->chunk_start.ensure((nb + 1) * 8)); CK(h->slot_base.ensure((nb + 1) * 4)); CK(h->entry.ensure(nb * 8)); CK(h->exitb.ensure(nb * 8)); CK(h->count.ensure(nb * 4)); CK(h->rec_base.ensure((nb + 1) * 4)); CK(h->slots.ensure(n_slots * 2 + 64)); CK(h->walk_list.ensure(64));
+        CK(cudaMemcpyAsync(h->chunk_start.p, cstart.data(), (nb + 1) * 8, cudaMemcpyHostToDevice, sm));
+        CK(cudaMemcpyAsync(h->slot_base.p, sbase.data(), (nb + 1) * 4, cudaMemcpyHostToDevice, sm));
+        CK(cudaMemsetAsync(h->entry.p, 0xFF, nb * 8, sm));
+        int64_t anchor = first_batch ? h->entry0 : -(int64_t)carry_len;
+        CK(cudaMemcpyAsync(h->entry.p, &anchor, 8, cudaMemcpyHostToDevice, sm));
+        CK(cudaMemsetAsync(h->misc.p, 0, 64, sm));
+        // records that START at or after the shard limit belong to the next rank
+        int64_t u_limit = (int64_t)ub; if (h->limit_abs_u < batch_u0 + ub) u_limit = h->limit_abs_u > batch_u0 ? (int64_t)(h->limit_abs_u - batch_u0) : 0;
+        ScanParams sp{u0, -(int64_t)carry_len, (int64_t)ub, (int)nref, h->ref_len_d.as<uint32_t>(), h->ref_lin0_d.as<uint64_t>()};
+        k2_guess_entries<<<(unsigned)((nb * 32 + 255) / 256), 256, 0, sm>>>(sp, h->chunk_start.as<int64_t>(), (uint32_t)nb, h->entry.as<int64_t>());
+        CK(cudaGetLastError()); st.gpu_launches++;
+        ScanParams spw = sp;
+        k2_walk<<<(unsigned)((nb + 127) / 128), 128, 0, sm>>>(spw, h->chunk_start.as<int64_t>(), (uint32_t)nb, h->entry.as<int64_t>(), h->slot_base.as<uint32_t>(), h->slots.as<uint16_t>(), h->count.as<uint32_t>(), h->exitb.as<int64_t>(), (int*)h->misc.p, nullptr, 0);
+        CK(cudaGetLastError()); st.gpu_launches++;
+        std::vector<int64_t> ent(nb), ext(nb); std::vector<uint32_t> cnt(nb);
+        CK(cudaMemcpyAsync(ent.data(), h->entry.p, nb * 8, cudaMemcpyDeviceToHost, sm));
+        CK(cudaMemcpyAsync(ext.data(), h->exitb.p, nb * 8, cudaMemcpyDeviceToHost, sm));
+        CK(cudaMemcpyAsync(cnt.data(), h->count.p, nb * 4, cudaMemcpyDeviceToHost, sm));
+        int walk_err = 0; CK(cudaMemcpyAsync(&walk_err, h->misc.p, 4, cudaMemcpyDeviceToHost, sm));
+        CK(cudaStreamSynchronize(sm));
+        for (size_t i = 0; i < nb; i++) if (stt[i]) return fail(h, BDEPTH_ERR_FORMAT, "DEFLATE error %d in BGZF block at offset %llu", stt[i], (unsigned long long)B[b + i].coff);
+        // ---- exact chain verification (host, control plane): entry[i] must equal the running exit
+        int64_t cur = anchor; int64_t tail = (int64_t)ub;
+        for (size_t i = 0; i < nb; i++) {
+            int64_t true_e = (cur < cstart[i + 1]) ? cur : ENTRY_NONE;
+            if (true_e != ENTRY_NONE && true_e < cstart[i]) return fail(h, BDEPTH_ERR_FORMAT, "internal: record chain went backwards");
+            if (ent[i] != true_e) {
+                st.chain_fixups++;
+                uint32_t ci = (uint32_t)i;
+                CK(cudaMemcpyAsync((int64_t*)h->entry.p + i, &true_e, 8, cudaMemcpyHostToDevice, sm));
+                CK(cudaMemcpyAsync(h->walk_list.p, &ci, 4, cudaMemcpyHostToDevice, sm));
+                k2_walk<<<1, 32, 0, sm>>>(spw, h->chunk_start.as<int64_t>(), (uint32_t)nb, h->entry.as<int64_t>(), h->slot_base.as<uint32_t>(), h->slots.as<uint16_t>(), h->count.as<uint32_t>(), h->exitb.as<int64_t>(), (int*)h->misc.p, h->walk_list.as<uint32_t>(), 1);
+                CK(cudaGetLastError()); st.gpu_launches++;
+                CK(cudaMemcpyAsync(&ext[i], (int64_t*)h->exitb.p + i, 8, cudaMemcpyDeviceToHost, sm));
+                CK(cudaMemcpyAsync(&cnt[i], (uint32_t*)h->count.p + i, 4, cudaMemcpyDeviceToHost, sm));
+                CK(cudaMemcpyAsync(&walk_err, h->misc.p, 4, cudaMemcpyDeviceToHost, sm));
+                CK(cudaStreamSynchronize(sm));
+                ent[i] = true_e;
+            }
+            if (true_e != ENTRY_NONE) {
+                cur = ext[i];
+                if (ext[i] < cstart[i + 1]) {      // the walk stopped inside its own block: incomplete tail record
+                    for (size_t j = i + 1; j < nb; j++) cnt[j] = 0;
+                    break;
+                }
+            }
+        }
+        if (walk_err) return fail(h, BDEPTH_ERR_FORMAT, "corrupt BAM record chain (block_size < 32)");
+        tail = cur < (int64_t)ub ? cur : (int64_t)ub;     // first byte not consumed by a complete record
+        // ---- shard limit: drop records starting at/after u_limit (host trims counts; offsets are sorted)
+        std::vector<uint32_t> rbase(nb + 1); uint64_t R = 0;
+        bool limited = u_limit < (int64_t)ub;
+        std::vector<uint16_t> tmp_slots;
+        for (size_t i = 0; i < nb; i++) {
+            if (limited && cnt[i]) {
+                if (cstart[i] >= u_limit) cnt[i] = 0;
+                else if (cstart[i + 1] > u_limit) {   // partial: count slots below the limit
+                    tmp_slots.resize(cnt[i]);
+                    CK(cudaMemcpy(tmp_slots.data(), (uint16_t*)h->slots.p + sbase[i], cnt[i] * 2, cudaMemcpyDeviceToHost));
+                    uint32_t k = 0; while (k < cnt[i] && cstart[i] + tmp_slots[k] < u_limit) k++;
+                    cnt[i] = k;
+                }
+            }
+            rbase[i] = (uint32_t)R; R += cnt[i];
+        }
+        rbase[nb] = (uint32_t)R;
+        if (R > 0xFFFFFFF0ull) return fail(h, BDEPTH_ERR_ARG, "batch too large");
+        CK(cudaMemcpyAsync(h->count.p, cnt.data(), nb * 4, cudaMemcpyHostToDevice, sm));
+        if (limited && tail < u_limit && tail < (int64_t)ub && b1 < B.size()) return fail(h, BDEPTH_ERR_FORMAT, "record at the shard boundary spans more than %u BGZF blocks", SHARD_EXTRA_BLOCKS);
+        CK(cudaMemcpyAsync(h->rec_base.p, rbase.data(), (nb + 1) * 4, cudaMemcpyHostToDevice, sm));
+        st.n_records += R;
+        // ---- K2 decode
+        size_t Rc = R ? R : 1;
+        CK(h->soa_start.ensure(Rc * 8)); CK(h->soa_span.ensure(Rc * 4)); CK(h->soa_meta.ensure(Rc * 4)); CK(h->soa_off.ensure(Rc * 8)); CK(h->soa_ncl.ensure(Rc * 4)); CK(h->soa_lseq.ensure(Rc * 4)); CK(h->long_list.ensure(Rc * 4));
+        RecordSoA soa{h->soa_start.as<uint64_t>(), h->soa_span.as<uint32_t>(), h->soa_meta.as<uint32_t>(), h->soa_off.as<int64_t>(), h->soa_ncl.as<uint32_t>(), h->soa_lseq.as<int32_t>()};
+        ScanStats zs{0, 0, 0, 0, ~0ull, 0};
+        CK(cudaMemcpyAsync(h->scan_stats.p, &zs, sizeof zs, cudaMemcpyHostToDevice, sm));
+        if (mode == RUN_SCAN_ONLY && !h->ref_has.p) { CK(h->ref_has.ensure((nref / 32 + 2) * 4)); CK(cudaMemsetAsync(h->ref_has.p, 0, (nref / 32 + 2) * 4, sm)); }
+        k2_decode<<<(unsigned)((nb * 32 + 255) / 256), 256, 0, sm>>>(sp, h->chunk_start.as<int64_t>(), (uint32_t)nb, h->slot_base.as<uint32_t>(), h->slots.as<uint16_t>(), h->count.as<uint32_t>(), h->rec_base.as<uint32_t>(), soa, h->mapq_gt, h->flag_reject, h->scan_stats.as<ScanStats>(), h->long_list.as<uint32_t>(), h->ref_has.as<uint32_t>());
+        CK(cudaGetLastError()); st.gpu_launches++;
+        ScanStats ss; CK(cudaMemcpyAsync(&ss, h->scan_stats.p, sizeof ss, cudaMemcpyDeviceToHost, sm));
+        CK(cudaEventRecord(e3, sm));
+        CK(cudaStreamSynchronize(sm));
+        st.n_records_pass += ss.n_pass; st.n_cigar_ops += ss.n_cigar; st.seq_bytes += ss.seq_bytes; st.long_reads += ss.n_long;
+        if (mode == RUN_SCAN_ONLY) {
+            if (ro && R) {
+                uint64_t n = std::min<uint64_t>(R, ro->scan_cap > ro->scan_n ? ro->scan_cap - ro->scan_n : 0);
+                std::vector<uint64_t> hs(n), ho(n); std::vector<uint32_t> hsp(n), hm(n), hn(n);
+                CK(cudaMemcpy(hs.data(), soa.start, n * 8, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(ho.data(), soa.off, n * 8, cudaMemcpyDeviceToHost));
+                CK(cudaMemcpy(hsp.data(), soa.span, n * 4, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(hm.data(), soa.meta, n * 4, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(hn.data(), soa.ncl, n * 4, cudaMemcpyDeviceToHost));
+                for (uint64_t i = 0; i < n; i++) {
+                    uint64_t k = ro->scan_n + i; int32_t rid = -1, p = -1;
+                    if (hs[i] != 0xFFFFFFFFFFFFFFFEull) { size_t lo = 0, hi = nref; while (lo + 1 < hi) { size_t m = (lo + hi) / 2; if (h->hdr.ref_lin0[m] <= hs[i]) lo = m; else hi = m; } while (lo + 1 < nref && h->hdr.ref_lin0[lo + 1] <= hs[i] && h->hdr.ref_len[lo] == 0) lo++; rid = (int32_t)lo; p = (int32_t)(hs[i] - h->hdr.ref_lin0[lo]); }
+                    if (ro->ref_id) ro->ref_id[k] = rid; if (ro->pos) ro->pos[k] = p; if (ro->span) ro->span[k] = hsp[i];
+                    if (ro->flag) ro->flag[k] = (uint16_t)(hm[i] >> 16); if (ro->mapq) ro->mapq[k] = (uint8_t)(hm[i] >> 8); if (ro->n_cigar) ro->n_cigar[k] = (uint16_t)(hn[i] >> 8);
+                    if (ro->rec_off) ro->rec_off[k] = batch_u0 + ho[i] - 4;       // absolute offset of the block_size field
+                }
+            }
+            if (ro) ro->scan_n += R;
+        }
+        // ---- K3
+        if (mode == RUN_FULL && ss.n_pass) {
+            uint64_t gmin = ss.min_start, gmax = ss.max_end;
+            uint64_t t_lo = (gmin - h->cnt_base) / TILE_POS, t_hi = (gmax - h->cnt_base + TILE_POS - 1) / TILE_POS;
+            uint64_t n_tiles = t_hi - t_lo; uint64_t tiles_base = h->cnt_base + t_lo * TILE_POS;
+            if (t_hi * TILE_POS > h->win_len) return fail(h, BDEPTH_ERR_FORMAT, "read extends past the end of the reference space");
+            CK(h->tile_first.ensure((n_tiles + 2) * 4)); CK(h->tile_lo.ensure((n_tiles + 2) * 4));
+            k_fill_u32<<<(unsigned)((n_tiles + 2 + 255) / 256), 256, 0, sm>>>(h->tile_first.as<uint32_t>(), (uint32_t)R, n_tiles + 2);
+            CK(cudaMemsetAsync(h->tile_lo.p, 0xFF, (n_tiles + 2) * 4, sm));
+            k3_tile_index<<<(unsigned)((R + 255) / 256), 256, 0, sm>>>(soa, (uint32_t)R, tiles_base, (uint32_t)n_tiles, h->tile_first.as<uint32_t>(), h->tile_lo.as<uint32_t>());
+            CK(cudaGetLastError()); st.gpu_launches += 2;
+            if (ss.n_long) {
+                if (h->minq) k3_scatter_long<true><<<(unsigned)((ss.n_long * 32 + 255) / 256), 256, 0, sm>>>(soa, u0, h->long_list.as<uint32_t>(), (uint32_t)ss.n_long, h->cnt_base, h->win_len, h->counts.as<uint32_t>(), h->minq);
+                else k3_scatter_long<false><<<(unsigned)((ss.n_long * 32 + 255) / 256), 256, 0, sm>>>(soa, u0, h->long_list.as<uint32_t>(), (uint32_t)ss.n_long, h->cnt_base, h->win_len, h->counts.as<uint32_t>(), 0);
+                CK(cudaGetLastError()); st.gpu_launches++;
+            }
+            if (h->minq) k3_gather<true><<<(unsigned)n_tiles, 256, 0, sm>>>(soa, u0, tiles_base, h->cnt_base, h->win_len, h->tile_first.as<uint32_t>(), h->tile_lo.as<uint32_t>(), h->counts.as<uint32_t>(), h->minq);
+            else k3_gather<false><<<(unsigned)n_tiles, 256, 0, sm>>>(soa, u0, tiles_base, h->cnt_base, h->win_len, h->tile_first.as<uint32_t>(), h->tile_lo.as<uint32_t>(), h->counts.as<uint32_t>(), 0);
+            CK(cudaGetLastError()); st.gpu_launches++;
+        }
+        CK(cudaEventRecord(e4, sm));
+        // ---- carry the incomplete tail record to the front of the next batch
+        uint64_t new_carry = (uint64_t)((int64_t)ub - tail);
+        if (!last_batch && new_carry) {
+            if (new_carry > CARRY_MAX) return fail(h, BDEPTH_ERR_FORMAT, "BAM record larger than %zu bytes", CARRY_MAX);
+            CK(cudaMemcpyAsync(u0 - new_carry, u0 + tail, new_carry, cudaMemcpyDeviceToDevice, sm));
+        }
+        CK(cudaStreamSynchronize(sm));
+        { float t; CK(cudaEventElapsedTime(&t, e0, e1)); ms_h2d += t; CK(cudaEventElapsedTime(&t, e1, e2)); ms_k1 += t; CK(cudaEventElapsedTime(&t, e2, e3)); ms_k2 += t; CK(cudaEventElapsedTime(&t, e3, e4)); ms_k3 += t; }
+        carry_len = last_batch ? 0 : new_carry; first_batch = false; b = b1;
+    }
+    st.ms_h2d = ms_h2d; st.ms_inflate = ms_k1; st.ms_scan = ms_k2; st.ms_coverage = ms_k3;
+    st.positions = mode == RUN_FULL ? h->hdr.total_len : 0;
+    if (mode == RUN_FULL) {
+        h->ref_has_host.assign(nref / 32 + 2, 0);
+        CK(cudaMemcpy(h->ref_has_host.data(), h->ref_has.p, (nref / 32 + 2) * 4, cudaMemcpyDeviceToHost));
+    }
+    st.host_wall_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_host0).count();
+    return 0;
+}
+
+// merged, sorted regions clipped to reference lengths
+void normalize_regions(const bdepth* h, const bdepth_region* r, size_t n, std::vector<bdepth_region>& out) {
+    out.clear();
+    for (size_t i = 0; i < n; i++) {
+        if (r[i].ref_id >= h->hdr.ref_len.size() || r[i].start >= r[i].end) continue;
+        bdepth_region g = r[i]; if (g.end > h->hdr.ref_len[g.ref_id]) g.end = h->hdr.ref_len[g.ref_id]; if (g.start >= g.end) continue;
+        out.push_back(g);
+    }
+    std::sort(out.begin(), out.end(), [](const bdepth_region& a, const bdepth_region& b) { return a.ref_id != b.ref_id ? a.ref_id < b.ref_id : a.start != b.start ? a.start < b.start : a.end < b.end; });
+    size_t m = 0;
+    for (size_t i = 0; i < out.size(); i++) { if (m && out[m - 1].ref_id == out[i].ref_id && out[m - 1].end >= out[i].start) out[m - 1].end = std::max(out[m - 1].end, out[i].end); else out[m++] = out[i]; }
+    out.resize(m);
+}
+
+}  // namespace
+
+// =============================================================================== C ABI
+extern "C" {
+
+int bdepth_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) return 0; return n; }
+
+static int open_common(bdepth* h, bdepth_t** out) {
+    int rc = finish_open(h);
+    if (rc) { g_open_error = h->err; bdepth_close(h); return rc; }
+    *out = h; return 0;
+}
+
+int bdepth_open(const char* bam_path, int device, bdepth_t** out) {
+    if (!bam_path || !out) return fail(nullptr, BDEPTH_ERR_ARG, "null argument");
+    bdepth* h = new bdepth(); h->device = device;
+    h->fd = open(bam_path, O_RDONLY);
+    if (h->fd < 0) { delete h; return fail(nullptr, BDEPTH_ERR_IO, "Cannot open file `%s' in mode `rb' (No such file or directory)", bam_path); }
+    struct stat sb; if (fstat(h->fd, &sb) != 0 || sb.st_size == 0) { close(h->fd); delete h; return fail(nullptr, BDEPTH_ERR_IO, "cannot stat `%s' or file is empty", bam_path); }
+    h->file_len = (size_t)sb.st_size;
+    void* m = mmap(nullptr, h->file_len, PROT_READ, MAP_PRIVATE, h->fd, 0);
+    if (m == MAP_FAILED) { close(h->fd); delete h; return fail(nullptr, BDEPTH_ERR_IO, "cannot mmap `%s'", bam_path); }
+    madvise(m, h->file_len, MADV_SEQUENTIAL);
+    h->file = (const uint8_t*)m; h->mapped = true;
+    // index lookup as BaiFile does (baifile.d:98-113): <file>.bai, else <file minus extension>.bai
+    std::string p1 = std::string(bam_path) + ".bai", p2; { std::string s(bam_path); size_t dot = s.rfind('.'); p2 = (dot == std::string::npos ? s + "." : s.substr(0, dot + 1)) + "bai"; }
+    for (const std::string& bp : {p1, p2}) {
+        FILE* f = fopen(bp.c_str(), "rb"); if (!f) continue;
+        fseek(f, 0, SEEK_END); long n = ftell(f); fseek(f, 0, SEEK_SET);
+        std::vector<uint8_t> buf(n > 0 ? n : 0); if (n > 0 && fread(buf.data(), 1, n, f) != (size_t)n) { fclose(f); continue; }
+        fclose(f); h->has_index = true; parse_bai(buf.data(), buf.size(), h->bai); break;
+    }
+    return open_common(h, out);
+}
+
+int bdepth_open_memory(const void* bam, size_t bam_len, const void* bai, size_t bai_len, int device, bdepth_t** out) {
+    if (!bam || !bam_len || !out) return fail(nullptr, BDEPTH_ERR_ARG, "null argument");
+    bdepth* h = new bdepth(); h->device = device; h->file = (const uint8_t*)bam; h->file_len = bam_len;
+    if (bai && bai_len) { h->has_index = true; parse_bai((const uint8_t*)bai, bai_len, h->bai); }
+    return open_common(h, out);
+}
+
+void bdepth_close(bdepth_t* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    DevBuf* bufs[] = {&h->comp, &h->descs, &h->status, &h->ubuf, &h->chunk_start, &h->entry, &h->exitb, &h->count, &h->slot_base, &h->slots, &h->rec_base, &h->walk_list, &h->soa_start, &h->soa_span, &h->soa_meta, &h->soa_off, &h->soa_ncl, &h->soa_lseq, &h->long_list, &h->tile_first, &h->tile_lo, &h->counts, &h->ref_len_d, &h->ref_lin0_d, &h->scan_stats, &h->ref_has, &h->misc};
+    for (DevBuf* b : bufs) b->release();
+    if (h->pinned) cudaFreeHost(h->pinned);
+    if (h->s_main) { cudaStreamDestroy(h->s_main); cudaStreamDestroy(h->s_copy); for (auto& e : h->ev) cudaEventDestroy(e); }
+    if (h->mapped) munmap((void*)h->file, h->file_len);
+    if (h->fd >= 0) close(h->fd);
+    delete h;
+}
+
+const char* bdepth_last_error(const bdepth_t* h) { return h ? h->err.c_str() : g_open_error.c_str(); }
+
+int bdepth_n_ref(const bdepth_t* h) { return (int)h->hdr.ref_len.size(); }
+const char* bdepth_ref_name(const bdepth_t* h, int i) { return (i >= 0 && (size_t)i < h->hdr.ref_names.size()) ? h->hdr.ref_names[i].c_str() : nullptr; }
+uint32_t bdepth_ref_length(const bdepth_t* h, int i) { return (i >= 0 && (size_t)i < h->hdr.ref_len.size()) ? h->hdr.ref_len[i] : 0; }
+const char* bdepth_header_text(const bdepth_t* h, size_t* len) { if (len) *len = h->hdr.text.size(); return h->hdr.text.c_str(); }
+int bdepth_is_coordinate_sorted(const bdepth_t* h) { return h->hdr.so_coordinate ? 1 : 0; }
+int bdepth_has_index(const bdepth_t* h) { return h->has_index ? 1 : 0; }
+int bdepth_n_samples(const bdepth_t* h) { return (int)h->hdr.sample_names.size(); }
+const char* bdepth_sample_name(const bdepth_t* h, int i) { return (i >= 0 && (size_t)i < h->hdr.sample_names.size()) ? h->hdr.sample_names[i].c_str() : nullptr; }
+
+int bdepth_set_filter(bdepth_t* h, int mapq_gt, uint32_t flag_reject_mask) { h->mapq_gt = mapq_gt; h->flag_reject = flag_reject_mask; return 0; }
+int bdepth_set_min_baseq(bdepth_t* h, uint32_t q) { h->minq = q > 255 ? 255 : q; return 0; }
+int bdepth_set_regions(bdepth_t* h, const bdepth_region* r, size_t n) { normalize_regions(h, r, n, h->regions); return 0; }
+int bdepth_set_shard(bdepth_t* h, int rank, int world, const void* nccl_unique_id) {
+    if (world < 1 || rank < 0 || rank >= world) return fail(h, BDEPTH_ERR_ARG, "bad shard %d/%d", rank, world);
+    if (world > 1 && !h->bai.valid) return fail(h, BDEPTH_ERR_NOINDEX, "sharding needs the BAI linear index");
+    (void)nccl_unique_id;
+    h->rank = rank; h->world = world; h->shard_ready = false; h->staged = false;
+    return 0;
+}
+int bdepth_nccl_unique_id(void* out128) { (void)out128; return fail(nullptr, BDEPTH_ERR_NCCL, "NCCL exchange is not built into this library yet"); }
+int bdepth_set_tuning(bdepth_t* h, uint64_t batch_inflated_bytes, uint64_t window_positions) {
+    if (batch_inflated_bytes) h->batch_u = std::max<uint64_t>(batch_inflated_bytes, 1 << 20);
+    h->window_positions = window_positions; h->staged = false;
+    return 0;
+}
+
+int bdepth_stage(bdepth_t* h) {
+    int rc = init_device(h); if (rc) return rc;
+    rc = prepare_shard(h); if (rc) return rc;
+    if (h->blk_lo >= h->blk_hi) { h->staged = false; return 0; }
+    const auto& B = h->blocks;
+    uint64_t f0 = B[h->blk_lo].coff & ~3ull, f1 = B[h->blk_hi - 1].coff + B[h->blk_hi - 1].bsize;
+    CK(h->comp.ensure(f1 - f0 + 256));
+    CK(cudaMemcpyAsync(h->comp.p, h->file + f0, f1 - f0, cudaMemcpyHostToDevice, h->s_main));
+    CK(cudaMemsetAsync((uint8_t*)h->comp.p + (f1 - f0), 0, 128, h->s_main));
+    CK(cudaStreamSynchronize(h->s_main));
+    h->staged = true; h->staged_file_off = f0;
+    return 0;
+}
+
+// ---- base mode: D2H of the counters in EMIT_CHUNK pieces, split at reference boundaries
+int bdepth_run_base(bdepth_t* h, bdepth_tile_cb cb, void* user) {
+    int rc = run_pipeline(h, RUN_FULL, nullptr); if (rc) return rc;
+    cudaStream_t sm = h->s_main;
+    cudaEvent_t e0 = h->ev[5], e1 = h->ev[6];
+    rc = ensure_pinned(h, 2 * EMIT_CHUNK * N_PLANES * 4); if (rc) return rc;
+    // covered positions (rows of default `depth base`)
+    CK(cudaMemsetAsync(h->misc.p, 0, 8, sm));
+    k_count_covered<<<2048, 256, 0, sm>>>(h->counts.as<uint32_t>(), h->win_len, 0, h->hdr.total_len, (unsigned long long*)h->misc.p);
+    CK(cudaGetLastError()); h->st.gpu_launches++;
+    unsigned long long cov = 0; CK(cudaMemcpyAsync(&cov, h->misc.p, 8, cudaMemcpyDeviceToHost, sm));
+    CK(cudaEventRecord(e0, sm));
+    // ranges to deliver: whole genome, or the merged regions
+    struct Range { uint64_t a, b; };
+    std::vector<Range> ranges;
+    if (h->regions.empty()) { if (h->hdr.total_len) ranges.push_back({0, h->hdr.total_len}); }
+    else for (auto& g : h->regions) ranges.push_back({h->hdr.ref_lin0[g.ref_id] + g.start, h->hdr.ref_lin0[g.ref_id] + g.end});
+    // chunk list
+    std::vector<Range> chunks;
+    for (auto& r : ranges) for (uint64_t a = r.a; a < r.b; a += EMIT_CHUNK) chunks.push_back({a, std::min<uint64_t>(r.b, a + EMIT_CHUNK)});
+    auto issue = [&](size_t ci) -> int {
+        uint32_t* dst = (uint32_t*)h->pinned + (ci & 1) * EMIT_CHUNK * N_PLANES; uint64_t n = chunks[ci].b - chunks[ci].a;
+        for (int pl = 0; pl < N_PLANES; pl++) CK(cudaMemcpyAsync(dst + (size_t)pl * EMIT_CHUNK, h->counts.as<uint32_t>() + (uint64_t)pl * h->win_len + (chunks[ci].a - h->cnt_base), n * 4, cudaMemcpyDeviceToHost, sm));
+        CK(cudaEventRecord(h->ev[8 + (ci & 1)], sm));
+        return 0;
+    };
+    const size_t nref = h->hdr.ref_len.size();
+    if (!chunks.empty()) { rc = issue(0); if (rc) return rc; }
+    for (size_t ci = 0; ci < chunks.size(); ci++) {
+        CK(cudaEventSynchronize(h->ev[8 + (ci & 1)]));
+        if (ci + 1 < chunks.size()) { rc = issue(ci + 1); if (rc) return rc; }
+        if (!cb) continue;
+        const uint32_t* src = (const uint32_t*)h->pinned + (ci & 1) * EMIT_CHUNK * N_PLANES;
+        uint64_t a = chunks[ci].a, bnd = chunks[ci].b;
+        // split at reference boundaries
+        size_t ref = std::upper_bound(h->hdr.ref_lin0.begin(), h->hdr.ref_lin0.end(), a) - h->hdr.ref_lin0.begin() - 1;
+        while (a < bnd && ref < nref) {
+            uint64_t rend = h->hdr.ref_lin0[ref] + h->hdr.ref_len[ref];
+            if (a >= rend) { ref++; continue; }
+            uint64_t e = std::min(bnd, rend);
+            bdepth_tile t{(int32_t)ref, (uint32_t)(a - h->hdr.ref_lin0[ref]), (uint32_t)(e - a), (uint32_t)EMIT_CHUNK, src + (a - chunks[ci].a)};
+            if (cb(user, &t)) return fail(h, BDEPTH_ERR_CALLBACK, "tile callback aborted");
+            a = e;
+        }
+    }
+    CK(cudaEventRecord(e1, sm)); CK(cudaStreamSynchronize(sm));
+    h->st.covered_positions = cov;
+    float t; CK(cudaEventElapsedTime(&t, e0, e1)); h->st.ms_d2h = t;
+    h->st.ms_total_device = h->st.ms_h2d + h->st.ms_inflate + h->st.ms_scan + h->st.ms_coverage + h->st.ms_d2h;
+    return 0;
+}
+
+int bdepth_run_windows(bdepth_t* h, uint32_t window, uint32_t overlap, const uint32_t* thr, size_t n_thr, bdepth_stat_cb cb, void* user) {
+    (void)window; (void)overlap; (void)thr; (void)n_thr; (void)cb; (void)user;
+    return fail(h, BDEPTH_ERR_ARG, "window mode: not implemented yet");
+}
+int bdepth_run_regions(bdepth_t* h, const bdepth_region* regions, size_t n, const uint32_t* thr, size_t n_thr, bdepth_stat_cb cb, void* user) {
+    (void)regions; (void)n; (void)thr; (void)n_thr; (void)cb; (void)user;
+    return fail(h, BDEPTH_ERR_ARG, "region mode: not implemented yet");
+}
+
+int bdepth_get_stats(const bdepth_t* h, bdepth_stats* out) { if (!h || !out) return BDEPTH_ERR_ARG; *out = h->st; return 0; }
+
+int64_t bdepth_inflate_to_host(bdepth_t* h, void* dst, uint64_t cap) {
+    RunOut ro; ro.inflate_dst = (uint8_t*)dst; ro.inflate_cap = cap;
+    // whole shard block range, including header blocks, so the result is comparable to a plain inflate of the file
+    int rc = init_device(h); if (rc) return rc;
+    rc = prepare_shard(h); if (rc) return rc;
+    size_t save_lo = h->blk_lo; if (h->world == 1) h->blk_lo = 0;
+    bool save_staged = h->staged; h->staged = false;
+    rc = run_pipeline(h, RUN_INFLATE_ONLY, &ro);
+    h->blk_lo = save_lo; (void)save_staged;
+    if (rc) return rc;
+    return (int64_t)ro.inflate_len;
+}
+
+int64_t bdepth_scan_to_host(bdepth_t* h, uint64_t cap, int32_t* ref_id, int32_t* pos, uint32_t* span, uint16_t* flag, uint8_t* mapq, uint16_t* n_cigar, uint64_t* rec_off) {
+    RunOut ro; ro.scan_cap = cap; ro.ref_id = ref_id; ro.pos = pos; ro.span = span; ro.flag = flag; ro.mapq = mapq; ro.n_cigar = n_cigar; ro.rec_off = rec_off;
+    int rc = run_pipeline(h, RUN_SCAN_ONLY, &ro);
+    if (rc) return rc;
+    return (int64_t)ro.scan_n;
+}
+
+}  // extern "C"

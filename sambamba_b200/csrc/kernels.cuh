@@ -1,0 +1,465 @@
+// kernels.cuh -- the sm_100a kernels of the depth hot path.
+//
+//   K1  k1_inflate          lane-per-BGZF-block DEFLATE (inflate_core.cuh)
+//   K2  k2_guess_entries    first record start of every BGZF block (speculative, verified)
+//       k2_walk             per-block record chain walk -> record offsets, exit offset
+//       k2_decode           record header + CIGAR -> columnar SoA (warp per block)
+//   K3  k3_tile_index       per-tile read ranges (tile_first / tile_lo)
+//       k3_gather           per-position gather: every thread owns 4 consecutive positions and
+//                           accumulates all reads covering them in registers (no atomics)
+//       k3_scatter_long     reads spanning > SPAN_SHORT (spliced / long reads): warp per read,
+//                           RED atomics
+//   R   k_tile_covered, k_bucket_stats, k_read_windows, k_read_regions : reducers for the
+//       base / window / region front ends
+//
+// Semantics restated (file:line under /root/reference):
+//   record layout      BioD/bio/std/hts/bam/read.d:907-1003, readrange.d:118-173
+//   CIGAR predicates   BioD/bio/std/hts/bam/cigar.d:58-148 (CIGAR_TYPE :116)
+//   filter             sambamba/depth.d:1159, filtering.d:163-167,194-214
+//   basesCovered()>0   BioD/bio/std/hts/bam/pileup.d:509-519, read.d:255-262
+//   per-base counters  sambamba/depth.d:495-556 (writeColumn), base.d:186 (nt16 -> nt5)
+//   region/window      sambamba/depth.d:661-698 (countRead), :760-845 (push), :847-876
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "inflate_core.cuh"
+
+namespace bdk {
+
+constexpr int TILE_POS = 1024;          // positions per K3 CTA (256 threads x 4)
+constexpr uint32_t SPAN_SHORT = 1024;   // reads spanning more go to the scatter path
+constexpr int N_PLANES = 7;
+constexpr int64_t ENTRY_NONE = -1;
+
+// ------------------------------------------------------------------------------------- K1
+struct BlockDesc {
+    uint64_t coff;      // byte offset of the raw deflate data inside the compressed buffer
+    uint64_t uoff;      // byte offset of the output inside the inflated buffer
+    uint32_t csize;
+    uint32_t isize;
+};
+
+__global__ void __launch_bounds__(32) k1_inflate(const uint32_t* __restrict__ comp, const BlockDesc* __restrict__ blocks,
+                                                 uint32_t n_blocks, uint8_t* __restrict__ u, int* __restrict__ status) {
+    extern __shared__ uint32_t smem[];
+    uint32_t lane = threadIdx.x;
+    uint32_t b = blockIdx.x * 32u + lane;
+    uint8_t lens[320];
+    if (b < n_blocks) {
+        BlockDesc d = blocks[b];
+        SmemTab tab{smem + lane};
+        ByteOut out{u + d.uoff};
+        int rc = inflate_block(tab, comp, d.coff, d.csize, out, d.isize, lens);
+        status[b] = rc;
+    }
+}
+
+// ------------------------------------------------------------------------------------- K2
+__device__ __forceinline__ uint32_t ldu32(const uint8_t* p) {
+    return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
+}
+__device__ __forceinline__ uint32_t ldu16(const uint8_t* p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8); }
+
+struct ScanParams {
+    const uint8_t* u;          // inflated stream; offsets below are relative to it (may be negative for the carry)
+    int64_t u_begin;           // first valid byte (<= 0 when a carry precedes the batch)
+    int64_t u_end;             // one past the last valid byte
+    int n_ref;
+    const uint32_t* ref_len;
+    const uint64_t* ref_lin0;  // linear coordinate of position 0 of each reference
+};
+
+// A record header at offset o is plausible if its fixed fields are mutually consistent.
+__device__ __forceinline__ bool plausible_record(const ScanParams& sp, int64_t o, int64_t* next) {
+    if (o + 36 > sp.u_end) return false;
+    const uint8_t* p = sp.u + o;
+    uint32_t bs = ldu32(p);
+    if (bs < 32u || bs > (1u << 28)) return false;
+    int32_t ref = (int32_t)ldu32(p + 4), pos = (int32_t)ldu32(p + 8);
+    if (ref < -1 || ref >= sp.n_ref || pos < -1) return false;
+    if (ref >= 0 && (uint32_t)pos > sp.ref_len[ref]) return false;
+    uint32_t l_name = p[12];
+    uint32_t n_cigar = ldu16(p + 16);
+    int32_t l_seq = (int32_t)ldu32(p + 20);
+    int32_t nref = (int32_t)ldu32(p + 24), npos = (int32_t)ldu32(p + 28);
+    if (l_name < 1 || l_seq < 0 || nref < -1 || nref >= sp.n_ref || npos < -1) return false;
+    uint64_t need = 32ull + l_name + 4ull * n_cigar + ((uint64_t)l_seq + 1) / 2 + (uint64_t)l_seq;
+    if (need > bs) return false;
+    int64_t nul = o + 36 + l_name - 1;
+    if (nul < sp.u_end && sp.u[nul] != 0) return false;
+    *next = o + 4 + (int64_t)bs;
+    return true;
+}
+
+// One warp per BGZF block: the smallest offset in the block at which a chain of 3 plausible
+// records starts.  Result is only a GUESS; k2_walk + host verification make it exact.
+__global__ void k2_guess_entries(ScanParams sp, const int64_t* __restrict__ chunk_start, uint32_t n_chunks, int64_t* __restrict__ entry) {
+    uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= n_chunks) return;
+    if (warp == 0) return;                 // chunk 0 is anchored by the caller
+    int64_t c0 = chunk_start[warp], c1 = chunk_start[warp + 1];
+    int64_t found = ENTRY_NONE;
+    for (int64_t base = c0; base < c1; base += 32) {
+        int64_t o = base + lane, nx = 0;
+        bool ok = o < c1 && plausible_record(sp, o, &nx);
+        if (ok) {
+            // follow two more records (each must be plausible unless it runs off the stream end)
+            int64_t o2 = nx, n2 = 0;
+            if (o2 + 36 <= sp.u_end) { ok = plausible_record(sp, o2, &n2); if (ok && n2 + 36 <= sp.u_end) { int64_t n3; ok = plausible_record(sp, n2, &n3); } }
+        }
+        unsigned m = __ballot_sync(0xFFFFFFFFu, ok);
+        if (m) { found = base + (__ffs(m) - 1); break; }
+    }
+    if (lane == 0) entry[warp] = found;
+}
+
+// One thread per block: walk the record chain from entry[c] while the record STARTS inside the
+// block.  Writes the start offsets (relative to chunk_start) and the exit offset.
+// walk_list (optional) restricts the launch to the listed chunks (fix-up passes).
+__global__ void k2_walk(ScanParams sp, const int64_t* __restrict__ chunk_start, uint32_t n_chunks, const int64_t* __restrict__ entry,
+                        const uint32_t* __restrict__ slot_base, uint16_t* __restrict__ slots, uint32_t* __restrict__ count,
+                        int64_t* __restrict__ exit_off, int* __restrict__ err, const uint32_t* __restrict__ walk_list, uint32_t n_list) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t c;
+    if (walk_list) { if (t >= n_list) return; c = walk_list[t]; } else { if (t >= n_chunks) return; c = t; }
+    int64_t o = entry[c], c0 = chunk_start[c], c1 = chunk_start[c + 1];
+    uint32_t n = 0;
+    if (o != ENTRY_NONE) {
+        uint16_t* sl = slots + slot_base[c];
+        while (o < c1) {
+            if (o + 4 > sp.u_end) break;                       // size field itself is cut: tail
+            uint32_t bs = ldu32(sp.u + o);
+            if (bs < 32u) { atomicExch(err, 1); break; }       // corrupt chain
+            if (o + 4 + (int64_t)bs > sp.u_end) break;          // incomplete record: tail, carried to the next batch
+            sl[n++] = (uint16_t)(o - c0);
+            o += 4 + (int64_t)bs;
+        }
+    }
+    count[c] = n;
+    exit_off[c] = o;
+}
+
+// Columnar SoA written by k2_decode (one row per record, file order).
+struct RecordSoA {
+    uint64_t* start;     // linear coordinate of the first reference base (UINT64_MAX-1 when unplaced)
+    uint32_t* span;      // reference bases covered, clipped to the reference end; 0 => contributes nothing
+    uint32_t* meta;      // flag << 16 | mapq << 8 | bit0 pass | bit1 long
+    int64_t* off;        // offset of the record's refID field relative to the batch's inflated bytes (negative inside the carry)
+    uint32_t* ncl;       // n_cigar << 8 | l_read_name
+    int32_t*  lseq;
+};
+struct ScanStats {      // device-side accumulators
+    unsigned long long n_pass, n_cigar, seq_bytes, max_end, min_start, n_long;
+};
+
+__device__ __forceinline__ bool cig_rcons(uint32_t op) { return op == 0 || op == 2 || op == 3 || op == 7 || op == 8; }
+__device__ __forceinline__ bool cig_qcons(uint32_t op) { return op == 0 || op == 1 || op == 4 || op == 7 || op == 8; }
+__device__ __forceinline__ bool cig_match(uint32_t op) { return op == 0 || op == 7 || op == 8; }
+
+__global__ void k2_decode(ScanParams sp, const int64_t* __restrict__ chunk_start, uint32_t n_chunks, const uint32_t* __restrict__ slot_base,
+                          const uint16_t* __restrict__ slots, const uint32_t* __restrict__ count, const uint32_t* __restrict__ rec_base,
+                          RecordSoA soa, int mapq_gt, uint32_t flag_reject, ScanStats* __restrict__ st, uint32_t* __restrict__ long_list,
+                          uint32_t* __restrict__ ref_has_reads) {
+    uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= n_chunks) return;
+    uint32_t n = count[warp];
+    int64_t c0 = chunk_start[warp];
+    const uint16_t* sl = slots + slot_base[warp];
+    uint32_t rb = rec_base[warp];
+    unsigned long long loc_pass = 0, loc_cig = 0, loc_seq = 0, loc_maxend = 0, loc_minstart = ~0ull;
+    for (uint32_t k = lane; k < n; k += 32) {
+        int64_t o = c0 + sl[k];
+        const uint8_t* p = sp.u + o + 4;
+        int32_t ref = (int32_t)ldu32(p), pos = (int32_t)ldu32(p + 4);
+        uint32_t bmn = ldu32(p + 8), fnc = ldu32(p + 12);
+        int32_t l_seq = (int32_t)ldu32(p + 16);
+        uint32_t l_name = bmn & 0xFF, mapq = (bmn >> 8) & 0xFF, flag = fnc >> 16, n_cigar = fnc & 0xFFFF;
+        const uint8_t* cg = p + 32 + l_name;
+        uint64_t span = 0;
+        for (uint32_t i = 0; i < n_cigar; i++) { uint32_t c = ldu32(cg + 4 * i); if (cig_rcons(c & 15)) span += c >> 4; }
+        bool placed = ref >= 0 && ref < sp.n_ref && pos >= 0;
+        bool pass = placed && ((int)mapq > mapq_gt) && !(flag & flag_reject) && !(flag & 4u) && span > 0;
+        uint64_t start = placed ? sp.ref_lin0[ref] + (uint64_t)pos : 0xFFFFFFFFFFFFFFFEull;
+        uint32_t span_eff = 0;
+        if (pass) {
+            uint64_t room = (uint32_t)pos < sp.ref_len[ref] ? (uint64_t)sp.ref_len[ref] - (uint32_t)pos : 0;
+            span_eff = (uint32_t)(span < room ? span : room);
+            if (span_eff == 0) pass = false;
+        }
+        bool is_long = pass && span_eff > SPAN_SHORT;
+        uint32_t r = rb + k;
+        soa.start[r] = start; soa.span[r] = span_eff;
+        soa.meta[r] = (flag << 16) | (mapq << 8) | (pass ? 1u : 0u) | (is_long ? 2u : 0u);
+        soa.off[r] = o + 4; soa.ncl[r] = (n_cigar << 8) | l_name; soa.lseq[r] = l_seq;
+        loc_cig += n_cigar;
+        if (pass) {
+            loc_pass++; loc_seq += ((uint64_t)l_seq + 1) / 2;
+            if (start + span_eff > loc_maxend) loc_maxend = start + span_eff;
+            if (start < loc_minstart) loc_minstart = start;
+            atomicOr(&ref_has_reads[ref >> 5], 1u << (ref & 31));
+            if (is_long) { uint32_t idx = (uint32_t)atomicAdd(&st->n_long, 1ull); long_list[idx] = r; }
+        }
+    }
+    for (int s = 16; s; s >>= 1) {
+        loc_pass += __shfl_xor_sync(0xFFFFFFFFu, loc_pass, s); loc_cig += __shfl_xor_sync(0xFFFFFFFFu, loc_cig, s); loc_seq += __shfl_xor_sync(0xFFFFFFFFu, loc_seq, s);
+        unsigned long long m = __shfl_xor_sync(0xFFFFFFFFu, loc_maxend, s); if (m > loc_maxend) loc_maxend = m;
+        m = __shfl_xor_sync(0xFFFFFFFFu, loc_minstart, s); if (m < loc_minstart) loc_minstart = m;
+    }
+    if (lane == 0) {
+        if (loc_pass) atomicAdd(&st->n_pass, loc_pass);
+        if (loc_cig) atomicAdd(&st->n_cigar, loc_cig);
+        if (loc_seq) atomicAdd(&st->seq_bytes, loc_seq);
+        if (loc_maxend) atomicMax(&st->max_end, loc_maxend);
+        if (loc_minstart != ~0ull) atomicMin(&st->min_start, loc_minstart);
+    }
+}
+
+// ------------------------------------------------------------------------------------- K3
+// tile t covers linear positions [win_base + t*TILE_POS, +TILE_POS).
+// tile_first[t] = first record index whose start >= tile start   (n_tiles + 1 entries, pre-set to R)
+// tile_lo[t]    = smallest index of a passing short read overlapping tile t (pre-set to 0xFFFFFFFF)
+__global__ void k3_tile_index(RecordSoA soa, uint32_t R, uint64_t win_base, uint32_t n_tiles, uint32_t* __restrict__ tile_first, uint32_t* __restrict__ tile_lo) {
+    uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    uint64_t s = soa.start[r];
+    // boundaries: tiles whose start lies in (prev_start, s] get first = r
+    int64_t t_cur = s >= win_base ? (int64_t)((s - win_base + TILE_POS - 1) / TILE_POS) : 0;        // first tile with tile_start >= s ... see below
+    // tile_first[t] = min{ r : start[r] >= tile_start(t) }.  Record r is that minimum for all t with
+    // start[r-1] < tile_start(t) <= start[r].
+    int64_t t_hi = s >= win_base ? (int64_t)((s - win_base) / TILE_POS) : -1;                        // last tile with tile_start <= s
+    int64_t t_lo;
+    if (r == 0) t_lo = 0;
+    else { uint64_t ps = soa.start[r - 1]; t_lo = ps >= win_base ? (int64_t)((ps - win_base) / TILE_POS) + 1 : 0; }
+    (void)t_cur;
+    if (t_hi > (int64_t)n_tiles) t_hi = n_tiles;
+    for (int64_t t = t_lo; t <= t_hi; t++) tile_first[t] = r;
+    uint32_t m = soa.meta[r];
+    if ((m & 3u) == 1u && s >= win_base) {
+        uint64_t e = s + soa.span[r] - 1;
+        uint64_t ta = (s - win_base) / TILE_POS, tb = (e - win_base) / TILE_POS;
+        for (uint64_t t = ta; t <= tb && t < n_tiles; t++) atomicMin(&tile_lo[t], r);
+    }
+}
+
+__device__ __forceinline__ uint32_t ldg8(const uint8_t* p) { return (uint32_t)__ldg(p); }
+
+struct GatherAcc {
+    uint32_t packed[4];          // A,C,G,T as 4 x 8-bit fields per position
+    uint32_t wide[4][4];         // flushed A,C,G,T
+    uint32_t nN[4], del[4], skip[4];
+};
+
+// add base with reference offset x (relative to the read start) at query index q for slot j
+template <bool MINQ>
+__device__ __forceinline__ void add_base(GatherAcc& a, int j, const uint8_t* seq, const uint8_t* qual, uint32_t q, uint32_t lseq, uint32_t minq) {
+    if (q >= lseq) return;
+    if (MINQ) { if (ldg8(qual + q) < minq) return; }
+    uint32_t b = ldg8(seq + (q >> 1));
+    uint32_t nib = (q & 1) ? (b & 15u) : (b >> 4);
+    // nt16 -> nt5 (base.d:186): 1,2,4,8 -> A,C,G,T ; everything else N
+    if (__popc(nib) == 1) a.packed[j] += 1u << ((31 - __clz(nib)) * 8);
+    else a.nN[j]++;
+}
+
+template <bool MINQ>
+__global__ void __launch_bounds__(256) k3_gather(RecordSoA soa, const uint8_t* __restrict__ u, uint64_t tiles_base, uint64_t cnt_base, uint64_t win_len,
+                                                  const uint32_t* __restrict__ tile_first, const uint32_t* __restrict__ tile_lo,
+                                                  uint32_t* __restrict__ counts, uint32_t minq) {
+    uint32_t tile = blockIdx.x;
+    uint32_t lo = tile_lo[tile];
+    if (lo == 0xFFFFFFFFu) return;                       // no passing short read touches this tile
+    uint32_t hi = tile_first[tile + 1];
+    uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint64_t w0 = tiles_base + (uint64_t)tile * TILE_POS + warp * 128u, w1 = w0 + 128;
+    uint64_t p0 = w0 + 4u * lane;
+    GatherAcc a;
+#pragma unroll
+    for (int j = 0; j < 4; j++) { a.packed[j] = 0; a.nN[j] = a.del[j] = a.skip[j] = 0; for (int c = 0; c < 4; c++) a.wide[j][c] = 0; }
+    uint32_t since_flush = 0;
+    for (uint32_t base = lo; base < hi; base += 32) {
+        uint32_t r = base + lane;
+        uint64_t s = 0; uint32_t sp = 0; bool ov = false;
+        if (r < hi) {
+            s = soa.start[r]; sp = soa.span[r];
+            ov = (soa.meta[r] & 3u) == 1u && s < w1 && s + sp > w0;
+        }
+        // reads are sorted by start: once the first lane of a group starts at or past w1, we are done
+        uint64_t s_first = __shfl_sync(0xFFFFFFFFu, s, 0);
+        if (s_first >= w1) break;
+        unsigned m = __ballot_sync(0xFFFFFFFFu, ov);
+        while (m) {
+            int bsel = __ffs(m) - 1; m &= m - 1;
+            uint32_t rr = base + bsel;
+            uint64_t rs = __shfl_sync(0xFFFFFFFFu, s, bsel);
+            uint32_t rspan = __shfl_sync(0xFFFFFFFFu, sp, bsel);
+            int64_t off = soa.off[rr]; uint32_t ncl = soa.ncl[rr]; uint32_t lseq = (uint32_t)max(soa.lseq[rr], 0);
+            uint32_t n_cigar = ncl >> 8, l_name = ncl & 0xFF;
+            const uint8_t* rec = u + off;
+            const uint8_t* cg = rec + 32 + l_name;
+            const uint8_t* seq = cg + 4u * n_cigar;
+            const uint8_t* qual = seq + (lseq + 1) / 2;
+            int64_t rp = (int64_t)p0 - (int64_t)rs;        // reference offset of this lane's first position
+            uint32_t rpos = 0, qpos = 0;
+            for (uint32_t i = 0; i < n_cigar; i++) {
+                uint32_t c = ldu32(cg + 4 * i), len = c >> 4, op = c & 15;
+                if (cig_match(op)) {
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        int64_t x = rp + j - (int64_t)rpos;
+                        if (x >= 0 && x < (int64_t)len && (uint64_t)(rp + j) < rspan) add_base<MINQ>(a, j, seq, qual, qpos + (uint32_t)x, lseq, minq);
+                    }
+                    rpos += len; qpos += len;
+                } else if (op == 2 || op == 3) {
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        int64_t x = rp + j - (int64_t)rpos;
+                        if (x >= 0 && x < (int64_t)len && (uint64_t)(rp + j) < rspan) { if (op == 2) a.del[j]++; else a.skip[j]++; }
+                    }
+                    rpos += len;
+                } else if (cig_qcons(op)) qpos += len;
+                if ((int64_t)rpos > rp + 3) break;          // (warp-divergent exit is fine: remaining ops cannot touch this lane)
+            }
+            if (++since_flush == 255) {
+                since_flush = 0;
+#pragma unroll
+                for (int j = 0; j < 4; j++) { for (int c = 0; c < 4; c++) a.wide[j][c] += (a.packed[j] >> (8 * c)) & 255u; a.packed[j] = 0; }
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; j++) for (int c = 0; c < 4; c++) a.wide[j][c] += (a.packed[j] >> (8 * c)) & 255u;
+    // read-modify-write of this thread's 4 positions in each plane (16-byte vector accesses)
+    uint64_t idx = p0 - cnt_base;
+    if (idx + 4 > win_len) return;
+    uint32_t any = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) any |= a.wide[j][0] | a.wide[j][1] | a.wide[j][2] | a.wide[j][3] | a.nN[j] | a.del[j] | a.skip[j];
+    if (!any) return;
+#pragma unroll
+    for (int pl = 0; pl < N_PLANES; pl++) {
+        uint32_t v[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) v[j] = pl < 4 ? a.wide[j][pl] : pl == 4 ? a.nN[j] : pl == 5 ? a.del[j] : a.skip[j];
+        if (!(v[0] | v[1] | v[2] | v[3])) continue;
+        uint4* dst = reinterpret_cast<uint4*>(counts + (uint64_t)pl * win_len + idx);
+        uint4 cur = *dst;
+        cur.x += v[0]; cur.y += v[1]; cur.z += v[2]; cur.w += v[3];
+        *dst = cur;
+    }
+}
+
+// Long reads: one warp per read, lanes stride over the bases of each op, RED atomics.
+template <bool MINQ>
+__global__ void k3_scatter_long(RecordSoA soa, const uint8_t* __restrict__ u, const uint32_t* __restrict__ long_list, uint32_t n_long,
+                                uint64_t win_base, uint64_t win_len, uint32_t* __restrict__ counts, uint32_t minq) {
+    uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= n_long) return;
+    uint32_t rr = long_list[warp];
+    uint64_t rs = soa.start[rr]; uint32_t rspan = soa.span[rr];
+    int64_t off = soa.off[rr]; uint32_t ncl = soa.ncl[rr]; uint32_t lseq = (uint32_t)max(soa.lseq[rr], 0);
+    uint32_t n_cigar = ncl >> 8, l_name = ncl & 0xFF;
+    const uint8_t* rec = u + off; const uint8_t* cg = rec + 32 + l_name; const uint8_t* seq = cg + 4u * n_cigar; const uint8_t* qual = seq + (lseq + 1) / 2;
+    uint32_t rpos = 0, qpos = 0;
+    for (uint32_t i = 0; i < n_cigar; i++) {
+        uint32_t c = ldu32(cg + 4 * i), len = c >> 4, op = c & 15;
+        if (cig_match(op)) {
+            for (uint32_t x = lane; x < len; x += 32) {
+                uint32_t rp = rpos + x, q = qpos + x;
+                if (rp >= rspan || q >= lseq) continue;
+                uint64_t g = rs + rp; if (g < win_base || g - win_base >= win_len) continue;
+                if (MINQ) { if (ldg8(qual + q) < minq) continue; }
+                uint32_t b = ldg8(seq + (q >> 1)); uint32_t nib = (q & 1) ? (b & 15u) : (b >> 4);
+                uint32_t pl = (__popc(nib) == 1) ? (31 - __clz(nib)) : 4;
+                atomicAdd(counts + (uint64_t)pl * win_len + (g - win_base), 1u);
+            }
+            rpos += len; qpos += len;
+        } else if (op == 2 || op == 3) {
+            uint32_t pl = op == 2 ? 5 : 6;
+            for (uint32_t x = lane; x < len; x += 32) {
+                uint32_t rp = rpos + x; if (rp >= rspan) continue;
+                uint64_t g = rs + rp; if (g < win_base || g - win_base >= win_len) continue;
+                atomicAdd(counts + (uint64_t)pl * win_len + (g - win_base), 1u);
+            }
+            rpos += len;
+        } else if (cig_qcons(op)) qpos += len;
+    }
+}
+
+// ------------------------------------------------------------------------------------- reducers
+// number of positions in [a, b) (window-relative) whose 7 counters sum to > 0
+__global__ void k_count_covered(const uint32_t* __restrict__ counts, uint64_t win_len, uint64_t a, uint64_t b, unsigned long long* __restrict__ out) {
+    uint64_t i = a + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    unsigned long long n = 0;
+    for (; i < b; i += stride) {
+        uint32_t s = 0;
+#pragma unroll
+        for (int pl = 0; pl < N_PLANES; pl++) s |= counts[(uint64_t)pl * win_len + i];
+        n += s != 0;
+    }
+    for (int sft = 16; sft; sft >>= 1) n += __shfl_xor_sync(0xFFFFFFFFu, n, sft);
+    if ((threadIdx.x & 31) == 0 && n) atomicAdd(out, n);
+}
+
+// Segment statistics over the counters: one warp per segment [seg_a[i], seg_b[i]) (window-relative).
+// out_bases[i] += sum(A+C+G+T+N); out_cov[t][i] += #positions with all-7 sum >= thr[t].
+__global__ void k_segment_stats(const uint32_t* __restrict__ counts, uint64_t win_len, const uint64_t* __restrict__ seg_a, const uint64_t* __restrict__ seg_b,
+                                uint32_t n_seg, const uint32_t* __restrict__ thr, uint32_t n_thr, uint32_t* __restrict__ out_bases, uint32_t* __restrict__ out_cov /* [n_thr][n_seg] */) {
+    uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= n_seg) return;
+    uint64_t a = seg_a[warp], b = seg_b[warp];
+    uint32_t bases = 0; uint32_t cge[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (uint64_t i = a + lane; i < b; i += 32) {
+        uint32_t s5 = 0, s = 0;
+#pragma unroll
+        for (int pl = 0; pl < N_PLANES; pl++) { uint32_t v = counts[(uint64_t)pl * win_len + i]; s += v; if (pl < 5) s5 += v; }
+        bases += s5;
+        if (s) { for (uint32_t t = 0; t < n_thr && t < 8; t++) cge[t] += s >= thr[t]; }
+    }
+    for (int sft = 16; sft; sft >>= 1) { bases += __shfl_xor_sync(0xFFFFFFFFu, bases, sft); for (int t = 0; t < 8; t++) cge[t] += __shfl_xor_sync(0xFFFFFFFFu, cge[t], sft); }
+    if (lane == 0) { if (bases) atomicAdd(&out_bases[warp], bases); for (uint32_t t = 0; t < n_thr && t < 8; t++) if (cge[t]) atomicAdd(&out_cov[(uint64_t)t * n_seg + warp], cge[t]); }
+}
+
+// Per-read "countRead" (depth.d:661-669) against sorted segments: a read adds 1 to n_reads of every
+// segment in which it has >= 1 M/=/X base with quality >= minq.  Segments are given sorted by start
+// in LINEAR coordinates with pmax_end[i] = max(end[0..i]) for pruning; seg_id maps to the output slot.
+template <bool MINQ>
+__global__ void k_read_segments(RecordSoA soa, const uint8_t* __restrict__ u, uint32_t R, const uint64_t* __restrict__ seg_s, const uint64_t* __restrict__ seg_e,
+                                const uint64_t* __restrict__ pmax_end, const uint32_t* __restrict__ seg_id, const uint64_t* __restrict__ seg_min_start, uint32_t n_seg,
+                                uint32_t* __restrict__ out_reads, uint32_t minq) {
+    uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    if (!(soa.meta[r] & 1u)) return;
+    uint64_t rs = soa.start[r]; uint32_t rspan = soa.span[r]; uint64_t re = rs + rspan;
+    // candidates: segments with seg_s < re ; walk down from the last such while pmax_end > rs
+    uint32_t lo = 0, hi = n_seg;
+    while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (seg_s[mid] < re) lo = mid + 1; else hi = mid; }
+    if (lo == 0) return;
+    int64_t off = soa.off[r]; uint32_t ncl = soa.ncl[r]; uint32_t lseq = (uint32_t)max(soa.lseq[r], 0);
+    uint32_t n_cigar = ncl >> 8, l_name = ncl & 0xFF;
+    const uint8_t* rec = u + off; const uint8_t* cg = rec + 32 + l_name; const uint8_t* qual = cg + 4u * n_cigar + (lseq + 1) / 2;
+    for (int64_t k = (int64_t)lo - 1; k >= 0; k--) {
+        if (pmax_end[k] <= rs) break;
+        uint64_t a = seg_s[k], b = seg_e[k];
+        if (b <= rs || a >= re) continue;
+        if (seg_min_start && rs < seg_min_start[k]) continue;      // window-mode first-occurrence quirk (depth.d:1031-1032)
+        // any M base with q >= minq inside [a,b)?
+        bool hit = false; uint32_t rpos = 0, qpos = 0;
+        for (uint32_t i = 0; i < n_cigar && !hit; i++) {
+            uint32_t c = ldu32(cg + 4 * i), len = c >> 4, op = c & 15;
+            if (cig_match(op)) {
+                uint64_t ma = rs + rpos, mb = ma + len; if (mb > re) mb = re;
+                uint64_t xa = ma > a ? ma : a, xb = mb < b ? mb : b;
+                if (xa < xb) {
+                    if (!MINQ) hit = (qpos + (uint32_t)(xa - ma)) < lseq;
+                    else for (uint64_t g = xa; g < xb && !hit; g++) { uint32_t q = qpos + (uint32_t)(g - ma); if (q < lseq && ldg8(qual + q) >= minq) hit = true; }
+                }
+                rpos += len; qpos += len;
+            } else if (op == 2 || op == 3) rpos += len;
+            else if (cig_qcons(op)) qpos += len;
+        }
+        if (hit) atomicAdd(&out_reads[seg_id[k]], 1u);
+    }
+}
+
+}  // namespace bdk

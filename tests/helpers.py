@@ -1,0 +1,116 @@
+"""Shared test helpers: oracle bindings (TEST INFRASTRUCTURE), synthetic inputs."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+ORACLE_EXE = os.path.join(ROOT, "oracle", "_build", "depth_oracle")
+ORACLE_LIB = os.path.join(ROOT, "oracle", "_build", "liboracle.so")
+BAMGEN = os.path.join(ROOT, "tools", "_build", "bamgen")
+CLI = os.path.join(ROOT, "sambamba_b200", "_build", "sambamba-depth-b200")
+
+_orc = None
+
+
+class ScatterStats(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("n_records", "n_pass", "n_blocks", "ulen", "clen", "covered")] + \
+               [("t_inflate", C.c_double), ("t_scan", C.c_double)]
+
+
+def oracle():
+    global _orc
+    if _orc is None:
+        L = C.CDLL(ORACLE_LIB)
+        L.oracle_inflate_file.restype = C.c_int64
+        L.oracle_inflate_file.argtypes = [C.c_char_p, C.c_void_p, C.c_uint64]
+        L.oracle_base_counts.argtypes = [C.c_char_p, C.c_int, C.c_uint, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_uint64, C.POINTER(ScatterStats)]
+        L.oracle_bam_info.argtypes = [C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        L.oracle_last_error.restype = C.c_char_p
+        _orc = L
+    return _orc
+
+
+def oracle_inflate(path):
+    L = oracle()
+    n = L.oracle_inflate_file(path.encode(), None, 0)
+    assert n >= 0, L.oracle_last_error()
+    buf = np.zeros(max(1, n), np.uint8)
+    assert L.oracle_inflate_file(path.encode(), buf.ctypes.data_as(C.c_void_p), n) == n
+    return buf[:n]
+
+
+def oracle_info(path):
+    L = oracle()
+    nref, tot, ulen, nblk = C.c_int(), C.c_uint64(), C.c_uint64(), C.c_uint64()
+    assert L.oracle_bam_info(path.encode(), C.byref(nref), C.byref(tot), C.byref(ulen), C.byref(nblk)) == 0
+    return nref.value, tot.value, ulen.value, nblk.value
+
+
+def oracle_counts(path, mapq_gt=0, flag_reject=0x600, min_bq=0, threads=1):
+    """Closed-form per-read scatter oracle: counts[7, total_len]."""
+    L = oracle()
+    _, tot, _, _ = oracle_info(path)
+    out = np.zeros((7, max(1, tot)), np.uint32)
+    st = ScatterStats()
+    rc = L.oracle_base_counts(path.encode(), mapq_gt, flag_reject, min_bq, threads, 0, out.ctypes.data_as(C.c_void_p), max(1, tot), C.byref(st))
+    assert rc == 0, L.oracle_last_error()
+    return out[:, :tot], st
+
+
+def oracle_cli(args, stdin=None):
+    r = subprocess.run([ORACLE_EXE, "depth"] + list(args), capture_output=True)
+    return r.returncode, r.stdout, r.stderr
+
+
+def run_cli(args):
+    r = subprocess.run([CLI] + list(args), capture_output=True)
+    return r.returncode, r.stdout, r.stderr
+
+
+def gen_bam(path, *extra):
+    subprocess.check_call([BAMGEN, "-o", path] + [str(x) for x in extra], stderr=subprocess.DEVNULL)
+    return path
+
+
+def parse_records(u, first_off):
+    """Pure-numpy/py walk of an inflated BAM stream -> list of (off, ref, pos, flag, mapq, n_cigar, span)."""
+    import struct
+    out = []
+    o = first_off
+    n = len(u)
+    b = u.tobytes()
+    while o + 4 <= n:
+        bs = struct.unpack_from("<i", b, o)[0]
+        if o + 4 + bs > n:
+            break
+        ref, pos, bmn, fnc, lseq = struct.unpack_from("<iiIIi", b, o + 4)
+        lname = bmn & 0xFF
+        ncig = fnc & 0xFFFF
+        span = 0
+        for k in range(ncig):
+            c = struct.unpack_from("<I", b, o + 36 + lname + 4 * k)[0]
+            if (c & 15) in (0, 2, 3, 7, 8):
+                span += c >> 4
+        out.append((o, ref, pos, fnc >> 16, (bmn >> 8) & 0xFF, ncig, span))
+        o += 4 + bs
+    return out
+
+
+def header_first_record_offset(u):
+    import struct
+    b = u.tobytes()
+    l_text = struct.unpack_from("<i", b, 4)[0]
+    off = 8 + l_text
+    n_ref = struct.unpack_from("<i", b, off)[0]
+    off += 4
+    refs = []
+    for _ in range(n_ref):
+        ln = struct.unpack_from("<i", b, off)[0]
+        name = b[off + 4:off + 4 + ln - 1].decode()
+        L = struct.unpack_from("<i", b, off + 4 + ln)[0]
+        refs.append((name, L))
+        off += 8 + ln
+    return off, refs
