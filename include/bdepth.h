@@ -152,6 +152,9 @@ int bdepth_run_windows(bdepth_t* h, uint32_t window, uint32_t overlap, const uin
 int bdepth_run_regions(bdepth_t* h, const bdepth_region* regions, size_t n, const uint32_t* thresholds, size_t n_thresholds, bdepth_stat_cb cb, void* user);
 
 int bdepth_get_stats(const bdepth_t* h, bdepth_stats* out);
+/* After a run: 1 if the reference has at least one read that produced a pileup column (the
+ * condition under which depth.d:1225-1229 prints "Processing reference #k"). */
+int bdepth_ref_has_reads(const bdepth_t* h, int ref);
 
 /* ------------------------------------------------------------------ kernel-level entry points
  * (used by the parity tests and the roofline bench; same kernels as the runs above) */

@@ -90,6 +90,7 @@ def load_library():
     L.bdepth_run_windows.argtypes = [vp, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32), C.c_size_t, STAT_CB, vp]
     L.bdepth_run_regions.argtypes = [vp, C.POINTER(Region), C.c_size_t, C.POINTER(C.c_uint32), C.c_size_t, STAT_CB, vp]
     L.bdepth_get_stats.argtypes = [vp, C.POINTER(Stats)]
+    L.bdepth_ref_has_reads.argtypes = [vp, C.c_int]
     L.bdepth_inflate_to_host.argtypes = [vp, vp, C.c_uint64]
     L.bdepth_inflate_to_host.restype = C.c_int64
     L.bdepth_scan_to_host.argtypes = [vp, C.c_uint64] + [vp] * 7
@@ -103,7 +104,7 @@ EXPORTED_SYMBOLS = [
     "bdepth_ref_name", "bdepth_ref_length", "bdepth_header_text", "bdepth_is_coordinate_sorted", "bdepth_has_index",
     "bdepth_n_samples", "bdepth_sample_name", "bdepth_set_filter", "bdepth_set_min_baseq", "bdepth_set_regions",
     "bdepth_set_shard", "bdepth_nccl_unique_id", "bdepth_set_tuning", "bdepth_stage", "bdepth_run_base",
-    "bdepth_run_windows", "bdepth_run_regions", "bdepth_get_stats", "bdepth_inflate_to_host", "bdepth_scan_to_host",
+    "bdepth_run_windows", "bdepth_run_regions", "bdepth_get_stats", "bdepth_ref_has_reads", "bdepth_inflate_to_host", "bdepth_scan_to_host",
 ]
 
 

@@ -75,6 +75,8 @@ struct bdepth {
     uint64_t cnt_base = 0, win_len = 0;
     void* pinned = nullptr; size_t pinned_cap = 0;
     std::vector<uint32_t> ref_has_host;
+    // ---- optional per-read segment counting (window / region front ends), device arrays
+    struct SegSet { bool on = false; uint32_t n = 0; DevBuf s, e, pmax, id, reads; } seg;
     // ---- results
     bdepth_stats st{}; std::string err;
 };
@@ -374,6 +376,12 @@ int run_pipeline(bdepth* h, RunMode mode, RunOut* ro) {
             }
             if (ro) ro->scan_n += R;
         }
+        // ---- per-read segment counting (countRead, depth.d:661-669) for the window / region front ends
+        if (mode == RUN_FULL && h->seg.on && h->seg.n && ss.n_pass) {
+            if (h->minq) k_read_segments<true><<<(unsigned)((R + 127) / 128), 128, 0, sm>>>(soa, u0, (uint32_t)R, h->seg.s.as<uint64_t>(), h->seg.e.as<uint64_t>(), h->seg.pmax.as<uint64_t>(), h->seg.id.as<uint32_t>(), nullptr, h->seg.n, h->seg.reads.as<uint32_t>(), h->minq);
+            else k_read_segments<false><<<(unsigned)((R + 127) / 128), 128, 0, sm>>>(soa, u0, (uint32_t)R, h->seg.s.as<uint64_t>(), h->seg.e.as<uint64_t>(), h->seg.pmax.as<uint64_t>(), h->seg.id.as<uint32_t>(), nullptr, h->seg.n, h->seg.reads.as<uint32_t>(), 0);
+            CK(cudaGetLastError()); st.gpu_launches++;
+        }
         // ---- K3
         if (mode == RUN_FULL && ss.n_pass) {
             uint64_t gmin = ss.min_start, gmax = ss.max_end;
@@ -476,6 +484,7 @@ void bdepth_close(bdepth_t* h) {
     cudaSetDevice(h->device);
     DevBuf* bufs[] = {&h->comp, &h->descs, &h->status, &h->ubuf, &h->chunk_start, &h->entry, &h->exitb, &h->count, &h->slot_base, &h->slots, &h->rec_base, &h->walk_list, &h->soa_start, &h->soa_span, &h->soa_meta, &h->soa_off, &h->soa_ncl, &h->soa_lseq, &h->long_list, &h->tile_first, &h->tile_lo, &h->counts, &h->ref_len_d, &h->ref_lin0_d, &h->scan_stats, &h->ref_has, &h->misc};
     for (DevBuf* b : bufs) b->release();
+    h->seg.s.release(); h->seg.e.release(); h->seg.pmax.release(); h->seg.id.release(); h->seg.reads.release();
     if (h->pinned) cudaFreeHost(h->pinned);
     if (h->s_main) { cudaStreamDestroy(h->s_main); cudaStreamDestroy(h->s_copy); for (auto& e : h->ev) cudaEventDestroy(e); }
     if (h->mapped) munmap((void*)h->file, h->file_len);
@@ -577,13 +586,121 @@ int bdepth_run_base(bdepth_t* h, bdepth_tile_cb cb, void* user) {
     return 0;
 }
 
-int bdepth_run_windows(bdepth_t* h, uint32_t window, uint32_t overlap, const uint32_t* thr, size_t n_thr, bdepth_stat_cb cb, void* user) {
-    (void)window; (void)overlap; (void)thr; (void)n_thr; (void)cb; (void)user;
-    return fail(h, BDEPTH_ERR_ARG, "window mode: not implemented yet");
+// Shared by window and region modes.  segs: output-order list of (ref, start, end) with end possibly
+// past the reference end (windows); stats are computed over the part inside the reference.
+struct SegDef { uint32_t ref, start, end; };
+static int run_segments(bdepth* h, const std::vector<SegDef>& segs, const uint32_t* thr, size_t n_thr,
+                        std::vector<uint32_t>& reads, std::vector<uint32_t>& bases, std::vector<uint32_t>& cov) {
+    if (n_thr > 16) return fail(h, BDEPTH_ERR_ARG, "at most 16 coverage thresholds are supported");
+    int rc = init_device(h); if (rc) return rc;
+    const size_t n = segs.size();
+    reads.assign(n, 0); bases.assign(n, 0); cov.assign(n * std::max<size_t>(n_thr, 1), 0);
+    // linear-coordinate segments, clipped to the reference
+    std::vector<uint64_t> a(n), b(n);
+    for (size_t i = 0; i < n; i++) {
+        uint64_t L = h->hdr.ref_len[segs[i].ref], l0 = h->hdr.ref_lin0[segs[i].ref];
+        a[i] = l0 + std::min<uint64_t>(segs[i].start, L); b[i] = l0 + std::min<uint64_t>(segs[i].end, L);
+        if (b[i] < a[i]) b[i] = a[i];
+    }
+    // sorted view for the per-read kernel
+    std::vector<uint32_t> order(n); for (size_t i = 0; i < n; i++) order[i] = (uint32_t)i;
+    std::sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return a[x] != a[y] ? a[x] < a[y] : x < y; });
+    std::vector<uint64_t> ss(n), se(n), pm(n); uint64_t mx = 0;
+    for (size_t i = 0; i < n; i++) { ss[i] = a[order[i]]; se[i] = b[order[i]]; mx = std::max(mx, se[i]); pm[i] = mx; }
+    auto& S = h->seg;
+    size_t nn = n ? n : 1;
+    CK(S.s.ensure(nn * 8)); CK(S.e.ensure(nn * 8)); CK(S.pmax.ensure(nn * 8)); CK(S.id.ensure(nn * 4)); CK(S.reads.ensure(nn * 4));
+    if (n) {
+        CK(cudaMemcpy(S.s.p, ss.data(), n * 8, cudaMemcpyHostToDevice)); CK(cudaMemcpy(S.e.p, se.data(), n * 8, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(S.pmax.p, pm.data(), n * 8, cudaMemcpyHostToDevice)); CK(cudaMemcpy(S.id.p, order.data(), n * 4, cudaMemcpyHostToDevice));
+    }
+    CK(cudaMemset(S.reads.p, 0, nn * 4));
+    S.on = true; S.n = (uint32_t)n;
+    rc = run_pipeline(h, RUN_FULL, nullptr);
+    S.on = false;
+    if (rc) return rc;
+    cudaStream_t sm = h->s_main;
+    cudaEvent_t e0 = h->ev[5], e1 = h->ev[6];
+    CK(cudaEventRecord(e0, sm));
+    // per-segment sums over the counters (original order)
+    DevBuf da, db, dthr, dbases, dcov;
+    auto cleanup = [&]() { da.release(); db.release(); dthr.release(); dbases.release(); dcov.release(); };
+    cudaError_t ce;
+    if ((ce = da.ensure(nn * 8)) || (ce = db.ensure(nn * 8)) || (ce = dthr.ensure(64)) || (ce = dbases.ensure(nn * 4)) || (ce = dcov.ensure(nn * 4 * std::max<size_t>(n_thr, 1)))) { cleanup(); return fail(h, BDEPTH_ERR_CUDA, "out of device memory (%s)", cudaGetErrorString(ce)); }
+    for (size_t i = 0; i < n; i++) { a[i] -= h->cnt_base; b[i] -= h->cnt_base; }
+    if (n) { cudaMemcpyAsync(da.p, a.data(), n * 8, cudaMemcpyHostToDevice, sm); cudaMemcpyAsync(db.p, b.data(), n * 8, cudaMemcpyHostToDevice, sm); }
+    if (n_thr) cudaMemcpyAsync(dthr.p, thr, n_thr * 4, cudaMemcpyHostToDevice, sm);
+    cudaMemsetAsync(dbases.p, 0, nn * 4, sm); cudaMemsetAsync(dcov.p, 0, nn * 4 * std::max<size_t>(n_thr, 1), sm);
+    if (n) {
+        k_segment_stats<<<(unsigned)((n * 32 + 255) / 256), 256, 0, sm>>>(h->counts.as<uint32_t>(), h->win_len, da.as<uint64_t>(), db.as<uint64_t>(), (uint32_t)n, dthr.as<uint32_t>(), (uint32_t)n_thr, dbases.as<uint32_t>(), dcov.as<uint32_t>());
+        h->st.gpu_launches++;
+        cudaMemcpyAsync(bases.data(), dbases.p, n * 4, cudaMemcpyDeviceToHost, sm);
+        if (n_thr) cudaMemcpyAsync(cov.data(), dcov.p, n * n_thr * 4, cudaMemcpyDeviceToHost, sm);
+        cudaMemcpyAsync(reads.data(), S.reads.p, n * 4, cudaMemcpyDeviceToHost, sm);
+    }
+    cudaEventRecord(e1, sm);
+    ce = cudaStreamSynchronize(sm);
+    if (ce == cudaSuccess) ce = cudaGetLastError();
+    cleanup();
+    if (ce != cudaSuccess) return fail(h, BDEPTH_ERR_CUDA, "CUDA error in segment statistics: %s", cudaGetErrorString(ce));
+    float t = 0; cudaEventElapsedTime(&t, e0, e1); h->st.ms_reduce = t;
+    h->st.ms_total_device = h->st.ms_h2d + h->st.ms_inflate + h->st.ms_scan + h->st.ms_coverage + h->st.ms_reduce;
+    return 0;
 }
+
+static int deliver_segments(bdepth* h, const std::vector<SegDef>& segs, const std::vector<uint8_t>& emit, size_t n_thr,
+                            const std::vector<uint32_t>& reads, const std::vector<uint32_t>& bases, const std::vector<uint32_t>& cov, bdepth_stat_cb cb, void* user) {
+    if (!cb) return 0;
+    std::vector<uint32_t> c(std::max<size_t>(n_thr, 1));
+    uint64_t idx = 0;
+    for (size_t i = 0; i < segs.size(); i++) {
+        if (!emit.empty() && !emit[i]) continue;
+        for (size_t t = 0; t < n_thr; t++) c[t] = cov[t * segs.size() + i];
+        bdepth_region_stat s{(int32_t)segs[i].ref, segs[i].start, segs[i].end, reads[i], bases[i], c.data()};
+        if (cb(user, &s, idx++)) return fail(h, BDEPTH_ERR_CALLBACK, "stat callback aborted");
+    }
+    return 0;
+}
+
+int bdepth_run_windows(bdepth_t* h, uint32_t window, uint32_t overlap, const uint32_t* thr, size_t n_thr, bdepth_stat_cb cb, void* user) {
+    if (window == 0) return fail(h, BDEPTH_ERR_ARG, "positive window size must be specified");
+    if (overlap >= window) return fail(h, BDEPTH_ERR_ARG, "specified overlap is larger than window size");
+    const uint32_t step = window - overlap;
+    if (window % step) return fail(h, BDEPTH_ERR_ARG, "window mode on the GPU needs (window - overlap) to divide window (see DESIGN.md: the reference's slot collector is only position-consistent in that case)");
+    // every window slot the reference could print: full windows when the reference has reads
+    // (depth.d:1057,1071), ref_length / step windows when it has none (printEmptyWindows, depth.d:1039-1044)
+    std::vector<SegDef> segs; std::vector<uint32_t> n_full(h->hdr.ref_len.size()), n_empty(h->hdr.ref_len.size()); std::vector<size_t> first(h->hdr.ref_len.size());
+    for (size_t r = 0; r < h->hdr.ref_len.size(); r++) {
+        uint64_t L = h->hdr.ref_len[r];
+        n_full[r] = L >= window ? (uint32_t)((L - window) / step + 1) : 0; n_empty[r] = (uint32_t)(L / step);
+        uint32_t m = std::max(n_full[r], n_empty[r]); first[r] = segs.size();
+        for (uint32_t k = 0; k < m; k++) segs.push_back(SegDef{(uint32_t)r, k * step, k * step + window});
+    }
+    std::vector<uint32_t> reads, bases, cov;
+    int rc = run_segments(h, segs, thr, n_thr, reads, bases, cov); if (rc) return rc;
+    std::vector<uint8_t> emit(segs.size(), 0);
+    for (size_t r = 0; r < h->hdr.ref_len.size(); r++) {
+        bool has = (h->ref_has_host[r >> 5] >> (r & 31)) & 1;
+        uint32_t m = has ? n_full[r] : n_empty[r];
+        for (uint32_t k = 0; k < m; k++) emit[first[r] + k] = 1;
+    }
+    return deliver_segments(h, segs, emit, n_thr, reads, bases, cov, cb, user);
+}
+
 int bdepth_run_regions(bdepth_t* h, const bdepth_region* regions, size_t n, const uint32_t* thr, size_t n_thr, bdepth_stat_cb cb, void* user) {
-    (void)regions; (void)n; (void)thr; (void)n_thr; (void)cb; (void)user;
-    return fail(h, BDEPTH_ERR_ARG, "region mode: not implemented yet");
+    std::vector<SegDef> segs(n);
+    for (size_t i = 0; i < n; i++) {
+        if (regions[i].ref_id >= h->hdr.ref_len.size()) return fail(h, BDEPTH_ERR_ARG, "region %zu: reference id out of range", i);
+        segs[i] = SegDef{regions[i].ref_id, regions[i].start, regions[i].end};
+    }
+    std::vector<uint32_t> reads, bases, cov;
+    int rc = run_segments(h, segs, thr, n_thr, reads, bases, cov); if (rc) return rc;
+    return deliver_segments(h, segs, {}, n_thr, reads, bases, cov, cb, user);
+}
+
+int bdepth_ref_has_reads(const bdepth_t* h, int ref) {
+    if (ref < 0 || (size_t)ref >= h->hdr.ref_len.size() || h->ref_has_host.empty()) return 0;
+    return (h->ref_has_host[ref >> 5] >> (ref & 31)) & 1;
 }
 
 int bdepth_get_stats(const bdepth_t* h, bdepth_stats* out) { if (!h || !out) return BDEPTH_ERR_ARG; *out = h->st; return 0; }

@@ -39,19 +39,18 @@ struct BlockDesc {
     uint32_t isize;
 };
 
-__global__ void __launch_bounds__(32) k1_inflate(const uint32_t* __restrict__ comp, const BlockDesc* __restrict__ blocks,
+__global__ void __launch_bounds__(32, 7) k1_inflate(const uint32_t* __restrict__ comp, const BlockDesc* __restrict__ blocks,
                                                  uint32_t n_blocks, uint8_t* __restrict__ u, int* __restrict__ status) {
     extern __shared__ uint32_t smem[];
     uint32_t lane = threadIdx.x;
     uint32_t b = blockIdx.x * 32u + lane;
     uint8_t lens[320];
-    if (b < n_blocks) {
-        BlockDesc d = blocks[b];
-        SmemTab tab{smem + lane};
-        ByteOut out{u + d.uoff};
-        int rc = inflate_block(tab, comp, d.coff, d.csize, out, d.isize, lens);
-        status[b] = rc;
-    }
+    const bool active = b < n_blocks;
+    BlockDesc d = active ? blocks[b] : BlockDesc{0, 0, 0, 0};
+    SmemTab tab{smem + lane};
+    ByteOut out{u};
+    int rc = inflate_block(tab, comp, d.coff, d.csize, out, d.uoff, d.isize, lens, active);
+    if (active) status[b] = rc;
 }
 
 // ------------------------------------------------------------------------------------- K2
@@ -408,16 +407,29 @@ __global__ void k_segment_stats(const uint32_t* __restrict__ counts, uint64_t wi
     uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= n_seg) return;
     uint64_t a = seg_a[warp], b = seg_b[warp];
-    uint32_t bases = 0; uint32_t cge[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    uint32_t bases = 0; uint32_t cge[16];
+#pragma unroll
+    for (int t = 0; t < 16; t++) cge[t] = 0;
     for (uint64_t i = a + lane; i < b; i += 32) {
         uint32_t s5 = 0, s = 0;
 #pragma unroll
         for (int pl = 0; pl < N_PLANES; pl++) { uint32_t v = counts[(uint64_t)pl * win_len + i]; s += v; if (pl < 5) s5 += v; }
         bases += s5;
-        if (s) { for (uint32_t t = 0; t < n_thr && t < 8; t++) cge[t] += s >= thr[t]; }
+        if (s) {
+#pragma unroll
+            for (int t = 0; t < 16; t++) if ((uint32_t)t < n_thr) cge[t] += s >= thr[t];
+        }
     }
-    for (int sft = 16; sft; sft >>= 1) { bases += __shfl_xor_sync(0xFFFFFFFFu, bases, sft); for (int t = 0; t < 8; t++) cge[t] += __shfl_xor_sync(0xFFFFFFFFu, cge[t], sft); }
-    if (lane == 0) { if (bases) atomicAdd(&out_bases[warp], bases); for (uint32_t t = 0; t < n_thr && t < 8; t++) if (cge[t]) atomicAdd(&out_cov[(uint64_t)t * n_seg + warp], cge[t]); }
+    for (int sft = 16; sft; sft >>= 1) {
+        bases += __shfl_xor_sync(0xFFFFFFFFu, bases, sft);
+#pragma unroll
+        for (int t = 0; t < 16; t++) cge[t] += __shfl_xor_sync(0xFFFFFFFFu, cge[t], sft);
+    }
+    if (lane == 0) {
+        if (bases) atomicAdd(&out_bases[warp], bases);
+#pragma unroll
+        for (int t = 0; t < 16; t++) if ((uint32_t)t < n_thr && cge[t]) atomicAdd(&out_cov[(uint64_t)t * n_seg + warp], cge[t]);
+    }
 }
 
 // Per-read "countRead" (depth.d:661-669) against sorted segments: a read adds 1 to n_reads of every

@@ -30,18 +30,18 @@ extern "C" long emul_inflate_file(const char* path, uint8_t* dst, uint64_t cap, 
         if (isize == 0) break;
         if (uoff + isize > cap) return -2;
         memset(tab, 0xAB, sizeof tab);
-        FlatTab ft{tab}; ByteOut out{dst + uoff};
-        int rc = inflate_block(ft, words.data(), off + 12 + xlen, cdata, out, isize, lens);
+        FlatTab ft{tab}; ByteOut out{dst};
+        int rc = inflate_block(ft, words.data(), off + 12 + xlen, cdata, out, uoff, isize, lens);
         if (rc) { *first_err = rc; return -(100 + rc); }
         uoff += isize; off += total;
     }
     return (long)uoff;
 }
 // decode a single raw deflate stream (for crafted-stream tests); byte_off exercises misaligned starts
-extern "C" int emul_inflate_raw(const uint8_t* src, uint32_t n, uint8_t* dst, uint32_t isize, uint32_t byte_off) {
+extern "C" int emul_inflate_raw(const uint8_t* src, uint32_t n, uint8_t* dst, uint32_t isize, uint32_t byte_off, uint32_t out_off) {
     std::vector<uint32_t> words((n + byte_off + 64 + 3) / 4 + 16, 0);
     memcpy((uint8_t*)words.data() + byte_off, src, n);
     uint32_t tab[T_WORDS]; uint8_t lens[320]; memset(tab, 0xCD, sizeof tab);
     FlatTab ft{tab}; ByteOut out{dst};
-    return inflate_block(ft, words.data(), byte_off, n, out, isize, lens);
+    return inflate_block(ft, words.data(), byte_off, n, out, out_off, isize, lens);
 }
