@@ -1071,10 +1071,10 @@ error:
  * counts layout: [7][total_len] planes A,C,G,T,N,DEL,REFSKIP over the
  * concatenation of all references (ref_off[i] = sum of lengths before i).
  */
-typedef struct { uint64_t n_records, n_pass, n_blocks, ulen, clen, covered; double t_inflate, t_scan; } ScatterStats;
+typedef struct { uint64_t n_records, n_pass, n_blocks, ulen, clen, covered, min_lin, max_lin; double t_inflate, t_scan; } ScatterStats;
 
 int oracle_base_counts(const char *bam_path, int mapq_gt, unsigned flag_reject, int min_bq, int nthreads, size_t max_file_bytes,
-                       uint32_t *counts /* may be NULL to just size */, uint64_t counts_len_positions, ScatterStats *st) {
+                       uint32_t *counts /* [7][win_len], may be NULL to just scan */, uint64_t win_a /* first linear position of the window */, uint64_t win_len, ScatterStats *st) {
     Bam B; memset(&B, 0, sizeof B);
     double t0 = now_s();
     if (bgzf_load(&B.z, bam_path, nthreads, max_file_bytes)) return -1;
@@ -1082,9 +1082,8 @@ int oracle_base_counts(const char *bam_path, int mapq_gt, unsigned flag_reject, 
     if (bam_parse_header(&B, max_file_bytes != 0)) return -1;
     uint64_t total = 0; uint64_t *ref_off = calloc(B.n_ref + 1, sizeof *ref_off);
     for (int i = 0; i < B.n_ref; i++) { ref_off[i] = total; total += B.refs[i].length; } ref_off[B.n_ref] = total;
-    if (counts && counts_len_positions < total) { free(ref_off); return fail("counts buffer too small (%llu < %llu)", (unsigned long long)counts_len_positions, (unsigned long long)total); }
     uint64_t nrec = 0, npass = 0; size_t off = B.first_rec; const uint8_t *u = B.z.u;
-    uint64_t L = counts_len_positions;
+    uint64_t L = win_len, min_lin = UINT64_MAX, max_lin = 0;
     while (off + 4 <= B.z.ulen) {
         uint32_t bs = rd32(u + off); if (off + 4 + (size_t)bs > B.z.ulen) break;
         const uint8_t *rec = u + off + 4; off += 4 + (size_t)bs; nrec++;
@@ -1095,6 +1094,7 @@ int oracle_base_counts(const char *bam_path, int mapq_gt, unsigned flag_reject, 
         uint64_t span = 0; for (uint32_t i = 0; i < n_cigar; i++) { uint32_t c = rd32(cig + 4 * i); if (op_rcons(c)) span += op_len(c); }
         if (!span) continue;
         npass++;
+        { uint64_t g0 = ref_off[ref_id] + (uint32_t)pos, g1 = g0 + span; if (g0 < min_lin) min_lin = g0; if (g1 > max_lin) max_lin = g1; }
         if (!counts) continue;
         uint64_t base = ref_off[ref_id], rlen = B.refs[ref_id].length; uint64_t p = (uint64_t)(uint32_t)pos; uint32_t q = 0;
         for (uint32_t i = 0; i < n_cigar; i++) {
@@ -1103,18 +1103,20 @@ int oracle_base_counts(const char *bam_path, int mapq_gt, unsigned flag_reject, 
                 for (uint32_t k = 0; k < len; k++, p++, q++) {
                     if (p >= rlen || q >= (uint32_t)l_seq) continue;       /* clip at reference end (documented deviation for invalid input) */
                     if (qual[q] < min_bq) continue;
+                    uint64_t g = base + p; if (g < win_a || g - win_a >= L) continue;
                     uint8_t b = seq[q >> 1]; b = (q & 1) ? (b & 0xF) : (b >> 4);
-                    counts[(uint64_t)NT16_TO_NT5[b] * L + base + p]++;
+                    counts[(uint64_t)NT16_TO_NT5[b] * L + (g - win_a)]++;
                 }
             } else if (op_rcons(c)) {
                 int plane = (op == 2) ? 5 : 6;
-                for (uint32_t k = 0; k < len; k++, p++) if (p < rlen) counts[(uint64_t)plane * L + base + p]++;
+                for (uint32_t k = 0; k < len; k++, p++) if (p < rlen) { uint64_t g = base + p; if (g >= win_a && g - win_a < L) counts[(uint64_t)plane * L + (g - win_a)]++; }
             } else if (op_qcons(c)) q += len;
         }
     }
     if (st) {
         st->n_records = nrec; st->n_pass = npass; st->n_blocks = B.z.n_blocks; st->ulen = B.z.ulen; st->clen = B.z.file_len; st->t_inflate = t1 - t0; st->t_scan = now_s() - t1; st->covered = 0;
-        if (counts) { uint64_t cv = 0; for (uint64_t i = 0; i < total; i++) { uint32_t s = 0; for (int k = 0; k < 7; k++) s += counts[(uint64_t)k * L + i]; cv += s > 0; } st->covered = cv; }
+        st->min_lin = min_lin; st->max_lin = max_lin;
+        if (counts) { uint64_t cv = 0; for (uint64_t i = 0; i < L; i++) { uint32_t s = 0; for (int k = 0; k < 7; k++) s += counts[(uint64_t)k * L + i]; cv += s > 0; } st->covered = cv; }
     }
     free(ref_off); bgzf_free(&B.z);
     return 0;

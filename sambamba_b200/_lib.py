@@ -184,22 +184,40 @@ class BDepth:
         return s.as_dict()
 
     # runs
-    def run_base(self, collect=True):
-        """Returns counts[7, total_len] over the concatenated references when collect=True."""
+    def lin_to_regions(self, a, b):
+        """Split the linear window [a, b) at reference boundaries -> [(ref_id, start, end)]."""
+        refs = self.refs
+        out, lin = [], 0
+        for i, (_, L) in enumerate(refs):
+            lo, hi = max(a, lin), min(b, lin + L)
+            if lo < hi:
+                out.append((i, lo - lin, hi - lin))
+            lin += L
+        return out
+
+    def run_base(self, collect=True, window=None):
+        """Returns counts[7, n] over the linear window (default: the concatenated references)."""
         refs = self.refs
         lin0 = np.concatenate([[0], np.cumsum([l for _, l in refs])]).astype(np.int64)
-        out = np.zeros((7, int(lin0[-1])), np.uint32) if collect else None
+        wa, wb = (0, int(lin0[-1])) if window is None else window
+        if window is not None:
+            self.set_regions(self.lin_to_regions(wa, wb))
+        out = np.zeros((7, max(0, wb - wa)), np.uint32) if collect else None
 
         def cb(_user, tp):
             t = tp.contents
-            a = int(lin0[t.ref_id]) + t.start
+            a = int(lin0[t.ref_id]) + t.start - wa
             src = np.ctypeslib.as_array(t.counts, shape=(6 * t.stride + t.len,))
             for p in range(7):
                 out[p, a:a + t.len] = src[p * t.stride:p * t.stride + t.len]
             return 0
 
         cbf = TILE_CB(cb) if collect else C.cast(None, TILE_CB)
-        self._ck(self.L.bdepth_run_base(self.h, cbf, None))
+        try:
+            self._ck(self.L.bdepth_run_base(self.h, cbf, None))
+        finally:
+            if window is not None:
+                self.set_regions([])
         return out
 
     def _run_stats(self, fn):

@@ -105,7 +105,7 @@ int init_device(bdepth* h) {
     if (h->device < 0 || h->device >= n) return fail(h, BDEPTH_ERR_ARG, "device %d out of range (%d devices)", h->device, n);
     CK(cudaSetDevice(h->device));
     if (!h->s_main) { CK(cudaStreamCreateWithFlags(&h->s_main, cudaStreamNonBlocking)); CK(cudaStreamCreateWithFlags(&h->s_copy, cudaStreamNonBlocking)); for (auto& e2 : h->ev) CK(cudaEventCreate(&e2)); }
-    CK(cudaFuncSetAttribute(k1_inflate, cudaFuncAttributeMaxDynamicSharedMemorySize, T_WORDS * 32 * 4));
+    CK(cudaFuncSetAttribute(k1_inflate, cudaFuncAttributeMaxDynamicSharedMemorySize, K1_SMEM));
     return 0;
 }
 
@@ -120,7 +120,7 @@ int inflate_blocks_to_host(bdepth* h, size_t b0, size_t b1, std::vector<uint8_t>
     CK(cudaMemcpyAsync(h->comp.p, h->file + f0, f1 - f0, cudaMemcpyHostToDevice, h->s_main));
     CK(cudaMemsetAsync((uint8_t*)h->comp.p + (f1 - f0), 0, 128, h->s_main));
     CK(cudaMemcpyAsync(h->descs.p, d.data(), nb * sizeof(BlockDesc), cudaMemcpyHostToDevice, h->s_main));
-    k1_inflate<<<(unsigned)((nb + 31) / 32), 32, T_WORDS * 32 * 4, h->s_main>>>(h->comp.as<uint32_t>(), h->descs.as<BlockDesc>(), (uint32_t)nb, h->ubuf.as<uint8_t>() + CARRY_MAX, h->status.as<int>());
+    k1_inflate<<<(unsigned)((nb + 32 * K1_WARPS - 1) / (32 * K1_WARPS)), 32 * K1_WARPS, K1_SMEM, h->s_main>>>(h->comp.as<uint32_t>(), h->descs.as<BlockDesc>(), (uint32_t)nb, h->ubuf.as<uint8_t>() + CARRY_MAX, h->status.as<int>());
     CK(cudaGetLastError());
     std::vector<int> stt(nb); out.resize(ulen);
     CK(cudaMemcpyAsync(stt.data(), h->status.p, nb * sizeof(int), cudaMemcpyDeviceToHost, h->s_main));
@@ -206,10 +206,23 @@ int run_pipeline(bdepth* h, RunMode mode, RunOut* ro) {
     const size_t nref = h->hdr.ref_len.size();
     cudaStream_t sm = h->s_main;
 
-    // ---- counter window: the whole linear genome (SURVEY 7 "Memory": 28 B/position; 87 GB for GRCh38 fits 180 GB HBM)
+    // ---- counter window (28 B/position).  With a BAI the linear index bounds where reads can lie, so only that
+    // span of the linear genome is allocated; without one the whole genome is (87 GB for GRCh38, fits 180 GB HBM).
     if (mode == RUN_FULL) {
-        h->cnt_base = 0;
-        h->win_len = ((h->hdr.total_len + TILE_POS - 1) / TILE_POS + 1) * TILE_POS;
+        uint64_t lo = 0, hi = h->hdr.total_len;
+        if (h->bai.valid && h->bai.ioffsets.size() == nref && h->world == 1) {
+            lo = UINT64_MAX; hi = 0;
+            for (size_t r = 0; r < nref; r++) {
+                const auto& v = h->bai.ioffsets[r]; if (v.empty()) continue;
+                size_t k = 0; while (k < v.size() && v[k] == 0) k++;
+                if (k == v.size()) continue;
+                lo = std::min<uint64_t>(lo, h->hdr.ref_lin0[r] + std::min<uint64_t>((uint64_t)k << 14, h->hdr.ref_len[r]));
+                hi = std::max<uint64_t>(hi, h->hdr.ref_lin0[r] + std::min<uint64_t>((uint64_t)v.size() << 14, h->hdr.ref_len[r]));
+            }
+            if (lo > hi) { lo = 0; hi = 0; }
+        }
+        h->cnt_base = lo / TILE_POS * TILE_POS;
+        h->win_len = ((hi - h->cnt_base + TILE_POS - 1) / TILE_POS + 1) * TILE_POS;
         size_t need = (size_t)h->win_len * N_PLANES * 4;
         size_t free_b = 0, tot_b = 0; CK(cudaMemGetInfo(&free_b, &tot_b));
         if (need > h->counts.cap && need > free_b + h->counts.cap) return fail(h, BDEPTH_ERR_CUDA, "counter window needs %zu bytes of HBM, %zu free", need, free_b);
@@ -254,7 +267,7 @@ int run_pipeline(bdepth* h, RunMode mode, RunOut* ro) {
         uint8_t* u0 = h->ubuf.as<uint8_t>() + CARRY_MAX;     // offset 0 of this batch's inflated bytes
         CK(cudaEventRecord(e1, sm));
         // ---- K1
-        k1_inflate<<<(unsigned)((nb + 31) / 32), 32, T_WORDS * 32 * 4, sm>>>(d_comp, h->descs.as<BlockDesc>(), (uint32_t)nb, u0, h->status.as<int>());
+        k1_inflate<<<(unsigned)((nb + 32 * K1_WARPS - 1) / (32 * K1_WARPS)), 32 * K1_WARPS, K1_SMEM, sm>>>(d_comp, h->descs.as<BlockDesc>(), (uint32_t)nb, u0, h->status.as<int>());
         CK(cudaGetLastError()); st.gpu_launches++;
         CK(cudaEventRecord(e2, sm));
         std::vector<int> stt(nb);
@@ -385,6 +398,7 @@ int run_pipeline(bdepth* h, RunMode mode, RunOut* ro) {
         // ---- K3
         if (mode == RUN_FULL && ss.n_pass) {
             uint64_t gmin = ss.min_start, gmax = ss.max_end;
+            if (gmin < h->cnt_base || gmax > h->cnt_base + h->win_len) return fail(h, BDEPTH_ERR_FORMAT, "reads lie outside the span covered by the BAI linear index (stale index?)");
             uint64_t t_lo = (gmin - h->cnt_base) / TILE_POS, t_hi = (gmax - h->cnt_base + TILE_POS - 1) / TILE_POS;
             uint64_t n_tiles = t_hi - t_lo; uint64_t tiles_base = h->cnt_base + t_lo * TILE_POS;
             if (t_hi * TILE_POS > h->win_len) return fail(h, BDEPTH_ERR_FORMAT, "read extends past the end of the reference space");
@@ -542,7 +556,7 @@ int bdepth_run_base(bdepth_t* h, bdepth_tile_cb cb, void* user) {
     rc = ensure_pinned(h, 2 * EMIT_CHUNK * N_PLANES * 4); if (rc) return rc;
     // covered positions (rows of default `depth base`)
     CK(cudaMemsetAsync(h->misc.p, 0, 8, sm));
-    k_count_covered<<<2048, 256, 0, sm>>>(h->counts.as<uint32_t>(), h->win_len, 0, h->hdr.total_len, (unsigned long long*)h->misc.p);
+    k_count_covered<<<2048, 256, 0, sm>>>(h->counts.as<uint32_t>(), h->win_len, 0, h->win_len, (unsigned long long*)h->misc.p);
     CK(cudaGetLastError()); h->st.gpu_launches++;
     unsigned long long cov = 0; CK(cudaMemcpyAsync(&cov, h->misc.p, 8, cudaMemcpyDeviceToHost, sm));
     CK(cudaEventRecord(e0, sm));
@@ -555,8 +569,14 @@ int bdepth_run_base(bdepth_t* h, bdepth_tile_cb cb, void* user) {
     std::vector<Range> chunks;
     for (auto& r : ranges) for (uint64_t a = r.a; a < r.b; a += EMIT_CHUNK) chunks.push_back({a, std::min<uint64_t>(r.b, a + EMIT_CHUNK)});
     auto issue = [&](size_t ci) -> int {
-        uint32_t* dst = (uint32_t*)h->pinned + (ci & 1) * EMIT_CHUNK * N_PLANES; uint64_t n = chunks[ci].b - chunks[ci].a;
-        for (int pl = 0; pl < N_PLANES; pl++) CK(cudaMemcpyAsync(dst + (size_t)pl * EMIT_CHUNK, h->counts.as<uint32_t>() + (uint64_t)pl * h->win_len + (chunks[ci].a - h->cnt_base), n * 4, cudaMemcpyDeviceToHost, sm));
+        uint32_t* dst = (uint32_t*)h->pinned + (ci & 1) * EMIT_CHUNK * N_PLANES; uint64_t a = chunks[ci].a, b = chunks[ci].b;
+        // positions outside the counter window hold no reads: zeros
+        uint64_t wa = std::max(a, h->cnt_base), wb = std::min(b, h->cnt_base + h->win_len);
+        if (wa >= wb) { for (int pl = 0; pl < N_PLANES; pl++) memset(dst + (size_t)pl * EMIT_CHUNK, 0, (b - a) * 4); }
+        else {
+            if (wa > a || wb < b) for (int pl = 0; pl < N_PLANES; pl++) memset(dst + (size_t)pl * EMIT_CHUNK, 0, (b - a) * 4);
+            for (int pl = 0; pl < N_PLANES; pl++) CK(cudaMemcpyAsync(dst + (size_t)pl * EMIT_CHUNK + (wa - a), h->counts.as<uint32_t>() + (uint64_t)pl * h->win_len + (wa - h->cnt_base), (wb - wa) * 4, cudaMemcpyDeviceToHost, sm));
+        }
         CK(cudaEventRecord(h->ev[8 + (ci & 1)], sm));
         return 0;
     };
@@ -627,7 +647,10 @@ static int run_segments(bdepth* h, const std::vector<SegDef>& segs, const uint32
     auto cleanup = [&]() { da.release(); db.release(); dthr.release(); dbases.release(); dcov.release(); };
     cudaError_t ce;
     if ((ce = da.ensure(nn * 8)) || (ce = db.ensure(nn * 8)) || (ce = dthr.ensure(64)) || (ce = dbases.ensure(nn * 4)) || (ce = dcov.ensure(nn * 4 * std::max<size_t>(n_thr, 1)))) { cleanup(); return fail(h, BDEPTH_ERR_CUDA, "out of device memory (%s)", cudaGetErrorString(ce)); }
-    for (size_t i = 0; i < n; i++) { a[i] -= h->cnt_base; b[i] -= h->cnt_base; }
+    for (size_t i = 0; i < n; i++) {
+        uint64_t wa = std::min(std::max(a[i], h->cnt_base), h->cnt_base + h->win_len), wb = std::min(std::max(b[i], h->cnt_base), h->cnt_base + h->win_len);
+        a[i] = wa - h->cnt_base; b[i] = wb - h->cnt_base;
+    }
     if (n) { cudaMemcpyAsync(da.p, a.data(), n * 8, cudaMemcpyHostToDevice, sm); cudaMemcpyAsync(db.p, b.data(), n * 8, cudaMemcpyHostToDevice, sm); }
     if (n_thr) cudaMemcpyAsync(dthr.p, thr, n_thr * 4, cudaMemcpyHostToDevice, sm);
     cudaMemsetAsync(dbases.p, 0, nn * 4, sm); cudaMemsetAsync(dcov.p, 0, nn * 4 * std::max<size_t>(n_thr, 1), sm);

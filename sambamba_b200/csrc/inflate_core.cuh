@@ -6,24 +6,26 @@
 // arithmetic being restated is zlib's (third-party, not under /root/reference); RFC 1951 output
 // is deterministic so any correct inflater is bit-identical.
 //
-// Design (see DESIGN.md "K1").  A warp-per-block decoder issues ~150 instructions per symbol
+// Design (see DESIGN.md "K1").  A warp-per-block decoder issues ~200 instructions per symbol
 // with one useful lane; giving every lane its own block makes those instructions decode 32
 // symbols.  Consequences:
-//  * Tables must be tiny (they bound occupancy), so there is NO lookup table: decoding is
-//    canonical-Huffman arithmetic.  Measured on BAM data a first-level LUT misses on 5-10 % of
-//    symbols, i.e. in ~97 % of 32-lane iterations, so its fast path would almost never save the
-//    warp anything while costing 4x the shared memory.
+//  * Per-lane state bounds occupancy, and the kernel is instruction-latency bound, so tables are
+//    tiny and there is NO lookup table: decoding is canonical-Huffman arithmetic.  Measured on BAM
+//    data a first-level LUT misses on 5-10 % of symbols, i.e. in ~97 % of 32-lane iterations, so
+//    its fast path would almost never save the warp anything while costing 4x the shared memory.
 //      len = 1 + #{ j in 1..14 : peek15 >= lim[j] }      lim[] (left-justified) in REGISTERS
 //      sym = sorted[ (peek15 >> (15-len)) + delta[len] ]  two shared-memory loads
 //  * The SIMT loop is a flat state machine: each iteration a lane either decodes ONE symbol or
-//    moves ONE 8-byte round of a pending LZ77 copy, so no lane waits for another lane's match.
-//  * Output goes through a 256-byte per-lane ring in shared memory: literals are byte stores to
-//    shared memory, completed 16-byte lines leave as one aligned 16-byte global store, and
-//    matches with distance <= 240 are served from the ring.  Far matches read global memory; the
-//    loaded bytes are stored one iteration later, after the next symbol has been decoded, so the
-//    L2 round trip overlaps the Huffman arithmetic.
-//  per lane: 288 x u16 litlen symbols (144 w) + 15 x i16 delta (8 w) + 32 x u8 dist symbols (8 w)
-//            + delta (8 w) + ring (64 w) = 232 words = 928 B; 29 KB per warp; 7 warps per SM.
+//    moves ONE 4-byte round of a pending LZ77 copy, so no lane waits for another lane's match,
+//    and every iteration ends in a ballot that re-converges the warp.
+//  * Output is assembled a 32-bit word at a time in a register; complete words go to a 16-word
+//    per-lane ring in shared memory, complete 16-byte lines leave as one aligned 16-byte global
+//    store.  Matches at distance 8..56 are served from the ring, farther ones from global memory
+//    (two aligned word loads + funnel shift); the loaded word is appended one iteration later,
+//    after the next symbol has been decoded, so the L2 round trip overlaps the Huffman arithmetic.
+//    Distances below 8 (run-length style) take a byte-serial path.
+//  per lane: 288 x 10-bit litlen symbols (96 w) + 15 x i16 delta (8 w) + 32 x u8 dist symbols
+//            (8 w) + delta (8 w) + ring (16 w) = 136 words = 544 B; 17 KB per warp; 12 warps/SM.
 //
 // The code is __host__ __device__ so the exact same logic is unit-tested on the CPU against zlib
 // (tests/test_emul_inflate.py); the product only ever calls it from kernels.
@@ -32,8 +34,10 @@
 
 #if defined(__CUDACC__)
 #define BD_HD __host__ __device__ __forceinline__
+#define BD_HD_COLD __host__ __device__ __noinline__      // rare paths: keep them out of the hot loop's code and registers
 #else
 #define BD_HD inline
+#define BD_HD_COLD inline
 #endif
 
 namespace bdk {
@@ -59,14 +63,14 @@ enum InflateStatus : int {
 };
 
 // word offsets of the per-lane table regions
-constexpr int T_LL_SYMS = 0;       // 288 x u16
-constexpr int T_LL_DELTA = 144;    // 15 x i16 (index len-1), padded to 16
-constexpr int T_D_SYMS = 152;      // 32 x u8
-constexpr int T_D_DELTA = 160;     // 15 x i16
-constexpr int T_RING = 168;        // 256-byte output ring
-constexpr int RING_WORDS = 64;
-constexpr int T_WORDS = T_RING + RING_WORDS;   // 232
-constexpr uint32_t NEAR_MAX = 240;             // matches at most this far back are served from the ring
+constexpr int T_LL_SYMS = 0;       // 288 x 10 bit, three per word
+constexpr int T_LL_DELTA = 96;     // 15 x i16 (index len-1), padded to 16
+constexpr int T_D_SYMS = 104;      // 32 x u8
+constexpr int T_D_DELTA = 112;     // 15 x i16
+constexpr int T_RING = 120;        // output ring: the last 16 complete words
+constexpr int RING_WORDS = 16;
+constexpr int T_WORDS = T_RING + RING_WORDS;   // 136
+constexpr uint32_t NEAR_MAX = 4 * (RING_WORDS - 1) - 4;   // 56: farthest distance served from the ring
 
 // ---- table storage policies -------------------------------------------------------------
 // Lane-interleaved shared memory: word w of this lane lives at base[w * 32]; every lane always
@@ -75,22 +79,16 @@ struct SmemTab {
     uint32_t* base;
     BD_HD uint32_t ldw(int w) const { return base[w * 32]; }
     BD_HD void stw(int w, uint32_t v) const { base[w * 32] = v; }
-    BD_HD void ring_st8(uint32_t a, uint32_t v) const {
-        reinterpret_cast<uint8_t*>(base + T_RING * 32)[(((a >> 2) & (RING_WORDS - 1)) << 7) | (a & 3)] = (uint8_t)v;
-    }
-    BD_HD uint32_t ring_ld8(uint32_t a) const {
-        return reinterpret_cast<const uint8_t*>(base + T_RING * 32)[(((a >> 2) & (RING_WORDS - 1)) << 7) | (a & 3)];
-    }
     BD_HD uint32_t ring_ldw(uint32_t widx) const { return base[(T_RING + (widx & (RING_WORDS - 1))) * 32]; }
+    BD_HD void ring_stw(uint32_t widx, uint32_t v) const { base[(T_RING + (widx & (RING_WORDS - 1))) * 32] = v; }
 };
 // Plain array (host tests).
 struct FlatTab {
     uint32_t* base;
     BD_HD uint32_t ldw(int w) const { return base[w]; }
     BD_HD void stw(int w, uint32_t v) const { base[w] = v; }
-    BD_HD void ring_st8(uint32_t a, uint32_t v) const { reinterpret_cast<uint8_t*>(base + T_RING)[a & (RING_WORDS * 4 - 1)] = (uint8_t)v; }
-    BD_HD uint32_t ring_ld8(uint32_t a) const { return reinterpret_cast<const uint8_t*>(base + T_RING)[a & (RING_WORDS * 4 - 1)]; }
     BD_HD uint32_t ring_ldw(uint32_t widx) const { return base[T_RING + (widx & (RING_WORDS - 1))]; }
+    BD_HD void ring_stw(uint32_t widx, uint32_t v) const { base[T_RING + (widx & (RING_WORDS - 1))] = v; }
 };
 
 template <class Tab> BD_HD uint32_t tab_ld16(const Tab& t, int region, int i) {
@@ -110,6 +108,25 @@ template <class Tab> BD_HD void tab_st8(const Tab& t, int region, int i, uint32_
     int wi = region + (i >> 2), sh = (i & 3) * 8;
     uint32_t w = t.ldw(wi);
     t.stw(wi, (w & ~(0xFFu << sh)) | ((v & 0xFFu) << sh));
+}
+
+// 10-bit entries, three per word
+template <class Tab> BD_HD uint32_t tab_ld10(const Tab& t, int region, int i) {
+    uint32_t q = ((uint32_t)i * 0xAAABu) >> 17;          // i / 3 for i < 2^15
+    return (t.ldw(region + (int)q) >> (((uint32_t)i - 3 * q) * 10)) & 0x3FFu;
+}
+template <class Tab> BD_HD void tab_st10(const Tab& t, int region, int i, uint32_t v) {
+    uint32_t q = ((uint32_t)i * 0xAAABu) >> 17, sh = ((uint32_t)i - 3 * q) * 10;
+    uint32_t w = t.ldw(region + (int)q);
+    t.stw(region + (int)q, (w & ~(0x3FFu << sh)) | ((v & 0x3FFu) << sh));
+}
+
+BD_HD uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t shift_bits) {   // low 32 bits of (hi:lo) >> shift, shift in [0,32)
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_r(lo, hi, shift_bits);
+#else
+    return (uint32_t)((((uint64_t)hi << 32) | lo) >> shift_bits);
+#endif
 }
 
 BD_HD uint32_t bitrev32(uint32_t x) {
@@ -149,8 +166,33 @@ struct BitReader {
     BD_HD bool overrun() const { return wp > wend + 3; }
 };
 
-// Left-justified 15-bit limits, index len-1.  v[14] == 32768 for a complete code.
+// Left-justified 15-bit limits, index len-1 (v[14] == 32768 for a complete code), built in next_block.
 struct HuffLim { uint32_t v[15]; };
+// The same limits packed two per register for the hot loop: pk[p] = lim[2p] | lim[2p+1] << 16, with a
+// dummy 16th limit of 0x8000 (never reached: peek15 <= 0x7FFF).
+struct HuffPk { uint32_t pk[8]; };
+
+// number of j in 0..15 with rev15 >= limit j.  Guard-bit subtraction: (0x8000 | rev) - lim keeps bit 15
+// set iff rev >= lim (lim <= 0x8000), two limits per 32-bit subtract; the 16 guard bits are gathered with
+// sign-replicating byte permutes and counted with one POPC.  18 instructions, no dependent chain.
+BD_HD int count_ge16(uint32_t rev15, const HuffPk& h) {
+#if defined(__CUDA_ARCH__)
+    uint32_t x = rev15 * 0x00010001u + 0x80008000u;
+    uint32_t t0 = x - h.pk[0], t1 = x - h.pk[1], t2 = x - h.pk[2], t3 = x - h.pk[3];
+    uint32_t t4 = x - h.pk[4], t5 = x - h.pk[5], t6 = x - h.pk[6], t7 = x - h.pk[7];
+    uint32_t a, b, c, d;
+    asm("prmt.b32 %0, %1, %2, 0xFDB9;" : "=r"(a) : "r"(t0), "r"(t1));   // sign-fill of bytes 1,3 of each word
+    asm("prmt.b32 %0, %1, %2, 0xFDB9;" : "=r"(b) : "r"(t2), "r"(t3));
+    asm("prmt.b32 %0, %1, %2, 0xFDB9;" : "=r"(c) : "r"(t4), "r"(t5));
+    asm("prmt.b32 %0, %1, %2, 0xFDB9;" : "=r"(d) : "r"(t6), "r"(t7));
+    uint32_t m = (a & 0x01010101u) | (b & 0x02020202u) | (c & 0x04040404u) | (d & 0x08080808u);
+    return __popc(m);
+#else
+    int n = 0;
+    for (int p = 0; p < 8; p++) { n += rev15 >= (h.pk[p] & 0xFFFFu); n += rev15 >= (h.pk[p] >> 16); }
+    return n;
+#endif
+}
 
 // Build one canonical table from code lengths lens[0..n).  KIND 0 = litlen (u16 symbols),
 // 1 = dist (u8 symbols).  Mirrors zlib inflate_table()'s validity rules: over-subscribed ->
@@ -185,7 +227,7 @@ BD_HD int build_table(const Tab& t, const uint8_t* lens, int n, HuffLim& lim) {
     for (int s = 0; s < n; s++) {
         uint32_t l = lens[s];
         if (!l) continue;
-        if (KIND == 0) tab_st16(t, T_LL_SYMS, (int)nxt[l], (uint32_t)s); else tab_st8(t, T_D_SYMS, (int)nxt[l], (uint32_t)s);
+        if (KIND == 0) tab_st10(t, T_LL_SYMS, (int)nxt[l], (uint32_t)s); else tab_st8(t, T_D_SYMS, (int)nxt[l], (uint32_t)s);
         nxt[l]++;
     }
     return INF_OK;
@@ -193,23 +235,16 @@ BD_HD int build_table(const Tab& t, const uint8_t* lens, int n, HuffLim& lim) {
 
 // Decode one symbol of a canonical code.  Returns -1 on an invalid code; consumes its bits.
 template <class Tab, int KIND>
-BD_HD int decode_sym(const Tab& t, const HuffLim& lim, BitReader& br) {
+BD_HD int decode_sym(const Tab& t, const HuffPk& lim, BitReader& br) {
     uint32_t rev15 = bitrev32((uint32_t)br.bb) >> 17;
-    // 14 independent compares summed as a tree (a serial += chain would cost 14 dependent adds)
-#define BD_GE(j) ((rev15 >= lim.v[j]) ? 1 : 0)
-    int s0 = (BD_GE(0) + BD_GE(1)) + (BD_GE(2) + BD_GE(3));
-    int s1 = (BD_GE(4) + BD_GE(5)) + (BD_GE(6) + BD_GE(7));
-    int s2 = (BD_GE(8) + BD_GE(9)) + (BD_GE(10) + BD_GE(11));
-    int s3 = (BD_GE(12) + BD_GE(13)) + 1;
-#undef BD_GE
-    int L = (s0 + s1) + (s2 + s3);
-    if (rev15 >= lim.v[14]) return -1;
+    int L = 1 + count_ge16(rev15, lim);          // code length; 16 means "beyond the last code"
+    if (L > 15) return -1;
     int delta = (int)(int16_t)tab_ld16(t, KIND == 0 ? T_LL_DELTA : T_D_DELTA, L - 1);
     int idx = (int)(rev15 >> (15 - L)) + delta;
     if (idx < 0 || idx >= (KIND == 0 ? 288 : 32)) return -1;
     BD_STAT(KIND == 0 ? g_inflate_stats.len_hist[L]++ : 0);
     br.drop(L);
-    return KIND == 0 ? (int)tab_ld16(t, T_LL_SYMS, idx) : (int)tab_ld8(t, T_D_SYMS, idx);
+    return KIND == 0 ? (int)tab_ld10(t, T_LL_SYMS, idx) : (int)tab_ld8(t, T_D_SYMS, idx);
 }
 
 // Read the dynamic-block header and produce lens[] (RFC 1951 3.2.7).  lens must hold 320 bytes.
@@ -271,6 +306,7 @@ struct ByteOut {
     uint8_t* p;
     BD_HD void put(uint64_t i, uint32_t v) const { p[i] = (uint8_t)v; }
     BD_HD uint32_t get(uint64_t i) const { return p[i]; }
+    BD_HD uint32_t getw(uint64_t widx) const { return reinterpret_cast<const uint32_t*>(p)[widx]; }   // aligned word
     BD_HD void put16(uint64_t i, uint32_t a, uint32_t b, uint32_t c, uint32_t d) const {
 #if defined(__CUDA_ARCH__)
         *reinterpret_cast<uint4*>(p + i) = make_uint4(a, b, c, d);
@@ -294,36 +330,69 @@ enum { ST_HDR = 0, ST_SYM = 1, ST_STORED = 2, ST_DONE = 3 };
 #define BD_BALLOT(mask, pred) ((pred) ? 1u : 0u)
 #endif
 
-// A 16-byte line [line, line+16) of the output has just been completed: send it to memory.
-// Lines that begin before this block's first byte a0 are shared with the previous block, so only
-// this block's bytes are written, one by one.
+// Output assembly state: `cur` holds the bytes of the word being filled (absolute alignment).
+struct OutState { uint32_t cur; uint32_t opos; };
+
+// First line of a block that does not start on a 16-byte boundary: the line is shared with the
+// previous block, so only this block's bytes are written, one by one.
 template <class Tab, class Out>
-BD_HD void flush_line(const Tab& t, const Out& out, uint64_t line, uint64_t a0) {
-    if (line >= a0) {
-        uint32_t w = (uint32_t)(line >> 2);
-        out.put16(line, t.ring_ldw(w), t.ring_ldw(w + 1), t.ring_ldw(w + 2), t.ring_ldw(w + 3));
-    } else {
-        for (uint64_t a = a0; a < line + 16; a++) out.put(a, t.ring_ld8((uint32_t)a));
+BD_HD_COLD void flush_partial_line(Tab t, Out out, uint32_t widx, uint32_t last_word, uint64_t a0) {
+    uint64_t line = ((uint64_t)(widx - 3)) << 2;
+    for (uint64_t a = a0; a < line + 16; a++) {
+        uint32_t w = (uint32_t)(a >> 2) == widx ? last_word : t.ring_ldw((uint32_t)(a >> 2));
+        out.put(a, (w >> ((a & 3) * 8)) & 0xFFu);
     }
 }
 
-// Parse block headers until a block with content (or the end) is reached.  Returns an error code.
+// Append n (1..4) bytes held in the low bytes of d (upper bytes zero).  a0 < 2^34 so word indices fit 32 bits.
+// A completed word goes to the ring; a completed 16-byte line leaves as one aligned 16-byte store.
+template <class Tab, class Out>
+BD_HD void append_bytes(const Tab& t, const Out& out, OutState& os, uint64_t a0, uint32_t d, uint32_t n) {
+    uint64_t A = a0 + os.opos; uint32_t k = (uint32_t)A & 3;
+    uint64_t tt = (uint64_t)d << (8 * k);
+    uint32_t lo = os.cur | (uint32_t)tt;
+    if (k + n >= 4) {
+        uint32_t widx = (uint32_t)(A >> 2);
+        t.ring_stw(widx, lo);
+        if ((widx & 3) == 3) {
+            uint64_t line = ((uint64_t)(widx - 3)) << 2;
+            if (line >= a0) out.put16(line, t.ring_ldw(widx - 3), t.ring_ldw(widx - 2), t.ring_ldw(widx - 1), lo);
+            else flush_partial_line(t, out, widx, lo, a0);
+        }
+        os.cur = (uint32_t)(tt >> 32);
+    } else os.cur = lo;
+    os.opos += n;
+}
+
+// byte at absolute address A < a0 + opos (in the word being filled or in the ring)
 template <class Tab>
-BD_HD int next_block(const Tab& t, BitReader& br, HuffLim& ll, HuffLim& dd, uint8_t* lens, uint32_t pos, uint32_t isize,
-                     int& state, uint32_t& bfinal, uint32_t& stored_rem) {
-    while (state == ST_HDR) {
+BD_HD uint32_t recent_byte(const Tab& t, const OutState& os, uint64_t a0, uint64_t A) {
+    uint32_t w = (uint32_t)(A >> 2) == (uint32_t)((a0 + os.opos) >> 2) ? os.cur : t.ring_ldw((uint32_t)(A >> 2));
+    return (w >> (((uint32_t)A & 3) * 8)) & 0xFFu;
+}
+
+// Parse block headers until a block with content (or the end) is reached and build its tables.
+// Cold and out of line; the 30 Huffman limits are handed back through lim16 (the lens scratch), because a
+// by-reference HuffLim would force the hot loop's limit registers into local memory.
+struct HdrResult { BitReader br; int rc; int state; uint32_t bfinal, stored_rem; };
+// Everything is passed and returned BY VALUE: a by-reference BitReader would pin the hot loop's bit reservoir to
+// local memory (its address would escape into this out-of-line call).
+template <class Tab>
+BD_HD_COLD HdrResult next_block(Tab t, BitReader br, uint8_t* lens, uint32_t* limpk /* 16 words */, uint32_t pos, uint32_t isize) {
+    HdrResult r; r.rc = INF_OK; r.state = ST_HDR; r.bfinal = 0; r.stored_rem = 0;
+    while (r.state == ST_HDR) {
         br.refill();
-        bfinal = br.get(1); uint32_t btype = br.get(2);
+        r.bfinal = br.get(1); uint32_t btype = br.get(2);
         if (btype == 0) {
             br.drop(br.bc & 7);
             br.refill();
             uint32_t len = br.get(16); br.refill(); uint32_t nlen = br.get(16);
-            if ((len ^ 0xFFFFu) != nlen) return INF_ERR_STORED;
-            if (pos + len > isize) return INF_ERR_OVERRUN;
-            stored_rem = len;
-            state = len ? ST_STORED : (bfinal ? ST_DONE : ST_HDR);
+            if ((len ^ 0xFFFFu) != nlen) { r.rc = INF_ERR_STORED; break; }
+            if (pos + len > isize) { r.rc = INF_ERR_OVERRUN; break; }
+            r.stored_rem = len;
+            r.state = len ? ST_STORED : (r.bfinal ? ST_DONE : ST_HDR);
         } else if (btype == 3) {
-            return INF_ERR_BTYPE;
+            r.rc = INF_ERR_BTYPE; break;
         } else {
             int nl, nd;
             if (btype == 1) {
@@ -337,43 +406,61 @@ BD_HD int next_block(const Tab& t, BitReader& br, HuffLim& ll, HuffLim& dd, uint
                 for (int i = 0; i < 32; i++) lens[288 + i] = 5;
             } else {
                 int rc = read_dynamic_lens(br, lens, nl, nd);
-                if (rc) return rc;
+                if (rc) { r.rc = rc; break; }
             }
             BD_STAT(g_inflate_stats.tables++);
+            HuffLim ll, dd;
             int rc = build_table<Tab, 0>(t, lens, nl, ll);
-            if (rc) return rc;
-            rc = build_table<Tab, 1>(t, lens + nl, nd, dd);
-            if (rc) return rc;
-            state = ST_SYM;
+            if (!rc) rc = build_table<Tab, 1>(t, lens + nl, nd, dd);
+            if (rc) { r.rc = rc; break; }
+            for (int p2 = 0; p2 < 8; p2++) {
+                limpk[p2] = ll.v[2 * p2] | ((p2 < 7 ? ll.v[2 * p2 + 1] : 0x8000u) << 16);
+                limpk[8 + p2] = dd.v[2 * p2] | ((p2 < 7 ? dd.v[2 * p2 + 1] : 0x8000u) << 16);
+            }
+            r.state = ST_SYM;
         }
-        if (br.overrun()) return INF_ERR_INPUT;
+        if (br.overrun()) { r.rc = INF_ERR_INPUT; break; }
     }
-    return INF_OK;
+    r.br = br;
+    return r;
 }
 
 // Inflate one raw-deflate stream.  words/byte_off/nbytes locate the compressed data inside a
 // 4-byte-aligned buffer that has >= 64 readable bytes after the last block.  The block's isize
 // output bytes go to absolute stream offsets [a0, a0+isize) of `out`.  On the device ALL 32 lanes
 // of the warp must call this together; lanes without a block pass active = false.
+// scratch: 320 bytes for code lengths + 64 bytes for the limit hand-over, 4-byte aligned.
 template <class Tab, class Out>
-BD_HD int inflate_block(const Tab& t, const uint32_t* words, uint64_t byte_off, uint32_t nbytes, const Out& out, uint64_t a0, uint32_t isize, uint8_t* lens /* 320 B scratch */, bool active = true) {
+BD_HD int inflate_block(const Tab& t, const uint32_t* words, uint64_t byte_off, uint32_t nbytes, const Out& out, uint64_t a0, uint32_t isize, uint32_t* scratch /* 384 B */, bool active = true) {
     unsigned mask = BD_BALLOT(0xFFFFFFFFu, active);
     if (!active) return INF_OK;
+    uint8_t* lens = reinterpret_cast<uint8_t*>(scratch);
+    uint32_t* limpk = scratch + 80;
     BitReader br; br.init(words, byte_off, nbytes);
-    HuffLim ll, dd;
+    HuffPk ll, dd;
 #pragma unroll
-    for (int i = 0; i < 15; i++) { ll.v[i] = 0; dd.v[i] = 0; }
-    uint32_t pos = 0;                 // bytes produced so far (including match bytes still in flight)
+    for (int i = 0; i < 8; i++) { ll.pk[i] = 0; dd.pk[i] = 0; }
+    uint32_t pos = 0;                 // bytes decoded so far (some may still be in flight)
+    OutState os{0u, 0u};              // bytes actually appended
     int state = ST_HDR, rc = INF_OK; uint32_t bfinal = 0, stored_rem = 0;
-    // current match: bytes not yet loaded
-    uint32_t m_rem = 0, m_dist = 0, m_wrap = 0xFFFFFFFFu, m_dst = 0; bool m_near = false;
-    // loaded-but-not-yet-stored bytes of the previous round
-    uint32_t pend_lo = 0, pend_hi = 0, pend_n = 0, pend_pos = 0;
+    uint32_t m_rem = 0, m_dist = 0, m_dst = 0;      // current match: bytes not yet fetched
+    // In-flight bytes: every byte (literal or copied) is appended ONE ITERATION LATER, at the single append site
+    // below.  For far matches p_w0/p_w1 are the raw loaded words; they are first touched after the next symbol
+    // has been decoded, so the L2 round trip overlaps the Huffman arithmetic.
+    uint32_t p_w0 = 0, p_w1 = 0, p_sh = 0, p_n = 0;
     for (;;) {
         BD_STAT(g_inflate_stats.iters++);
         int sym = -1; bool have_sym = false;
         if (m_rem == 0) {
-            if (state == ST_HDR) { rc = next_block(t, br, ll, dd, lens, pos, isize, state, bfinal, stored_rem); if (rc) state = ST_DONE; }
+            if (state == ST_HDR) {
+                HdrResult hr = next_block(t, br, lens, limpk, pos, isize);
+                br = hr.br; rc = hr.rc; state = hr.state; bfinal = hr.bfinal; stored_rem = hr.stored_rem;
+                if (rc) state = ST_DONE;
+                else if (state == ST_SYM) {
+#pragma unroll
+                    for (int i = 0; i < 8; i++) { ll.pk[i] = limpk[i]; dd.pk[i] = limpk[8 + i]; }
+                }
+            }
             if (state == ST_SYM) {
                 br.refill(); sym = decode_sym<Tab, 0>(t, ll, br); have_sym = true;
                 if (sym < 0) { rc = INF_ERR_CODE; state = ST_DONE; have_sym = false; }
@@ -382,26 +469,18 @@ BD_HD int inflate_block(const Tab& t, const uint32_t* words, uint64_t byte_off, 
                 if (--stored_rem == 0) state = bfinal ? ST_DONE : ST_HDR;
             }
         }
-        // ---- A: store the bytes loaded in the previous round (their loads have had a whole decode to land)
-        if (pend_n) {
-            uint64_t a = a0 + pend_pos;
-#pragma unroll
-            for (int k = 0; k < 8; k++) if ((uint32_t)k < pend_n) t.ring_st8((uint32_t)(a + k), ((k < 4 ? pend_lo : pend_hi) >> ((k & 3) * 8)) & 0xFFu);
-            uint64_t e = a + pend_n;
-            if ((e >> 4) != (a >> 4)) flush_line(t, out, ((e >> 4) - 1) << 4, a0);
-            pend_n = 0;
+        // ---- A: the single append site
+        if (p_n) {
+            uint32_t d = funnel_r(p_w0, p_w1, p_sh);
+            if (p_n < 4) d &= (1u << (8 * p_n)) - 1u;
+            append_bytes(t, out, os, a0, d, p_n);
+            p_n = 0;
         }
         // ---- act on the decoded symbol
         if (have_sym) {
             if (sym < 256) {
                 if (pos >= isize) { rc = INF_ERR_OVERRUN; state = ST_DONE; }
-                else {
-                    BD_STAT(g_inflate_stats.lits++);
-                    uint64_t a = a0 + pos;
-                    t.ring_st8((uint32_t)a, (uint32_t)sym);
-                    if (((a + 1) & 15) == 0) flush_line(t, out, (a + 1) - 16, a0);
-                    pos++;
-                }
+                else { BD_STAT(g_inflate_stats.lits++); p_w0 = (uint32_t)sym; p_w1 = 0; p_sh = 0; p_n = 1; pos++; }
             } else if (sym == 256) {
                 state = bfinal ? ST_DONE : ST_HDR;
             } else {
@@ -427,39 +506,47 @@ BD_HD int inflate_block(const Tab& t, const uint32_t* words, uint64_t byte_off, 
                 else {
                     BD_STAT(g_inflate_stats.matches++); BD_STAT(g_inflate_stats.match_bytes += len); BD_STAT(g_inflate_stats.mlen_hist[len >= 64 ? 15 : len / 4]++);
                     BD_STAT(g_inflate_stats.near_matches += dist <= NEAR_MAX);
-                    m_dist = dist; m_wrap = dist < 8 ? dist : 0xFFFFFFFFu; m_near = dist <= NEAR_MAX;
-                    m_dst = pos; m_rem = len; pos += len;
+                    m_dist = dist; m_dst = pos; m_rem = len; pos += len;
                 }
             }
         }
-        // ---- B: load one round (<= 8 bytes) of the current match; they are stored next iteration
+        // ---- B: fetch one round (<= 4 bytes) of the current match.  Everything up to m_dst has been appended.
         if (m_rem) {
-            uint32_t n = m_rem < 8 ? m_rem : 8;
-            // byte k of this round equals byte (k mod dist) of the dist bytes that precede the round, all of which
-            // are already stored (the pattern is periodic with period dist); for dist >= 8 there is no wrap
-            uint64_t sbase = a0 + m_dst - m_dist; uint32_t m_o = 0;
-            pend_lo = 0; pend_hi = 0;
-#pragma unroll
-            for (int k = 0; k < 8; k++) {
-                if ((uint32_t)k < n) {
-                    uint32_t b = m_near ? t.ring_ld8((uint32_t)(sbase + m_o)) : out.get(sbase + m_o);
-                    if (k < 4) pend_lo |= b << (k * 8); else pend_hi |= b << ((k - 4) * 8);
-                    m_o++; if (m_o == m_wrap) m_o = 0;
-                }
+            uint32_t n = m_rem < 4 ? m_rem : 4;
+            uint64_t head = a0 + m_dst;
+            if (m_dist >= 8) {
+                // the 4 source bytes lie entirely in complete words: two aligned words + funnel shift (done at A)
+                uint64_t S = head - m_dist; uint32_t sw = (uint32_t)(S >> 2);
+                if (m_dist <= NEAR_MAX) { p_w0 = t.ring_ldw(sw); p_w1 = t.ring_ldw(sw + 1); }
+                else { p_w0 = out.getw(sw); p_w1 = out.getw((uint64_t)sw + 1); }
+                p_sh = ((uint32_t)S & 3) * 8;
+            } else {
+                // run-length style.  H = the 8 bytes before head (hi = most recent 4), from the word being filled
+                // and the two ring words before it.  The 4 output bytes are bytes (8-dist).. of H, with the
+                // dist-periodic continuation when dist < 4.
+                uint32_t hw = (uint32_t)(head >> 2), k8 = ((uint32_t)head & 3) * 8;
+                uint32_t w1 = t.ring_ldw(hw - 1), w2 = t.ring_ldw(hw - 2);
+                uint32_t hi = funnel_r(w1, os.cur, k8), lo = funnel_r(w2, w1, k8);
+                uint32_t w;
+                if (m_dist >= 4) w = m_dist == 4 ? hi : funnel_r(lo, hi, 8 * (8 - m_dist));
+                else if (m_dist == 1) w = (hi >> 24) * 0x01010101u;
+                else if (m_dist == 2) w = (hi >> 16) * 0x00010001u;
+                else w = (hi >> 8) | ((hi >> 8) << 24);
+                p_w0 = w; p_w1 = 0; p_sh = 0;
             }
-            pend_pos = m_dst; pend_n = n; m_dst += n; m_rem -= n;
+            p_n = n; m_dst += n; m_rem -= n;
         }
-        bool cont = !(state == ST_DONE && m_rem == 0 && pend_n == 0);
+        bool cont = !(state == ST_DONE && m_rem == 0 && p_n == 0);
         mask = BD_BALLOT(mask, cont);
         if (!cont) break;
     }
     if (rc) return rc;
     // flush the last, partial line (byte stores: the rest of the line belongs to the next block)
     {
-        uint64_t e = a0 + pos, ls = e & ~15ull; if (ls < a0) ls = a0;
-        for (uint64_t a = ls; a < e; a++) out.put(a, t.ring_ld8((uint32_t)a));
+        uint64_t e = a0 + os.opos, ls = e & ~15ull; if (ls < a0) ls = a0;
+        for (uint64_t a = ls; a < e; a++) out.put(a, recent_byte(t, os, a0, a));
     }
-    return pos == isize ? INF_OK : INF_ERR_SHORT;
+    return (pos == isize && os.opos == isize) ? INF_OK : INF_ERR_SHORT;
 }
 
 }  // namespace bdk

@@ -39,17 +39,19 @@ struct BlockDesc {
     uint32_t isize;
 };
 
-__global__ void __launch_bounds__(32, 7) k1_inflate(const uint32_t* __restrict__ comp, const BlockDesc* __restrict__ blocks,
-                                                 uint32_t n_blocks, uint8_t* __restrict__ u, int* __restrict__ status) {
+constexpr int K1_WARPS = 1;                                   // one warp per CTA; 12 CTAs per SM (17 KB + 1 KB each)
+constexpr int K1_SMEM = K1_WARPS * T_WORDS * 32 * 4;           // 17,408 B
+__global__ void __launch_bounds__(K1_WARPS * 32, 12) k1_inflate(const uint32_t* __restrict__ comp, const BlockDesc* __restrict__ blocks,
+                                                               uint32_t n_blocks, uint8_t* __restrict__ u, int* __restrict__ status) {
     extern __shared__ uint32_t smem[];
-    uint32_t lane = threadIdx.x;
-    uint32_t b = blockIdx.x * 32u + lane;
-    uint8_t lens[320];
+    uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t b = (blockIdx.x * K1_WARPS + warp) * 32u + lane;
+    uint32_t scratch[96];
     const bool active = b < n_blocks;
     BlockDesc d = active ? blocks[b] : BlockDesc{0, 0, 0, 0};
-    SmemTab tab{smem + lane};
+    SmemTab tab{smem + warp * (T_WORDS * 32) + lane};
     ByteOut out{u};
-    int rc = inflate_block(tab, comp, d.coff, d.csize, out, d.uoff, d.isize, lens, active);
+    int rc = inflate_block(tab, comp, d.coff, d.csize, out, d.uoff, d.isize, scratch, active);
     if (active) status[b] = rc;
 }
 

@@ -20,7 +20,7 @@ extern "C" long emul_inflate_file(const char* path, uint8_t* dst, uint64_t cap, 
     fclose(f);
     const uint8_t* file = (const uint8_t*)words.data();
     uint64_t off = 0, uoff = 0; *first_err = 0;
-    uint32_t tab[T_WORDS]; uint8_t lens[320];
+    uint32_t tab[T_WORDS]; uint32_t lens[96];
     while (off + 18 <= (uint64_t)n) {
         const uint8_t* p = file + off;
         uint32_t xlen = p[10] | (p[11] << 8), bsize = 0;
@@ -41,7 +41,7 @@ extern "C" long emul_inflate_file(const char* path, uint8_t* dst, uint64_t cap, 
 extern "C" int emul_inflate_raw(const uint8_t* src, uint32_t n, uint8_t* dst, uint32_t isize, uint32_t byte_off, uint32_t out_off) {
     std::vector<uint32_t> words((n + byte_off + 64 + 3) / 4 + 16, 0);
     memcpy((uint8_t*)words.data() + byte_off, src, n);
-    uint32_t tab[T_WORDS]; uint8_t lens[320]; memset(tab, 0xCD, sizeof tab);
+    uint32_t tab[T_WORDS]; uint32_t lens[96]; memset(tab, 0xCD, sizeof tab);
     FlatTab ft{tab}; ByteOut out{dst};
     return inflate_block(ft, words.data(), byte_off, n, out, out_off, isize, lens);
 }

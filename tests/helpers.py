@@ -16,7 +16,7 @@ _orc = None
 
 
 class ScatterStats(C.Structure):
-    _fields_ = [(n, C.c_uint64) for n in ("n_records", "n_pass", "n_blocks", "ulen", "clen", "covered")] + \
+    _fields_ = [(n, C.c_uint64) for n in ("n_records", "n_pass", "n_blocks", "ulen", "clen", "covered", "min_lin", "max_lin")] + \
                [("t_inflate", C.c_double), ("t_scan", C.c_double)]
 
 
@@ -26,7 +26,7 @@ def oracle():
         L = C.CDLL(ORACLE_LIB)
         L.oracle_inflate_file.restype = C.c_int64
         L.oracle_inflate_file.argtypes = [C.c_char_p, C.c_void_p, C.c_uint64]
-        L.oracle_base_counts.argtypes = [C.c_char_p, C.c_int, C.c_uint, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_uint64, C.POINTER(ScatterStats)]
+        L.oracle_base_counts.argtypes = [C.c_char_p, C.c_int, C.c_uint, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_uint64, C.c_uint64, C.POINTER(ScatterStats)]
         L.oracle_bam_info.argtypes = [C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         L.oracle_last_error.restype = C.c_char_p
         _orc = L
@@ -49,15 +49,34 @@ def oracle_info(path):
     return nref.value, tot.value, ulen.value, nblk.value
 
 
-def oracle_counts(path, mapq_gt=0, flag_reject=0x600, min_bq=0, threads=1):
-    """Closed-form per-read scatter oracle: counts[7, total_len]."""
+def oracle_scan(path, mapq_gt=0, flag_reject=0x600):
+    """Record counts and the linear-coordinate extent [min_lin, max_lin) of the passing reads."""
+    L = oracle()
+    st = ScatterStats()
+    rc = L.oracle_base_counts(path.encode(), mapq_gt, flag_reject, 0, 1, 0, None, 0, 0, C.byref(st))
+    assert rc == 0, L.oracle_last_error()
+    return st
+
+
+def oracle_counts(path, mapq_gt=0, flag_reject=0x600, min_bq=0, threads=1, window=None):
+    """Closed-form per-read scatter oracle: counts[7, n] over the linear window (default: whole genome)."""
     L = oracle()
     _, tot, _, _ = oracle_info(path)
-    out = np.zeros((7, max(1, tot)), np.uint32)
+    a, b = window if window is not None else (0, tot)
+    out = np.zeros((7, max(1, b - a)), np.uint32)
     st = ScatterStats()
-    rc = L.oracle_base_counts(path.encode(), mapq_gt, flag_reject, min_bq, threads, 0, out.ctypes.data_as(C.c_void_p), max(1, tot), C.byref(st))
+    rc = L.oracle_base_counts(path.encode(), mapq_gt, flag_reject, min_bq, threads, 0, out.ctypes.data_as(C.c_void_p), a, max(1, b - a), C.byref(st))
     assert rc == 0, L.oracle_last_error()
-    return out[:, :tot], st
+    return out[:, :b - a], st
+
+
+def interesting_window(path, pad=2000, **kw):
+    """Linear window around the passing reads (keeps tests on human-sized headers small)."""
+    st = oracle_scan(path, **kw)
+    _, tot, _, _ = oracle_info(path)
+    if st.n_pass == 0:
+        return (0, min(tot, 4096))
+    return (max(0, st.min_lin - pad), min(tot, st.max_lin + pad))
 
 
 def oracle_cli(args, stdin=None):
