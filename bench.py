@@ -1,0 +1,326 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the depth hot path (BASELINE.json metric: BAM GB/s for `depth base`).
+
+  python bench.py --gpus N --steps K --warmup W            # our arm (libbdepth.so through the C ABI)
+  python bench.py --impl reference --gpus N --steps K ...  # reference arm: the CPU implementation on host cores
+
+Workload (config.workload): BASELINE configs[1], the synthetic 30x chr20 BAM (64,444,167 bp, 12,888,833 x 150 bp
+reads, seed 20, zlib level 6, 0xFF00-byte BGZF blocks) generated on the box by tools/bamgen.c.  At N > 1 GPUs
+the input grows with N (N chromosomes of that size, weak scaling, the shape of BASELINE configs[3]) and is sharded
+by BGZF virtual offset at BAI linear-index record starts; boundary counters are exchanged over NCCL.
+
+A "step" is one complete `depth base` pass over the whole input:
+  value  : input already resident in HBM  -> K1 inflate -> K2 scan -> K3 coverage (+ NCCL boundary exchange),
+           timed with CUDA events on the library's stream (bdepth_stats.ms_span_device), max over ranks.
+  e2e    : bdepth_open_memory() on the BAM image in PINNED HOST memory + bdepth_run_base(): H2D of the compressed
+           bytes, all kernels, and D2H of the 7 x u32 per-position counters into pinned host memory, all inside
+           the timed region (host wall clock around the call, which ends in a stream synchronize).
+The file is 2.26 GB compressed / 3.76 GB inflated per chromosome unit, far larger than the 126 MB L2, so no L2
+flush is needed between steps (config.l2: "inputs >> L2").
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+READS_PER_UNIT = 12888833
+UNIT_LEN = 64444167
+NCU_TRAFFIC_BYTES_PER_LAUNCH = None      # filled from profiles/ once a --set full capture of this workload exists
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f)["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs, copy bandwidth)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def workload_path(n_units, reads_per_unit):
+    d = os.environ.get("BDEPTH_BENCH_DIR", "/tmp/bdepth_bench")
+    os.makedirs(d, exist_ok=True)
+    return os.path.join(d, f"synth_chr20x{n_units}_{reads_per_unit}.bam")
+
+
+def ensure_workload(n_units, reads_per_unit):
+    import __graft_entry__ as g
+    g.build(quiet=True)
+    path = workload_path(n_units, reads_per_unit)
+    if os.path.exists(path) and os.path.exists(path + ".bai"):
+        return path
+    tmp = path + f".tmp{os.getpid()}"
+    refs = []
+    for i in range(n_units):
+        refs += ["-r", (f"chr20:{UNIT_LEN}" if n_units == 1 else f"chr20_{i + 1}:{UNIT_LEN}")]
+    cmd = [os.path.join(ROOT, "tools", "_build", "bamgen"), "-o", tmp, "-n", str(reads_per_unit * n_units), "-s", "20",
+           "-t", str(min(64, os.cpu_count() or 8))] + refs
+    subprocess.check_call(cmd, stderr=subprocess.DEVNULL)
+    os.replace(tmp + ".bai", path + ".bai")
+    os.replace(tmp, path)
+    return path
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, gpu_index):
+        self.rows = []
+        self.proc = None
+        self.idx = gpu_index
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.idx), "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def pinned_file(path):
+    """Read a file into page-locked host memory (cudaHostAlloc through the runtime the library links)."""
+    rt = C.CDLL("libcudart.so.12")
+    n = os.path.getsize(path)
+    p = C.c_void_p()
+    rc = rt.cudaHostAlloc(C.byref(p), C.c_size_t(n), 0)
+    if rc:
+        raise RuntimeError(f"cudaHostAlloc failed: {rc}")
+    buf = (C.c_ubyte * n).from_address(p.value)
+    with open(path, "rb") as f:
+        got = f.readinto(buf)
+    assert got == n
+    import numpy as np
+    return np.ctypeslib.as_array(buf), (rt, p)
+
+
+def cpu_baseline(path, threads, sample_bytes):
+    """The reference's algorithm on the host cores (oracle port: zlib inflate on `threads` threads + the serial
+    column sweep and per-base printer), on a bounded prefix of the same BAM.  kind = "port": the reference is D
+    and cannot be compiled in this image."""
+    exe = os.path.join(ROOT, "oracle", "_build", "depth_oracle")
+    cmd = [exe, "--inflate-threads", str(threads), "--max-file-bytes", str(sample_bytes), "--stats", "depth", "base", path, "-o", "/dev/null"]
+    t0 = time.time()
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    dt = time.time() - t0
+    st = {}
+    for line in r.stderr.splitlines():
+        if line.startswith("{"):
+            st = json.loads(line)
+    nbytes = st.get("file_bytes", sample_bytes)
+    return {"value": nbytes / 1e9 / dt, "unit": "GB/s", "cores": threads, "kind": "port",
+            "sample": f"first {nbytes / 1e6:.0f} MB of the BAM ({st.get('columns', 0)} covered positions): inflate {st.get('t_inflate', 0):.2f} s on {threads} threads + serial pileup sweep/print {st.get('t_sweep', 0):.2f} s; wall {dt:.2f} s",
+            "covered_mbases_per_s": st.get("columns", 0) / 1e6 / dt}, dt, nbytes, st
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--reads-per-unit", type=int, default=READS_PER_UNIT, help="smaller values are for smoke tests only")
+    ap.add_argument("--cpu-sample-mb", type=int, default=256)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    a = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    n_units = max(1, a.gpus)
+    workload = (f"synthetic 30x chr20 BAM (BASELINE configs[1]): {n_units} x 64,444,167 bp, {a.reads_per_unit * n_units} x 150 bp reads, seed 20, "
+                "zlib-6 BGZF 0xFF00 blocks; `depth base`, default filter")
+    config = {"workload": workload, "mode": "depth base", "filter": "mapping_quality > 0 and not duplicate and not failed_quality_control",
+              "parallelism": f"bgzf-shard x{a.gpus}" if a.gpus > 1 else "single GPU", "l2": "inputs >> L2 (2.3 GB compressed, 3.8 GB inflated per unit)"}
+
+    # ------------------------------------------------------------------ reference arm (CPU)
+    if a.impl == "reference":
+        if rank != 0:
+            return 0
+        path = ensure_workload(n_units, a.reads_per_unit)
+        threads = os.cpu_count() or 1
+        times, nb = [], 0
+        for i in range(a.warmup + a.steps):
+            cb, dt, nb, st = cpu_baseline(path, threads, a.cpu_sample_mb << 20)
+            if i >= a.warmup:
+                times.append(dt)
+        dt = sum(times) / len(times)
+        v = nb / 1e9 / dt
+        cb["value"] = v
+        print(json.dumps({"impl": "reference", "metric": "bam_gb_per_s_depth_base", "value": v, "unit": "GB/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+                          "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+                          "config": config, "cpu_baseline": cb, "e2e": {"value": v, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                          "gpu_launches": 0}))
+        return 0
+
+    # ------------------------------------------------------------------ our arm
+    import numpy as np
+    import sambamba_b200 as sb
+    dist = None
+    uid = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        if rank == 0:
+            path = ensure_workload(n_units, a.reads_per_unit)
+        dist.barrier()
+        path = workload_path(n_units, a.reads_per_unit)
+        obj = [sb.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(obj, src=0)
+        uid = obj[0]
+    else:
+        path = ensure_workload(n_units, a.reads_per_unit)
+    file_bytes = os.path.getsize(path)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        import torch
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if dist is None:
+            return x
+        import torch
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    # ---- value: inputs resident in HBM
+    b = sb.BDepth(path, device=local_rank)
+    if world > 1:
+        b.set_shard(rank, world, uid)
+    b.stage()
+    for _ in range(a.warmup):
+        barrier()
+        b.run_resident()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    span, k1, k2, k3, ex, launches = [], [], [], [], [], 0
+    barrier()
+    for _ in range(a.steps):
+        barrier()
+        b.run_resident()
+        st = b.stats()
+        span.append(max_over_ranks(st["ms_span_device"]))
+        k1.append(st["ms_inflate"]); k2.append(st["ms_scan"]); k3.append(st["ms_coverage"]); ex.append(st["ms_exchange"])
+        launches += st["gpu_launches"]
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    st = b.stats()
+    ms_step = sum(span) / len(span)
+    covered = sum_over_ranks(st["covered_positions"])
+    total_launches = sum_over_ranks(launches)
+    k1_ms = sum(k1) / len(k1)
+    k1_bytes = st["cdata_bytes"] + st["inflated_bytes"]              # C + U of this rank's shard
+    k1_launches_per_step = st["n_batches"]
+    b.close()
+
+    # ---- e2e: host (pinned) buffers in, host (pinned) counters out, everything inside the timed region
+    img, keep = pinned_file(path)
+    bai = np.fromfile(path + ".bai", dtype=np.uint8)
+    e2e_t, d2h_bytes = [], 0
+    t0 = time.perf_counter()
+    h = sb.BDepth(memory=img, bai=bai, device=local_rank)          # session setup (BGZF index, header, buffers) is outside the steps
+    if world > 1:
+        h.set_shard(rank, world, uid)
+    open_s = time.perf_counter() - t0
+    cold_s = None
+    n_w = max(1, min(a.warmup, 3))
+    for i in range(n_w + a.steps):
+        barrier()
+        t0 = time.perf_counter()
+        h.run_base(collect=False)                                   # H2D of the compressed bytes + kernels + D2H of the counters
+        dt = time.perf_counter() - t0
+        s2 = h.stats()
+        d2h_bytes = (s2["own_hi"] - s2["own_lo"]) * 28
+        dt = max_over_ranks(dt)
+        if i == 0:
+            cold_s = dt + max_over_ranks(open_s)
+        if i >= n_w:
+            e2e_t.append(dt)
+    e2e_stats = h.stats()
+    h.close()
+    e2e_s = sum(e2e_t) / len(e2e_t)
+    h2d_total = file_bytes
+    d2h_total = sum_over_ranks(d2h_bytes)
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return 0
+    peak, peak_src = peaks()
+    value = file_bytes / 1e9 / (ms_step / 1e3)
+    out = {
+        "metric": "bam_gb_per_s_depth_base", "value": value, "unit": "GB/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+        "config": config,
+        "covered_mbases_per_s": covered / 1e6 / (ms_step / 1e3),
+        "stage_ms": {"k1_inflate": k1_ms, "k2_scan": sum(k2) / len(k2), "k3_coverage": sum(k3) / len(k3), "nccl_exchange": sum(ex) / len(ex)},
+        "e2e": {"value": file_bytes / 1e9 / e2e_s, "unit": "GB/s", "h2d_bytes_per_step": int(h2d_total), "d2h_bytes_per_step": int(d2h_total),
+                "ms_per_step": e2e_s * 1e3, "covered_mbases_per_s": covered / 1e6 / e2e_s, "first_call_incl_open_ms": cold_s * 1e3,
+                "device_ms": {k: e2e_stats[k] for k in ("ms_h2d", "ms_inflate", "ms_scan", "ms_coverage", "ms_d2h", "ms_span_device")},
+                "path": "bdepth_open_memory(pinned host BAM image) + bdepth_run_base -> 7 x u32 counters in pinned host memory"},
+        "gpu_launches": int(total_launches),
+        "roofline": {"kernel": "k1_inflate (lane-per-BGZF-block DEFLATE)", "bound": "hbm", "achieved": k1_bytes / 1e9 / (k1_ms / 1e3), "peak": peak, "unit": "GB/s",
+                     "frac": k1_bytes / 1e9 / (k1_ms / 1e3) / peak, "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH,
+                     "algorithmic_bytes_per_launch": int(k1_bytes / max(1, k1_launches_per_step)), "launches_per_step": k1_launches_per_step,
+                     "peak_source": peak_src, "note": "C + U per launch (SURVEY 8d) / CUDA-event duration of the launch on the library stream; DEFLATE decoding is instruction-latency bound, not HBM bound"},
+        "clocks": clocks,
+    }
+    if not a.no_cpu_baseline:
+        cb, _, _, _ = cpu_baseline(path, os.cpu_count() or 1, a.cpu_sample_mb << 20)
+        out["cpu_baseline"] = cb
+    print(json.dumps(out))
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -100,6 +100,10 @@ typedef struct {
     uint32_t n_batches;
     float ms_h2d, ms_inflate, ms_scan, ms_coverage, ms_reduce, ms_d2h, ms_total_device;
     double host_wall_ms;          /* wall clock of the whole call, host side                        */
+    float ms_span_device;         /* CUDA-event time from the first to the last device operation    */
+    float ms_exchange;            /* multi-GPU boundary exchange (NCCL)                             */
+    uint64_t own_lo, own_hi;      /* linear-coordinate range this rank owns after the exchange      */
+    uint64_t halo_bytes_sent;     /* boundary counters sent to the next ranks                       */
 } bdepth_stats;
 
 /* ------------------------------------------------------------------ lifecycle */
@@ -135,6 +139,10 @@ int bdepth_set_regions(bdepth_t* h, const bdepth_region* regions, size_t n);
  * world > 1 processes the shard without exchange (tiles then carry only this shard's reads). */
 int bdepth_set_shard(bdepth_t* h, int rank, int world, const void* nccl_unique_id);
 int bdepth_nccl_unique_id(void* out128);
+/* Host-only (no GPU needed): the world-1 interior shard boundaries as BGZF virtual offsets, i.e.
+ * the first linear-index record start at or after k * file_size / world (k = 1..world-1);
+ * UINT64_MAX when there is none.  Used by the sharding tests. */
+int bdepth_plan_shards(const char* bam_path, int world, uint64_t* out_voffsets);
 /* Tuning knobs (0 = default): uncompressed bytes per batch, positions in the counter window. */
 int bdepth_set_tuning(bdepth_t* h, uint64_t batch_inflated_bytes, uint64_t window_positions);
 
@@ -142,6 +150,8 @@ int bdepth_set_tuning(bdepth_t* h, uint64_t batch_inflated_bytes, uint64_t windo
 /* Stage the (shard of the) compressed file into HBM ahead of time; later runs then start with
  * inputs resident on the device (kernel-only timing).  Without it every run streams H2D itself. */
 int bdepth_stage(bdepth_t* h);
+/* Run the pipeline and leave the counters on the device (no tile delivery): kernel-only timing. */
+int bdepth_run_resident(bdepth_t* h);
 /* depth base: deliver every tile of the processed range in order.  cb may be NULL (benchmark). */
 int bdepth_run_base(bdepth_t* h, bdepth_tile_cb cb, void* user);
 /* depth window -w W --overlap O -T t...: stats for every window slot the reference would print

@@ -38,7 +38,8 @@ class Stats(C.Structure):
                                           "covered_positions", "long_reads", "chain_fixups")] + \
                [("gpu_launches", C.c_uint32), ("n_batches", C.c_uint32)] + \
                [(n, C.c_float) for n in ("ms_h2d", "ms_inflate", "ms_scan", "ms_coverage", "ms_reduce", "ms_d2h",
-                                         "ms_total_device")] + [("host_wall_ms", C.c_double)]
+                                         "ms_total_device")] + [("host_wall_ms", C.c_double), ("ms_span_device", C.c_float), ("ms_exchange", C.c_float),
+                                                                 ("own_lo", C.c_uint64), ("own_hi", C.c_uint64), ("halo_bytes_sent", C.c_uint64)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -86,6 +87,8 @@ def load_library():
     L.bdepth_nccl_unique_id.argtypes = [vp]
     L.bdepth_set_tuning.argtypes = [vp, C.c_uint64, C.c_uint64]
     L.bdepth_stage.argtypes = [vp]
+    L.bdepth_run_resident.argtypes = [vp]
+    L.bdepth_plan_shards.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_uint64)]
     L.bdepth_run_base.argtypes = [vp, TILE_CB, vp]
     L.bdepth_run_windows.argtypes = [vp, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32), C.c_size_t, STAT_CB, vp]
     L.bdepth_run_regions.argtypes = [vp, C.POINTER(Region), C.c_size_t, C.POINTER(C.c_uint32), C.c_size_t, STAT_CB, vp]
@@ -103,9 +106,27 @@ EXPORTED_SYMBOLS = [
     "bdepth_device_count", "bdepth_open", "bdepth_open_memory", "bdepth_close", "bdepth_last_error", "bdepth_n_ref",
     "bdepth_ref_name", "bdepth_ref_length", "bdepth_header_text", "bdepth_is_coordinate_sorted", "bdepth_has_index",
     "bdepth_n_samples", "bdepth_sample_name", "bdepth_set_filter", "bdepth_set_min_baseq", "bdepth_set_regions",
-    "bdepth_set_shard", "bdepth_nccl_unique_id", "bdepth_set_tuning", "bdepth_stage", "bdepth_run_base",
+    "bdepth_set_shard", "bdepth_nccl_unique_id", "bdepth_plan_shards", "bdepth_set_tuning", "bdepth_stage", "bdepth_run_resident", "bdepth_run_base",
     "bdepth_run_windows", "bdepth_run_regions", "bdepth_get_stats", "bdepth_ref_has_reads", "bdepth_inflate_to_host", "bdepth_scan_to_host",
 ]
+
+
+def nccl_unique_id():
+    L = load_library()
+    buf = (C.c_char * 128)()
+    rc = L.bdepth_nccl_unique_id(buf)
+    if rc:
+        raise BDepthError(rc, L.bdepth_last_error(None).decode())
+    return bytes(buf)
+
+
+def plan_shards(path, world):
+    L = load_library()
+    out = (C.c_uint64 * max(1, world - 1))()
+    rc = L.bdepth_plan_shards(os.fsencode(path), world, out)
+    if rc:
+        raise BDepthError(rc, L.bdepth_last_error(None).decode())
+    return list(out)[:world - 1]
 
 
 class BDepth:
@@ -170,13 +191,17 @@ class BDepth:
         self._ck(self.L.bdepth_set_regions(self.h, arr, len(regions)))
 
     def set_shard(self, rank, world, uid=None):
-        self._ck(self.L.bdepth_set_shard(self.h, rank, world, uid))
+        self._uid = C.create_string_buffer(uid, 128) if uid is not None else None
+        self._ck(self.L.bdepth_set_shard(self.h, rank, world, self._uid))
 
     def set_tuning(self, batch_bytes=0, window_positions=0):
         self._ck(self.L.bdepth_set_tuning(self.h, batch_bytes, window_positions))
 
     def stage(self):
         self._ck(self.L.bdepth_stage(self.h))
+
+    def run_resident(self):
+        self._ck(self.L.bdepth_run_resident(self.h))
 
     def stats(self):
         s = Stats()

@@ -7,6 +7,7 @@
 // then reducers + D2H for the chosen front end (base tiles, window stats, region stats).
 // There is no CPU fallback anywhere: if CUDA is unavailable every run returns BDEPTH_ERR_CUDA.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 #include <fcntl.h>
 #include <stdarg.h>
 #include <stdio.h>
@@ -49,6 +50,47 @@ constexpr uint32_t SHARD_EXTRA_BLOCKS = 8;
 
 enum RunMode { RUN_FULL = 0, RUN_INFLATE_ONLY = 1, RUN_SCAN_ONLY = 2 };
 
+// ---- NCCL, bound at run time (dlopen) so that single-GPU users need no NCCL at all and so that a host
+// process that already loaded NCCL (e.g. through torch) shares that one instance (same SONAME).
+struct NcclUid { char b[128]; };
+typedef void* NcclComm;
+struct NcclApi {
+    bool ok = false; std::string err;
+    int (*GetUniqueId)(NcclUid*) = nullptr;
+    int (*CommInitRank)(NcclComm*, int, NcclUid, int) = nullptr;
+    int (*CommDestroy)(NcclComm) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, NcclComm, cudaStream_t) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
+    int (*Send)(const void*, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
+    int (*Recv)(void*, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+constexpr int NCCL_UINT32 = 3, NCCL_UINT64 = 5, NCCL_SUM = 0;    // ncclDataType_t / ncclRedOp_t values (nccl.h)
+NcclApi& nccl() {
+    static NcclApi api; static bool tried = false;
+    if (tried) return api;
+    tried = true;
+    void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) { api.err = std::string("cannot load libnccl.so.2: ") + dlerror(); return api; }
+    bool all = true;
+    auto sym = [&](const char* n) { void* p = dlsym(lib, n); if (!p) { all = false; api.err = std::string("missing NCCL symbol ") + n; } return p; };
+    api.GetUniqueId = (int (*)(NcclUid*))sym("ncclGetUniqueId");
+    api.CommInitRank = (int (*)(NcclComm*, int, NcclUid, int))sym("ncclCommInitRank");
+    api.CommDestroy = (int (*)(NcclComm))sym("ncclCommDestroy");
+    api.AllGather = (int (*)(const void*, void*, size_t, int, NcclComm, cudaStream_t))sym("ncclAllGather");
+    api.AllReduce = (int (*)(const void*, void*, size_t, int, int, NcclComm, cudaStream_t))sym("ncclAllReduce");
+    api.Send = (int (*)(const void*, size_t, int, int, NcclComm, cudaStream_t))sym("ncclSend");
+    api.Recv = (int (*)(void*, size_t, int, int, NcclComm, cudaStream_t))sym("ncclRecv");
+    api.GroupStart = (int (*)())sym("ncclGroupStart");
+    api.GroupEnd = (int (*)())sym("ncclGroupEnd");
+    api.GetErrorString = (const char* (*)(int))sym("ncclGetErrorString");
+    api.ok = all;
+    return api;
+}
+
 }  // namespace
 
 struct bdepth {
@@ -61,14 +103,20 @@ struct bdepth {
     int mapq_gt = 0; uint32_t flag_reject = 0x600; uint32_t minq = 0;
     std::vector<bdepth_region> regions;   // merged, sorted
     int rank = 0, world = 1;
+    NcclComm comm = nullptr; bool have_uid = false; NcclUid uid{};
+    uint64_t own_lo = 0, own_hi = 0;      // linear range owned by this rank (whole genome when world == 1)
     uint64_t batch_u = 6ull << 30;
     uint64_t window_positions = 0;
     // ---- shard (resolved lazily)
     bool shard_ready = false;
     size_t blk_lo = 0, blk_hi = 0; int64_t entry0 = 0; uint64_t limit_abs_u = 0;
     // ---- device state
-    cudaStream_t s_main = nullptr, s_copy = nullptr;
-    cudaEvent_t ev[16] = {};
+    cudaStream_t s_main = nullptr, s_copy = nullptr, s_d2h = nullptr;
+    cudaEvent_t ev[32] = {};
+    DevBuf comp2[2];
+    cudaStream_t s_k1[4] = {};                        // K1 sub-launches of one batch run side by side
+    std::vector<cudaEvent_t> chunk_ev[2], k1_ev;      // per H2D chunk (per slot) / per K1 sub-launch
+    std::vector<size_t> chunk_end[2];                  // block index (exclusive) covered by each H2D chunk of a slot
     bool staged = false; uint64_t staged_file_off = 0;
     DevBuf comp, descs, status, ubuf, chunk_start, entry, exitb, count, slot_base, slots, rec_base, walk_list;
     DevBuf soa_start, soa_span, soa_meta, soa_off, soa_ncl, soa_lseq, long_list, tile_first, tile_lo, counts, ref_len_d, ref_lin0_d, scan_stats, ref_has, misc;
@@ -88,6 +136,7 @@ int fail(bdepth* h, int code, const char* fmt, ...) {
     if (h) h->err = buf; else g_open_error = buf;
     return code;
 }
+#define NK(call) do { int r__ = (call); if (r__ != 0) return fail(h, BDEPTH_ERR_NCCL, "NCCL error at %s:%d: %s", __FILE__, __LINE__, nccl().GetErrorString ? nccl().GetErrorString(r__) : "?"); } while (0)
 #define CK(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return fail(h, BDEPTH_ERR_CUDA, "CUDA error %s at %s:%d: %s", cudaGetErrorName(e__), __FILE__, __LINE__, cudaGetErrorString(e__)); } while (0)
 
 int ensure_pinned(bdepth* h, size_t n) {
@@ -104,7 +153,7 @@ int init_device(bdepth* h) {
     if (e != cudaSuccess || n <= 0) return fail(h, BDEPTH_ERR_CUDA, "no CUDA device available (%s); libbdepth has no CPU fallback", cudaGetErrorString(e));
     if (h->device < 0 || h->device >= n) return fail(h, BDEPTH_ERR_ARG, "device %d out of range (%d devices)", h->device, n);
     CK(cudaSetDevice(h->device));
-    if (!h->s_main) { CK(cudaStreamCreateWithFlags(&h->s_main, cudaStreamNonBlocking)); CK(cudaStreamCreateWithFlags(&h->s_copy, cudaStreamNonBlocking)); for (auto& e2 : h->ev) CK(cudaEventCreate(&e2)); }
+    if (!h->s_main) { CK(cudaStreamCreateWithFlags(&h->s_main, cudaStreamNonBlocking)); CK(cudaStreamCreateWithFlags(&h->s_copy, cudaStreamNonBlocking)); CK(cudaStreamCreateWithFlags(&h->s_d2h, cudaStreamNonBlocking)); for (auto& ks : h->s_k1) CK(cudaStreamCreateWithFlags(&ks, cudaStreamNonBlocking)); for (auto& e2 : h->ev) CK(cudaEventCreate(&e2)); }
     CK(cudaFuncSetAttribute(k1_inflate, cudaFuncAttributeMaxDynamicSharedMemorySize, K1_SMEM));
     return 0;
 }
@@ -152,6 +201,20 @@ int finish_open(bdepth* h) {
     return 0;
 }
 
+// Candidate shard boundaries: every distinct record start recorded in the BAI linear index.
+std::vector<uint64_t> shard_candidates(const BaiIndex& bai) {
+    std::vector<uint64_t> vos;
+    for (auto& v : bai.ioffsets) for (uint64_t x : v) if (x) vos.push_back(x);
+    std::sort(vos.begin(), vos.end()); vos.erase(std::unique(vos.begin(), vos.end()), vos.end());
+    return vos;
+}
+// k-th of `world` boundaries: first candidate whose compressed offset is >= k * file_len / world.
+uint64_t shard_cut_voffset(const std::vector<uint64_t>& vos, uint64_t file_len, int k, int world) {
+    uint64_t target = (uint64_t)((__uint128_t)file_len * (unsigned)k / (unsigned)world);
+    auto it = std::lower_bound(vos.begin(), vos.end(), target << 16);
+    return it == vos.end() ? UINT64_MAX : *it;
+}
+
 // Resolve the block range / entry / limit of this rank's shard.
 int prepare_shard(bdepth* h) {
     if (h->shard_ready) return 0;
@@ -161,16 +224,13 @@ int prepare_shard(bdepth* h) {
     uint64_t start_u = h->hdr.first_rec_off, end_u = h->total_u;
     if (h->world > 1) {
         if (!h->bai.valid) return fail(h, BDEPTH_ERR_NOINDEX, "sharding needs the BAI linear index");
-        std::vector<uint64_t> vos;
-        for (auto& v : h->bai.ioffsets) for (uint64_t x : v) if (x) vos.push_back(x);
-        std::sort(vos.begin(), vos.end()); vos.erase(std::unique(vos.begin(), vos.end()), vos.end());
+        std::vector<uint64_t> vos = shard_candidates(h->bai);
         auto cut = [&](int k) -> uint64_t {   // absolute inflated offset of the k-th shard boundary
             if (k <= 0) return h->hdr.first_rec_off;
             if (k >= h->world) return h->total_u;
-            uint64_t target = (uint64_t)((__uint128_t)h->file_len * (unsigned)k / (unsigned)h->world);
-            auto it = std::lower_bound(vos.begin(), vos.end(), target << 16);
-            if (it == vos.end()) return h->total_u;
-            uint64_t vo = *it; size_t b = block_of_c(vo >> 16);
+            uint64_t vo = shard_cut_voffset(vos, h->file_len, k, h->world);
+            if (vo == UINT64_MAX) return h->total_u;
+            size_t b = block_of_c(vo >> 16);
             if (B[b].coff != (vo >> 16)) return h->total_u;      // index does not match the file
             uint64_t u = B[b].uoff + (vo & 0xFFFF);
             return u < h->hdr.first_rec_off ? h->hdr.first_rec_off : u;
@@ -187,6 +247,129 @@ int prepare_shard(bdepth* h) {
     return 0;
 }
 
+// ---- base-mode delivery: D2H of finished counter ranges in EMIT_CHUNK pieces on a separate stream, double
+// buffered in pinned memory, split at reference boundaries for the callback.  advance(limit) may be called after
+// every batch: positions below the first read start of the following batch can no longer change (the file is
+// coordinate sorted), so their D2H overlaps the next batch's inflate.
+struct Emitter {
+    bdepth* h; bdepth_tile_cb cb; void* user;
+    struct Range { uint64_t a, b; };
+    std::vector<Range> ranges; size_t ri = 0; uint64_t pos = 0; bool started = false;
+    struct Slot { uint64_t a = 0, b = 0; } slot[2];
+    int head = 0, inflight = 0;
+    uint64_t d2h_bytes = 0;
+    int issue(int si, uint64_t a, uint64_t b) {
+        uint32_t* dst = (uint32_t*)h->pinned + (size_t)si * EMIT_CHUNK * N_PLANES;
+        uint64_t wa = std::max(a, h->cnt_base), wb = std::min(b, h->cnt_base + h->win_len);   // outside the window: zeros
+        if (wa >= wb || wa > a || wb < b) for (int pl = 0; pl < N_PLANES; pl++) memset(dst + (size_t)pl * EMIT_CHUNK, 0, (b - a) * 4);
+        if (wa < wb) for (int pl = 0; pl < N_PLANES; pl++) CK(cudaMemcpyAsync(dst + (size_t)pl * EMIT_CHUNK + (wa - a), h->counts.as<uint32_t>() + (uint64_t)pl * h->win_len + (wa - h->cnt_base), (wb - wa) * 4, cudaMemcpyDeviceToHost, h->s_d2h));
+        CK(cudaEventRecord(h->ev[8 + si], h->s_d2h));
+        slot[si].a = a; slot[si].b = b; d2h_bytes += (b - a) * N_PLANES * 4;
+        return 0;
+    }
+    int deliver_oldest() {
+        int si = (head + 2 - inflight) & 1;     // oldest in-flight slot
+        CK(cudaEventSynchronize(h->ev[8 + si]));
+        inflight--;
+        if (!cb) return 0;
+        const uint32_t* src = (const uint32_t*)h->pinned + (size_t)si * EMIT_CHUNK * N_PLANES;
+        uint64_t a = slot[si].a, bnd = slot[si].b; const size_t nref = h->hdr.ref_len.size();
+        size_t ref = std::upper_bound(h->hdr.ref_lin0.begin(), h->hdr.ref_lin0.end(), a) - h->hdr.ref_lin0.begin() - 1;
+        while (a < bnd && ref < nref) {
+            uint64_t rend = h->hdr.ref_lin0[ref] + h->hdr.ref_len[ref];
+            if (a >= rend) { ref++; continue; }
+            uint64_t e = std::min(bnd, rend);
+            bdepth_tile t{(int32_t)ref, (uint32_t)(a - h->hdr.ref_lin0[ref]), (uint32_t)(e - a), (uint32_t)EMIT_CHUNK, src + (a - slot[si].a)};
+            if (cb(user, &t)) return fail(h, BDEPTH_ERR_CALLBACK, "tile callback aborted");
+            a = e;
+        }
+        return 0;
+    }
+    // everything below `limit` (linear coordinate) is final once `ready` (recorded on the main stream) has fired
+    int advance(uint64_t limit, cudaEvent_t ready) {
+        if (ready) CK(cudaStreamWaitEvent(h->s_d2h, ready, 0));
+        if (!started) { started = true; if (!ranges.empty()) pos = ranges[0].a; }
+        while (ri < ranges.size()) {
+            const Range& r = ranges[ri];
+            uint64_t a = std::max(pos, r.a);
+            if (a >= r.b) { ri++; if (ri < ranges.size()) pos = ranges[ri].a; continue; }
+            if (a >= limit) break;
+            uint64_t b = std::min(std::min(r.b, limit), a + (uint64_t)EMIT_CHUNK);
+            if (inflight == 2) { int rc = deliver_oldest(); if (rc) return rc; }
+            int rc = issue(head, a, b); if (rc) return rc;
+            head ^= 1; inflight++; pos = b;
+        }
+        return 0;
+    }
+    int finish() { while (inflight) { int rc = deliver_oldest(); if (rc) return rc; } return 0; }
+};
+
+__global__ void k_add_u32(uint32_t* __restrict__ dst, const uint32_t* __restrict__ src, uint64_t n) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; if (i < n) dst[i] += src[i];
+}
+
+// Multi-GPU boundary exchange.  Rank k holds the counters of ITS reads, which start in
+// [min_k, min_{k+1}) but may run past min_{k+1}.  Ownership of position p goes to the last rank whose first
+// read starts at or before p; every rank sends the part of its counters that lies in a later rank's range
+// (7 planes, packed) with ncclSend/ncclRecv inside one group, and the owner adds it.  One all-gather of
+// (min_start, max_end) per rank tells everybody the ranges.  Also reduces the per-reference "has reads" bits.
+int exchange_boundaries(bdepth* h, uint64_t shard_min, uint64_t shard_max) {
+    NcclApi& N = nccl(); cudaStream_t sm = h->s_main; const int W = h->world, me = h->rank;
+    cudaEvent_t e0 = h->ev[12], e1 = h->ev[13];
+    CK(cudaEventRecord(e0, sm));
+    DevBuf dpair, dall; CK(dpair.ensure(16)); CK(dall.ensure(16 * (size_t)W));
+    uint64_t mine[2] = {shard_min, shard_max};
+    CK(cudaMemcpyAsync(dpair.p, mine, 16, cudaMemcpyHostToDevice, sm));
+    NK(N.AllGather(dpair.p, dall.p, 2, NCCL_UINT64, h->comm, sm));
+    std::vector<uint64_t> all(2 * (size_t)W);
+    CK(cudaMemcpyAsync(all.data(), dall.p, 16 * (size_t)W, cudaMemcpyDeviceToHost, sm));
+    CK(cudaStreamSynchronize(sm));
+    auto nonempty = [&](int r) { return all[2 * r] != UINT64_MAX; };
+    auto own_lo = [&](int r) -> uint64_t { for (int q = 0; q < r; q++) if (nonempty(q)) return all[2 * r]; return 0; };   // first non-empty rank owns from 0
+    auto own_hi = [&](int r) -> uint64_t { for (int q = r + 1; q < W; q++) if (nonempty(q)) return all[2 * q]; return h->hdr.total_len; };
+    struct Xfer { int peer; uint64_t lo, hi; };
+    std::vector<Xfer> sends, recvs;
+    if (nonempty(me)) for (int j = me + 1; j < W; j++) if (nonempty(j) && all[2 * j] < shard_max) { uint64_t lo = std::max(all[2 * j], shard_min), hi = std::min(shard_max, own_hi(j)); if (lo < hi) sends.push_back({j, lo, hi}); }
+    if (nonempty(me)) for (int i = 0; i < me; i++) if (nonempty(i) && all[2 * i + 1] > all[2 * me]) { uint64_t lo = std::max(all[2 * me], all[2 * i]), hi = std::min(all[2 * i + 1], own_hi(me)); if (lo < hi) recvs.push_back({i, lo, hi}); }
+    uint64_t tot = 0; for (auto& x : sends) tot += x.hi - x.lo; uint64_t sent = tot; for (auto& x : recvs) tot += x.hi - x.lo;
+    DevBuf stage; CK(stage.ensure((size_t)std::max<uint64_t>(tot, 1) * N_PLANES * 4));
+    uint32_t* sp = stage.as<uint32_t>(); uint64_t off = 0;
+    std::vector<uint64_t> soff, roff;
+    for (auto& x : sends) {   // pack the 7 planes of the slice contiguously
+        uint64_t n = x.hi - x.lo; soff.push_back(off);
+        CK(cudaMemcpy2DAsync(sp + off, n * 4, h->counts.as<uint32_t>() + (x.lo - h->cnt_base), h->win_len * 4, n * 4, N_PLANES, cudaMemcpyDeviceToDevice, sm));
+        off += n * N_PLANES;
+    }
+    for (auto& x : recvs) { roff.push_back(off); off += (x.hi - x.lo) * N_PLANES; }
+    NK(N.GroupStart());
+    for (size_t i = 0; i < sends.size(); i++) NK(N.Send(sp + soff[i], (sends[i].hi - sends[i].lo) * N_PLANES, NCCL_UINT32, sends[i].peer, h->comm, sm));
+    for (size_t i = 0; i < recvs.size(); i++) NK(N.Recv(sp + roff[i], (recvs[i].hi - recvs[i].lo) * N_PLANES, NCCL_UINT32, recvs[i].peer, h->comm, sm));
+    NK(N.GroupEnd());
+    for (size_t i = 0; i < recvs.size(); i++) {
+        uint64_t n = recvs[i].hi - recvs[i].lo;
+        for (int pl = 0; pl < N_PLANES; pl++) k_add_u32<<<(unsigned)((n + 255) / 256), 256, 0, sm>>>(h->counts.as<uint32_t>() + (uint64_t)pl * h->win_len + (recvs[i].lo - h->cnt_base), sp + roff[i] + (uint64_t)pl * n, n);
+        h->st.gpu_launches += N_PLANES;
+    }
+    // which references have reads: OR over ranks == (sum > 0)
+    size_t nw = h->hdr.ref_len.size() / 32 + 2;
+    DevBuf bits; CK(bits.ensure(nw * 32 * 4));
+    {   // expand bits -> counts, all-reduce, compress back (tiny)
+        std::vector<uint32_t> hb(nw); CK(cudaMemcpyAsync(hb.data(), h->ref_has.p, nw * 4, cudaMemcpyDeviceToHost, sm)); CK(cudaStreamSynchronize(sm));
+        std::vector<uint32_t> ex(nw * 32); for (size_t i = 0; i < nw * 32; i++) ex[i] = (hb[i >> 5] >> (i & 31)) & 1;
+        CK(cudaMemcpyAsync(bits.p, ex.data(), nw * 32 * 4, cudaMemcpyHostToDevice, sm));
+        NK(N.AllReduce(bits.p, bits.p, nw * 32, NCCL_UINT32, NCCL_SUM, h->comm, sm));
+        CK(cudaMemcpyAsync(ex.data(), bits.p, nw * 32 * 4, cudaMemcpyDeviceToHost, sm)); CK(cudaStreamSynchronize(sm));
+        for (size_t i = 0; i < nw; i++) { uint32_t v = 0; for (int b = 0; b < 32; b++) if (ex[i * 32 + b]) v |= 1u << b; hb[i] = v; }
+        CK(cudaMemcpyAsync(h->ref_has.p, hb.data(), nw * 4, cudaMemcpyHostToDevice, sm));
+    }
+    CK(cudaEventRecord(e1, sm)); CK(cudaStreamSynchronize(sm));
+    float t = 0; CK(cudaEventElapsedTime(&t, e0, e1)); h->st.ms_exchange = t; h->st.halo_bytes_sent = sent * N_PLANES * 4;
+    // ownership: an empty rank owns nothing
+    if (nonempty(me)) { h->own_lo = own_lo(me); h->own_hi = own_hi(me); } else { h->own_lo = h->own_hi = 0; }
+    dpair.release(); dall.release(); stage.release(); bits.release();
+    return 0;
+}
+
 struct RunOut {                    // optional sinks for the kernel-level entry points
     uint8_t* inflate_dst = nullptr; uint64_t inflate_cap = 0; uint64_t inflate_len = 0;
     uint64_t scan_cap = 0; uint64_t scan_n = 0;
@@ -196,7 +379,7 @@ struct RunOut {                    // optional sinks for the kernel-level entry 
 __global__ void k_fill_u32(uint32_t* p, uint32_t v, uint64_t n) { uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; if (i < n) p[i] = v; }
 
 // The pipeline: leaves the per-position counters of the whole shard in h->counts (RUN_FULL).
-int run_pipeline(bdepth* h, RunMode mode, RunOut* ro) {
+int run_pipeline(bdepth* h, RunMode mode, RunOut* ro, Emitter* em = nullptr) {
     int rc = init_device(h); if (rc) return rc;
     rc = prepare_shard(h); if (rc) return rc;
     auto t_host0 = std::chrono::steady_clock::now();
@@ -236,8 +419,37 @@ int run_pipeline(bdepth* h, RunMode mode, RunOut* ro) {
 
     float ms_h2d = 0, ms_k1 = 0, ms_k2 = 0, ms_k3 = 0;
     uint64_t carry_len = 0; bool first_batch = true;
+    uint64_t shard_min = UINT64_MAX, shard_max = 0;
+    CK(cudaEventRecord(h->ev[10], sm));
     size_t b = h->blk_lo;
     if (ro) { ro->inflate_len = 0; ro->scan_n = 0; }
+    if (!h->staged) {   // size both compressed-data buffers for the largest batch up front (ensure() must not reallocate mid-flight)
+        uint64_t mx = 0; for (size_t bb = h->blk_lo; bb < h->blk_hi;) { size_t e = bb; uint64_t u = 0; while (e < h->blk_hi && (e == bb || u + B[e].isize <= h->batch_u)) { u += B[e].isize; e++; } mx = std::max<uint64_t>(mx, B[e - 1].coff + B[e - 1].bsize - (B[bb].coff & ~3ull)); bb = e; }
+        CK(h->comp2[0].ensure(mx + 256)); CK(h->comp2[1].ensure(mx + 256));
+    }
+    size_t batch_no = 0;
+    auto batch_end = [&](size_t bb) { size_t e = bb; uint64_t u = 0; while (e < h->blk_hi && (e == bb || u + B[e].isize <= h->batch_u)) { u += B[e].isize; e++; } return e; };
+    // H2D of blocks [bb, be) into comp2[slot]; waits until K1 of the batch that used the slot two batches ago is done
+    constexpr size_t H2D_CHUNK_BLOCKS = 8192;      // ~320 MB of compressed data, 256 K1 warps per sub-launch
+    auto issue_h2d = [&](size_t no, size_t bb, size_t be) -> int {
+        int slot = (int)(no & 1);
+        uint64_t g0 = B[bb].coff & ~3ull;
+        if (no >= 2) CK(cudaStreamWaitEvent(h->s_copy, h->ev[16 + slot], 0));
+        CK(cudaEventRecord(h->ev[18 + slot], h->s_copy));
+        h->chunk_end[slot].clear();
+        size_t nch = 0;
+        for (size_t c0 = bb; c0 < be; c0 += H2D_CHUNK_BLOCKS, nch++) {
+            size_t c1 = std::min(be, c0 + H2D_CHUNK_BLOCKS);
+            uint64_t a = c0 == bb ? g0 : B[c0].coff, e = B[c1 - 1].coff + B[c1 - 1].bsize;
+            CK(cudaMemcpyAsync((uint8_t*)h->comp2[slot].p + (a - g0), h->file + a, e - a, cudaMemcpyHostToDevice, h->s_copy));
+            if (c1 == be) CK(cudaMemsetAsync((uint8_t*)h->comp2[slot].p + (e - g0), 0, 128, h->s_copy));
+            if (h->chunk_ev[slot].size() <= nch) { cudaEvent_t ne; CK(cudaEventCreateWithFlags(&ne, cudaEventDisableTiming)); h->chunk_ev[slot].push_back(ne); }
+            CK(cudaEventRecord(h->chunk_ev[slot][nch], h->s_copy));
+            h->chunk_end[slot].push_back(c1);
+        }
+        CK(cudaEventRecord(h->ev[14 + slot], h->s_copy));
+        return 0;
+    };
     while (b < h->blk_hi) {
         // ---- batch extent
         size_t b1 = b; uint64_t ub = 0;
@@ -245,17 +457,16 @@ int run_pipeline(bdepth* h, RunMode mode, RunOut* ro) {
         const size_t nb = b1 - b; const bool last_batch = b1 == h->blk_hi;
         const uint64_t batch_u0 = B[b].uoff;               // absolute inflated offset of the batch start
         st.n_batches++; st.n_blocks += nb; st.inflated_bytes += ub;
-        // ---- compressed bytes on the device
+        // ---- compressed bytes on the device: H2D runs on the copy stream into one of two buffers, so the copy of
+        // batch i+1 overlaps the kernels of batch i
         uint64_t f0 = B[b].coff & ~3ull, f1 = B[b1 - 1].coff + B[b1 - 1].bsize;
         const uint32_t* d_comp; uint64_t comp_base_off;
         cudaEvent_t e0 = h->ev[0], e1 = h->ev[1], e2 = h->ev[2], e3 = h->ev[3], e4 = h->ev[4];
         CK(cudaEventRecord(e0, sm));
         if (h->staged) { d_comp = h->comp.as<uint32_t>(); comp_base_off = h->staged_file_off; }
         else {
-            CK(h->comp.ensure(f1 - f0 + 256));
-            CK(cudaMemcpyAsync(h->comp.p, h->file + f0, f1 - f0, cudaMemcpyHostToDevice, sm));
-            CK(cudaMemsetAsync((uint8_t*)h->comp.p + (f1 - f0), 0, 128, sm));
-            d_comp = h->comp.as<uint32_t>(); comp_base_off = f0;
+            if (batch_no == 0) { int rcp = issue_h2d(0, b, b1); if (rcp) return rcp; }
+            d_comp = h->comp2[batch_no & 1].as<uint32_t>(); comp_base_off = f0;
         }
         st.file_bytes += f1 - B[b].coff;
         // ---- descriptors
@@ -266,10 +477,29 @@ int run_pipeline(bdepth* h, RunMode mode, RunOut* ro) {
         CK(cudaMemcpyAsync(h->descs.p, d.data(), nb * sizeof(BlockDesc), cudaMemcpyHostToDevice, sm));
         uint8_t* u0 = h->ubuf.as<uint8_t>() + CARRY_MAX;     // offset 0 of this batch's inflated bytes
         CK(cudaEventRecord(e1, sm));
-        // ---- K1
-        k1_inflate<<<(unsigned)((nb + 32 * K1_WARPS - 1) / (32 * K1_WARPS)), 32 * K1_WARPS, K1_SMEM, sm>>>(d_comp, h->descs.as<BlockDesc>(), (uint32_t)nb, u0, h->status.as<int>());
-        CK(cudaGetLastError()); st.gpu_launches++;
+        // ---- K1: when the input is streaming in, one sub-launch per H2D chunk, spread over a few streams so that
+        // they run side by side (a lone sub-launch cannot fill the GPU: every lane owns a whole BGZF block)
+        if (h->staged) {
+            k1_inflate<<<(unsigned)((nb + 32 * K1_WARPS - 1) / (32 * K1_WARPS)), 32 * K1_WARPS, K1_SMEM, sm>>>(d_comp, h->descs.as<BlockDesc>(), (uint32_t)nb, u0, h->status.as<int>());
+            CK(cudaGetLastError()); st.gpu_launches++;
+        } else {
+            int slot = (int)(batch_no & 1); size_t c0 = b;
+            for (size_t j = 0; j < h->chunk_end[slot].size(); j++) {
+                size_t c1 = h->chunk_end[slot][j]; cudaStream_t ks = h->s_k1[j & 3];
+                CK(cudaStreamWaitEvent(ks, e1, 0)); CK(cudaStreamWaitEvent(ks, h->chunk_ev[slot][j], 0));
+                uint32_t n = (uint32_t)(c1 - c0);
+                k1_inflate<<<(n + 32 * K1_WARPS - 1) / (32 * K1_WARPS), 32 * K1_WARPS, K1_SMEM, ks>>>(d_comp, h->descs.as<BlockDesc>() + (c0 - b), n, u0, h->status.as<int>() + (c0 - b));
+                CK(cudaGetLastError()); st.gpu_launches++;
+                if (h->k1_ev.size() <= j) { cudaEvent_t ne; CK(cudaEventCreateWithFlags(&ne, cudaEventDisableTiming)); h->k1_ev.push_back(ne); }
+                CK(cudaEventRecord(h->k1_ev[j], ks)); CK(cudaStreamWaitEvent(sm, h->k1_ev[j], 0));
+                c0 = c1;
+            }
+        }
         CK(cudaEventRecord(e2, sm));
+        if (!h->staged) {
+            CK(cudaEventRecord(h->ev[16 + (batch_no & 1)], sm));            // this batch's compressed buffer is free again
+            if (b1 < h->blk_hi) { int rcp = issue_h2d(batch_no + 1, b1, batch_end(b1)); if (rcp) return rcp; }
+        }
         std::vector<int> stt(nb);
         CK(cudaMemcpyAsync(stt.data(), h->status.p, nb * sizeof(int), cudaMemcpyDeviceToHost, sm));
         if (mode == RUN_INFLATE_ONLY) {
@@ -280,8 +510,8 @@ int run_pipeline(bdepth* h, RunMode mode, RunOut* ro) {
                 CK(cudaMemcpy(ro->inflate_dst + ro->inflate_len, u0, ub, cudaMemcpyDeviceToHost));
             }
             if (ro) ro->inflate_len += ub;
-            float t; CK(cudaEventElapsedTime(&t, e0, e1)); ms_h2d += t; CK(cudaEventElapsedTime(&t, e1, e2)); ms_k1 += t;
-            b = b1; continue;
+            float t; CK(cudaEventElapsedTime(&t, e1, e2)); ms_k1 += t;
+            b = b1; batch_no++; continue;
         }
         // ---- K2: chunk table
         std::vector<int64_t> cstart(nb + 1); std::vector<uint32_t> sbase(nb + 1);
@@ -364,7 +594,7 @@ int run_pipeline(bdepth* h, RunMode mode, RunOut* ro) {
         size_t Rc = R ? R : 1;
         CK(h->soa_start.ensure(Rc * 8)); CK(h->soa_span.ensure(Rc * 4)); CK(h->soa_meta.ensure(Rc * 4)); CK(h->soa_off.ensure(Rc * 8)); CK(h->soa_ncl.ensure(Rc * 4)); CK(h->soa_lseq.ensure(Rc * 4)); CK(h->long_list.ensure(Rc * 4));
         RecordSoA soa{h->soa_start.as<uint64_t>(), h->soa_span.as<uint32_t>(), h->soa_meta.as<uint32_t>(), h->soa_off.as<int64_t>(), h->soa_ncl.as<uint32_t>(), h->soa_lseq.as<int32_t>()};
-        ScanStats zs{0, 0, 0, 0, ~0ull, 0};
+        ScanStats zs{0, 0, 0, 0, ~0ull, 0, 0};
         CK(cudaMemcpyAsync(h->scan_stats.p, &zs, sizeof zs, cudaMemcpyHostToDevice, sm));
         if (mode == RUN_SCAN_ONLY && !h->ref_has.p) { CK(h->ref_has.ensure((nref / 32 + 2) * 4)); CK(cudaMemsetAsync(h->ref_has.p, 0, (nref / 32 + 2) * 4, sm)); }
         k2_decode<<<(unsigned)((nb * 32 + 255) / 256), 256, 0, sm>>>(sp, h->chunk_start.as<int64_t>(), (uint32_t)nb, h->slot_base.as<uint32_t>(), h->slots.as<uint16_t>(), h->count.as<uint32_t>(), h->rec_base.as<uint32_t>(), soa, h->mapq_gt, h->flag_reject, h->scan_stats.as<ScanStats>(), h->long_list.as<uint32_t>(), h->ref_has.as<uint32_t>());
@@ -373,6 +603,7 @@ int run_pipeline(bdepth* h, RunMode mode, RunOut* ro) {
         CK(cudaEventRecord(e3, sm));
         CK(cudaStreamSynchronize(sm));
         st.n_records_pass += ss.n_pass; st.n_cigar_ops += ss.n_cigar; st.seq_bytes += ss.seq_bytes; st.long_reads += ss.n_long;
+        if (ss.n_pass) { shard_min = std::min<uint64_t>(shard_min, ss.min_start); shard_max = std::max<uint64_t>(shard_max, ss.max_end); }
         if (mode == RUN_SCAN_ONLY) {
             if (ro && R) {
                 uint64_t n = std::min<uint64_t>(R, ro->scan_cap > ro->scan_n ? ro->scan_cap - ro->scan_n : 0);
@@ -417,6 +648,7 @@ int run_pipeline(bdepth* h, RunMode mode, RunOut* ro) {
             CK(cudaGetLastError()); st.gpu_launches++;
         }
         CK(cudaEventRecord(e4, sm));
+        if (em && mode == RUN_FULL && h->world == 1 && !last_batch && ss.n_pass) { int rce = em->advance(ss.max_start / TILE_POS * TILE_POS, e4); if (rce) return rce; }
         // ---- carry the incomplete tail record to the front of the next batch
         uint64_t new_carry = (uint64_t)((int64_t)ub - tail);
         if (!last_batch && new_carry) {
@@ -424,15 +656,21 @@ int run_pipeline(bdepth* h, RunMode mode, RunOut* ro) {
             CK(cudaMemcpyAsync(u0 - new_carry, u0 + tail, new_carry, cudaMemcpyDeviceToDevice, sm));
         }
         CK(cudaStreamSynchronize(sm));
-        { float t; CK(cudaEventElapsedTime(&t, e0, e1)); ms_h2d += t; CK(cudaEventElapsedTime(&t, e1, e2)); ms_k1 += t; CK(cudaEventElapsedTime(&t, e2, e3)); ms_k2 += t; CK(cudaEventElapsedTime(&t, e3, e4)); ms_k3 += t; }
-        carry_len = last_batch ? 0 : new_carry; first_batch = false; b = b1;
+        { float t; if (!h->staged) { CK(cudaEventElapsedTime(&t, h->ev[18 + (batch_no & 1)], h->ev[14 + (batch_no & 1)])); ms_h2d += t; } CK(cudaEventElapsedTime(&t, e1, e2)); ms_k1 += t; CK(cudaEventElapsedTime(&t, e2, e3)); ms_k2 += t; CK(cudaEventElapsedTime(&t, e3, e4)); ms_k3 += t; }
+        carry_len = last_batch ? 0 : new_carry; first_batch = false; b = b1; batch_no++;
     }
     st.ms_h2d = ms_h2d; st.ms_inflate = ms_k1; st.ms_scan = ms_k2; st.ms_coverage = ms_k3;
     st.positions = mode == RUN_FULL ? h->hdr.total_len : 0;
+    h->own_lo = 0; h->own_hi = h->hdr.total_len;
     if (mode == RUN_FULL) {
+        if (h->world > 1 && h->comm) { rc = exchange_boundaries(h, shard_min, shard_max); if (rc) return rc; }
         h->ref_has_host.assign(nref / 32 + 2, 0);
-        CK(cudaMemcpy(h->ref_has_host.data(), h->ref_has.p, (nref / 32 + 2) * 4, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpyAsync(h->ref_has_host.data(), h->ref_has.p, (nref / 32 + 2) * 4, cudaMemcpyDeviceToHost, sm));
     }
+    CK(cudaEventRecord(h->ev[11], sm));
+    CK(cudaStreamSynchronize(sm));
+    { float t = 0; CK(cudaEventElapsedTime(&t, h->ev[10], h->ev[11])); st.ms_span_device = t; }
+    st.own_lo = h->own_lo; st.own_hi = h->own_hi;
     st.host_wall_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_host0).count();
     return 0;
 }
@@ -499,8 +737,10 @@ void bdepth_close(bdepth_t* h) {
     DevBuf* bufs[] = {&h->comp, &h->descs, &h->status, &h->ubuf, &h->chunk_start, &h->entry, &h->exitb, &h->count, &h->slot_base, &h->slots, &h->rec_base, &h->walk_list, &h->soa_start, &h->soa_span, &h->soa_meta, &h->soa_off, &h->soa_ncl, &h->soa_lseq, &h->long_list, &h->tile_first, &h->tile_lo, &h->counts, &h->ref_len_d, &h->ref_lin0_d, &h->scan_stats, &h->ref_has, &h->misc};
     for (DevBuf* b : bufs) b->release();
     h->seg.s.release(); h->seg.e.release(); h->seg.pmax.release(); h->seg.id.release(); h->seg.reads.release();
+    if (h->comm) { nccl().CommDestroy(h->comm); h->comm = nullptr; }
     if (h->pinned) cudaFreeHost(h->pinned);
-    if (h->s_main) { cudaStreamDestroy(h->s_main); cudaStreamDestroy(h->s_copy); for (auto& e : h->ev) cudaEventDestroy(e); }
+    if (h->s_main) { cudaStreamDestroy(h->s_main); cudaStreamDestroy(h->s_copy); cudaStreamDestroy(h->s_d2h); for (auto& ks : h->s_k1) cudaStreamDestroy(ks); for (auto& e : h->ev) cudaEventDestroy(e); for (int q = 0; q < 2; q++) for (auto& e : h->chunk_ev[q]) cudaEventDestroy(e); for (auto& e : h->k1_ev) cudaEventDestroy(e); }
+    h->comp2[0].release(); h->comp2[1].release();
     if (h->mapped) munmap((void*)h->file, h->file_len);
     if (h->fd >= 0) close(h->fd);
     delete h;
@@ -523,11 +763,44 @@ int bdepth_set_regions(bdepth_t* h, const bdepth_region* r, size_t n) { normaliz
 int bdepth_set_shard(bdepth_t* h, int rank, int world, const void* nccl_unique_id) {
     if (world < 1 || rank < 0 || rank >= world) return fail(h, BDEPTH_ERR_ARG, "bad shard %d/%d", rank, world);
     if (world > 1 && !h->bai.valid) return fail(h, BDEPTH_ERR_NOINDEX, "sharding needs the BAI linear index");
-    (void)nccl_unique_id;
+    if (h->comm) { nccl().CommDestroy(h->comm); h->comm = nullptr; }
     h->rank = rank; h->world = world; h->shard_ready = false; h->staged = false;
+    if (world > 1 && nccl_unique_id) {
+        NcclApi& N = nccl();
+        if (!N.ok) return fail(h, BDEPTH_ERR_NCCL, "%s", N.err.c_str());
+        int rc = init_device(h); if (rc) return rc;
+        memcpy(h->uid.b, nccl_unique_id, 128);
+        NK(N.CommInitRank(&h->comm, world, h->uid, rank));
+    }
     return 0;
 }
-int bdepth_nccl_unique_id(void* out128) { (void)out128; return fail(nullptr, BDEPTH_ERR_NCCL, "NCCL exchange is not built into this library yet"); }
+int bdepth_nccl_unique_id(void* out128) {
+    NcclApi& N = nccl();
+    if (!N.ok) return fail(nullptr, BDEPTH_ERR_NCCL, "%s", N.err.c_str());
+    NcclUid u; int r = N.GetUniqueId(&u);
+    if (r) return fail(nullptr, BDEPTH_ERR_NCCL, "ncclGetUniqueId: %s", N.GetErrorString(r));
+    memcpy(out128, u.b, 128);
+    return 0;
+}
+// Host-only shard planning: needs the BGZF block index and the BAI, no device.
+int bdepth_plan_shards(const char* bam_path, int world, uint64_t* out) {
+    if (!bam_path || world < 1 || (world > 1 && !out)) return fail(nullptr, BDEPTH_ERR_ARG, "bad argument");
+    int fd = open(bam_path, O_RDONLY); if (fd < 0) return fail(nullptr, BDEPTH_ERR_IO, "cannot open %s", bam_path);
+    struct stat sb; fstat(fd, &sb);
+    void* m = mmap(nullptr, (size_t)sb.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+    if (m == MAP_FAILED) { close(fd); return fail(nullptr, BDEPTH_ERR_IO, "cannot mmap %s", bam_path); }
+    std::vector<HostBlock> blocks; uint64_t tu = 0;
+    std::string e = index_bgzf((const uint8_t*)m, (size_t)sb.st_size, blocks, &tu);
+    munmap(m, (size_t)sb.st_size); close(fd);
+    if (!e.empty()) return fail(nullptr, BDEPTH_ERR_FORMAT, "%s", e.c_str());
+    BaiIndex bai;
+    { std::string p1 = std::string(bam_path) + ".bai"; FILE* f = fopen(p1.c_str(), "rb"); if (!f) return fail(nullptr, BDEPTH_ERR_NOINDEX, "no index %s", p1.c_str());
+      fseek(f, 0, SEEK_END); long n = ftell(f); fseek(f, 0, SEEK_SET); std::vector<uint8_t> buf(n); if (fread(buf.data(), 1, n, f) != (size_t)n) { fclose(f); return fail(nullptr, BDEPTH_ERR_IO, "read error"); } fclose(f);
+      if (!parse_bai(buf.data(), buf.size(), bai)) return fail(nullptr, BDEPTH_ERR_FORMAT, "bad BAI"); }
+    std::vector<uint64_t> vos = shard_candidates(bai);
+    for (int k = 1; k < world; k++) out[k - 1] = shard_cut_voffset(vos, (uint64_t)sb.st_size, k, world);
+    return 0;
+}
 int bdepth_set_tuning(bdepth_t* h, uint64_t batch_inflated_bytes, uint64_t window_positions) {
     if (batch_inflated_bytes) h->batch_u = std::max<uint64_t>(batch_inflated_bytes, 1 << 20);
     h->window_positions = window_positions; h->staged = false;
@@ -548,61 +821,46 @@ int bdepth_stage(bdepth_t* h) {
     return 0;
 }
 
-// ---- base mode: D2H of the counters in EMIT_CHUNK pieces, split at reference boundaries
-int bdepth_run_base(bdepth_t* h, bdepth_tile_cb cb, void* user) {
+int bdepth_run_resident(bdepth_t* h) {
     int rc = run_pipeline(h, RUN_FULL, nullptr); if (rc) return rc;
     cudaStream_t sm = h->s_main;
-    cudaEvent_t e0 = h->ev[5], e1 = h->ev[6];
-    rc = ensure_pinned(h, 2 * EMIT_CHUNK * N_PLANES * 4); if (rc) return rc;
-    // covered positions (rows of default `depth base`)
     CK(cudaMemsetAsync(h->misc.p, 0, 8, sm));
-    k_count_covered<<<2048, 256, 0, sm>>>(h->counts.as<uint32_t>(), h->win_len, 0, h->win_len, (unsigned long long*)h->misc.p);
-    CK(cudaGetLastError()); h->st.gpu_launches++;
+    uint64_t a = std::max(h->own_lo, h->cnt_base) - h->cnt_base, b = std::min(h->own_hi, h->cnt_base + h->win_len) - h->cnt_base;
+    if (b > a) { k_count_covered<<<2048, 256, 0, sm>>>(h->counts.as<uint32_t>(), h->win_len, a, b, (unsigned long long*)h->misc.p); CK(cudaGetLastError()); h->st.gpu_launches++; }
+    unsigned long long cov = 0; CK(cudaMemcpyAsync(&cov, h->misc.p, 8, cudaMemcpyDeviceToHost, sm)); CK(cudaStreamSynchronize(sm));
+    h->st.covered_positions = cov;
+    h->st.ms_total_device = h->st.ms_h2d + h->st.ms_inflate + h->st.ms_scan + h->st.ms_coverage + h->st.ms_exchange;
+    return 0;
+}
+
+// ---- base mode: D2H of the counters in EMIT_CHUNK pieces, split at reference boundaries
+int bdepth_run_base(bdepth_t* h, bdepth_tile_cb cb, void* user) {
+    int rc = init_device(h); if (rc) return rc;
+    rc = ensure_pinned(h, 2 * EMIT_CHUNK * N_PLANES * 4); if (rc) return rc;
+    Emitter em{h, cb, user};
+    // ranges to deliver: whole genome, or the merged regions (sorted)
+    if (h->regions.empty()) { if (h->hdr.total_len) em.ranges.push_back({0, h->hdr.total_len}); }
+    else for (auto& g : h->regions) em.ranges.push_back({h->hdr.ref_lin0[g.ref_id] + g.start, h->hdr.ref_lin0[g.ref_id] + g.end});
+    rc = run_pipeline(h, RUN_FULL, nullptr, &em); if (rc) { em.finish(); return rc; }
+    cudaStream_t sm = h->s_main;
+    cudaEvent_t e0 = h->ev[5], e1 = h->ev[6];
+    // covered positions (rows of default `depth base`), over the range this rank owns
+    CK(cudaMemsetAsync(h->misc.p, 0, 8, sm));
+    { uint64_t ca = std::max(h->own_lo, h->cnt_base) - h->cnt_base, cb2 = std::min(h->own_hi, h->cnt_base + h->win_len) - h->cnt_base;
+      if (cb2 > ca) { k_count_covered<<<2048, 256, 0, sm>>>(h->counts.as<uint32_t>(), h->win_len, ca, cb2, (unsigned long long*)h->misc.p); CK(cudaGetLastError()); h->st.gpu_launches++; } }
     unsigned long long cov = 0; CK(cudaMemcpyAsync(&cov, h->misc.p, 8, cudaMemcpyDeviceToHost, sm));
     CK(cudaEventRecord(e0, sm));
-    // ranges to deliver: whole genome, or the merged regions
-    struct Range { uint64_t a, b; };
-    std::vector<Range> ranges;
-    if (h->regions.empty()) { if (h->hdr.total_len) ranges.push_back({0, h->hdr.total_len}); }
-    else for (auto& g : h->regions) ranges.push_back({h->hdr.ref_lin0[g.ref_id] + g.start, h->hdr.ref_lin0[g.ref_id] + g.end});
-    // chunk list
-    std::vector<Range> chunks;
-    for (auto& r : ranges) for (uint64_t a = r.a; a < r.b; a += EMIT_CHUNK) chunks.push_back({a, std::min<uint64_t>(r.b, a + EMIT_CHUNK)});
-    auto issue = [&](size_t ci) -> int {
-        uint32_t* dst = (uint32_t*)h->pinned + (ci & 1) * EMIT_CHUNK * N_PLANES; uint64_t a = chunks[ci].a, b = chunks[ci].b;
-        // positions outside the counter window hold no reads: zeros
-        uint64_t wa = std::max(a, h->cnt_base), wb = std::min(b, h->cnt_base + h->win_len);
-        if (wa >= wb) { for (int pl = 0; pl < N_PLANES; pl++) memset(dst + (size_t)pl * EMIT_CHUNK, 0, (b - a) * 4); }
-        else {
-            if (wa > a || wb < b) for (int pl = 0; pl < N_PLANES; pl++) memset(dst + (size_t)pl * EMIT_CHUNK, 0, (b - a) * 4);
-            for (int pl = 0; pl < N_PLANES; pl++) CK(cudaMemcpyAsync(dst + (size_t)pl * EMIT_CHUNK + (wa - a), h->counts.as<uint32_t>() + (uint64_t)pl * h->win_len + (wa - h->cnt_base), (wb - wa) * 4, cudaMemcpyDeviceToHost, sm));
-        }
-        CK(cudaEventRecord(h->ev[8 + (ci & 1)], sm));
-        return 0;
-    };
-    const size_t nref = h->hdr.ref_len.size();
-    if (!chunks.empty()) { rc = issue(0); if (rc) return rc; }
-    for (size_t ci = 0; ci < chunks.size(); ci++) {
-        CK(cudaEventSynchronize(h->ev[8 + (ci & 1)]));
-        if (ci + 1 < chunks.size()) { rc = issue(ci + 1); if (rc) return rc; }
-        if (!cb) continue;
-        const uint32_t* src = (const uint32_t*)h->pinned + (ci & 1) * EMIT_CHUNK * N_PLANES;
-        uint64_t a = chunks[ci].a, bnd = chunks[ci].b;
-        // split at reference boundaries
-        size_t ref = std::upper_bound(h->hdr.ref_lin0.begin(), h->hdr.ref_lin0.end(), a) - h->hdr.ref_lin0.begin() - 1;
-        while (a < bnd && ref < nref) {
-            uint64_t rend = h->hdr.ref_lin0[ref] + h->hdr.ref_len[ref];
-            if (a >= rend) { ref++; continue; }
-            uint64_t e = std::min(bnd, rend);
-            bdepth_tile t{(int32_t)ref, (uint32_t)(a - h->hdr.ref_lin0[ref]), (uint32_t)(e - a), (uint32_t)EMIT_CHUNK, src + (a - chunks[ci].a)};
-            if (cb(user, &t)) return fail(h, BDEPTH_ERR_CALLBACK, "tile callback aborted");
-            a = e;
-        }
+    if (h->world > 1) {   // multi-GPU: ranks deliver disjoint, ordered pieces: clip the not-yet-delivered ranges to the owned range
+        std::vector<Emitter::Range> clipped;
+        for (auto& r : em.ranges) { uint64_t a = std::max(r.a, h->own_lo), b = std::min(r.b, h->own_hi); if (a < b) clipped.push_back({a, b}); }
+        em.ranges = clipped; em.ri = 0; em.started = false;
     }
-    CK(cudaEventRecord(e1, sm)); CK(cudaStreamSynchronize(sm));
+    rc = em.advance(UINT64_MAX, e0); if (rc) { em.finish(); return rc; }
+    rc = em.finish(); if (rc) return rc;
+    CK(cudaEventRecord(e1, h->s_d2h)); CK(cudaStreamSynchronize(h->s_d2h)); CK(cudaStreamSynchronize(sm));
     h->st.covered_positions = cov;
-    float t; CK(cudaEventElapsedTime(&t, e0, e1)); h->st.ms_d2h = t;
-    h->st.ms_total_device = h->st.ms_h2d + h->st.ms_inflate + h->st.ms_scan + h->st.ms_coverage + h->st.ms_d2h;
+    float t = 0; CK(cudaEventElapsedTime(&t, e0, e1)); h->st.ms_d2h = t;      // the part of the D2H that was not hidden behind the kernels
+    h->st.ms_total_device = h->st.ms_h2d + h->st.ms_inflate + h->st.ms_scan + h->st.ms_coverage + h->st.ms_exchange + h->st.ms_d2h;
     return 0;
 }
 
@@ -648,7 +906,8 @@ static int run_segments(bdepth* h, const std::vector<SegDef>& segs, const uint32
     cudaError_t ce;
     if ((ce = da.ensure(nn * 8)) || (ce = db.ensure(nn * 8)) || (ce = dthr.ensure(64)) || (ce = dbases.ensure(nn * 4)) || (ce = dcov.ensure(nn * 4 * std::max<size_t>(n_thr, 1)))) { cleanup(); return fail(h, BDEPTH_ERR_CUDA, "out of device memory (%s)", cudaGetErrorString(ce)); }
     for (size_t i = 0; i < n; i++) {
-        uint64_t wa = std::min(std::max(a[i], h->cnt_base), h->cnt_base + h->win_len), wb = std::min(std::max(b[i], h->cnt_base), h->cnt_base + h->win_len);
+        uint64_t lo = std::max(h->cnt_base, h->own_lo), hi = std::min(h->cnt_base + h->win_len, h->own_hi); if (hi < lo) hi = lo;
+        uint64_t wa = std::min(std::max(a[i], lo), hi), wb = std::min(std::max(b[i], lo), hi);
         a[i] = wa - h->cnt_base; b[i] = wb - h->cnt_base;
     }
     if (n) { cudaMemcpyAsync(da.p, a.data(), n * 8, cudaMemcpyHostToDevice, sm); cudaMemcpyAsync(db.p, b.data(), n * 8, cudaMemcpyHostToDevice, sm); }
@@ -657,6 +916,12 @@ static int run_segments(bdepth* h, const std::vector<SegDef>& segs, const uint32
     if (n) {
         k_segment_stats<<<(unsigned)((n * 32 + 255) / 256), 256, 0, sm>>>(h->counts.as<uint32_t>(), h->win_len, da.as<uint64_t>(), db.as<uint64_t>(), (uint32_t)n, dthr.as<uint32_t>(), (uint32_t)n_thr, dbases.as<uint32_t>(), dcov.as<uint32_t>());
         h->st.gpu_launches++;
+        if (h->world > 1 && h->comm) {   // per-segment partial sums are additive over ranks
+            NcclApi& N = nccl();
+            N.AllReduce(dbases.p, dbases.p, n, NCCL_UINT32, NCCL_SUM, h->comm, sm);
+            if (n_thr) N.AllReduce(dcov.p, dcov.p, n * n_thr, NCCL_UINT32, NCCL_SUM, h->comm, sm);
+            N.AllReduce(S.reads.p, S.reads.p, n, NCCL_UINT32, NCCL_SUM, h->comm, sm);
+        }
         cudaMemcpyAsync(bases.data(), dbases.p, n * 4, cudaMemcpyDeviceToHost, sm);
         if (n_thr) cudaMemcpyAsync(cov.data(), dcov.p, n * n_thr * 4, cudaMemcpyDeviceToHost, sm);
         cudaMemcpyAsync(reads.data(), S.reads.p, n * 4, cudaMemcpyDeviceToHost, sm);

@@ -150,7 +150,7 @@ struct RecordSoA {
     int32_t*  lseq;
 };
 struct ScanStats {      // device-side accumulators
-    unsigned long long n_pass, n_cigar, seq_bytes, max_end, min_start, n_long;
+    unsigned long long n_pass, n_cigar, seq_bytes, max_end, min_start, n_long, max_start;
 };
 
 __device__ __forceinline__ bool cig_rcons(uint32_t op) { return op == 0 || op == 2 || op == 3 || op == 7 || op == 8; }
@@ -167,7 +167,7 @@ __global__ void k2_decode(ScanParams sp, const int64_t* __restrict__ chunk_start
     int64_t c0 = chunk_start[warp];
     const uint16_t* sl = slots + slot_base[warp];
     uint32_t rb = rec_base[warp];
-    unsigned long long loc_pass = 0, loc_cig = 0, loc_seq = 0, loc_maxend = 0, loc_minstart = ~0ull;
+    unsigned long long loc_pass = 0, loc_cig = 0, loc_seq = 0, loc_maxend = 0, loc_minstart = ~0ull, loc_maxstart = 0;
     for (uint32_t k = lane; k < n; k += 32) {
         int64_t o = c0 + sl[k];
         const uint8_t* p = sp.u + o + 4;
@@ -197,6 +197,7 @@ __global__ void k2_decode(ScanParams sp, const int64_t* __restrict__ chunk_start
             loc_pass++; loc_seq += ((uint64_t)l_seq + 1) / 2;
             if (start + span_eff > loc_maxend) loc_maxend = start + span_eff;
             if (start < loc_minstart) loc_minstart = start;
+            if (start > loc_maxstart) loc_maxstart = start;
             atomicOr(&ref_has_reads[ref >> 5], 1u << (ref & 31));
             if (is_long) { uint32_t idx = (uint32_t)atomicAdd(&st->n_long, 1ull); long_list[idx] = r; }
         }
@@ -205,6 +206,7 @@ __global__ void k2_decode(ScanParams sp, const int64_t* __restrict__ chunk_start
         loc_pass += __shfl_xor_sync(0xFFFFFFFFu, loc_pass, s); loc_cig += __shfl_xor_sync(0xFFFFFFFFu, loc_cig, s); loc_seq += __shfl_xor_sync(0xFFFFFFFFu, loc_seq, s);
         unsigned long long m = __shfl_xor_sync(0xFFFFFFFFu, loc_maxend, s); if (m > loc_maxend) loc_maxend = m;
         m = __shfl_xor_sync(0xFFFFFFFFu, loc_minstart, s); if (m < loc_minstart) loc_minstart = m;
+        m = __shfl_xor_sync(0xFFFFFFFFu, loc_maxstart, s); if (m > loc_maxstart) loc_maxstart = m;
     }
     if (lane == 0) {
         if (loc_pass) atomicAdd(&st->n_pass, loc_pass);
@@ -212,6 +214,7 @@ __global__ void k2_decode(ScanParams sp, const int64_t* __restrict__ chunk_start
         if (loc_seq) atomicAdd(&st->seq_bytes, loc_seq);
         if (loc_maxend) atomicMax(&st->max_end, loc_maxend);
         if (loc_minstart != ~0ull) atomicMin(&st->min_start, loc_minstart);
+        if (loc_maxstart) atomicMax(&st->max_start, loc_maxstart);
     }
 }
 

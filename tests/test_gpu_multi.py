@@ -1,0 +1,93 @@
+"""Multi-GPU sharding: BGZF virtual-offset shards cut at BAI linear-index record starts, one process
+per GPU, boundary counters exchanged with NCCL send/recv inside the library.  Needs >= 2 GPUs."""
+import multiprocessing as mp
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import helpers
+
+pytestmark = pytest.mark.gpu
+
+
+def _n_gpus():
+    try:
+        import sambamba_b200 as sb
+        return sb.load_library().bdepth_device_count()
+    except Exception:
+        return 0
+
+
+def _rank_main(rank, world, path, uid, mode, q):
+    try:
+        sys.path.insert(0, helpers.ROOT)
+        import sambamba_b200 as sb
+        with sb.BDepth(path, device=rank) as b:
+            b.set_shard(rank, world, uid)
+            if mode == "base":
+                got = b.run_base()
+                st = b.stats()
+                lo, hi = st["own_lo"], st["own_hi"]
+                q.put((rank, "ok", lo, hi, got[:, lo:hi].copy(), st))
+            else:
+                rows = b.run_windows(1000, 0, [1, 10])
+                q.put((rank, "ok", 0, 0, rows, b.stats()))
+    except Exception as e:  # pragma: no cover
+        q.put((rank, "err", 0, 0, repr(e), None))
+
+
+def _run(world, path, mode):
+    import sambamba_b200 as sb
+    uid = sb.nccl_unique_id()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    ps = [ctx.Process(target=_rank_main, args=(r, world, path, uid, mode, q)) for r in range(world)]
+    for p in ps:
+        p.start()
+    res = [q.get(timeout=300) for _ in range(world)]
+    for p in ps:
+        p.join(timeout=60)
+    res.sort(key=lambda r: r[0])
+    for r in res:
+        assert r[1] == "ok", r
+    return res
+
+
+@pytest.fixture(scope="module")
+def bam(tmp_path_factory):
+    d = tmp_path_factory.mktemp("multi")
+    return helpers.gen_bam(str(d / "m.bam"), "-r", "chrA:2000000", "-r", "chrB:700", "-r", "chrC:1500000", "-n", 300000, "-s", 11, "-t", 8)
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_sharded_base_equals_oracle(bam, world):
+    if _n_gpus() < world:
+        pytest.skip(f"needs {world} GPUs")
+    want, ost = helpers.oracle_counts(bam)
+    res = _run(world, bam, "base")
+    got = np.zeros_like(want)
+    prev_hi = 0
+    total_records = 0
+    for rank, _, lo, hi, arr, st in res:
+        assert lo == prev_hi or hi == lo, "owned ranges must tile the genome in rank order"
+        got[:, lo:hi] = arr
+        prev_hi = max(prev_hi, hi)
+        total_records += st["n_records"]
+    assert prev_hi == want.shape[1]
+    assert total_records == ost.n_records, "every record belongs to exactly one shard"
+    assert np.array_equal(got, want)
+    assert sum(r[5]["covered_positions"] for r in res) == int((want.sum(axis=0) > 0).sum())
+    assert any(r[5]["halo_bytes_sent"] > 0 for r in res), "reads straddling a shard boundary must be exchanged"
+
+
+def test_sharded_windows_equal_single_gpu(bam):
+    if _n_gpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    import sambamba_b200 as sb
+    with sb.BDepth(bam) as b:
+        want = b.run_windows(1000, 0, [1, 10])
+    res = _run(2, bam, "windows")
+    for r in res:
+        assert r[4] == want      # the statistics are all-reduced, so every rank holds the full table
