@@ -1,0 +1,97 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/bdepth.h declares (no compute
+calls), the product path fails loudly without a GPU, and host-only logic (shard planning, BED handling in the
+CLI) behaves.  No GPU needed."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import pytest
+
+import helpers
+from helpers import GOLDEN, ROOT
+
+
+def test_library_exports_every_declared_symbol():
+    import sambamba_b200 as sb
+    from sambamba_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "bdepth.h")).read()
+    declared = set(re.findall(r"\b(bdepth_[a-z_0-9]+)\s*\(", hdr)) - {"bdepth_tile_cb", "bdepth_stat_cb"}
+    L = C.CDLL(sb.lib_path())
+    for name in sorted(declared):
+        assert hasattr(L, name), f"libbdepth.so does not export {name}"
+    assert declared == set(_lib.EXPORTED_SYMBOLS), declared ^ set(_lib.EXPORTED_SYMBOLS)
+
+
+def _no_gpu():
+    import sambamba_b200 as sb
+    return sb.load_library().bdepth_device_count() == 0
+
+
+def test_no_cpu_fallback_without_gpu():
+    if not _no_gpu():
+        pytest.skip("a GPU is present")
+    import sambamba_b200 as sb
+    with pytest.raises(sb.BDepthError) as e:
+        sb.BDepth(os.path.join(GOLDEN, "issue_193.bam"))
+    assert e.value.code == -5 and "no CPU fallback" in e.value.msg
+    rc, out, err = helpers.run_cli(["depth", "base", os.path.join(GOLDEN, "issue_193.bam")])
+    assert rc == 1 and err.startswith(b"sambamba-depth: ") and b"no CPU fallback" in err
+
+
+def test_product_sources_never_touch_the_oracle():
+    for root, _, files in os.walk(os.path.join(ROOT, "sambamba_b200")):
+        for f in files:
+            if f.endswith((".cu", ".cuh", ".cpp", ".hpp", ".py", ".h", ".d")):
+                txt = open(os.path.join(root, f), errors="ignore").read()
+                assert "oracle/" not in txt and "liboracle" not in txt and "depth_oracle" not in txt, f
+    assert "oracle" not in open(os.path.join(ROOT, "include", "bdepth.h")).read()
+
+
+def test_cli_usage_and_argument_errors_need_no_gpu():
+    rc, out, err = helpers.run_cli([])
+    assert rc == 0 and b"Usage: sambamba-depth region|window|base" in err
+    rc, out, err = helpers.run_cli(["depth", "frobnicate", "x.bam"])
+    assert rc == 0 and b"Usage:" in err
+    rc, out, err = helpers.run_cli(["depth", "region", "x.bam"])
+    assert rc == 1 and b"BED file or a region must be provided in region mode" in err
+    rc, out, err = helpers.run_cli(["depth", "window", "x.bam"])
+    assert rc == 1 and b"positive window size must be specified" in err
+    rc, out, err = helpers.run_cli(["depth", "window", "-w", "10", "--overlap", "10", "x.bam"])
+    assert rc == 1 and b"specified overlap is larger than window size" in err
+    rc, out, err = helpers.run_cli(["depth", "base", "-m", "x.bam"])
+    assert rc == 1 and b"not available in the GPU engine yet" in err
+    rc, out, err = helpers.run_cli(["depth", "base", "/nonexistent/x.bam"])
+    assert rc == 1 and b"Cannot open file" in err
+
+
+def test_shard_plan_is_a_partition_at_record_starts(tmp_path):
+    """bdepth_plan_shards is host-only: boundaries must be BAI linear-index record starts, increasing, and each
+    must be the start of a record in the inflated stream."""
+    import sambamba_b200 as sb
+    p = helpers.gen_bam(str(tmp_path / "s.bam"), "-r", "chrA:900000", "-r", "chrB:600000", "-n", 60000, "-s", 3, "-t", 2)
+    u = helpers.oracle_inflate(p)
+    first, _ = helpers.header_first_record_offset(u)
+    starts = {r[0] for r in helpers.parse_records(u, first)}
+    # block table: compressed offset -> inflated offset
+    raw = open(p, "rb").read()
+    off, uoff, table = 0, 0, {}
+    while off + 18 <= len(raw):
+        bs = int.from_bytes(raw[off + 16:off + 18], "little") + 1
+        isz = int.from_bytes(raw[off + bs - 4:off + bs], "little")
+        if isz == 0:
+            break
+        table[off] = uoff
+        uoff += isz
+        off += bs
+    for world in (2, 3, 4, 8):
+        cuts = sb.plan_shards(p, world)
+        assert len(cuts) == world - 1
+        real = [c for c in cuts if c != 2 ** 64 - 1]
+        assert real == sorted(real)
+        for k, vo in enumerate(cuts, start=1):
+            if vo == 2 ** 64 - 1:
+                continue
+            assert (vo >> 16) in table, "boundary must point at a BGZF block start"
+            assert table[vo >> 16] + (vo & 0xFFFF) in starts, "boundary must be a record start"
+            assert (vo >> 16) >= k * len(raw) // world - 70000

@@ -1,0 +1,141 @@
+"""Pins the CPU oracle (oracle/depth_oracle.c) on the reference's own golden vectors:
+test/test_suite.sh:149-154 (issue_193), :156-162 (issue_204), :176-194 (issue225), and the column
+known-answer test in BioD/bio/std/hts/bam/pileup.d:699-857.  No GPU needed."""
+import os
+import struct
+import zlib
+
+import numpy as np
+import pytest
+
+import helpers
+from helpers import GOLDEN
+
+
+def G(f):
+    return os.path.join(GOLDEN, f)
+
+
+def test_issue_193_depth_base():
+    rc, out, err = helpers.oracle_cli(["base", G("issue_193.bam")])
+    assert rc == 0
+    assert out == open(G("issue_193_expected_output.txt"), "rb").read()
+    assert b"Processing reference #1" in err
+
+
+def test_issue_225_depth_base_with_and_without_L():
+    for extra in ([], ["-L", "chrM"]):
+        rc, out, _ = helpers.oracle_cli(["base", "-c", "1"] + extra + [G("issue225.bam")])
+        assert rc == 0 and out == open(G("issue225.out"), "rb").read(), extra
+        rc, out, _ = helpers.oracle_cli(["base", "-c", "0"] + extra + [G("issue225.bam")])
+        assert rc == 0 and out == open(G("issue225.z.out"), "rb").read(), extra
+
+
+def test_issue_204_region_fix_mate_overlaps():
+    rc, out, _ = helpers.oracle_cli(["region", G("issue_204.bam"), "-L", "2:166868600-166868813", "-T", "15", "-T", "20", "-T", "25", "-m"])
+    assert rc == 0
+    assert out == open(G("issue_204_expected_output.txt"), "rb").read()
+
+
+def test_closed_form_equals_sweep_on_all_fixtures(tmp_path):
+    """The per-read scatter oracle (used at full size) must agree with the column sweep (pinned above)."""
+    files = [G(f) for f in ("issue_193.bam", "issue225.bam", "issue_204.bam", "mate_overlaps_1_3M_4M.bam")]
+    files.append(helpers.gen_bam(str(tmp_path / "t.bam"), "--preset", "tiny", "-t", 2))
+    for p in files:
+        for minq in (0, 25):
+            win = helpers.interesting_window(p)
+            counts, _ = helpers.oracle_counts(p, min_bq=minq, window=win)
+            rc, out, _ = helpers.oracle_cli(["base", "-q", str(minq), p])
+            assert rc == 0
+            # rows: REF POS COV A C G T DEL REFSKIP SAMPLE ; N = COV - (A+C+G+T+DEL+REFSKIP)
+            with helpers_refs(p) as lin0:
+                seen = 0
+                for line in out.splitlines()[1:]:
+                    f = line.split(b"\t")
+                    g = lin0[f[0].decode()] + int(f[1]) - win[0]
+                    a, c, gg, t, d, s = (int(x) for x in f[3:9])
+                    cov = int(f[2])
+                    col = counts[:, g]
+                    assert (col[0], col[1], col[2], col[3], col[5], col[6]) == (a, c, gg, t, d, s), (p, line)
+                    assert int(col.sum()) == cov, (p, line)
+                    seen += 1
+                assert seen == int((counts.sum(axis=0) > 0).sum()), p
+
+
+class helpers_refs:
+    def __init__(self, path):
+        u = helpers.oracle_inflate(path)
+        _, refs = helpers.header_first_record_offset(u)
+        self.lin0, lin = {}, 0
+        for name, L in refs:
+            self.lin0[name] = lin
+            lin += L
+
+    def __enter__(self):
+        return self.lin0
+
+    def __exit__(self, *a):
+        return False
+
+
+# ---- the pileup.d unittest reads (BioD/bio/std/hts/bam/pileup.d:703-740) written as a BAM by hand
+SEQS = ["ATTATGGACATTGTTTCCGTTATCATCATCATCATCATCATCATCATTATCATC", "GACATTGTTTCCGTTATCATCATCATCATCATCATCATCATCATCATCATCATC",
+        "ATTGTTTCCGTTATCATCATCATCATCATCATCATCATCATCATCATCATCACC", "TGTTTCCGTTATCATCATCATCATCATCATCATCATCATCATCATCATCACCAC",
+        "TCCGTTATCATCATCATCATCATCATCATCATCATCATCATCATCACCACCACC", "GTTATCATCATCATCATCATCATCATCATCATCATCATCATCATCGTCACCCTG",
+        "TCATCATCATCATAATCATCATCATCATCATCATCATCGTCACCCTGTGTTGAG", "TCATCATCATCGTCACCCTGTGTTGAGGACAGAAGTAATTTCCCTTTCTTGGCT",
+        "TCATCATCATCATCACCACCACCACCCTGTGTTGAGGACAGAAGTAATATCCCT", "CACCACCACCCTGTGTTGAGGACAGAAGTAATTTCCCTTTCTTGGCTGGTCACC"]
+CIGARS = [[(54, 0)], [(54, 0)], [(50, 0), (3, 1), (1, 0)], [(54, 0)], [(54, 0)], [(54, 0)], [(2, 4), (52, 0)],
+          [(16, 0), (15, 2), (38, 0)], [(13, 0), (3, 1), (38, 0)], [(54, 0)]]
+POS = [758, 764, 767, 769, 773, 776, 785, 795, 804, 817]
+
+
+def write_bam(path, refs, reads, rg=None):
+    """Minimal BAM + dummy BAI writer for hand-made reads: (ref, pos, mapq, flag, cigar[(len,op)], seq, name)."""
+    text = "@HD\tVN:1.6\tSO:coordinate\n" + "".join(f"@SQ\tSN:{n}\tLN:{l}\n" for n, l in refs)
+    if rg:
+        text += "".join(f"@RG\tID:{i}\tSM:{s}\n" for i, s in rg)
+    body = b"BAM\1" + struct.pack("<i", len(text)) + text.encode() + struct.pack("<i", len(refs))
+    for n, l in refs:
+        body += struct.pack("<i", len(n) + 1) + n.encode() + b"\0" + struct.pack("<i", l)
+    code = {c: i for i, c in enumerate("=ACMGRSVTWYHKDBN")}
+    for ref, pos, mapq, flag, cigar, seq, name in reads:
+        nm = name.encode() + b"\0"
+        packed = bytearray()
+        for i in range(0, len(seq), 2):
+            packed.append((code[seq[i]] << 4) | (code[seq[i + 1]] if i + 1 < len(seq) else 0))
+        rec = struct.pack("<iiIIiiii", ref, pos, (4680 << 16) | (mapq << 8) | len(nm), (flag << 16) | len(cigar), len(seq), -1, -1, 0)
+        rec += nm + b"".join(struct.pack("<I", (l << 4) | op) for l, op in cigar) + bytes(packed) + bytes([30] * len(seq))
+        body += struct.pack("<i", len(rec)) + rec
+    with open(path, "wb") as f:
+        for i in range(0, len(body), 0xFF00):
+            chunk = body[i:i + 0xFF00]
+            c = zlib.compressobj(6, zlib.DEFLATED, -15)
+            d = c.compress(chunk) + c.flush()
+            f.write(b"\x1f\x8b\x08\x04\0\0\0\0\0\xff\x06\0BC\x02\0" + struct.pack("<H", len(d) + 25) + d + struct.pack("<II", zlib.crc32(chunk), len(chunk)))
+        f.write(bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000"))
+    with open(path + ".bai", "wb") as f:      # empty-but-valid index: depth only checks that it exists (depth.d:1166)
+        f.write(b"BAI\1" + struct.pack("<i", len(refs)) + b"".join(struct.pack("<ii", 0, 0) for _ in refs) + struct.pack("<Q", 0))
+    return path
+
+
+def test_pileup_unittest_columns(tmp_path):
+    reads = [(0, POS[i], 60, 0, CIGARS[i], SEQS[i], f"r{i}") for i in range(10)]
+    p = write_bam(str(tmp_path / "u.bam"), [("20", 2000)], reads)
+    rc, out, _ = helpers.oracle_cli(["base", p])
+    assert rc == 0
+    rows = {int(l.split(b"\t")[1]): [int(x) for x in l.split(b"\t")[2:9]] for l in out.splitlines()[1:]}
+
+    def bases(s):   # expected column string -> (COV, A, C, G, T, DEL, REFSKIP)
+        return [len(s), s.count("A"), s.count("C"), s.count("G"), s.count("T"), s.count("-"), 0]
+    # pileup.d:806-840: the column strings asserted by the reference's own unit test
+    assert rows[796] == bases("CCCCCCAC")
+    assert rows[805] == bases("TCCCCCCCC")
+    assert rows[806] == bases("AAAAAAAGA")
+    assert rows[821] == bases("AAGG-AA")
+    assert rows[826] == bases("CCCCCC")
+    assert rows[849] == bases("TAT")
+    # and the closed form agrees
+    counts, _ = helpers.oracle_counts(p)
+    for pos, r in rows.items():
+        col = counts[:, pos]
+        assert [int(col.sum()), col[0], col[1], col[2], col[3], col[5], col[6]] == r
