@@ -114,7 +114,7 @@ struct bdepth {
     cudaStream_t s_main = nullptr, s_copy = nullptr, s_d2h = nullptr;
     cudaEvent_t ev[32] = {};
     DevBuf comp2[2];
-    cudaStream_t s_k1[4] = {};                        // K1 sub-launches of one batch run side by side
+    cudaStream_t s_k1[16] = {};                       // K1 sub-launches of one batch run side by side (one stream each)
     std::vector<cudaEvent_t> chunk_ev[2], k1_ev;      // per H2D chunk (per slot) / per K1 sub-launch
     std::vector<size_t> chunk_end[2];                  // block index (exclusive) covered by each H2D chunk of a slot
     bool staged = false; uint64_t staged_file_off = 0;
@@ -430,7 +430,7 @@ int run_pipeline(bdepth* h, RunMode mode, RunOut* ro, Emitter* em = nullptr) {
     size_t batch_no = 0;
     auto batch_end = [&](size_t bb) { size_t e = bb; uint64_t u = 0; while (e < h->blk_hi && (e == bb || u + B[e].isize <= h->batch_u)) { u += B[e].isize; e++; } return e; };
     // H2D of blocks [bb, be) into comp2[slot]; waits until K1 of the batch that used the slot two batches ago is done
-    constexpr size_t H2D_CHUNK_BLOCKS = 8192;      // ~320 MB of compressed data, 256 K1 warps per sub-launch
+    constexpr size_t H2D_CHUNK_BLOCKS = 13 * 32 * 16;   // 6656 blocks = 16 K1 CTAs (13 warps each) per sub-launch, ~260 MB of compressed data
     auto issue_h2d = [&](size_t no, size_t bb, size_t be) -> int {
         int slot = (int)(no & 1);
         uint64_t g0 = B[bb].coff & ~3ull;
@@ -485,7 +485,7 @@ int run_pipeline(bdepth* h, RunMode mode, RunOut* ro, Emitter* em = nullptr) {
         } else {
             int slot = (int)(batch_no & 1); size_t c0 = b;
             for (size_t j = 0; j < h->chunk_end[slot].size(); j++) {
-                size_t c1 = h->chunk_end[slot][j]; cudaStream_t ks = h->s_k1[j & 3];
+                size_t c1 = h->chunk_end[slot][j]; cudaStream_t ks = h->s_k1[j & 15];
                 CK(cudaStreamWaitEvent(ks, e1, 0)); CK(cudaStreamWaitEvent(ks, h->chunk_ev[slot][j], 0));
                 uint32_t n = (uint32_t)(c1 - c0);
                 k1_inflate<<<(n + 32 * K1_WARPS - 1) / (32 * K1_WARPS), 32 * K1_WARPS, K1_SMEM, ks>>>(d_comp, h->descs.as<BlockDesc>() + (c0 - b), n, u0, h->status.as<int>() + (c0 - b));

@@ -20,12 +20,14 @@
 //    and every iteration ends in a ballot that re-converges the warp.
 //  * Output is assembled a 32-bit word at a time in a register; complete words go to a 16-word
 //    per-lane ring in shared memory, complete 16-byte lines leave as one aligned 16-byte global
-//    store.  Matches at distance 8..56 are served from the ring, farther ones from global memory
-//    (two aligned word loads + funnel shift); the loaded word is appended one iteration later,
-//    after the next symbol has been decoded, so the L2 round trip overlaps the Huffman arithmetic.
+//    store.  Matches at distance 8..24 are served from the ring, farther ones from global memory with two
+//    4-byte cp.async copies into shared memory that are consumed one iteration later, after the next symbol
+//    has been decoded, so the L2/DRAM round trip overlaps the Huffman arithmetic.  The compressed input arrives
+//    through a two-slot 16-byte cp.async FIFO per lane.
 //    Distances below 8 (run-length style) take a byte-serial path.
 //  per lane: 288 x 10-bit litlen symbols (96 w) + 15 x i16 delta (8 w) + 32 x u8 dist symbols
-//            (8 w) + delta (8 w) + ring (16 w) = 136 words = 544 B; 17 KB per warp; 12 warps/SM.
+//            (8 w) + delta (8 w) + ring (8 w) + far landing zone (2 w) = 130 words, + 32 B input FIFO
+//            = 552 B; 17.25 KB per warp; 12 warps/SM.
 //
 // The code is __host__ __device__ so the exact same logic is unit-tested on the CPU against zlib
 // (tests/test_emul_inflate.py); the product only ever calls it from kernels.
@@ -67,16 +69,33 @@ constexpr int T_LL_SYMS = 0;       // 288 x 10 bit, three per word
 constexpr int T_LL_DELTA = 96;     // 15 x i16 (index len-1), padded to 16
 constexpr int T_D_SYMS = 104;      // 32 x u8
 constexpr int T_D_DELTA = 112;     // 15 x i16
-constexpr int T_RING = 120;        // output ring: the last 16 complete words
-constexpr int RING_WORDS = 16;
-constexpr int T_WORDS = T_RING + RING_WORDS;   // 136
-constexpr uint32_t NEAR_MAX = 4 * (RING_WORDS - 1) - 4;   // 56: farthest distance served from the ring
+constexpr int T_RING = 120;        // output ring: the last 8 complete words
+constexpr int RING_WORDS = 8;
+constexpr int T_FAR = T_RING + RING_WORDS;     // 2 words: landing zone of the asynchronous far-match fetch
+constexpr int T_WORDS = T_FAR + 2;             // 130 lane-interleaved words
+constexpr int FIFO_BYTES_PER_LANE = 32;        // two 16-byte slots of compressed input per lane (lane-major, after the interleaved words)
+constexpr int SMEM_BYTES_PER_WARP = T_WORDS * 128 + 32 * FIFO_BYTES_PER_LANE;   // 17,664 B -> 12 warps per SM
+constexpr uint32_t NEAR_MAX = 4 * (RING_WORDS - 1) - 4;   // 24: farthest distance served from the ring
 
 // ---- table storage policies -------------------------------------------------------------
 // Lane-interleaved shared memory: word w of this lane lives at base[w * 32]; every lane always
 // hits its own bank, so data-dependent indices never conflict.
+#if defined(__CUDA_ARCH__)
+// Ampere-style asynchronous copies (LDGSTS).  Their completion is tracked by cp.async groups, NOT by the register
+// scoreboard, so a copy issued at the end of one loop iteration is still in flight at the top of the next; plain
+// loads whose result crosses the loop back-edge are waited for at the back-edge by the compiler (that wait was
+// 30 % of all stall samples in profiles/r1_k1_inflate_ncu_full_summary.txt).
+__device__ __forceinline__ void cp_async16(uint32_t saddr, const void* g) { asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(saddr), "l"(g) : "memory"); }
+__device__ __forceinline__ void cp_async4(uint32_t saddr, const void* g) { asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(saddr), "l"(g) : "memory"); }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+__device__ __forceinline__ uint32_t lds32(uint32_t saddr) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr) : "memory"); return v; }
+#endif
+
 struct SmemTab {
     uint32_t* base;
+    uint32_t fifo_sa;      // shared-space address of this lane's input slot 0 (slot 1 at +512)
+    uint32_t far_sa;       // shared-space address of this lane's far-fetch word 0 (word 1 at +128)
     BD_HD uint32_t ldw(int w) const { return base[w * 32]; }
     BD_HD void stw(int w, uint32_t v) const { base[w * 32] = v; }
     BD_HD uint32_t ring_ldw(uint32_t widx) const { return base[(T_RING + (widx & (RING_WORDS - 1))) * 32]; }
@@ -85,6 +104,7 @@ struct SmemTab {
 // Plain array (host tests).
 struct FlatTab {
     uint32_t* base;
+    uint32_t fifo_sa = 0, far_sa = 0;
     BD_HD uint32_t ldw(int w) const { return base[w]; }
     BD_HD void stw(int w, uint32_t v) const { base[w] = v; }
     BD_HD uint32_t ring_ldw(uint32_t widx) const { return base[T_RING + (widx & (RING_WORDS - 1))]; }
@@ -141,14 +161,41 @@ BD_HD uint32_t bitrev32(uint32_t x) {
 #endif
 }
 
-// ---- bit reader: 64-bit reservoir fed by aligned 32-bit words, next word always prefetched --
+// ---- bit reader: 64-bit reservoir.  On the device the compressed bytes arrive through a two-slot, 16-byte
+// cp.async FIFO in shared memory (every 32-byte DRAM sector is fetched once or twice instead of eight times,
+// 16-32 bytes ahead of use); on the host (tests) it reads the words directly.
 struct BitReader {
+    uint64_t bb;
+    int bc;
+#if defined(__CUDA_ARCH__)
+    const uint8_t* gnext;   // next 16-byte chunk to prefetch
+    uint32_t fifo_sa, widx, consumed, limit_words;
+    __device__ __forceinline__ uint32_t next_word() {
+        if ((widx & 3) == 0) cp_async_wait<1>();       // entering a slot: its refill is older than the newest group
+        uint32_t slot = fifo_sa + ((widx & 4) ? 512u : 0u);
+        uint32_t w = lds32(slot + (widx & 3) * 4);
+        if ((widx & 3) == 3) { cp_async16(slot, gnext); cp_async_commit(); gnext += 16; }
+        widx = (widx + 1) & 7; consumed++;
+        return w;
+    }
+    __device__ __forceinline__ void init(const uint32_t* words, uint64_t byte_off, uint32_t nbytes, uint32_t fifo_shared_addr) {
+        const uint8_t* g0 = reinterpret_cast<const uint8_t*>(words) + (byte_off & ~15ull);
+        fifo_sa = fifo_shared_addr;
+        cp_async16(fifo_sa, g0); cp_async_commit(); cp_async16(fifo_sa + 512, g0 + 16); cp_async_commit();
+        gnext = g0 + 32; cp_async_wait<0>();
+        widx = (uint32_t)(byte_off & 15) >> 2; consumed = 0;
+        limit_words = (uint32_t)(((byte_off & 15) + nbytes + 3) >> 2) + 3;
+        unsigned mis = (unsigned)(byte_off & 3);
+        bb = (uint64_t)next_word() >> (8 * mis);
+        bc = 32 - 8 * (int)mis;
+    }
+    __device__ __forceinline__ void refill() { if (bc <= 32) { bb |= (uint64_t)next_word() << bc; bc += 32; } }   // afterwards bc >= 33
+    __device__ __forceinline__ bool overrun() const { return consumed > limit_words; }
+#else
     const uint32_t* wp;     // address of the prefetched word
     const uint32_t* wend;   // one past the last word that may contain stream bits
-    uint64_t bb;
-    uint32_t nw;            // prefetched next word
-    int bc;
-    BD_HD void init(const uint32_t* words, uint64_t byte_off, uint32_t nbytes) {
+    uint32_t nw;
+    void init(const uint32_t* words, uint64_t byte_off, uint32_t nbytes, uint32_t) {
         wp = words + (byte_off >> 2);
         wend = words + ((byte_off + nbytes + 3) >> 2);
         unsigned mis = (unsigned)(byte_off & 3);
@@ -156,14 +203,12 @@ struct BitReader {
         bc = 32 - 8 * (int)mis;
         nw = *wp;
     }
-    BD_HD void refill() {   // afterwards bc >= 33
-        if (bc <= 32) { bb |= (uint64_t)nw << bc; bc += 32; nw = *++wp; }
-    }
+    void refill() { if (bc <= 32) { bb |= (uint64_t)nw << bc; bc += 32; nw = *++wp; } }
+    bool overrun() const { return wp > wend + 3; }
+#endif
     BD_HD uint32_t peek(int n) const { return (uint32_t)bb & ((1u << n) - 1u); }
     BD_HD void drop(int n) { bb >>= n; bc -= n; }
     BD_HD uint32_t get(int n) { uint32_t v = peek(n); drop(n); return v; }
-    // the reservoir + prefetch run at most three words past the last stream word
-    BD_HD bool overrun() const { return wp > wend + 3; }
 };
 
 // Left-justified 15-bit limits, index len-1 (v[14] == 32768 for a complete code), built in next_block.
@@ -436,7 +481,7 @@ BD_HD int inflate_block(const Tab& t, const uint32_t* words, uint64_t byte_off, 
     if (!active) return INF_OK;
     uint8_t* lens = reinterpret_cast<uint8_t*>(scratch);
     uint32_t* limpk = scratch + 80;
-    BitReader br; br.init(words, byte_off, nbytes);
+    BitReader br; br.init(words, byte_off, nbytes, t.fifo_sa);
     HuffPk ll, dd;
 #pragma unroll
     for (int i = 0; i < 8; i++) { ll.pk[i] = 0; dd.pk[i] = 0; }
@@ -447,7 +492,7 @@ BD_HD int inflate_block(const Tab& t, const uint32_t* words, uint64_t byte_off, 
     // In-flight bytes: every byte (literal or copied) is appended ONE ITERATION LATER, at the single append site
     // below.  For far matches p_w0/p_w1 are the raw loaded words; they are first touched after the next symbol
     // has been decoded, so the L2 round trip overlaps the Huffman arithmetic.
-    uint32_t p_w0 = 0, p_w1 = 0, p_sh = 0, p_n = 0;
+    uint32_t p_w0 = 0, p_w1 = 0, p_sh = 0, p_n = 0; bool p_far = false;
     for (;;) {
         BD_STAT(g_inflate_stats.iters++);
         int sym = -1; bool have_sym = false;
@@ -471,6 +516,9 @@ BD_HD int inflate_block(const Tab& t, const uint32_t* words, uint64_t byte_off, 
         }
         // ---- A: the single append site
         if (p_n) {
+#if defined(__CUDA_ARCH__)
+            if (p_far) { cp_async_wait<0>(); p_w0 = lds32(t.far_sa); p_w1 = lds32(t.far_sa + 128); p_far = false; }
+#endif
             uint32_t d = funnel_r(p_w0, p_w1, p_sh);
             if (p_n < 4) d &= (1u << (8 * p_n)) - 1u;
             append_bytes(t, out, os, a0, d, p_n);
@@ -518,7 +566,14 @@ BD_HD int inflate_block(const Tab& t, const uint32_t* words, uint64_t byte_off, 
                 // the 4 source bytes lie entirely in complete words: two aligned words + funnel shift (done at A)
                 uint64_t S = head - m_dist; uint32_t sw = (uint32_t)(S >> 2);
                 if (m_dist <= NEAR_MAX) { p_w0 = t.ring_ldw(sw); p_w1 = t.ring_ldw(sw + 1); }
-                else { p_w0 = out.getw(sw); p_w1 = out.getw((uint64_t)sw + 1); }
+                else {
+#if defined(__CUDA_ARCH__)
+                    const uint32_t* gsrc = reinterpret_cast<const uint32_t*>(out.p) + sw;       // asynchronous: lands in shared memory, read at A
+                    cp_async4(t.far_sa, gsrc); cp_async4(t.far_sa + 128, gsrc + 1); cp_async_commit(); p_far = true;
+#else
+                    p_w0 = out.getw(sw); p_w1 = out.getw((uint64_t)sw + 1);
+#endif
+                }
                 p_sh = ((uint32_t)S & 3) * 8;
             } else {
                 // run-length style.  H = the 8 bytes before head (hi = most recent 4), from the word being filled

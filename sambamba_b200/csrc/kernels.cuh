@@ -39,9 +39,13 @@ struct BlockDesc {
     uint32_t isize;
 };
 
-constexpr int K1_WARPS = 1;                                   // one warp per CTA; 12 CTAs per SM (17 KB + 1 KB each)
-constexpr int K1_SMEM = K1_WARPS * T_WORDS * 32 * 4;           // 17,408 B
-__global__ void __launch_bounds__(K1_WARPS * 32, 12) k1_inflate(const uint32_t* __restrict__ comp, const BlockDesc* __restrict__ blocks,
+// One CTA of 13 warps per SM: 13 x 17,664 B = 229,632 B of dynamic shared memory (the per-CTA 1 KB system
+// reservation is paid once, which is what lets a 13th warp fit).  148 x 13 x 32 = 61,568 BGZF blocks in flight:
+// a 30x chromosome (57.6 k blocks) is a single wave with no tail (12 one-warp CTAs per SM left 5 warps for a
+// second wave that cost 35 % of the kernel time, profiles/k1_history.md).
+constexpr int K1_WARPS = 13;
+constexpr int K1_SMEM = K1_WARPS * SMEM_BYTES_PER_WARP;         // 229,632 B
+__global__ void __launch_bounds__(K1_WARPS * 32, 1) k1_inflate(const uint32_t* __restrict__ comp, const BlockDesc* __restrict__ blocks,
                                                                uint32_t n_blocks, uint8_t* __restrict__ u, int* __restrict__ status) {
     extern __shared__ uint32_t smem[];
     uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -49,17 +53,24 @@ __global__ void __launch_bounds__(K1_WARPS * 32, 12) k1_inflate(const uint32_t* 
     uint32_t scratch[96];
     const bool active = b < n_blocks;
     BlockDesc d = active ? blocks[b] : BlockDesc{0, 0, 0, 0};
-    SmemTab tab{smem + warp * (T_WORDS * 32) + lane};
+    uint32_t* wbase = smem + warp * (SMEM_BYTES_PER_WARP / 4);
+    SmemTab tab{wbase + lane, (uint32_t)__cvta_generic_to_shared(wbase + T_WORDS * 32) + lane * 16, (uint32_t)__cvta_generic_to_shared(wbase + T_FAR * 32 + lane)};
     ByteOut out{u};
     int rc = inflate_block(tab, comp, d.coff, d.csize, out, d.uoff, d.isize, scratch, active);
     if (active) status[b] = rc;
 }
 
 // ------------------------------------------------------------------------------------- K2
+// Unaligned little-endian loads from the inflated stream: two aligned 32-bit loads + funnel shift (records are
+// byte-aligned; four byte loads per field made k2_decode LSU-queue bound: profiles/r1_k2_k3_ncu_full_summary.txt).
+// The buffer has >= 256 readable bytes after its end, so touching the following word is always legal.
 __device__ __forceinline__ uint32_t ldu32(const uint8_t* p) {
-    return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
+    uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(a & ~uintptr_t(3));
+    uint32_t lo = __ldg(w), hi = __ldg(w + 1);
+    return __funnelshift_r(lo, hi, (uint32_t)(a & 3) * 8);
 }
-__device__ __forceinline__ uint32_t ldu16(const uint8_t* p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8); }
+__device__ __forceinline__ uint32_t ldu16(const uint8_t* p) { return ldu32(p) & 0xFFFFu; }
 
 struct ScanParams {
     const uint8_t* u;          // inflated stream; offsets below are relative to it (may be negative for the carry)
@@ -168,12 +179,17 @@ __global__ void k2_decode(ScanParams sp, const int64_t* __restrict__ chunk_start
     const uint16_t* sl = slots + slot_base[warp];
     uint32_t rb = rec_base[warp];
     unsigned long long loc_pass = 0, loc_cig = 0, loc_seq = 0, loc_maxend = 0, loc_minstart = ~0ull, loc_maxstart = 0;
+    uint32_t has_word = 0xFFFFFFFFu, has_bits = 0;      // per-lane pending "reference has reads" bits (one atomic per warp, not per read)
     for (uint32_t k = lane; k < n; k += 32) {
         int64_t o = c0 + sl[k];
         const uint8_t* p = sp.u + o + 4;
-        int32_t ref = (int32_t)ldu32(p), pos = (int32_t)ldu32(p + 4);
-        uint32_t bmn = ldu32(p + 8), fnc = ldu32(p + 12);
-        int32_t l_seq = (int32_t)ldu32(p + 16);
+        // refID, pos, bin_mq_nl, flag_nc, l_seq: 20 consecutive bytes = 6 aligned words + 5 funnel shifts
+        uintptr_t pa = reinterpret_cast<uintptr_t>(p);
+        const uint32_t* pw = reinterpret_cast<const uint32_t*>(pa & ~uintptr_t(3)); uint32_t psh = (uint32_t)(pa & 3) * 8;
+        uint32_t h0 = __ldg(pw), h1 = __ldg(pw + 1), h2 = __ldg(pw + 2), h3 = __ldg(pw + 3), h4 = __ldg(pw + 4), h5 = __ldg(pw + 5);
+        int32_t ref = (int32_t)__funnelshift_r(h0, h1, psh), pos = (int32_t)__funnelshift_r(h1, h2, psh);
+        uint32_t bmn = __funnelshift_r(h2, h3, psh), fnc = __funnelshift_r(h3, h4, psh);
+        int32_t l_seq = (int32_t)__funnelshift_r(h4, h5, psh);
         uint32_t l_name = bmn & 0xFF, mapq = (bmn >> 8) & 0xFF, flag = fnc >> 16, n_cigar = fnc & 0xFFFF;
         const uint8_t* cg = p + 32 + l_name;
         uint64_t span = 0;
@@ -198,9 +214,16 @@ __global__ void k2_decode(ScanParams sp, const int64_t* __restrict__ chunk_start
             if (start + span_eff > loc_maxend) loc_maxend = start + span_eff;
             if (start < loc_minstart) loc_minstart = start;
             if (start > loc_maxstart) loc_maxstart = start;
-            atomicOr(&ref_has_reads[ref >> 5], 1u << (ref & 31));
+            if ((uint32_t)(ref >> 5) != has_word) { if (has_bits) atomicOr(&ref_has_reads[has_word], has_bits); has_word = (uint32_t)(ref >> 5); has_bits = 0; }
+            has_bits |= 1u << (ref & 31);
             if (is_long) { uint32_t idx = (uint32_t)atomicAdd(&st->n_long, 1ull); long_list[idx] = r; }
         }
+    }
+    {   // flush the has-reads bits: in the common case the whole warp saw one bitmap word -> one atomic
+        uint32_t w0 = __shfl_sync(0xFFFFFFFFu, has_word, 0);
+        bool same = __all_sync(0xFFFFFFFFu, has_word == w0 || has_bits == 0);
+        if (same) { uint32_t allb = __reduce_or_sync(0xFFFFFFFFu, has_bits); uint32_t ww = __reduce_min_sync(0xFFFFFFFFu, has_bits ? has_word : 0xFFFFFFFFu); if (lane == 0 && allb) atomicOr(&ref_has_reads[ww], allb); }
+        else if (has_bits) atomicOr(&ref_has_reads[has_word], has_bits);
     }
     for (int s = 16; s; s >>= 1) {
         loc_pass += __shfl_xor_sync(0xFFFFFFFFu, loc_pass, s); loc_cig += __shfl_xor_sync(0xFFFFFFFFu, loc_cig, s); loc_seq += __shfl_xor_sync(0xFFFFFFFFu, loc_seq, s);
@@ -302,26 +325,49 @@ __global__ void __launch_bounds__(256) k3_gather(RecordSoA soa, const uint8_t* _
             const uint8_t* cg = rec + 32 + l_name;
             const uint8_t* seq = cg + 4u * n_cigar;
             const uint8_t* qual = seq + (lseq + 1) / 2;
-            int64_t rp = (int64_t)p0 - (int64_t)rs;        // reference offset of this lane's first position
-            uint32_t rpos = 0, qpos = 0;
-            for (uint32_t i = 0; i < n_cigar; i++) {
-                uint32_t c = ldu32(cg + 4 * i), len = c >> 4, op = c & 15;
-                if (cig_match(op)) {
+            const int32_t rp = (int32_t)((int64_t)p0 - (int64_t)rs);      // reference offset of this lane's first position (|rp| < span + 128)
+            const uint32_t c0 = ldu32(cg);
+            if (n_cigar == 1 && cig_match(c0 & 15)) {
+                // ---- fast path (90 % of short reads): one M/=/X op.  The 4 bases of this lane sit in at most 3
+                // sequence bytes: one unaligned 32-bit load, nibbles picked by shifts.
+                uint32_t L = min(min(c0 >> 4, rspan), lseq);
+                if (rp + 3 >= 0 && rp < (int32_t)L) {
+                    uint32_t xb = rp > 0 ? (uint32_t)rp : 0u, bq = xb >> 1;
+                    uint32_t w = ldu32(seq + bq), wq = 0;
+                    if (MINQ) wq = ldu32(qual + xb);
 #pragma unroll
                     for (int j = 0; j < 4; j++) {
-                        int64_t x = rp + j - (int64_t)rpos;
-                        if (x >= 0 && x < (int64_t)len && (uint64_t)(rp + j) < rspan) add_base<MINQ>(a, j, seq, qual, qpos + (uint32_t)x, lseq, minq);
+                        int32_t x = rp + j;
+                        if (x >= 0 && x < (int32_t)L) {
+                            bool okq = true;
+                            if (MINQ) okq = ((wq >> (8 * ((uint32_t)x - xb))) & 0xFFu) >= minq;
+                            uint32_t n = (uint32_t)x - 2 * bq;                       // nibble index inside w (0..7), high nibble first
+                            uint32_t nib = (w >> (8 * (n >> 1) + ((n & 1) ? 0 : 4))) & 15u;
+                            if (okq) { if (__popc(nib) == 1) a.packed[j] += 1u << ((31 - __clz(nib)) * 8); else a.nN[j]++; }
+                        }
                     }
-                    rpos += len; qpos += len;
-                } else if (op == 2 || op == 3) {
+                }
+            } else {
+                uint32_t rpos = 0, qpos = 0;
+                for (uint32_t i = 0; i < n_cigar; i++) {
+                    uint32_t c = i == 0 ? c0 : ldu32(cg + 4 * i), len = c >> 4, op = c & 15;
+                    if (cig_match(op)) {
 #pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        int64_t x = rp + j - (int64_t)rpos;
-                        if (x >= 0 && x < (int64_t)len && (uint64_t)(rp + j) < rspan) { if (op == 2) a.del[j]++; else a.skip[j]++; }
-                    }
-                    rpos += len;
-                } else if (cig_qcons(op)) qpos += len;
-                if ((int64_t)rpos > rp + 3) break;          // (warp-divergent exit is fine: remaining ops cannot touch this lane)
+                        for (int j = 0; j < 4; j++) {
+                            int32_t x = rp + j - (int32_t)rpos;
+                            if (x >= 0 && x < (int32_t)len && (uint32_t)(rp + j) < rspan) add_base<MINQ>(a, j, seq, qual, qpos + (uint32_t)x, lseq, minq);
+                        }
+                        rpos += len; qpos += len;
+                    } else if (op == 2 || op == 3) {
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            int32_t x = rp + j - (int32_t)rpos;
+                            if (x >= 0 && x < (int32_t)len && (uint32_t)(rp + j) < rspan) { if (op == 2) a.del[j]++; else a.skip[j]++; }
+                        }
+                        rpos += len;
+                    } else if (cig_qcons(op)) qpos += len;
+                    if ((int32_t)rpos > rp + 3) break;          // (warp-divergent exit is fine: remaining ops cannot touch this lane)
+                }
             }
             if (++since_flush == 255) {
                 since_flush = 0;
