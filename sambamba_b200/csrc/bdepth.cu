@@ -105,6 +105,7 @@ struct bdepth {
     int rank = 0, world = 1;
     NcclComm comm = nullptr; bool have_uid = false; NcclUid uid{};
     uint64_t own_lo = 0, own_hi = 0;      // linear range owned by this rank (whole genome when world == 1)
+    bool bai_window_ok = true;            // cleared when the linear index turns out not to describe the file
     uint64_t batch_u = 6ull << 30;
     uint64_t window_positions = 0;
     // ---- shard (resolved lazily)
@@ -393,7 +394,7 @@ int run_pipeline(bdepth* h, RunMode mode, RunOut* ro, Emitter* em = nullptr) {
     // span of the linear genome is allocated; without one the whole genome is (87 GB for GRCh38, fits 180 GB HBM).
     if (mode == RUN_FULL) {
         uint64_t lo = 0, hi = h->hdr.total_len;
-        if (h->bai.valid && h->bai.ioffsets.size() == nref && h->world == 1) {
+        if (h->bai.valid && h->bai_window_ok && h->bai.ioffsets.size() == nref && h->world == 1) {
             lo = UINT64_MAX; hi = 0;
             for (size_t r = 0; r < nref; r++) {
                 const auto& v = h->bai.ioffsets[r]; if (v.empty()) continue;
@@ -402,7 +403,7 @@ int run_pipeline(bdepth* h, RunMode mode, RunOut* ro, Emitter* em = nullptr) {
                 lo = std::min<uint64_t>(lo, h->hdr.ref_lin0[r] + std::min<uint64_t>((uint64_t)k << 14, h->hdr.ref_len[r]));
                 hi = std::max<uint64_t>(hi, h->hdr.ref_lin0[r] + std::min<uint64_t>((uint64_t)v.size() << 14, h->hdr.ref_len[r]));
             }
-            if (lo > hi) { lo = 0; hi = 0; }
+            if (lo >= hi) { lo = 0; hi = h->hdr.total_len; }      // an index without linear entries says nothing
         }
         h->cnt_base = lo / TILE_POS * TILE_POS;
         h->win_len = ((hi - h->cnt_base + TILE_POS - 1) / TILE_POS + 1) * TILE_POS;
@@ -629,7 +630,13 @@ int run_pipeline(bdepth* h, RunMode mode, RunOut* ro, Emitter* em = nullptr) {
         // ---- K3
         if (mode == RUN_FULL && ss.n_pass) {
             uint64_t gmin = ss.min_start, gmax = ss.max_end;
-            if (gmin < h->cnt_base || gmax > h->cnt_base + h->win_len) return fail(h, BDEPTH_ERR_FORMAT, "reads lie outside the span covered by the BAI linear index (stale index?)");
+            if (gmin < h->cnt_base || gmax > h->cnt_base + h->win_len) {
+                // the index does not describe this file (the reference only checks that one exists, depth.d:1166):
+                // start over with the whole genome as the counter window
+                if (!h->bai_window_ok) return fail(h, BDEPTH_ERR_FORMAT, "read extends past the end of the reference space");
+                h->bai_window_ok = false; CK(cudaStreamSynchronize(sm));
+                return run_pipeline(h, mode, ro, em);
+            }
             uint64_t t_lo = (gmin - h->cnt_base) / TILE_POS, t_hi = (gmax - h->cnt_base + TILE_POS - 1) / TILE_POS;
             uint64_t n_tiles = t_hi - t_lo; uint64_t tiles_base = h->cnt_base + t_lo * TILE_POS;
             if (t_hi * TILE_POS > h->win_len) return fail(h, BDEPTH_ERR_FORMAT, "read extends past the end of the reference space");
@@ -966,13 +973,29 @@ int bdepth_run_windows(bdepth_t* h, uint32_t window, uint32_t overlap, const uin
     }
     std::vector<uint32_t> reads, bases, cov;
     int rc = run_segments(h, segs, thr, n_thr, reads, bases, cov); if (rc) return rc;
-    std::vector<uint8_t> emit(segs.size(), 0);
-    for (size_t r = 0; r < h->hdr.ref_len.size(); r++) {
+    // Which slots the reference prints: full windows of references with reads (depth.d:1057,1071), length/step
+    // windows of references without (printEmptyWindows, depth.d:1039-1044).  Quirk kept for drop-in output: in
+    // close() (depth.d:1070-1076) the FIRST trailing reference without reads is printed before the window state is
+    // reset, so its windows continue from where the last reference with reads stopped.
+    const size_t nref = h->hdr.ref_len.size();
+    long last_has = -1;
+    for (size_t r = 0; r < nref; r++) if ((h->ref_has_host[r >> 5] >> (r & 31)) & 1) last_has = (long)r;
+    if (!cb) return 0;
+    std::vector<uint32_t> c(std::max<size_t>(n_thr, 1)), zero(std::max<size_t>(n_thr, 1), 0);
+    uint64_t idx = 0;
+    for (size_t r = 0; r < nref; r++) {
         bool has = (h->ref_has_host[r >> 5] >> (r & 31)) & 1;
         uint32_t m = has ? n_full[r] : n_empty[r];
-        for (uint32_t k = 0; k < m; k++) emit[first[r] + k] = 1;
+        uint32_t shift = (!has && last_has >= 0 && (long)r == last_has + 1) ? n_full[last_has] * step : 0;
+        for (uint32_t k = 0; k < m; k++) {
+            size_t i = first[r] + k;
+            bdepth_region_stat st;
+            if (shift) st = bdepth_region_stat{(int32_t)r, shift + k * step, shift + k * step + window, 0, 0, zero.data()};
+            else { for (size_t t = 0; t < n_thr; t++) c[t] = cov[t * segs.size() + i]; st = bdepth_region_stat{(int32_t)r, segs[i].start, segs[i].end, reads[i], bases[i], c.data()}; }
+            if (cb(user, &st, idx++)) return fail(h, BDEPTH_ERR_CALLBACK, "stat callback aborted");
+        }
     }
-    return deliver_segments(h, segs, emit, n_thr, reads, bases, cov, cb, user);
+    return 0;
 }
 
 int bdepth_run_regions(bdepth_t* h, const bdepth_region* regions, size_t n, const uint32_t* thr, size_t n_thr, bdepth_stat_cb cb, void* user) {

@@ -1,0 +1,125 @@
+"""Edge cases the reference's fixtures do not cover (no N/P/=/X, no stored blocks, no odd framing):
+hand-made BAMs through the GPU engine vs the oracle (counters and CLI text)."""
+import os
+import random
+
+import numpy as np
+import pytest
+
+import helpers
+
+pytestmark = pytest.mark.gpu
+
+
+def rnd_seq(r, n):
+    return "".join(r.choice("ACGTN" if r.random() < 0.02 else "ACGT") for _ in range(n))
+
+
+def compare(path, minq=0, **flt):
+    import sambamba_b200 as sb
+    want, ost = helpers.oracle_counts(path, min_bq=minq, **flt)
+    with sb.BDepth(path) as b:
+        if flt:
+            b.set_filter(flt.get("mapq_gt", 0), flt.get("flag_reject", 0x600))
+        b.set_min_baseq(minq)
+        got = b.run_base()
+        st = b.stats()
+    assert got.shape == want.shape
+    bad = np.argwhere(got != want)
+    assert bad.size == 0, (path, bad[:4])
+    assert st["n_records"] == ost.n_records and st["n_records_pass"] == ost.n_pass
+    return st
+
+
+def cli_same(args):
+    rc1, out1, err1 = helpers.run_cli(args)
+    rc2, out2, err2 = helpers.oracle_cli(args)
+    assert rc1 == rc2 and out1 == out2, (args, err1[:300], out1[:300], out2[:300])
+
+
+def test_header_only_and_all_filtered(tmp_path):
+    p = helpers.write_bam(str(tmp_path / "empty.bam"), [("c1", 500), ("c2", 300)], [])
+    compare(p)
+    for args in (["base", p], ["base", "-c", "0", p], ["window", "-w", "100", p], ["region", "-L", "c2:10-200", p]):
+        cli_same(args)
+    r = random.Random(1)
+    reads = [(0, 10 * i, 0, 0, [(50, 0)], rnd_seq(r, 50), f"q{i}") for i in range(20)]          # MAPQ 0
+    reads += [(0, 300 + i, 60, 0x400, [(50, 0)], rnd_seq(r, 50), f"d{i}") for i in range(5)]     # duplicates
+    reads += [(-1, -1, 0, 4, [], rnd_seq(r, 30), f"u{i}") for i in range(5)]                      # unmapped tail
+    p = helpers.write_bam(str(tmp_path / "filtered.bam"), [("c1", 500), ("c2", 300)], reads)
+    st = compare(p)
+    assert st["n_records"] == 30 and st["n_records_pass"] == 0
+    compare(p, mapq_gt=-1, flag_reject=0)
+    cli_same(["base", "-F", "", p])
+    cli_same(["window", "-w", "64", "-F", "", p])
+
+
+def test_every_cigar_op_and_clipping_at_reference_end(tmp_path):
+    r = random.Random(2)
+    L = 4000
+    reads = []
+    specs = [
+        [(30, 0)], [(10, 4), (40, 0)], [(5, 5), (20, 0), (3, 1), (20, 0), (4, 5)], [(20, 0), (7, 2), (30, 0)], [(25, 0), (300, 3), (25, 0)],
+        [(10, 7), (5, 8), (10, 7)], [(10, 0), (2, 6), (10, 0)], [(15, 0), (1500, 3), (15, 0), (2, 2), (10, 0)], [(50, 0), (4, 4)],
+        [(12, 0), (1, 1), (12, 0), (1, 2), (12, 0), (1, 1), (12, 0)],
+    ]
+    pos = 5
+    for i, cg in enumerate(specs * 6):
+        qlen = sum(l for l, op in cg if op in (0, 1, 4, 7, 8))
+        reads.append((0, pos, 30 + i % 30, 0x10 if i % 3 else 0, cg, rnd_seq(r, qlen), f"r{i}"))
+        pos += r.randint(0, 60)
+    # reads hanging over the end of the reference are clipped by both implementations
+    reads.append((0, L - 20, 60, 0, [(50, 0)], rnd_seq(r, 50), "over1"))
+    reads.append((0, L - 5, 60, 0, [(10, 0), (30, 2), (10, 0)], rnd_seq(r, 20), "over2"))
+    reads.sort(key=lambda x: x[1])
+    quals = [[r.randint(2, 41) for _ in x[5]] for x in reads]
+    p = helpers.write_bam(str(tmp_path / "ops.bam"), [("c1", L), ("c2", 100)], reads, quals=quals)
+    st = compare(p)
+    assert st["long_reads"] >= 6           # the 1500N reads take the scatter path
+    compare(p, minq=20)
+    # text parity needs valid input: the reference's sweep prints columns PAST the reference end for overhanging
+    # reads (no bounds check, release build), which the engine clips
+    keep = [i for i, x in enumerate(reads) if not x[6].startswith("over")]
+    p2 = helpers.write_bam(str(tmp_path / "ops_valid.bam"), [("c1", L), ("c2", 100)], [reads[i] for i in keep], quals=[quals[i] for i in keep])
+    for args in (["base", p2], ["base", "-q", "25", "-c", "0", p2], ["window", "-w", "250", "-T", "2", p2], ["region", "-L", "c1:100-900", "-q", "10", p2]):
+        cli_same(args)
+
+
+def test_long_reads_spanning_many_bgzf_blocks(tmp_path):
+    r = random.Random(3)
+    reads = []
+    pos = 100
+    for i in range(12):
+        ops = []
+        n = r.randint(3000, 9000)
+        for k in range(n):
+            ops.append((r.randint(5, 40), 0))
+            ops.append((r.randint(1, 3), r.choice([1, 2])))
+        ops.append((20, 0))
+        qlen = sum(l for l, op in ops if op in (0, 1, 4, 7, 8))
+        reads.append((0, pos, 60, 0, ops, rnd_seq(r, qlen), f"long{i}"))       # ~150-400 kb records, > 65535 would need CG; stay below
+        pos += r.randint(1000, 50000)
+    reads = [x for x in reads if len(x[4]) < 65535]
+    p = helpers.write_bam(str(tmp_path / "long.bam"), [("chrL", 2_000_000)], reads, block=0x4000)   # small blocks: every record spans many
+    st = compare(p)
+    assert st["long_reads"] == len(reads)
+    import sambamba_b200 as sb
+    want, _ = helpers.oracle_counts(p)
+    with sb.BDepth(p) as b:
+        b.set_tuning(batch_bytes=1 << 20)          # force the carry path: records straddle batches
+        got = b.run_base()
+        assert b.stats()["n_batches"] >= 2
+    assert np.array_equal(got, want)
+
+
+def test_odd_block_sizes_and_levels(tmp_path):
+    r = random.Random(4)
+    reads = [(i % 2, 50 + 3 * (i // 2), 60, 0, [(40, 0)], rnd_seq(r, 40), f"r{i}") for i in range(3000)]
+    reads.sort(key=lambda x: (x[0], x[1]))
+    for block, level in ((1, 6), (37, 1), (300, 9), (65280, 0), (4096, 6)):
+        if block == 1:
+            reads_ = reads[:40]
+        else:
+            reads_ = reads
+        p = helpers.write_bam(str(tmp_path / f"b{block}.bam"), [("a", 5000), ("b", 5000)], reads_, block=max(block, 1), level=level)
+        compare(p)

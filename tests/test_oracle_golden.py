@@ -89,38 +89,9 @@ CIGARS = [[(54, 0)], [(54, 0)], [(50, 0), (3, 1), (1, 0)], [(54, 0)], [(54, 0)],
 POS = [758, 764, 767, 769, 773, 776, 785, 795, 804, 817]
 
 
-def write_bam(path, refs, reads, rg=None):
-    """Minimal BAM + dummy BAI writer for hand-made reads: (ref, pos, mapq, flag, cigar[(len,op)], seq, name)."""
-    text = "@HD\tVN:1.6\tSO:coordinate\n" + "".join(f"@SQ\tSN:{n}\tLN:{l}\n" for n, l in refs)
-    if rg:
-        text += "".join(f"@RG\tID:{i}\tSM:{s}\n" for i, s in rg)
-    body = b"BAM\1" + struct.pack("<i", len(text)) + text.encode() + struct.pack("<i", len(refs))
-    for n, l in refs:
-        body += struct.pack("<i", len(n) + 1) + n.encode() + b"\0" + struct.pack("<i", l)
-    code = {c: i for i, c in enumerate("=ACMGRSVTWYHKDBN")}
-    for ref, pos, mapq, flag, cigar, seq, name in reads:
-        nm = name.encode() + b"\0"
-        packed = bytearray()
-        for i in range(0, len(seq), 2):
-            packed.append((code[seq[i]] << 4) | (code[seq[i + 1]] if i + 1 < len(seq) else 0))
-        rec = struct.pack("<iiIIiiii", ref, pos, (4680 << 16) | (mapq << 8) | len(nm), (flag << 16) | len(cigar), len(seq), -1, -1, 0)
-        rec += nm + b"".join(struct.pack("<I", (l << 4) | op) for l, op in cigar) + bytes(packed) + bytes([30] * len(seq))
-        body += struct.pack("<i", len(rec)) + rec
-    with open(path, "wb") as f:
-        for i in range(0, len(body), 0xFF00):
-            chunk = body[i:i + 0xFF00]
-            c = zlib.compressobj(6, zlib.DEFLATED, -15)
-            d = c.compress(chunk) + c.flush()
-            f.write(b"\x1f\x8b\x08\x04\0\0\0\0\0\xff\x06\0BC\x02\0" + struct.pack("<H", len(d) + 25) + d + struct.pack("<II", zlib.crc32(chunk), len(chunk)))
-        f.write(bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000"))
-    with open(path + ".bai", "wb") as f:      # empty-but-valid index: depth only checks that it exists (depth.d:1166)
-        f.write(b"BAI\1" + struct.pack("<i", len(refs)) + b"".join(struct.pack("<ii", 0, 0) for _ in refs) + struct.pack("<Q", 0))
-    return path
-
-
 def test_pileup_unittest_columns(tmp_path):
     reads = [(0, POS[i], 60, 0, CIGARS[i], SEQS[i], f"r{i}") for i in range(10)]
-    p = write_bam(str(tmp_path / "u.bam"), [("20", 2000)], reads)
+    p = helpers.write_bam(str(tmp_path / "u.bam"), [("20", 2000)], reads)
     rc, out, _ = helpers.oracle_cli(["base", p])
     assert rc == 0
     rows = {int(l.split(b"\t")[1]): [int(x) for x in l.split(b"\t")[2:9]] for l in out.splitlines()[1:]}
