@@ -193,7 +193,6 @@ def main():
     import numpy as np
     import sambamba_b200 as sb
     dist = None
-    uid = None
     if world > 1:
         import torch
         import torch.distributed as dist
@@ -203,11 +202,17 @@ def main():
             path = ensure_workload(n_units, a.reads_per_unit)
         dist.barrier()
         path = workload_path(n_units, a.reads_per_unit)
-        obj = [sb.nccl_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(obj, src=0)
-        uid = obj[0]
     else:
         path = ensure_workload(n_units, a.reads_per_unit)
+
+    def fresh_uid():
+        """A NCCL unique id can seed exactly one communicator: every handle gets its own (rank 0 creates, all receive)."""
+        if dist is None:
+            return None
+        obj = [sb.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(obj, src=0)
+        return obj[0]
+
     file_bytes = os.path.getsize(path)
 
     def barrier():
@@ -233,7 +238,7 @@ def main():
     # ---- value: inputs resident in HBM
     b = sb.BDepth(path, device=local_rank)
     if world > 1:
-        b.set_shard(rank, world, uid)
+        b.set_shard(rank, world, fresh_uid())
     b.stage()
     for _ in range(a.warmup):
         barrier()
@@ -268,7 +273,7 @@ def main():
     t0 = time.perf_counter()
     h = sb.BDepth(memory=img, bai=bai, device=local_rank)          # session setup (BGZF index, header, buffers) is outside the steps
     if world > 1:
-        h.set_shard(rank, world, uid)
+        h.set_shard(rank, world, fresh_uid())
     open_s = time.perf_counter() - t0
     cold_s = None
     n_w = max(1, min(a.warmup, 3))
@@ -308,7 +313,7 @@ def main():
                 "path": "bdepth_open_memory(pinned host BAM image) + bdepth_run_base -> 7 x u32 counters in pinned host memory"},
         "gpu_launches": int(total_launches),
         "roofline": {"kernel": "k1_inflate (lane-per-BGZF-block DEFLATE)", "bound": "hbm", "achieved": k1_bytes / 1e9 / (k1_ms / 1e3), "peak": peak, "unit": "GB/s",
-                     "frac": k1_bytes / 1e9 / (k1_ms / 1e3) / peak, "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH,
+                     "frac": k1_bytes / 1e9 / (k1_ms / 1e3) / peak, "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH if (a.gpus == 1 and a.reads_per_unit == READS_PER_UNIT) else None,
                      "algorithmic_bytes_per_launch": int(k1_bytes / max(1, k1_launches_per_step)), "launches_per_step": k1_launches_per_step,
                      "peak_source": peak_src, "note": "C + U per launch (SURVEY 8d) / CUDA-event duration of the launch on the library stream; DEFLATE decoding is instruction-latency bound, not HBM bound"},
         "clocks": clocks,
