@@ -66,6 +66,8 @@ typedef struct {
     uint32_t len;        /* number of positions                           */
     uint32_t stride;     /* elements between planes                       */
     const uint32_t* counts;
+    uint32_t n_samples;  /* counter sets in the tile: samples of the @RG table (depth.d:1170-1181), or 1 */
+    uint32_t sample_stride; /* elements between the plane-0 starts of consecutive samples            */
 } bdepth_tile;
 enum { BDEPTH_PLANE_A = 0, BDEPTH_PLANE_C, BDEPTH_PLANE_G, BDEPTH_PLANE_T, BDEPTH_PLANE_N, BDEPTH_PLANE_DEL, BDEPTH_PLANE_REFSKIP, BDEPTH_N_PLANES };
 
@@ -79,6 +81,7 @@ typedef struct {
     uint32_t n_reads;
     uint32_t n_bases;
     const uint32_t* cov_ge;   /* n_thresholds entries */
+    int32_t  sample_id;       /* regions outer, samples inner, as the reference prints them */
 } bdepth_region_stat;
 typedef int (*bdepth_stat_cb)(void* user, const bdepth_region_stat* stat, uint64_t index);
 
@@ -131,6 +134,8 @@ const char* bdepth_sample_name(const bdepth_t* h, int i);
  * default (depth.d:1159): mapq_gt = 0, mask = 0x400 | 0x200.  -F "" : mapq_gt = -1, mask = 0. */
 int bdepth_set_filter(bdepth_t* h, int mapq_gt, uint32_t flag_reject_mask);
 int bdepth_set_min_baseq(bdepth_t* h, uint32_t min_base_quality);
+/* --combined (depth.d:1131): one counter set for all samples.  Default: one per @RG sample (<= 64). */
+int bdepth_set_combined(bdepth_t* h, int combined);
 /* Restrict runs to reads overlapping these regions (any order; merged internally).  n = 0 clears. */
 int bdepth_set_regions(bdepth_t* h, const bdepth_region* regions, size_t n);
 /* Multi-GPU: this process handles shard `rank` of `world` (BGZF virtual-offset ranges cut at BAI

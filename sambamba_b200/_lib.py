@@ -24,12 +24,12 @@ class Region(C.Structure):
 
 class Tile(C.Structure):
     _fields_ = [("ref_id", C.c_int32), ("start", C.c_uint32), ("len", C.c_uint32), ("stride", C.c_uint32),
-                ("counts", C.POINTER(C.c_uint32))]
+                ("counts", C.POINTER(C.c_uint32)), ("n_samples", C.c_uint32), ("sample_stride", C.c_uint32)]
 
 
 class RegionStat(C.Structure):
     _fields_ = [("ref_id", C.c_int32), ("start", C.c_uint32), ("end", C.c_uint32), ("n_reads", C.c_uint32),
-                ("n_bases", C.c_uint32), ("cov_ge", C.POINTER(C.c_uint32))]
+                ("n_bases", C.c_uint32), ("cov_ge", C.POINTER(C.c_uint32)), ("sample_id", C.c_int32)]
 
 
 class Stats(C.Structure):
@@ -82,6 +82,7 @@ def load_library():
     L.bdepth_sample_name.restype = C.c_char_p
     L.bdepth_set_filter.argtypes = [vp, C.c_int, C.c_uint32]
     L.bdepth_set_min_baseq.argtypes = [vp, C.c_uint32]
+    L.bdepth_set_combined.argtypes = [vp, C.c_int]
     L.bdepth_set_regions.argtypes = [vp, C.POINTER(Region), C.c_size_t]
     L.bdepth_set_shard.argtypes = [vp, C.c_int, C.c_int, vp]
     L.bdepth_nccl_unique_id.argtypes = [vp]
@@ -105,7 +106,7 @@ def load_library():
 EXPORTED_SYMBOLS = [
     "bdepth_device_count", "bdepth_open", "bdepth_open_memory", "bdepth_close", "bdepth_last_error", "bdepth_n_ref",
     "bdepth_ref_name", "bdepth_ref_length", "bdepth_header_text", "bdepth_is_coordinate_sorted", "bdepth_has_index",
-    "bdepth_n_samples", "bdepth_sample_name", "bdepth_set_filter", "bdepth_set_min_baseq", "bdepth_set_regions",
+    "bdepth_n_samples", "bdepth_sample_name", "bdepth_set_filter", "bdepth_set_min_baseq", "bdepth_set_combined", "bdepth_set_regions",
     "bdepth_set_shard", "bdepth_nccl_unique_id", "bdepth_plan_shards", "bdepth_set_tuning", "bdepth_stage", "bdepth_run_resident", "bdepth_run_base",
     "bdepth_run_windows", "bdepth_run_regions", "bdepth_get_stats", "bdepth_ref_has_reads", "bdepth_inflate_to_host", "bdepth_scan_to_host",
 ]
@@ -186,6 +187,9 @@ class BDepth:
     def set_min_baseq(self, q):
         self._ck(self.L.bdepth_set_min_baseq(self.h, q))
 
+    def set_combined(self, on=True):
+        self._ck(self.L.bdepth_set_combined(self.h, 1 if on else 0))
+
     def set_regions(self, regions):
         arr = (Region * max(1, len(regions)))(*[Region(*r) for r in regions])
         self._ck(self.L.bdepth_set_regions(self.h, arr, len(regions)))
@@ -227,14 +231,18 @@ class BDepth:
         wa, wb = (0, int(lin0[-1])) if window is None else window
         if window is not None:
             self.set_regions(self.lin_to_regions(wa, wb))
-        out = np.zeros((7, max(0, wb - wa)), np.uint32) if collect else None
+        box = {}
 
         def cb(_user, tp):
             t = tp.contents
+            if "out" not in box:
+                box["out"] = np.zeros((t.n_samples, 7, max(0, wb - wa)), np.uint32)
             a = int(lin0[t.ref_id]) + t.start - wa
-            src = np.ctypeslib.as_array(t.counts, shape=(6 * t.stride + t.len,))
-            for p in range(7):
-                out[p, a:a + t.len] = src[p * t.stride:p * t.stride + t.len]
+            src = np.ctypeslib.as_array(t.counts, shape=((t.n_samples - 1) * t.sample_stride + 6 * t.stride + t.len,))
+            for si in range(t.n_samples):
+                for p in range(7):
+                    o = si * t.sample_stride + p * t.stride
+                    box["out"][si, p, a:a + t.len] = src[o:o + t.len]
             return 0
 
         cbf = TILE_CB(cb) if collect else C.cast(None, TILE_CB)
@@ -243,7 +251,12 @@ class BDepth:
         finally:
             if window is not None:
                 self.set_regions([])
-        return out
+        if not collect:
+            return None
+        out = box.get("out")
+        if out is None:
+            return np.zeros((7, max(0, wb - wa)), np.uint32)
+        return out[0] if out.shape[0] == 1 else out          # [7, n] for a single counter set, [S, 7, n] per sample
 
     def _run_stats(self, fn):
         rows = []
@@ -251,7 +264,7 @@ class BDepth:
 
         def cb(_user, sp, idx):
             s = sp.contents
-            rows.append((s.ref_id, s.start, s.end, s.n_reads, s.n_bases, [s.cov_ge[i] for i in range(nthr)]))
+            rows.append((s.ref_id, s.start, s.end, s.n_reads, s.n_bases, [s.cov_ge[i] for i in range(nthr)], s.sample_id))
             return 0
         self._ck(fn(STAT_CB(cb)))
         return rows

@@ -106,6 +106,9 @@ struct bdepth {
     NcclComm comm = nullptr; bool have_uid = false; NcclUid uid{};
     uint64_t own_lo = 0, own_hi = 0;      // linear range owned by this rank (whole genome when world == 1)
     bool bai_window_ok = true;            // cleared when the linear index turns out not to describe the file
+    bool combined = false;                // --combined: one counter set for all samples
+    uint32_t S = 1;                       // counter sets in the current run (samples, or 1)
+    DevBuf rg_ids, rg_offs, rg_samp;
     uint64_t batch_u = 6ull << 30;
     uint64_t window_positions = 0;
     // ---- shard (resolved lazily)
@@ -259,13 +262,16 @@ struct Emitter {
     struct Slot { uint64_t a = 0, b = 0; } slot[2];
     int head = 0, inflight = 0;
     uint64_t d2h_bytes = 0;
+    // the pinned double buffer holds 2 x [S][7][chunk] ; chunk shrinks with the number of samples
+    size_t chunk() const { return EMIT_CHUNK / h->S; }
     int issue(int si, uint64_t a, uint64_t b) {
+        const int NP = N_PLANES * (int)h->S; const size_t CH = chunk();
         uint32_t* dst = (uint32_t*)h->pinned + (size_t)si * EMIT_CHUNK * N_PLANES;
         uint64_t wa = std::max(a, h->cnt_base), wb = std::min(b, h->cnt_base + h->win_len);   // outside the window: zeros
-        if (wa >= wb || wa > a || wb < b) for (int pl = 0; pl < N_PLANES; pl++) memset(dst + (size_t)pl * EMIT_CHUNK, 0, (b - a) * 4);
-        if (wa < wb) for (int pl = 0; pl < N_PLANES; pl++) CK(cudaMemcpyAsync(dst + (size_t)pl * EMIT_CHUNK + (wa - a), h->counts.as<uint32_t>() + (uint64_t)pl * h->win_len + (wa - h->cnt_base), (wb - wa) * 4, cudaMemcpyDeviceToHost, h->s_d2h));
+        if (wa >= wb || wa > a || wb < b) for (int pl = 0; pl < NP; pl++) memset(dst + (size_t)pl * CH, 0, (b - a) * 4);
+        if (wa < wb) for (int pl = 0; pl < NP; pl++) CK(cudaMemcpyAsync(dst + (size_t)pl * CH + (wa - a), h->counts.as<uint32_t>() + (uint64_t)pl * h->win_len + (wa - h->cnt_base), (wb - wa) * 4, cudaMemcpyDeviceToHost, h->s_d2h));
         CK(cudaEventRecord(h->ev[8 + si], h->s_d2h));
-        slot[si].a = a; slot[si].b = b; d2h_bytes += (b - a) * N_PLANES * 4;
+        slot[si].a = a; slot[si].b = b; d2h_bytes += (b - a) * NP * 4;
         return 0;
     }
     int deliver_oldest() {
@@ -280,7 +286,7 @@ struct Emitter {
             uint64_t rend = h->hdr.ref_lin0[ref] + h->hdr.ref_len[ref];
             if (a >= rend) { ref++; continue; }
             uint64_t e = std::min(bnd, rend);
-            bdepth_tile t{(int32_t)ref, (uint32_t)(a - h->hdr.ref_lin0[ref]), (uint32_t)(e - a), (uint32_t)EMIT_CHUNK, src + (a - slot[si].a)};
+            bdepth_tile t{(int32_t)ref, (uint32_t)(a - h->hdr.ref_lin0[ref]), (uint32_t)(e - a), (uint32_t)chunk(), src + (a - slot[si].a), h->S, (uint32_t)(chunk() * N_PLANES)};
             if (cb(user, &t)) return fail(h, BDEPTH_ERR_CALLBACK, "tile callback aborted");
             a = e;
         }
@@ -295,7 +301,7 @@ struct Emitter {
             uint64_t a = std::max(pos, r.a);
             if (a >= r.b) { ri++; if (ri < ranges.size()) pos = ranges[ri].a; continue; }
             if (a >= limit) break;
-            uint64_t b = std::min(std::min(r.b, limit), a + (uint64_t)EMIT_CHUNK);
+            uint64_t b = std::min(std::min(r.b, limit), a + (uint64_t)chunk());
             if (inflight == 2) { int rc = deliver_oldest(); if (rc) return rc; }
             int rc = issue(head, a, b); if (rc) return rc;
             head ^= 1; inflight++; pos = b;
@@ -333,23 +339,24 @@ int exchange_boundaries(bdepth* h, uint64_t shard_min, uint64_t shard_max) {
     if (nonempty(me)) for (int j = me + 1; j < W; j++) if (nonempty(j) && all[2 * j] < shard_max) { uint64_t lo = std::max(all[2 * j], shard_min), hi = std::min(shard_max, own_hi(j)); if (lo < hi) sends.push_back({j, lo, hi}); }
     if (nonempty(me)) for (int i = 0; i < me; i++) if (nonempty(i) && all[2 * i + 1] > all[2 * me]) { uint64_t lo = std::max(all[2 * me], all[2 * i]), hi = std::min(all[2 * i + 1], own_hi(me)); if (lo < hi) recvs.push_back({i, lo, hi}); }
     uint64_t tot = 0; for (auto& x : sends) tot += x.hi - x.lo; uint64_t sent = tot; for (auto& x : recvs) tot += x.hi - x.lo;
-    DevBuf stage; CK(stage.ensure((size_t)std::max<uint64_t>(tot, 1) * N_PLANES * 4));
+    const int NP = N_PLANES * (int)h->S;      // all counter planes of all samples
+    DevBuf stage; CK(stage.ensure((size_t)std::max<uint64_t>(tot, 1) * NP * 4));
     uint32_t* sp = stage.as<uint32_t>(); uint64_t off = 0;
     std::vector<uint64_t> soff, roff;
     for (auto& x : sends) {   // pack the 7 planes of the slice contiguously
         uint64_t n = x.hi - x.lo; soff.push_back(off);
-        CK(cudaMemcpy2DAsync(sp + off, n * 4, h->counts.as<uint32_t>() + (x.lo - h->cnt_base), h->win_len * 4, n * 4, N_PLANES, cudaMemcpyDeviceToDevice, sm));
-        off += n * N_PLANES;
+        CK(cudaMemcpy2DAsync(sp + off, n * 4, h->counts.as<uint32_t>() + (x.lo - h->cnt_base), h->win_len * 4, n * 4, NP, cudaMemcpyDeviceToDevice, sm));
+        off += n * NP;
     }
-    for (auto& x : recvs) { roff.push_back(off); off += (x.hi - x.lo) * N_PLANES; }
+    for (auto& x : recvs) { roff.push_back(off); off += (x.hi - x.lo) * NP; }
     NK(N.GroupStart());
-    for (size_t i = 0; i < sends.size(); i++) NK(N.Send(sp + soff[i], (sends[i].hi - sends[i].lo) * N_PLANES, NCCL_UINT32, sends[i].peer, h->comm, sm));
-    for (size_t i = 0; i < recvs.size(); i++) NK(N.Recv(sp + roff[i], (recvs[i].hi - recvs[i].lo) * N_PLANES, NCCL_UINT32, recvs[i].peer, h->comm, sm));
+    for (size_t i = 0; i < sends.size(); i++) NK(N.Send(sp + soff[i], (sends[i].hi - sends[i].lo) * NP, NCCL_UINT32, sends[i].peer, h->comm, sm));
+    for (size_t i = 0; i < recvs.size(); i++) NK(N.Recv(sp + roff[i], (recvs[i].hi - recvs[i].lo) * NP, NCCL_UINT32, recvs[i].peer, h->comm, sm));
     NK(N.GroupEnd());
     for (size_t i = 0; i < recvs.size(); i++) {
         uint64_t n = recvs[i].hi - recvs[i].lo;
-        for (int pl = 0; pl < N_PLANES; pl++) k_add_u32<<<(unsigned)((n + 255) / 256), 256, 0, sm>>>(h->counts.as<uint32_t>() + (uint64_t)pl * h->win_len + (recvs[i].lo - h->cnt_base), sp + roff[i] + (uint64_t)pl * n, n);
-        h->st.gpu_launches += N_PLANES;
+        for (int pl = 0; pl < NP; pl++) k_add_u32<<<(unsigned)((n + 255) / 256), 256, 0, sm>>>(h->counts.as<uint32_t>() + (uint64_t)pl * h->win_len + (recvs[i].lo - h->cnt_base), sp + roff[i] + (uint64_t)pl * n, n);
+        h->st.gpu_launches += NP;
     }
     // which references have reads: OR over ranks == (sum > 0)
     size_t nw = h->hdr.ref_len.size() / 32 + 2;
@@ -364,7 +371,7 @@ int exchange_boundaries(bdepth* h, uint64_t shard_min, uint64_t shard_max) {
         CK(cudaMemcpyAsync(h->ref_has.p, hb.data(), nw * 4, cudaMemcpyHostToDevice, sm));
     }
     CK(cudaEventRecord(e1, sm)); CK(cudaStreamSynchronize(sm));
-    float t = 0; CK(cudaEventElapsedTime(&t, e0, e1)); h->st.ms_exchange = t; h->st.halo_bytes_sent = sent * N_PLANES * 4;
+    float t = 0; CK(cudaEventElapsedTime(&t, e0, e1)); h->st.ms_exchange = t; h->st.halo_bytes_sent = sent * NP * 4;
     // ownership: an empty rank owns nothing
     if (nonempty(me)) { h->own_lo = own_lo(me); h->own_hi = own_hi(me); } else { h->own_lo = h->own_hi = 0; }
     dpair.release(); dall.release(); stage.release(); bits.release();
@@ -407,7 +414,9 @@ int run_pipeline(bdepth* h, RunMode mode, RunOut* ro, Emitter* em = nullptr) {
         }
         h->cnt_base = lo / TILE_POS * TILE_POS;
         h->win_len = ((hi - h->cnt_base + TILE_POS - 1) / TILE_POS + 1) * TILE_POS;
-        size_t need = (size_t)h->win_len * N_PLANES * 4;
+        h->S = (h->combined || h->hdr.sample_names.size() <= 1) ? 1u : (uint32_t)h->hdr.sample_names.size();
+        if (h->S > 64) return fail(h, BDEPTH_ERR_ARG, "%u samples: per-sample output supports at most 64 (use --combined)", h->S);
+        size_t need = (size_t)h->win_len * N_PLANES * 4 * h->S;
         size_t free_b = 0, tot_b = 0; CK(cudaMemGetInfo(&free_b, &tot_b));
         if (need > h->counts.cap && need > free_b + h->counts.cap) return fail(h, BDEPTH_ERR_CUDA, "counter window needs %zu bytes of HBM, %zu free", need, free_b);
         CK(h->counts.ensure(need));
@@ -415,6 +424,15 @@ int run_pipeline(bdepth* h, RunMode mode, RunOut* ro, Emitter* em = nullptr) {
         CK(h->ref_has.ensure((nref / 32 + 2) * 4)); CK(cudaMemsetAsync(h->ref_has.p, 0, (nref / 32 + 2) * 4, sm));
     }
     CK(h->scan_stats.ensure(sizeof(ScanStats)));
+    RgTable rgt{nullptr, nullptr, nullptr, 0};
+    if (mode == RUN_FULL && h->S > 1) {      // @RG ID -> sample table for the per-read RG lookup (depth.d:240-250)
+        std::vector<uint8_t> ids; std::vector<uint32_t> offs; std::vector<uint8_t> samp;
+        for (size_t g = 0; g < h->hdr.rg_ids.size(); g++) { offs.push_back((uint32_t)ids.size()); ids.insert(ids.end(), h->hdr.rg_ids[g].begin(), h->hdr.rg_ids[g].end()); ids.push_back(0); samp.push_back((uint8_t)h->hdr.rg_sample[g]); }
+        CK(h->rg_ids.ensure(ids.size() + 8)); CK(h->rg_offs.ensure(offs.size() * 4 + 8)); CK(h->rg_samp.ensure(samp.size() + 8));
+        CK(cudaMemcpyAsync(h->rg_ids.p, ids.data(), ids.size(), cudaMemcpyHostToDevice, sm)); CK(cudaMemcpyAsync(h->rg_offs.p, offs.data(), offs.size() * 4, cudaMemcpyHostToDevice, sm)); CK(cudaMemcpyAsync(h->rg_samp.p, samp.data(), samp.size(), cudaMemcpyHostToDevice, sm));
+        CK(cudaStreamSynchronize(sm));
+        rgt = RgTable{h->rg_ids.as<uint8_t>(), h->rg_offs.as<uint32_t>(), h->rg_samp.as<uint8_t>(), (uint32_t)offs.size()};
+    }
     { uint64_t shard_u = h->blk_hi > h->blk_lo ? B[h->blk_hi - 1].uoff + B[h->blk_hi - 1].isize - B[h->blk_lo].uoff : 0; CK(h->ubuf.ensure(CARRY_MAX + std::min<uint64_t>(h->batch_u + 65536, shard_u) + 256)); }
     CK(h->misc.ensure(64));
 
@@ -595,14 +613,15 @@ int run_pipeline(bdepth* h, RunMode mode, RunOut* ro, Emitter* em = nullptr) {
         size_t Rc = R ? R : 1;
         CK(h->soa_start.ensure(Rc * 8)); CK(h->soa_span.ensure(Rc * 4)); CK(h->soa_meta.ensure(Rc * 4)); CK(h->soa_off.ensure(Rc * 8)); CK(h->soa_ncl.ensure(Rc * 4)); CK(h->soa_lseq.ensure(Rc * 4)); CK(h->long_list.ensure(Rc * 4));
         RecordSoA soa{h->soa_start.as<uint64_t>(), h->soa_span.as<uint32_t>(), h->soa_meta.as<uint32_t>(), h->soa_off.as<int64_t>(), h->soa_ncl.as<uint32_t>(), h->soa_lseq.as<int32_t>()};
-        ScanStats zs{0, 0, 0, 0, ~0ull, 0, 0};
+        ScanStats zs{0, 0, 0, 0, ~0ull, 0, 0, ~0ull};
         CK(cudaMemcpyAsync(h->scan_stats.p, &zs, sizeof zs, cudaMemcpyHostToDevice, sm));
         if (mode == RUN_SCAN_ONLY && !h->ref_has.p) { CK(h->ref_has.ensure((nref / 32 + 2) * 4)); CK(cudaMemsetAsync(h->ref_has.p, 0, (nref / 32 + 2) * 4, sm)); }
-        k2_decode<<<(unsigned)((nb * 32 + 255) / 256), 256, 0, sm>>>(sp, h->chunk_start.as<int64_t>(), (uint32_t)nb, h->slot_base.as<uint32_t>(), h->slots.as<uint16_t>(), h->count.as<uint32_t>(), h->rec_base.as<uint32_t>(), soa, h->mapq_gt, h->flag_reject, h->scan_stats.as<ScanStats>(), h->long_list.as<uint32_t>(), h->ref_has.as<uint32_t>());
+        k2_decode<<<(unsigned)((nb * 32 + 255) / 256), 256, 0, sm>>>(sp, h->chunk_start.as<int64_t>(), (uint32_t)nb, h->slot_base.as<uint32_t>(), h->slots.as<uint16_t>(), h->count.as<uint32_t>(), h->rec_base.as<uint32_t>(), soa, h->mapq_gt, h->flag_reject, h->scan_stats.as<ScanStats>(), h->long_list.as<uint32_t>(), h->ref_has.as<uint32_t>(), rgt);
         CK(cudaGetLastError()); st.gpu_launches++;
         ScanStats ss; CK(cudaMemcpyAsync(&ss, h->scan_stats.p, sizeof ss, cudaMemcpyDeviceToHost, sm));
         CK(cudaEventRecord(e3, sm));
         CK(cudaStreamSynchronize(sm));
+        if (ss.rg_err != ~0ull) return fail(h, BDEPTH_ERR_FORMAT, "error in read #%llu of the batch: its read group is not present in the header", ss.rg_err);
         st.n_records_pass += ss.n_pass; st.n_cigar_ops += ss.n_cigar; st.seq_bytes += ss.seq_bytes; st.long_reads += ss.n_long;
         if (ss.n_pass) { shard_min = std::min<uint64_t>(shard_min, ss.min_start); shard_max = std::max<uint64_t>(shard_max, ss.max_end); }
         if (mode == RUN_SCAN_ONLY) {
@@ -623,8 +642,8 @@ int run_pipeline(bdepth* h, RunMode mode, RunOut* ro, Emitter* em = nullptr) {
         }
         // ---- per-read segment counting (countRead, depth.d:661-669) for the window / region front ends
         if (mode == RUN_FULL && h->seg.on && h->seg.n && ss.n_pass) {
-            if (h->minq) k_read_segments<true><<<(unsigned)((R + 127) / 128), 128, 0, sm>>>(soa, u0, (uint32_t)R, h->seg.s.as<uint64_t>(), h->seg.e.as<uint64_t>(), h->seg.pmax.as<uint64_t>(), h->seg.id.as<uint32_t>(), nullptr, h->seg.n, h->seg.reads.as<uint32_t>(), h->minq);
-            else k_read_segments<false><<<(unsigned)((R + 127) / 128), 128, 0, sm>>>(soa, u0, (uint32_t)R, h->seg.s.as<uint64_t>(), h->seg.e.as<uint64_t>(), h->seg.pmax.as<uint64_t>(), h->seg.id.as<uint32_t>(), nullptr, h->seg.n, h->seg.reads.as<uint32_t>(), 0);
+            if (h->minq) k_read_segments<true><<<(unsigned)((R + 127) / 128), 128, 0, sm>>>(soa, u0, (uint32_t)R, h->seg.s.as<uint64_t>(), h->seg.e.as<uint64_t>(), h->seg.pmax.as<uint64_t>(), h->seg.id.as<uint32_t>(), nullptr, h->seg.n, h->seg.reads.as<uint32_t>(), h->minq, h->S);
+            else k_read_segments<false><<<(unsigned)((R + 127) / 128), 128, 0, sm>>>(soa, u0, (uint32_t)R, h->seg.s.as<uint64_t>(), h->seg.e.as<uint64_t>(), h->seg.pmax.as<uint64_t>(), h->seg.id.as<uint32_t>(), nullptr, h->seg.n, h->seg.reads.as<uint32_t>(), 0, h->S);
             CK(cudaGetLastError()); st.gpu_launches++;
         }
         // ---- K3
@@ -645,14 +664,17 @@ int run_pipeline(bdepth* h, RunMode mode, RunOut* ro, Emitter* em = nullptr) {
             CK(cudaMemsetAsync(h->tile_lo.p, 0xFF, (n_tiles + 2) * 4, sm));
             k3_tile_index<<<(unsigned)((R + 255) / 256), 256, 0, sm>>>(soa, (uint32_t)R, tiles_base, (uint32_t)n_tiles, h->tile_first.as<uint32_t>(), h->tile_lo.as<uint32_t>());
             CK(cudaGetLastError()); st.gpu_launches += 2;
-            if (ss.n_long) {
-                if (h->minq) k3_scatter_long<true><<<(unsigned)((ss.n_long * 32 + 255) / 256), 256, 0, sm>>>(soa, u0, h->long_list.as<uint32_t>(), (uint32_t)ss.n_long, h->cnt_base, h->win_len, h->counts.as<uint32_t>(), h->minq);
-                else k3_scatter_long<false><<<(unsigned)((ss.n_long * 32 + 255) / 256), 256, 0, sm>>>(soa, u0, h->long_list.as<uint32_t>(), (uint32_t)ss.n_long, h->cnt_base, h->win_len, h->counts.as<uint32_t>(), 0);
+            for (uint32_t si = 0; si < h->S; si++) {      // one counter set per sample (one pass when combined / single sample)
+                uint32_t* cnt = h->counts.as<uint32_t>() + (uint64_t)si * N_PLANES * h->win_len; int sel = h->S > 1 ? (int)si : -1;
+                if (ss.n_long) {
+                    if (h->minq) k3_scatter_long<true><<<(unsigned)((ss.n_long * 32 + 255) / 256), 256, 0, sm>>>(soa, u0, h->long_list.as<uint32_t>(), (uint32_t)ss.n_long, h->cnt_base, h->win_len, cnt, h->minq, sel);
+                    else k3_scatter_long<false><<<(unsigned)((ss.n_long * 32 + 255) / 256), 256, 0, sm>>>(soa, u0, h->long_list.as<uint32_t>(), (uint32_t)ss.n_long, h->cnt_base, h->win_len, cnt, 0, sel);
+                    CK(cudaGetLastError()); st.gpu_launches++;
+                }
+                if (h->minq) k3_gather<true><<<(unsigned)n_tiles, 256, 0, sm>>>(soa, u0, tiles_base, h->cnt_base, h->win_len, h->tile_first.as<uint32_t>(), h->tile_lo.as<uint32_t>(), cnt, h->minq, sel);
+                else k3_gather<false><<<(unsigned)n_tiles, 256, 0, sm>>>(soa, u0, tiles_base, h->cnt_base, h->win_len, h->tile_first.as<uint32_t>(), h->tile_lo.as<uint32_t>(), cnt, 0, sel);
                 CK(cudaGetLastError()); st.gpu_launches++;
             }
-            if (h->minq) k3_gather<true><<<(unsigned)n_tiles, 256, 0, sm>>>(soa, u0, tiles_base, h->cnt_base, h->win_len, h->tile_first.as<uint32_t>(), h->tile_lo.as<uint32_t>(), h->counts.as<uint32_t>(), h->minq);
-            else k3_gather<false><<<(unsigned)n_tiles, 256, 0, sm>>>(soa, u0, tiles_base, h->cnt_base, h->win_len, h->tile_first.as<uint32_t>(), h->tile_lo.as<uint32_t>(), h->counts.as<uint32_t>(), 0);
-            CK(cudaGetLastError()); st.gpu_launches++;
         }
         CK(cudaEventRecord(e4, sm));
         if (em && mode == RUN_FULL && h->world == 1 && !last_batch && ss.n_pass) { int rce = em->advance(ss.max_start / TILE_POS * TILE_POS, e4); if (rce) return rce; }
@@ -743,6 +765,7 @@ void bdepth_close(bdepth_t* h) {
     cudaSetDevice(h->device);
     DevBuf* bufs[] = {&h->comp, &h->descs, &h->status, &h->ubuf, &h->chunk_start, &h->entry, &h->exitb, &h->count, &h->slot_base, &h->slots, &h->rec_base, &h->walk_list, &h->soa_start, &h->soa_span, &h->soa_meta, &h->soa_off, &h->soa_ncl, &h->soa_lseq, &h->long_list, &h->tile_first, &h->tile_lo, &h->counts, &h->ref_len_d, &h->ref_lin0_d, &h->scan_stats, &h->ref_has, &h->misc};
     for (DevBuf* b : bufs) b->release();
+    h->rg_ids.release(); h->rg_offs.release(); h->rg_samp.release();
     h->seg.s.release(); h->seg.e.release(); h->seg.pmax.release(); h->seg.id.release(); h->seg.reads.release();
     if (h->comm) { nccl().CommDestroy(h->comm); h->comm = nullptr; }
     if (h->pinned) cudaFreeHost(h->pinned);
@@ -765,6 +788,7 @@ int bdepth_n_samples(const bdepth_t* h) { return (int)h->hdr.sample_names.size()
 const char* bdepth_sample_name(const bdepth_t* h, int i) { return (i >= 0 && (size_t)i < h->hdr.sample_names.size()) ? h->hdr.sample_names[i].c_str() : nullptr; }
 
 int bdepth_set_filter(bdepth_t* h, int mapq_gt, uint32_t flag_reject_mask) { h->mapq_gt = mapq_gt; h->flag_reject = flag_reject_mask; return 0; }
+int bdepth_set_combined(bdepth_t* h, int combined) { h->combined = combined != 0; return 0; }
 int bdepth_set_min_baseq(bdepth_t* h, uint32_t q) { h->minq = q > 255 ? 255 : q; return 0; }
 int bdepth_set_regions(bdepth_t* h, const bdepth_region* r, size_t n) { normalize_regions(h, r, n, h->regions); return 0; }
 int bdepth_set_shard(bdepth_t* h, int rank, int world, const void* nccl_unique_id) {
@@ -833,7 +857,7 @@ int bdepth_run_resident(bdepth_t* h) {
     cudaStream_t sm = h->s_main;
     CK(cudaMemsetAsync(h->misc.p, 0, 8, sm));
     uint64_t a = std::max(h->own_lo, h->cnt_base) - h->cnt_base, b = std::min(h->own_hi, h->cnt_base + h->win_len) - h->cnt_base;
-    if (b > a) { k_count_covered<<<2048, 256, 0, sm>>>(h->counts.as<uint32_t>(), h->win_len, a, b, (unsigned long long*)h->misc.p); CK(cudaGetLastError()); h->st.gpu_launches++; }
+    if (b > a) { k_count_covered<<<2048, 256, 0, sm>>>(h->counts.as<uint32_t>(), h->win_len, a, b, (unsigned long long*)h->misc.p, N_PLANES * (int)h->S); CK(cudaGetLastError()); h->st.gpu_launches++; }
     unsigned long long cov = 0; CK(cudaMemcpyAsync(&cov, h->misc.p, 8, cudaMemcpyDeviceToHost, sm)); CK(cudaStreamSynchronize(sm));
     h->st.covered_positions = cov;
     h->st.ms_total_device = h->st.ms_h2d + h->st.ms_inflate + h->st.ms_scan + h->st.ms_coverage + h->st.ms_exchange;
@@ -854,7 +878,7 @@ int bdepth_run_base(bdepth_t* h, bdepth_tile_cb cb, void* user) {
     // covered positions (rows of default `depth base`), over the range this rank owns
     CK(cudaMemsetAsync(h->misc.p, 0, 8, sm));
     { uint64_t ca = std::max(h->own_lo, h->cnt_base) - h->cnt_base, cb2 = std::min(h->own_hi, h->cnt_base + h->win_len) - h->cnt_base;
-      if (cb2 > ca) { k_count_covered<<<2048, 256, 0, sm>>>(h->counts.as<uint32_t>(), h->win_len, ca, cb2, (unsigned long long*)h->misc.p); CK(cudaGetLastError()); h->st.gpu_launches++; } }
+      if (cb2 > ca) { k_count_covered<<<2048, 256, 0, sm>>>(h->counts.as<uint32_t>(), h->win_len, ca, cb2, (unsigned long long*)h->misc.p, N_PLANES * (int)h->S); CK(cudaGetLastError()); h->st.gpu_launches++; } }
     unsigned long long cov = 0; CK(cudaMemcpyAsync(&cov, h->misc.p, 8, cudaMemcpyDeviceToHost, sm));
     CK(cudaEventRecord(e0, sm));
     if (h->world > 1) {   // multi-GPU: ranks deliver disjoint, ordered pieces: clip the not-yet-delivered ranges to the owned range
@@ -879,7 +903,9 @@ static int run_segments(bdepth* h, const std::vector<SegDef>& segs, const uint32
     if (n_thr > 16) return fail(h, BDEPTH_ERR_ARG, "at most 16 coverage thresholds are supported");
     int rc = init_device(h); if (rc) return rc;
     const size_t n = segs.size();
-    reads.assign(n, 0); bases.assign(n, 0); cov.assign(n * std::max<size_t>(n_thr, 1), 0);
+    const size_t NS = (h->combined || h->hdr.sample_names.size() <= 1) ? 1 : h->hdr.sample_names.size();   // layout: [sample][..]
+    const size_t nt1 = std::max<size_t>(n_thr, 1);
+    reads.assign(NS * n, 0); bases.assign(NS * n, 0); cov.assign(NS * n * nt1, 0);
     // linear-coordinate segments, clipped to the reference
     std::vector<uint64_t> a(n), b(n);
     for (size_t i = 0; i < n; i++) {
@@ -894,12 +920,12 @@ static int run_segments(bdepth* h, const std::vector<SegDef>& segs, const uint32
     for (size_t i = 0; i < n; i++) { ss[i] = a[order[i]]; se[i] = b[order[i]]; mx = std::max(mx, se[i]); pm[i] = mx; }
     auto& S = h->seg;
     size_t nn = n ? n : 1;
-    CK(S.s.ensure(nn * 8)); CK(S.e.ensure(nn * 8)); CK(S.pmax.ensure(nn * 8)); CK(S.id.ensure(nn * 4)); CK(S.reads.ensure(nn * 4));
+    CK(S.s.ensure(nn * 8)); CK(S.e.ensure(nn * 8)); CK(S.pmax.ensure(nn * 8)); CK(S.id.ensure(nn * 4)); CK(S.reads.ensure(NS * nn * 4));
     if (n) {
         CK(cudaMemcpy(S.s.p, ss.data(), n * 8, cudaMemcpyHostToDevice)); CK(cudaMemcpy(S.e.p, se.data(), n * 8, cudaMemcpyHostToDevice));
         CK(cudaMemcpy(S.pmax.p, pm.data(), n * 8, cudaMemcpyHostToDevice)); CK(cudaMemcpy(S.id.p, order.data(), n * 4, cudaMemcpyHostToDevice));
     }
-    CK(cudaMemset(S.reads.p, 0, nn * 4));
+    CK(cudaMemset(S.reads.p, 0, NS * nn * 4));
     S.on = true; S.n = (uint32_t)n;
     rc = run_pipeline(h, RUN_FULL, nullptr);
     S.on = false;
@@ -911,7 +937,7 @@ static int run_segments(bdepth* h, const std::vector<SegDef>& segs, const uint32
     DevBuf da, db, dthr, dbases, dcov;
     auto cleanup = [&]() { da.release(); db.release(); dthr.release(); dbases.release(); dcov.release(); };
     cudaError_t ce;
-    if ((ce = da.ensure(nn * 8)) || (ce = db.ensure(nn * 8)) || (ce = dthr.ensure(64)) || (ce = dbases.ensure(nn * 4)) || (ce = dcov.ensure(nn * 4 * std::max<size_t>(n_thr, 1)))) { cleanup(); return fail(h, BDEPTH_ERR_CUDA, "out of device memory (%s)", cudaGetErrorString(ce)); }
+    if ((ce = da.ensure(nn * 8)) || (ce = db.ensure(nn * 8)) || (ce = dthr.ensure(64)) || (ce = dbases.ensure(NS * nn * 4)) || (ce = dcov.ensure(NS * nn * 4 * nt1))) { cleanup(); return fail(h, BDEPTH_ERR_CUDA, "out of device memory (%s)", cudaGetErrorString(ce)); }
     for (size_t i = 0; i < n; i++) {
         uint64_t lo = std::max(h->cnt_base, h->own_lo), hi = std::min(h->cnt_base + h->win_len, h->own_hi); if (hi < lo) hi = lo;
         uint64_t wa = std::min(std::max(a[i], lo), hi), wb = std::min(std::max(b[i], lo), hi);
@@ -919,19 +945,21 @@ static int run_segments(bdepth* h, const std::vector<SegDef>& segs, const uint32
     }
     if (n) { cudaMemcpyAsync(da.p, a.data(), n * 8, cudaMemcpyHostToDevice, sm); cudaMemcpyAsync(db.p, b.data(), n * 8, cudaMemcpyHostToDevice, sm); }
     if (n_thr) cudaMemcpyAsync(dthr.p, thr, n_thr * 4, cudaMemcpyHostToDevice, sm);
-    cudaMemsetAsync(dbases.p, 0, nn * 4, sm); cudaMemsetAsync(dcov.p, 0, nn * 4 * std::max<size_t>(n_thr, 1), sm);
+    cudaMemsetAsync(dbases.p, 0, NS * nn * 4, sm); cudaMemsetAsync(dcov.p, 0, NS * nn * 4 * nt1, sm);
     if (n) {
-        k_segment_stats<<<(unsigned)((n * 32 + 255) / 256), 256, 0, sm>>>(h->counts.as<uint32_t>(), h->win_len, da.as<uint64_t>(), db.as<uint64_t>(), (uint32_t)n, dthr.as<uint32_t>(), (uint32_t)n_thr, dbases.as<uint32_t>(), dcov.as<uint32_t>());
-        h->st.gpu_launches++;
+        for (size_t si = 0; si < NS; si++) {
+            k_segment_stats<<<(unsigned)((n * 32 + 255) / 256), 256, 0, sm>>>(h->counts.as<uint32_t>() + (uint64_t)si * N_PLANES * h->win_len, h->win_len, da.as<uint64_t>(), db.as<uint64_t>(), (uint32_t)n, dthr.as<uint32_t>(), (uint32_t)n_thr, dbases.as<uint32_t>() + si * n, dcov.as<uint32_t>() + si * n * nt1);
+            h->st.gpu_launches++;
+        }
         if (h->world > 1 && h->comm) {   // per-segment partial sums are additive over ranks
             NcclApi& N = nccl();
-            N.AllReduce(dbases.p, dbases.p, n, NCCL_UINT32, NCCL_SUM, h->comm, sm);
-            if (n_thr) N.AllReduce(dcov.p, dcov.p, n * n_thr, NCCL_UINT32, NCCL_SUM, h->comm, sm);
-            N.AllReduce(S.reads.p, S.reads.p, n, NCCL_UINT32, NCCL_SUM, h->comm, sm);
+            N.AllReduce(dbases.p, dbases.p, NS * n, NCCL_UINT32, NCCL_SUM, h->comm, sm);
+            if (n_thr) N.AllReduce(dcov.p, dcov.p, NS * n * n_thr, NCCL_UINT32, NCCL_SUM, h->comm, sm);
+            N.AllReduce(S.reads.p, S.reads.p, NS * n, NCCL_UINT32, NCCL_SUM, h->comm, sm);
         }
-        cudaMemcpyAsync(bases.data(), dbases.p, n * 4, cudaMemcpyDeviceToHost, sm);
-        if (n_thr) cudaMemcpyAsync(cov.data(), dcov.p, n * n_thr * 4, cudaMemcpyDeviceToHost, sm);
-        cudaMemcpyAsync(reads.data(), S.reads.p, n * 4, cudaMemcpyDeviceToHost, sm);
+        cudaMemcpyAsync(bases.data(), dbases.p, NS * n * 4, cudaMemcpyDeviceToHost, sm);
+        if (n_thr) cudaMemcpyAsync(cov.data(), dcov.p, NS * n * n_thr * 4, cudaMemcpyDeviceToHost, sm);
+        cudaMemcpyAsync(reads.data(), S.reads.p, NS * n * 4, cudaMemcpyDeviceToHost, sm);
     }
     cudaEventRecord(e1, sm);
     ce = cudaStreamSynchronize(sm);
@@ -943,16 +971,16 @@ static int run_segments(bdepth* h, const std::vector<SegDef>& segs, const uint32
     return 0;
 }
 
-static int deliver_segments(bdepth* h, const std::vector<SegDef>& segs, const std::vector<uint8_t>& emit, size_t n_thr,
-                            const std::vector<uint32_t>& reads, const std::vector<uint32_t>& bases, const std::vector<uint32_t>& cov, bdepth_stat_cb cb, void* user) {
-    if (!cb) return 0;
-    std::vector<uint32_t> c(std::max<size_t>(n_thr, 1));
-    uint64_t idx = 0;
-    for (size_t i = 0; i < segs.size(); i++) {
-        if (!emit.empty() && !emit[i]) continue;
-        for (size_t t = 0; t < n_thr; t++) c[t] = cov[t * segs.size() + i];
-        bdepth_region_stat s{(int32_t)segs[i].ref, segs[i].start, segs[i].end, reads[i], bases[i], c.data()};
-        if (cb(user, &s, idx++)) return fail(h, BDEPTH_ERR_CALLBACK, "stat callback aborted");
+// results are laid out [sample][segment] (cov: [sample][threshold][segment]); delivery order is the reference's:
+// regions outer, samples inner (depth.d:925-930, :946-949)
+static int deliver_one(bdepth* h, const SegDef& sd, size_t i, size_t n, size_t n_thr, const std::vector<uint32_t>& reads, const std::vector<uint32_t>& bases,
+                       const std::vector<uint32_t>& cov, bool zero, bdepth_stat_cb cb, void* user, uint64_t idx) {
+    const size_t NS = (h->combined || h->hdr.sample_names.size() <= 1) ? 1 : h->hdr.sample_names.size(), nt1 = std::max<size_t>(n_thr, 1);
+    std::vector<uint32_t> c(nt1, 0);
+    for (size_t si = 0; si < NS; si++) {
+        if (!zero) for (size_t t = 0; t < n_thr; t++) c[t] = cov[si * n * nt1 + t * n + i];
+        bdepth_region_stat st{(int32_t)sd.ref, sd.start, sd.end, zero ? 0u : reads[si * n + i], zero ? 0u : bases[si * n + i], c.data(), (int32_t)si};
+        if (cb(user, &st, idx)) return fail(h, BDEPTH_ERR_CALLBACK, "stat callback aborted");
     }
     return 0;
 }
@@ -981,7 +1009,6 @@ int bdepth_run_windows(bdepth_t* h, uint32_t window, uint32_t overlap, const uin
     long last_has = -1;
     for (size_t r = 0; r < nref; r++) if ((h->ref_has_host[r >> 5] >> (r & 31)) & 1) last_has = (long)r;
     if (!cb) return 0;
-    std::vector<uint32_t> c(std::max<size_t>(n_thr, 1)), zero(std::max<size_t>(n_thr, 1), 0);
     uint64_t idx = 0;
     for (size_t r = 0; r < nref; r++) {
         bool has = (h->ref_has_host[r >> 5] >> (r & 31)) & 1;
@@ -989,10 +1016,8 @@ int bdepth_run_windows(bdepth_t* h, uint32_t window, uint32_t overlap, const uin
         uint32_t shift = (!has && last_has >= 0 && (long)r == last_has + 1) ? n_full[last_has] * step : 0;
         for (uint32_t k = 0; k < m; k++) {
             size_t i = first[r] + k;
-            bdepth_region_stat st;
-            if (shift) st = bdepth_region_stat{(int32_t)r, shift + k * step, shift + k * step + window, 0, 0, zero.data()};
-            else { for (size_t t = 0; t < n_thr; t++) c[t] = cov[t * segs.size() + i]; st = bdepth_region_stat{(int32_t)r, segs[i].start, segs[i].end, reads[i], bases[i], c.data()}; }
-            if (cb(user, &st, idx++)) return fail(h, BDEPTH_ERR_CALLBACK, "stat callback aborted");
+            SegDef sd = shift ? SegDef{(uint32_t)r, shift + k * step, shift + k * step + window} : segs[i];
+            rc = deliver_one(h, sd, i, segs.size(), n_thr, reads, bases, cov, shift != 0, cb, user, idx++); if (rc) return rc;
         }
     }
     return 0;
@@ -1006,7 +1031,9 @@ int bdepth_run_regions(bdepth_t* h, const bdepth_region* regions, size_t n, cons
     }
     std::vector<uint32_t> reads, bases, cov;
     int rc = run_segments(h, segs, thr, n_thr, reads, bases, cov); if (rc) return rc;
-    return deliver_segments(h, segs, {}, n_thr, reads, bases, cov, cb, user);
+    if (!cb) return 0;
+    for (size_t i = 0; i < n; i++) { rc = deliver_one(h, segs[i], i, n, n_thr, reads, bases, cov, false, cb, user, i); if (rc) return rc; }
+    return 0;
 }
 
 int bdepth_ref_has_reads(const bdepth_t* h, int ref) {

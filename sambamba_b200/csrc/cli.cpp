@@ -7,8 +7,7 @@
 // D binding that would replace this file is in sambamba_b200/d/bdepth.d and INTEGRATION.md.
 //
 // Not supported through the GPU path yet (rejected with a message, never silently wrong):
-//   -F with anything but the default filter or "" ; -m ; several BAM files ; per-sample output for
-//   multi-sample headers (use --combined).
+//   -F with anything but the default filter or "" ; -m ; several BAM files ; more than 64 samples without --combined.
 #include <math.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -137,7 +136,7 @@ static void parse_region_string(const std::string& s, std::string& ref, uint32_t
 struct Ctx {
     bdepth_t* h = nullptr; Out out; int mode = 0;
     double min_cov = 0, max_cov = 1e50; bool combined = false, annotate = false;
-    std::vector<std::string> ref_names; std::string sample;
+    std::vector<std::string> ref_names; std::vector<std::string> samples;
     std::vector<uint32_t> thr;
     // region mode
     std::vector<std::string> raw_lines; bool window_mode = false;
@@ -147,20 +146,26 @@ struct Ctx {
 static int base_tile_cb(void* user, const bdepth_tile* t) {
     Ctx& c = *(Ctx*)user; Out& o = c.out;
     const std::string& name = c.ref_names[t->ref_id];
-    const uint32_t* P[7]; for (int p = 0; p < 7; p++) P[p] = t->counts + (size_t)p * t->stride;
+    const uint32_t S = t->n_samples;
     for (uint32_t i = 0; i < t->len; i++) {
-        uint64_t a = P[0][i], cc = P[1][i], g = P[2][i], tt = P[3][i], n = P[4][i], d = P[5][i], s = P[6][i];
-        uint64_t total = a + cc + g + tt + n + d + s;
-        // depth.d:539-541: row printed iff min_cov <= COV <= max_cov (or -a).  A position without any read and a
-        // covered position are indistinguishable here only when COV == 0, where both print the same text.
-        bool ok = (double)total >= c.min_cov && (double)total <= c.max_cov;
-        if (!ok && !c.annotate) continue;
-        if (total == 0 && c.min_cov > 0) continue;             // no column at all: nothing is written when min_cov > 0 (depth.d:568-572)
-        o.str(name.data(), name.size()); o.ch('\t'); o.u64((uint64_t)t->start + i); o.ch('\t'); o.u64(total);
-        o.ch('\t'); o.u64(a); o.ch('\t'); o.u64(cc); o.ch('\t'); o.u64(g); o.ch('\t'); o.u64(tt); o.ch('\t'); o.u64(d); o.ch('\t'); o.u64(s);
-        if (!c.combined) { o.ch('\t'); o.str(c.sample.data(), c.sample.size()); }
-        if (c.annotate) { o.ch('\t'); o.ch(total == 0 ? (c.min_cov > 0 ? 'n' : 'y') : (ok ? 'y' : 'n')); }
-        o.ch('\n');
+        // does any sample have a column here?  (min_cov > 0: positions without any read print nothing, depth.d:568-572)
+        uint64_t any = 0;
+        for (uint32_t si = 0; si < S; si++) for (int p = 0; p < 7; p++) any |= t->counts[(size_t)si * t->sample_stride + (size_t)p * t->stride + i];
+        if (!any && c.min_cov > 0) continue;
+        for (uint32_t si = 0; si < S; si++) {
+            const uint32_t* P = t->counts + (size_t)si * t->sample_stride + i;
+            uint64_t a = P[0], cc = P[t->stride], g = P[2 * (size_t)t->stride], tt = P[3 * (size_t)t->stride], n = P[4 * (size_t)t->stride], d = P[5 * (size_t)t->stride], s = P[6 * (size_t)t->stride];
+            uint64_t total = a + cc + g + tt + n + d + s;
+            // depth.d:539-541: row printed iff min_cov <= COV <= max_cov (or -a); a failing sample ends the position
+            // (`return`, not `continue`: the remaining samples are dropped -- SURVEY quirk 2)
+            bool ok = (double)total >= c.min_cov && (double)total <= c.max_cov;
+            if (!ok && !c.annotate) break;
+            o.str(name.data(), name.size()); o.ch('\t'); o.u64((uint64_t)t->start + i); o.ch('\t'); o.u64(total);
+            o.ch('\t'); o.u64(a); o.ch('\t'); o.u64(cc); o.ch('\t'); o.u64(g); o.ch('\t'); o.u64(tt); o.ch('\t'); o.u64(d); o.ch('\t'); o.u64(s);
+            if (!c.combined) { const std::string& sn = c.samples[si]; o.ch('\t'); o.str(sn.data(), sn.size()); }
+            if (c.annotate) { o.ch('\t'); o.ch(!any ? (c.min_cov > 0 ? 'n' : 'y') : (ok ? 'y' : 'n')); }
+            o.ch('\n');
+        }
     }
     return 0;
 }
@@ -179,7 +184,7 @@ static int stat_cb(void* user, const bdepth_region_stat* s, uint64_t idx) {
         if (c.thr[j] == 0) pct = 100.0f;
         o.ch('\t'); o.g(pct);
     }
-    if (!c.combined) { o.ch('\t'); o.str(c.sample.data(), c.sample.size()); }
+    if (!c.combined) { const std::string& sn = c.samples[s->sample_id]; o.ch('\t'); o.str(sn.data(), sn.size()); }
     if (c.annotate) { o.ch('\t'); o.ch(ok ? 'y' : 'n'); }
     o.ch('\n');
     return 0;
@@ -266,8 +271,8 @@ int main(int argc, char** argv) {
     if (!bdepth_has_index(c.h)) return die("All files must be indexed");
     int nref = bdepth_n_ref(c.h);
     for (int i = 0; i < nref; i++) c.ref_names.push_back(bdepth_ref_name(c.h, i));
-    if (bdepth_n_samples(c.h) > 1 && !c.combined) return die("multi-sample header: per-sample output is not available in the GPU engine yet (use --combined)");
-    c.sample = bdepth_sample_name(c.h, 0);
+    for (int i = 0; i < bdepth_n_samples(c.h); i++) c.samples.push_back(bdepth_sample_name(c.h, i));
+    bdepth_set_combined(c.h, c.combined ? 1 : 0);
     bdepth_set_filter(c.h, mapq_gt, flag_reject);
     bdepth_set_min_baseq(c.h, (uint32_t)min_bq);
     auto find_ref = [&](const std::string& n) { for (int i = 0; i < nref; i++) if (c.ref_names[i] == n) return i; return -1; };

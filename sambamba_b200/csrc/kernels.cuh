@@ -155,14 +155,44 @@ __global__ void k2_walk(ScanParams sp, const int64_t* __restrict__ chunk_start, 
 struct RecordSoA {
     uint64_t* start;     // linear coordinate of the first reference base (UINT64_MAX-1 when unplaced)
     uint32_t* span;      // reference bases covered, clipped to the reference end; 0 => contributes nothing
-    uint32_t* meta;      // flag << 16 | mapq << 8 | bit0 pass | bit1 long
+    uint32_t* meta;      // flag << 16 | mapq << 8 | sample << 2 | bit1 long | bit0 pass
     int64_t* off;        // offset of the record's refID field relative to the batch's inflated bytes (negative inside the carry)
     uint32_t* ncl;       // n_cigar << 8 | l_read_name
     int32_t*  lseq;
 };
 struct ScanStats {      // device-side accumulators
-    unsigned long long n_pass, n_cigar, seq_bytes, max_end, min_start, n_long, max_start;
+    unsigned long long n_pass, n_cigar, seq_bytes, max_end, min_start, n_long, max_start, rg_err;   // rg_err: 1 + index of the first read with an unknown RG
 };
+// @RG ID -> sample table (depth.d:1170-1181); ids are NUL-terminated, concatenated.  n_rg == 0 disables the scan.
+struct RgTable { const uint8_t* ids; const uint32_t* offs; const uint8_t* sample_of; uint32_t n_rg; };
+
+// CustomBamRead (depth.d:240-250): linear scan of the aux area for RG:Z (read.d:1070-1087); returns the sample id,
+// 0 when the read has no RG tag, -1 when its read group is not in the header.
+__device__ __forceinline__ int sample_of_record(const RgTable& rg, const uint8_t* aux, const uint8_t* end) {
+    while (aux + 3 <= end) {
+        uint8_t t0 = aux[0], t1 = aux[1], ty = aux[2];
+        const uint8_t* v = aux + 3;
+        if (t0 == 'R' && t1 == 'G' && ty == 'Z') {
+            for (uint32_t g = 0; g < rg.n_rg; g++) {
+                const uint8_t* id = rg.ids + rg.offs[g]; const uint8_t* q = v; bool eq = true;
+                while (q < end && *q) { if (*id != *q) { eq = false; break; } id++; q++; }
+                if (eq && *id == 0) return rg.sample_of[g];
+            }
+            return -1;
+        }
+        size_t n;
+        switch (ty) {
+        case 'A': case 'c': case 'C': n = 1; break;
+        case 's': case 'S': n = 2; break;
+        case 'i': case 'I': case 'f': n = 4; break;
+        case 'Z': case 'H': { const uint8_t* q = v; while (q < end && *q) q++; n = (size_t)(q - v) + 1; break; }
+        case 'B': { if (v + 5 > end) return 0; uint8_t st = v[0]; uint32_t cnt = ldu32(v + 1); size_t es = (st == 'c' || st == 'C') ? 1 : (st == 's' || st == 'S') ? 2 : 4; n = 5 + es * cnt; break; }
+        default: return 0;
+        }
+        aux = v + n;
+    }
+    return 0;
+}
 
 __device__ __forceinline__ bool cig_rcons(uint32_t op) { return op == 0 || op == 2 || op == 3 || op == 7 || op == 8; }
 __device__ __forceinline__ bool cig_qcons(uint32_t op) { return op == 0 || op == 1 || op == 4 || op == 7 || op == 8; }
@@ -171,7 +201,7 @@ __device__ __forceinline__ bool cig_match(uint32_t op) { return op == 0 || op ==
 __global__ void k2_decode(ScanParams sp, const int64_t* __restrict__ chunk_start, uint32_t n_chunks, const uint32_t* __restrict__ slot_base,
                           const uint16_t* __restrict__ slots, const uint32_t* __restrict__ count, const uint32_t* __restrict__ rec_base,
                           RecordSoA soa, int mapq_gt, uint32_t flag_reject, ScanStats* __restrict__ st, uint32_t* __restrict__ long_list,
-                          uint32_t* __restrict__ ref_has_reads) {
+                          uint32_t* __restrict__ ref_has_reads, RgTable rg) {
     uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= n_chunks) return;
     uint32_t n = count[warp];
@@ -205,8 +235,15 @@ __global__ void k2_decode(ScanParams sp, const int64_t* __restrict__ chunk_start
         }
         bool is_long = pass && span_eff > SPAN_SHORT;
         uint32_t r = rb + k;
+        uint32_t sample = 0;
+        if (rg.n_rg && pass) {
+            uint32_t bs = ldu32(sp.u + o);
+            int sid = sample_of_record(rg, cg + 4u * n_cigar + ((uint32_t)l_seq + 1) / 2 + (uint32_t)l_seq, p + bs);
+            if (sid < 0) { atomicMin(&st->rg_err, (unsigned long long)r + 1); sid = 0; }
+            sample = (uint32_t)sid & 63u;
+        }
         soa.start[r] = start; soa.span[r] = span_eff;
-        soa.meta[r] = (flag << 16) | (mapq << 8) | (pass ? 1u : 0u) | (is_long ? 2u : 0u);
+        soa.meta[r] = (flag << 16) | (mapq << 8) | (sample << 2) | (pass ? 1u : 0u) | (is_long ? 2u : 0u);
         soa.off[r] = o + 4; soa.ncl[r] = (n_cigar << 8) | l_name; soa.lseq[r] = l_seq;
         loc_cig += n_cigar;
         if (pass) {
@@ -291,7 +328,7 @@ __device__ __forceinline__ void add_base(GatherAcc& a, int j, const uint8_t* seq
 template <bool MINQ>
 __global__ void __launch_bounds__(256) k3_gather(RecordSoA soa, const uint8_t* __restrict__ u, uint64_t tiles_base, uint64_t cnt_base, uint64_t win_len,
                                                   const uint32_t* __restrict__ tile_first, const uint32_t* __restrict__ tile_lo,
-                                                  uint32_t* __restrict__ counts, uint32_t minq) {
+                                                  uint32_t* __restrict__ counts, uint32_t minq, int sample_sel) {
     uint32_t tile = blockIdx.x;
     uint32_t lo = tile_lo[tile];
     if (lo == 0xFFFFFFFFu) return;                       // no passing short read touches this tile
@@ -308,7 +345,8 @@ __global__ void __launch_bounds__(256) k3_gather(RecordSoA soa, const uint8_t* _
         uint64_t s = 0; uint32_t sp = 0; bool ov = false;
         if (r < hi) {
             s = soa.start[r]; sp = soa.span[r];
-            ov = (soa.meta[r] & 3u) == 1u && s < w1 && s + sp > w0;
+            uint32_t mt = soa.meta[r];
+            ov = (mt & 3u) == 1u && (sample_sel < 0 || (int)((mt >> 2) & 63u) == sample_sel) && s < w1 && s + sp > w0;
         }
         // reads are sorted by start: once the first lane of a group starts at or past w1, we are done
         uint64_t s_first = __shfl_sync(0xFFFFFFFFu, s, 0);
@@ -401,10 +439,11 @@ __global__ void __launch_bounds__(256) k3_gather(RecordSoA soa, const uint8_t* _
 // Long reads: one warp per read, lanes stride over the bases of each op, RED atomics.
 template <bool MINQ>
 __global__ void k3_scatter_long(RecordSoA soa, const uint8_t* __restrict__ u, const uint32_t* __restrict__ long_list, uint32_t n_long,
-                                uint64_t win_base, uint64_t win_len, uint32_t* __restrict__ counts, uint32_t minq) {
+                                uint64_t win_base, uint64_t win_len, uint32_t* __restrict__ counts, uint32_t minq, int sample_sel) {
     uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= n_long) return;
     uint32_t rr = long_list[warp];
+    if (sample_sel >= 0 && (int)((soa.meta[rr] >> 2) & 63u) != sample_sel) return;
     uint64_t rs = soa.start[rr]; uint32_t rspan = soa.span[rr];
     int64_t off = soa.off[rr]; uint32_t ncl = soa.ncl[rr]; uint32_t lseq = (uint32_t)max(soa.lseq[rr], 0);
     uint32_t n_cigar = ncl >> 8, l_name = ncl & 0xFF;
@@ -437,14 +476,13 @@ __global__ void k3_scatter_long(RecordSoA soa, const uint8_t* __restrict__ u, co
 
 // ------------------------------------------------------------------------------------- reducers
 // number of positions in [a, b) (window-relative) whose 7 counters sum to > 0
-__global__ void k_count_covered(const uint32_t* __restrict__ counts, uint64_t win_len, uint64_t a, uint64_t b, unsigned long long* __restrict__ out) {
+__global__ void k_count_covered(const uint32_t* __restrict__ counts, uint64_t win_len, uint64_t a, uint64_t b, unsigned long long* __restrict__ out, int n_planes) {
     uint64_t i = a + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     unsigned long long n = 0;
     for (; i < b; i += stride) {
         uint32_t s = 0;
-#pragma unroll
-        for (int pl = 0; pl < N_PLANES; pl++) s |= counts[(uint64_t)pl * win_len + i];
+        for (int pl = 0; pl < n_planes; pl++) s |= counts[(uint64_t)pl * win_len + i];
         n += s != 0;
     }
     for (int sft = 16; sft; sft >>= 1) n += __shfl_xor_sync(0xFFFFFFFFu, n, sft);
@@ -489,10 +527,11 @@ __global__ void k_segment_stats(const uint32_t* __restrict__ counts, uint64_t wi
 template <bool MINQ>
 __global__ void k_read_segments(RecordSoA soa, const uint8_t* __restrict__ u, uint32_t R, const uint64_t* __restrict__ seg_s, const uint64_t* __restrict__ seg_e,
                                 const uint64_t* __restrict__ pmax_end, const uint32_t* __restrict__ seg_id, const uint64_t* __restrict__ seg_min_start, uint32_t n_seg,
-                                uint32_t* __restrict__ out_reads, uint32_t minq) {
+                                uint32_t* __restrict__ out_reads /* [n_samples][n_seg] */, uint32_t minq, uint32_t n_samples) {
     uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= R) return;
     if (!(soa.meta[r] & 1u)) return;
+    const uint32_t samp = n_samples > 1 ? ((soa.meta[r] >> 2) & 63u) : 0u;
     uint64_t rs = soa.start[r]; uint32_t rspan = soa.span[r]; uint64_t re = rs + rspan;
     // candidates: segments with seg_s < re ; walk down from the last such while pmax_end > rs
     uint32_t lo = 0, hi = n_seg;
@@ -521,7 +560,7 @@ __global__ void k_read_segments(RecordSoA soa, const uint8_t* __restrict__ u, ui
             } else if (op == 2 || op == 3) rpos += len;
             else if (cig_qcons(op)) qpos += len;
         }
-        if (hit) atomicAdd(&out_reads[seg_id[k]], 1u);
+        if (hit) atomicAdd(&out_reads[(uint64_t)samp * n_seg + seg_id[k]], 1u);
     }
 }
 

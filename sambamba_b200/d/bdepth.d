@@ -23,10 +23,10 @@ enum : int {
 struct bdepth_region { uint ref_id, start, end; }
 
 /// counts is SoA: plane p (A,C,G,T,N,DEL,REFSKIP) at counts[p*stride .. p*stride+len]
-struct bdepth_tile { int ref_id; uint start, len, stride; const(uint)* counts; }
+struct bdepth_tile { int ref_id; uint start, len, stride; const(uint)* counts; uint n_samples, sample_stride; }
 alias bdepth_tile_cb = int function(void* user, const(bdepth_tile)* tile);
 
-struct bdepth_region_stat { int ref_id; uint start, end, n_reads, n_bases; const(uint)* cov_ge; }
+struct bdepth_region_stat { int ref_id; uint start, end, n_reads, n_bases; const(uint)* cov_ge; int sample_id; }
 alias bdepth_stat_cb = int function(void* user, const(bdepth_region_stat)* s, ulong index);
 
 struct bdepth_stats {
@@ -56,6 +56,7 @@ const(char)* bdepth_sample_name(const(bdepth_t)* h, int i);
 
 int bdepth_set_filter(bdepth_t* h, int mapq_gt, uint flag_reject_mask);
 int bdepth_set_min_baseq(bdepth_t* h, uint q);
+int bdepth_set_combined(bdepth_t* h, int combined);
 int bdepth_set_regions(bdepth_t* h, const(bdepth_region)* r, size_t n);
 int bdepth_set_shard(bdepth_t* h, int rank, int world, const(void)* nccl_unique_id);
 int bdepth_nccl_unique_id(void* out128);

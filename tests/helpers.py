@@ -135,9 +135,9 @@ def header_first_record_offset(u):
     return off, refs
 
 
-def write_bam(path, refs, reads, rg=None, block=0xFF00, level=6, quals=None):
+def write_bam(path, refs, reads, rg=None, block=0xFF00, level=6, quals=None, tags=None):
     """Minimal BAM + dummy BAI writer for hand-made reads: (ref, pos, mapq, flag, cigar[(len,op)], seq, name).
-    quals: optional list of per-read quality lists (default 30 everywhere)."""
+    quals: optional list of per-read quality lists (default 30 everywhere); tags: optional per-read raw aux bytes."""
     import struct
     import zlib
     text = "@HD\tVN:1.6\tSO:coordinate\n" + "".join(f"@SQ\tSN:{n}\tLN:{l}\n" for n, l in refs)
@@ -153,7 +153,7 @@ def write_bam(path, refs, reads, rg=None, block=0xFF00, level=6, quals=None):
         for i in range(0, len(seq), 2):
             packed.append((code[seq[i]] << 4) | (code[seq[i + 1]] if i + 1 < len(seq) else 0))
         rec = struct.pack("<iiIIiiii", ref, pos, (4680 << 16) | (mapq << 8) | len(nm), (flag << 16) | len(cigar), len(seq), -1, -1, 0)
-        rec += nm + b"".join(struct.pack("<I", (l << 4) | op) for l, op in cigar) + bytes(packed) + (bytes(quals[ri]) if quals else bytes([30] * len(seq)))
+        rec += nm + b"".join(struct.pack("<I", (l << 4) | op) for l, op in cigar) + bytes(packed) + (bytes(quals[ri]) if quals else bytes([30] * len(seq))) + (tags[ri] if tags else b"")
         body += struct.pack("<i", len(rec)) + rec
     with open(path, "wb") as f:
         for i in range(0, len(body), block):

@@ -123,3 +123,45 @@ def test_odd_block_sizes_and_levels(tmp_path):
             reads_ = reads
         p = helpers.write_bam(str(tmp_path / f"b{block}.bam"), [("a", 5000), ("b", 5000)], reads_, block=max(block, 1), level=level)
         compare(p)
+
+
+def test_multi_sample_header(tmp_path):
+    """@RG -> sample table (depth.d:1170-1181), per-read RG lookup (depth.d:240-250), per-sample rows incl. the
+    `return`-not-`continue` quirk of writeColumn (depth.d:540-541), --combined."""
+    r = random.Random(7)
+    rg = [("rgA", "S1"), ("rgB", "S1"), ("rgC", "S2"), ("rgD", "S3")]
+    reads, tags = [], []
+    pos = 3
+    for i in range(900):
+        cg = [(40, 0)] if i % 7 else [(15, 0), (3, 2), (25, 0)]
+        reads.append((i % 2 if i > 450 else 0, pos % 2500, 60, 0, cg, rnd_seq(r, 40), f"m{i}"))
+        k = i % 9
+        tags.append(b"NMC\x01" + (b"" if k == 8 else b"RGZ" + rg[k % 4][0].encode() + b"\0") + b"ASC\x20")
+        pos += r.randint(0, 9)
+    order = sorted(range(len(reads)), key=lambda i: (reads[i][0], reads[i][1]))
+    reads = [reads[i] for i in order]
+    tags = [tags[i] for i in order]
+    p = helpers.write_bam(str(tmp_path / "ms.bam"), [("c1", 3000), ("c2", 3000), ("c3", 400)], reads, rg=rg, tags=tags)
+    import sambamba_b200 as sb
+    with sb.BDepth(p) as b:
+        assert b.samples == ["S1", "S2", "S3"]
+        per = b.run_base()
+        assert per.shape[0] == 3
+        b.set_combined(True)
+        comb = b.run_base()
+    want, _ = helpers.oracle_counts(p)
+    assert np.array_equal(comb, want)
+    assert np.array_equal(per.sum(axis=0), want)
+    bed = tmp_path / "ms.bed"
+    bed.write_text("c1\t10\t500\nc2\t100\t900\tx\nc1\t400\t1200\n")
+    for args in (["base", p], ["base", "-c", "4", p], ["base", "-c", "0", "-L", "c1:100-300", p], ["base", "-a", "-c", "6", p], ["base", "--combined", p],
+                 ["window", "-w", "500", "-T", "3", p], ["window", "-w", "500", "--combined", "-c", "2", p], ["region", "-L", str(bed), "-T", "2", "-T", "9", p],
+                 ["region", "-L", "c2", "-a", "-c", "3", p]):
+        cli_same(args)
+    # a read group that is not in the header is an error in both implementations
+    tags2 = list(tags)
+    tags2[5] = b"RGZnope\0"
+    p2 = helpers.write_bam(str(tmp_path / "bad.bam"), [("c1", 3000), ("c2", 3000), ("c3", 400)], reads, rg=rg, tags=tags2)
+    rc1, _, err1 = helpers.run_cli(["base", p2])
+    rc2, _, err2 = helpers.oracle_cli(["base", p2])
+    assert rc1 == 1 and rc2 == 1 and b"read group" in err1 and b"not present in the header" in err2
