@@ -166,6 +166,13 @@ int bdepth_run_windows(bdepth_t* h, uint32_t window, uint32_t overlap, const uin
 /* depth region: stats for the given regions, delivered in the given order. */
 int bdepth_run_regions(bdepth_t* h, const bdepth_region* regions, size_t n, const uint32_t* thresholds, size_t n_thresholds, bdepth_stat_cb cb, void* user);
 
+/* `depth base` with the row text produced on the GPU: the rows PerBasePrinter would print
+ * (depth.d:534-555, zero rows :452-487) for one sample or --combined, delivered in order as text chunks.
+ * Returns BDEPTH_ERR_ARG for multi-sample per-sample output (use bdepth_run_base and format on the host). */
+typedef struct { double min_cov, max_cov; int annotate; } bdepth_text_opts;
+typedef int (*bdepth_text_cb)(void* user, const char* text, size_t len);
+int bdepth_run_base_text(bdepth_t* h, const bdepth_text_opts* opts, bdepth_text_cb cb, void* user);
+
 int bdepth_get_stats(const bdepth_t* h, bdepth_stats* out);
 /* After a run: 1 if the reference has at least one read that produced a pileup column (the
  * condition under which depth.d:1225-1229 prints "Processing reference #k"). */

@@ -45,6 +45,11 @@ class Stats(C.Structure):
         return {n: getattr(self, n) for n, _ in self._fields_}
 
 
+class TextOpts(C.Structure):
+    _fields_ = [("min_cov", C.c_double), ("max_cov", C.c_double), ("annotate", C.c_int)]
+
+
+TEXT_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t)
 TILE_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(Tile))
 STAT_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(RegionStat), C.c_uint64)
 
@@ -91,6 +96,7 @@ def load_library():
     L.bdepth_run_resident.argtypes = [vp]
     L.bdepth_plan_shards.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_uint64)]
     L.bdepth_run_base.argtypes = [vp, TILE_CB, vp]
+    L.bdepth_run_base_text.argtypes = [vp, C.POINTER(TextOpts), TEXT_CB, vp]
     L.bdepth_run_windows.argtypes = [vp, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32), C.c_size_t, STAT_CB, vp]
     L.bdepth_run_regions.argtypes = [vp, C.POINTER(Region), C.c_size_t, C.POINTER(C.c_uint32), C.c_size_t, STAT_CB, vp]
     L.bdepth_get_stats.argtypes = [vp, C.POINTER(Stats)]
@@ -107,7 +113,7 @@ EXPORTED_SYMBOLS = [
     "bdepth_device_count", "bdepth_open", "bdepth_open_memory", "bdepth_close", "bdepth_last_error", "bdepth_n_ref",
     "bdepth_ref_name", "bdepth_ref_length", "bdepth_header_text", "bdepth_is_coordinate_sorted", "bdepth_has_index",
     "bdepth_n_samples", "bdepth_sample_name", "bdepth_set_filter", "bdepth_set_min_baseq", "bdepth_set_combined", "bdepth_set_regions",
-    "bdepth_set_shard", "bdepth_nccl_unique_id", "bdepth_plan_shards", "bdepth_set_tuning", "bdepth_stage", "bdepth_run_resident", "bdepth_run_base",
+    "bdepth_set_shard", "bdepth_nccl_unique_id", "bdepth_plan_shards", "bdepth_set_tuning", "bdepth_stage", "bdepth_run_resident", "bdepth_run_base", "bdepth_run_base_text",
     "bdepth_run_windows", "bdepth_run_regions", "bdepth_get_stats", "bdepth_ref_has_reads", "bdepth_inflate_to_host", "bdepth_scan_to_host",
 ]
 
@@ -257,6 +263,18 @@ class BDepth:
         if out is None:
             return np.zeros((7, max(0, wb - wa)), np.uint32)
         return out[0] if out.shape[0] == 1 else out          # [7, n] for a single counter set, [S, 7, n] per sample
+
+    def run_base_text(self, min_cov=1.0, max_cov=1e50, annotate=False, collect=True):
+        """`depth base` rows formatted on the GPU; returns the text (bytes) when collect=True."""
+        parts = []
+
+        def cb(_user, ptr, n):
+            if collect:
+                parts.append(C.string_at(ptr, n))
+            return 0
+        opts = TextOpts(min_cov, max_cov, 1 if annotate else 0)
+        self._ck(self.L.bdepth_run_base_text(self.h, C.byref(opts), TEXT_CB(cb), None))
+        return b"".join(parts)
 
     def _run_stats(self, fn):
         rows = []

@@ -109,6 +109,7 @@ struct bdepth {
     bool combined = false;                // --combined: one counter set for all samples
     uint32_t S = 1;                       // counter sets in the current run (samples, or 1)
     DevBuf rg_ids, rg_offs, rg_samp;
+    DevBuf text[2], text_tiles, text_offs, text_zero;
     uint64_t batch_u = 6ull << 30;
     uint64_t window_positions = 0;
     // ---- shard (resolved lazily)
@@ -766,6 +767,7 @@ void bdepth_close(bdepth_t* h) {
     DevBuf* bufs[] = {&h->comp, &h->descs, &h->status, &h->ubuf, &h->chunk_start, &h->entry, &h->exitb, &h->count, &h->slot_base, &h->slots, &h->rec_base, &h->walk_list, &h->soa_start, &h->soa_span, &h->soa_meta, &h->soa_off, &h->soa_ncl, &h->soa_lseq, &h->long_list, &h->tile_first, &h->tile_lo, &h->counts, &h->ref_len_d, &h->ref_lin0_d, &h->scan_stats, &h->ref_has, &h->misc};
     for (DevBuf* b : bufs) b->release();
     h->rg_ids.release(); h->rg_offs.release(); h->rg_samp.release();
+    h->text[0].release(); h->text[1].release(); h->text_tiles.release(); h->text_offs.release(); h->text_zero.release();
     h->seg.s.release(); h->seg.e.release(); h->seg.pmax.release(); h->seg.id.release(); h->seg.reads.release();
     if (h->comm) { nccl().CommDestroy(h->comm); h->comm = nullptr; }
     if (h->pinned) cudaFreeHost(h->pinned);
@@ -891,6 +893,91 @@ int bdepth_run_base(bdepth_t* h, bdepth_tile_cb cb, void* user) {
     CK(cudaEventRecord(e1, h->s_d2h)); CK(cudaStreamSynchronize(h->s_d2h)); CK(cudaStreamSynchronize(sm));
     h->st.covered_positions = cov;
     float t = 0; CK(cudaEventElapsedTime(&t, e0, e1)); h->st.ms_d2h = t;      // the part of the D2H that was not hidden behind the kernels
+    h->st.ms_total_device = h->st.ms_h2d + h->st.ms_inflate + h->st.ms_scan + h->st.ms_coverage + h->st.ms_exchange + h->st.ms_d2h;
+    return 0;
+}
+
+// ---- base mode with GPU-side text
+int bdepth_run_base_text(bdepth_t* h, const bdepth_text_opts* o, bdepth_text_cb cb, void* user) {
+    if (!o) return fail(h, BDEPTH_ERR_ARG, "null options");
+    if (!h->combined && h->hdr.sample_names.size() > 1) return fail(h, BDEPTH_ERR_ARG, "GPU text formatting handles one sample or --combined; use bdepth_run_base for per-sample rows");
+    int rc = run_pipeline(h, RUN_FULL, nullptr); if (rc) return rc;
+    cudaStream_t sm = h->s_main;
+    cudaEvent_t e0 = h->ev[5], e1 = h->ev[6];
+    CK(cudaEventRecord(e0, sm));
+    CK(cudaMemsetAsync(h->misc.p, 0, 8, sm));
+    { uint64_t ca = std::max(h->own_lo, h->cnt_base) - h->cnt_base, cb2 = std::min(h->own_hi, h->cnt_base + h->win_len) - h->cnt_base;
+      if (cb2 > ca) { k_count_covered<<<2048, 256, 0, sm>>>(h->counts.as<uint32_t>(), h->win_len, ca, cb2, (unsigned long long*)h->misc.p, N_PLANES * (int)h->S); CK(cudaGetLastError()); h->st.gpu_launches++; } }
+    unsigned long long cov = 0; CK(cudaMemcpyAsync(&cov, h->misc.p, 8, cudaMemcpyDeviceToHost, sm));
+    TextParams tp; memset(&tp, 0, sizeof tp);
+    tp.min_cov = o->min_cov; tp.max_cov = o->max_cov; tp.annotate = o->annotate ? 1 : 0; tp.with_sample = h->combined ? 0 : 1;
+    const std::string& sn = h->hdr.sample_names[0];
+    if (sn.size() > 255) return fail(h, BDEPTH_ERR_ARG, "sample name too long");
+    tp.sample_len = (uint32_t)sn.size(); memcpy(tp.sample, sn.data(), sn.size());
+    constexpr size_t TEXT_BUF = 128ull << 20;
+    rc = ensure_pinned(h, std::max<size_t>(2 * TEXT_BUF, 2 * EMIT_CHUNK * N_PLANES * 4)); if (rc) return rc;
+    CK(h->text[0].ensure(TEXT_BUF)); CK(h->text[1].ensure(TEXT_BUF));
+    // linear ranges to print (whole genome or merged regions), clipped to what this rank owns, cut at reference ends,
+    // at the counter-window edges (outside it every counter is zero) and into chunks whose text fits the buffer
+    struct Piece { uint32_t ref; uint64_t a, b; bool in_window; };
+    std::vector<Piece> pieces;
+    auto add_range = [&](uint64_t a, uint64_t b) {
+        a = std::max(a, h->own_lo); b = std::min(b, h->own_hi);
+        while (a < b) {
+            size_t ref = std::upper_bound(h->hdr.ref_lin0.begin(), h->hdr.ref_lin0.end(), a) - h->hdr.ref_lin0.begin() - 1;
+            while (ref < h->hdr.ref_len.size() && a >= h->hdr.ref_lin0[ref] + h->hdr.ref_len[ref]) ref++;
+            if (ref >= h->hdr.ref_len.size()) break;
+            uint64_t e = std::min(b, h->hdr.ref_lin0[ref] + h->hdr.ref_len[ref]);
+            bool inw = a >= h->cnt_base && a < h->cnt_base + h->win_len;
+            if (inw) e = std::min(e, h->cnt_base + h->win_len); else if (a < h->cnt_base) e = std::min(e, h->cnt_base);
+            size_t max_row = h->hdr.ref_names[ref].size() + sn.size() + 96;
+            uint64_t cp = std::max<uint64_t>(TEXT_TILE, (TEXT_BUF / max_row) / TEXT_TILE * TEXT_TILE);
+            e = std::min(e, a + cp);
+            if (inw || o->min_cov <= 0) pieces.push_back({(uint32_t)ref, a, e, inw});      // zero rows only exist when min_cov == 0
+            a = e;
+        }
+    };
+    if (h->regions.empty()) add_range(0, h->hdr.total_len);
+    else for (auto& g : h->regions) add_range(h->hdr.ref_lin0[g.ref_id] + g.start, h->hdr.ref_lin0[g.ref_id] + g.end);
+    uint64_t max_piece = 0; for (auto& p : pieces) max_piece = std::max(max_piece, p.b - p.a);
+    CK(h->text_tiles.ensure((max_piece / TEXT_TILE + 2) * 4)); CK(h->text_offs.ensure((max_piece / TEXT_TILE + 2) * 8 + 16));
+    bool need_zero = false; for (auto& p : pieces) need_zero |= !p.in_window;
+    if (need_zero) { CK(h->text_zero.ensure(max_piece * 4 + 64)); CK(cudaMemsetAsync(h->text_zero.p, 0, max_piece * 4 + 64, sm)); }
+    size_t pend_len[2] = {0, 0}; bool pend[2] = {false, false};
+    auto deliver = [&](int slot) -> int {
+        if (!pend[slot]) return 0;
+        CK(cudaEventSynchronize(h->ev[8 + slot])); pend[slot] = false;
+        if (cb && pend_len[slot] && cb(user, (const char*)h->pinned + (size_t)slot * TEXT_BUF, pend_len[slot])) return fail(h, BDEPTH_ERR_CALLBACK, "text callback aborted");
+        return 0;
+    };
+    for (size_t i = 0; i < pieces.size(); i++) {
+        const Piece& p = pieces[i]; int slot = (int)(i & 1);
+        rc = deliver(slot); if (rc) return rc;                       // the slot's previous chunk must be consumed before reuse
+        const std::string& nm = h->hdr.ref_names[p.ref];
+        if (nm.size() > 255) return fail(h, BDEPTH_ERR_ARG, "reference name too long");
+        tp.name_len = (uint32_t)nm.size(); memcpy(tp.name, nm.data(), nm.size());
+        uint32_t n = (uint32_t)(p.b - p.a), n_tiles = (n + TEXT_TILE - 1) / TEXT_TILE, pos0 = (uint32_t)(p.a - h->hdr.ref_lin0[p.ref]);
+        const uint32_t* cnt = p.in_window ? h->counts.as<uint32_t>() : h->text_zero.as<uint32_t>();
+        uint64_t wl = p.in_window ? h->win_len : 0, idx0 = p.in_window ? p.a - h->cnt_base : 0;
+        unsigned long long* tot_d = (unsigned long long*)((uint8_t*)h->text_offs.p + (size_t)(max_piece / TEXT_TILE + 2) * 8);
+        k_text_len<<<n_tiles, 256, 0, sm>>>(tp, cnt, wl, idx0, pos0, n, h->text_tiles.as<uint32_t>());
+        k_text_scan<<<1, 1024, 0, sm>>>(h->text_tiles.as<uint32_t>(), n_tiles, (unsigned long long*)h->text_offs.p, tot_d);
+        unsigned long long tot = 0; CK(cudaMemcpyAsync(&tot, tot_d, 8, cudaMemcpyDeviceToHost, sm));
+        CK(cudaStreamSynchronize(sm));
+        if (tot > TEXT_BUF) return fail(h, BDEPTH_ERR_ARG, "internal: text chunk larger than its buffer");
+        if (tot) {
+            k_text_write<<<n_tiles, 256, 0, sm>>>(tp, cnt, wl, idx0, pos0, n, (const unsigned long long*)h->text_offs.p, h->text[slot].as<char>());
+            CK(cudaGetLastError());
+            CK(cudaMemcpyAsync((char*)h->pinned + (size_t)slot * TEXT_BUF, h->text[slot].p, tot, cudaMemcpyDeviceToHost, sm));
+        }
+        h->st.gpu_launches += tot ? 3 : 2;
+        CK(cudaEventRecord(h->ev[8 + slot], sm)); pend[slot] = true; pend_len[slot] = tot;
+        rc = deliver(slot ^ 1); if (rc) return rc;                   // hand out the previous chunk while this one is in flight
+    }
+    rc = deliver(0); if (rc) return rc; rc = deliver(1); if (rc) return rc;
+    CK(cudaEventRecord(e1, sm)); CK(cudaStreamSynchronize(sm));
+    h->st.covered_positions = cov;
+    float t = 0; CK(cudaEventElapsedTime(&t, e0, e1)); h->st.ms_d2h = t;
     h->st.ms_total_device = h->st.ms_h2d + h->st.ms_inflate + h->st.ms_scan + h->st.ms_coverage + h->st.ms_exchange + h->st.ms_d2h;
     return 0;
 }

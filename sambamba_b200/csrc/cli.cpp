@@ -170,6 +170,11 @@ static int base_tile_cb(void* user, const bdepth_tile* t) {
     return 0;
 }
 
+static int text_cb(void* user, const char* text, size_t len) {
+    Ctx& c = *(Ctx*)user; c.out.flush();
+    return fwrite(text, 1, len, c.out.f) == len ? 0 : 1;
+}
+
 static int stat_cb(void* user, const bdepth_region_stat* s, uint64_t idx) {
     Ctx& c = *(Ctx*)user; Out& o = c.out;
     uint32_t length = s->end - s->start;
@@ -295,7 +300,9 @@ int main(int argc, char** argv) {
     }
     if (c.mode == 0) {
         if (has_bed) { if (regs.empty()) { c.out.flush(); bdepth_close(c.h); return 0; } bdepth_set_regions(c.h, regs.data(), regs.size()); }
-        rc = bdepth_run_base(c.h, base_tile_cb, &c);
+        // rows are formatted on the GPU when there is a single counter set; per-sample rows are formatted here
+        if (c.combined || c.samples.size() == 1) { bdepth_text_opts to{c.min_cov, c.max_cov, c.annotate ? 1 : 0}; rc = bdepth_run_base_text(c.h, &to, text_cb, &c); }
+        else rc = bdepth_run_base(c.h, base_tile_cb, &c);
     } else if (c.mode == 1) {
         rc = bdepth_run_regions(c.h, regs.data(), regs.size(), c.thr.data(), c.thr.size(), stat_cb, &c);
     } else {

@@ -564,4 +564,93 @@ __global__ void k_read_segments(RecordSoA soa, const uint8_t* __restrict__ u, ui
     }
 }
 
+
+// ------------------------------------------------------------------------------------- text
+// GPU formatting of `depth base` rows (PerBasePrinter.writeColumn, depth.d:534-555, and the zero rows of
+// writeEmptyColumns, depth.d:452-487) for one sample / --combined:
+//   <ref>\t<pos>\t<COV>\t<A>\t<C>\t<G>\t<T>\t<DEL>\t<REFSKIP>[\t<sample>][\t<y|n>]\n
+// Pass 1 sums the row lengths per 1024-position tile, a single block scans the tile sums, pass 2 re-derives the
+// lengths, scans inside the tile and writes the bytes.  The host only fwrite()s.
+struct TextParams {
+    double min_cov, max_cov;
+    int annotate, with_sample;
+    uint32_t name_len, sample_len;
+    char name[256], sample[256];
+};
+__device__ __forceinline__ uint32_t dec_digits(uint32_t v) {
+    return v < 10u ? 1u : v < 100u ? 2u : v < 1000u ? 3u : v < 10000u ? 4u : v < 100000u ? 5u : v < 1000000u ? 6u : v < 10000000u ? 7u : v < 100000000u ? 8u : v < 1000000000u ? 9u : 10u;
+}
+__device__ __forceinline__ char* put_dec(char* p, uint32_t v) {     // writes v, returns the end
+    uint32_t n = dec_digits(v); char* e = p + n;
+    do { *--e = (char)('0' + v % 10u); v /= 10u; } while (v);
+    return p + n;
+}
+// row length of one position, 0 when the row is not printed
+__device__ __forceinline__ uint32_t text_row(const TextParams& tp, const uint32_t* __restrict__ counts, uint64_t win_len, uint64_t idx, uint32_t pos, uint32_t* v, bool* okp) {
+    uint32_t total = 0;
+#pragma unroll
+    for (int pl = 0; pl < N_PLANES; pl++) { v[pl] = counts[(uint64_t)pl * win_len + idx]; total += v[pl]; }
+    bool ok = (double)total >= tp.min_cov && (double)total <= tp.max_cov;
+    *okp = ok;
+    if (!ok && !tp.annotate) return 0;
+    if (total == 0 && tp.min_cov > 0) return 0;          // no column at all: nothing is written when min_cov > 0 (depth.d:568-572)
+    uint32_t len = tp.name_len + 1 + dec_digits(pos) + 1 + dec_digits(total);
+    len += 1 + dec_digits(v[0]) + 1 + dec_digits(v[1]) + 1 + dec_digits(v[2]) + 1 + dec_digits(v[3]) + 1 + dec_digits(v[5]) + 1 + dec_digits(v[6]);
+    if (tp.with_sample) len += 1 + tp.sample_len;
+    if (tp.annotate) len += 2;
+    return len + 1;
+}
+// pass 1: tile_sum[t] = bytes of tile t (TEXT_TILE positions starting at idx0 + t*TEXT_TILE)
+constexpr int TEXT_TILE = 1024;
+__global__ void __launch_bounds__(256) k_text_len(TextParams tp, const uint32_t* __restrict__ counts, uint64_t win_len, uint64_t idx0, uint32_t pos0, uint32_t n, uint32_t* __restrict__ tile_sum) {
+    __shared__ uint32_t wsum[8];
+    uint32_t base = blockIdx.x * TEXT_TILE, s = 0;
+    for (int k = 0; k < 4; k++) {
+        uint32_t i = base + threadIdx.x * 4 + k; uint32_t v[N_PLANES]; bool ok;
+        if (i < n) s += text_row(tp, counts, win_len, idx0 + i, pos0 + i, v, &ok);
+    }
+    for (int sh = 16; sh; sh >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, sh);
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) { uint32_t t = 0; for (int w = 0; w < 8; w++) t += wsum[w]; tile_sum[blockIdx.x] = t; }
+}
+// exclusive scan of up to 1024*16 tile sums by one block (64-bit offsets)
+__global__ void __launch_bounds__(1024) k_text_scan(const uint32_t* __restrict__ tile_sum, uint32_t n_tiles, unsigned long long* __restrict__ tile_off, unsigned long long* __restrict__ total) {
+    __shared__ unsigned long long part[1024];
+    uint32_t per = (n_tiles + 1023) / 1024, lo = threadIdx.x * per, hi = min(n_tiles, lo + per);
+    unsigned long long s = 0;
+    for (uint32_t i = lo; i < hi; i++) s += tile_sum[i];
+    part[threadIdx.x] = s; __syncthreads();
+    if (threadIdx.x == 0) { unsigned long long a = 0; for (int i = 0; i < 1024; i++) { unsigned long long t = part[i]; part[i] = a; a += t; } *total = a; }
+    __syncthreads();
+    unsigned long long a = part[threadIdx.x];
+    for (uint32_t i = lo; i < hi; i++) { tile_off[i] = a; a += tile_sum[i]; }
+}
+// pass 2: write the rows
+__global__ void __launch_bounds__(256) k_text_write(TextParams tp, const uint32_t* __restrict__ counts, uint64_t win_len, uint64_t idx0, uint32_t pos0, uint32_t n,
+                                                    const unsigned long long* __restrict__ tile_off, char* __restrict__ out) {
+    __shared__ uint32_t wsum[8];
+    uint32_t base = blockIdx.x * TEXT_TILE, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t len[4], v[4][N_PLANES]; bool ok[4]; uint32_t mine = 0;
+    for (int k = 0; k < 4; k++) { uint32_t i = base + threadIdx.x * 4 + k; len[k] = i < n ? text_row(tp, counts, win_len, idx0 + i, pos0 + i, v[k], &ok[k]) : 0; mine += len[k]; }
+    uint32_t incl = mine;
+    for (int sh = 1; sh < 32; sh <<= 1) { uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, sh); if (lane >= (uint32_t)sh) incl += t; }
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    uint32_t woff = 0; for (uint32_t w = 0; w < warp; w++) woff += wsum[w];
+    char* p = out + tile_off[blockIdx.x] + woff + (incl - mine);
+    for (int k = 0; k < 4; k++) {
+        if (!len[k]) continue;
+        uint32_t i = base + threadIdx.x * 4 + k; const uint32_t* c = v[k];
+        uint32_t total = c[0] + c[1] + c[2] + c[3] + c[4] + c[5] + c[6];
+        for (uint32_t q = 0; q < tp.name_len; q++) *p++ = tp.name[q];
+        *p++ = '\t'; p = put_dec(p, pos0 + i); *p++ = '\t'; p = put_dec(p, total);
+        *p++ = '\t'; p = put_dec(p, c[0]); *p++ = '\t'; p = put_dec(p, c[1]); *p++ = '\t'; p = put_dec(p, c[2]); *p++ = '\t'; p = put_dec(p, c[3]);
+        *p++ = '\t'; p = put_dec(p, c[5]); *p++ = '\t'; p = put_dec(p, c[6]);
+        if (tp.with_sample) { *p++ = '\t'; for (uint32_t q = 0; q < tp.sample_len; q++) *p++ = tp.sample[q]; }
+        if (tp.annotate) { *p++ = '\t'; *p++ = total == 0 ? (tp.min_cov > 0 ? 'n' : 'y') : (ok[k] ? 'y' : 'n'); }
+        *p++ = '\n';
+    }
+}
+
 }  // namespace bdk

@@ -68,6 +68,9 @@ int bdepth_run_resident(bdepth_t* h);
 int bdepth_run_base(bdepth_t* h, bdepth_tile_cb cb, void* user);
 int bdepth_run_windows(bdepth_t* h, uint window, uint overlap, const(uint)* thr, size_t n_thr, bdepth_stat_cb cb, void* user);
 int bdepth_run_regions(bdepth_t* h, const(bdepth_region)* r, size_t n, const(uint)* thr, size_t n_thr, bdepth_stat_cb cb, void* user);
+struct bdepth_text_opts { double min_cov, max_cov; int annotate; }
+alias bdepth_text_cb = int function(void* user, const(char)* text, size_t len);
+int bdepth_run_base_text(bdepth_t* h, const(bdepth_text_opts)* o, bdepth_text_cb cb, void* user);
 int bdepth_get_stats(const(bdepth_t)* h, bdepth_stats* s);
 int bdepth_ref_has_reads(const(bdepth_t)* h, int r);
 long bdepth_inflate_to_host(bdepth_t* h, void* dst, ulong cap);
