@@ -160,8 +160,9 @@ int bdepth_run_resident(bdepth_t* h);
 /* depth base: deliver every tile of the processed range in order.  cb may be NULL (benchmark). */
 int bdepth_run_base(bdepth_t* h, bdepth_tile_cb cb, void* user);
 /* depth window -w W --overlap O -T t...: stats for every window slot the reference would print
- * (all full windows of every reference, in order; depth.d:1051-1076).  O must satisfy
- * (W - O) divides W for GPU evaluation. */
+ * (all full windows of every reference, in order; depth.d:1051-1076), any O < W.  The reference's ring-slot
+ * behaviour is reproduced in closed form (early threshold collection when W-O does not divide W, the
+ * first-occurrence quirk of reference 0, the leftovers printed under the first trailing empty reference). */
 int bdepth_run_windows(bdepth_t* h, uint32_t window, uint32_t overlap, const uint32_t* thresholds, size_t n_thresholds, bdepth_stat_cb cb, void* user);
 /* depth region: stats for the given regions, delivered in the given order. */
 int bdepth_run_regions(bdepth_t* h, const bdepth_region* regions, size_t n, const uint32_t* thresholds, size_t n_thresholds, bdepth_stat_cb cb, void* user);

@@ -129,7 +129,7 @@ struct bdepth {
     void* pinned = nullptr; size_t pinned_cap = 0;
     std::vector<uint32_t> ref_has_host;
     // ---- optional per-read segment counting (window / region front ends), device arrays
-    struct SegSet { bool on = false; uint32_t n = 0; DevBuf s, e, pmax, id, reads; } seg;
+    struct SegSet { bool on = false; uint32_t n = 0; bool has_min = false; DevBuf s, e, pmax, id, reads, minstart, bases_reads; } seg;
     // ---- results
     bdepth_stats st{}; std::string err;
 };
@@ -643,8 +643,8 @@ int run_pipeline(bdepth* h, RunMode mode, RunOut* ro, Emitter* em = nullptr) {
         }
         // ---- per-read segment counting (countRead, depth.d:661-669) for the window / region front ends
         if (mode == RUN_FULL && h->seg.on && h->seg.n && ss.n_pass) {
-            if (h->minq) k_read_segments<true><<<(unsigned)((R + 127) / 128), 128, 0, sm>>>(soa, u0, (uint32_t)R, h->seg.s.as<uint64_t>(), h->seg.e.as<uint64_t>(), h->seg.pmax.as<uint64_t>(), h->seg.id.as<uint32_t>(), nullptr, h->seg.n, h->seg.reads.as<uint32_t>(), h->minq, h->S);
-            else k_read_segments<false><<<(unsigned)((R + 127) / 128), 128, 0, sm>>>(soa, u0, (uint32_t)R, h->seg.s.as<uint64_t>(), h->seg.e.as<uint64_t>(), h->seg.pmax.as<uint64_t>(), h->seg.id.as<uint32_t>(), nullptr, h->seg.n, h->seg.reads.as<uint32_t>(), 0, h->S);
+            if (h->minq) k_read_segments<true><<<(unsigned)((R + 127) / 128), 128, 0, sm>>>(soa, u0, (uint32_t)R, h->seg.s.as<uint64_t>(), h->seg.e.as<uint64_t>(), h->seg.pmax.as<uint64_t>(), h->seg.id.as<uint32_t>(), h->seg.has_min ? h->seg.minstart.as<uint64_t>() : nullptr, h->seg.n, h->seg.reads.as<uint32_t>(), h->minq, h->S, h->seg.has_min ? h->seg.bases_reads.as<uint32_t>() : nullptr);
+            else k_read_segments<false><<<(unsigned)((R + 127) / 128), 128, 0, sm>>>(soa, u0, (uint32_t)R, h->seg.s.as<uint64_t>(), h->seg.e.as<uint64_t>(), h->seg.pmax.as<uint64_t>(), h->seg.id.as<uint32_t>(), h->seg.has_min ? h->seg.minstart.as<uint64_t>() : nullptr, h->seg.n, h->seg.reads.as<uint32_t>(), 0, h->S, h->seg.has_min ? h->seg.bases_reads.as<uint32_t>() : nullptr);
             CK(cudaGetLastError()); st.gpu_launches++;
         }
         // ---- K3
@@ -768,7 +768,7 @@ void bdepth_close(bdepth_t* h) {
     for (DevBuf* b : bufs) b->release();
     h->rg_ids.release(); h->rg_offs.release(); h->rg_samp.release();
     h->text[0].release(); h->text[1].release(); h->text_tiles.release(); h->text_offs.release(); h->text_zero.release();
-    h->seg.s.release(); h->seg.e.release(); h->seg.pmax.release(); h->seg.id.release(); h->seg.reads.release();
+    h->seg.s.release(); h->seg.e.release(); h->seg.pmax.release(); h->seg.id.release(); h->seg.reads.release(); h->seg.minstart.release(); h->seg.bases_reads.release();
     if (h->comm) { nccl().CommDestroy(h->comm); h->comm = nullptr; }
     if (h->pinned) cudaFreeHost(h->pinned);
     if (h->s_main) { cudaStreamDestroy(h->s_main); cudaStreamDestroy(h->s_copy); cudaStreamDestroy(h->s_d2h); for (auto& ks : h->s_k1) cudaStreamDestroy(ks); for (auto& e : h->ev) cudaEventDestroy(e); for (int q = 0; q < 2; q++) for (auto& e : h->chunk_ev[q]) cudaEventDestroy(e); for (auto& e : h->k1_ev) cudaEventDestroy(e); }
@@ -984,7 +984,7 @@ int bdepth_run_base_text(bdepth_t* h, const bdepth_text_opts* o, bdepth_text_cb 
 
 // Shared by window and region modes.  segs: output-order list of (ref, start, end) with end possibly
 // past the reference end (windows); stats are computed over the part inside the reference.
-struct SegDef { uint32_t ref, start, end; };
+struct SegDef { uint32_t ref, start, end; uint32_t cov_ext = 0;  /* thresholds are counted from start - cov_ext */ uint32_t min_read_start = 0;  /* != 0: only reads starting at/after it count (quirk 6) */ };
 static int run_segments(bdepth* h, const std::vector<SegDef>& segs, const uint32_t* thr, size_t n_thr,
                         std::vector<uint32_t>& reads, std::vector<uint32_t>& bases, std::vector<uint32_t>& cov) {
     if (n_thr > 16) return fail(h, BDEPTH_ERR_ARG, "at most 16 coverage thresholds are supported");
@@ -1003,16 +1003,21 @@ static int run_segments(bdepth* h, const std::vector<SegDef>& segs, const uint32
     // sorted view for the per-read kernel
     std::vector<uint32_t> order(n); for (size_t i = 0; i < n; i++) order[i] = (uint32_t)i;
     std::sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return a[x] != a[y] ? a[x] < a[y] : x < y; });
-    std::vector<uint64_t> ss(n), se(n), pm(n); uint64_t mx = 0;
-    for (size_t i = 0; i < n; i++) { ss[i] = a[order[i]]; se[i] = b[order[i]]; mx = std::max(mx, se[i]); pm[i] = mx; }
+    std::vector<uint64_t> ss(n), se(n), pm(n), ms(n); uint64_t mx = 0; bool has_min = false;
+    for (size_t i = 0; i < n; i++) {
+        ss[i] = a[order[i]]; se[i] = b[order[i]]; mx = std::max(mx, se[i]); pm[i] = mx;
+        const SegDef& sd = segs[order[i]]; ms[i] = sd.min_read_start ? h->hdr.ref_lin0[sd.ref] + sd.min_read_start : 0; has_min |= ms[i] != 0;
+    }
     auto& S = h->seg;
     size_t nn = n ? n : 1;
-    CK(S.s.ensure(nn * 8)); CK(S.e.ensure(nn * 8)); CK(S.pmax.ensure(nn * 8)); CK(S.id.ensure(nn * 4)); CK(S.reads.ensure(NS * nn * 4));
+    CK(S.s.ensure(nn * 8)); CK(S.e.ensure(nn * 8)); CK(S.pmax.ensure(nn * 8)); CK(S.id.ensure(nn * 4)); CK(S.reads.ensure(NS * nn * 4)); CK(S.minstart.ensure(nn * 8)); CK(S.bases_reads.ensure(NS * nn * 4));
     if (n) {
         CK(cudaMemcpy(S.s.p, ss.data(), n * 8, cudaMemcpyHostToDevice)); CK(cudaMemcpy(S.e.p, se.data(), n * 8, cudaMemcpyHostToDevice));
         CK(cudaMemcpy(S.pmax.p, pm.data(), n * 8, cudaMemcpyHostToDevice)); CK(cudaMemcpy(S.id.p, order.data(), n * 4, cudaMemcpyHostToDevice));
     }
-    CK(cudaMemset(S.reads.p, 0, NS * nn * 4));
+    CK(cudaMemset(S.reads.p, 0, NS * nn * 4)); CK(cudaMemset(S.bases_reads.p, 0, NS * nn * 4));
+    if (n) CK(cudaMemcpy(S.minstart.p, ms.data(), n * 8, cudaMemcpyHostToDevice));
+    S.has_min = has_min;
     S.on = true; S.n = (uint32_t)n;
     rc = run_pipeline(h, RUN_FULL, nullptr);
     S.on = false;
@@ -1021,21 +1026,24 @@ static int run_segments(bdepth* h, const std::vector<SegDef>& segs, const uint32
     cudaEvent_t e0 = h->ev[5], e1 = h->ev[6];
     CK(cudaEventRecord(e0, sm));
     // per-segment sums over the counters (original order)
-    DevBuf da, db, dthr, dbases, dcov;
-    auto cleanup = [&]() { da.release(); db.release(); dthr.release(); dbases.release(); dcov.release(); };
+    DevBuf da, dac, db, dthr, dbases, dcov;
+    auto cleanup = [&]() { da.release(); dac.release(); db.release(); dthr.release(); dbases.release(); dcov.release(); };
     cudaError_t ce;
-    if ((ce = da.ensure(nn * 8)) || (ce = db.ensure(nn * 8)) || (ce = dthr.ensure(64)) || (ce = dbases.ensure(NS * nn * 4)) || (ce = dcov.ensure(NS * nn * 4 * nt1))) { cleanup(); return fail(h, BDEPTH_ERR_CUDA, "out of device memory (%s)", cudaGetErrorString(ce)); }
+    if ((ce = da.ensure(nn * 8)) || (ce = dac.ensure(nn * 8)) || (ce = db.ensure(nn * 8)) || (ce = dthr.ensure(64)) || (ce = dbases.ensure(NS * nn * 4)) || (ce = dcov.ensure(NS * nn * 4 * nt1))) { cleanup(); return fail(h, BDEPTH_ERR_CUDA, "out of device memory (%s)", cudaGetErrorString(ce)); }
+    std::vector<uint64_t> acv(n); std::vector<uint32_t> qbases;
     for (size_t i = 0; i < n; i++) {
         uint64_t lo = std::max(h->cnt_base, h->own_lo), hi = std::min(h->cnt_base + h->win_len, h->own_hi); if (hi < lo) hi = lo;
-        uint64_t wa = std::min(std::max(a[i], lo), hi), wb = std::min(std::max(b[i], lo), hi);
-        a[i] = wa - h->cnt_base; b[i] = wb - h->cnt_base;
+        uint64_t sc = segs[i].start - std::min(segs[i].cov_ext, segs[i].start);
+        uint64_t acov = h->hdr.ref_lin0[segs[i].ref] + std::min<uint64_t>(sc, h->hdr.ref_len[segs[i].ref]);
+        uint64_t wa = std::min(std::max(a[i], lo), hi), wb = std::min(std::max(b[i], lo), hi), wc = std::min(std::max(acov, lo), hi);
+        a[i] = wa - h->cnt_base; b[i] = wb - h->cnt_base; acv[i] = wc - h->cnt_base;
     }
-    if (n) { cudaMemcpyAsync(da.p, a.data(), n * 8, cudaMemcpyHostToDevice, sm); cudaMemcpyAsync(db.p, b.data(), n * 8, cudaMemcpyHostToDevice, sm); }
+    if (n) { cudaMemcpyAsync(da.p, a.data(), n * 8, cudaMemcpyHostToDevice, sm); cudaMemcpyAsync(dac.p, acv.data(), n * 8, cudaMemcpyHostToDevice, sm); cudaMemcpyAsync(db.p, b.data(), n * 8, cudaMemcpyHostToDevice, sm); }
     if (n_thr) cudaMemcpyAsync(dthr.p, thr, n_thr * 4, cudaMemcpyHostToDevice, sm);
     cudaMemsetAsync(dbases.p, 0, NS * nn * 4, sm); cudaMemsetAsync(dcov.p, 0, NS * nn * 4 * nt1, sm);
     if (n) {
         for (size_t si = 0; si < NS; si++) {
-            k_segment_stats<<<(unsigned)((n * 32 + 255) / 256), 256, 0, sm>>>(h->counts.as<uint32_t>() + (uint64_t)si * N_PLANES * h->win_len, h->win_len, da.as<uint64_t>(), db.as<uint64_t>(), (uint32_t)n, dthr.as<uint32_t>(), (uint32_t)n_thr, dbases.as<uint32_t>() + si * n, dcov.as<uint32_t>() + si * n * nt1);
+            k_segment_stats<<<(unsigned)((n * 32 + 255) / 256), 256, 0, sm>>>(h->counts.as<uint32_t>() + (uint64_t)si * N_PLANES * h->win_len, h->win_len, da.as<uint64_t>(), dac.as<uint64_t>(), db.as<uint64_t>(), (uint32_t)n, dthr.as<uint32_t>(), (uint32_t)n_thr, dbases.as<uint32_t>() + si * n, dcov.as<uint32_t>() + si * n * nt1);
             h->st.gpu_launches++;
         }
         if (h->world > 1 && h->comm) {   // per-segment partial sums are additive over ranks
@@ -1043,16 +1051,19 @@ static int run_segments(bdepth* h, const std::vector<SegDef>& segs, const uint32
             N.AllReduce(dbases.p, dbases.p, NS * n, NCCL_UINT32, NCCL_SUM, h->comm, sm);
             if (n_thr) N.AllReduce(dcov.p, dcov.p, NS * n * n_thr, NCCL_UINT32, NCCL_SUM, h->comm, sm);
             N.AllReduce(S.reads.p, S.reads.p, NS * n, NCCL_UINT32, NCCL_SUM, h->comm, sm);
+            if (has_min) N.AllReduce(S.bases_reads.p, S.bases_reads.p, NS * n, NCCL_UINT32, NCCL_SUM, h->comm, sm);
         }
         cudaMemcpyAsync(bases.data(), dbases.p, NS * n * 4, cudaMemcpyDeviceToHost, sm);
         if (n_thr) cudaMemcpyAsync(cov.data(), dcov.p, NS * n * n_thr * 4, cudaMemcpyDeviceToHost, sm);
         cudaMemcpyAsync(reads.data(), S.reads.p, NS * n * 4, cudaMemcpyDeviceToHost, sm);
+        if (has_min) { qbases.resize(NS * n); cudaMemcpyAsync(qbases.data(), S.bases_reads.p, NS * n * 4, cudaMemcpyDeviceToHost, sm); }
     }
     cudaEventRecord(e1, sm);
     ce = cudaStreamSynchronize(sm);
     if (ce == cudaSuccess) ce = cudaGetLastError();
     cleanup();
     if (ce != cudaSuccess) return fail(h, BDEPTH_ERR_CUDA, "CUDA error in segment statistics: %s", cudaGetErrorString(ce));
+    if (!qbases.empty()) for (size_t si = 0; si < NS; si++) for (size_t i = 0; i < n; i++) if (segs[i].min_read_start) bases[si * n + i] = qbases[si * n + i];
     float t = 0; cudaEventElapsedTime(&t, e0, e1); h->st.ms_reduce = t;
     h->st.ms_total_device = h->st.ms_h2d + h->st.ms_inflate + h->st.ms_scan + h->st.ms_coverage + h->st.ms_reduce;
     return 0;
@@ -1076,22 +1087,35 @@ int bdepth_run_windows(bdepth_t* h, uint32_t window, uint32_t overlap, const uin
     if (window == 0) return fail(h, BDEPTH_ERR_ARG, "positive window size must be specified");
     if (overlap >= window) return fail(h, BDEPTH_ERR_ARG, "specified overlap is larger than window size");
     const uint32_t step = window - overlap;
-    if (window % step) return fail(h, BDEPTH_ERR_ARG, "window mode on the GPU needs (window - overlap) to divide window (see DESIGN.md: the reference's slot collector is only position-consistent in that case)");
+    const uint32_t nslot = (window + step - 1) / step;          // ring slots of PerWindowPrinter (depth.d:1026-1029)
+    const uint32_t ext = nslot * step - window;                  // a slot reused for window m >= nslot starts collecting
+                                                                 // thresholds `ext` positions before the window (WindowStatsCollector
+                                                                 // updates all nslot slots once position >= window, depth.d:215-226)
     // every window slot the reference could print: full windows when the reference has reads
     // (depth.d:1057,1071), ref_length / step windows when it has none (printEmptyWindows, depth.d:1039-1044)
     std::vector<SegDef> segs; std::vector<uint32_t> n_full(h->hdr.ref_len.size()), n_empty(h->hdr.ref_len.size()); std::vector<size_t> first(h->hdr.ref_len.size());
     for (size_t r = 0; r < h->hdr.ref_len.size(); r++) {
         uint64_t L = h->hdr.ref_len[r];
         n_full[r] = L >= window ? (uint32_t)((L - window) / step + 1) : 0; n_empty[r] = (uint32_t)(L / step);
-        uint32_t m = std::max(n_full[r], n_empty[r]); first[r] = segs.size();
-        for (uint32_t k = 0; k < m; k++) segs.push_back(SegDef{(uint32_t)r, k * step, k * step + window});
+        // + nslot: the ring's content after the last full window (partial windows at the reference end), see below
+        uint32_t m = std::max(n_full[r] + nslot, n_empty[r]); first[r] = segs.size();
+        for (uint32_t k = 0; k < m; k++) {
+            SegDef sd{(uint32_t)r, k * step, k * step + window};
+            if (k >= nslot) sd.cov_ext = ext;
+            // slots start with is_first_occurrence == false (depth.d:1031-1032); until a slot has been finished once it only
+            // counts reads that start inside it.  That affects windows 1..nslot-1 of reference 0 (later references are
+            // preceded by resetAllWindows, depth.d:951-960).
+            if (r == 0 && k >= 1 && k < nslot) sd.min_read_start = k * step;
+            segs.push_back(sd);
+        }
     }
     std::vector<uint32_t> reads, bases, cov;
     int rc = run_segments(h, segs, thr, n_thr, reads, bases, cov); if (rc) return rc;
     // Which slots the reference prints: full windows of references with reads (depth.d:1057,1071), length/step
     // windows of references without (printEmptyWindows, depth.d:1039-1044).  Quirk kept for drop-in output: in
     // close() (depth.d:1070-1076) the FIRST trailing reference without reads is printed before the window state is
-    // reset, so its windows continue from where the last reference with reads stopped.
+    // reset, so its windows continue from where the last reference with reads stopped -- and its first nslot rows
+    // carry what the ring still holds: the statistics of the partial windows at the end of that last reference.
     const size_t nref = h->hdr.ref_len.size();
     long last_has = -1;
     for (size_t r = 0; r < nref; r++) if ((h->ref_has_host[r >> 5] >> (r & 31)) & 1) last_has = (long)r;
@@ -1103,8 +1127,9 @@ int bdepth_run_windows(bdepth_t* h, uint32_t window, uint32_t overlap, const uin
         uint32_t shift = (!has && last_has >= 0 && (long)r == last_has + 1) ? n_full[last_has] * step : 0;
         for (uint32_t k = 0; k < m; k++) {
             size_t i = first[r] + k;
-            SegDef sd = shift ? SegDef{(uint32_t)r, shift + k * step, shift + k * step + window} : segs[i];
-            rc = deliver_one(h, sd, i, segs.size(), n_thr, reads, bases, cov, shift != 0, cb, user, idx++); if (rc) return rc;
+            SegDef sd = segs[i];
+            if (shift) { sd = SegDef{(uint32_t)r, shift + k * step, shift + k * step + window}; i = first[last_has] + n_full[last_has] + k; }
+            rc = deliver_one(h, sd, i, segs.size(), n_thr, reads, bases, cov, shift != 0 && k >= nslot, cb, user, idx++); if (rc) return rc;
         }
     }
     return 0;

@@ -491,19 +491,21 @@ __global__ void k_count_covered(const uint32_t* __restrict__ counts, uint64_t wi
 
 // Segment statistics over the counters: one warp per segment [seg_a[i], seg_b[i]) (window-relative).
 // out_bases[i] += sum(A+C+G+T+N); out_cov[t][i] += #positions with all-7 sum >= thr[t].
-__global__ void k_segment_stats(const uint32_t* __restrict__ counts, uint64_t win_len, const uint64_t* __restrict__ seg_a, const uint64_t* __restrict__ seg_b,
+__global__ void k_segment_stats(const uint32_t* __restrict__ counts, uint64_t win_len, const uint64_t* __restrict__ seg_a, const uint64_t* __restrict__ seg_a_cov, const uint64_t* __restrict__ seg_b,
                                 uint32_t n_seg, const uint32_t* __restrict__ thr, uint32_t n_thr, uint32_t* __restrict__ out_bases, uint32_t* __restrict__ out_cov /* [n_thr][n_seg] */) {
     uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= n_seg) return;
-    uint64_t a = seg_a[warp], b = seg_b[warp];
+    // bases are summed over [a, b); thresholds are counted over [a_cov, b) with a_cov <= a (the reference's window
+    // slots start collecting coverage before their window begins when the step does not divide the window)
+    uint64_t a = seg_a[warp], ac = seg_a_cov[warp], b = seg_b[warp];
     uint32_t bases = 0; uint32_t cge[16];
 #pragma unroll
     for (int t = 0; t < 16; t++) cge[t] = 0;
-    for (uint64_t i = a + lane; i < b; i += 32) {
+    for (uint64_t i = ac + lane; i < b; i += 32) {
         uint32_t s5 = 0, s = 0;
 #pragma unroll
         for (int pl = 0; pl < N_PLANES; pl++) { uint32_t v = counts[(uint64_t)pl * win_len + i]; s += v; if (pl < 5) s5 += v; }
-        bases += s5;
+        if (i >= a) bases += s5;
         if (s) {
 #pragma unroll
             for (int t = 0; t < 16; t++) if ((uint32_t)t < n_thr) cge[t] += s >= thr[t];
@@ -527,7 +529,7 @@ __global__ void k_segment_stats(const uint32_t* __restrict__ counts, uint64_t wi
 template <bool MINQ>
 __global__ void k_read_segments(RecordSoA soa, const uint8_t* __restrict__ u, uint32_t R, const uint64_t* __restrict__ seg_s, const uint64_t* __restrict__ seg_e,
                                 const uint64_t* __restrict__ pmax_end, const uint32_t* __restrict__ seg_id, const uint64_t* __restrict__ seg_min_start, uint32_t n_seg,
-                                uint32_t* __restrict__ out_reads /* [n_samples][n_seg] */, uint32_t minq, uint32_t n_samples) {
+                                uint32_t* __restrict__ out_reads /* [n_samples][n_seg] */, uint32_t minq, uint32_t n_samples, uint32_t* __restrict__ out_bases_reads) {
     uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= R) return;
     if (!(soa.meta[r] & 1u)) return;
@@ -544,22 +546,24 @@ __global__ void k_read_segments(RecordSoA soa, const uint8_t* __restrict__ u, ui
         if (pmax_end[k] <= rs) break;
         uint64_t a = seg_s[k], b = seg_e[k];
         if (b <= rs || a >= re) continue;
-        if (seg_min_start && rs < seg_min_start[k]) continue;      // window-mode first-occurrence quirk (depth.d:1031-1032)
-        // any M base with q >= minq inside [a,b)?
-        bool hit = false; uint32_t rpos = 0, qpos = 0;
-        for (uint32_t i = 0; i < n_cigar && !hit; i++) {
+        const bool q6 = seg_min_start && seg_min_start[k] != 0;     // window-mode first-occurrence quirk (depth.d:1031-1032):
+        if (q6 && rs < seg_min_start[k]) continue;                  // such a slot only ever sees reads that START inside it
+        // any M base with q >= minq inside [a,b)?  (for quirk slots: how many, their n_bases comes from countRead alone)
+        bool hit = false; uint32_t rpos = 0, qpos = 0, nb = 0;
+        for (uint32_t i = 0; i < n_cigar && (q6 || !hit); i++) {
             uint32_t c = ldu32(cg + 4 * i), len = c >> 4, op = c & 15;
             if (cig_match(op)) {
                 uint64_t ma = rs + rpos, mb = ma + len; if (mb > re) mb = re;
                 uint64_t xa = ma > a ? ma : a, xb = mb < b ? mb : b;
                 if (xa < xb) {
-                    if (!MINQ) hit = (qpos + (uint32_t)(xa - ma)) < lseq;
-                    else for (uint64_t g = xa; g < xb && !hit; g++) { uint32_t q = qpos + (uint32_t)(g - ma); if (q < lseq && ldg8(qual + q) >= minq) hit = true; }
+                    if (!MINQ && !q6) hit = (qpos + (uint32_t)(xa - ma)) < lseq;
+                    else for (uint64_t g = xa; g < xb && (q6 || !hit); g++) { uint32_t q = qpos + (uint32_t)(g - ma); if (q < lseq && (!MINQ || ldg8(qual + q) >= minq)) { hit = true; nb++; } }
                 }
                 rpos += len; qpos += len;
             } else if (op == 2 || op == 3) rpos += len;
             else if (cig_qcons(op)) qpos += len;
         }
+        if (q6 && nb && out_bases_reads) atomicAdd(&out_bases_reads[(uint64_t)samp * n_seg + seg_id[k]], nb);
         if (hit) atomicAdd(&out_reads[(uint64_t)samp * n_seg + seg_id[k]], 1u);
     }
 }

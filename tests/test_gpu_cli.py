@@ -70,6 +70,17 @@ def test_window_modes_match_oracle(tiny):
         check_same(args)
 
 
+def test_overlapping_windows_match_oracle(tiny):
+    # the reference keeps ceil(w/step) ring slots (depth.d:1026-1029); a reused slot collects thresholds before its window
+    # starts when step does not divide w (depth.d:215-226), and the first reference's initial slots only count reads
+    # that start inside them (is_first_occurrence starts false, depth.d:1031-1032) -- both reproduced in closed form
+    p, _, _ = tiny
+    for args in (["window", "-w", "1000", "--overlap", "500", p], ["window", "-w", "1000", "--overlap", "300", "-T", "3", "-T", "9", p],
+                 ["window", "-w", "1000", "--overlap", "900", "-T", "5", p], ["window", "-w", "777", "--overlap", "100", "-T", "4", "-q", "20", p],
+                 ["window", "-w", "640", "--overlap", "639", "-T", "6", "-L", "ctgB", p], ["window", "-w", "1500", "--overlap", "1100", "-T", "2", "-c", "6", "-a", p]):
+        check_same(args)
+
+
 def test_region_modes_match_oracle(tiny):
     p, bed, sbed = tiny
     for args in (["region", "-L", sbed, p], ["region", "-L", sbed, "-T", "3", "-T", "10", p], ["region", "-L", bed, "-T", "8", p],

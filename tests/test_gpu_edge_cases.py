@@ -165,3 +165,25 @@ def test_multi_sample_header(tmp_path):
     rc1, _, err1 = helpers.run_cli(["base", p2])
     rc2, _, err2 = helpers.oracle_cli(["base", p2])
     assert rc1 == 1 and rc2 == 1 and b"read group" in err1 and b"not present in the header" in err2
+
+
+def test_overlapping_windows_first_reference_without_reads(tmp_path):
+    # reads only on the 2nd and 3rd reference: the empty first reference is printed through printEmptyWindows
+    # (depth.d:1037-1042), which also resets the slots, so the first-occurrence quirk of reference 0 does not apply
+    r = random.Random(11)
+    reads = []
+    for ref in (1, 2):
+        for i in range(600):
+            n = r.randint(30, 120)
+            reads.append((ref, r.randint(0, 5000 - 130), 60, 0, [(n, 0)], rnd_seq(r, n), f"r{ref}_{i}"))
+    reads.sort(key=lambda x: (x[0], x[1]))
+    p = helpers.write_bam(str(tmp_path / "w.bam"), [("e0", 3000), ("c1", 5000), ("c2", 5000), ("e3", 2500)], reads)
+    for args in (["window", "-w", "400", "--overlap", "100", "-T", "3", p], ["window", "-w", "400", "--overlap", "200", p],
+                 ["window", "-w", "250", "--overlap", "249", "-T", "10", "-L", "c2", p]):
+        cli_same(args)
+    # and with reads on reference 0 (quirk applies there only)
+    reads0 = [(0, r.randint(0, 2800), 60, 0, [(100, 0)], rnd_seq(r, 100), f"z{i}") for i in range(300)]
+    reads0.sort(key=lambda x: x[1])
+    p2 = helpers.write_bam(str(tmp_path / "w0.bam"), [("e0", 3000), ("c1", 5000), ("c2", 5000), ("e3", 2500)], reads0 + reads)
+    for args in (["window", "-w", "400", "--overlap", "100", "-T", "3", p2], ["window", "-w", "330", "--overlap", "300", "-T", "2", "-q", "15", p2]):
+        cli_same(args)
