@@ -148,8 +148,10 @@ int bdepth_nccl_unique_id(void* out128);
  * the first linear-index record start at or after k * file_size / world (k = 1..world-1);
  * UINT64_MAX when there is none.  Used by the sharding tests. */
 int bdepth_plan_shards(const char* bam_path, int world, uint64_t* out_voffsets);
-/* Tuning knobs (0 = default): uncompressed bytes per batch, positions in the counter window. */
-int bdepth_set_tuning(bdepth_t* h, uint64_t batch_inflated_bytes, uint64_t window_positions);
+/* Tuning knobs (0 = default): uncompressed bytes per batch (one inflate buffer in HBM); BGZF blocks per
+ * host-to-device chunk, which is also the sub-batch whose scan / coverage / delivery overlaps the inflate of
+ * the chunks that arrive after it. */
+int bdepth_set_tuning(bdepth_t* h, uint64_t batch_inflated_bytes, uint64_t chunk_blocks);
 
 /* ------------------------------------------------------------------ runs */
 /* Stage the (shard of the) compressed file into HBM ahead of time; later runs then start with

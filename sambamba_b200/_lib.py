@@ -204,8 +204,8 @@ class BDepth:
         self._uid = C.create_string_buffer(uid, 128) if uid is not None else None
         self._ck(self.L.bdepth_set_shard(self.h, rank, world, self._uid))
 
-    def set_tuning(self, batch_bytes=0, window_positions=0):
-        self._ck(self.L.bdepth_set_tuning(self.h, batch_bytes, window_positions))
+    def set_tuning(self, batch_bytes=0, chunk_blocks=0):
+        self._ck(self.L.bdepth_set_tuning(self.h, batch_bytes, chunk_blocks))
 
     def stage(self):
         self._ck(self.L.bdepth_stage(self.h))

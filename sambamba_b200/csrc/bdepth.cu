@@ -44,6 +44,29 @@ struct DevBuf {
     template <class T> T* as() const { return (T*)p; }
 };
 
+// Small control-plane transfers (block tables up, chain/scan results down) do not go through the copy engines:
+// those queue in order behind the bulk H2D of the compressed file and the bulk D2H of finished counters, which
+// cost every sub-batch milliseconds.  They live in mapped pinned memory and a tiny kernel moves the words.
+struct HostScratch {
+    uint8_t* hp = nullptr; uint8_t* dp = nullptr; size_t cap = 0, used = 0;
+    cudaError_t ensure(size_t n) {          // only while nothing in flight refers to it
+        if (n <= cap) return cudaSuccess;
+        if (hp) { cudaDeviceSynchronize(); cudaFreeHost(hp); hp = nullptr; dp = nullptr; cap = 0; }
+        cudaError_t e = cudaHostAlloc((void**)&hp, n + n / 4, cudaHostAllocMapped);
+        if (e != cudaSuccess) return e;
+        e = cudaHostGetDevicePointer((void**)&dp, hp, 0);
+        if (e == cudaSuccess) cap = n + n / 4;
+        used = 0;
+        return e;
+    }
+    uint8_t* take(size_t n) { size_t a = (used + 15) & ~size_t(15); if (a + n > cap) return nullptr; used = a + n; return hp + a; }
+    uint8_t* dev(const void* host) const { return dp + ((const uint8_t*)host - hp); }
+    void release() { if (hp) cudaFreeHost(hp); hp = nullptr; dp = nullptr; cap = used = 0; }
+};
+__global__ void k_copy_words(uint32_t* __restrict__ dst, const uint32_t* __restrict__ src, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+
 constexpr size_t CARRY_MAX = 64ull << 20;
 constexpr size_t EMIT_CHUNK = 4ull << 20;     // positions per D2H chunk
 constexpr uint32_t SHARD_EXTRA_BLOCKS = 8;
@@ -111,7 +134,7 @@ struct bdepth {
     DevBuf rg_ids, rg_offs, rg_samp;
     DevBuf text[2], text_tiles, text_offs, text_zero;
     uint64_t batch_u = 6ull << 30;
-    uint64_t window_positions = 0;
+    uint64_t chunk_blocks = 13 * 32 * 16;              // BGZF blocks per H2D chunk = per K1 sub-launch = per sub-batch: 6656 blocks = 16 K1 CTAs, ~260 MB compressed
     // ---- shard (resolved lazily)
     bool shard_ready = false;
     size_t blk_lo = 0, blk_hi = 0; int64_t entry0 = 0; uint64_t limit_abs_u = 0;
@@ -127,6 +150,7 @@ struct bdepth {
     DevBuf soa_start, soa_span, soa_meta, soa_off, soa_ncl, soa_lseq, long_list, tile_first, tile_lo, counts, ref_len_d, ref_lin0_d, scan_stats, ref_has, misc;
     uint64_t cnt_base = 0, win_len = 0;
     void* pinned = nullptr; size_t pinned_cap = 0;
+    HostScratch hs;
     std::vector<uint32_t> ref_has_host;
     // ---- optional per-read segment counting (window / region front ends), device arrays
     struct SegSet { bool on = false; uint32_t n = 0; bool has_min = false; DevBuf s, e, pmax, id, reads, minstart, bases_reads; } seg;
@@ -147,6 +171,7 @@ int fail(bdepth* h, int code, const char* fmt, ...) {
 int ensure_pinned(bdepth* h, size_t n) {
     if (n <= h->pinned_cap) return 0;
     if (h->pinned) cudaFreeHost(h->pinned);
+    h->hs.release();
     h->pinned = nullptr; h->pinned_cap = 0;
     CK(cudaMallocHost(&h->pinned, n));
     h->pinned_cap = n;
@@ -436,6 +461,23 @@ int run_pipeline(bdepth* h, RunMode mode, RunOut* ro, Emitter* em = nullptr) {
     }
     { uint64_t shard_u = h->blk_hi > h->blk_lo ? B[h->blk_hi - 1].uoff + B[h->blk_hi - 1].isize - B[h->blk_lo].uoff : 0; CK(h->ubuf.ensure(CARRY_MAX + std::min<uint64_t>(h->batch_u + 65536, shard_u) + 256)); }
     CK(h->misc.ensure(64));
+    HostScratch& hs = h->hs;
+    // up(): host words -> device buffer; down(): device words -> mapped host memory, readable after the next
+    // synchronisation of the main stream.  Both are stream-ordered kernels on the main stream.
+    auto up = [&](void* dst_dev, const void* src, size_t bytes) -> int {
+        if (!bytes) return 0;
+        uint8_t* m = hs.take(bytes); if (!m) return fail(h, BDEPTH_ERR_CUDA, "internal: host scratch exhausted");
+        memcpy(m, src, bytes);
+        k_copy_words<<<(unsigned)std::min<size_t>((bytes / 4 + 255) / 256, 512), 256, 0, sm>>>((uint32_t*)dst_dev, (const uint32_t*)hs.dev(m), bytes / 4);
+        return 0;
+    };
+    auto down = [&](const void* src_dev, size_t bytes) -> uint8_t* {
+        uint8_t* m = hs.take(bytes ? bytes : 4); if (!m) return nullptr;
+        if (bytes) k_copy_words<<<(unsigned)std::min<size_t>((bytes / 4 + 255) / 256, 512), 256, 0, sm>>>((uint32_t*)hs.dev(m), (const uint32_t*)src_dev, bytes / 4);
+        return m;
+    };
+#define UP(dst, src, bytes) do { int rcu_ = up((dst), (src), (bytes)); if (rcu_) return rcu_; } while (0)
+#define DOWN(var, type, src, bytes) type* var = (type*)down((src), (bytes)); if (!var) return fail(h, BDEPTH_ERR_CUDA, "internal: host scratch exhausted")
 
     float ms_h2d = 0, ms_k1 = 0, ms_k2 = 0, ms_k3 = 0;
     uint64_t carry_len = 0; bool first_batch = true;
@@ -450,7 +492,7 @@ int run_pipeline(bdepth* h, RunMode mode, RunOut* ro, Emitter* em = nullptr) {
     size_t batch_no = 0;
     auto batch_end = [&](size_t bb) { size_t e = bb; uint64_t u = 0; while (e < h->blk_hi && (e == bb || u + B[e].isize <= h->batch_u)) { u += B[e].isize; e++; } return e; };
     // H2D of blocks [bb, be) into comp2[slot]; waits until K1 of the batch that used the slot two batches ago is done
-    constexpr size_t H2D_CHUNK_BLOCKS = 13 * 32 * 16;   // 6656 blocks = 16 K1 CTAs (13 warps each) per sub-launch, ~260 MB of compressed data
+    const size_t H2D_CHUNK_BLOCKS = h->chunk_blocks;
     auto issue_h2d = [&](size_t no, size_t bb, size_t be) -> int {
         int slot = (int)(no & 1);
         uint64_t g0 = B[bb].coff & ~3ull;
@@ -494,14 +536,18 @@ int run_pipeline(bdepth* h, RunMode mode, RunOut* ro, Emitter* em = nullptr) {
         for (size_t i = 0; i < nb; i++) { const HostBlock& hb = B[b + i]; d[i] = BlockDesc{hb.coff + hb.cdata_off - comp_base_off, hb.uoff - batch_u0, hb.csize, hb.isize}; csum += hb.csize; }
         st.cdata_bytes += csum;
         CK(h->descs.ensure(nb * sizeof(BlockDesc))); CK(h->status.ensure(nb * sizeof(int))); CK(h->ubuf.ensure(CARRY_MAX + ub + 256));
-        CK(cudaMemcpyAsync(h->descs.p, d.data(), nb * sizeof(BlockDesc), cudaMemcpyHostToDevice, sm));
+        CK(hs.ensure(nb * (sizeof(BlockDesc) + 192) + 16384)); hs.used = 0;      // nothing is in flight here: every sub-batch ends synchronised
+        UP(h->descs.p, d.data(), nb * sizeof(BlockDesc));
         uint8_t* u0 = h->ubuf.as<uint8_t>() + CARRY_MAX;     // offset 0 of this batch's inflated bytes
         CK(cudaEventRecord(e1, sm));
+        struct Sub { size_t s0, s1; int ev_lo, ev_hi; };     // blocks [s0, s1) are inflated once k1_ev[ev_lo..ev_hi] have fired
+        std::vector<Sub> subs;
         // ---- K1: when the input is streaming in, one sub-launch per H2D chunk, spread over a few streams so that
         // they run side by side (a lone sub-launch cannot fill the GPU: every lane owns a whole BGZF block)
         if (h->staged) {
             k1_inflate<<<(unsigned)((nb + 32 * K1_WARPS - 1) / (32 * K1_WARPS)), 32 * K1_WARPS, K1_SMEM, sm>>>(d_comp, h->descs.as<BlockDesc>(), (uint32_t)nb, u0, h->status.as<int>());
             CK(cudaGetLastError()); st.gpu_launches++;
+            subs.push_back(Sub{b, b1, 0, -1});
         } else {
             int slot = (int)(batch_no & 1); size_t c0 = b;
             for (size_t j = 0; j < h->chunk_end[slot].size(); j++) {
@@ -511,17 +557,24 @@ int run_pipeline(bdepth* h, RunMode mode, RunOut* ro, Emitter* em = nullptr) {
                 k1_inflate<<<(n + 32 * K1_WARPS - 1) / (32 * K1_WARPS), 32 * K1_WARPS, K1_SMEM, ks>>>(d_comp, h->descs.as<BlockDesc>() + (c0 - b), n, u0, h->status.as<int>() + (c0 - b));
                 CK(cudaGetLastError()); st.gpu_launches++;
                 if (h->k1_ev.size() <= j) { cudaEvent_t ne; CK(cudaEventCreateWithFlags(&ne, cudaEventDisableTiming)); h->k1_ev.push_back(ne); }
-                CK(cudaEventRecord(h->k1_ev[j], ks)); CK(cudaStreamWaitEvent(sm, h->k1_ev[j], 0));
+                CK(cudaEventRecord(h->k1_ev[j], ks));
+                // Sub-batches: a lane needs ~60 ms for its block however empty the GPU is, so the scan / coverage /
+                // delivery of the blocks that arrived first runs while the later chunks are still being inflated.
+                if (mode == RUN_FULL) subs.push_back(Sub{c0, c1, (int)j, (int)j}); else { if (subs.empty()) subs.push_back(Sub{b, b1, 0, (int)j}); subs[0].ev_hi = (int)j; }
                 c0 = c1;
             }
         }
+        if (!h->staged && b1 < h->blk_hi) { int rcp = issue_h2d(batch_no + 1, b1, batch_end(b1)); if (rcp) return rcp; }
+        const size_t mb = b, mb1 = b1; const uint64_t m_u0abs = batch_u0; uint8_t* const m_u0 = u0; const bool m_last = last_batch;
+        for (size_t sbi = 0; sbi < subs.size(); sbi++) {
+        const size_t b = subs[sbi].s0, b1 = subs[sbi].s1, nb = b1 - b;                  // from here on: the sub-batch
+        const uint64_t batch_u0 = B[b].uoff, ub = B[b1 - 1].uoff + B[b1 - 1].isize - batch_u0;
+        uint8_t* const u0 = m_u0 + (batch_u0 - m_u0abs);
+        const bool last_sub = sbi + 1 == subs.size(), last_batch = m_last && last_sub;
+        for (int j = subs[sbi].ev_lo; j <= subs[sbi].ev_hi; j++) CK(cudaStreamWaitEvent(sm, h->k1_ev[j], 0));
         CK(cudaEventRecord(e2, sm));
-        if (!h->staged) {
-            CK(cudaEventRecord(h->ev[16 + (batch_no & 1)], sm));            // this batch's compressed buffer is free again
-            if (b1 < h->blk_hi) { int rcp = issue_h2d(batch_no + 1, b1, batch_end(b1)); if (rcp) return rcp; }
-        }
-        std::vector<int> stt(nb);
-        CK(cudaMemcpyAsync(stt.data(), h->status.p, nb * sizeof(int), cudaMemcpyDeviceToHost, sm));
+        if (!h->staged && last_sub) CK(cudaEventRecord(h->ev[16 + (batch_no & 1)], sm));     // this batch's compressed buffer is free again
+        DOWN(stt, int, h->status.as<int>() + (b - mb), nb * sizeof(int));
         if (mode == RUN_INFLATE_ONLY) {
             CK(cudaStreamSynchronize(sm));
             for (size_t i = 0; i < nb; i++) if (stt[i]) return fail(h, BDEPTH_ERR_FORMAT, "DEFLATE error %d in BGZF block at offset %llu", stt[i], (unsigned long long)B[b + i].coff);
@@ -531,19 +584,19 @@ int run_pipeline(bdepth* h, RunMode mode, RunOut* ro, Emitter* em = nullptr) {
             }
             if (ro) ro->inflate_len += ub;
             float t; CK(cudaEventElapsedTime(&t, e1, e2)); ms_k1 += t;
-            b = b1; batch_no++; continue;
+            continue;
         }
         // ---- K2: chunk table
         std::vector<int64_t> cstart(nb + 1); std::vector<uint32_t> sbase(nb + 1);
-        { uint64_t acc = 0; for (size_t i = 0; i < nb; i++) { cstart[i] = (int64_t)d[i].uoff; sbase[i] = (uint32_t)acc; uint64_t sz = d[i].isize + (i == 0 ? carry_len : 0); acc += sz / 36 + 2; } cstart[nb] = (int64_t)ub; sbase[nb] = (uint32_t)acc; cstart[0] = -(int64_t)carry_len;
+        { uint64_t acc = 0; for (size_t i = 0; i < nb; i++) { cstart[i] = (int64_t)(B[b + i].uoff - batch_u0); sbase[i] = (uint32_t)acc; uint64_t sz = B[b + i].isize + (i == 0 ? carry_len : 0); acc += sz / 36 + 2; } cstart[nb] = (int64_t)ub; sbase[nb] = (uint32_t)acc; cstart[0] = -(int64_t)carry_len;
           if (acc > 0xFFFFFFFFull) return fail(h, BDEPTH_ERR_ARG, "batch too large"); }
         const uint64_t n_slots = sbase[nb];
         CK(h->chunk_start.ensure((nb + 1) * 8)); CK(h->slot_base.ensure((nb + 1) * 4)); CK(h->entry.ensure(nb * 8)); CK(h->exitb.ensure(nb * 8)); CK(h->count.ensure(nb * 4)); CK(h->rec_base.ensure((nb + 1) * 4)); CK(h->slots.ensure(n_slots * 2 + 64)); CK(h->walk_list.ensure(64));
-        CK(cudaMemcpyAsync(h->chunk_start.p, cstart.data(), (nb + 1) * 8, cudaMemcpyHostToDevice, sm));
-        CK(cudaMemcpyAsync(h->slot_base.p, sbase.data(), (nb + 1) * 4, cudaMemcpyHostToDevice, sm));
-        CK(cudaMemsetAsync(h->entry.p, 0xFF, nb * 8, sm));
+        UP(h->chunk_start.p, cstart.data(), (nb + 1) * 8);
+        UP(h->slot_base.p, sbase.data(), (nb + 1) * 4);
+        CK(cudaMemsetAsync(h->entry.p, ENTRY_NONE_BYTE, nb * 8, sm));
         int64_t anchor = first_batch ? h->entry0 : -(int64_t)carry_len;
-        CK(cudaMemcpyAsync(h->entry.p, &anchor, 8, cudaMemcpyHostToDevice, sm));
+        UP(h->entry.p, &anchor, 8);
         CK(cudaMemsetAsync(h->misc.p, 0, 64, sm));
         // records that START at or after the shard limit belong to the next rank
         int64_t u_limit = (int64_t)ub; if (h->limit_abs_u < batch_u0 + ub) u_limit = h->limit_abs_u > batch_u0 ? (int64_t)(h->limit_abs_u - batch_u0) : 0;
@@ -553,12 +606,10 @@ int run_pipeline(bdepth* h, RunMode mode, RunOut* ro, Emitter* em = nullptr) {
         ScanParams spw = sp;
         k2_walk<<<(unsigned)((nb + 127) / 128), 128, 0, sm>>>(spw, h->chunk_start.as<int64_t>(), (uint32_t)nb, h->entry.as<int64_t>(), h->slot_base.as<uint32_t>(), h->slots.as<uint16_t>(), h->count.as<uint32_t>(), h->exitb.as<int64_t>(), (int*)h->misc.p, nullptr, 0);
         CK(cudaGetLastError()); st.gpu_launches++;
-        std::vector<int64_t> ent(nb), ext(nb); std::vector<uint32_t> cnt(nb);
-        CK(cudaMemcpyAsync(ent.data(), h->entry.p, nb * 8, cudaMemcpyDeviceToHost, sm));
-        CK(cudaMemcpyAsync(ext.data(), h->exitb.p, nb * 8, cudaMemcpyDeviceToHost, sm));
-        CK(cudaMemcpyAsync(cnt.data(), h->count.p, nb * 4, cudaMemcpyDeviceToHost, sm));
-        int walk_err = 0; CK(cudaMemcpyAsync(&walk_err, h->misc.p, 4, cudaMemcpyDeviceToHost, sm));
+        DOWN(ent, int64_t, h->entry.p, nb * 8); DOWN(ext, int64_t, h->exitb.p, nb * 8); DOWN(cnt, uint32_t, h->count.p, nb * 4);      // host-owned once synchronised
+        DOWN(werr, int, h->misc.p, 4);
         CK(cudaStreamSynchronize(sm));
+        int walk_err = *werr;
         for (size_t i = 0; i < nb; i++) if (stt[i]) return fail(h, BDEPTH_ERR_FORMAT, "DEFLATE error %d in BGZF block at offset %llu", stt[i], (unsigned long long)B[b + i].coff);
         // ---- exact chain verification (host, control plane): entry[i] must equal the running exit
         int64_t cur = anchor; int64_t tail = (int64_t)ub;
@@ -568,14 +619,13 @@ int run_pipeline(bdepth* h, RunMode mode, RunOut* ro, Emitter* em = nullptr) {
             if (ent[i] != true_e) {
                 st.chain_fixups++;
                 uint32_t ci = (uint32_t)i;
-                CK(cudaMemcpyAsync((int64_t*)h->entry.p + i, &true_e, 8, cudaMemcpyHostToDevice, sm));
-                CK(cudaMemcpyAsync(h->walk_list.p, &ci, 4, cudaMemcpyHostToDevice, sm));
+                UP((int64_t*)h->entry.p + i, &true_e, 8);
+                UP(h->walk_list.p, &ci, 4);
                 k2_walk<<<1, 32, 0, sm>>>(spw, h->chunk_start.as<int64_t>(), (uint32_t)nb, h->entry.as<int64_t>(), h->slot_base.as<uint32_t>(), h->slots.as<uint16_t>(), h->count.as<uint32_t>(), h->exitb.as<int64_t>(), (int*)h->misc.p, h->walk_list.as<uint32_t>(), 1);
                 CK(cudaGetLastError()); st.gpu_launches++;
-                CK(cudaMemcpyAsync(&ext[i], (int64_t*)h->exitb.p + i, 8, cudaMemcpyDeviceToHost, sm));
-                CK(cudaMemcpyAsync(&cnt[i], (uint32_t*)h->count.p + i, 4, cudaMemcpyDeviceToHost, sm));
-                CK(cudaMemcpyAsync(&walk_err, h->misc.p, 4, cudaMemcpyDeviceToHost, sm));
+                DOWN(fx_ext, int64_t, (int64_t*)h->exitb.p + i, 8); DOWN(fx_cnt, uint32_t, (uint32_t*)h->count.p + i, 4); DOWN(fx_err, int, h->misc.p, 4);
                 CK(cudaStreamSynchronize(sm));
+                ext[i] = *fx_ext; cnt[i] = *fx_cnt; walk_err = *fx_err;
                 ent[i] = true_e;
             }
             if (true_e != ENTRY_NONE) {
@@ -598,7 +648,7 @@ int run_pipeline(bdepth* h, RunMode mode, RunOut* ro, Emitter* em = nullptr) {
                 else if (cstart[i + 1] > u_limit) {   // partial: count slots below the limit
                     tmp_slots.resize(cnt[i]);
                     CK(cudaMemcpy(tmp_slots.data(), (uint16_t*)h->slots.p + sbase[i], cnt[i] * 2, cudaMemcpyDeviceToHost));
-                    uint32_t k = 0; while (k < cnt[i] && cstart[i] + tmp_slots[k] < u_limit) k++;
+                    uint32_t k = 0; while (k < cnt[i] && ((k == 0 || cstart[i] > 0) ? cstart[i] : 0) + tmp_slots[k] < u_limit) k++;     // slot encoding: see k2_walk
                     cnt[i] = k;
                 }
             }
@@ -606,22 +656,23 @@ int run_pipeline(bdepth* h, RunMode mode, RunOut* ro, Emitter* em = nullptr) {
         }
         rbase[nb] = (uint32_t)R;
         if (R > 0xFFFFFFF0ull) return fail(h, BDEPTH_ERR_ARG, "batch too large");
-        CK(cudaMemcpyAsync(h->count.p, cnt.data(), nb * 4, cudaMemcpyHostToDevice, sm));
-        if (limited && tail < u_limit && tail < (int64_t)ub && b1 < B.size()) return fail(h, BDEPTH_ERR_FORMAT, "record at the shard boundary spans more than %u BGZF blocks", SHARD_EXTRA_BLOCKS);
-        CK(cudaMemcpyAsync(h->rec_base.p, rbase.data(), (nb + 1) * 4, cudaMemcpyHostToDevice, sm));
+        UP(h->count.p, cnt, nb * 4);
+        if (limited && last_batch && tail < u_limit && tail < (int64_t)ub && b1 < B.size()) return fail(h, BDEPTH_ERR_FORMAT, "record at the shard boundary spans more than %u BGZF blocks", SHARD_EXTRA_BLOCKS);
+        UP(h->rec_base.p, rbase.data(), (nb + 1) * 4);
         st.n_records += R;
         // ---- K2 decode
         size_t Rc = R ? R : 1;
         CK(h->soa_start.ensure(Rc * 8)); CK(h->soa_span.ensure(Rc * 4)); CK(h->soa_meta.ensure(Rc * 4)); CK(h->soa_off.ensure(Rc * 8)); CK(h->soa_ncl.ensure(Rc * 4)); CK(h->soa_lseq.ensure(Rc * 4)); CK(h->long_list.ensure(Rc * 4));
         RecordSoA soa{h->soa_start.as<uint64_t>(), h->soa_span.as<uint32_t>(), h->soa_meta.as<uint32_t>(), h->soa_off.as<int64_t>(), h->soa_ncl.as<uint32_t>(), h->soa_lseq.as<int32_t>()};
         ScanStats zs{0, 0, 0, 0, ~0ull, 0, 0, ~0ull};
-        CK(cudaMemcpyAsync(h->scan_stats.p, &zs, sizeof zs, cudaMemcpyHostToDevice, sm));
+        UP(h->scan_stats.p, &zs, sizeof zs);
         if (mode == RUN_SCAN_ONLY && !h->ref_has.p) { CK(h->ref_has.ensure((nref / 32 + 2) * 4)); CK(cudaMemsetAsync(h->ref_has.p, 0, (nref / 32 + 2) * 4, sm)); }
         k2_decode<<<(unsigned)((nb * 32 + 255) / 256), 256, 0, sm>>>(sp, h->chunk_start.as<int64_t>(), (uint32_t)nb, h->slot_base.as<uint32_t>(), h->slots.as<uint16_t>(), h->count.as<uint32_t>(), h->rec_base.as<uint32_t>(), soa, h->mapq_gt, h->flag_reject, h->scan_stats.as<ScanStats>(), h->long_list.as<uint32_t>(), h->ref_has.as<uint32_t>(), rgt);
         CK(cudaGetLastError()); st.gpu_launches++;
-        ScanStats ss; CK(cudaMemcpyAsync(&ss, h->scan_stats.p, sizeof ss, cudaMemcpyDeviceToHost, sm));
+        DOWN(ssp, ScanStats, h->scan_stats.p, sizeof(ScanStats));
         CK(cudaEventRecord(e3, sm));
         CK(cudaStreamSynchronize(sm));
+        const ScanStats ss = *ssp;
         if (ss.rg_err != ~0ull) return fail(h, BDEPTH_ERR_FORMAT, "error in read #%llu of the batch: its read group is not present in the header", ss.rg_err);
         st.n_records_pass += ss.n_pass; st.n_cigar_ops += ss.n_cigar; st.seq_bytes += ss.seq_bytes; st.long_reads += ss.n_long;
         if (ss.n_pass) { shard_min = std::min<uint64_t>(shard_min, ss.min_start); shard_max = std::max<uint64_t>(shard_max, ss.max_end); }
@@ -654,7 +705,7 @@ int run_pipeline(bdepth* h, RunMode mode, RunOut* ro, Emitter* em = nullptr) {
                 // the index does not describe this file (the reference only checks that one exists, depth.d:1166):
                 // start over with the whole genome as the counter window
                 if (!h->bai_window_ok) return fail(h, BDEPTH_ERR_FORMAT, "read extends past the end of the reference space");
-                h->bai_window_ok = false; CK(cudaStreamSynchronize(sm));
+                h->bai_window_ok = false; CK(cudaDeviceSynchronize());
                 return run_pipeline(h, mode, ro, em);
             }
             uint64_t t_lo = (gmin - h->cnt_base) / TILE_POS, t_hi = (gmax - h->cnt_base + TILE_POS - 1) / TILE_POS;
@@ -681,13 +732,16 @@ int run_pipeline(bdepth* h, RunMode mode, RunOut* ro, Emitter* em = nullptr) {
         if (em && mode == RUN_FULL && h->world == 1 && !last_batch && ss.n_pass) { int rce = em->advance(ss.max_start / TILE_POS * TILE_POS, e4); if (rce) return rce; }
         // ---- carry the incomplete tail record to the front of the next batch
         uint64_t new_carry = (uint64_t)((int64_t)ub - tail);
-        if (!last_batch && new_carry) {
+        if (!last_batch && last_sub && new_carry) {      // inside a batch the tail already sits right below the next sub-batch
             if (new_carry > CARRY_MAX) return fail(h, BDEPTH_ERR_FORMAT, "BAM record larger than %zu bytes", CARRY_MAX);
-            CK(cudaMemcpyAsync(u0 - new_carry, u0 + tail, new_carry, cudaMemcpyDeviceToDevice, sm));
+            CK(cudaMemcpyAsync(m_u0 - new_carry, u0 + tail, new_carry, cudaMemcpyDeviceToDevice, sm));
         }
         CK(cudaStreamSynchronize(sm));
-        { float t; if (!h->staged) { CK(cudaEventElapsedTime(&t, h->ev[18 + (batch_no & 1)], h->ev[14 + (batch_no & 1)])); ms_h2d += t; } CK(cudaEventElapsedTime(&t, e1, e2)); ms_k1 += t; CK(cudaEventElapsedTime(&t, e2, e3)); ms_k2 += t; CK(cudaEventElapsedTime(&t, e3, e4)); ms_k3 += t; }
-        carry_len = last_batch ? 0 : new_carry; first_batch = false; b = b1; batch_no++;
+        { float t; if (!h->staged && last_sub) { CK(cudaEventElapsedTime(&t, h->ev[18 + (batch_no & 1)], h->ev[14 + (batch_no & 1)])); ms_h2d += t; } if (last_sub) { CK(cudaEventElapsedTime(&t, e1, e2)); ms_k1 += t; } CK(cudaEventElapsedTime(&t, e2, e3)); ms_k2 += t; CK(cudaEventElapsedTime(&t, e3, e4)); ms_k3 += t; }
+        carry_len = last_batch ? 0 : new_carry; first_batch = false;
+        hs.used = 0;      // synchronised above: the scratch is free again
+        }   // sub-batches
+        b = mb1; batch_no++;
     }
     st.ms_h2d = ms_h2d; st.ms_inflate = ms_k1; st.ms_scan = ms_k2; st.ms_coverage = ms_k3;
     st.positions = mode == RUN_FULL ? h->hdr.total_len : 0;
@@ -771,6 +825,7 @@ void bdepth_close(bdepth_t* h) {
     h->seg.s.release(); h->seg.e.release(); h->seg.pmax.release(); h->seg.id.release(); h->seg.reads.release(); h->seg.minstart.release(); h->seg.bases_reads.release();
     if (h->comm) { nccl().CommDestroy(h->comm); h->comm = nullptr; }
     if (h->pinned) cudaFreeHost(h->pinned);
+    h->hs.release();
     if (h->s_main) { cudaStreamDestroy(h->s_main); cudaStreamDestroy(h->s_copy); cudaStreamDestroy(h->s_d2h); for (auto& ks : h->s_k1) cudaStreamDestroy(ks); for (auto& e : h->ev) cudaEventDestroy(e); for (int q = 0; q < 2; q++) for (auto& e : h->chunk_ev[q]) cudaEventDestroy(e); for (auto& e : h->k1_ev) cudaEventDestroy(e); }
     h->comp2[0].release(); h->comp2[1].release();
     if (h->mapped) munmap((void*)h->file, h->file_len);
@@ -834,9 +889,10 @@ int bdepth_plan_shards(const char* bam_path, int world, uint64_t* out) {
     for (int k = 1; k < world; k++) out[k - 1] = shard_cut_voffset(vos, (uint64_t)sb.st_size, k, world);
     return 0;
 }
-int bdepth_set_tuning(bdepth_t* h, uint64_t batch_inflated_bytes, uint64_t window_positions) {
+int bdepth_set_tuning(bdepth_t* h, uint64_t batch_inflated_bytes, uint64_t chunk_blocks) {
     if (batch_inflated_bytes) h->batch_u = std::max<uint64_t>(batch_inflated_bytes, 1 << 20);
-    h->window_positions = window_positions; h->staged = false;
+    if (chunk_blocks) h->chunk_blocks = chunk_blocks;
+    h->staged = false;
     return 0;
 }
 

@@ -29,7 +29,10 @@ namespace bdk {
 constexpr int TILE_POS = 1024;          // positions per K3 CTA (256 threads x 4)
 constexpr uint32_t SPAN_SHORT = 1024;   // reads spanning more go to the scatter path
 constexpr int N_PLANES = 7;
-constexpr int64_t ENTRY_NONE = -1;
+// "no record starts in this block".  Not -1: an entry of -1 is legal (a sub-batch that begins with one carried byte of
+// the next record's size field).  The byte pattern 0x80.. lets cudaMemset initialise an entry table.
+constexpr int64_t ENTRY_NONE = (int64_t)0x8080808080808080ull;
+constexpr int ENTRY_NONE_BYTE = 0x80;
 
 // ------------------------------------------------------------------------------------- K1
 struct BlockDesc {
@@ -143,7 +146,9 @@ __global__ void k2_walk(ScanParams sp, const int64_t* __restrict__ chunk_start, 
             uint32_t bs = ldu32(sp.u + o);
             if (bs < 32u) { atomicExch(err, 1); break; }       // corrupt chain
             if (o + 4 + (int64_t)bs > sp.u_end) break;          // incomplete record: tail, carried to the next batch
-            sl[n++] = (uint16_t)(o - c0);
+            // 16-bit offsets: relative to the chunk start, except that after the first record of a chunk that begins
+            // inside the carried tail (c0 < 0) the base is 0 -- a full 64 KB block plus a carry does not fit 16 bits
+            sl[n] = (uint16_t)(o - ((n == 0 || c0 > 0) ? c0 : 0)); n++;
             o += 4 + (int64_t)bs;
         }
     }
@@ -211,7 +216,7 @@ __global__ void k2_decode(ScanParams sp, const int64_t* __restrict__ chunk_start
     unsigned long long loc_pass = 0, loc_cig = 0, loc_seq = 0, loc_maxend = 0, loc_minstart = ~0ull, loc_maxstart = 0;
     uint32_t has_word = 0xFFFFFFFFu, has_bits = 0;      // per-lane pending "reference has reads" bits (one atomic per warp, not per read)
     for (uint32_t k = lane; k < n; k += 32) {
-        int64_t o = c0 + sl[k];
+        int64_t o = ((k == 0 || c0 > 0) ? c0 : 0) + sl[k];
         const uint8_t* p = sp.u + o + 4;
         // refID, pos, bin_mq_nl, flag_nc, l_seq: 20 consecutive bytes = 6 aligned words + 5 funnel shifts
         uintptr_t pa = reinterpret_cast<uintptr_t>(p);

@@ -106,7 +106,7 @@ def test_long_reads_spanning_many_bgzf_blocks(tmp_path):
     import sambamba_b200 as sb
     want, _ = helpers.oracle_counts(p)
     with sb.BDepth(p) as b:
-        b.set_tuning(batch_bytes=1 << 20)          # force the carry path: records straddle batches
+        b.set_tuning(batch_bytes=1 << 20, chunk_blocks=2)          # force the carry path: records straddle batches and sub-batches
         got = b.run_base()
         assert b.stats()["n_batches"] >= 2
     assert np.array_equal(got, want)

@@ -87,6 +87,22 @@ def test_multi_batch_equals_single_batch(sb, synth):
     assert np.array_equal(got, want)
 
 
+@pytest.mark.parametrize("chunk_blocks", [1, 3, 16])
+def test_sub_batches_equal_single_pass(sb, synth, chunk_blocks):
+    # every H2D chunk is a sub-batch whose scan/coverage runs while later chunks are still being inflated; records that
+    # straddle a sub-batch boundary are carried in place.  Tiny chunks put a boundary after (almost) every BGZF block.
+    p = synth["mid"]
+    want, _ = helpers.oracle_counts(p)
+    with sb.BDepth(p) as b:
+        b.set_tuning(chunk_blocks=chunk_blocks)
+        got = b.run_base()
+        assert np.array_equal(got, want)
+        b.set_tuning(batch_bytes=5 << 20, chunk_blocks=chunk_blocks)     # several batches of several sub-batches
+        got = b.run_base()
+        assert b.stats()["n_batches"] > 3
+    assert np.array_equal(got, want)
+
+
 def test_filter_none(sb, synth):
     p = synth["tiny"]
     want, _ = helpers.oracle_counts(p, mapq_gt=-1, flag_reject=0)
