@@ -278,18 +278,25 @@ BD_HD int build_table(const Tab& t, const uint8_t* lens, int n, HuffLim& lim) {
     return INF_OK;
 }
 
-// Decode one symbol of a canonical code.  Returns -1 on an invalid code; consumes its bits.
+// Decode the symbol at the bottom of `bits` (the low 32 bits of the reservoir, >= 15 of them valid) without
+// consuming anything: returns the symbol (-1 on an invalid code) and its length in L.
 template <class Tab, int KIND>
-BD_HD int decode_sym(const Tab& t, const HuffPk& lim, BitReader& br) {
-    uint32_t rev15 = bitrev32((uint32_t)br.bb) >> 17;
-    int L = 1 + count_ge16(rev15, lim);          // code length; 16 means "beyond the last code"
+BD_HD int decode_sym_at(const Tab& t, const HuffPk& lim, uint32_t bits, int& L) {
+    uint32_t rev15 = bitrev32(bits) >> 17;
+    L = 1 + count_ge16(rev15, lim);          // code length; 16 means "beyond the last code"
     if (L > 15) return -1;
     int delta = (int)(int16_t)tab_ld16(t, KIND == 0 ? T_LL_DELTA : T_D_DELTA, L - 1);
     int idx = (int)(rev15 >> (15 - L)) + delta;
     if (idx < 0 || idx >= (KIND == 0 ? 288 : 32)) return -1;
     BD_STAT(KIND == 0 ? g_inflate_stats.len_hist[L]++ : 0);
-    br.drop(L);
     return KIND == 0 ? (int)tab_ld10(t, T_LL_SYMS, idx) : (int)tab_ld8(t, T_D_SYMS, idx);
+}
+// Decode one symbol of a canonical code.  Returns -1 on an invalid code; consumes its bits.
+template <class Tab, int KIND>
+BD_HD int decode_sym(const Tab& t, const HuffPk& lim, BitReader& br) {
+    int L; int sym = decode_sym_at<Tab, KIND>(t, lim, (uint32_t)br.bb, L);
+    if (sym >= 0) br.drop(L);
+    return sym;
 }
 
 // Read the dynamic-block header and produce lens[] (RFC 1951 3.2.7).  lens must hold 320 bytes.
@@ -495,7 +502,7 @@ BD_HD int inflate_block(const Tab& t, const uint32_t* words, uint64_t byte_off, 
     uint32_t p_w0 = 0, p_w1 = 0, p_sh = 0, p_n = 0; bool p_far = false;
     for (;;) {
         BD_STAT(g_inflate_stats.iters++);
-        int sym = -1; bool have_sym = false;
+        int sym = -1; bool have_sym = false; uint32_t lit2 = 0, n_lit = 1;
         if (m_rem == 0) {
             if (state == ST_HDR) {
                 HdrResult hr = next_block(t, br, lens, limpk, pos, isize);
@@ -509,6 +516,13 @@ BD_HD int inflate_block(const Tab& t, const uint32_t* words, uint64_t byte_off, 
             if (state == ST_SYM) {
                 br.refill(); sym = decode_sym<Tab, 0>(t, ll, br); have_sym = true;
                 if (sym < 0) { rc = INF_ERR_CODE; state = ST_DONE; have_sym = false; }
+                else if (sym < 256 && pos + 2 <= isize) {
+                    // Three of four symbols of BAM data are literals and most follow another literal: look at the
+                    // next symbol too (>= 18 valid bits remain after a refill and one code) and take it in the same
+                    // iteration if it is a literal.  Anything else stays in the reservoir for the next iteration.
+                    int L2; int s2 = decode_sym_at<Tab, 0>(t, ll, (uint32_t)br.bb, L2);
+                    if (s2 >= 0 && s2 < 256) { br.drop(L2); lit2 = (uint32_t)s2; n_lit = 2; }
+                }
             } else if (state == ST_STORED) {
                 br.refill(); sym = (int)br.get(8); have_sym = true;
                 if (--stored_rem == 0) state = bfinal ? ST_DONE : ST_HDR;
@@ -528,7 +542,7 @@ BD_HD int inflate_block(const Tab& t, const uint32_t* words, uint64_t byte_off, 
         if (have_sym) {
             if (sym < 256) {
                 if (pos >= isize) { rc = INF_ERR_OVERRUN; state = ST_DONE; }
-                else { BD_STAT(g_inflate_stats.lits++); p_w0 = (uint32_t)sym; p_w1 = 0; p_sh = 0; p_n = 1; pos++; }
+                else { BD_STAT(g_inflate_stats.lits += n_lit); p_w0 = (uint32_t)sym | (lit2 << 8); p_w1 = 0; p_sh = 0; p_n = n_lit; pos += n_lit; }
             } else if (sym == 256) {
                 state = bfinal ? ST_DONE : ST_HDR;
             } else {
