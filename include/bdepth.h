@@ -148,6 +148,11 @@ int bdepth_nccl_unique_id(void* out128);
  * the first linear-index record start at or after k * file_size / world (k = 1..world-1);
  * UINT64_MAX when there is none.  Used by the sharding tests. */
 int bdepth_plan_shards(const char* bam_path, int world, uint64_t* out_voffsets);
+/* Host-only (no GPU needed): the merged list of BGZF virtual-offset ranges [beg, end) a query for `regions`
+ * has to read, computed from the BAI bins and linear index as getGroupChunks does
+ * (BioD/bio/std/hts/bam/randomaccessmanager.d:247-294).  Writes up to `cap` (beg, end) pairs, returns the number
+ * of ranges (or a negative error).  With regions set, the run entry points stage and inflate only these. */
+long bdepth_plan_region_chunks(const char* bam_path, const bdepth_region* regions, size_t n, uint64_t* out_pairs, size_t cap);
 /* Tuning knobs (0 = default): uncompressed bytes per batch (one inflate buffer in HBM); BGZF blocks per
  * host-to-device chunk, which is also the sub-batch whose scan / coverage / delivery overlaps the inflate of
  * the chunks that arrive after it. */

@@ -95,6 +95,8 @@ def load_library():
     L.bdepth_stage.argtypes = [vp]
     L.bdepth_run_resident.argtypes = [vp]
     L.bdepth_plan_shards.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_uint64)]
+    L.bdepth_plan_region_chunks.argtypes = [C.c_char_p, C.POINTER(Region), C.c_size_t, C.POINTER(C.c_uint64), C.c_size_t]
+    L.bdepth_plan_region_chunks.restype = C.c_long
     L.bdepth_run_base.argtypes = [vp, TILE_CB, vp]
     L.bdepth_run_base_text.argtypes = [vp, C.POINTER(TextOpts), TEXT_CB, vp]
     L.bdepth_run_windows.argtypes = [vp, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32), C.c_size_t, STAT_CB, vp]
@@ -113,7 +115,7 @@ EXPORTED_SYMBOLS = [
     "bdepth_device_count", "bdepth_open", "bdepth_open_memory", "bdepth_close", "bdepth_last_error", "bdepth_n_ref",
     "bdepth_ref_name", "bdepth_ref_length", "bdepth_header_text", "bdepth_is_coordinate_sorted", "bdepth_has_index",
     "bdepth_n_samples", "bdepth_sample_name", "bdepth_set_filter", "bdepth_set_min_baseq", "bdepth_set_combined", "bdepth_set_regions",
-    "bdepth_set_shard", "bdepth_nccl_unique_id", "bdepth_plan_shards", "bdepth_set_tuning", "bdepth_stage", "bdepth_run_resident", "bdepth_run_base", "bdepth_run_base_text",
+    "bdepth_set_shard", "bdepth_nccl_unique_id", "bdepth_plan_shards", "bdepth_plan_region_chunks", "bdepth_set_tuning", "bdepth_stage", "bdepth_run_resident", "bdepth_run_base", "bdepth_run_base_text",
     "bdepth_run_windows", "bdepth_run_regions", "bdepth_get_stats", "bdepth_ref_has_reads", "bdepth_inflate_to_host", "bdepth_scan_to_host",
 ]
 
@@ -134,6 +136,18 @@ def plan_shards(path, world):
     if rc:
         raise BDepthError(rc, L.bdepth_last_error(None).decode())
     return list(out)[:world - 1]
+
+
+def plan_region_chunks(path, regions):
+    """Host-only: merged BGZF virtual-offset ranges [(beg, end), ...] a query for regions [(ref_id, start, end)] reads."""
+    L = load_library()
+    arr = (Region * max(1, len(regions)))(*[Region(*r) for r in regions])
+    n = L.bdepth_plan_region_chunks(os.fsencode(path), arr, len(regions), None, 0)
+    if n < 0:
+        raise BDepthError(n, L.bdepth_last_error(None).decode())
+    out = (C.c_uint64 * max(1, 2 * n))()
+    L.bdepth_plan_region_chunks(os.fsencode(path), arr, len(regions), out, n)
+    return [(out[2 * i], out[2 * i + 1]) for i in range(n)]
 
 
 class BDepth:

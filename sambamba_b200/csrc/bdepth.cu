@@ -138,6 +138,14 @@ struct bdepth {
     // ---- shard (resolved lazily)
     bool shard_ready = false;
     size_t blk_lo = 0, blk_hi = 0; int64_t entry0 = 0; uint64_t limit_abs_u = 0;
+    // Sparse staging for region queries: only the BGZF blocks inside the BAI chunk list of the
+    // regions are copied, inflated and scanned.  vblocks = those blocks with uoff re-based to a compact stream;
+    // a segment is one merged chunk: it starts at a record (seg_entry = offset inside its first block) and ends at
+    // one (seg_limit = offset inside its last block at which the walk stops).
+    bool sparse_ok = true;                            // cleared when the index turns out not to describe the file
+    bool sparse_on = false;                           // this run uses vblocks
+    std::vector<HostBlock> vblocks; std::vector<int32_t> seg_entry /* -1: not a segment start */; std::vector<uint32_t> seg_limit /* UINT32_MAX: none */;
+    DevBuf anchors_idx, anchors_val, chunk_limit;
     // ---- device state
     cudaStream_t s_main = nullptr, s_copy = nullptr, s_d2h = nullptr;
     cudaEvent_t ev[32] = {};
@@ -404,6 +412,60 @@ int exchange_boundaries(bdepth* h, uint64_t shard_min, uint64_t shard_max) {
     return 0;
 }
 
+// Build the sparse block list for the current regions.  Returns false when sparse staging does not apply (no
+// regions, no usable index, several ranks, input staged as a whole) or would not save anything.
+static bool plan_sparse(bdepth* h) {
+    h->sparse_on = false;
+    if (h->regions.empty() || !h->sparse_ok || h->world != 1 || h->staged || !h->bai.valid || h->bai.bins.size() != h->hdr.ref_len.size()) return false;
+    const auto& B = h->blocks; if (B.empty()) return false;
+    {   // a credible index starts where the records start (a dummy or foreign .bai is accepted by the reference, which only
+        // checks that one exists, depth.d:1166 -- it must not make reads disappear here)
+        uint64_t mn = UINT64_MAX; for (uint64_t v : h->bai.min_chunk_beg) mn = std::min(mn, v);
+        size_t lo = 0, hi = B.size(); while (lo + 1 < hi) { size_t m = (lo + hi) / 2; if (B[m].uoff <= h->hdr.first_rec_off) lo = m; else hi = m; }
+        uint64_t vo_first = (B[lo].coff << 16) | (h->hdr.first_rec_off - B[lo].uoff);
+        if (h->hdr.first_rec_off - B[lo].uoff >= B[lo].isize && lo + 1 < B.size()) vo_first = B[lo + 1].coff << 16;
+        if (mn != vo_first) { h->sparse_ok = false; return false; }
+    }
+    std::vector<HostRegion> rg; rg.reserve(h->regions.size());
+    for (auto& g : h->regions) rg.push_back(HostRegion{g.ref_id, g.start, g.end});
+    std::vector<BaiChunk> cs = region_chunks(h->bai, rg);
+    auto block_at = [&](uint64_t coff) -> long { size_t lo = 0, hi = B.size(); while (lo + 1 < hi) { size_t m = (lo + hi) / 2; if (B[m].coff <= coff) lo = m; else hi = m; } return B[lo].coff == coff ? (long)lo : -1; };
+    struct Seg { size_t b0, b1; uint32_t entry, limit; };      // blocks [b0, b1], entry inside b0, limit inside b1
+    std::vector<Seg> segs;
+    for (const BaiChunk& c : cs) {
+        long kb = block_at(c.beg >> 16), ke = block_at(c.end >> 16);
+        uint32_t wb = (uint32_t)(c.beg & 0xFFFF), we = (uint32_t)(c.end & 0xFFFF);
+        if (kb < 0) { h->sparse_ok = false; return false; }                                   // the index does not describe this file
+        if (ke < 0) { if ((c.end >> 16) >= h->file_len || (c.end >> 16) >= B.back().coff + B.back().bsize) { ke = (long)B.size() - 1; we = B.back().isize; } else { h->sparse_ok = false; return false; } }
+        if (wb >= B[kb].isize) { kb++; wb = 0; if ((size_t)kb >= B.size()) continue; }      // "end of block" == start of the next one
+        if (we == 0) { if (ke == 0) continue; ke--; we = B[ke].isize; }
+        if (we > B[ke].isize) { h->sparse_ok = false; return false; }
+        if (ke < kb || (ke == kb && we <= wb)) continue;
+        // the header blocks are never part of a segment; a chunk cannot begin before the first record
+        if (B[kb].uoff + wb < h->hdr.first_rec_off) { h->sparse_ok = false; return false; }
+        if (!segs.empty() && (size_t)kb <= segs.back().b1) {         // touches the previous segment's last block: one segment
+            if ((size_t)ke > segs.back().b1 || ((size_t)ke == segs.back().b1 && we > segs.back().limit)) { segs.back().b1 = (size_t)ke; segs.back().limit = we; }
+            continue;
+        }
+        segs.push_back(Seg{(size_t)kb, (size_t)ke, wb, we});
+    }
+    size_t nsel = 0; for (auto& sg : segs) nsel += sg.b1 - sg.b0 + 1;
+    if (nsel * 10 > B.size() * 9) return false;                      // nearly the whole file: the plain path is simpler
+    h->vblocks.clear(); h->seg_entry.clear(); h->seg_limit.clear();
+    h->vblocks.reserve(nsel); h->seg_entry.reserve(nsel); h->seg_limit.reserve(nsel);
+    uint64_t vu = 0;
+    for (auto& sg : segs) for (size_t k = sg.b0; k <= sg.b1; k++) {
+        HostBlock hb = B[k]; hb.uoff = vu; vu += hb.isize;
+        h->vblocks.push_back(hb); h->seg_entry.push_back(k == sg.b0 ? (int32_t)sg.entry : -1); h->seg_limit.push_back(k == sg.b1 ? sg.limit : UINT32_MAX);
+    }
+    h->sparse_on = true;
+    return true;
+}
+
+__global__ void k_scatter_i64(int64_t* __restrict__ dst, const uint32_t* __restrict__ idx, const int64_t* __restrict__ val, uint32_t n) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) dst[idx[i]] = val[i];
+}
+
 struct RunOut {                    // optional sinks for the kernel-level entry points
     uint8_t* inflate_dst = nullptr; uint64_t inflate_cap = 0; uint64_t inflate_len = 0;
     uint64_t scan_cap = 0; uint64_t scan_n = 0;
@@ -419,7 +481,9 @@ int run_pipeline(bdepth* h, RunMode mode, RunOut* ro, Emitter* em = nullptr) {
     auto t_host0 = std::chrono::steady_clock::now();
     bdepth_stats& st = h->st; uint32_t launches0 = 0;
     st = bdepth_stats{}; st.gpu_launches = launches0;
-    const auto& B = h->blocks;
+    const bool sparse = mode == RUN_FULL && plan_sparse(h);
+    const std::vector<HostBlock>& B = sparse ? h->vblocks : h->blocks;
+    const size_t blk_lo = sparse ? 0 : h->blk_lo, blk_hi = sparse ? B.size() : h->blk_hi;
     const size_t nref = h->hdr.ref_len.size();
     cudaStream_t sm = h->s_main;
 
@@ -459,7 +523,7 @@ int run_pipeline(bdepth* h, RunMode mode, RunOut* ro, Emitter* em = nullptr) {
         CK(cudaStreamSynchronize(sm));
         rgt = RgTable{h->rg_ids.as<uint8_t>(), h->rg_offs.as<uint32_t>(), h->rg_samp.as<uint8_t>(), (uint32_t)offs.size()};
     }
-    { uint64_t shard_u = h->blk_hi > h->blk_lo ? B[h->blk_hi - 1].uoff + B[h->blk_hi - 1].isize - B[h->blk_lo].uoff : 0; CK(h->ubuf.ensure(CARRY_MAX + std::min<uint64_t>(h->batch_u + 65536, shard_u) + 256)); }
+    { uint64_t shard_u = blk_hi > blk_lo ? B[blk_hi - 1].uoff + B[blk_hi - 1].isize - B[blk_lo].uoff : 0; CK(h->ubuf.ensure(CARRY_MAX + std::min<uint64_t>(h->batch_u + 65536, shard_u) + 256)); }
     CK(h->misc.ensure(64));
     HostScratch& hs = h->hs;
     // up(): host words -> device buffer; down(): device words -> mapped host memory, readable after the next
@@ -483,28 +547,48 @@ int run_pipeline(bdepth* h, RunMode mode, RunOut* ro, Emitter* em = nullptr) {
     uint64_t carry_len = 0; bool first_batch = true;
     uint64_t shard_min = UINT64_MAX, shard_max = 0;
     CK(cudaEventRecord(h->ev[10], sm));
-    size_t b = h->blk_lo;
+    size_t b = blk_lo;
     if (ro) { ro->inflate_len = 0; ro->scan_n = 0; }
     if (!h->staged) {   // size both compressed-data buffers for the largest batch up front (ensure() must not reallocate mid-flight)
-        uint64_t mx = 0; for (size_t bb = h->blk_lo; bb < h->blk_hi;) { size_t e = bb; uint64_t u = 0; while (e < h->blk_hi && (e == bb || u + B[e].isize <= h->batch_u)) { u += B[e].isize; e++; } mx = std::max<uint64_t>(mx, B[e - 1].coff + B[e - 1].bsize - (B[bb].coff & ~3ull)); bb = e; }
+        uint64_t mx = 0;
+        for (size_t bb = blk_lo; bb < blk_hi;) {
+            size_t e = bb; uint64_t u = 0, cb = 0; while (e < blk_hi && (e == bb || u + B[e].isize <= h->batch_u)) { u += B[e].isize; cb += B[e].bsize; e++; }
+            mx = std::max<uint64_t>(mx, sparse ? cb + 8 : B[e - 1].coff + B[e - 1].bsize - (B[bb].coff & ~3ull)); bb = e;
+        }
         CK(h->comp2[0].ensure(mx + 256)); CK(h->comp2[1].ensure(mx + 256));
     }
     size_t batch_no = 0;
-    auto batch_end = [&](size_t bb) { size_t e = bb; uint64_t u = 0; while (e < h->blk_hi && (e == bb || u + B[e].isize <= h->batch_u)) { u += B[e].isize; e++; } return e; };
+    auto batch_end = [&](size_t bb) { size_t e = bb; uint64_t u = 0; while (e < blk_hi && (e == bb || u + B[e].isize <= h->batch_u)) { u += B[e].isize; e++; } return e; };
     // H2D of blocks [bb, be) into comp2[slot]; waits until K1 of the batch that used the slot two batches ago is done
     const size_t H2D_CHUNK_BLOCKS = h->chunk_blocks;
+    // dco[slot][i] = where block bb+i of the batch sits in comp2[slot].  Plain runs keep the file layout (one copy
+    // per chunk); sparse runs pack the selected blocks back to back (one copy per run of file-adjacent blocks).
+    std::vector<uint64_t> dco[2];
     auto issue_h2d = [&](size_t no, size_t bb, size_t be) -> int {
         int slot = (int)(no & 1);
         uint64_t g0 = B[bb].coff & ~3ull;
         if (no >= 2) CK(cudaStreamWaitEvent(h->s_copy, h->ev[16 + slot], 0));
         CK(cudaEventRecord(h->ev[18 + slot], h->s_copy));
         h->chunk_end[slot].clear();
+        dco[slot].resize(be - bb);
+        { uint64_t acc = 0; for (size_t i = bb; i < be; i++) { dco[slot][i - bb] = sparse ? acc : B[i].coff - g0; acc += B[i].bsize; } }
         size_t nch = 0;
         for (size_t c0 = bb; c0 < be; c0 += H2D_CHUNK_BLOCKS, nch++) {
             size_t c1 = std::min(be, c0 + H2D_CHUNK_BLOCKS);
-            uint64_t a = c0 == bb ? g0 : B[c0].coff, e = B[c1 - 1].coff + B[c1 - 1].bsize;
-            CK(cudaMemcpyAsync((uint8_t*)h->comp2[slot].p + (a - g0), h->file + a, e - a, cudaMemcpyHostToDevice, h->s_copy));
-            if (c1 == be) CK(cudaMemsetAsync((uint8_t*)h->comp2[slot].p + (e - g0), 0, 128, h->s_copy));
+            uint64_t dev_end;
+            if (!sparse) {
+                uint64_t a = c0 == bb ? g0 : B[c0].coff, e = B[c1 - 1].coff + B[c1 - 1].bsize;
+                CK(cudaMemcpyAsync((uint8_t*)h->comp2[slot].p + (a - g0), h->file + a, e - a, cudaMemcpyHostToDevice, h->s_copy));
+                dev_end = e - g0;
+            } else {
+                for (size_t r0 = c0; r0 < c1;) {
+                    size_t r1 = r0 + 1; while (r1 < c1 && B[r1].coff == B[r1 - 1].coff + B[r1 - 1].bsize) r1++;
+                    CK(cudaMemcpyAsync((uint8_t*)h->comp2[slot].p + dco[slot][r0 - bb], h->file + B[r0].coff, B[r1 - 1].coff + B[r1 - 1].bsize - B[r0].coff, cudaMemcpyHostToDevice, h->s_copy));
+                    r0 = r1;
+                }
+                dev_end = dco[slot][c1 - 1 - bb] + B[c1 - 1].bsize;
+            }
+            if (c1 == be) CK(cudaMemsetAsync((uint8_t*)h->comp2[slot].p + dev_end, 0, 128, h->s_copy));
             if (h->chunk_ev[slot].size() <= nch) { cudaEvent_t ne; CK(cudaEventCreateWithFlags(&ne, cudaEventDisableTiming)); h->chunk_ev[slot].push_back(ne); }
             CK(cudaEventRecord(h->chunk_ev[slot][nch], h->s_copy));
             h->chunk_end[slot].push_back(c1);
@@ -512,28 +596,30 @@ int run_pipeline(bdepth* h, RunMode mode, RunOut* ro, Emitter* em = nullptr) {
         CK(cudaEventRecord(h->ev[14 + slot], h->s_copy));
         return 0;
     };
-    while (b < h->blk_hi) {
+    while (b < blk_hi) {
         // ---- batch extent
         size_t b1 = b; uint64_t ub = 0;
-        while (b1 < h->blk_hi && (b1 == b || ub + B[b1].isize <= h->batch_u)) { ub += B[b1].isize; b1++; }
-        const size_t nb = b1 - b; const bool last_batch = b1 == h->blk_hi;
+        while (b1 < blk_hi && (b1 == b || ub + B[b1].isize <= h->batch_u)) { ub += B[b1].isize; b1++; }
+        const size_t nb = b1 - b; const bool last_batch = b1 == blk_hi;
         const uint64_t batch_u0 = B[b].uoff;               // absolute inflated offset of the batch start
         st.n_batches++; st.n_blocks += nb; st.inflated_bytes += ub;
         // ---- compressed bytes on the device: H2D runs on the copy stream into one of two buffers, so the copy of
         // batch i+1 overlaps the kernels of batch i
-        uint64_t f0 = B[b].coff & ~3ull, f1 = B[b1 - 1].coff + B[b1 - 1].bsize;
-        const uint32_t* d_comp; uint64_t comp_base_off;
+        const uint32_t* d_comp;
         cudaEvent_t e0 = h->ev[0], e1 = h->ev[1], e2 = h->ev[2], e3 = h->ev[3], e4 = h->ev[4];
         CK(cudaEventRecord(e0, sm));
-        if (h->staged) { d_comp = h->comp.as<uint32_t>(); comp_base_off = h->staged_file_off; }
+        if (h->staged) d_comp = h->comp.as<uint32_t>();
         else {
             if (batch_no == 0) { int rcp = issue_h2d(0, b, b1); if (rcp) return rcp; }
-            d_comp = h->comp2[batch_no & 1].as<uint32_t>(); comp_base_off = f0;
+            d_comp = h->comp2[batch_no & 1].as<uint32_t>();
         }
-        st.file_bytes += f1 - B[b].coff;
         // ---- descriptors
         std::vector<BlockDesc> d(nb); uint64_t csum = 0;
-        for (size_t i = 0; i < nb; i++) { const HostBlock& hb = B[b + i]; d[i] = BlockDesc{hb.coff + hb.cdata_off - comp_base_off, hb.uoff - batch_u0, hb.csize, hb.isize}; csum += hb.csize; }
+        for (size_t i = 0; i < nb; i++) {
+            const HostBlock& hb = B[b + i];
+            uint64_t dev_off = h->staged ? hb.coff - h->staged_file_off : dco[batch_no & 1][i];
+            d[i] = BlockDesc{dev_off + hb.cdata_off, hb.uoff - batch_u0, hb.csize, hb.isize}; csum += hb.csize; st.file_bytes += hb.bsize;
+        }
         st.cdata_bytes += csum;
         CK(h->descs.ensure(nb * sizeof(BlockDesc))); CK(h->status.ensure(nb * sizeof(int))); CK(h->ubuf.ensure(CARRY_MAX + ub + 256));
         CK(hs.ensure(nb * (sizeof(BlockDesc) + 192) + 16384)); hs.used = 0;      // nothing is in flight here: every sub-batch ends synchronised
@@ -564,7 +650,7 @@ int run_pipeline(bdepth* h, RunMode mode, RunOut* ro, Emitter* em = nullptr) {
                 c0 = c1;
             }
         }
-        if (!h->staged && b1 < h->blk_hi) { int rcp = issue_h2d(batch_no + 1, b1, batch_end(b1)); if (rcp) return rcp; }
+        if (!h->staged && b1 < blk_hi) { int rcp = issue_h2d(batch_no + 1, b1, batch_end(b1)); if (rcp) return rcp; }
         const size_t mb = b, mb1 = b1; const uint64_t m_u0abs = batch_u0; uint8_t* const m_u0 = u0; const bool m_last = last_batch;
         for (size_t sbi = 0; sbi < subs.size(); sbi++) {
         const size_t b = subs[sbi].s0, b1 = subs[sbi].s1, nb = b1 - b;                  // from here on: the sub-batch
@@ -587,6 +673,8 @@ int run_pipeline(bdepth* h, RunMode mode, RunOut* ro, Emitter* em = nullptr) {
             continue;
         }
         // ---- K2: chunk table
+        const bool seg0 = sparse && h->seg_entry[b] >= 0;      // the sub-batch begins a new region-query chunk: nothing is carried into it
+        if (seg0) carry_len = 0;
         std::vector<int64_t> cstart(nb + 1); std::vector<uint32_t> sbase(nb + 1);
         { uint64_t acc = 0; for (size_t i = 0; i < nb; i++) { cstart[i] = (int64_t)(B[b + i].uoff - batch_u0); sbase[i] = (uint32_t)acc; uint64_t sz = B[b + i].isize + (i == 0 ? carry_len : 0); acc += sz / 36 + 2; } cstart[nb] = (int64_t)ub; sbase[nb] = (uint32_t)acc; cstart[0] = -(int64_t)carry_len;
           if (acc > 0xFFFFFFFFull) return fail(h, BDEPTH_ERR_ARG, "batch too large"); }
@@ -595,16 +683,31 @@ int run_pipeline(bdepth* h, RunMode mode, RunOut* ro, Emitter* em = nullptr) {
         UP(h->chunk_start.p, cstart.data(), (nb + 1) * 8);
         UP(h->slot_base.p, sbase.data(), (nb + 1) * 4);
         CK(cudaMemsetAsync(h->entry.p, ENTRY_NONE_BYTE, nb * 8, sm));
-        int64_t anchor = first_batch ? h->entry0 : -(int64_t)carry_len;
+        int64_t anchor = seg0 ? (int64_t)h->seg_entry[b] : first_batch ? h->entry0 : -(int64_t)carry_len;
         UP(h->entry.p, &anchor, 8);
         CK(cudaMemsetAsync(h->misc.p, 0, 64, sm));
         // records that START at or after the shard limit belong to the next rank
-        int64_t u_limit = (int64_t)ub; if (h->limit_abs_u < batch_u0 + ub) u_limit = h->limit_abs_u > batch_u0 ? (int64_t)(h->limit_abs_u - batch_u0) : 0;
+        int64_t u_limit = (int64_t)ub; if (!sparse && h->limit_abs_u < batch_u0 + ub) u_limit = h->limit_abs_u > batch_u0 ? (int64_t)(h->limit_abs_u - batch_u0) : 0;
         ScanParams sp{u0, -(int64_t)carry_len, (int64_t)ub, (int)nref, h->ref_len_d.as<uint32_t>(), h->ref_lin0_d.as<uint64_t>()};
         k2_guess_entries<<<(unsigned)((nb * 32 + 255) / 256), 256, 0, sm>>>(sp, h->chunk_start.as<int64_t>(), (uint32_t)nb, h->entry.as<int64_t>());
         CK(cudaGetLastError()); st.gpu_launches++;
+        const int64_t* d_limit = nullptr;
+        if (sparse) {       // chunks of the region query: exact entries at their first blocks, walk limits at their last ones
+            std::vector<uint32_t> ai; std::vector<int64_t> av; std::vector<int64_t> lim(nb, INT64_MAX);
+            for (size_t i = 0; i < nb; i++) {
+                if (i && h->seg_entry[b + i] >= 0) { ai.push_back((uint32_t)i); av.push_back(cstart[i] + h->seg_entry[b + i]); }
+                if (h->seg_limit[b + i] != UINT32_MAX) lim[i] = (i ? cstart[i] : 0) + (int64_t)h->seg_limit[b + i];
+            }
+            CK(h->chunk_limit.ensure(nb * 8)); UP(h->chunk_limit.p, lim.data(), nb * 8); d_limit = h->chunk_limit.as<int64_t>();
+            if (!ai.empty()) {
+                CK(h->anchors_idx.ensure(ai.size() * 4)); CK(h->anchors_val.ensure(av.size() * 8));
+                UP(h->anchors_idx.p, ai.data(), ai.size() * 4); UP(h->anchors_val.p, av.data(), av.size() * 8);
+                k_scatter_i64<<<(unsigned)((ai.size() + 255) / 256), 256, 0, sm>>>(h->entry.as<int64_t>(), h->anchors_idx.as<uint32_t>(), h->anchors_val.as<int64_t>(), (uint32_t)ai.size());
+                CK(cudaGetLastError()); st.gpu_launches++;
+            }
+        }
         ScanParams spw = sp;
-        k2_walk<<<(unsigned)((nb + 127) / 128), 128, 0, sm>>>(spw, h->chunk_start.as<int64_t>(), (uint32_t)nb, h->entry.as<int64_t>(), h->slot_base.as<uint32_t>(), h->slots.as<uint16_t>(), h->count.as<uint32_t>(), h->exitb.as<int64_t>(), (int*)h->misc.p, nullptr, 0);
+        k2_walk<<<(unsigned)((nb + 127) / 128), 128, 0, sm>>>(spw, h->chunk_start.as<int64_t>(), (uint32_t)nb, h->entry.as<int64_t>(), h->slot_base.as<uint32_t>(), h->slots.as<uint16_t>(), h->count.as<uint32_t>(), h->exitb.as<int64_t>(), (int*)h->misc.p, nullptr, 0, d_limit);
         CK(cudaGetLastError()); st.gpu_launches++;
         DOWN(ent, int64_t, h->entry.p, nb * 8); DOWN(ext, int64_t, h->exitb.p, nb * 8); DOWN(cnt, uint32_t, h->count.p, nb * 4);      // host-owned once synchronised
         DOWN(werr, int, h->misc.p, 4);
@@ -614,6 +717,7 @@ int run_pipeline(bdepth* h, RunMode mode, RunOut* ro, Emitter* em = nullptr) {
         // ---- exact chain verification (host, control plane): entry[i] must equal the running exit
         int64_t cur = anchor; int64_t tail = (int64_t)ub;
         for (size_t i = 0; i < nb; i++) {
+            if (sparse && i && h->seg_entry[b + i] >= 0) cur = cstart[i] + h->seg_entry[b + i];     // a new chunk: the chain restarts at its first record
             int64_t true_e = (cur < cstart[i + 1]) ? cur : ENTRY_NONE;
             if (true_e != ENTRY_NONE && true_e < cstart[i]) return fail(h, BDEPTH_ERR_FORMAT, "internal: record chain went backwards");
             if (ent[i] != true_e) {
@@ -621,7 +725,7 @@ int run_pipeline(bdepth* h, RunMode mode, RunOut* ro, Emitter* em = nullptr) {
                 uint32_t ci = (uint32_t)i;
                 UP((int64_t*)h->entry.p + i, &true_e, 8);
                 UP(h->walk_list.p, &ci, 4);
-                k2_walk<<<1, 32, 0, sm>>>(spw, h->chunk_start.as<int64_t>(), (uint32_t)nb, h->entry.as<int64_t>(), h->slot_base.as<uint32_t>(), h->slots.as<uint16_t>(), h->count.as<uint32_t>(), h->exitb.as<int64_t>(), (int*)h->misc.p, h->walk_list.as<uint32_t>(), 1);
+                k2_walk<<<1, 32, 0, sm>>>(spw, h->chunk_start.as<int64_t>(), (uint32_t)nb, h->entry.as<int64_t>(), h->slot_base.as<uint32_t>(), h->slots.as<uint16_t>(), h->count.as<uint32_t>(), h->exitb.as<int64_t>(), (int*)h->misc.p, h->walk_list.as<uint32_t>(), 1, d_limit);
                 CK(cudaGetLastError()); st.gpu_launches++;
                 DOWN(fx_ext, int64_t, (int64_t*)h->exitb.p + i, 8); DOWN(fx_cnt, uint32_t, (uint32_t*)h->count.p + i, 4); DOWN(fx_err, int, h->misc.p, 4);
                 CK(cudaStreamSynchronize(sm));
@@ -630,6 +734,15 @@ int run_pipeline(bdepth* h, RunMode mode, RunOut* ro, Emitter* em = nullptr) {
             }
             if (true_e != ENTRY_NONE) {
                 cur = ext[i];
+                if (sparse && h->seg_limit[b + i] != UINT32_MAX) {      // last block of a chunk: the chain must end exactly at the chunk end
+                    if (ext[i] != (i ? cstart[i] : 0) + (int64_t)h->seg_limit[b + i]) {
+                        // the index does not describe this file (the reference only checks that one exists): plain pass instead
+                        h->sparse_ok = false; CK(cudaDeviceSynchronize());
+                        return run_pipeline(h, mode, ro, em);
+                    }
+                    cur = INT64_MAX / 2;                                  // nothing follows until the next chunk begins
+                    continue;
+                }
                 if (ext[i] < cstart[i + 1]) {      // the walk stopped inside its own block: incomplete tail record
                     for (size_t j = i + 1; j < nb; j++) cnt[j] = 0;
                     break;
@@ -818,6 +931,7 @@ int bdepth_open_memory(const void* bam, size_t bam_len, const void* bai, size_t 
 void bdepth_close(bdepth_t* h) {
     if (!h) return;
     cudaSetDevice(h->device);
+    h->anchors_idx.release(); h->anchors_val.release(); h->chunk_limit.release();
     DevBuf* bufs[] = {&h->comp, &h->descs, &h->status, &h->ubuf, &h->chunk_start, &h->entry, &h->exitb, &h->count, &h->slot_base, &h->slots, &h->rec_base, &h->walk_list, &h->soa_start, &h->soa_span, &h->soa_meta, &h->soa_off, &h->soa_ncl, &h->soa_lseq, &h->long_list, &h->tile_first, &h->tile_lo, &h->counts, &h->ref_len_d, &h->ref_lin0_d, &h->scan_stats, &h->ref_has, &h->misc};
     for (DevBuf* b : bufs) b->release();
     h->rg_ids.release(); h->rg_offs.release(); h->rg_samp.release();
@@ -888,6 +1002,20 @@ int bdepth_plan_shards(const char* bam_path, int world, uint64_t* out) {
     std::vector<uint64_t> vos = shard_candidates(bai);
     for (int k = 1; k < world; k++) out[k - 1] = shard_cut_voffset(vos, (uint64_t)sb.st_size, k, world);
     return 0;
+}
+// Host-only: the merged BAI chunk list a region query reads (what bdepth_run_* stage when regions are set).
+long bdepth_plan_region_chunks(const char* bam_path, const bdepth_region* regions, size_t n, uint64_t* out_pairs, size_t cap) {
+    if (!bam_path || (n && !regions)) return fail(nullptr, BDEPTH_ERR_ARG, "bad argument");
+    BaiIndex bai;
+    { std::string p1 = std::string(bam_path) + ".bai"; FILE* f = fopen(p1.c_str(), "rb"); if (!f) return fail(nullptr, BDEPTH_ERR_NOINDEX, "no index %s", p1.c_str());
+      fseek(f, 0, SEEK_END); long nb = ftell(f); fseek(f, 0, SEEK_SET); std::vector<uint8_t> buf(nb); if (fread(buf.data(), 1, nb, f) != (size_t)nb) { fclose(f); return fail(nullptr, BDEPTH_ERR_IO, "read error"); } fclose(f);
+      if (!parse_bai(buf.data(), buf.size(), bai)) return fail(nullptr, BDEPTH_ERR_FORMAT, "bad BAI"); }
+    std::vector<HostRegion> rg;
+    for (size_t i = 0; i < n; i++) if (regions[i].start < regions[i].end) rg.push_back(HostRegion{regions[i].ref_id, regions[i].start, regions[i].end});
+    std::sort(rg.begin(), rg.end(), [](const HostRegion& a, const HostRegion& b) { return a.ref != b.ref ? a.ref < b.ref : a.start < b.start; });
+    std::vector<BaiChunk> cs = region_chunks(bai, rg);
+    for (size_t i = 0; i < cs.size() && i < cap; i++) { out_pairs[2 * i] = cs[i].beg; out_pairs[2 * i + 1] = cs[i].end; }
+    return (long)cs.size();
 }
 int bdepth_set_tuning(bdepth_t* h, uint64_t batch_inflated_bytes, uint64_t chunk_blocks) {
     if (batch_inflated_bytes) h->batch_u = std::max<uint64_t>(batch_inflated_bytes, 1 << 20);
@@ -1198,7 +1326,12 @@ int bdepth_run_regions(bdepth_t* h, const bdepth_region* regions, size_t n, cons
         segs[i] = SegDef{regions[i].ref_id, regions[i].start, regions[i].end};
     }
     std::vector<uint32_t> reads, bases, cov;
-    int rc = run_segments(h, segs, thr, n_thr, reads, bases, cov); if (rc) return rc;
+    // only reads overlapping a region matter: let the pipeline stage just the BAI chunks of these regions
+    const bool tmp_regions = h->regions.empty() && n;
+    if (tmp_regions) normalize_regions(h, regions, n, h->regions);
+    int rc = run_segments(h, segs, thr, n_thr, reads, bases, cov);
+    if (tmp_regions) h->regions.clear();
+    if (rc) return rc;
     if (!cb) return 0;
     for (size_t i = 0; i < n; i++) { rc = deliver_one(h, segs[i], i, n, n_thr, reads, bases, cov, false, cb, user, i); if (rc) return rc; }
     return 0;

@@ -10,6 +10,7 @@
 #include <string.h>
 #include <string>
 #include <vector>
+#include <algorithm>
 
 namespace bdk {
 
@@ -131,16 +132,19 @@ static inline int parse_bam_header(const uint8_t* u, size_t n, BamHeader& h, std
 }
 
 // BAI: only the linear index (ioffsets) and the per-reference chunk extents are needed here.
+struct BaiChunk { uint64_t beg, end; };             // BGZF virtual offsets [beg, end)
+struct BaiBin { uint32_t bin; std::vector<BaiChunk> chunks; };
 struct BaiIndex {
     bool valid = false;
     std::vector<std::vector<uint64_t>> ioffsets;   // per reference
     std::vector<uint64_t> min_chunk_beg;           // per reference, smallest chunk_beg (UINT64_MAX if none)
+    std::vector<std::vector<BaiBin>> bins;         // per reference (the metadata pseudo-bin 37450 is dropped)
 };
 static inline bool parse_bai(const uint8_t* b, size_t n, BaiIndex& idx) {
     if (n < 8 || memcmp(b, "BAI\1", 4)) return false;
     size_t off = 4; int32_t n_ref = (int32_t)h_rd32(b + off); off += 4;
     if (n_ref < 0) return false;
-    idx.ioffsets.assign(n_ref, {}); idx.min_chunk_beg.assign(n_ref, UINT64_MAX);
+    idx.ioffsets.assign(n_ref, {}); idx.min_chunk_beg.assign(n_ref, UINT64_MAX); idx.bins.assign(n_ref, {});
     for (int r = 0; r < n_ref; r++) {
         if (off + 4 > n) return false;
         uint32_t n_bin = h_rd32(b + off); off += 4;
@@ -148,7 +152,11 @@ static inline bool parse_bai(const uint8_t* b, size_t n, BaiIndex& idx) {
             if (off + 8 > n) return false;
             uint32_t bin = h_rd32(b + off), n_chunk = h_rd32(b + off + 4); off += 8;
             if (off + 16ull * n_chunk > n) return false;
-            if (bin != 37450) for (uint32_t c = 0; c < n_chunk; c++) { uint64_t beg = h_rd64(b + off + 16ull * c); if (beg < idx.min_chunk_beg[r]) idx.min_chunk_beg[r] = beg; }
+            if (bin != 37450) {
+                BaiBin bb; bb.bin = bin; bb.chunks.resize(n_chunk);
+                for (uint32_t c = 0; c < n_chunk; c++) { uint64_t beg = h_rd64(b + off + 16ull * c); bb.chunks[c] = BaiChunk{beg, h_rd64(b + off + 16ull * c + 8)}; if (beg < idx.min_chunk_beg[r]) idx.min_chunk_beg[r] = beg; }
+                idx.bins[r].push_back(std::move(bb));
+            }
             off += 16ull * n_chunk;
         }
         if (off + 4 > n) return false;
@@ -160,6 +168,43 @@ static inline bool parse_bai(const uint8_t* b, size_t n, BaiIndex& idx) {
     }
     idx.valid = true;
     return true;
+}
+
+
+// The chunk list a region query has to read, as the reference computes it (getGroupChunks,
+// BioD/bio/std/hts/bam/randomaccessmanager.d:247-294): the bins that can overlap a region (5 levels over the 16 kb
+// leaves), their chunks that end after the linear-index offset of the first region, sorted, overlaps merged.
+// `regions` = (ref, start, end) sorted by (ref, start), start < end.  A superset is always safe: reads that do
+// not overlap a region contribute nothing to what is printed for the regions.
+struct HostRegion { uint32_t ref, start, end; };
+static inline std::vector<BaiChunk> region_chunks(const BaiIndex& bai, const std::vector<HostRegion>& regions) {
+    std::vector<BaiChunk> cs;
+    size_t i = 0;
+    std::vector<uint8_t> sel(37450);
+    while (i < regions.size()) {
+        size_t j = i; uint32_t ref = regions[i].ref;
+        while (j < regions.size() && regions[j].ref == ref) j++;
+        if (ref < bai.bins.size() && !bai.bins[ref].empty()) {
+            std::fill(sel.begin(), sel.end(), 0); sel[0] = 1;
+            for (size_t r = i; r < j; r++) {
+                uint32_t beg = regions[r].start, end = regions[r].end - 1; uint32_t k;
+                for (k = 1 + (beg >> 26); k <= 1 + (end >> 26); ++k) sel[k] = 1;
+                for (k = 9 + (beg >> 23); k <= 9 + (end >> 23); ++k) sel[k] = 1;
+                for (k = 73 + (beg >> 20); k <= 73 + (end >> 20); ++k) sel[k] = 1;
+                for (k = 585 + (beg >> 17); k <= 585 + (end >> 17); ++k) sel[k] = 1;
+                for (k = 4681 + (beg >> 14); k <= 4681 + (end >> 14); ++k) if (k < 37450) sel[k] = 1;
+            }
+            // linear index: no read that overlaps the first region starts before this offset (0 = unknown)
+            uint64_t min_off = 0; const auto& lin = bai.ioffsets[ref]; size_t w = regions[i].start >> 14;
+            if (w < lin.size()) min_off = lin[w];
+            for (const BaiBin& b : bai.bins[ref]) if (b.bin < 37450 && sel[b.bin]) for (const BaiChunk& c : b.chunks) if (c.end > min_off && c.beg < c.end) cs.push_back(BaiChunk{std::max(c.beg, min_off), c.end});
+        }
+        i = j;
+    }
+    std::sort(cs.begin(), cs.end(), [](const BaiChunk& a, const BaiChunk& b) { return a.beg != b.beg ? a.beg < b.beg : a.end < b.end; });
+    std::vector<BaiChunk> m;
+    for (const BaiChunk& c : cs) { if (!m.empty() && c.beg <= m.back().end) m.back().end = std::max(m.back().end, c.end); else m.push_back(c); }
+    return m;
 }
 
 }  // namespace bdk

@@ -133,11 +133,13 @@ __global__ void k2_guess_entries(ScanParams sp, const int64_t* __restrict__ chun
 // walk_list (optional) restricts the launch to the listed chunks (fix-up passes).
 __global__ void k2_walk(ScanParams sp, const int64_t* __restrict__ chunk_start, uint32_t n_chunks, const int64_t* __restrict__ entry,
                         const uint32_t* __restrict__ slot_base, uint16_t* __restrict__ slots, uint32_t* __restrict__ count,
-                        int64_t* __restrict__ exit_off, int* __restrict__ err, const uint32_t* __restrict__ walk_list, uint32_t n_list) {
+                        int64_t* __restrict__ exit_off, int* __restrict__ err, const uint32_t* __restrict__ walk_list, uint32_t n_list,
+                        const int64_t* __restrict__ chunk_limit /* optional: the walk of chunk c stops at this offset (end of a region-query chunk) */) {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t c;
     if (walk_list) { if (t >= n_list) return; c = walk_list[t]; } else { if (t >= n_chunks) return; c = t; }
     int64_t o = entry[c], c0 = chunk_start[c], c1 = chunk_start[c + 1];
+    if (chunk_limit && chunk_limit[c] < c1) c1 = chunk_limit[c];
     uint32_t n = 0;
     if (o != ENTRY_NONE) {
         uint16_t* sl = slots + slot_base[c];

@@ -61,6 +61,7 @@ int bdepth_set_regions(bdepth_t* h, const(bdepth_region)* r, size_t n);
 int bdepth_set_shard(bdepth_t* h, int rank, int world, const(void)* nccl_unique_id);
 int bdepth_nccl_unique_id(void* out128);
 int bdepth_plan_shards(const(char)* bam_path, int world, ulong* out_voffsets);
+long bdepth_plan_region_chunks(const(char)* bam_path, const(bdepth_region)* regions, size_t n, ulong* out_pairs, size_t cap);
 int bdepth_set_tuning(bdepth_t* h, ulong batch_inflated_bytes, ulong chunk_blocks);
 
 int bdepth_stage(bdepth_t* h);

@@ -95,3 +95,52 @@ def test_shard_plan_is_a_partition_at_record_starts(tmp_path):
             assert (vo >> 16) in table, "boundary must point at a BGZF block start"
             assert table[vo >> 16] + (vo & 0xFFFF) in starts, "boundary must be a record start"
             assert (vo >> 16) >= k * len(raw) // world - 70000
+
+
+def test_region_chunk_plan_covers_every_overlapping_record(tmp_path):
+    """bdepth_plan_region_chunks is host-only: every record that overlaps a region must start inside one of the planned
+    virtual-offset ranges (a superset is fine -- the reference also only narrows by bins, randomaccessmanager.d:247-294),
+    ranges are sorted, disjoint and begin at record starts; narrow queries must plan far less than the file."""
+    import random
+    import sambamba_b200 as sb
+    p = helpers.gen_bam(str(tmp_path / "s.bam"), "-r", "chrA:2000000", "-r", "chrB:300", "-r", "chrC:700000", "-n", 150000, "-s", 5, "-t", 3)
+    u = helpers.oracle_inflate(p)
+    first, refs = helpers.header_first_record_offset(u)
+    recs = helpers.parse_records(u, first)
+    raw = open(p, "rb").read()
+    off, uoff, blocks = 0, 0, []          # (inflated offset, file offset)
+    while off + 18 <= len(raw):
+        bs = int.from_bytes(raw[off + 16:off + 18], "little") + 1
+        isz = int.from_bytes(raw[off + bs - 4:off + bs], "little")
+        if isz == 0:
+            break
+        blocks.append((uoff, off))
+        uoff += isz
+        off += bs
+    import bisect
+    ustarts = [b[0] for b in blocks]
+
+    def voffset(o):
+        k = bisect.bisect_right(ustarts, o) - 1
+        return (blocks[k][1] << 16) | (o - blocks[k][0])
+    rec_vo = [voffset(r[0]) for r in recs]
+    vo_set = set(rec_vo)
+    rnd = random.Random(1)
+    queries = [[(0, 1000, 1200)], [(2, 0, 700000)], [(0, 1999000, 2000000), (2, 10, 20)], [(1, 0, 300)],
+               [(0, rnd.randrange(0, 1990000), 0) for _ in range(40)]]
+    queries[-1] = sorted((r, s, s + rnd.randrange(1, 3000)) for r, s, _ in queries[-1])
+    total_span = max(rec_vo) - min(rec_vo)
+    for q in queries:
+        chunks = sb.plan_region_chunks(p, q)
+        assert chunks == sorted(chunks) and all(b < e for b, e in chunks)
+        assert all(chunks[i][1] < chunks[i + 1][0] for i in range(len(chunks) - 1)), "ranges must be disjoint"
+        assert all(b in vo_set for b, _ in chunks), "a range must begin at a record start"
+        begs = [b for b, _ in chunks]
+        for r, vo in zip(recs, rec_vo):
+            _, ref, pos, _flag, _mq, _nc, span = r
+            if ref < 0 or not any(ref == g[0] and pos < g[2] and pos + max(span, 1) > g[1] for g in q):
+                continue
+            k = bisect.bisect_right(begs, vo) - 1
+            assert k >= 0 and chunks[k][0] <= vo < chunks[k][1], (q, r)
+    small = sb.plan_region_chunks(p, [(0, 1000, 1200)])
+    assert sum((e >> 16) - (b >> 16) for b, e in small) < 0.05 * (total_span >> 16)

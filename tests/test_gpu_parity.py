@@ -72,7 +72,8 @@ def test_k3_base_counts_bit_exact(sb, synth, minq):
         assert got.shape == want.shape, p
         bad = np.argwhere(got != want)
         assert bad.size == 0, (p, bad[:5], got[:, bad[0][1]] if bad.size else None, want[:, bad[0][1]] if bad.size else None)
-        assert st["n_records"] == ost.n_records and st["n_records_pass"] == ost.n_pass, p
+        # a window query stages only the BAI chunks of the window: records outside them (unplaced reads) are never read
+        assert st["n_records"] <= ost.n_records and st["n_records_pass"] == ost.n_pass, p
         assert st["covered_positions"] == int((want.sum(axis=0) > 0).sum()), p      # everything covered lies inside the window
 
 
