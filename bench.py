@@ -33,7 +33,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 READS_PER_UNIT = 12888833
 UNIT_LEN = 64444167
-NCU_TRAFFIC_BYTES_PER_LAUNCH = 50358292000  # dram__bytes_read.sum + dram__bytes_write.sum of k1_inflate on this workload (profiles/r1_k1_v6_cpasync_ncu_full_summary.txt)
+NCU_TRAFFIC_BYTES_PER_LAUNCH = 50975621000  # dram__bytes_read.sum + dram__bytes_write.sum of k1_inflate on this workload (profiles/r1_k1_v8_two_literal_ncu_full_summary.txt)
 
 
 def peaks():

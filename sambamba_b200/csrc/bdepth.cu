@@ -533,11 +533,12 @@ int run_pipeline(bdepth* h, RunMode mode, RunOut* ro, Emitter* em = nullptr) {
         uint8_t* m = hs.take(bytes); if (!m) return fail(h, BDEPTH_ERR_CUDA, "internal: host scratch exhausted");
         memcpy(m, src, bytes);
         k_copy_words<<<(unsigned)std::min<size_t>((bytes / 4 + 255) / 256, 512), 256, 0, sm>>>((uint32_t*)dst_dev, (const uint32_t*)hs.dev(m), bytes / 4);
+        st.gpu_launches++;
         return 0;
     };
     auto down = [&](const void* src_dev, size_t bytes) -> uint8_t* {
         uint8_t* m = hs.take(bytes ? bytes : 4); if (!m) return nullptr;
-        if (bytes) k_copy_words<<<(unsigned)std::min<size_t>((bytes / 4 + 255) / 256, 512), 256, 0, sm>>>((uint32_t*)hs.dev(m), (const uint32_t*)src_dev, bytes / 4);
+        if (bytes) { k_copy_words<<<(unsigned)std::min<size_t>((bytes / 4 + 255) / 256, 512), 256, 0, sm>>>((uint32_t*)hs.dev(m), (const uint32_t*)src_dev, bytes / 4); st.gpu_launches++; }
         return m;
     };
 #define UP(dst, src, bytes) do { int rcu_ = up((dst), (src), (bytes)); if (rcu_) return rcu_; } while (0)
