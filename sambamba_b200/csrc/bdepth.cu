@@ -688,7 +688,7 @@ int run_pipeline(bdepth* h, RunMode mode, RunOut* ro, Emitter* em = nullptr) {
         UP(h->entry.p, &anchor, 8);
         CK(cudaMemsetAsync(h->misc.p, 0, 64, sm));
         // records that START at or after the shard limit belong to the next rank
-        int64_t u_limit = (int64_t)ub; if (!sparse && h->limit_abs_u < batch_u0 + ub) u_limit = h->limit_abs_u > batch_u0 ? (int64_t)(h->limit_abs_u - batch_u0) : 0;
+        int64_t u_limit = (int64_t)ub; if (!sparse && h->limit_abs_u < batch_u0 + ub) u_limit = (int64_t)h->limit_abs_u - (int64_t)batch_u0;      // may be negative: the limit lies before this sub-batch, and a carried record that starts at or after it is not ours either
         ScanParams sp{u0, -(int64_t)carry_len, (int64_t)ub, (int)nref, h->ref_len_d.as<uint32_t>(), h->ref_lin0_d.as<uint64_t>()};
         k2_guess_entries<<<(unsigned)((nb * 32 + 255) / 256), 256, 0, sm>>>(sp, h->chunk_start.as<int64_t>(), (uint32_t)nb, h->entry.as<int64_t>());
         CK(cudaGetLastError()); st.gpu_launches++;
@@ -1353,7 +1353,7 @@ int64_t bdepth_inflate_to_host(bdepth_t* h, void* dst, uint64_t cap) {
     size_t save_lo = h->blk_lo; if (h->world == 1) h->blk_lo = 0;
     bool save_staged = h->staged; h->staged = false;
     rc = run_pipeline(h, RUN_INFLATE_ONLY, &ro);
-    h->blk_lo = save_lo; (void)save_staged;
+    h->blk_lo = save_lo; h->staged = save_staged;
     if (rc) return rc;
     return (int64_t)ro.inflate_len;
 }

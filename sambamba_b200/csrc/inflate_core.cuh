@@ -74,7 +74,7 @@ constexpr int RING_WORDS = 8;
 constexpr int T_FAR = T_RING + RING_WORDS;     // 2 words: landing zone of the asynchronous far-match fetch
 constexpr int T_WORDS = T_FAR + 2;             // 130 lane-interleaved words
 constexpr int FIFO_BYTES_PER_LANE = 32;        // two 16-byte slots of compressed input per lane (lane-major, after the interleaved words)
-constexpr int SMEM_BYTES_PER_WARP = T_WORDS * 128 + 32 * FIFO_BYTES_PER_LANE;   // 17,664 B -> 12 warps per SM
+constexpr int SMEM_BYTES_PER_WARP = T_WORDS * 128 + 32 * FIFO_BYTES_PER_LANE;   // 17,664 B -> one 13-warp CTA per SM (kernels.cuh)
 constexpr uint32_t NEAR_MAX = 4 * (RING_WORDS - 1) - 4;   // 24: farthest distance served from the ring
 
 // ---- table storage policies -------------------------------------------------------------

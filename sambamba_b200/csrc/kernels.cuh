@@ -294,14 +294,12 @@ __global__ void k3_tile_index(RecordSoA soa, uint32_t R, uint64_t win_base, uint
     if (r >= R) return;
     uint64_t s = soa.start[r];
     // boundaries: tiles whose start lies in (prev_start, s] get first = r
-    int64_t t_cur = s >= win_base ? (int64_t)((s - win_base + TILE_POS - 1) / TILE_POS) : 0;        // first tile with tile_start >= s ... see below
     // tile_first[t] = min{ r : start[r] >= tile_start(t) }.  Record r is that minimum for all t with
     // start[r-1] < tile_start(t) <= start[r].
     int64_t t_hi = s >= win_base ? (int64_t)((s - win_base) / TILE_POS) : -1;                        // last tile with tile_start <= s
     int64_t t_lo;
     if (r == 0) t_lo = 0;
     else { uint64_t ps = soa.start[r - 1]; t_lo = ps >= win_base ? (int64_t)((ps - win_base) / TILE_POS) + 1 : 0; }
-    (void)t_cur;
     if (t_hi > (int64_t)n_tiles) t_hi = n_tiles;
     for (int64_t t = t_lo; t <= t_hi; t++) tile_first[t] = r;
     uint32_t m = soa.meta[r];
