@@ -1122,6 +1122,80 @@ int oracle_base_counts(const char *bam_path, int mapq_gt, unsigned flag_reject, 
     return 0;
 }
 
+/* --------------------------------------------- closed form for -m (fix-mate-overlaps), base mode
+ * The sweep (base_write_column above, depth.d:495-556 with detectOverlappingMates :319-388 and selectBetterMate
+ * :391-399) counts, in every column, each PAIR of same-name reads once: only the better mate contributes (either on
+ * a D/N there -> the one with the higher MAPQ, second on ties; else the one with the higher base quality, second on
+ * ties).  Pairs are adjacent entries of the column's reads sorted by (name hash, arrival order), so of three
+ * same-name reads present in a column the first two pair up and the third counts alone.  Reads that are not in a
+ * pair in a column count as usual (state none/past).  Restated per name group instead of per column of the whole
+ * file: start from the plain closed form, then, for every group of same-name reads, walk the columns where at
+ * least two of them are present and take the loser's contribution out again.
+ * Cross-checked against the sweep in tests/test_oracle_golden.py.  Test infrastructure only. */
+typedef struct { uint64_t h; uint32_t idx; } MateKey;
+static int mate_key_cmp(const void *a, const void *b) { const MateKey *x = a, *y = b; if (x->h != y->h) return x->h < y->h ? -1 : 1; return x->idx < y->idx ? -1 : (x->idx > y->idx); }
+
+int oracle_base_counts_fix_mates(const char *bam_path, int mapq_gt, unsigned flag_reject, int min_bq,
+                                 uint32_t *counts /* [7][win_len] */, uint64_t win_a, uint64_t win_len, uint64_t *n_pair_columns) {
+    if (oracle_base_counts(bam_path, mapq_gt, flag_reject, min_bq, 1, 0, counts, win_a, win_len, NULL)) return -1;
+    Bam B; memset(&B, 0, sizeof B);
+    if (bgzf_load(&B.z, bam_path, 1, 0)) return -1;
+    if (bam_parse_header(&B, 0)) return -1;
+    uint64_t *ref_off = calloc(B.n_ref + 1, sizeof *ref_off); { uint64_t t = 0; for (int i = 0; i < B.n_ref; i++) { ref_off[i] = t; t += B.refs[i].length; } }
+    PRead *rd = NULL; size_t n = 0, cap = 0;
+    size_t off = B.first_rec; const uint8_t *u = B.z.u;
+    while (off + 4 <= B.z.ulen) {
+        uint32_t bs = rd32(u + off); if (off + 4 + (size_t)bs > B.z.ulen) break;
+        PRead r; if (parse_record(&B, u + off + 4, bs, &r)) { free(rd); free(ref_off); return -1; }
+        off += 4 + (size_t)bs;
+        if (!((int)r.mapq > mapq_gt) || (r.flag & flag_reject) || (r.flag & 0x4) || r.ref_id < 0 || r.ref_id >= B.n_ref || bases_covered(&r) <= 0) continue;
+        if (n == cap) { cap = cap ? cap * 2 : 1024; rd = realloc(rd, cap * sizeof *rd); }
+        rd[n++] = r;
+    }
+    MateKey *key = malloc((n ? n : 1) * sizeof *key);
+    for (size_t i = 0; i < n; i++) { key[i].h = rd[i].name_hash; key[i].idx = (uint32_t)i; }
+    qsort(key, n, sizeof *key, mate_key_cmp);
+    uint64_t pair_cols = 0; const uint64_t L = win_len;
+    for (size_t g0 = 0; g0 < n;) {
+        size_t g1 = g0 + 1; while (g1 < n && key[g1].h == key[g0].h) g1++;
+        size_t gn = g1 - g0;
+        if (gn >= 2) {
+            /* members in arrival (file) order; cursors start when the column reaches a member's start */
+            PRead **m = malloc(gn * sizeof *m); uint8_t *started = calloc(gn, 1);
+            int64_t lo = INT64_MAX, hi = 0;
+            for (size_t k = 0; k < gn; k++) { m[k] = &rd[key[g0 + k].idx]; int64_t a = (int64_t)(ref_off[m[k]->ref_id] + (uint32_t)m[k]->pos), b = (int64_t)(ref_off[m[k]->ref_id] + m[k]->end_pos); if (a < lo) lo = a; if (b > hi) hi = b; }
+            for (int64_t g = lo; g < hi; g++) {
+                PRead *pres[64]; size_t np = 0;
+                for (size_t k = 0; k < gn; k++) {
+                    int64_t a = (int64_t)(ref_off[m[k]->ref_id] + (uint32_t)m[k]->pos), b = (int64_t)(ref_off[m[k]->ref_id] + m[k]->end_pos);
+                    if (g < a || g >= b) continue;
+                    if (!started[k]) { pread_init_cursor(m[k]); started[k] = 1; } else pread_increment(m[k]);
+                    if (np < 64) pres[np++] = m[k];
+                }
+                for (size_t i = 0; i + 1 < np;) {
+                    PRead *r1 = pres[i], *r2 = pres[i + 1];
+                    if (!(r1->ref_id == r2->ref_id && r1->sample_id == r2->sample_id && r1->l_read_name == r2->l_read_name && !memcmp(r1->name, r2->name, r1->l_read_name))) { i++; continue; }
+                    PRead *win = select_better_mate(r1, r2), *lose = win == r1 ? r2 : r1;
+                    pair_cols++;
+                    if (g >= (int64_t)win_a && (uint64_t)(g - (int64_t)win_a) < L) {
+                        uint64_t x = (uint64_t)(g - (int64_t)win_a);
+                        char c = pread_base(lose);
+                        /* what base_process_current would have added for the loser (depth.d:568-585) */
+                        if (c == '-') counts[(uint64_t)(((lose->cur_op & 0xF) == 2) ? 5 : 6) * L + x]--;
+                        else if (pread_qual(lose) >= min_bq) counts[(uint64_t)base5_of_char(c) * L + x]--;
+                    }
+                    i += 2;
+                }
+            }
+            free(m); free(started);
+        }
+        g0 = g1;
+    }
+    if (n_pair_columns) *n_pair_columns = pair_cols;
+    free(key); free(rd); free(ref_off); bgzf_free(&B.z);
+    return 0;
+}
+
 /* header info for Python tests */
 int oracle_bam_info(const char *bam_path, int *n_ref, uint64_t *total_len, uint64_t *ulen, uint64_t *n_blocks) {
     Bam B; memset(&B, 0, sizeof B);

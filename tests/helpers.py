@@ -27,6 +27,7 @@ def oracle():
         L.oracle_inflate_file.restype = C.c_int64
         L.oracle_inflate_file.argtypes = [C.c_char_p, C.c_void_p, C.c_uint64]
         L.oracle_base_counts.argtypes = [C.c_char_p, C.c_int, C.c_uint, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_uint64, C.c_uint64, C.POINTER(ScatterStats)]
+        L.oracle_base_counts_fix_mates.argtypes = [C.c_char_p, C.c_int, C.c_uint, C.c_int, C.c_void_p, C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64)]
         L.oracle_bam_info.argtypes = [C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         L.oracle_last_error.restype = C.c_char_p
         _orc = L
@@ -68,6 +69,18 @@ def oracle_counts(path, mapq_gt=0, flag_reject=0x600, min_bq=0, threads=1, windo
     rc = L.oracle_base_counts(path.encode(), mapq_gt, flag_reject, min_bq, threads, 0, out.ctypes.data_as(C.c_void_p), a, max(1, b - a), C.byref(st))
     assert rc == 0, L.oracle_last_error()
     return out[:, :b - a], st
+
+
+def oracle_counts_fix_mates(path, mapq_gt=0, flag_reject=0x600, min_bq=0, window=None):
+    """Closed form for `-m` (base mode): counts[7, n] over the linear window and the number of (pair, column) fixes."""
+    L = oracle()
+    n_ref, total, ulen, nblk = oracle_info(path)
+    a, b = (0, total) if window is None else window
+    counts = np.zeros((7, max(0, b - a)), np.uint32)
+    npc = C.c_uint64()
+    rc = L.oracle_base_counts_fix_mates(path.encode(), mapq_gt, flag_reject, min_bq, counts.ctypes.data_as(C.c_void_p), a, b - a, C.byref(npc))
+    assert rc == 0, L.oracle_last_error()
+    return counts, npc.value
 
 
 def interesting_window(path, pad=2000, **kw):

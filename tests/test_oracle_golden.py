@@ -62,6 +62,55 @@ def test_closed_form_equals_sweep_on_all_fixtures(tmp_path):
                 assert seen == int((counts.sum(axis=0) > 0).sum()), p
 
 
+def test_closed_form_for_fix_mate_overlaps_equals_sweep(tmp_path):
+    """`-m` in base mode as a per-name-group closed form (groundwork for the GPU kernel) against the faithful sweep."""
+    import random
+    r = random.Random(8)
+    files = [G("issue_204.bam"), G("mate_overlaps_1_3M_4M.bam")]
+    # hand-made pairs: overlapping mates with deletions / skips / different MAPQ, three reads of one name, same name on
+    # two references, a filtered mate
+    L = 4000
+    reads = []
+    def seq(n):
+        return "".join(r.choice("ACGT") for _ in range(n))
+    for i in range(120):
+        s1 = r.randrange(0, L - 400); s2 = s1 + r.randrange(0, 140)
+        c1 = r.choice([[(100, 0)], [(40, 0), (5, 2), (55, 0)], [(30, 0), (20, 3), (60, 0)], [(10, 4), (90, 0)], [(50, 0), (4, 1), (46, 0)]])
+        c2 = r.choice([[(100, 0)], [(20, 0), (8, 2), (72, 0)], [(60, 0), (30, 3), (30, 0)], [(95, 0), (5, 4)]])
+        q1 = sum(l for l, op in c1 if op in (0, 1, 4)); q2 = sum(l for l, op in c2 if op in (0, 1, 4))
+        reads.append((0, s1, r.choice([60, 60, 20, 7]), 0x63, c1, seq(q1), f"p{i}"))
+        reads.append((0, s2, r.choice([60, 60, 20, 7, 0]), 0x93, c2, seq(q2), f"p{i}"))
+        if i % 17 == 0:
+            reads.append((0, s1 + 20, 50, 0x800, [(80, 0)], seq(80), f"p{i}"))          # a third read of the same name
+        if i % 23 == 0:
+            reads.append((1, 100 + i, 60, 0, [(50, 0)], seq(50), f"p{i}"))              # same name on another reference
+    reads.sort(key=lambda x: (x[0], x[1]))
+    quals = [[r.randint(2, 41) for _ in x[5]] for x in reads]
+    files.append(helpers.write_bam(str(tmp_path / "pairs.bam"), [("c1", L), ("c2", 600)], reads, quals=quals))
+    total_fixes = 0
+    for p in files:
+        for minq in (0, 20):
+            win = helpers.interesting_window(p)
+            counts, fixes = helpers.oracle_counts_fix_mates(p, min_bq=minq, window=win)
+            plain, _ = helpers.oracle_counts(p, min_bq=minq, window=win)
+            total_fixes += fixes
+            assert fixes > 0 and (counts != plain).any(), p
+            rc, out, _ = helpers.oracle_cli(["base", "-m", "-c", "0", "-q", str(minq), p])
+            assert rc == 0
+            with helpers_refs(p) as lin0:
+                for line in out.splitlines()[1:]:
+                    f = line.split(b"\t")
+                    g = lin0[f[0].decode()] + int(f[1]) - win[0]
+                    if g < 0 or g >= counts.shape[1]:
+                        assert int(f[2]) == 0
+                        continue
+                    a, c, gg, t, d, s = (int(x) for x in f[3:9])
+                    col = counts[:, g]
+                    assert (col[0], col[1], col[2], col[3], col[5], col[6]) == (a, c, gg, t, d, s), (p, minq, line, col)
+                    assert int(col.sum()) == int(f[2]), (p, minq, line)
+    assert total_fixes > 1000
+
+
 class helpers_refs:
     def __init__(self, path):
         u = helpers.oracle_inflate(path)
