@@ -1172,19 +1172,55 @@ int oracle_base_counts_fix_mates(const char *bam_path, int mapq_gt, unsigned fla
                     if (!started[k]) { pread_init_cursor(m[k]); started[k] = 1; } else pread_increment(m[k]);
                     if (np < 64) pres[np++] = m[k];
                 }
-                for (size_t i = 0; i + 1 < np;) {
-                    PRead *r1 = pres[i], *r2 = pres[i + 1];
-                    if (!(r1->ref_id == r2->ref_id && r1->sample_id == r2->sample_id && r1->l_read_name == r2->l_read_name && !memcmp(r1->name, r2->name, r1->l_read_name))) { i++; continue; }
-                    PRead *win = select_better_mate(r1, r2), *lose = win == r1 ? r2 : r1;
-                    pair_cols++;
-                    if (g >= (int64_t)win_a && (uint64_t)(g - (int64_t)win_a) < L) {
-                        uint64_t x = (uint64_t)(g - (int64_t)win_a);
-                        char c = pread_base(lose);
-                        /* what base_process_current would have added for the loser (depth.d:568-585) */
-                        if (c == '-') counts[(uint64_t)(((lose->cur_op & 0xF) == 2) ? 5 : 6) * L + x]--;
-                        else if (pread_qual(lose) >= min_bq) counts[(uint64_t)base5_of_char(c) * L + x]--;
+                /* detectOverlappingMates restricted to this name: adjacent pairs in arrival order; the read left over
+                 * (or alone) goes to `past` if it had been flagged -- unless it is the very last entry of the column's
+                 * hash-sorted array AND its predecessor has the same hash (depth.d:380-384), in which case it keeps its
+                 * state.  A read in state `detected` is skipped by the plain loop, every pair adds its better mate. */
+                PRead *pa[32], *pb[32]; size_t npairs = 0;
+                for (size_t i = 0; i < np;) {
+                    if (i + 1 < np) {
+                        PRead *r1 = pres[i], *r2 = pres[i + 1];
+                        if (r1->sample_id == r2->sample_id && r1->l_read_name == r2->l_read_name && !memcmp(r1->name, r2->name, r1->l_read_name)) {
+                            if (npairs < 32) { pa[npairs] = r1; pb[npairs] = r2; npairs++; }
+                            if (r1->mate_overlap == MO_NONE) r1->mate_overlap = MO_DETECTED;
+                            if (r2->mate_overlap == MO_NONE) r2->mate_overlap = MO_DETECTED;
+                            i += 2; continue;
+                        }
+                        i += 1; continue;          /* same hash, different name: the reference moves on without touching the state */
                     }
-                    i += 2;
+                    /* the last present read of this name, not consumed by a pair */
+                    PRead *r = pres[i];
+                    if (r->mate_overlap != MO_NONE) {
+                        int keep = 0;
+                        if (np >= 2) {               /* its predecessor in the sorted array has the same hash: `past` only if something follows it */
+                            int follows = 0;
+                            for (size_t q = 0; q < n && !follows; q++) {
+                                const PRead *o = &rd[q];
+                                if (o->name_hash <= r->name_hash || o->ref_id != r->ref_id) continue;
+                                int64_t a = (int64_t)(ref_off[o->ref_id] + (uint32_t)o->pos), b = (int64_t)(ref_off[o->ref_id] + o->end_pos);
+                                if (g >= a && g < b) follows = 1;
+                            }
+                            keep = !follows;
+                        }
+                        if (!keep) r->mate_overlap = MO_PAST;
+                    }
+                    i += 1;
+                }
+                if (npairs) pair_cols += npairs;
+                if (g >= (int64_t)win_a && (uint64_t)(g - (int64_t)win_a) < L) {
+                    uint64_t x = (uint64_t)(g - (int64_t)win_a);
+                    /* the plain closed form counted every present read once; take out what the sweep does not count
+                     * (reads in state `detected`) and add what it counts on top (the better mate of every pair) */
+                    for (size_t k = 0; k < np; k++) if (pres[k]->mate_overlap == MO_DETECTED) {
+                        char c = pread_base(pres[k]);
+                        if (c == '-') counts[(uint64_t)(((pres[k]->cur_op & 0xF) == 2) ? 5 : 6) * L + x]--;
+                        else if (pread_qual(pres[k]) >= min_bq) counts[(uint64_t)base5_of_char(c) * L + x]--;
+                    }
+                    for (size_t k = 0; k < npairs; k++) {
+                        PRead *w = select_better_mate(pa[k], pb[k]); char c = pread_base(w);
+                        if (c == '-') counts[(uint64_t)(((w->cur_op & 0xF) == 2) ? 5 : 6) * L + x]++;
+                        else if (pread_qual(w) >= min_bq) counts[(uint64_t)base5_of_char(c) * L + x]++;
+                    }
                 }
             }
             free(m); free(started);
