@@ -107,6 +107,10 @@ typedef struct {
     float ms_exchange;            /* multi-GPU boundary exchange (NCCL)                             */
     uint64_t own_lo, own_hi;      /* linear-coordinate range this rank owns after the exchange      */
     uint64_t halo_bytes_sent;     /* boundary counters sent to the next ranks                       */
+    uint64_t mate_pairs;          /* -m: overlapping pairs of one name fixed                        */
+    uint64_t mate_pair_columns;   /* -m: (pair, column) decisions of selectBetterMate               */
+    uint64_t mate_groups;         /* -m: names with three or more overlapping reads                 */
+    float ms_mates;               /* -m: km_hash + km_link + km_fix (contained in ms_coverage)      */
 } bdepth_stats;
 
 /* ------------------------------------------------------------------ lifecycle */
@@ -134,6 +138,14 @@ const char* bdepth_sample_name(const bdepth_t* h, int i);
  * default (depth.d:1159): mapq_gt = 0, mask = 0x400 | 0x200.  -F "" : mapq_gt = -1, mask = 0. */
 int bdepth_set_filter(bdepth_t* h, int mapq_gt, uint32_t flag_reject_mask);
 int bdepth_set_min_baseq(bdepth_t* h, uint32_t min_base_quality);
+/* -m / --fix-mate-overlaps (depth.d:1133; detectOverlappingMates :319-388, selectBetterMate :391-399, the -m branches
+ * of writeColumn :521-530 and PerRegionPrinter.push :760-845): where two reads of one name (same sample) overlap,
+ * every column counts only the better mate.  Available for bdepth_run_base / _run_base_text / _run_regions /
+ * _run_resident on one rank; the whole (shard of the) file is then processed as one batch.  bdepth_run_windows
+ * returns BDEPTH_ERR_ARG with it.  Names with three or more overlapping reads follow the reference's
+ * detected/past state machine in base mode and are refused (BDEPTH_ERR_ARG) in region mode and where the reference's
+ * outcome depends on unrelated reads of the column (depth.d:380-384). */
+int bdepth_set_fix_mates(bdepth_t* h, int on);
 /* --combined (depth.d:1131): one counter set for all samples.  Default: one per @RG sample (<= 64). */
 int bdepth_set_combined(bdepth_t* h, int combined);
 /* Restrict runs to reads overlapping these regions (any order; merged internally).  n = 0 clears. */

@@ -23,6 +23,7 @@
 #include "../../include/bdepth.h"
 #include "host_bam.hpp"
 #include "kernels.cuh"
+#include "mates.cuh"
 
 using namespace bdk;
 
@@ -130,6 +131,8 @@ struct bdepth {
     uint64_t own_lo = 0, own_hi = 0;      // linear range owned by this rank (whole genome when world == 1)
     bool bai_window_ok = true;            // cleared when the linear index turns out not to describe the file
     bool combined = false;                // --combined: one counter set for all samples
+    bool fix_mates = false;               // -m: overlapping mates count once per column (mates.cuh)
+    DevBuf m_hash, m_flag, m_flt, m_ctl;
     uint32_t S = 1;                       // counter sets in the current run (samples, or 1)
     DevBuf rg_ids, rg_offs, rg_samp;
     DevBuf text[2], text_tiles, text_offs, text_zero;
@@ -161,7 +164,7 @@ struct bdepth {
     HostScratch hs;
     std::vector<uint32_t> ref_has_host;
     // ---- optional per-read segment counting (window / region front ends), device arrays
-    struct SegSet { bool on = false; uint32_t n = 0; bool has_min = false; DevBuf s, e, pmax, id, reads, minstart, bases_reads; } seg;
+    struct SegSet { bool on = false; uint32_t n = 0; bool has_min = false; DevBuf s, e, pmax, id, reads, minstart, bases_reads, mbases; } seg;
     // ---- results
     bdepth_stats st{}; std::string err;
 };
@@ -482,6 +485,11 @@ int run_pipeline(bdepth* h, RunMode mode, RunOut* ro, Emitter* em = nullptr) {
     bdepth_stats& st = h->st; uint32_t launches0 = 0;
     st = bdepth_stats{}; st.gpu_launches = launches0;
     const bool sparse = mode == RUN_FULL && plan_sparse(h);
+    // -m pairs reads of one name wherever they sit in the shard: the whole shard is one batch (and one sub-batch), so
+    // that every record of the SoA and the bytes behind it are resident when the mate kernels run
+    const bool fix = mode == RUN_FULL && h->fix_mates;
+    if (fix && h->world > 1) return fail(h, BDEPTH_ERR_ARG, "fix-mate-overlaps is not available with several ranks yet");
+    const uint64_t eff_batch_u = fix ? (UINT64_MAX >> 2) : h->batch_u;
     const std::vector<HostBlock>& B = sparse ? h->vblocks : h->blocks;
     const size_t blk_lo = sparse ? 0 : h->blk_lo, blk_hi = sparse ? B.size() : h->blk_hi;
     const size_t nref = h->hdr.ref_len.size();
@@ -515,7 +523,7 @@ int run_pipeline(bdepth* h, RunMode mode, RunOut* ro, Emitter* em = nullptr) {
     }
     CK(h->scan_stats.ensure(sizeof(ScanStats)));
     RgTable rgt{nullptr, nullptr, nullptr, 0};
-    if (mode == RUN_FULL && h->S > 1) {      // @RG ID -> sample table for the per-read RG lookup (depth.d:240-250)
+    if (mode == RUN_FULL && (h->S > 1 || (fix && h->hdr.sample_names.size() > 1))) {      // @RG ID -> sample table for the per-read RG lookup (depth.d:240-250); mates pair within a sample
         std::vector<uint8_t> ids; std::vector<uint32_t> offs; std::vector<uint8_t> samp;
         for (size_t g = 0; g < h->hdr.rg_ids.size(); g++) { offs.push_back((uint32_t)ids.size()); ids.insert(ids.end(), h->hdr.rg_ids[g].begin(), h->hdr.rg_ids[g].end()); ids.push_back(0); samp.push_back((uint8_t)h->hdr.rg_sample[g]); }
         CK(h->rg_ids.ensure(ids.size() + 8)); CK(h->rg_offs.ensure(offs.size() * 4 + 8)); CK(h->rg_samp.ensure(samp.size() + 8));
@@ -523,7 +531,7 @@ int run_pipeline(bdepth* h, RunMode mode, RunOut* ro, Emitter* em = nullptr) {
         CK(cudaStreamSynchronize(sm));
         rgt = RgTable{h->rg_ids.as<uint8_t>(), h->rg_offs.as<uint32_t>(), h->rg_samp.as<uint8_t>(), (uint32_t)offs.size()};
     }
-    { uint64_t shard_u = blk_hi > blk_lo ? B[blk_hi - 1].uoff + B[blk_hi - 1].isize - B[blk_lo].uoff : 0; CK(h->ubuf.ensure(CARRY_MAX + std::min<uint64_t>(h->batch_u + 65536, shard_u) + 256)); }
+    { uint64_t shard_u = blk_hi > blk_lo ? B[blk_hi - 1].uoff + B[blk_hi - 1].isize - B[blk_lo].uoff : 0; CK(h->ubuf.ensure(CARRY_MAX + std::min<uint64_t>(eff_batch_u + 65536, shard_u) + 256)); }
     CK(h->misc.ensure(64));
     HostScratch& hs = h->hs;
     // up(): host words -> device buffer; down(): device words -> mapped host memory, readable after the next
@@ -553,13 +561,13 @@ int run_pipeline(bdepth* h, RunMode mode, RunOut* ro, Emitter* em = nullptr) {
     if (!h->staged) {   // size both compressed-data buffers for the largest batch up front (ensure() must not reallocate mid-flight)
         uint64_t mx = 0;
         for (size_t bb = blk_lo; bb < blk_hi;) {
-            size_t e = bb; uint64_t u = 0, cb = 0; while (e < blk_hi && (e == bb || u + B[e].isize <= h->batch_u)) { u += B[e].isize; cb += B[e].bsize; e++; }
+            size_t e = bb; uint64_t u = 0, cb = 0; while (e < blk_hi && (e == bb || u + B[e].isize <= eff_batch_u)) { u += B[e].isize; cb += B[e].bsize; e++; }
             mx = std::max<uint64_t>(mx, sparse ? cb + 8 : B[e - 1].coff + B[e - 1].bsize - (B[bb].coff & ~3ull)); bb = e;
         }
         CK(h->comp2[0].ensure(mx + 256)); CK(h->comp2[1].ensure(mx + 256));
     }
     size_t batch_no = 0;
-    auto batch_end = [&](size_t bb) { size_t e = bb; uint64_t u = 0; while (e < blk_hi && (e == bb || u + B[e].isize <= h->batch_u)) { u += B[e].isize; e++; } return e; };
+    auto batch_end = [&](size_t bb) { size_t e = bb; uint64_t u = 0; while (e < blk_hi && (e == bb || u + B[e].isize <= eff_batch_u)) { u += B[e].isize; e++; } return e; };
     // H2D of blocks [bb, be) into comp2[slot]; waits until K1 of the batch that used the slot two batches ago is done
     const size_t H2D_CHUNK_BLOCKS = h->chunk_blocks;
     // dco[slot][i] = where block bb+i of the batch sits in comp2[slot].  Plain runs keep the file layout (one copy
@@ -600,7 +608,7 @@ int run_pipeline(bdepth* h, RunMode mode, RunOut* ro, Emitter* em = nullptr) {
     while (b < blk_hi) {
         // ---- batch extent
         size_t b1 = b; uint64_t ub = 0;
-        while (b1 < blk_hi && (b1 == b || ub + B[b1].isize <= h->batch_u)) { ub += B[b1].isize; b1++; }
+        while (b1 < blk_hi && (b1 == b || ub + B[b1].isize <= eff_batch_u)) { ub += B[b1].isize; b1++; }
         const size_t nb = b1 - b; const bool last_batch = b1 == blk_hi;
         const uint64_t batch_u0 = B[b].uoff;               // absolute inflated offset of the batch start
         st.n_batches++; st.n_blocks += nb; st.inflated_bytes += ub;
@@ -648,7 +656,7 @@ int run_pipeline(bdepth* h, RunMode mode, RunOut* ro, Emitter* em = nullptr) {
                 // Sub-batches: a lane needs ~60 ms for its block however empty the GPU is, so the scan / coverage /
                 // delivery of the blocks that arrived first runs while the later chunks are still being inflated.
                 // (one rank only: with several ranks the batch is scanned as a whole, the flow that was validated on 2 GPUs)
-                if (mode == RUN_FULL && h->world == 1) subs.push_back(Sub{c0, c1, (int)j, (int)j}); else { if (subs.empty()) subs.push_back(Sub{b, b1, 0, (int)j}); subs[0].ev_hi = (int)j; }
+                if (mode == RUN_FULL && h->world == 1 && !fix) subs.push_back(Sub{c0, c1, (int)j, (int)j}); else { if (subs.empty()) subs.push_back(Sub{b, b1, 0, (int)j}); subs[0].ev_hi = (int)j; }
                 c0 = c1;
             }
         }
@@ -843,6 +851,38 @@ int run_pipeline(bdepth* h, RunMode mode, RunOut* ro, Emitter* em = nullptr) {
                 CK(cudaGetLastError()); st.gpu_launches++;
             }
         }
+        // ---- -m: take the worse mate of every overlapping pair out again (mates.cuh)
+        if (fix && ss.n_pass) {
+            if (!last_batch || !last_sub || subs.size() != 1 || batch_no != 0) return fail(h, BDEPTH_ERR_ARG, "internal: fix-mate-overlaps needs the shard in one batch");
+            cudaEvent_t em0 = h->ev[20], em1 = h->ev[21];
+            CK(cudaEventRecord(em0, sm));
+            CK(h->m_hash.ensure(Rc * 8)); CK(h->m_flag.ensure(Rc * 4)); CK(h->m_ctl.ensure(64));
+            std::vector<uint64_t> fl;                 // -L: merged regions (sorted, disjoint) in linear coordinates, starts then ends
+            for (auto& g : h->regions) fl.push_back(h->hdr.ref_lin0[g.ref_id] + g.start);
+            for (auto& g : h->regions) fl.push_back(h->hdr.ref_lin0[g.ref_id] + g.end);
+            const uint32_t n_flt = (uint32_t)h->regions.size();
+            CK(h->m_flt.ensure(fl.size() * 8 + 16));
+            if (n_flt) CK(cudaMemcpyAsync(h->m_flt.p, fl.data(), fl.size() * 8, cudaMemcpyHostToDevice, sm));
+            CK(cudaMemsetAsync(h->m_ctl.p, 0, 64, sm));
+            const bool segm = h->seg.on && h->seg.n;
+            MateParams mp{soa.start, soa.span, soa.meta, soa.off, soa.ncl, soa.lseq, u0, (uint32_t)R, h->m_hash.as<uint64_t>(), h->m_flag.as<uint32_t>(),
+                          h->m_flt.as<uint64_t>(), h->m_flt.as<uint64_t>() + n_flt, n_flt, h->counts.as<uint32_t>(), h->cnt_base, h->win_len, h->S, h->minq,
+                          segm ? h->seg.s.as<uint64_t>() : nullptr, segm ? h->seg.e.as<uint64_t>() : nullptr, segm ? h->seg.pmax.as<uint64_t>() : nullptr, segm ? h->seg.id.as<uint32_t>() : nullptr,
+                          segm ? h->seg.n : 0u, segm ? h->seg.reads.as<uint32_t>() : nullptr, segm ? h->seg.mbases.as<uint32_t>() : nullptr, h->S, 0,
+                          (int*)h->m_ctl.p, (unsigned long long*)((uint8_t*)h->m_ctl.p + 16)};
+            const unsigned mg = (unsigned)((R + 127) / 128);
+            km_hash<<<mg, 128, 0, sm>>>(mp); km_link<<<mg, 128, 0, sm>>>(mp); km_fix<<<mg, 128, 0, sm>>>(mp);
+            CK(cudaGetLastError()); st.gpu_launches += 3;
+            CK(cudaEventRecord(em1, sm));
+            struct { int err[4]; unsigned long long stat[3]; } ctl;
+            CK(cudaMemcpyAsync(&ctl, h->m_ctl.p, sizeof ctl, cudaMemcpyDeviceToHost, sm));
+            CK(cudaStreamSynchronize(sm));
+            if (ctl.err[0] == MATE_ERR_TOO_MANY) return fail(h, BDEPTH_ERR_ARG, "fix-mate-overlaps: more than %d overlapping reads share one name (record #%d of the batch)", MATE_MAX_MEMBERS, ctl.err[1]);
+            if (ctl.err[0] == MATE_ERR_AMBIGUOUS) return fail(h, BDEPTH_ERR_ARG, "fix-mate-overlaps: four or more overlapping reads of one name around read #%d: the reference's result there depends on unrelated reads of the column (depth.d:380-384) and is not reproduced", ctl.err[1]);
+            if (ctl.err[0] == MATE_ERR_REGION_GROUP) return fail(h, BDEPTH_ERR_ARG, "fix-mate-overlaps in region mode: three or more overlapping reads share one name (around read #%d); only pairs are supported there", ctl.err[1]);
+            st.mate_pairs = ctl.stat[0]; st.mate_pair_columns = ctl.stat[1]; st.mate_groups = ctl.stat[2];
+            { float t = 0; CK(cudaEventElapsedTime(&t, em0, em1)); st.ms_mates = t; }
+        }
         CK(cudaEventRecord(e4, sm));
         if (em && mode == RUN_FULL && h->world == 1 && !last_batch && ss.n_pass) { int rce = em->advance(ss.max_start / TILE_POS * TILE_POS, e4); if (rce) return rce; }
         // ---- carry the incomplete tail record to the front of the next batch
@@ -938,7 +978,8 @@ void bdepth_close(bdepth_t* h) {
     for (DevBuf* b : bufs) b->release();
     h->rg_ids.release(); h->rg_offs.release(); h->rg_samp.release();
     h->text[0].release(); h->text[1].release(); h->text_tiles.release(); h->text_offs.release(); h->text_zero.release();
-    h->seg.s.release(); h->seg.e.release(); h->seg.pmax.release(); h->seg.id.release(); h->seg.reads.release(); h->seg.minstart.release(); h->seg.bases_reads.release();
+    h->seg.s.release(); h->seg.e.release(); h->seg.pmax.release(); h->seg.id.release(); h->seg.reads.release(); h->seg.minstart.release(); h->seg.bases_reads.release(); h->seg.mbases.release();
+    h->m_hash.release(); h->m_flag.release(); h->m_flt.release(); h->m_ctl.release();
     if (h->comm) { nccl().CommDestroy(h->comm); h->comm = nullptr; }
     if (h->pinned) cudaFreeHost(h->pinned);
     h->hs.release();
@@ -962,6 +1003,7 @@ const char* bdepth_sample_name(const bdepth_t* h, int i) { return (i >= 0 && (si
 
 int bdepth_set_filter(bdepth_t* h, int mapq_gt, uint32_t flag_reject_mask) { h->mapq_gt = mapq_gt; h->flag_reject = flag_reject_mask; return 0; }
 int bdepth_set_combined(bdepth_t* h, int combined) { h->combined = combined != 0; return 0; }
+int bdepth_set_fix_mates(bdepth_t* h, int on) { h->fix_mates = on != 0; return 0; }
 int bdepth_set_min_baseq(bdepth_t* h, uint32_t q) { h->minq = q > 255 ? 255 : q; return 0; }
 int bdepth_set_regions(bdepth_t* h, const bdepth_region* r, size_t n) { normalize_regions(h, r, n, h->regions); return 0; }
 int bdepth_set_shard(bdepth_t* h, int rank, int world, const void* nccl_unique_id) {
@@ -1196,12 +1238,12 @@ static int run_segments(bdepth* h, const std::vector<SegDef>& segs, const uint32
     }
     auto& S = h->seg;
     size_t nn = n ? n : 1;
-    CK(S.s.ensure(nn * 8)); CK(S.e.ensure(nn * 8)); CK(S.pmax.ensure(nn * 8)); CK(S.id.ensure(nn * 4)); CK(S.reads.ensure(NS * nn * 4)); CK(S.minstart.ensure(nn * 8)); CK(S.bases_reads.ensure(NS * nn * 4));
+    CK(S.s.ensure(nn * 8)); CK(S.e.ensure(nn * 8)); CK(S.pmax.ensure(nn * 8)); CK(S.id.ensure(nn * 4)); CK(S.reads.ensure(NS * nn * 4)); CK(S.minstart.ensure(nn * 8)); CK(S.bases_reads.ensure(NS * nn * 4)); CK(S.mbases.ensure(NS * nn * 4));
     if (n) {
         CK(cudaMemcpy(S.s.p, ss.data(), n * 8, cudaMemcpyHostToDevice)); CK(cudaMemcpy(S.e.p, se.data(), n * 8, cudaMemcpyHostToDevice));
         CK(cudaMemcpy(S.pmax.p, pm.data(), n * 8, cudaMemcpyHostToDevice)); CK(cudaMemcpy(S.id.p, order.data(), n * 4, cudaMemcpyHostToDevice));
     }
-    CK(cudaMemset(S.reads.p, 0, NS * nn * 4)); CK(cudaMemset(S.bases_reads.p, 0, NS * nn * 4));
+    CK(cudaMemset(S.reads.p, 0, NS * nn * 4)); CK(cudaMemset(S.bases_reads.p, 0, NS * nn * 4)); CK(cudaMemset(S.mbases.p, 0, NS * nn * 4));
     if (n) CK(cudaMemcpy(S.minstart.p, ms.data(), n * 8, cudaMemcpyHostToDevice));
     S.has_min = has_min;
     S.on = true; S.n = (uint32_t)n;
@@ -1216,7 +1258,7 @@ static int run_segments(bdepth* h, const std::vector<SegDef>& segs, const uint32
     auto cleanup = [&]() { da.release(); dac.release(); db.release(); dthr.release(); dbases.release(); dcov.release(); };
     cudaError_t ce;
     if ((ce = da.ensure(nn * 8)) || (ce = dac.ensure(nn * 8)) || (ce = db.ensure(nn * 8)) || (ce = dthr.ensure(64)) || (ce = dbases.ensure(NS * nn * 4)) || (ce = dcov.ensure(NS * nn * 4 * nt1))) { cleanup(); return fail(h, BDEPTH_ERR_CUDA, "out of device memory (%s)", cudaGetErrorString(ce)); }
-    std::vector<uint64_t> acv(n); std::vector<uint32_t> qbases;
+    std::vector<uint64_t> acv(n); std::vector<uint32_t> qbases, mbases;
     for (size_t i = 0; i < n; i++) {
         uint64_t lo = std::max(h->cnt_base, h->own_lo), hi = std::min(h->cnt_base + h->win_len, h->own_hi); if (hi < lo) hi = lo;
         uint64_t sc = segs[i].start - std::min(segs[i].cov_ext, segs[i].start);
@@ -1243,6 +1285,7 @@ static int run_segments(bdepth* h, const std::vector<SegDef>& segs, const uint32
         if (n_thr) cudaMemcpyAsync(cov.data(), dcov.p, NS * n * n_thr * 4, cudaMemcpyDeviceToHost, sm);
         cudaMemcpyAsync(reads.data(), S.reads.p, NS * n * 4, cudaMemcpyDeviceToHost, sm);
         if (has_min) { qbases.resize(NS * n); cudaMemcpyAsync(qbases.data(), S.bases_reads.p, NS * n * 4, cudaMemcpyDeviceToHost, sm); }
+        if (h->fix_mates) { mbases.resize(NS * n); cudaMemcpyAsync(mbases.data(), S.mbases.p, NS * n * 4, cudaMemcpyDeviceToHost, sm); }      // -m: what n_bases has on top of the base planes (mates.cuh)
     }
     cudaEventRecord(e1, sm);
     ce = cudaStreamSynchronize(sm);
@@ -1250,6 +1293,7 @@ static int run_segments(bdepth* h, const std::vector<SegDef>& segs, const uint32
     cleanup();
     if (ce != cudaSuccess) return fail(h, BDEPTH_ERR_CUDA, "CUDA error in segment statistics: %s", cudaGetErrorString(ce));
     if (!qbases.empty()) for (size_t si = 0; si < NS; si++) for (size_t i = 0; i < n; i++) if (segs[i].min_read_start) bases[si * n + i] = qbases[si * n + i];
+    if (!mbases.empty()) for (size_t k = 0; k < NS * n; k++) bases[k] += mbases[k];
     float t = 0; cudaEventElapsedTime(&t, e0, e1); h->st.ms_reduce = t;
     h->st.ms_total_device = h->st.ms_h2d + h->st.ms_inflate + h->st.ms_scan + h->st.ms_coverage + h->st.ms_reduce;
     return 0;
@@ -1271,6 +1315,7 @@ static int deliver_one(bdepth* h, const SegDef& sd, size_t i, size_t n, size_t n
 
 int bdepth_run_windows(bdepth_t* h, uint32_t window, uint32_t overlap, const uint32_t* thr, size_t n_thr, bdepth_stat_cb cb, void* user) {
     if (window == 0) return fail(h, BDEPTH_ERR_ARG, "positive window size must be specified");
+    if (h->fix_mates) return fail(h, BDEPTH_ERR_ARG, "fix-mate-overlaps is not available in window mode yet (base and region modes are)");
     if (overlap >= window) return fail(h, BDEPTH_ERR_ARG, "specified overlap is larger than window size");
     const uint32_t step = window - overlap;
     const uint32_t nslot = (window + step - 1) / step;          // ring slots of PerWindowPrinter (depth.d:1026-1029)

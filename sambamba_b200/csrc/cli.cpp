@@ -7,7 +7,7 @@
 // D binding that would replace this file is in sambamba_b200/d/bdepth.d and INTEGRATION.md.
 //
 // Not supported through the GPU path yet (rejected with a message, never silently wrong):
-//   -F with anything but the default filter or "" ; -m ; several BAM files ; more than 64 samples without --combined.
+//   -F with anything but the default filter or "" ; -m in window mode ; several BAM files ; more than 64 samples without --combined.
 #include <math.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -259,7 +259,7 @@ int main(int argc, char** argv) {
             if (!(overlap < window)) return die("specified overlap is larger than window size");
         }
     }
-    if (fix_mates) return die("-m/--fix-mate-overlaps is not available in the GPU engine yet");
+    if (fix_mates && c.mode == 2) return die("-m/--fix-mate-overlaps is not available in window mode in the GPU engine yet");
     int mapq_gt = 0; uint32_t flag_reject = 0x600;
     if (has_query) {
         if (query.empty()) { mapq_gt = -1; flag_reject = 0; }
@@ -280,6 +280,7 @@ int main(int argc, char** argv) {
     bdepth_set_combined(c.h, c.combined ? 1 : 0);
     bdepth_set_filter(c.h, mapq_gt, flag_reject);
     bdepth_set_min_baseq(c.h, (uint32_t)min_bq);
+    bdepth_set_fix_mates(c.h, fix_mates ? 1 : 0);
     auto find_ref = [&](const std::string& n) { for (int i = 0; i < nref; i++) if (c.ref_names[i] == n) return i; return -1; };
     if (c.mode == 2) region_header(c, 3);
 

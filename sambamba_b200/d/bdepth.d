@@ -37,6 +37,8 @@ struct bdepth_stats {
     double host_wall_ms;
     float ms_span_device, ms_exchange;
     ulong own_lo, own_hi, halo_bytes_sent;
+    ulong mate_pairs, mate_pair_columns, mate_groups;
+    float ms_mates;
 }
 
 int bdepth_device_count();
@@ -56,6 +58,7 @@ const(char)* bdepth_sample_name(const(bdepth_t)* h, int i);
 
 int bdepth_set_filter(bdepth_t* h, int mapq_gt, uint flag_reject_mask);
 int bdepth_set_min_baseq(bdepth_t* h, uint q);
+int bdepth_set_fix_mates(bdepth_t* h, int on);   // -m, depth.d:1133
 int bdepth_set_combined(bdepth_t* h, int combined);
 int bdepth_set_regions(bdepth_t* h, const(bdepth_region)* r, size_t n);
 int bdepth_set_shard(bdepth_t* h, int rank, int world, const(void)* nccl_unique_id);
@@ -89,6 +92,7 @@ long bdepth_scan_to_host(bdepth_t* h, ulong cap, int* ref_id, int* pos, uint* sp
      enforce(bdepth_has_index(h), "All files must be indexed");                           // depth.d:1166
      bdepth_set_filter(h, 0, 0x600);              // default filter, depth.d:1159
      bdepth_set_min_baseq(h, printer.min_base_quality);
+     bdepth_set_fix_mates(h, printer.fix_mate_overlaps);                                   // depth.d:1133
      final switch (mode) {
        case Mode.base:   bdepth_run_base(h, &onTile, cast(void*) printer);   break;  // PerBasePrinter rows from tile planes
        case Mode.window: bdepth_run_windows(h, w, overlap, thr.ptr, thr.length, &onStat, cast(void*) printer); break;

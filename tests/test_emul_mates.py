@@ -486,3 +486,19 @@ def test_golden_issue_204_region(em, tmp_path):
     row = ["2", str(a), str(b), str(n_reads), _fmt_g(np.float32(n_bases) / ln)] + [_fmt_g(np.float32(int((cov >= t).sum())) * np.float32(100) / ln) for t in (15, 20, 25)]
     want = open(os.path.join(GOLDEN, "issue_204_expected_output.txt")).read().split("\n")[1].split("\t")
     assert row == want[:len(row)], (row, want)
+
+
+def test_generated_pairs_with_real_cigar_mix(em, tmp_path):
+    """tools/bamgen --pairs: the synthetic mix of SURVEY 8d (150 bp reads, I/D/S/N CIGARs) with mates sharing names."""
+    p = helpers.gen_bam(str(tmp_path / "gp.bam"), "--preset", "tiny", "-n", 6000, "--pairs", 6, "-t", 2)
+    soa = Soa(p)
+    for minq in (0, 25):
+        want, npc = helpers.oracle_counts_fix_mates(p, min_bq=minq)
+        plain, _ = helpers.oracle_counts(p, min_bq=minq)
+        c = np.ascontiguousarray(plain[None])
+        rc, stat, _, _, err = run_emul(em, soa, c, 1, minq=minq, order=2)
+        assert rc == 0, err
+        assert stat[1] == npc and npc > 10000
+        assert np.array_equal(c[0], want)
+    regs = [(0, 100, 900), (0, 1000, 1200), (0, 1200, 1207), (1, 10, 20), (2, 5, 40000)]
+    check_regions(em, p, regs, [3, 10], 0, tmp_path)

@@ -37,11 +37,9 @@ def test_golden_issue_225():
 
 
 def test_region_204_without_m_matches_oracle():
-    # the reference's golden file for issue_204 uses -m (not in the GPU engine yet); without -m the oracle is the checker
+    # the reference's golden file for issue_204 uses -m (tests/test_zz_gpu_mates.py); without -m the oracle is the checker
     out, _ = check_same(["region", G("issue_204.bam"), "-L", "2:166868600-166868813", "-T", "15", "-T", "20", "-T", "25"])
     assert b"41\t20.2196\t89.7196\t61.215\t20.5607" in out
-    rc, _, err = helpers.run_cli(["region", G("issue_204.bam"), "-L", "2:166868600-166868813", "-m"])
-    assert rc == 1 and b"sambamba-depth:" in err
 
 
 @pytest.fixture(scope="module")

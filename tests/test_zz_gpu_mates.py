@@ -1,0 +1,113 @@
+"""`-m` / --fix-mate-overlaps through the GPU: libbdepth.so's km_hash / km_link / km_fix after K3.
+
+The device functions are the ones tests/test_emul_mates.py runs on the CPU against the oracle's column sweep; what
+only hardware can show is the launch plumbing (single-batch mode, parameter block, region arrays).  This file was
+written after the round's GPU budget was spent, so its first hardware run is still pending: the tests execute (and
+report XPASS when green) but do not gate the suite until they have been seen green once -- then the xfail marker goes.
+The file sorts last on purpose: nothing runs after it in the same process."""
+import os
+
+import numpy as np
+import pytest
+
+import helpers
+from helpers import GOLDEN
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600),
+              pytest.mark.xfail(strict=False, reason="first hardware run pending (GPU budget of the round was spent before -m was wired in)")]
+
+
+def G(f):
+    return os.path.join(GOLDEN, f)
+
+
+def check_same(args):
+    rc1, out1, err1 = helpers.run_cli(args)
+    rc2, out2, err2 = helpers.oracle_cli(args)
+    assert rc1 == rc2, (args, err1, err2)
+    assert out1 == out2, (args, out1[:400], out2[:400])
+    return out1
+
+
+@pytest.fixture(scope="module")
+def pairs(tmp_path_factory):
+    d = tmp_path_factory.mktemp("mates")
+    p = helpers.gen_bam(str(d / "pairs.bam"), "--preset", "tiny", "-n", 20000, "--pairs", 6, "-t", 4)
+    big = helpers.gen_bam(str(d / "pairs2.bam"), "-r", "chrA:900000", "-r", "chrB:600000", "-n", 120000, "--pairs", 5, "-s", 9, "-t", 4)
+    sbed = d / "s.bed"
+    sbed.write_text("ctgA\t100\t900\nctgA\t1000\t1200\nctgA\t1200\t1207\nctgB\t10\t20\nctgC\t5\t40000\n")
+    obed = d / "o.bed"
+    obed.write_text("ctgA\t100\t900\tgeneA\nctgA\t850\t1200\tgeneB\nctgC\t0\t52000\nctgB\t10\t20\nctgA\t29000\t31000\tedge\n")
+    return p, big, str(sbed), str(obed)
+
+
+def test_golden_issue_204_region_with_m():
+    """The reference's only region-mode golden vector (test/test_suite.sh:156-162): byte-identical through the GPU."""
+    rc, out, err = helpers.run_cli(["depth", "region", G("issue_204.bam"), "-L", "2:166868600-166868813", "-T", "15", "-T", "20", "-T", "25", "-m"])
+    assert rc == 0, err
+    assert out == open(G("issue_204_expected_output.txt"), "rb").read()
+
+
+def test_mate_overlaps_fixture():
+    bed = G("mate_overlaps_1_3M_4M.bed")
+    check_same(["base", "-m", G("mate_overlaps_1_3M_4M.bam")])
+    check_same(["base", "-m", "-c", "0", "-L", bed, G("mate_overlaps_1_3M_4M.bam")])
+    check_same(["region", "-m", "-L", bed, "-T", "1", "-T", "2", G("mate_overlaps_1_3M_4M.bam")])
+
+
+def test_base_counters_match_closed_form(pairs):
+    import sambamba_b200 as sb
+    for p in pairs[:2]:
+        for minq in (0, 25):
+            want, npc = helpers.oracle_counts_fix_mates(p, min_bq=minq)
+            with sb.BDepth(p) as b:
+                b.set_fix_mates(True)
+                b.set_min_baseq(minq)
+                got = b.run_base()
+                st = b.stats()
+            assert npc > 10000 and st["mate_pair_columns"] == npc and st["mate_pairs"] > 100
+            assert got.shape == want.shape and np.array_equal(got, want)
+            # staged input (one K1 launch) takes the same single-batch path
+            with sb.BDepth(p) as b:
+                b.set_fix_mates(True)
+                b.set_min_baseq(minq)
+                b.stage()
+                assert np.array_equal(b.run_base(), want)
+
+
+def test_cli_base_and_region_match_oracle(pairs):
+    p, _, sbed, obed = pairs
+    for args in (["base", "-m", p], ["base", "-m", "-c", "0", "-q", "20", p], ["base", "-m", "--combined", "-a", "-c", "4", p],
+                 ["base", "-m", "-L", sbed, "-c", "0", p], ["base", "-m", "-L", "ctgA:1,000-2000", p],
+                 ["region", "-m", "-L", sbed, "-T", "3", "-T", "10", p], ["region", "-m", "-L", sbed, "-q", "25", "-T", "0", "-T", "6", p],
+                 ["region", "-m", "-L", obed, "-T", "8", p], ["region", "-m", "-L", "ctgA:5000-6000", "-a", "-c", "7.9", p]):
+        check_same(args)
+
+
+def test_multi_sample_pairs(tmp_path):
+    import test_emul_mates as tem
+    rg = [("g1", "S1"), ("g2", "S2"), ("g3", "S1")]
+    p = tem.make_pairs_bam(str(tmp_path / "ms.bam"), 7, rg=rg)
+    check_same(["base", "-m", "-c", "0", p])
+    check_same(["base", "-m", "--combined", p])
+    check_same(["region", "-m", "-L", "c1:100-900", "-T", "2", p])
+
+
+def test_groups_and_refusals(tmp_path, pairs):
+    import test_emul_mates as tem
+    import sambamba_b200 as sb
+    done = 0
+    for seed in range(10, 16):
+        p = tem.make_pairs_bam(str(tmp_path / f"tri{seed}.bam"), seed, n_frag=120, triples=0.5)
+        rc, out, err = helpers.run_cli(["base", "-m", "-c", "0", "--combined", p])
+        if rc == 1 and b"depends on unrelated reads" in err:
+            continue
+        assert rc == 0, err
+        rc2, out2, _ = helpers.oracle_cli(["base", "-m", "-c", "0", "--combined", p])
+        assert out == out2
+        done += 1
+        rc, _, err = helpers.run_cli(["region", "-m", "-L", "c1:1-4000", p])
+        assert rc == 1 and b"only pairs are supported" in err
+    assert done >= 2
+    rc, _, err = helpers.run_cli(["window", "-w", "100", "-m", pairs[0]])
+    assert rc == 1 and b"window mode" in err

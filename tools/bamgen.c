@@ -14,7 +14,7 @@
  * every 4096-read chunk owns an RNG seeded from (seed, chunk index).
  *
  * usage: bamgen -o out.bam [-n reads] [-s seed] [-t threads] [-l level]
- *               [-r name:len]... | --preset chr20|wgs|tiny  [--stored-every K]
+ *               [-r name:len]... | --preset chr20|wgs|tiny  [--stored-every K] [--pairs K]
  */
 #define _GNU_SOURCE
 #include <stdint.h>
@@ -76,6 +76,7 @@ typedef struct {
 
 static inline void put32(uint8_t *p, uint32_t v) { p[0] = (uint8_t)v; p[1] = (uint8_t)(v >> 8); p[2] = (uint8_t)(v >> 16); p[3] = (uint8_t)(v >> 24); }
 
+static uint64_t g_pairs = 0;
 static void gen_read(GenJob *j, Rng *r, uint64_t idx) {
     /* stratified-uniform sorted position in usable linear space */
     double x = ((double)idx + rng_u(r)) / (double)j->total_reads * (double)g_G;
@@ -99,7 +100,9 @@ static void gen_read(GenJob *j, Rng *r, uint64_t idx) {
     int32_t mpos = pos + (int32_t)rng_below(r, 1001) - 500; if (mpos < 0) mpos = 0; if ((uint32_t)mpos >= rlen) mpos = (int32_t)rlen - 1;
     int32_t tlen = mpos >= pos ? mpos - pos + READ_LEN : -(pos - mpos + READ_LEN);
     /* record */
-    char name[16]; int l_name = snprintf(name, sizeof name, "r%09llu", (unsigned long long)idx) + 1;
+    /* --pairs K: read idx and read idx + K (about K read spacings further along) share a name, like overlapping mates */
+    uint64_t name_id = g_pairs ? (idx / (2 * g_pairs)) * g_pairs + (idx % g_pairs) : idx;
+    char name[16]; int l_name = snprintf(name, sizeof name, "r%09llu", (unsigned long long)name_id) + 1;
     static const char RG[] = "RGZrg1"; /* + NUL */
     size_t rec = 32 + (size_t)l_name + 4 * (size_t)nc + (READ_LEN + 1) / 2 + READ_LEN + 7 + 4 + 4;
     if (j->len + 4 + rec > j->cap) { j->cap = (j->cap + 4 + rec) * 2; j->buf = realloc(j->buf, j->cap); if (!j->buf) die("oom"); }
@@ -240,9 +243,10 @@ int main(int argc, char **argv) {
         else if (!strcmp(argv[i], "-t") && i + 1 < argc) nthreads = atoi(argv[++i]);
         else if (!strcmp(argv[i], "-l") && i + 1 < argc) level = atoi(argv[++i]);
         else if (!strcmp(argv[i], "--stored-every") && i + 1 < argc) stored_every = atoi(argv[++i]);
+        else if (!strcmp(argv[i], "--pairs") && i + 1 < argc) g_pairs = strtoull(argv[++i], NULL, 10);
         else if (!strcmp(argv[i], "--preset") && i + 1 < argc) preset = argv[++i];
         else if (!strcmp(argv[i], "-r") && i + 1 < argc) { char *s = argv[++i], *c = strrchr(s, ':'); if (!c) die("bad -r name:len"); refs = realloc(refs, (nref + 1) * sizeof(Ref)); memset(&refs[nref], 0, sizeof(Ref)); snprintf(refs[nref].name, 64, "%.*s", (int)(c - s), s); refs[nref].len = (uint32_t)strtoul(c + 1, NULL, 10); nref++; }
-        else die("usage: bamgen -o out.bam [-n reads] [-s seed] [-t threads] [-l level] [-r name:len]... [--preset chr20|wgs|tiny] [--stored-every K]");
+        else die("usage: bamgen -o out.bam [-n reads] [-s seed] [-t threads] [-l level] [-r name:len]... [--preset chr20|wgs|tiny] [--stored-every K] [--pairs K]");
     }
     if (!out) die("-o required");
     if (preset && !strcmp(preset, "chr20")) { refs = calloc(1, sizeof(Ref)); strcpy(refs[0].name, "chr20"); refs[0].len = 64444167; nref = 1; if (!n_reads) n_reads = 12888833; }
