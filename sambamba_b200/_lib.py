@@ -87,6 +87,7 @@ def load_library():
     L.bdepth_sample_name.argtypes = [vp, C.c_int]
     L.bdepth_sample_name.restype = C.c_char_p
     L.bdepth_set_filter.argtypes = [vp, C.c_int, C.c_uint32]
+    L.bdepth_set_filter_query.argtypes = [vp, C.c_char_p]
     L.bdepth_set_min_baseq.argtypes = [vp, C.c_uint32]
     L.bdepth_set_fix_mates.argtypes = [vp, C.c_int]
     L.bdepth_set_combined.argtypes = [vp, C.c_int]
@@ -116,7 +117,7 @@ def load_library():
 EXPORTED_SYMBOLS = [
     "bdepth_device_count", "bdepth_open", "bdepth_open_memory", "bdepth_close", "bdepth_last_error", "bdepth_n_ref",
     "bdepth_ref_name", "bdepth_ref_length", "bdepth_header_text", "bdepth_is_coordinate_sorted", "bdepth_has_index",
-    "bdepth_n_samples", "bdepth_sample_name", "bdepth_set_filter", "bdepth_set_min_baseq", "bdepth_set_fix_mates", "bdepth_set_combined", "bdepth_set_regions",
+    "bdepth_n_samples", "bdepth_sample_name", "bdepth_set_filter", "bdepth_set_filter_query", "bdepth_set_min_baseq", "bdepth_set_fix_mates", "bdepth_set_combined", "bdepth_set_regions",
     "bdepth_set_shard", "bdepth_nccl_unique_id", "bdepth_plan_shards", "bdepth_plan_region_chunks", "bdepth_set_tuning", "bdepth_stage", "bdepth_run_resident", "bdepth_run_base", "bdepth_run_base_text",
     "bdepth_run_windows", "bdepth_run_regions", "bdepth_get_stats", "bdepth_ref_has_reads", "bdepth_inflate_to_host", "bdepth_scan_to_host",
 ]
@@ -205,6 +206,9 @@ class BDepth:
     # config
     def set_filter(self, mapq_gt=0, flag_reject=0x600):
         self._ck(self.L.bdepth_set_filter(self.h, mapq_gt, flag_reject))
+
+    def set_filter_query(self, query):
+        self._ck(self.L.bdepth_set_filter_query(self.h, query.encode()))
 
     def set_min_baseq(self, q):
         self._ck(self.L.bdepth_set_min_baseq(self.h, q))

@@ -24,6 +24,7 @@
 #include "host_bam.hpp"
 #include "kernels.cuh"
 #include "mates.cuh"
+#include "host_filter.hpp"
 
 using namespace bdk;
 
@@ -132,6 +133,7 @@ struct bdepth {
     bool bai_window_ok = true;            // cleared when the linear index turns out not to describe the file
     bool combined = false;                // --combined: one counter set for all samples
     bool fix_mates = false;               // -m: overlapping mates count once per column (mates.cuh)
+    bool has_fprog = false; FilterProg fprog; DevBuf fprog_d;      // -F: compiled query (filter.cuh); otherwise mapq_gt / flag_reject
     DevBuf m_hash, m_flag, m_flt, m_ctl;
     uint32_t S = 1;                       // counter sets in the current run (samples, or 1)
     DevBuf rg_ids, rg_offs, rg_samp;
@@ -522,6 +524,8 @@ int run_pipeline(bdepth* h, RunMode mode, RunOut* ro, Emitter* em = nullptr) {
         CK(h->ref_has.ensure((nref / 32 + 2) * 4)); CK(cudaMemsetAsync(h->ref_has.p, 0, (nref / 32 + 2) * 4, sm));
     }
     CK(h->scan_stats.ensure(sizeof(ScanStats)));
+    const FilterProg* d_fprog = nullptr;
+    if (h->has_fprog) { CK(h->fprog_d.ensure(sizeof(FilterProg))); CK(cudaMemcpyAsync(h->fprog_d.p, &h->fprog, sizeof(FilterProg), cudaMemcpyHostToDevice, sm)); CK(cudaStreamSynchronize(sm)); d_fprog = h->fprog_d.as<FilterProg>(); }
     RgTable rgt{nullptr, nullptr, nullptr, 0};
     if (mode == RUN_FULL && (h->S > 1 || (fix && h->hdr.sample_names.size() > 1))) {      // @RG ID -> sample table for the per-read RG lookup (depth.d:240-250); mates pair within a sample
         std::vector<uint8_t> ids; std::vector<uint32_t> offs; std::vector<uint8_t> samp;
@@ -790,7 +794,10 @@ int run_pipeline(bdepth* h, RunMode mode, RunOut* ro, Emitter* em = nullptr) {
         ScanStats zs{0, 0, 0, 0, ~0ull, 0, 0, ~0ull};
         UP(h->scan_stats.p, &zs, sizeof zs);
         if (mode == RUN_SCAN_ONLY && !h->ref_has.p) { CK(h->ref_has.ensure((nref / 32 + 2) * 4)); CK(cudaMemsetAsync(h->ref_has.p, 0, (nref / 32 + 2) * 4, sm)); }
-        k2_decode<<<(unsigned)((nb * 32 + 255) / 256), 256, 0, sm>>>(sp, h->chunk_start.as<int64_t>(), (uint32_t)nb, h->slot_base.as<uint32_t>(), h->slots.as<uint16_t>(), h->count.as<uint32_t>(), h->rec_base.as<uint32_t>(), soa, h->mapq_gt, h->flag_reject, h->scan_stats.as<ScanStats>(), h->long_list.as<uint32_t>(), h->ref_has.as<uint32_t>(), rgt);
+        if (d_fprog)
+            k2_decode<true><<<(unsigned)((nb * 32 + 255) / 256), 256, 0, sm>>>(sp, h->chunk_start.as<int64_t>(), (uint32_t)nb, h->slot_base.as<uint32_t>(), h->slots.as<uint16_t>(), h->count.as<uint32_t>(), h->rec_base.as<uint32_t>(), soa, h->mapq_gt, h->flag_reject, h->scan_stats.as<ScanStats>(), h->long_list.as<uint32_t>(), h->ref_has.as<uint32_t>(), rgt, d_fprog);
+        else
+            k2_decode<false><<<(unsigned)((nb * 32 + 255) / 256), 256, 0, sm>>>(sp, h->chunk_start.as<int64_t>(), (uint32_t)nb, h->slot_base.as<uint32_t>(), h->slots.as<uint16_t>(), h->count.as<uint32_t>(), h->rec_base.as<uint32_t>(), soa, h->mapq_gt, h->flag_reject, h->scan_stats.as<ScanStats>(), h->long_list.as<uint32_t>(), h->ref_has.as<uint32_t>(), rgt, d_fprog);
         CK(cudaGetLastError()); st.gpu_launches++;
         DOWN(ssp, ScanStats, h->scan_stats.p, sizeof(ScanStats));
         CK(cudaEventRecord(e3, sm));
@@ -979,7 +986,7 @@ void bdepth_close(bdepth_t* h) {
     h->rg_ids.release(); h->rg_offs.release(); h->rg_samp.release();
     h->text[0].release(); h->text[1].release(); h->text_tiles.release(); h->text_offs.release(); h->text_zero.release();
     h->seg.s.release(); h->seg.e.release(); h->seg.pmax.release(); h->seg.id.release(); h->seg.reads.release(); h->seg.minstart.release(); h->seg.bases_reads.release(); h->seg.mbases.release();
-    h->m_hash.release(); h->m_flag.release(); h->m_flt.release(); h->m_ctl.release();
+    h->m_hash.release(); h->m_flag.release(); h->m_flt.release(); h->m_ctl.release(); h->fprog_d.release();
     if (h->comm) { nccl().CommDestroy(h->comm); h->comm = nullptr; }
     if (h->pinned) cudaFreeHost(h->pinned);
     h->hs.release();
@@ -1001,7 +1008,18 @@ int bdepth_has_index(const bdepth_t* h) { return h->has_index ? 1 : 0; }
 int bdepth_n_samples(const bdepth_t* h) { return (int)h->hdr.sample_names.size(); }
 const char* bdepth_sample_name(const bdepth_t* h, int i) { return (i >= 0 && (size_t)i < h->hdr.sample_names.size()) ? h->hdr.sample_names[i].c_str() : nullptr; }
 
-int bdepth_set_filter(bdepth_t* h, int mapq_gt, uint32_t flag_reject_mask) { h->mapq_gt = mapq_gt; h->flag_reject = flag_reject_mask; return 0; }
+int bdepth_set_filter(bdepth_t* h, int mapq_gt, uint32_t flag_reject_mask) { h->mapq_gt = mapq_gt; h->flag_reject = flag_reject_mask; h->has_fprog = false; return 0; }
+int bdepth_set_filter_query(bdepth_t* h, const char* query) {
+    if (!query) return fail(h, BDEPTH_ERR_ARG, "null filter");
+    const std::string q(query);
+    if (q.empty()) return bdepth_set_filter(h, -1, 0);                                                     // NullFilter, filtering.d:41-42
+    if (q == "mapping_quality > 0 and not duplicate and not failed_quality_control") return bdepth_set_filter(h, 0, 0x600);   // depth.d:1159
+    FilterCompiler fc(h->hdr.ref_names);
+    std::string e = fc.compile(q, h->fprog);
+    if (!e.empty()) { h->has_fprog = false; return fail(h, BDEPTH_ERR_ARG, "%s", e.c_str()); }
+    h->has_fprog = true;
+    return 0;
+}
 int bdepth_set_combined(bdepth_t* h, int combined) { h->combined = combined != 0; return 0; }
 int bdepth_set_fix_mates(bdepth_t* h, int on) { h->fix_mates = on != 0; return 0; }
 int bdepth_set_min_baseq(bdepth_t* h, uint32_t q) { h->minq = q > 255 ? 255 : q; return 0; }

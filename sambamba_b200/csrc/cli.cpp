@@ -7,7 +7,7 @@
 // D binding that would replace this file is in sambamba_b200/d/bdepth.d and INTEGRATION.md.
 //
 // Not supported through the GPU path yet (rejected with a message, never silently wrong):
-//   -F with anything but the default filter or "" ; -m in window mode ; several BAM files ; more than 64 samples without --combined.
+//   -F with regular expressions or sequence / cigar comparisons ; -m in window mode ; several BAM files ; more than 64 samples without --combined.
 #include <math.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -261,10 +261,6 @@ int main(int argc, char** argv) {
     }
     if (fix_mates && c.mode == 2) return die("-m/--fix-mate-overlaps is not available in window mode in the GPU engine yet");
     int mapq_gt = 0; uint32_t flag_reject = 0x600;
-    if (has_query) {
-        if (query.empty()) { mapq_gt = -1; flag_reject = 0; }
-        else if (query != "mapping_quality > 0 and not duplicate and not failed_quality_control") return die("only the default filter or -F \"\" is available in the GPU engine yet");
-    }
     if (a.v.size() < 2) return die("no input BAM given");
     if (a.v.size() > 2) return die("several BAM files: not available in the GPU engine yet");
     const std::string bam_path = a.v[1];
@@ -279,6 +275,7 @@ int main(int argc, char** argv) {
     for (int i = 0; i < bdepth_n_samples(c.h); i++) c.samples.push_back(bdepth_sample_name(c.h, i));
     bdepth_set_combined(c.h, c.combined ? 1 : 0);
     bdepth_set_filter(c.h, mapq_gt, flag_reject);
+    if (has_query && bdepth_set_filter_query(c.h, query.c_str())) return die(bdepth_last_error(c.h));      // createFilterFromQuery, depth.d:1159
     bdepth_set_min_baseq(c.h, (uint32_t)min_bq);
     bdepth_set_fix_mates(c.h, fix_mates ? 1 : 0);
     auto find_ref = [&](const std::string& n) { for (int i = 0; i < nref; i++) if (c.ref_names[i] == n) return i; return -1; };

@@ -1,0 +1,147 @@
+// filter.cuh -- per-record evaluation of a compiled `-F` filter expression (SURVEY 8a row a9 beyond the default
+// predicate; rank 4 of 8f).
+//
+// Replaces: the Filter tree createFilterFromQuery builds (sambamba/utils/common/filtering.d:40-51) and its node
+// classes -- FlagFilter / ChimericFilter (:163-178), IntegerFieldFilter (:197-214, avg_base_quality :192-194),
+// TagExistenceFilter (:216-232), IntegerTagFilter (:235-254), StringFieldFilter (read_name, strand; :257-277),
+// StringTagFilter (:280-302), And/Or/NotFilter (:86-115) -- evaluated through five virtual calls per read in the
+// reference, here as a postfix program of at most FILTER_MAX_OPS fixed-size operations that k2_decode runs per
+// record.  host_filter.hpp compiles the query text (queryparser.d grammar) into it.
+//
+// __host__ __device__ and free of warp intrinsics: tests/emul/emul_filter.cpp runs the same code on the CPU.
+#pragma once
+#include <stdint.h>
+#ifndef BD_HD
+#if defined(__CUDACC__)
+#define BD_HD __host__ __device__ __forceinline__
+#else
+#define BD_HD inline
+#endif
+#endif
+
+namespace bdk {
+
+constexpr int FILTER_MAX_OPS = 48;
+constexpr int FILTER_POOL = 256;
+
+enum FilterOpCode : uint8_t {
+    FO_CONST = 0,      // push imm != 0
+    FO_FLAG,           // push (flag & imm) != 0                                  FlagFilter
+    FO_CHIMERIC,       // paired && !unmapped && !mate_unmapped && ref != mate    ChimericFilter
+    FO_INTFIELD,       // push field[a] <cmp> imm                                 IntegerFieldFilter
+    FO_AVGQ,           // push avg_base_quality <cmp> imm (float32)
+    FO_INTTAG,         // push tag[b] is integer/float && value <cmp> imm         IntegerTagFilter
+    FO_TAGNULL,        // cmp == : tag absent; cmp != : tag present               TagExistenceFilter
+    FO_NAME,           // push read_name <cmp> pool[s_off, s_len)                 StringFieldFilter("read_name")
+    FO_STRAND,         // push strand <cmp> pool[s_off]                           StringFieldFilter("strand")
+    FO_STRTAG,         // push string/char tag <cmp> pool[...]                    StringTagFilter
+    FO_AND, FO_OR, FO_NOT
+};
+enum FilterCmp : uint8_t { FC_GT = 0, FC_LT, FC_GE, FC_LE, FC_EQ, FC_NE };
+enum FilterField : uint8_t { FF_REF_ID = 0, FF_POSITION, FF_MAPQ, FF_SEQ_LEN, FF_MATE_REF_ID, FF_MATE_POSITION, FF_TLEN };
+
+struct FilterOp { uint8_t op, cmp, a, pad; uint16_t tag; uint8_t s_off, s_len; int64_t imm; };      // 16 bytes
+struct FilterProg { uint32_t n; uint32_t pad; FilterOp ops[FILTER_MAX_OPS]; char pool[FILTER_POOL]; };
+
+template <class T> BD_HD bool f_cmp(uint8_t c, T a, T b) {
+    switch (c) { case FC_GT: return a > b; case FC_LT: return a < b; case FC_GE: return a >= b; case FC_LE: return a <= b; case FC_EQ: return a == b; default: return a != b; }
+}
+BD_HD uint32_t f_ld32(const uint8_t* q) { return (uint32_t)q[0] | ((uint32_t)q[1] << 8) | ((uint32_t)q[2] << 16) | ((uint32_t)q[3] << 24); }
+// D string comparison: code units in order, then length
+BD_HD int f_strcmp(const uint8_t* a, uint32_t na, const char* b, uint32_t nb) {
+    uint32_t n = na < nb ? na : nb;
+    for (uint32_t i = 0; i < n; i++) { uint8_t x = a[i], y = (uint8_t)b[i]; if (x != y) return x < y ? -1 : 1; }
+    return na == nb ? 0 : (na < nb ? -1 : 1);
+}
+// linear scan of the aux area for a tag (read.d:1070-1087): returns the value pointer and its type, or nullptr
+BD_HD const uint8_t* f_find_tag(const uint8_t* aux, const uint8_t* end, uint16_t tag, uint8_t* type) {
+    while (aux + 3 <= end) {
+        uint8_t ty = aux[2]; const uint8_t* v = aux + 3;
+        if (((uint16_t)aux[0] | ((uint16_t)aux[1] << 8)) == tag) { *type = ty; return v; }
+        uint64_t n;
+        switch (ty) {
+        case 'A': case 'c': case 'C': n = 1; break;
+        case 's': case 'S': n = 2; break;
+        case 'i': case 'I': case 'f': n = 4; break;
+        case 'Z': case 'H': { const uint8_t* q = v; while (q < end && *q) q++; n = (uint64_t)(q - v) + 1; break; }
+        case 'B': { if (v + 5 > end) return nullptr; uint8_t st = v[0]; uint32_t cnt = f_ld32(v + 1); uint64_t es = (st == 'c' || st == 'C') ? 1 : (st == 's' || st == 'S') ? 2 : 4; n = 5 + es * cnt; break; }
+        default: return nullptr;
+        }
+        if (n > (uint64_t)(end - v)) return nullptr;
+        aux = v + n;
+    }
+    return nullptr;
+}
+BD_HD float f_bits2float(uint32_t b) {
+#if defined(__CUDA_ARCH__)
+    return __uint_as_float(b);
+#else
+    union { uint32_t u; float f; } x; x.u = b; return x.f;
+#endif
+}
+
+// rec points at the refID field of the record, rec_size is its block_size
+BD_HD bool filter_eval(const FilterProg& fp, const uint8_t* rec, uint32_t rec_size) {
+    uint64_t stack = 0; int sp = 0;                    // bit stack (programs are at most FILTER_MAX_OPS long)
+    const uint32_t bmn = f_ld32(rec + 8), fnc = f_ld32(rec + 12);
+    const uint32_t l_name = bmn & 0xFFu, mapq = (bmn >> 8) & 0xFFu, flag = fnc >> 16, n_cigar = fnc & 0xFFFFu;
+    const int32_t l_seq = (int32_t)f_ld32(rec + 16);
+    const uint32_t lq = l_seq > 0 ? (uint32_t)l_seq : 0u;
+    const uint8_t* qual = rec + 32 + l_name + 4u * n_cigar + (lq + 1) / 2;
+    const uint8_t* aux = qual + lq; const uint8_t* end = rec + rec_size;
+    for (uint32_t i = 0; i < fp.n; i++) {
+        const FilterOp& o = fp.ops[i]; bool r = false;
+        switch (o.op) {
+        case FO_CONST: r = o.imm != 0; break;
+        case FO_FLAG: r = (flag & (uint32_t)o.imm) != 0; break;
+        case FO_CHIMERIC: r = (flag & 1u) && !(flag & 4u) && !(flag & 8u) && (int32_t)f_ld32(rec) != (int32_t)f_ld32(rec + 20); break;
+        case FO_INTFIELD: {
+            int64_t v;
+            switch (o.a) {
+            case FF_REF_ID: v = (int32_t)f_ld32(rec); break;
+            case FF_POSITION: v = (int32_t)f_ld32(rec + 4); break;
+            case FF_MAPQ: v = mapq; break;
+            case FF_SEQ_LEN: v = l_seq; break;
+            case FF_MATE_REF_ID: v = (int32_t)f_ld32(rec + 20); break;
+            case FF_MATE_POSITION: v = (int32_t)f_ld32(rec + 24); break;
+            default: v = (int32_t)f_ld32(rec + 28); break;
+            }
+            r = f_cmp<int64_t>(o.cmp, v, o.imm); break; }
+        case FO_AVGQ: {      // reduce!"a+b"(0.0f, base_qualities) / sequence_length, compared as float (filtering.d:192-194)
+            float s = 0.0f; for (uint32_t k = 0; k < lq && qual + k < end; k++) s += (float)qual[k];
+            float avg = s / (float)l_seq;
+            r = f_cmp<float>(o.cmp, avg, (float)o.imm); break; }
+        case FO_INTTAG: case FO_TAGNULL: case FO_STRTAG: {
+            uint8_t ty = 0; const uint8_t* v = aux <= end ? f_find_tag(aux, end, o.tag, &ty) : nullptr;
+            if (o.op == FO_TAGNULL) { r = (o.cmp == FC_EQ) == (v == nullptr); break; }
+            if (!v) { r = false; break; }
+            if (o.op == FO_INTTAG) {
+                int64_t iv = 0; bool isint = true;
+                switch (ty) {
+                case 'c': iv = (int8_t)v[0]; break; case 'C': iv = v[0]; break;
+                case 's': iv = (int16_t)(v[0] | (v[1] << 8)); break; case 'S': iv = (uint16_t)(v[0] | (v[1] << 8)); break;
+                case 'i': iv = (int32_t)f_ld32(v); break; case 'I': iv = f_ld32(v); break;
+                default: isint = false; break;
+                }
+                if (isint) r = f_cmp<int64_t>(o.cmp, iv, o.imm);
+                else if (ty == 'f') r = f_cmp<float>(o.cmp, f_bits2float(f_ld32(v)), (float)o.imm);
+                else r = false;
+            } else {
+                if (ty == 'Z' || ty == 'H') { const uint8_t* q = v; while (q < end && *q) q++; r = f_cmp<int>(o.cmp, f_strcmp(v, (uint32_t)(q - v), fp.pool + o.s_off, o.s_len), 0); }
+                else if (ty == 'A') r = o.s_len == 1 && f_cmp<int>(o.cmp, (int)v[0], (int)(uint8_t)fp.pool[o.s_off]);
+                else r = false;
+            }
+            break; }
+        case FO_NAME: r = f_cmp<int>(o.cmp, f_strcmp(rec + 32, l_name ? l_name - 1 : 0, fp.pool + o.s_off, o.s_len), 0); break;
+        case FO_STRAND: r = f_cmp<int>(o.cmp, (flag & 0x10u) ? '-' : '+', (int)(uint8_t)fp.pool[o.s_off]); break;
+        case FO_AND: { bool b = (stack >> (sp - 1)) & 1, a = (stack >> (sp - 2)) & 1; sp -= 2; r = a && b; break; }
+        case FO_OR: { bool b = (stack >> (sp - 1)) & 1, a = (stack >> (sp - 2)) & 1; sp -= 2; r = a || b; break; }
+        case FO_NOT: { bool a = (stack >> (sp - 1)) & 1; sp -= 1; r = !a; break; }
+        default: r = false; break;
+        }
+        stack = (stack & ~(1ull << sp)) | ((uint64_t)(r ? 1 : 0) << sp); sp++;
+    }
+    return sp > 0 ? ((stack >> (sp - 1)) & 1) != 0 : true;
+}
+
+}  // namespace bdk

@@ -23,6 +23,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "inflate_core.cuh"
+#include "filter.cuh"
 
 namespace bdk {
 
@@ -205,10 +206,14 @@ __device__ __forceinline__ bool cig_rcons(uint32_t op) { return op == 0 || op ==
 __device__ __forceinline__ bool cig_qcons(uint32_t op) { return op == 0 || op == 1 || op == 4 || op == 7 || op == 8; }
 __device__ __forceinline__ bool cig_match(uint32_t op) { return op == 0 || op == 7 || op == 8; }
 
+// out of line: the default predicate's path through k2_decode keeps its registers
+__device__ __noinline__ bool filter_eval_cold(const FilterProg* fp, const uint8_t* rec, uint32_t rec_size) { return filter_eval(*fp, rec, rec_size); }
+
+template <bool FILTER>      // FILTER: a compiled -F query decides (its own instantiation, so that the default predicate's kernel keeps its register count)
 __global__ void k2_decode(ScanParams sp, const int64_t* __restrict__ chunk_start, uint32_t n_chunks, const uint32_t* __restrict__ slot_base,
                           const uint16_t* __restrict__ slots, const uint32_t* __restrict__ count, const uint32_t* __restrict__ rec_base,
                           RecordSoA soa, int mapq_gt, uint32_t flag_reject, ScanStats* __restrict__ st, uint32_t* __restrict__ long_list,
-                          uint32_t* __restrict__ ref_has_reads, RgTable rg) {
+                          uint32_t* __restrict__ ref_has_reads, RgTable rg, const FilterProg* __restrict__ fprog /* compiled -F query, or nullptr: mapq_gt / flag_reject */) {
     uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= n_chunks) return;
     uint32_t n = count[warp];
@@ -232,7 +237,8 @@ __global__ void k2_decode(ScanParams sp, const int64_t* __restrict__ chunk_start
         uint64_t span = 0;
         for (uint32_t i = 0; i < n_cigar; i++) { uint32_t c = ldu32(cg + 4 * i); if (cig_rcons(c & 15)) span += c >> 4; }
         bool placed = ref >= 0 && ref < sp.n_ref && pos >= 0;
-        bool pass = placed && ((int)mapq > mapq_gt) && !(flag & flag_reject) && !(flag & 4u) && span > 0;
+        bool pass = placed && !(flag & 4u) && span > 0;
+        if (pass) { if (FILTER) pass = filter_eval_cold(fprog, p, ldu32(sp.u + o)); else pass = ((int)mapq > mapq_gt) && !(flag & flag_reject); }
         uint64_t start = placed ? sp.ref_lin0[ref] + (uint64_t)pos : 0xFFFFFFFFFFFFFFFEull;
         uint32_t span_eff = 0;
         if (pass) {

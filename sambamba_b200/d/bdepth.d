@@ -57,6 +57,7 @@ int bdepth_n_samples(const(bdepth_t)* h);
 const(char)* bdepth_sample_name(const(bdepth_t)* h, int i);
 
 int bdepth_set_filter(bdepth_t* h, int mapq_gt, uint flag_reject_mask);
+int bdepth_set_filter_query(bdepth_t* h, const(char)* query);   // -F, depth.d:1121
 int bdepth_set_min_baseq(bdepth_t* h, uint q);
 int bdepth_set_fix_mates(bdepth_t* h, int on);   // -m, depth.d:1133
 int bdepth_set_combined(bdepth_t* h, int combined);

@@ -180,3 +180,39 @@ def write_bam(path, refs, reads, rg=None, block=0xFF00, level=6, quals=None, tag
     return path
 
 
+
+
+def write_bgzf(path, body, n_ref, block=0xFF00, level=6):
+    """BGZF-compress an inflated BAM stream and put an empty-but-valid index next to it."""
+    import struct
+    import zlib
+    with open(path, "wb") as f:
+        for i in range(0, len(body), block):
+            chunk = body[i:i + block]
+            c = zlib.compressobj(level, zlib.DEFLATED, -15)
+            d = c.compress(chunk) + c.flush()
+            f.write(b"\x1f\x8b\x08\x04\0\0\0\0\0\xff\x06\0BC\x02\0" + struct.pack("<H", len(d) + 25) + d + struct.pack("<II", zlib.crc32(chunk), len(chunk)))
+        f.write(bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000"))
+    with open(path + ".bai", "wb") as f:
+        f.write(b"BAI\1" + struct.pack("<i", n_ref) + b"".join(struct.pack("<ii", 0, 0) for _ in range(n_ref)) + struct.pack("<Q", 0))
+    return path
+
+
+def subset_bam(src, dst, keep):
+    """Copy of src holding only the records i (file order) with keep[i] true -- what a read filter leaves."""
+    import struct
+    u = oracle_inflate(src)
+    first, refs = header_first_record_offset(u)
+    b = u.tobytes()
+    out = [b[:first]]
+    o, i = first, 0
+    while o + 4 <= len(b):
+        bs = struct.unpack_from("<i", b, o)[0]
+        if o + 4 + bs > len(b):
+            break
+        if keep[i]:
+            out.append(b[o:o + 4 + bs])
+        o += 4 + bs
+        i += 1
+    assert i == len(keep)
+    return write_bgzf(dst, b"".join(out), len(refs))

@@ -1,0 +1,209 @@
+"""CPU-side check of the `-F` filter: the query compiler (sambamba_b200/csrc/host_filter.hpp, grammar of
+sambamba/utils/common/queryparser.d) and the per-record evaluator k2_decode runs (sambamba_b200/csrc/filter.cuh,
+semantics of sambamba/utils/common/filtering.d) compiled for the host, against hand-written Python predicates
+stating what each query means.  No GPU needed."""
+import ctypes as C
+import os
+import random
+import struct
+
+import numpy as np
+import pytest
+
+import helpers
+from helpers import ROOT
+
+
+@pytest.fixture(scope="module")
+def em():
+    L = C.CDLL(os.path.join(ROOT, "tests", "emul", "libemul_filter.so"))
+    L.emul_filter_prog_size.restype = C.c_size_t
+    return L
+
+
+class Rec:
+    __slots__ = ("ref", "pos", "mapq", "flag", "lseq", "mref", "mpos", "tlen", "name", "qual", "tags", "off", "size")
+
+
+def parse_all(u):
+    first, refs = helpers.header_first_record_offset(u)
+    b = u.tobytes()
+    out, o = [], first
+    while o + 4 <= len(b):
+        bs = struct.unpack_from("<i", b, o)[0]
+        if o + 4 + bs > len(b):
+            break
+        r = Rec()
+        r.ref, r.pos, bmn, fnc, r.lseq, r.mref, r.mpos, r.tlen = struct.unpack_from("<iiIIiiii", b, o + 4)
+        ln, r.mapq, r.flag, nc = bmn & 0xFF, (bmn >> 8) & 0xFF, fnc >> 16, fnc & 0xFFFF
+        r.name = b[o + 36:o + 36 + ln - 1]
+        q0 = o + 36 + ln + 4 * nc + (r.lseq + 1) // 2
+        r.qual = b[q0:q0 + r.lseq]
+        r.tags = {}
+        a, end = q0 + r.lseq, o + 4 + bs
+        while a + 3 <= end:
+            tag, ty, v = b[a:a + 2].decode(), chr(b[a + 2]), a + 3
+            if ty in "AcC":
+                n = 1
+            elif ty in "sS":
+                n = 2
+            elif ty in "iIf":
+                n = 4
+            elif ty in "ZH":
+                n = b.index(b"\0", v) - v + 1
+            else:
+                st, cnt = chr(b[v]), struct.unpack_from("<I", b, v + 1)[0]
+                n = 5 + cnt * (1 if st in "cC" else 2 if st in "sS" else 4)
+            val = {"A": lambda: b[v:v + 1], "c": lambda: struct.unpack_from("<b", b, v)[0], "C": lambda: b[v], "s": lambda: struct.unpack_from("<h", b, v)[0],
+                   "S": lambda: struct.unpack_from("<H", b, v)[0], "i": lambda: struct.unpack_from("<i", b, v)[0], "I": lambda: struct.unpack_from("<I", b, v)[0],
+                   "f": lambda: np.float32(struct.unpack_from("<f", b, v)[0]), "Z": lambda: b[v:v + n - 1], "H": lambda: b[v:v + n - 1], "B": lambda: None}[ty]()
+            r.tags.setdefault(tag, (ty, val))
+            a = v + n
+        r.off, r.size = o + 4, bs
+        out.append(r)
+        o += 4 + bs
+    return refs, out
+
+
+def itag(r, t):
+    """IntegerTagFilter's operand: the value if the tag is an integer or float, else None."""
+    ty, v = r.tags.get(t, (None, None))
+    return v if ty in ("c", "C", "s", "S", "i", "I", "f") else None
+
+
+def stag(r, t):
+    ty, v = r.tags.get(t, (None, None))
+    return v if ty in ("Z", "H") else None
+
+
+def avgq(r):
+    s = np.float32(0)
+    for x in r.qual:
+        s = np.float32(s + np.float32(x))
+    with np.errstate(all="ignore"):
+        return np.float32(s) / np.float32(r.lseq)
+
+
+def make_bam(path, seed=3, n=1500):
+    rnd = random.Random(seed)
+    refs = [("c1", 9000), ("c2", 5000), ("weird name", 700)]
+    reads, quals, tags = [], [], []
+    for i in range(n):
+        ref = rnd.randrange(3)
+        L = rnd.choice([0, 20, 35, 50])
+        cig = [(L, 0)] if L else [(10, 0)]
+        pos = rnd.randint(0, refs[ref][1] - 60)
+        flag = 0
+        for bit, pr in ((1, .8), (2, .5), (4, .03), (8, .1), (16, .5), (32, .5), (64, .4), (128, .4), (256, .1), (512, .05), (1024, .1), (2048, .05)):
+            if rnd.random() < pr:
+                flag |= bit
+        name = rnd.choice(["read", "r", "zz", "frag"]) + str(rnd.randint(0, 40))
+        reads.append((ref, pos, rnd.choice([0, 1, 10, 29, 30, 31, 60, 255]), flag, cig, "".join(rnd.choice("ACGT") for _ in range(L)), name))
+        quals.append([rnd.randint(0, 41) for _ in range(L)])
+        t = b""
+        if rnd.random() < .8:
+            k = rnd.random()
+            v = rnd.randint(0, 7)
+            t += b"NM" + (b"C" + bytes([v]) if k < .3 else b"c" + struct.pack("<b", v - 3) if k < .5 else b"i" + struct.pack("<i", v * 1000 - 2000) if k < .7 else b"f" + struct.pack("<f", v / 2.0) if k < .85 else b"Z" + b"x\0")
+        if rnd.random() < .5:
+            t += b"RGZ" + rnd.choice([b"grp1", b"grp2", b"g"]) + b"\0"
+        if rnd.random() < .3:
+            t += b"XTA" + rnd.choice([b"U", b"R"])
+        if rnd.random() < .2:
+            t += b"ZBBs" + struct.pack("<I", 3) + struct.pack("<hhh", 1, 2, 3) + b"ASS" + struct.pack("<H", rnd.randint(0, 60000))
+        tags.append(t)
+    order = sorted(range(n), key=lambda j: (reads[j][0], reads[j][1]))
+    helpers.write_bam(path, refs, [reads[j] for j in order], quals=[quals[j] for j in order], tags=[tags[j] for j in order])
+    # mate fields are -1/-1/0 from write_bam: patch a few through a second pass is not needed -- mate_ref_id == -1 everywhere is itself a case
+    return path
+
+
+QUERIES = [
+    ("mapping_quality > 0 and not duplicate and not failed_quality_control", lambda r: r.mapq > 0 and not r.flag & 0x400 and not r.flag & 0x200),
+    ("mapping_quality >= 30", lambda r: r.mapq >= 30),
+    ("mapping_quality>=30 and(paired or not proper_pair)", lambda r: r.mapq >= 30 and (bool(r.flag & 1) or not r.flag & 2)),
+    ("not (unmapped or mate_is_unmapped) and first_of_pair", lambda r: not (r.flag & 4 or r.flag & 8) and bool(r.flag & 0x40)),
+    ("not unmapped or mate_is_unmapped and first_of_pair", lambda r: (not r.flag & 4) or (bool(r.flag & 8) and bool(r.flag & 0x40))),
+    ("second_of_pair and reverse_strand and not mate_is_reverse_strand", lambda r: bool(r.flag & 0x80) and bool(r.flag & 0x10) and not r.flag & 0x20),
+    ("secondary_alignment or supplementary", lambda r: bool(r.flag & 0x100) or bool(r.flag & 0x800)),
+    ("chimeric", lambda r: bool(r.flag & 1) and not r.flag & 4 and not r.flag & 8 and r.ref != r.mref),
+    ("ref_id == 1 and position < 2000", lambda r: r.ref == 1 and r.pos < 2000),
+    ("position >= 100 and position <= 4000 and ref_id != 2", lambda r: 100 <= r.pos <= 4000 and r.ref != 2),
+    ("sequence_length > 20 and template_length == 0", lambda r: r.lseq > 20 and r.tlen == 0),
+    ("mate_ref_id == -1 and mate_position < 0", lambda r: r.mref == -1 and r.mpos < 0),
+    ("avg_base_quality >= 20", lambda r: bool(avgq(r) >= np.float32(20))),
+    ("not avg_base_quality < 21", lambda r: not bool(avgq(r) < np.float32(21))),
+    ("avg_base_quality != 20", lambda r: bool(avgq(r) != np.float32(20))),
+    ("[NM] == 0", lambda r: itag(r, "NM") is not None and itag(r, "NM") == 0),
+    ("[NM] < 2", lambda r: itag(r, "NM") is not None and itag(r, "NM") < 2),
+    ("[NM] >= 1000 or [AS] > 30000", lambda r: (itag(r, "NM") is not None and itag(r, "NM") >= 1000) or (itag(r, "AS") is not None and itag(r, "AS") > 30000)),
+    ("[NM] != 3", lambda r: itag(r, "NM") is not None and itag(r, "NM") != 3),
+    ("[NM] == null", lambda r: "NM" not in r.tags),
+    ("[RG] != null and [ZB] != null", lambda r: "RG" in r.tags and "ZB" in r.tags),
+    ("[RG] == 'grp1'", lambda r: stag(r, "RG") == b"grp1"),
+    ("[RG] > 'g' and [RG] <= 'grp1'", lambda r: stag(r, "RG") is not None and b"g" < stag(r, "RG") <= b"grp1"),
+    ("[XT] == 'U'", lambda r: r.tags.get("XT", (None, None)) == ("A", b"U")),
+    ("[XT] != 'UU'", lambda r: False),                                        # char tag against a longer string: false whatever the operator
+    ("[NM] == 'x'", lambda r: stag(r, "NM") == b"x"),
+    ("read_name == 'read7'", lambda r: r.name == b"read7"),
+    ("read_name >= 'r' and read_name < 'read3'", lambda r: b"r" <= r.name < b"read3"),
+    ("read_name != 'it\\'s'", lambda r: True),
+    ("strand == '+'", lambda r: not r.flag & 0x10),
+    ("strand != '+' and ref_name == 'c2'", lambda r: bool(r.flag & 0x10) and r.ref == 1),
+    ("ref_name == 'weird name' or ref_name == 'nope'", lambda r: r.ref == 2),
+    ("ref_name != 'nope' and mate_ref_name == '*'", lambda r: r.mref == -1),
+    ("notpaired", lambda r: not r.flag & 1),
+    ("duplicate  and\tnot\nfailed_quality_control", lambda r: bool(r.flag & 0x400) and not r.flag & 0x200),
+    ("((mapping_quality > 10))", lambda r: r.mapq > 10),
+    ("mapping_quality > -1 and position > +5", lambda r: r.pos > 5),
+]
+
+BAD = ["", "mapping_quality", "mapping_quality >", "paired and", "(paired", "paired)", "paired unmapped", "read_name =~ /^r/", "[RG] =~ /x/", "sequence == 'ACGT'",
+       "cigar == '50M'", "ref_name > 'c1'", "mapping_quality == 'x'", "read_name == 5", "position == null", "5 > 3", "not 5", "paired and 5", "frobnicate", "[NMX] == 1",
+       "mapping_quality > 5 > 3"]
+
+
+def compile_q(em, q, refs):
+    prog = (C.c_uint8 * em.emul_filter_prog_size())()
+    err = C.create_string_buffer(512)
+    rc = em.emul_filter_compile(q.encode(), "\n".join(n for n, _ in refs).encode(), prog, err, 512)
+    return rc, prog, err.value.decode()
+
+
+def test_queries_against_python_predicates(em, tmp_path):
+    p = make_bam(str(tmp_path / "f.bam"))
+    u = helpers.oracle_inflate(p)
+    refs, recs = parse_all(u)
+    offs = np.array([r.off for r in recs], np.uint64)
+    sizes = np.array([r.size for r in recs], np.uint32)
+    out = np.zeros(len(recs), np.uint8)
+    for q, fn in QUERIES:
+        rc, prog, err = compile_q(em, q, refs)
+        assert rc == 0, (q, err)
+        em.emul_filter_eval(prog, u.ctypes.data_as(C.c_void_p), offs.ctypes.data_as(C.c_void_p), sizes.ctypes.data_as(C.c_void_p), C.c_uint64(len(recs)), out.ctypes.data_as(C.c_void_p))
+        want = np.array([1 if fn(r) else 0 for r in recs], np.uint8)
+        assert np.array_equal(out, want), (q, int((out != want).sum()), int(want.sum()))
+        if q not in ("read_name != 'it\\'s'", "[XT] != 'UU'", "mapping_quality > -1 and position > +5", "ref_name != 'nope' and mate_ref_name == '*'", "mate_ref_id == -1 and mate_position < 0"):
+            assert 0 < want.sum() < len(recs), (q, "the test data does not exercise this query")
+
+
+def test_malformed_and_unsupported_queries_are_refused(em):
+    for q in BAD:
+        if q == "":
+            continue            # the empty query is NullFilter (filtering.d:41-42), handled before the compiler
+        rc, _, err = compile_q(em, q, [("c1", 1)])
+        assert rc == 1 and err, q
+
+
+def test_prefiltered_input_method(tmp_path):
+    """The GPU tests compare `-F query` on a file with `-F ""` on the file reduced to the kept reads; check that
+    method where the oracle knows both sides: the default filter."""
+    p = make_bam(str(tmp_path / "f.bam"), seed=9, n=800)
+    u = helpers.oracle_inflate(p)
+    _, recs = parse_all(u)
+    q, fn = QUERIES[0]
+    sub = helpers.subset_bam(p, str(tmp_path / "sub.bam"), [bool(fn(r)) for r in recs])
+    for mode in (["base", "-c", "0"], ["window", "-w", "500", "-T", "2"], ["region", "-L", "c1:100-3000", "-T", "1"]):
+        rc1, out1, _ = helpers.oracle_cli(mode + [p])
+        rc2, out2, _ = helpers.oracle_cli(mode + ["-F", "", sub])
+        assert rc1 == 0 and rc2 == 0 and out1 == out2 and len(out1) > 1000, mode
