@@ -133,6 +133,7 @@ struct bdepth {
     bool bai_window_ok = true;            // cleared when the linear index turns out not to describe the file
     bool combined = false;                // --combined: one counter set for all samples
     bool fix_mates = false;               // -m: overlapping mates count once per column (mates.cuh)
+    bool k1_small = false;                // BDEPTH_K1_STREAM_WARPS=4: streaming K1 sub-launches in 4-warp CTAs (experiment)
     bool has_fprog = false; FilterProg fprog; DevBuf fprog_d;      // -F: compiled query (filter.cuh); otherwise mapq_gt / flag_reject
     DevBuf m_hash, m_flag, m_flt, m_ctl;
     uint32_t S = 1;                       // counter sets in the current run (samples, or 1)
@@ -198,6 +199,8 @@ int init_device(bdepth* h) {
     CK(cudaSetDevice(h->device));
     if (!h->s_main) { CK(cudaStreamCreateWithFlags(&h->s_main, cudaStreamNonBlocking)); CK(cudaStreamCreateWithFlags(&h->s_copy, cudaStreamNonBlocking)); CK(cudaStreamCreateWithFlags(&h->s_d2h, cudaStreamNonBlocking)); for (auto& ks : h->s_k1) CK(cudaStreamCreateWithFlags(&ks, cudaStreamNonBlocking)); for (auto& e2 : h->ev) CK(cudaEventCreate(&e2)); }
     CK(cudaFuncSetAttribute(k1_inflate, cudaFuncAttributeMaxDynamicSharedMemorySize, K1_SMEM));
+    { const char* e = getenv("BDEPTH_K1_STREAM_WARPS"); h->k1_small = e && atoi(e) == K1S_WARPS; }      // experiment, see kernels.cuh
+    if (h->k1_small) { CK(cudaFuncSetAttribute(k1_inflate_small, cudaFuncAttributeMaxDynamicSharedMemorySize, K1S_SMEM)); CK(cudaFuncSetAttribute(k1_inflate_small, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)); }
     return 0;
 }
 
@@ -653,7 +656,8 @@ int run_pipeline(bdepth* h, RunMode mode, RunOut* ro, Emitter* em = nullptr) {
                 size_t c1 = h->chunk_end[slot][j]; cudaStream_t ks = h->s_k1[j & 15];
                 CK(cudaStreamWaitEvent(ks, e1, 0)); CK(cudaStreamWaitEvent(ks, h->chunk_ev[slot][j], 0));
                 uint32_t n = (uint32_t)(c1 - c0);
-                k1_inflate<<<(n + 32 * K1_WARPS - 1) / (32 * K1_WARPS), 32 * K1_WARPS, K1_SMEM, ks>>>(d_comp, h->descs.as<BlockDesc>() + (c0 - b), n, u0, h->status.as<int>() + (c0 - b));
+                if (h->k1_small) k1_inflate_small<<<(n + 32 * K1S_WARPS - 1) / (32 * K1S_WARPS), 32 * K1S_WARPS, K1S_SMEM, ks>>>(d_comp, h->descs.as<BlockDesc>() + (c0 - b), n, u0, h->status.as<int>() + (c0 - b));
+                else k1_inflate<<<(n + 32 * K1_WARPS - 1) / (32 * K1_WARPS), 32 * K1_WARPS, K1_SMEM, ks>>>(d_comp, h->descs.as<BlockDesc>() + (c0 - b), n, u0, h->status.as<int>() + (c0 - b));
                 CK(cudaGetLastError()); st.gpu_launches++;
                 if (h->k1_ev.size() <= j) { cudaEvent_t ne; CK(cudaEventCreateWithFlags(&ne, cudaEventDisableTiming)); h->k1_ev.push_back(ne); }
                 CK(cudaEventRecord(h->k1_ev[j], ks));

@@ -64,6 +64,30 @@ __global__ void __launch_bounds__(K1_WARPS * 32, 1) k1_inflate(const uint32_t* _
     if (active) status[b] = rc;
 }
 
+// EXPERIMENT (off by default, BDEPTH_K1_STREAM_WARPS=4): the same lane logic in 4-warp CTAs, three of which fit one SM
+// (3 x 70,656 B of shared memory).  When the input is streaming in, a K1 sub-launch of one H2D chunk is 208 warps:
+// as 16 CTAs of 13 warps it fills 16 SMs to the brim and every lane runs at the full-SM pace (~50 ms per block)
+// while 130 SMs idle; as 52 CTAs of 4 warps the block scheduler spreads it over 52 SMs with one warp per
+// scheduler, where a lane runs at close to its lone pace (26.7 ms), and SMs only fill up as later chunks arrive.
+// Same total throughput once the GPU is full (12 instead of 13 warps per SM), shorter drain after the last byte.
+// Never measured: DESIGN.md section 10.
+constexpr int K1S_WARPS = 4;
+constexpr int K1S_SMEM = K1S_WARPS * SMEM_BYTES_PER_WARP;       // 70,656 B
+__global__ void __launch_bounds__(K1S_WARPS * 32, 3) k1_inflate_small(const uint32_t* __restrict__ comp, const BlockDesc* __restrict__ blocks,
+                                                                      uint32_t n_blocks, uint8_t* __restrict__ u, int* __restrict__ status) {
+    extern __shared__ uint32_t smem[];
+    uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t b = (blockIdx.x * K1S_WARPS + warp) * 32u + lane;
+    uint32_t scratch[96];
+    const bool active = b < n_blocks;
+    BlockDesc d = active ? blocks[b] : BlockDesc{0, 0, 0, 0};
+    uint32_t* wbase = smem + warp * (SMEM_BYTES_PER_WARP / 4);
+    SmemTab tab{wbase + lane, (uint32_t)__cvta_generic_to_shared(wbase + T_WORDS * 32) + lane * 16, (uint32_t)__cvta_generic_to_shared(wbase + T_FAR * 32 + lane)};
+    ByteOut out{u};
+    int rc = inflate_block(tab, comp, d.coff, d.csize, out, d.uoff, d.isize, scratch, active);
+    if (active) status[b] = rc;
+}
+
 // ------------------------------------------------------------------------------------- K2
 // Unaligned little-endian loads from the inflated stream: two aligned 32-bit loads + funnel shift (records are
 // byte-aligned; four byte loads per field made k2_decode LSU-queue bound: profiles/r1_k2_k3_ncu_full_summary.txt).
