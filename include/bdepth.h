@@ -148,8 +148,8 @@ int bdepth_set_min_baseq(bdepth_t* h, uint32_t min_base_quality);
 /* -m / --fix-mate-overlaps (depth.d:1133; detectOverlappingMates :319-388, selectBetterMate :391-399, the -m branches
  * of writeColumn :521-530 and PerRegionPrinter.push :760-845): where two reads of one name (same sample) overlap,
  * every column counts only the better mate.  Available for bdepth_run_base / _run_base_text / _run_regions /
- * _run_resident on one rank; the whole (shard of the) file is then processed as one batch.  bdepth_run_windows
- * returns BDEPTH_ERR_ARG with it.  Names with three or more overlapping reads follow the reference's
+ * _run_windows (overlap 0 only) / _run_resident on one rank; the whole (shard of the) file is then processed as one
+ * batch.  bdepth_run_windows with an overlap returns BDEPTH_ERR_ARG with it.  Names with three or more overlapping reads follow the reference's
  * detected/past state machine in base mode and are refused (BDEPTH_ERR_ARG) in region mode and where the reference's
  * outcome depends on unrelated reads of the column (depth.d:380-384). */
 int bdepth_set_fix_mates(bdepth_t* h, int on);

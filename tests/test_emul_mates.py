@@ -502,3 +502,28 @@ def test_generated_pairs_with_real_cigar_mix(em, tmp_path):
         assert np.array_equal(c[0], want)
     regs = [(0, 100, 900), (0, 1000, 1200), (0, 1200, 1207), (1, 10, 20), (2, 5, 40000)]
     check_regions(em, p, regs, [3, 10], 0, tmp_path)
+
+
+@pytest.mark.parametrize("seed,w", [(31, 100), (32, 333), (33, 64), (34, 1000)])
+def test_pairs_window_mode_without_overlap(em, tmp_path, seed, w):
+    """`depth window -w W -m` with --overlap 0: one ring slot, every column lies in the window being filled, windows
+    follow each other like sorted adjacent regions (first_occ is set again when a window is finished, depth.d:962-972)."""
+    p = make_pairs_bam(str(tmp_path / f"win{seed}.bam"), seed, n_frag=500)
+    soa = Soa(p)
+    for minq in (0, 20):
+        args = ["window", "-w", str(w), "-m", "--combined", "-T", "2", "-T", "6"] + (["-q", str(minq)] if minq else []) + [p]
+        rc, out, err = helpers.oracle_cli(args)
+        assert rc == 0, err
+        want = [l.split("\t") for l in out.decode().split("\n")[1:] if l]
+        regs = []
+        for ref, (_, ln) in enumerate(soa.refs):
+            regs += [(ref, k * w, (k + 1) * w) for k in range(ln // w)]
+        extra = [(ref, (ln // w) * w, (ln // w + 1) * w) for ref, (_, ln) in enumerate(soa.refs)]      # the partial window at the end of a reference is a segment too (never printed)
+        allr = regs + extra
+        segs = [(soa.lin0[r] + a, soa.lin0[r] + min(b, soa.refs[r][1])) for r, a, b in allr]
+        counts = soa.plain_counts(1, minq)
+        rc, stat, sreads, smb, e = run_emul(em, soa, counts, 1, minq=minq, segs=segs)
+        assert rc == 0, e
+        got = region_rows(soa, counts, regs, [2, 6], sreads, smb, minq, 1)
+        got = [[x for x in g if x is not None] for g in got]
+        assert got == want

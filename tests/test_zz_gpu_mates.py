@@ -109,5 +109,14 @@ def test_groups_and_refusals(tmp_path, pairs):
         rc, _, err = helpers.run_cli(["region", "-m", "-L", "c1:1-4000", p])
         assert rc == 1 and b"only pairs are supported" in err
     assert done >= 2
-    rc, _, err = helpers.run_cli(["window", "-w", "100", "-m", pairs[0]])
-    assert rc == 1 and b"window mode" in err
+    rc, _, err = helpers.run_cli(["window", "-w", "100", "--overlap", "50", "-m", pairs[0]])
+    assert rc == 1 and b"overlapping windows" in err
+
+
+def test_window_mode_without_overlap(pairs, tmp_path):
+    import test_emul_mates as tem
+    p = pairs[0]
+    for args in (["window", "-w", "1000", "-m", p], ["window", "-w", "777", "-m", "-T", "3", "-T", "9", "-q", "20", p], ["window", "-w", "64", "-m", "--combined", "-a", "-c", "5", p]):
+        check_same(args)
+    q = tem.make_pairs_bam(str(tmp_path / "w.bam"), 41, n_frag=500)
+    check_same(["window", "-w", "100", "-m", "-T", "2", q])
