@@ -832,6 +832,7 @@ int run_pipeline(bdepth* h, RunMode mode, RunOut* ro, Emitter* em = nullptr) {
             else k_read_segments<false><<<(unsigned)((R + 127) / 128), 128, 0, sm>>>(soa, u0, (uint32_t)R, h->seg.s.as<uint64_t>(), h->seg.e.as<uint64_t>(), h->seg.pmax.as<uint64_t>(), h->seg.id.as<uint32_t>(), h->seg.has_min ? h->seg.minstart.as<uint64_t>() : nullptr, h->seg.n, h->seg.reads.as<uint32_t>(), 0, h->S, h->seg.has_min ? h->seg.bases_reads.as<uint32_t>() : nullptr);
             CK(cudaGetLastError()); st.gpu_launches++;
         }
+        uint64_t idx_tiles_base = 0; uint32_t idx_n_tiles = 0;      // K3's per-tile read index of this sub-batch (the mate kernels look reads up through it)
         // ---- K3
         if (mode == RUN_FULL && ss.n_pass) {
             uint64_t gmin = ss.min_start, gmax = ss.max_end;
@@ -844,6 +845,7 @@ int run_pipeline(bdepth* h, RunMode mode, RunOut* ro, Emitter* em = nullptr) {
             }
             uint64_t t_lo = (gmin - h->cnt_base) / TILE_POS, t_hi = (gmax - h->cnt_base + TILE_POS - 1) / TILE_POS;
             uint64_t n_tiles = t_hi - t_lo; uint64_t tiles_base = h->cnt_base + t_lo * TILE_POS;
+            idx_tiles_base = tiles_base; idx_n_tiles = (uint32_t)n_tiles;
             if (t_hi * TILE_POS > h->win_len) return fail(h, BDEPTH_ERR_FORMAT, "read extends past the end of the reference space");
             CK(h->tile_first.ensure((n_tiles + 2) * 4)); CK(h->tile_lo.ensure((n_tiles + 2) * 4));
             k_fill_u32<<<(unsigned)((n_tiles + 2 + 255) / 256), 256, 0, sm>>>(h->tile_first.as<uint32_t>(), (uint32_t)R, n_tiles + 2);
@@ -879,7 +881,8 @@ int run_pipeline(bdepth* h, RunMode mode, RunOut* ro, Emitter* em = nullptr) {
             MateParams mp{soa.start, soa.span, soa.meta, soa.off, soa.ncl, soa.lseq, u0, (uint32_t)R, h->m_hash.as<uint64_t>(), h->m_flag.as<uint32_t>(),
                           h->m_flt.as<uint64_t>(), h->m_flt.as<uint64_t>() + n_flt, n_flt, h->counts.as<uint32_t>(), h->cnt_base, h->win_len, h->S, h->minq,
                           segm ? h->seg.s.as<uint64_t>() : nullptr, segm ? h->seg.e.as<uint64_t>() : nullptr, segm ? h->seg.pmax.as<uint64_t>() : nullptr, segm ? h->seg.id.as<uint32_t>() : nullptr,
-                          segm ? h->seg.n : 0u, segm ? h->seg.reads.as<uint32_t>() : nullptr, segm ? h->seg.mbases.as<uint32_t>() : nullptr, h->S, 0,
+                          segm ? h->seg.n : 0u, segm ? h->seg.reads.as<uint32_t>() : nullptr, segm ? h->seg.mbases.as<uint32_t>() : nullptr, h->S,
+                          h->tile_lo.as<uint32_t>(), idx_tiles_base, idx_n_tiles, h->long_list.as<uint32_t>(), (uint32_t)ss.n_long, 0,
                           (int*)h->m_ctl.p, (unsigned long long*)((uint8_t*)h->m_ctl.p + 16)};
             const unsigned mg = (unsigned)((R + 127) / 128);
             km_hash<<<mg, 128, 0, sm>>>(mp); km_link<<<mg, 128, 0, sm>>>(mp); km_fix<<<mg, 128, 0, sm>>>(mp);
@@ -889,8 +892,6 @@ int run_pipeline(bdepth* h, RunMode mode, RunOut* ro, Emitter* em = nullptr) {
             CK(cudaMemcpyAsync(&ctl, h->m_ctl.p, sizeof ctl, cudaMemcpyDeviceToHost, sm));
             CK(cudaStreamSynchronize(sm));
             if (ctl.err[0] == MATE_ERR_TOO_MANY) return fail(h, BDEPTH_ERR_ARG, "fix-mate-overlaps: more than %d overlapping reads share one name (record #%d of the batch)", MATE_MAX_MEMBERS, ctl.err[1]);
-            if (ctl.err[0] == MATE_ERR_AMBIGUOUS) return fail(h, BDEPTH_ERR_ARG, "fix-mate-overlaps: four or more overlapping reads of one name around read #%d: the reference's result there depends on unrelated reads of the column (depth.d:380-384) and is not reproduced", ctl.err[1]);
-            if (ctl.err[0] == MATE_ERR_REGION_GROUP) return fail(h, BDEPTH_ERR_ARG, "fix-mate-overlaps in region mode: three or more overlapping reads share one name (around read #%d); only pairs are supported there", ctl.err[1]);
             st.mate_pairs = ctl.stat[0]; st.mate_pair_columns = ctl.stat[1]; st.mate_groups = ctl.stat[2];
             { float t = 0; CK(cudaEventElapsedTime(&t, em0, em1)); st.ms_mates = t; }
         }

@@ -36,7 +36,7 @@
 namespace bdk {
 
 constexpr int MATE_MAX_MEMBERS = 8;
-enum MateErr : int { MATE_OK = 0, MATE_ERR_TOO_MANY = 1, MATE_ERR_AMBIGUOUS = 2, MATE_ERR_REGION_GROUP = 3 };
+enum MateErr : int { MATE_OK = 0, MATE_ERR_TOO_MANY = 1 };
 enum MateFlag : uint32_t { MF_INSTREAM = 1u, MF_HAS_PRED = 2u, MF_HAS_SUCC = 4u };
 
 struct MateParams {
@@ -53,6 +53,9 @@ struct MateParams {
     // has on top of the A/C/G/T/N planes
     const uint64_t* seg_s; const uint64_t* seg_e; const uint64_t* seg_pmax; const uint32_t* seg_id; uint32_t n_seg;
     uint32_t* seg_reads; uint32_t* seg_mbases; uint32_t n_samples_out;
+    // K3's read index, for the one question that needs the other reads of a column (mate_follows): per 1024-position
+    // tile the first passing short read overlapping it, and the list of long reads
+    const uint32_t* tile_lo; uint64_t tiles_base; uint32_t n_tiles; const uint32_t* long_list; uint32_t n_long;
     int force_general;           // tests: send pairs through the state-machine path as well
     int* err;                    // err[0] = MateErr, err[1] = record index
     unsigned long long* stat;    // [0] pairs, [1] (pair, column) fixes, [2] components with more than two members
@@ -240,16 +243,49 @@ BD_HD void mate_fix_pair(const MateParams& p, const MRead& A, const MRead& B) {
     if (p.n_seg) mate_pair_regions(p, A, B);
 }
 
+// Is a read with a larger name hash present in column g?  Then a read of hash h is not the last entry of the column's
+// hash-sorted array (depth.d:380-384 treats the last entry differently).  Same search as k3_gather: the short reads from
+// the tile's first overlapping one up to the last that starts at or before g, plus the long reads.
+BD_HD bool mate_follows(const MateParams& p, uint64_t h, uint64_t g) {
+    if (g >= p.tiles_base) {
+        uint64_t t = (g - p.tiles_base) >> 10;
+        if (t < p.n_tiles) {
+            uint32_t lo = p.tile_lo[t];
+            if (lo != 0xFFFFFFFFu)
+                for (uint32_t k = lo; k < p.R && p.start[k] <= g; k++)
+                    if ((p.meta[k] & 3u) == 1u && (p.mflag[k] & MF_INSTREAM) && p.start[k] + p.span[k] > g && p.mhash[k] > h) return true;
+        }
+    }
+    for (uint32_t i = 0; i < p.n_long; i++) {
+        uint32_t k = p.long_list[i];
+        if ((p.mflag[k] & MF_INSTREAM) && p.start[k] <= g && p.start[k] + p.span[k] > g && p.mhash[k] > h) return true;
+    }
+    return false;
+}
+
 // Three or more overlapping reads of one name hash: replay detectOverlappingMates for this name column by column.
 // In a column the present reads of the name are adjacent in the hash-sorted array, in file order; neighbours pair up
 // (first with second, third with fourth); a read that was flagged before and is alone again becomes `past`.  A read
-// in state `detected` is skipped by the plain loop, every pair adds its better mate (depth.d:521-530) -- so a `past`
-// read that pairs again counts twice, as in the reference.
+// in state `detected` / `fixed` is skipped by the plain loop, every pair adds its better mate (depth.d:521-530) -- so a
+// `past` read that pairs again counts twice, as in the reference.
+//
+// Region mode (n_seg > 0) replays PerRegionPrinter.push (depth.d:760-845) for the members as well and books the
+// difference between what the reference accumulates and what the reducers will compute from the counters and the
+// plain per-read count:
+//   reference  countRead of a member in the first column of the region it is present in (not if `fixed` by then),
+//              countPreviouslySeenMateOverlaps in the region's first column, uncountOverlappingMates for pairs not yet
+//              `fixed`, one base per column for a `past` member / a pair's better mate whose quality reaches -q
+//              (255 on D/N); pair members become `fixed` after a column that lies in a region;
+//   reducers   n_bases = A/C/G/T/N counters of the region's columns, n_reads = members with a counted base in it.
+// Nothing here needs reads outside the component: a member that started before a region is present in the region's
+// first column, so that column is the region's first visited one.
 BD_HD void mate_fix_group(const MateParams& p, const uint32_t* idx, int n, uint32_t leader) {
-    MRead M[MATE_MAX_MEMBERS]; MCur C[MATE_MAX_MEMBERS]; uint8_t st[MATE_MAX_MEMBERS];
+    MRead M[MATE_MAX_MEMBERS]; MCur C[MATE_MAX_MEMBERS]; uint8_t st[MATE_MAX_MEMBERS];      // 0 none, 1 detected, 2 fixed, 3 past
     uint64_t lo = ~0ull, hi = 0;
     for (int k = 0; k < n; k++) { m_load(p, idx[k], M[k]); st[k] = 0; if (M[k].s < lo) lo = M[k].s; if (M[k].e > hi) hi = M[k].e; }
-    unsigned long long cols = 0, pairs_seen = 0;
+    unsigned long long cols = 0;
+    uint32_t seg_hi = 0;
+    if (p.n_seg) { uint32_t l = 0, h2 = p.n_seg; while (l < h2) { uint32_t mid = (l + h2) >> 1; if (p.seg_s[mid] < hi) l = mid + 1; else h2 = mid; } seg_hi = l; }   // segments starting before the component ends
     for (uint64_t g = lo; g < hi; g++) {
         int pres[MATE_MAX_MEMBERS], kind[MATE_MAX_MEMBERS]; uint32_t q[MATE_MAX_MEMBERS]; int np = 0;
         for (int k = 0; k < n; k++) if (g >= M[k].s && g < M[k].e) { q[k] = 0; kind[k] = m_at(M[k], C[k], (uint32_t)(g - M[k].s), &q[k]); pres[np++] = k; }
@@ -263,22 +299,61 @@ BD_HD void mate_fix_group(const MateParams& p, const uint32_t* idx, int n, uint3
             }
             int a = pres[i];
             if (st[a]) {
-                // Alone again.  If it is the last entry of the column's whole sorted array and its predecessor has the same
-                // hash, the reference leaves a `detected` read as it is (depth.d:380-384) -- that depends on every other
-                // read of the column; refuse rather than guess.
-                if (np >= 2 && st[a] == 1) m_err(p, MATE_ERR_AMBIGUOUS, leader); else st[a] = 3;
+                // Alone again: `past` -- unless it is the very last entry of the column's sorted array and its predecessor has
+                // the same hash; then the reference leaves it as it is (depth.d:380-384).
+                if (!(np >= 2 && st[a] != 3 && !mate_follows(p, p.mhash[idx[a]], g))) st[a] = 3;
             }
             i += 1;
         }
-        for (int i = 0; i < np; i++) { int k = pres[i]; if (st[k] == 1) m_count(p, m_planes(p, M[k].sample), m_plane(M[k], kind[k], q[k], p.minq), g, 0xFFFFFFFFu); }
+        int win[MATE_MAX_MEMBERS / 2];
+        for (int i = 0; i < np; i++) { int k = pres[i]; if (st[k] == 1 || st[k] == 2) m_count(p, m_planes(p, M[k].sample), m_plane(M[k], kind[k], q[k], p.minq), g, 0xFFFFFFFFu); }
         for (int j = 0; j < npairs; j++) {
-            int a = pa[j], b = pb[j]; bool fw = m_first_wins(M[a], kind[a], q[a], M[b], kind[b], q[b]); int w = fw ? a : b;
+            int a = pa[j], b = pb[j]; bool fw = m_first_wins(M[a], kind[a], q[a], M[b], kind[b], q[b]); int w = fw ? a : b; win[j] = w;
             m_count(p, m_planes(p, M[w].sample), m_plane(M[w], kind[w], q[w], p.minq), g, 1u);
         }
-        cols += (unsigned long long)npairs; pairs_seen += npairs ? 1 : 0;
+        cols += (unsigned long long)npairs;
+        if (p.n_seg) {
+            bool in_region = false;
+            for (int64_t k = (int64_t)seg_hi - 1; k >= 0; k--) {
+                if (p.seg_pmax[k] <= g) break;
+                const uint64_t a = p.seg_s[k], b = p.seg_e[k];
+                if (g < a || g >= b) continue;
+                in_region = true;
+                const uint64_t slot = p.seg_id[k];
+#define M_SAMP(X) ((uint64_t)(p.n_samples_out > 1 ? M[X].sample : 0u) * p.n_seg + slot)
+                for (int i = 0; i < np; i++) {               // countRead where the member enters the region
+                    int x = pres[i];
+                    if (g != (a > M[x].s ? a : M[x].s)) continue;
+                    uint32_t f = mate_full(M[x], a, b, p.minq);
+                    if (f) m_add(&p.seg_reads[M_SAMP(x)], 0xFFFFFFFFu);                         // the plain count had it as a read of its own
+                    if (st[x] != 2) { m_add(&p.seg_mbases[M_SAMP(x)], f); if (f) m_add(&p.seg_reads[M_SAMP(x)], 1u); }
+                }
+                for (int j = 0; j < npairs; j++) {
+                    int x = pa[j], y = pb[j];
+                    uint32_t fx = mate_full(M[x], a, b, p.minq), fy = mate_full(M[y], a, b, p.minq);
+                    if (g == a && st[x] == 2) { if (fx + fy) m_add(&p.seg_reads[M_SAMP(x)], 1u); }     // countPreviouslySeenMateOverlaps
+                    if (!(st[x] == 2 && st[y] == 2)) {                                                     // uncountOverlappingMates
+                        uint32_t nx = M[x].s == g ? fx : mate_full(M[x], a > g ? a : g, b, p.minq), ny = M[y].s == g ? fy : mate_full(M[y], a > g ? a : g, b, p.minq);
+                        m_add(&p.seg_mbases[M_SAMP(x)], 0u - (nx + ny));
+                        m_add(&p.seg_reads[M_SAMP(x)], 0u - (uint32_t)((fx > 0) + (fy > 0)) + (uint32_t)(fx + fy > 0));
+                    }
+                }
+                for (int i = 0; i < np; i++) {               // per column: what the reference adds, minus what the counters hold
+                    int x = pres[i]; int pl = m_plane(M[x], kind[x], q[x], p.minq);
+                    if (st[x] == 3 && m_qual(M[x], kind[x], q[x]) >= p.minq) m_add(&p.seg_mbases[M_SAMP(x)], 1u);
+                    if ((st[x] == 0 || st[x] == 3) && pl >= 0 && pl <= 4) m_add(&p.seg_mbases[M_SAMP(x)], 0xFFFFFFFFu);
+                }
+                for (int j = 0; j < npairs; j++) {
+                    int w = win[j]; int pl = m_plane(M[w], kind[w], q[w], p.minq);
+                    if (m_qual(M[w], kind[w], q[w]) >= p.minq) m_add(&p.seg_mbases[M_SAMP(w)], 1u);
+                    if (pl >= 0 && pl <= 4) m_add(&p.seg_mbases[M_SAMP(w)], 0xFFFFFFFFu);
+                }
+#undef M_SAMP
+            }
+            if (in_region) for (int j = 0; j < npairs; j++) { st[pa[j]] = 2; st[pb[j]] = 2; }
+        }
     }
     m_stat(&p.stat[1], cols); m_stat(&p.stat[2], 1);
-    (void)pairs_seen;
 }
 
 BD_HD void mate_fix_one(const MateParams& p, uint32_t r) {
@@ -298,9 +373,7 @@ BD_HD void mate_fix_one(const MateParams& p, uint32_t r) {
         return;
     }
     if (n < 2) return;
-    if (p.n_seg && n > 2) { m_err(p, MATE_ERR_REGION_GROUP, r); return; }
     mate_fix_group(p, idx, n, r);
-    if (p.n_seg && n == 2) { MRead A, B; m_load(p, idx[0], A); m_load(p, idx[1], B); if (m_same_name(A, B)) mate_pair_regions(p, A, B); }
 }
 
 #if defined(__CUDACC__)

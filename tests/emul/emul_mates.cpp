@@ -16,8 +16,18 @@ extern "C" int emul_mates(const uint8_t* u, uint32_t R, const uint64_t* start, c
                           uint32_t* seg_reads, uint32_t* seg_mbases, uint32_t n_samples_out, int force_general, int order, int* err2, unsigned long long* stat3) {
     std::vector<uint64_t> mhash(R ? R : 1); std::vector<uint32_t> mflag(R ? R : 1);
     err2[0] = err2[1] = 0; stat3[0] = stat3[1] = stat3[2] = 0;
+    // K3's read index as k3_tile_index / k2_decode build it (kernels.cuh): passing short reads per 1024-position tile, long-read list
+    uint64_t gmin = ~0ull, gmax = 0;
+    for (uint32_t r = 0; r < R; r++) if (meta[r] & 1u) { gmin = std::min(gmin, start[r]); gmax = std::max(gmax, start[r] + span[r]); }
+    uint64_t tiles_base = gmin == ~0ull ? 0 : gmin / 1024 * 1024; uint32_t n_tiles = gmin == ~0ull ? 0 : (uint32_t)((gmax - tiles_base + 1023) / 1024);
+    std::vector<uint32_t> tile_lo(n_tiles + 2, 0xFFFFFFFFu), long_list;
+    for (uint32_t r = 0; r < R; r++) {
+        if ((meta[r] & 3u) == 3u) long_list.push_back(r);
+        if ((meta[r] & 3u) == 1u) for (uint64_t t = (start[r] - tiles_base) / 1024; t <= (start[r] + span[r] - 1 - tiles_base) / 1024 && t < n_tiles; t++) tile_lo[t] = std::min(tile_lo[t], r);
+    }
     MateParams p{start, span, meta, off, ncl, lseq, u, R, mhash.data(), mflag.data(), flt_s, flt_e, n_flt, counts, cnt_base, win_len, S, minq,
-                 seg_s, seg_e, seg_pmax, seg_id, n_seg, seg_reads, seg_mbases, n_samples_out, force_general, err2, stat3};
+                 seg_s, seg_e, seg_pmax, seg_id, n_seg, seg_reads, seg_mbases, n_samples_out,
+                 tile_lo.data(), tiles_base, n_tiles, long_list.data(), (uint32_t)long_list.size(), force_general, err2, stat3};
     std::vector<uint32_t> ord(R); std::iota(ord.begin(), ord.end(), 0u);
     if (order == 1) std::reverse(ord.begin(), ord.end());
     if (order == 2) { uint64_t s = 88172645463325252ull; for (uint32_t i = R; i > 1; i--) { s ^= s << 13; s ^= s >> 7; s ^= s << 17; std::swap(ord[i - 1], ord[s % i]); } }

@@ -93,22 +93,16 @@ def test_multi_sample_pairs(tmp_path):
     check_same(["region", "-m", "-L", "c1:100-900", "-T", "2", p])
 
 
-def test_groups_and_refusals(tmp_path, pairs):
+def test_groups_of_three_and_more(tmp_path, pairs):
+    """Supplementary alignments sharing a name: the per-name replay of the reference's state machine, base and region mode."""
     import test_emul_mates as tem
-    import sambamba_b200 as sb
-    done = 0
     for seed in range(10, 16):
         p = tem.make_pairs_bam(str(tmp_path / f"tri{seed}.bam"), seed, n_frag=120, triples=0.5)
-        rc, out, err = helpers.run_cli(["base", "-m", "-c", "0", "--combined", p])
-        if rc == 1 and b"depends on unrelated reads" in err:
-            continue
-        assert rc == 0, err
-        rc2, out2, _ = helpers.oracle_cli(["base", "-m", "-c", "0", "--combined", p])
-        assert out == out2
-        done += 1
-        rc, _, err = helpers.run_cli(["region", "-m", "-L", "c1:1-4000", p])
-        assert rc == 1 and b"only pairs are supported" in err
-    assert done >= 2
+        check_same(["base", "-m", "-c", "0", "--combined", p])
+        check_same(["region", "-m", "-L", "c1:1-4000", "-T", "2", p])
+        bed = tmp_path / f"b{seed}.bed"
+        bed.write_text("".join(f"c1\t{a}\t{a + w}\n" for a, w in ((50, 7), (57, 200), (300, 1), (400, 90), (490, 600), (1500, 30))) + "c2\t10\t2000\n")
+        check_same(["region", "-m", "-L", str(bed), "-T", "1", "-T", "4", p])
     rc, _, err = helpers.run_cli(["window", "-w", "100", "--overlap", "50", "-m", pairs[0]])
     assert rc == 1 and b"overlapping windows" in err
 
