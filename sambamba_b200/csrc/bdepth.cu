@@ -134,6 +134,7 @@ struct bdepth {
     bool combined = false;                // --combined: one counter set for all samples
     bool fix_mates = false;               // -m: overlapping mates count once per column (mates.cuh)
     bool k1_small = false;                // BDEPTH_K1_STREAM_WARPS=4: streaming K1 sub-launches in 4-warp CTAs (experiment)
+    bool k3_pre = false;                  // BDEPTH_K3_PREFETCH=1: k3_gather with lane-parallel record prefetch (experiment)
     bool has_fprog = false; FilterProg fprog; DevBuf fprog_d;      // -F: compiled query (filter.cuh); otherwise mapq_gt / flag_reject
     DevBuf m_hash, m_flag, m_flt, m_ctl;
     uint32_t S = 1;                       // counter sets in the current run (samples, or 1)
@@ -200,6 +201,7 @@ int init_device(bdepth* h) {
     if (!h->s_main) { CK(cudaStreamCreateWithFlags(&h->s_main, cudaStreamNonBlocking)); CK(cudaStreamCreateWithFlags(&h->s_copy, cudaStreamNonBlocking)); CK(cudaStreamCreateWithFlags(&h->s_d2h, cudaStreamNonBlocking)); for (auto& ks : h->s_k1) CK(cudaStreamCreateWithFlags(&ks, cudaStreamNonBlocking)); for (auto& e2 : h->ev) CK(cudaEventCreate(&e2)); }
     CK(cudaFuncSetAttribute(k1_inflate, cudaFuncAttributeMaxDynamicSharedMemorySize, K1_SMEM));
     { const char* e = getenv("BDEPTH_K1_STREAM_WARPS"); h->k1_small = e && atoi(e) == K1S_WARPS; }      // experiment, see kernels.cuh
+    { const char* e = getenv("BDEPTH_K3_PREFETCH"); h->k3_pre = e && atoi(e) == 1; }
     if (h->k1_small) { CK(cudaFuncSetAttribute(k1_inflate_small, cudaFuncAttributeMaxDynamicSharedMemorySize, K1S_SMEM)); CK(cudaFuncSetAttribute(k1_inflate_small, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)); }
     return 0;
 }
@@ -859,8 +861,11 @@ int run_pipeline(bdepth* h, RunMode mode, RunOut* ro, Emitter* em = nullptr) {
                     else k3_scatter_long<false><<<(unsigned)((ss.n_long * 32 + 255) / 256), 256, 0, sm>>>(soa, u0, h->long_list.as<uint32_t>(), (uint32_t)ss.n_long, h->cnt_base, h->win_len, cnt, 0, sel);
                     CK(cudaGetLastError()); st.gpu_launches++;
                 }
-                if (h->minq) k3_gather<true><<<(unsigned)n_tiles, 256, 0, sm>>>(soa, u0, tiles_base, h->cnt_base, h->win_len, h->tile_first.as<uint32_t>(), h->tile_lo.as<uint32_t>(), cnt, h->minq, sel);
-                else k3_gather<false><<<(unsigned)n_tiles, 256, 0, sm>>>(soa, u0, tiles_base, h->cnt_base, h->win_len, h->tile_first.as<uint32_t>(), h->tile_lo.as<uint32_t>(), cnt, 0, sel);
+                if (h->k3_pre) {       // experiment, see kernels.cuh
+                    if (h->minq) k3_gather<true, true><<<(unsigned)n_tiles, 256, 0, sm>>>(soa, u0, tiles_base, h->cnt_base, h->win_len, h->tile_first.as<uint32_t>(), h->tile_lo.as<uint32_t>(), cnt, h->minq, sel);
+                    else k3_gather<false, true><<<(unsigned)n_tiles, 256, 0, sm>>>(soa, u0, tiles_base, h->cnt_base, h->win_len, h->tile_first.as<uint32_t>(), h->tile_lo.as<uint32_t>(), cnt, 0, sel);
+                } else if (h->minq) k3_gather<true, false><<<(unsigned)n_tiles, 256, 0, sm>>>(soa, u0, tiles_base, h->cnt_base, h->win_len, h->tile_first.as<uint32_t>(), h->tile_lo.as<uint32_t>(), cnt, h->minq, sel);
+                else k3_gather<false, false><<<(unsigned)n_tiles, 256, 0, sm>>>(soa, u0, tiles_base, h->cnt_base, h->win_len, h->tile_first.as<uint32_t>(), h->tile_lo.as<uint32_t>(), cnt, 0, sel);
                 CK(cudaGetLastError()); st.gpu_launches++;
             }
         }

@@ -360,7 +360,12 @@ __device__ __forceinline__ void add_base(GatherAcc& a, int j, const uint8_t* seq
     else a.nN[j]++;
 }
 
-template <bool MINQ>
+// PRE (EXPERIMENT, off by default, BDEPTH_K3_PREFETCH=1): the lane that holds candidate read base+i also loads that
+// read's off / ncl / lseq / first CIGAR word, 32 reads per load instruction, and the per-read step takes them by
+// shuffle.  Without it every selected read costs a chain of four dependent global loads (off -> ncl/lseq -> CIGAR
+// word -> sequence bytes) that all 32 lanes wait for: ~56 reads per warp x ~2 us; the kernel's 7.4 ms is about what
+// that latency chain predicts at 32 resident warps per SM.  Never measured: DESIGN.md section 10.
+template <bool MINQ, bool PRE>
 __global__ void __launch_bounds__(256) k3_gather(RecordSoA soa, const uint8_t* __restrict__ u, uint64_t tiles_base, uint64_t cnt_base, uint64_t win_len,
                                                   const uint32_t* __restrict__ tile_first, const uint32_t* __restrict__ tile_lo,
                                                   uint32_t* __restrict__ counts, uint32_t minq, int sample_sel) {
@@ -378,10 +383,12 @@ __global__ void __launch_bounds__(256) k3_gather(RecordSoA soa, const uint8_t* _
     for (uint32_t base = lo; base < hi; base += 32) {
         uint32_t r = base + lane;
         uint64_t s = 0; uint32_t sp = 0; bool ov = false;
+        int64_t off_l = 0; uint32_t ncl_l = 0, lseq_l = 0, c0_l = 0;
         if (r < hi) {
             s = soa.start[r]; sp = soa.span[r];
             uint32_t mt = soa.meta[r];
             ov = (mt & 3u) == 1u && (sample_sel < 0 || (int)((mt >> 2) & 63u) == sample_sel) && s < w1 && s + sp > w0;
+            if (PRE && ov) { off_l = soa.off[r]; ncl_l = soa.ncl[r]; lseq_l = (uint32_t)max(soa.lseq[r], 0); c0_l = ldu32(u + off_l + 32 + (ncl_l & 0xFF)); }
         }
         // reads are sorted by start: once the first lane of a group starts at or past w1, we are done
         uint64_t s_first = __shfl_sync(0xFFFFFFFFu, s, 0);
@@ -392,14 +399,16 @@ __global__ void __launch_bounds__(256) k3_gather(RecordSoA soa, const uint8_t* _
             uint32_t rr = base + bsel;
             uint64_t rs = __shfl_sync(0xFFFFFFFFu, s, bsel);
             uint32_t rspan = __shfl_sync(0xFFFFFFFFu, sp, bsel);
-            int64_t off = soa.off[rr]; uint32_t ncl = soa.ncl[rr]; uint32_t lseq = (uint32_t)max(soa.lseq[rr], 0);
+            int64_t off; uint32_t ncl, lseq;
+            if (PRE) { off = __shfl_sync(0xFFFFFFFFu, off_l, bsel); ncl = __shfl_sync(0xFFFFFFFFu, ncl_l, bsel); lseq = __shfl_sync(0xFFFFFFFFu, lseq_l, bsel); }
+            else { off = soa.off[rr]; ncl = soa.ncl[rr]; lseq = (uint32_t)max(soa.lseq[rr], 0); }
             uint32_t n_cigar = ncl >> 8, l_name = ncl & 0xFF;
             const uint8_t* rec = u + off;
             const uint8_t* cg = rec + 32 + l_name;
             const uint8_t* seq = cg + 4u * n_cigar;
             const uint8_t* qual = seq + (lseq + 1) / 2;
             const int32_t rp = (int32_t)((int64_t)p0 - (int64_t)rs);      // reference offset of this lane's first position (|rp| < span + 128)
-            const uint32_t c0 = ldu32(cg);
+            const uint32_t c0 = PRE ? __shfl_sync(0xFFFFFFFFu, c0_l, bsel) : ldu32(cg);
             if (n_cigar == 1 && cig_match(c0 & 15)) {
                 // ---- fast path (90 % of short reads): one M/=/X op.  The 4 bases of this lane sit in at most 3
                 // sequence bytes: one unaligned 32-bit load, nibbles picked by shifts.
