@@ -278,6 +278,9 @@ def main():
     h = sb.BDepth(memory=img, bai=bai, device=local_rank)          # session setup (BGZF index, header, buffers) is outside the steps
     if world > 1:
         h.set_shard(rank, world, fresh_uid())
+    chunk_blocks = int(os.environ.get("BDEPTH_BENCH_CHUNK_BLOCKS", "0"))       # tuning sweep: BGZF blocks per H2D chunk = per K1 sub-launch = per sub-batch
+    if chunk_blocks:
+        h.set_tuning(0, chunk_blocks)
     open_s = time.perf_counter() - t0
     cold_s = None
     n_w = max(1, min(a.warmup, 3))
@@ -314,7 +317,8 @@ def main():
         "e2e": {"value": file_bytes / 1e9 / e2e_s, "unit": "GB/s", "h2d_bytes_per_step": int(h2d_total), "d2h_bytes_per_step": int(d2h_total),
                 "ms_per_step": e2e_s * 1e3, "covered_mbases_per_s": covered / 1e6 / e2e_s, "first_call_incl_open_ms": cold_s * 1e3,
                 "device_ms": {k: e2e_stats[k] for k in ("ms_h2d", "ms_inflate", "ms_scan", "ms_coverage", "ms_d2h", "ms_span_device")},
-                "path": "bdepth_open_memory(pinned host BAM image) + bdepth_run_base -> 7 x u32 counters in pinned host memory", "host_input": host_kind},
+                "path": "bdepth_open_memory(pinned host BAM image) + bdepth_run_base -> 7 x u32 counters in pinned host memory", "host_input": host_kind, "chunk_blocks": chunk_blocks or "default (6656)",
+                "variants": {k: os.environ[k] for k in ("BDEPTH_K1_STREAM_WARPS", "BDEPTH_K3_PREFETCH") if k in os.environ}},
         "gpu_launches": int(total_launches),
         "roofline": {"kernel": "k1_inflate (lane-per-BGZF-block DEFLATE)", "bound": "hbm", "achieved": k1_bytes / 1e9 / (k1_ms / 1e3), "peak": peak, "unit": "GB/s",
                      "frac": k1_bytes / 1e9 / (k1_ms / 1e3) / peak, "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH if (a.gpus == 1 and a.reads_per_unit == READS_PER_UNIT) else None,

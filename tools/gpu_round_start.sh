@@ -14,6 +14,10 @@ timeout 900 python bench.py --steps 5 --warmup 3 > $OUT/bench_n1.json 2> $OUT/be
 # 3. K1 experiment: 4-warp CTAs for the streaming sub-launches (kernels.cuh k1_inflate_small); compare e2e.ms_per_step
 BDEPTH_K1_STREAM_WARPS=4 timeout 900 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > $OUT/bench_n1_k1small.json 2> $OUT/bench_n1_k1small.err
 BDEPTH_K3_PREFETCH=1 timeout 900 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > $OUT/bench_n1_k3pre.json 2> $OUT/bench_n1_k3pre.err      # compare stage_ms.k3_coverage
+for cb in 1664 3328 13312; do       # H2D chunk / sub-batch size sweep (default 6656 blocks), with and without the 4-warp CTAs
+  BDEPTH_BENCH_CHUNK_BLOCKS=$cb timeout 600 python bench.py --steps 3 --warmup 2 --no-cpu-baseline > $OUT/bench_n1_cb$cb.json 2> $OUT/bench_n1_cb$cb.err
+  BDEPTH_BENCH_CHUNK_BLOCKS=$cb BDEPTH_K1_STREAM_WARPS=4 timeout 600 python bench.py --steps 3 --warmup 2 --no-cpu-baseline > $OUT/bench_n1_cb${cb}_k1small.json 2> $OUT/bench_n1_cb${cb}_k1small.err
+done
 # 4. -m on the bench workload with real pairs: cost of km_hash / km_link / km_fix (ms_mates) next to K3
 timeout 900 python - > $OUT/mates_probe.log 2>&1 <<'PY'
 import os, sys, json
@@ -31,4 +35,4 @@ with sb.BDepth(p) as b:
 PY
 # 5. launch list of one staged pass (cold-cache, serialised: compare shares, not absolutes)
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline > $OUT/ncu_bench.log 2>&1
-tail -3 $OUT/pytest_gpu.log; cat $OUT/bench_n1.json | head -c 600; echo; grep -o '"e2e": {"value": [0-9.]*' $OUT/bench_n1.json $OUT/bench_n1_k1small.json; grep -o '"k3_coverage": [0-9.]*' $OUT/bench_n1.json $OUT/bench_n1_k3pre.json
+tail -3 $OUT/pytest_gpu.log; cat $OUT/bench_n1.json | head -c 600; echo; grep -o '"e2e": {"value": [0-9.]*' $OUT/bench_n1*.json; grep -o '"k3_coverage": [0-9.]*' $OUT/bench_n1.json $OUT/bench_n1_k3pre.json
