@@ -168,7 +168,7 @@ struct bdepth {
     HostScratch hs;
     std::vector<uint32_t> ref_has_host;
     // ---- optional per-read segment counting (window / region front ends), device arrays
-    struct SegSet { bool on = false; uint32_t n = 0; bool has_min = false; DevBuf s, e, pmax, id, reads, minstart, bases_reads, mbases; } seg;
+    struct SegSet { bool on = false; uint32_t n = 0; bool has_min = false, has_u = false; uint64_t ext_max = 0; DevBuf s, e, pmax, id, reads, minstart, bases_reads, mbases, ustart; } seg;
     // ---- results
     bdepth_stats st{}; std::string err;
 };
@@ -887,6 +887,7 @@ int run_pipeline(bdepth* h, RunMode mode, RunOut* ro, Emitter* em = nullptr) {
                           h->m_flt.as<uint64_t>(), h->m_flt.as<uint64_t>() + n_flt, n_flt, h->counts.as<uint32_t>(), h->cnt_base, h->win_len, h->S, h->minq,
                           segm ? h->seg.s.as<uint64_t>() : nullptr, segm ? h->seg.e.as<uint64_t>() : nullptr, segm ? h->seg.pmax.as<uint64_t>() : nullptr, segm ? h->seg.id.as<uint32_t>() : nullptr,
                           segm ? h->seg.n : 0u, segm ? h->seg.reads.as<uint32_t>() : nullptr, segm ? h->seg.mbases.as<uint32_t>() : nullptr, h->S,
+                          segm && h->seg.has_u ? h->seg.ustart.as<uint64_t>() : nullptr, segm && h->seg.has_u && h->seg.has_min ? h->seg.minstart.as<uint64_t>() : nullptr, segm && h->seg.has_u ? h->seg.ext_max : 0ull,
                           h->tile_lo.as<uint32_t>(), idx_tiles_base, idx_n_tiles, h->long_list.as<uint32_t>(), (uint32_t)ss.n_long, 0,
                           (int*)h->m_ctl.p, (unsigned long long*)((uint8_t*)h->m_ctl.p + 16)};
             const unsigned mg = (unsigned)((R + 127) / 128);
@@ -995,7 +996,7 @@ void bdepth_close(bdepth_t* h) {
     for (DevBuf* b : bufs) b->release();
     h->rg_ids.release(); h->rg_offs.release(); h->rg_samp.release();
     h->text[0].release(); h->text[1].release(); h->text_tiles.release(); h->text_offs.release(); h->text_zero.release();
-    h->seg.s.release(); h->seg.e.release(); h->seg.pmax.release(); h->seg.id.release(); h->seg.reads.release(); h->seg.minstart.release(); h->seg.bases_reads.release(); h->seg.mbases.release();
+    h->seg.s.release(); h->seg.e.release(); h->seg.pmax.release(); h->seg.id.release(); h->seg.reads.release(); h->seg.minstart.release(); h->seg.bases_reads.release(); h->seg.mbases.release(); h->seg.ustart.release();
     h->m_hash.release(); h->m_flag.release(); h->m_flt.release(); h->m_ctl.release(); h->fprog_d.release();
     if (h->comm) { nccl().CommDestroy(h->comm); h->comm = nullptr; }
     if (h->pinned) cudaFreeHost(h->pinned);
@@ -1259,10 +1260,13 @@ static int run_segments(bdepth* h, const std::vector<SegDef>& segs, const uint32
     // sorted view for the per-read kernel
     std::vector<uint32_t> order(n); for (size_t i = 0; i < n; i++) order[i] = (uint32_t)i;
     std::sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return a[x] != a[y] ? a[x] < a[y] : x < y; });
-    std::vector<uint64_t> ss(n), se(n), pm(n), ms(n); uint64_t mx = 0; bool has_min = false;
+    std::vector<uint64_t> ss(n), se(n), pm(n), ms(n), us(n); uint64_t mx = 0, ext_max = 0; bool has_min = false, has_u = false;
     for (size_t i = 0; i < n; i++) {
         ss[i] = a[order[i]]; se[i] = b[order[i]]; mx = std::max(mx, se[i]); pm[i] = mx;
         const SegDef& sd = segs[order[i]]; ms[i] = sd.min_read_start ? h->hdr.ref_lin0[sd.ref] + sd.min_read_start : 0; has_min |= ms[i] != 0;
+        // first column in which the reference updates this slot (thresholds and, with -m, the per-column terms start there)
+        uint64_t sc = sd.start - std::min(sd.cov_ext, sd.start);
+        us[i] = std::min(ss[i], h->hdr.ref_lin0[sd.ref] + std::min<uint64_t>(sc, h->hdr.ref_len[sd.ref])); has_u |= sd.cov_ext != 0 || sd.min_read_start != 0; ext_max = std::max<uint64_t>(ext_max, ss[i] - us[i]);
     }
     auto& S = h->seg;
     size_t nn = n ? n : 1;
@@ -1273,7 +1277,8 @@ static int run_segments(bdepth* h, const std::vector<SegDef>& segs, const uint32
     }
     CK(cudaMemset(S.reads.p, 0, NS * nn * 4)); CK(cudaMemset(S.bases_reads.p, 0, NS * nn * 4)); CK(cudaMemset(S.mbases.p, 0, NS * nn * 4));
     if (n) CK(cudaMemcpy(S.minstart.p, ms.data(), n * 8, cudaMemcpyHostToDevice));
-    S.has_min = has_min;
+    CK(S.ustart.ensure(nn * 8)); if (n) CK(cudaMemcpy(S.ustart.p, us.data(), n * 8, cudaMemcpyHostToDevice));
+    S.has_min = has_min; S.has_u = has_u; S.ext_max = ext_max;
     S.on = true; S.n = (uint32_t)n;
     rc = run_pipeline(h, RUN_FULL, nullptr);
     S.on = false;
@@ -1343,11 +1348,8 @@ static int deliver_one(bdepth* h, const SegDef& sd, size_t i, size_t n, size_t n
 
 int bdepth_run_windows(bdepth_t* h, uint32_t window, uint32_t overlap, const uint32_t* thr, size_t n_thr, bdepth_stat_cb cb, void* user) {
     if (window == 0) return fail(h, BDEPTH_ERR_ARG, "positive window size must be specified");
-    // -m: with --overlap 0 there is one ring slot, every column lies in the window being filled and windows follow each other
-    // like sorted adjacent regions (mate_pair_regions applies as it is).  Overlapping windows update slots whose window does
-    // not contain the column (depth.d:215-226), which also leaks the per-column -m terms: not derived yet.
-    if (h->fix_mates && overlap != 0) return fail(h, BDEPTH_ERR_ARG, "fix-mate-overlaps with overlapping windows is not available in the GPU engine yet (use --overlap 0)");
-    if (overlap >= window) return fail(h, BDEPTH_ERR_ARG, "specified overlap is larger than window size");
+    // -m: a window is a segment with an update range (ring slots are updated before their window begins when the step does
+    // not divide the window) and, for reference 0's first slots, without a first occurrence; mates.cuh replays both.
     const uint32_t step = window - overlap;
     const uint32_t nslot = (window + step - 1) / step;          // ring slots of PerWindowPrinter (depth.d:1026-1029)
     const uint32_t ext = nslot * step - window;                  // a slot reused for window m >= nslot starts collecting

@@ -7,7 +7,7 @@
 // D binding that would replace this file is in sambamba_b200/d/bdepth.d and INTEGRATION.md.
 //
 // Not supported through the GPU path yet (rejected with a message, never silently wrong):
-//   -F with regular expressions or sequence / cigar comparisons ; -m with --overlap > 0 ; several BAM files ; more than 64 samples without --combined.
+//   -F with regular expressions or sequence / cigar comparisons ; several BAM files ; more than 64 samples without --combined.
 #include <math.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -259,7 +259,6 @@ int main(int argc, char** argv) {
             if (!(overlap < window)) return die("specified overlap is larger than window size");
         }
     }
-    if (fix_mates && c.mode == 2 && overlap != 0) return die("-m/--fix-mate-overlaps with overlapping windows is not available in the GPU engine yet");
     int mapq_gt = 0; uint32_t flag_reject = 0x600;
     if (a.v.size() < 2) return die("no input BAM given");
     if (a.v.size() > 2) return die("several BAM files: not available in the GPU engine yet");

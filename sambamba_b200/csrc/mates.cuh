@@ -53,6 +53,11 @@ struct MateParams {
     // has on top of the A/C/G/T/N planes
     const uint64_t* seg_s; const uint64_t* seg_e; const uint64_t* seg_pmax; const uint32_t* seg_id; uint32_t n_seg;
     uint32_t* seg_reads; uint32_t* seg_mbases; uint32_t n_samples_out;
+    // overlapping windows (nullptr / 0 otherwise): a ring slot is updated from seg_u[k] <= seg_s[k] on (the reference
+    // updates all slots once position >= window, depth.d:215-226, so the per-column terms of a window start collecting
+    // before the window does), and reference 0's first slots only ever count reads that start at or after seg_qmin[k]
+    // (is_first_occurrence starts false, depth.d:1031-1032).  Same order as seg_s.
+    const uint64_t* seg_u; const uint64_t* seg_qmin; uint64_t seg_ext_max;
     // K3's read index, for the one question that needs the other reads of a column (mate_follows): per 1024-position
     // tile the first passing short read overlapping it, and the list of long reads
     const uint32_t* tile_lo; uint64_t tiles_base; uint32_t n_tiles; const uint32_t* long_list; uint32_t n_long;
@@ -285,7 +290,7 @@ BD_HD void mate_fix_group(const MateParams& p, const uint32_t* idx, int n, uint3
     for (int k = 0; k < n; k++) { m_load(p, idx[k], M[k]); st[k] = 0; if (M[k].s < lo) lo = M[k].s; if (M[k].e > hi) hi = M[k].e; }
     unsigned long long cols = 0;
     uint32_t seg_hi = 0;
-    if (p.n_seg) { uint32_t l = 0, h2 = p.n_seg; while (l < h2) { uint32_t mid = (l + h2) >> 1; if (p.seg_s[mid] < hi) l = mid + 1; else h2 = mid; } seg_hi = l; }   // segments starting before the component ends
+    if (p.n_seg) { uint32_t l = 0, h2 = p.n_seg; while (l < h2) { uint32_t mid = (l + h2) >> 1; if (p.seg_s[mid] < hi + p.seg_ext_max) l = mid + 1; else h2 = mid; } seg_hi = l; }   // segments that are updated before the component ends
     for (uint64_t g = lo; g < hi; g++) {
         int pres[MATE_MAX_MEMBERS], kind[MATE_MAX_MEMBERS]; uint32_t q[MATE_MAX_MEMBERS]; int np = 0;
         for (int k = 0; k < n; k++) if (g >= M[k].s && g < M[k].e) { q[k] = 0; kind[k] = m_at(M[k], C[k], (uint32_t)(g - M[k].s), &q[k]); pres[np++] = k; }
@@ -317,21 +322,26 @@ BD_HD void mate_fix_group(const MateParams& p, const uint32_t* idx, int n, uint3
             for (int64_t k = (int64_t)seg_hi - 1; k >= 0; k--) {
                 if (p.seg_pmax[k] <= g) break;
                 const uint64_t a = p.seg_s[k], b = p.seg_e[k];
-                if (g < a || g >= b) continue;
+                const uint64_t ua = p.seg_u ? p.seg_u[k] : a;                            // first column in which the slot is updated
+                const uint64_t qmin = p.seg_qmin ? p.seg_qmin[k] : 0;                    // != 0: the slot never sees a first occurrence
+                if (g < ua || g >= b) continue;
                 in_region = true;
+                const bool in_w = g >= a, quirk = qmin != 0;
                 const uint64_t slot = p.seg_id[k];
 #define M_SAMP(X) ((uint64_t)(p.n_samples_out > 1 ? M[X].sample : 0u) * p.n_seg + slot)
                 for (int i = 0; i < np; i++) {               // countRead where the member enters the region
                     int x = pres[i];
-                    if (g != (a > M[x].s ? a : M[x].s)) continue;
+                    if (g != (ua > M[x].s ? ua : M[x].s)) continue;
+                    if (quirk && M[x].s < qmin) continue;                                       // present before the slot's first update: never handed to countRead, not in the plain count either
                     uint32_t f = mate_full(M[x], a, b, p.minq);
                     if (f) m_add(&p.seg_reads[M_SAMP(x)], 0xFFFFFFFFu);                         // the plain count had it as a read of its own
+                    if (quirk) m_add(&p.seg_mbases[M_SAMP(x)], 0u - f);                         // ... and, for such a slot, its bases (k_read_segments' own sum)
                     if (st[x] != 2) { m_add(&p.seg_mbases[M_SAMP(x)], f); if (f) m_add(&p.seg_reads[M_SAMP(x)], 1u); }
                 }
                 for (int j = 0; j < npairs; j++) {
                     int x = pa[j], y = pb[j];
                     uint32_t fx = mate_full(M[x], a, b, p.minq), fy = mate_full(M[y], a, b, p.minq);
-                    if (g == a && st[x] == 2) { if (fx + fy) m_add(&p.seg_reads[M_SAMP(x)], 1u); }     // countPreviouslySeenMateOverlaps
+                    if (g == ua && !quirk && st[x] == 2) { if (fx + fy) m_add(&p.seg_reads[M_SAMP(x)], 1u); }     // countPreviouslySeenMateOverlaps
                     if (!(st[x] == 2 && st[y] == 2)) {                                                     // uncountOverlappingMates
                         uint32_t nx = M[x].s == g ? fx : mate_full(M[x], a > g ? a : g, b, p.minq), ny = M[y].s == g ? fy : mate_full(M[y], a > g ? a : g, b, p.minq);
                         m_add(&p.seg_mbases[M_SAMP(x)], 0u - (nx + ny));
@@ -341,12 +351,12 @@ BD_HD void mate_fix_group(const MateParams& p, const uint32_t* idx, int n, uint3
                 for (int i = 0; i < np; i++) {               // per column: what the reference adds, minus what the counters hold
                     int x = pres[i]; int pl = m_plane(M[x], kind[x], q[x], p.minq);
                     if (st[x] == 3 && m_qual(M[x], kind[x], q[x]) >= p.minq) m_add(&p.seg_mbases[M_SAMP(x)], 1u);
-                    if ((st[x] == 0 || st[x] == 3) && pl >= 0 && pl <= 4) m_add(&p.seg_mbases[M_SAMP(x)], 0xFFFFFFFFu);
+                    if (in_w && !quirk && (st[x] == 0 || st[x] == 3) && pl >= 0 && pl <= 4) m_add(&p.seg_mbases[M_SAMP(x)], 0xFFFFFFFFu);
                 }
                 for (int j = 0; j < npairs; j++) {
                     int w = win[j]; int pl = m_plane(M[w], kind[w], q[w], p.minq);
                     if (m_qual(M[w], kind[w], q[w]) >= p.minq) m_add(&p.seg_mbases[M_SAMP(w)], 1u);
-                    if (pl >= 0 && pl <= 4) m_add(&p.seg_mbases[M_SAMP(w)], 0xFFFFFFFFu);
+                    if (in_w && !quirk && pl >= 0 && pl <= 4) m_add(&p.seg_mbases[M_SAMP(w)], 0xFFFFFFFFu);
                 }
 #undef M_SAMP
             }
@@ -367,7 +377,7 @@ BD_HD void mate_fix_one(const MateParams& p, uint32_t r) {
         idx[n++] = k;
         uint64_t e = p.start[k] + p.span[k]; if (e > reach) reach = e;
     }
-    if (n == 2 && !p.force_general) {
+    if (n == 2 && !p.force_general && !p.seg_u) {
         MRead A, B; m_load(p, idx[0], A); m_load(p, idx[1], B);
         if (m_same_name(A, B)) mate_fix_pair(p, A, B);
         return;

@@ -13,7 +13,8 @@ extern "C" int emul_mates(const uint8_t* u, uint32_t R, const uint64_t* start, c
                           const uint32_t* ncl, const int32_t* lseq, const uint64_t* flt_s, const uint64_t* flt_e, uint32_t n_flt,
                           uint32_t* counts, uint64_t cnt_base, uint64_t win_len, uint32_t S, uint32_t minq,
                           const uint64_t* seg_s, const uint64_t* seg_e, const uint64_t* seg_pmax, const uint32_t* seg_id, uint32_t n_seg,
-                          uint32_t* seg_reads, uint32_t* seg_mbases, uint32_t n_samples_out, int force_general, int order, int* err2, unsigned long long* stat3) {
+                          uint32_t* seg_reads, uint32_t* seg_mbases, uint32_t n_samples_out, int force_general, int order, int* err2, unsigned long long* stat3,
+                          const uint64_t* seg_u, const uint64_t* seg_qmin, uint64_t seg_ext_max) {
     std::vector<uint64_t> mhash(R ? R : 1); std::vector<uint32_t> mflag(R ? R : 1);
     err2[0] = err2[1] = 0; stat3[0] = stat3[1] = stat3[2] = 0;
     // K3's read index as k3_tile_index / k2_decode build it (kernels.cuh): passing short reads per 1024-position tile, long-read list
@@ -26,7 +27,7 @@ extern "C" int emul_mates(const uint8_t* u, uint32_t R, const uint64_t* start, c
         if ((meta[r] & 3u) == 1u) for (uint64_t t = (start[r] - tiles_base) / 1024; t <= (start[r] + span[r] - 1 - tiles_base) / 1024 && t < n_tiles; t++) tile_lo[t] = std::min(tile_lo[t], r);
     }
     MateParams p{start, span, meta, off, ncl, lseq, u, R, mhash.data(), mflag.data(), flt_s, flt_e, n_flt, counts, cnt_base, win_len, S, minq,
-                 seg_s, seg_e, seg_pmax, seg_id, n_seg, seg_reads, seg_mbases, n_samples_out,
+                 seg_s, seg_e, seg_pmax, seg_id, n_seg, seg_reads, seg_mbases, n_samples_out, seg_u, seg_qmin, seg_ext_max,
                  tile_lo.data(), tiles_base, n_tiles, long_list.data(), (uint32_t)long_list.size(), force_general, err2, stat3};
     std::vector<uint32_t> ord(R); std::iota(ord.begin(), ord.end(), 0u);
     if (order == 1) std::reverse(ord.begin(), ord.end());

@@ -59,8 +59,6 @@ def test_cli_usage_and_argument_errors_need_no_gpu():
     assert rc == 1 and b"positive window size must be specified" in err
     rc, out, err = helpers.run_cli(["depth", "window", "-w", "10", "--overlap", "10", "x.bam"])
     assert rc == 1 and b"specified overlap is larger than window size" in err
-    rc, out, err = helpers.run_cli(["depth", "window", "-w", "10", "--overlap", "5", "-m", "x.bam"])
-    assert rc == 1 and b"overlapping windows is not available in the GPU engine yet" in err
     rc, out, err = helpers.run_cli(["depth", "base", "/nonexistent/x.bam"])
     assert rc == 1 and b"Cannot open file" in err
 

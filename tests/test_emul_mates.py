@@ -168,7 +168,7 @@ class Soa:
         return n
 
 
-def run_emul(em, soa, counts, S, minq=0, flt=None, segs=None, n_samples_out=1, force_general=0, order=0, cnt_base=0):
+def run_emul(em, soa, counts, S, minq=0, flt=None, segs=None, n_samples_out=1, force_general=0, order=0, cnt_base=0, seg_u=None, seg_qmin=None, ext_max=0):
     """counts: [S, 7, total] (modified in place).  flt: merged linear (start, end) list.  segs: linear (start, end) list in
     output order.  Returns (err, stats, seg_reads_delta [n_samples_out, n_seg], seg_mbases)."""
     fs = np.array([x[0] for x in (flt or [])], np.uint64)
@@ -179,6 +179,8 @@ def run_emul(em, soa, counts, S, minq=0, flt=None, segs=None, n_samples_out=1, f
     se = np.array([segs[i][1] for i in order_idx], np.uint64)
     pm = np.maximum.accumulate(se) if n_seg else np.zeros(0, np.uint64)
     sid = np.array(order_idx, np.uint32)
+    su = np.array([seg_u[i] for i in order_idx], np.uint64) if seg_u is not None else None
+    sq = np.array([seg_qmin[i] for i in order_idx], np.uint64) if seg_qmin is not None else None
     sreads = np.zeros((n_samples_out, max(n_seg, 1)), np.uint32)
     smb = np.zeros((n_samples_out, max(n_seg, 1)), np.uint32)
     err = (C.c_int * 2)()
@@ -188,7 +190,8 @@ def run_emul(em, soa, counts, S, minq=0, flt=None, segs=None, n_samples_out=1, f
                        _ptr(soa.ncl, U32P), _ptr(soa.lseq, I32P), _ptr(fs, U64P), _ptr(fe, U64P), C.c_uint32(len(fs)),
                        _ptr(counts, U32P), C.c_uint64(cnt_base), C.c_uint64(counts.shape[2]), C.c_uint32(S), C.c_uint32(minq),
                        _ptr(ss, U64P), _ptr(se, U64P), _ptr(pm, U64P), _ptr(sid, U32P), C.c_uint32(n_seg), _ptr(sreads, U32P), _ptr(smb, U32P),
-                       C.c_uint32(n_samples_out), C.c_int(force_general), C.c_int(order), err, stat)
+                       C.c_uint32(n_samples_out), C.c_int(force_general), C.c_int(order), err, stat,
+                       _ptr(su, U64P) if seg_u is not None else C.cast(None, U64P), _ptr(sq, U64P) if seg_qmin is not None else C.cast(None, U64P), C.c_uint64(ext_max))
     return rc, list(stat), sreads.view(np.int32)[:, :n_seg], smb.view(np.int32)[:, :n_seg], (err[0], err[1])      # corrections are signed (the library adds them modulo 2^32)
 
 
@@ -563,3 +566,95 @@ def test_region_mode_groups_of_three_and_more(em, tmp_path):
     rnd = random.Random(77)
     regs = [(rnd.randrange(2), a, a + rnd.choice([5, 60, 300])) for a in (rnd.randint(0, 2000) for _ in range(30))]
     check_regions(em, p, regs, [2], 0, tmp_path)
+
+
+def window_segments(soa, w, overlap):
+    """The slots bdepth_run_windows defines (bdepth.cu): per reference max(n_full + nslot, n_empty) windows k*step, with the
+    early-update extent of reused ring slots and the first-occurrence quirk of reference 0's first slots."""
+    step = w - overlap
+    nslot = (w + step - 1) // step
+    ext = nslot * step - w
+    segs, n_full = [], []
+    for r, (_, L) in enumerate(soa.refs):
+        nf = (L - w) // step + 1 if L >= w else 0
+        n_full.append(nf)
+        for k in range(max(nf + nslot, L // step)):
+            segs.append(dict(ref=r, start=k * step, end=k * step + w, cov_ext=ext if k >= nslot else 0, qmin=k * step if (r == 0 and 1 <= k < nslot) else 0))
+    return segs, n_full, step
+
+
+def window_rows(soa, counts, segs, n_full, thr, sreads, smb, minq):
+    """Rows of `depth window` for references that all have reads, as run_segments + the reducers compute them: bases over
+    the window, thresholds from the slot's first updated column, reads starting at/after qmin for the quirk slots."""
+    rows, i0 = [], 0
+    per_ref = {}
+    for i, sd in enumerate(segs):
+        per_ref.setdefault(sd["ref"], []).append(i)
+    for r, idxs in per_ref.items():
+        L, l0 = soa.refs[r][1], soa.lin0[r]
+        for i in idxs[:n_full[r]]:
+            sd = segs[i]
+            a, b = l0 + min(sd["start"], L), l0 + min(sd["end"], L)
+            ac = l0 + min(sd["start"] - min(sd["cov_ext"], sd["start"]), L)
+            if sd["qmin"]:
+                nb, nr = 0, 0
+                for start, span, sample, cig, sq, ql, lseq, ok in soa.recs:
+                    if not ok or start < l0 + sd["qmin"] or start >= b or start + span <= a:
+                        continue
+                    rp = qp = n = 0
+                    for c in cig:
+                        ln, op = c >> 4, c & 15
+                        if op in (0, 7, 8):
+                            for k in range(ln):
+                                g = start + rp + k
+                                if a <= g < b and rp + k < span and qp + k < lseq and soa.u[ql + qp + k] >= minq:
+                                    n += 1
+                            rp += ln
+                            qp += ln
+                        elif op in (2, 3):
+                            rp += ln
+                        elif op in (1, 4):
+                            qp += ln
+                    nb += n
+                    nr += n > 0
+            else:
+                nb = int(counts[0, :5, a:b].sum())
+                nr = sum(soa.read_hits(a, b, minq).values())
+            nb = (nb + int(smb[0, i])) & 0xFFFFFFFF
+            nr = (nr + int(sreads[0, i])) & 0xFFFFFFFF
+            cov = counts[0, :, ac:b].sum(axis=0)
+            ln = np.float32(sd["end"] - sd["start"])
+            f = [soa.refs[r][0], str(sd["start"]), str(sd["end"]), str(nr), _fmt_g(np.float32(nb) / ln)]
+            for t in thr:
+                f.append("100" if t == 0 else _fmt_g(np.float32(int((cov >= t).sum())) * np.float32(100) / ln))
+            rows.append(f)
+    return rows
+
+
+@pytest.mark.parametrize("seed,w,overlap", [(51, 100, 50), (52, 100, 30), (53, 90, 80), (54, 333, 100), (55, 64, 63)])
+def test_overlapping_windows(em, tmp_path, seed, w, overlap):
+    """`depth window --overlap` with and without -m.  Without -m this checks the test's own statement of what the library
+    computes for ring slots (early threshold collection, first-occurrence quirk); with -m the per-name replay adds its terms."""
+    p = make_pairs_bam(str(tmp_path / f"ow{seed}.bam"), seed, n_frag=300, refs=(("c1", 2200), ("c2", 1300)), triples=0.2 if seed % 2 else 0.0)
+    soa = Soa(p)
+    segs, n_full, step = window_segments(soa, w, overlap)
+    lin = [(soa.lin0[s["ref"]] + min(s["start"], soa.refs[s["ref"]][1]), soa.lin0[s["ref"]] + min(s["end"], soa.refs[s["ref"]][1])) for s in segs]
+    us = [min(a, soa.lin0[s["ref"]] + min(s["start"] - min(s["cov_ext"], s["start"]), soa.refs[s["ref"]][1])) for s, (a, _) in zip(segs, lin)]
+    qm = [soa.lin0[s["ref"]] + s["qmin"] if s["qmin"] else 0 for s in segs]
+    for minq in (0, 20):
+        base_args = ["window", "-w", str(w), "--overlap", str(overlap), "--combined", "-T", "2", "-T", "5"] + (["-q", str(minq)] if minq else [])
+        # without -m: zero corrections
+        rc, out, err = helpers.oracle_cli(base_args + [p])
+        assert rc == 0, err
+        want = [l.split("\t") for l in out.decode().split("\n")[1:] if l]
+        counts = soa.plain_counts(1, minq)
+        z = np.zeros((1, len(segs)), np.int64)
+        assert window_rows(soa, counts, segs, n_full, [2, 5], z, z, minq) == want
+        # with -m
+        rc, out, err = helpers.oracle_cli(base_args + ["-m", p])
+        assert rc == 0, err
+        want = [l.split("\t") for l in out.decode().split("\n")[1:] if l]
+        rc, stat, sreads, smb, e = run_emul(em, soa, counts, 1, minq=minq, segs=lin, seg_u=us, seg_qmin=qm, ext_max=max(a - u for (a, _), u in zip(lin, us)), order=seed % 3)
+        assert rc == 0, e
+        got = window_rows(soa, counts, segs, n_full, [2, 5], sreads, smb, minq)
+        assert got == want

@@ -103,14 +103,16 @@ def test_groups_of_three_and_more(tmp_path, pairs):
         bed = tmp_path / f"b{seed}.bed"
         bed.write_text("".join(f"c1\t{a}\t{a + w}\n" for a, w in ((50, 7), (57, 200), (300, 1), (400, 90), (490, 600), (1500, 30))) + "c2\t10\t2000\n")
         check_same(["region", "-m", "-L", str(bed), "-T", "1", "-T", "4", p])
-    rc, _, err = helpers.run_cli(["window", "-w", "100", "--overlap", "50", "-m", pairs[0]])
-    assert rc == 1 and b"overlapping windows" in err
 
 
-def test_window_mode_without_overlap(pairs, tmp_path):
+def test_window_mode(pairs, tmp_path):
     import test_emul_mates as tem
     p = pairs[0]
     for args in (["window", "-w", "1000", "-m", p], ["window", "-w", "777", "-m", "-T", "3", "-T", "9", "-q", "20", p], ["window", "-w", "64", "-m", "--combined", "-a", "-c", "5", p]):
         check_same(args)
-    q = tem.make_pairs_bam(str(tmp_path / "w.bam"), 41, n_frag=500)
+    q = tem.make_pairs_bam(str(tmp_path / "w.bam"), 41, n_frag=500, triples=0.2)
     check_same(["window", "-w", "100", "-m", "-T", "2", q])
+    # overlapping windows: ring slots updated before their window begins, first-occurrence quirk of reference 0
+    for w, o in ((100, 50), (100, 30), (90, 80), (64, 63)):
+        check_same(["window", "-w", str(w), "--overlap", str(o), "-m", "-T", "2", "-T", "5", q])
+    check_same(["window", "-w", "1000", "--overlap", "300", "-m", "-T", "3", p])
