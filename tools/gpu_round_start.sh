@@ -7,7 +7,7 @@ set -u
 OUT=gpurun_out/round_start; mkdir -p $OUT
 python -c "import __graft_entry__ as g; g.build(quiet=True)" > $OUT/build.log 2>&1
 # 1. the whole GPU suite; -rxX lists the non-gating tests (xfail / XPASS) of test_zz_gpu_*.py with their outcome
-timeout 1500 python -m pytest tests -m gpu -q -rxX -p no:cacheprovider > $OUT/pytest_gpu.log 2>&1; echo "pytest exit $?" >> $OUT/pytest_gpu.log
+BDEPTH_FULLSIZE=1 timeout 2400 python -m pytest tests -m gpu -q -rxXs -p no:cacheprovider > $OUT/pytest_gpu.log 2>&1; echo "pytest exit $?" >> $OUT/pytest_gpu.log
 # 2. smoke + headline bench (N = 1)
 timeout 300 python __graft_entry__.py smoke > $OUT/smoke.log 2>&1
 timeout 900 python bench.py --steps 5 --warmup 3 > $OUT/bench_n1.json 2> $OUT/bench_n1.err
