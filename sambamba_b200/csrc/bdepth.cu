@@ -6,7 +6,7 @@
 //   ->  K2 decode (SoA)  ->  K3 tile index / long-read scatter / per-position gather
 // then reducers + D2H for the chosen front end (base tiles, window stats, region stats).
 // There is no CPU fallback anywhere: if CUDA is unavailable every run returns BDEPTH_ERR_CUDA.
-#include <cuda_runtime.h>
+#include "launch.cuh"
 #include <dlfcn.h>
 #include <fcntl.h>
 #include <stdarg.h>
@@ -69,6 +69,11 @@ __global__ void k_copy_words(uint32_t* __restrict__ dst, const uint32_t* __restr
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
 }
 
+#ifdef BDEPTH_EMULATE_SHIM
+constexpr unsigned COUNT_GRID = 4;           // grid-stride reducer: any grid gives the same sum; the CPU emulation runs blocks one by one
+#else
+constexpr unsigned COUNT_GRID = 2048;
+#endif
 constexpr size_t CARRY_MAX = 64ull << 20;
 constexpr size_t EMIT_CHUNK = 4ull << 20;     // positions per D2H chunk
 constexpr uint32_t SHARD_EXTRA_BLOCKS = 8;
@@ -217,7 +222,7 @@ int inflate_blocks_to_host(bdepth* h, size_t b0, size_t b1, std::vector<uint8_t>
     CK(cudaMemcpyAsync(h->comp.p, h->file + f0, f1 - f0, cudaMemcpyHostToDevice, h->s_main));
     CK(cudaMemsetAsync((uint8_t*)h->comp.p + (f1 - f0), 0, 128, h->s_main));
     CK(cudaMemcpyAsync(h->descs.p, d.data(), nb * sizeof(BlockDesc), cudaMemcpyHostToDevice, h->s_main));
-    k1_inflate<<<(unsigned)((nb + 32 * K1_WARPS - 1) / (32 * K1_WARPS)), 32 * K1_WARPS, K1_SMEM, h->s_main>>>(h->comp.as<uint32_t>(), h->descs.as<BlockDesc>(), (uint32_t)nb, h->ubuf.as<uint8_t>() + CARRY_MAX, h->status.as<int>());
+    BD_LAUNCH((unsigned)((nb + 32 * K1_WARPS - 1) / (32 * K1_WARPS)), 32 * K1_WARPS, K1_SMEM, h->s_main, k1_inflate)(h->comp.as<uint32_t>(), h->descs.as<BlockDesc>(), (uint32_t)nb, h->ubuf.as<uint8_t>() + CARRY_MAX, h->status.as<int>());
     CK(cudaGetLastError());
     std::vector<int> stt(nb); out.resize(ulen);
     CK(cudaMemcpyAsync(stt.data(), h->status.p, nb * sizeof(int), cudaMemcpyDeviceToHost, h->s_main));
@@ -399,7 +404,7 @@ int exchange_boundaries(bdepth* h, uint64_t shard_min, uint64_t shard_max) {
     NK(N.GroupEnd());
     for (size_t i = 0; i < recvs.size(); i++) {
         uint64_t n = recvs[i].hi - recvs[i].lo;
-        for (int pl = 0; pl < NP; pl++) k_add_u32<<<(unsigned)((n + 255) / 256), 256, 0, sm>>>(h->counts.as<uint32_t>() + (uint64_t)pl * h->win_len + (recvs[i].lo - h->cnt_base), sp + roff[i] + (uint64_t)pl * n, n);
+        for (int pl = 0; pl < NP; pl++) BD_LAUNCH((unsigned)((n + 255) / 256), 256, 0, sm, k_add_u32)(h->counts.as<uint32_t>() + (uint64_t)pl * h->win_len + (recvs[i].lo - h->cnt_base), sp + roff[i] + (uint64_t)pl * n, n);
         h->st.gpu_launches += NP;
     }
     // which references have reads: OR over ranks == (sum > 0)
@@ -549,13 +554,13 @@ int run_pipeline(bdepth* h, RunMode mode, RunOut* ro, Emitter* em = nullptr) {
         if (!bytes) return 0;
         uint8_t* m = hs.take(bytes); if (!m) return fail(h, BDEPTH_ERR_CUDA, "internal: host scratch exhausted");
         memcpy(m, src, bytes);
-        k_copy_words<<<(unsigned)std::min<size_t>((bytes / 4 + 255) / 256, 512), 256, 0, sm>>>((uint32_t*)dst_dev, (const uint32_t*)hs.dev(m), bytes / 4);
+        BD_LAUNCH((unsigned)std::min<size_t>((bytes / 4 + 255) / 256, 512), 256, 0, sm, k_copy_words)((uint32_t*)dst_dev, (const uint32_t*)hs.dev(m), bytes / 4);
         st.gpu_launches++;
         return 0;
     };
     auto down = [&](const void* src_dev, size_t bytes) -> uint8_t* {
         uint8_t* m = hs.take(bytes ? bytes : 4); if (!m) return nullptr;
-        if (bytes) { k_copy_words<<<(unsigned)std::min<size_t>((bytes / 4 + 255) / 256, 512), 256, 0, sm>>>((uint32_t*)hs.dev(m), (const uint32_t*)src_dev, bytes / 4); st.gpu_launches++; }
+        if (bytes) { BD_LAUNCH((unsigned)std::min<size_t>((bytes / 4 + 255) / 256, 512), 256, 0, sm, k_copy_words)((uint32_t*)hs.dev(m), (const uint32_t*)src_dev, bytes / 4); st.gpu_launches++; }
         return m;
     };
 #define UP(dst, src, bytes) do { int rcu_ = up((dst), (src), (bytes)); if (rcu_) return rcu_; } while (0)
@@ -649,7 +654,7 @@ int run_pipeline(bdepth* h, RunMode mode, RunOut* ro, Emitter* em = nullptr) {
         // ---- K1: when the input is streaming in, one sub-launch per H2D chunk, spread over a few streams so that
         // they run side by side (a lone sub-launch cannot fill the GPU: every lane owns a whole BGZF block)
         if (h->staged) {
-            k1_inflate<<<(unsigned)((nb + 32 * K1_WARPS - 1) / (32 * K1_WARPS)), 32 * K1_WARPS, K1_SMEM, sm>>>(d_comp, h->descs.as<BlockDesc>(), (uint32_t)nb, u0, h->status.as<int>());
+            BD_LAUNCH((unsigned)((nb + 32 * K1_WARPS - 1) / (32 * K1_WARPS)), 32 * K1_WARPS, K1_SMEM, sm, k1_inflate)(d_comp, h->descs.as<BlockDesc>(), (uint32_t)nb, u0, h->status.as<int>());
             CK(cudaGetLastError()); st.gpu_launches++;
             subs.push_back(Sub{b, b1, 0, -1});
         } else {
@@ -658,8 +663,8 @@ int run_pipeline(bdepth* h, RunMode mode, RunOut* ro, Emitter* em = nullptr) {
                 size_t c1 = h->chunk_end[slot][j]; cudaStream_t ks = h->s_k1[j & 15];
                 CK(cudaStreamWaitEvent(ks, e1, 0)); CK(cudaStreamWaitEvent(ks, h->chunk_ev[slot][j], 0));
                 uint32_t n = (uint32_t)(c1 - c0);
-                if (h->k1_small) k1_inflate_small<<<(n + 32 * K1S_WARPS - 1) / (32 * K1S_WARPS), 32 * K1S_WARPS, K1S_SMEM, ks>>>(d_comp, h->descs.as<BlockDesc>() + (c0 - b), n, u0, h->status.as<int>() + (c0 - b));
-                else k1_inflate<<<(n + 32 * K1_WARPS - 1) / (32 * K1_WARPS), 32 * K1_WARPS, K1_SMEM, ks>>>(d_comp, h->descs.as<BlockDesc>() + (c0 - b), n, u0, h->status.as<int>() + (c0 - b));
+                if (h->k1_small) BD_LAUNCH((n + 32 * K1S_WARPS - 1) / (32 * K1S_WARPS), 32 * K1S_WARPS, K1S_SMEM, ks, k1_inflate_small)(d_comp, h->descs.as<BlockDesc>() + (c0 - b), n, u0, h->status.as<int>() + (c0 - b));
+                else BD_LAUNCH((n + 32 * K1_WARPS - 1) / (32 * K1_WARPS), 32 * K1_WARPS, K1_SMEM, ks, k1_inflate)(d_comp, h->descs.as<BlockDesc>() + (c0 - b), n, u0, h->status.as<int>() + (c0 - b));
                 CK(cudaGetLastError()); st.gpu_launches++;
                 if (h->k1_ev.size() <= j) { cudaEvent_t ne; CK(cudaEventCreateWithFlags(&ne, cudaEventDisableTiming)); h->k1_ev.push_back(ne); }
                 CK(cudaEventRecord(h->k1_ev[j], ks));
@@ -709,7 +714,7 @@ int run_pipeline(bdepth* h, RunMode mode, RunOut* ro, Emitter* em = nullptr) {
         // records that START at or after the shard limit belong to the next rank
         int64_t u_limit = (int64_t)ub; if (!sparse && h->limit_abs_u < batch_u0 + ub) u_limit = (int64_t)h->limit_abs_u - (int64_t)batch_u0;      // may be negative: the limit lies before this sub-batch, and a carried record that starts at or after it is not ours either
         ScanParams sp{u0, -(int64_t)carry_len, (int64_t)ub, (int)nref, h->ref_len_d.as<uint32_t>(), h->ref_lin0_d.as<uint64_t>()};
-        k2_guess_entries<<<(unsigned)((nb * 32 + 255) / 256), 256, 0, sm>>>(sp, h->chunk_start.as<int64_t>(), (uint32_t)nb, h->entry.as<int64_t>());
+        BD_LAUNCH((unsigned)((nb * 32 + 255) / 256), 256, 0, sm, k2_guess_entries)(sp, h->chunk_start.as<int64_t>(), (uint32_t)nb, h->entry.as<int64_t>());
         CK(cudaGetLastError()); st.gpu_launches++;
         const int64_t* d_limit = nullptr;
         if (sparse) {       // chunks of the region query: exact entries at their first blocks, walk limits at their last ones
@@ -722,12 +727,12 @@ int run_pipeline(bdepth* h, RunMode mode, RunOut* ro, Emitter* em = nullptr) {
             if (!ai.empty()) {
                 CK(h->anchors_idx.ensure(ai.size() * 4)); CK(h->anchors_val.ensure(av.size() * 8));
                 UP(h->anchors_idx.p, ai.data(), ai.size() * 4); UP(h->anchors_val.p, av.data(), av.size() * 8);
-                k_scatter_i64<<<(unsigned)((ai.size() + 255) / 256), 256, 0, sm>>>(h->entry.as<int64_t>(), h->anchors_idx.as<uint32_t>(), h->anchors_val.as<int64_t>(), (uint32_t)ai.size());
+                BD_LAUNCH((unsigned)((ai.size() + 255) / 256), 256, 0, sm, k_scatter_i64)(h->entry.as<int64_t>(), h->anchors_idx.as<uint32_t>(), h->anchors_val.as<int64_t>(), (uint32_t)ai.size());
                 CK(cudaGetLastError()); st.gpu_launches++;
             }
         }
         ScanParams spw = sp;
-        k2_walk<<<(unsigned)((nb + 127) / 128), 128, 0, sm>>>(spw, h->chunk_start.as<int64_t>(), (uint32_t)nb, h->entry.as<int64_t>(), h->slot_base.as<uint32_t>(), h->slots.as<uint16_t>(), h->count.as<uint32_t>(), h->exitb.as<int64_t>(), (int*)h->misc.p, nullptr, 0, d_limit);
+        BD_LAUNCH((unsigned)((nb + 127) / 128), 128, 0, sm, k2_walk)(spw, h->chunk_start.as<int64_t>(), (uint32_t)nb, h->entry.as<int64_t>(), h->slot_base.as<uint32_t>(), h->slots.as<uint16_t>(), h->count.as<uint32_t>(), h->exitb.as<int64_t>(), (int*)h->misc.p, nullptr, 0, d_limit);
         CK(cudaGetLastError()); st.gpu_launches++;
         DOWN(ent, int64_t, h->entry.p, nb * 8); DOWN(ext, int64_t, h->exitb.p, nb * 8); DOWN(cnt, uint32_t, h->count.p, nb * 4);      // host-owned once synchronised
         DOWN(werr, int, h->misc.p, 4);
@@ -745,7 +750,7 @@ int run_pipeline(bdepth* h, RunMode mode, RunOut* ro, Emitter* em = nullptr) {
                 uint32_t ci = (uint32_t)i;
                 UP((int64_t*)h->entry.p + i, &true_e, 8);
                 UP(h->walk_list.p, &ci, 4);
-                k2_walk<<<1, 32, 0, sm>>>(spw, h->chunk_start.as<int64_t>(), (uint32_t)nb, h->entry.as<int64_t>(), h->slot_base.as<uint32_t>(), h->slots.as<uint16_t>(), h->count.as<uint32_t>(), h->exitb.as<int64_t>(), (int*)h->misc.p, h->walk_list.as<uint32_t>(), 1, d_limit);
+                BD_LAUNCH(1, 32, 0, sm, k2_walk)(spw, h->chunk_start.as<int64_t>(), (uint32_t)nb, h->entry.as<int64_t>(), h->slot_base.as<uint32_t>(), h->slots.as<uint16_t>(), h->count.as<uint32_t>(), h->exitb.as<int64_t>(), (int*)h->misc.p, h->walk_list.as<uint32_t>(), 1, d_limit);
                 CK(cudaGetLastError()); st.gpu_launches++;
                 DOWN(fx_ext, int64_t, (int64_t*)h->exitb.p + i, 8); DOWN(fx_cnt, uint32_t, (uint32_t*)h->count.p + i, 4); DOWN(fx_err, int, h->misc.p, 4);
                 CK(cudaStreamSynchronize(sm));
@@ -801,9 +806,9 @@ int run_pipeline(bdepth* h, RunMode mode, RunOut* ro, Emitter* em = nullptr) {
         UP(h->scan_stats.p, &zs, sizeof zs);
         if (mode == RUN_SCAN_ONLY && !h->ref_has.p) { CK(h->ref_has.ensure((nref / 32 + 2) * 4)); CK(cudaMemsetAsync(h->ref_has.p, 0, (nref / 32 + 2) * 4, sm)); }
         if (d_fprog)
-            k2_decode<true><<<(unsigned)((nb * 32 + 255) / 256), 256, 0, sm>>>(sp, h->chunk_start.as<int64_t>(), (uint32_t)nb, h->slot_base.as<uint32_t>(), h->slots.as<uint16_t>(), h->count.as<uint32_t>(), h->rec_base.as<uint32_t>(), soa, h->mapq_gt, h->flag_reject, h->scan_stats.as<ScanStats>(), h->long_list.as<uint32_t>(), h->ref_has.as<uint32_t>(), rgt, d_fprog);
+            BD_LAUNCH((unsigned)((nb * 32 + 255) / 256), 256, 0, sm, k2_decode<true>)(sp, h->chunk_start.as<int64_t>(), (uint32_t)nb, h->slot_base.as<uint32_t>(), h->slots.as<uint16_t>(), h->count.as<uint32_t>(), h->rec_base.as<uint32_t>(), soa, h->mapq_gt, h->flag_reject, h->scan_stats.as<ScanStats>(), h->long_list.as<uint32_t>(), h->ref_has.as<uint32_t>(), rgt, d_fprog);
         else
-            k2_decode<false><<<(unsigned)((nb * 32 + 255) / 256), 256, 0, sm>>>(sp, h->chunk_start.as<int64_t>(), (uint32_t)nb, h->slot_base.as<uint32_t>(), h->slots.as<uint16_t>(), h->count.as<uint32_t>(), h->rec_base.as<uint32_t>(), soa, h->mapq_gt, h->flag_reject, h->scan_stats.as<ScanStats>(), h->long_list.as<uint32_t>(), h->ref_has.as<uint32_t>(), rgt, d_fprog);
+            BD_LAUNCH((unsigned)((nb * 32 + 255) / 256), 256, 0, sm, k2_decode<false>)(sp, h->chunk_start.as<int64_t>(), (uint32_t)nb, h->slot_base.as<uint32_t>(), h->slots.as<uint16_t>(), h->count.as<uint32_t>(), h->rec_base.as<uint32_t>(), soa, h->mapq_gt, h->flag_reject, h->scan_stats.as<ScanStats>(), h->long_list.as<uint32_t>(), h->ref_has.as<uint32_t>(), rgt, d_fprog);
         CK(cudaGetLastError()); st.gpu_launches++;
         DOWN(ssp, ScanStats, h->scan_stats.p, sizeof(ScanStats));
         CK(cudaEventRecord(e3, sm));
@@ -830,8 +835,8 @@ int run_pipeline(bdepth* h, RunMode mode, RunOut* ro, Emitter* em = nullptr) {
         }
         // ---- per-read segment counting (countRead, depth.d:661-669) for the window / region front ends
         if (mode == RUN_FULL && h->seg.on && h->seg.n && ss.n_pass) {
-            if (h->minq) k_read_segments<true><<<(unsigned)((R + 127) / 128), 128, 0, sm>>>(soa, u0, (uint32_t)R, h->seg.s.as<uint64_t>(), h->seg.e.as<uint64_t>(), h->seg.pmax.as<uint64_t>(), h->seg.id.as<uint32_t>(), h->seg.has_min ? h->seg.minstart.as<uint64_t>() : nullptr, h->seg.n, h->seg.reads.as<uint32_t>(), h->minq, h->S, h->seg.has_min ? h->seg.bases_reads.as<uint32_t>() : nullptr);
-            else k_read_segments<false><<<(unsigned)((R + 127) / 128), 128, 0, sm>>>(soa, u0, (uint32_t)R, h->seg.s.as<uint64_t>(), h->seg.e.as<uint64_t>(), h->seg.pmax.as<uint64_t>(), h->seg.id.as<uint32_t>(), h->seg.has_min ? h->seg.minstart.as<uint64_t>() : nullptr, h->seg.n, h->seg.reads.as<uint32_t>(), 0, h->S, h->seg.has_min ? h->seg.bases_reads.as<uint32_t>() : nullptr);
+            if (h->minq) BD_LAUNCH((unsigned)((R + 127) / 128), 128, 0, sm, k_read_segments<true>)(soa, u0, (uint32_t)R, h->seg.s.as<uint64_t>(), h->seg.e.as<uint64_t>(), h->seg.pmax.as<uint64_t>(), h->seg.id.as<uint32_t>(), h->seg.has_min ? h->seg.minstart.as<uint64_t>() : nullptr, h->seg.n, h->seg.reads.as<uint32_t>(), h->minq, h->S, h->seg.has_min ? h->seg.bases_reads.as<uint32_t>() : nullptr);
+            else BD_LAUNCH((unsigned)((R + 127) / 128), 128, 0, sm, k_read_segments<false>)(soa, u0, (uint32_t)R, h->seg.s.as<uint64_t>(), h->seg.e.as<uint64_t>(), h->seg.pmax.as<uint64_t>(), h->seg.id.as<uint32_t>(), h->seg.has_min ? h->seg.minstart.as<uint64_t>() : nullptr, h->seg.n, h->seg.reads.as<uint32_t>(), 0, h->S, h->seg.has_min ? h->seg.bases_reads.as<uint32_t>() : nullptr);
             CK(cudaGetLastError()); st.gpu_launches++;
         }
         uint64_t idx_tiles_base = 0; uint32_t idx_n_tiles = 0;      // K3's per-tile read index of this sub-batch (the mate kernels look reads up through it)
@@ -850,22 +855,22 @@ int run_pipeline(bdepth* h, RunMode mode, RunOut* ro, Emitter* em = nullptr) {
             idx_tiles_base = tiles_base; idx_n_tiles = (uint32_t)n_tiles;
             if (t_hi * TILE_POS > h->win_len) return fail(h, BDEPTH_ERR_FORMAT, "read extends past the end of the reference space");
             CK(h->tile_first.ensure((n_tiles + 2) * 4)); CK(h->tile_lo.ensure((n_tiles + 2) * 4));
-            k_fill_u32<<<(unsigned)((n_tiles + 2 + 255) / 256), 256, 0, sm>>>(h->tile_first.as<uint32_t>(), (uint32_t)R, n_tiles + 2);
+            BD_LAUNCH((unsigned)((n_tiles + 2 + 255) / 256), 256, 0, sm, k_fill_u32)(h->tile_first.as<uint32_t>(), (uint32_t)R, n_tiles + 2);
             CK(cudaMemsetAsync(h->tile_lo.p, 0xFF, (n_tiles + 2) * 4, sm));
-            k3_tile_index<<<(unsigned)((R + 255) / 256), 256, 0, sm>>>(soa, (uint32_t)R, tiles_base, (uint32_t)n_tiles, h->tile_first.as<uint32_t>(), h->tile_lo.as<uint32_t>());
+            BD_LAUNCH((unsigned)((R + 255) / 256), 256, 0, sm, k3_tile_index)(soa, (uint32_t)R, tiles_base, (uint32_t)n_tiles, h->tile_first.as<uint32_t>(), h->tile_lo.as<uint32_t>());
             CK(cudaGetLastError()); st.gpu_launches += 2;
             for (uint32_t si = 0; si < h->S; si++) {      // one counter set per sample (one pass when combined / single sample)
                 uint32_t* cnt = h->counts.as<uint32_t>() + (uint64_t)si * N_PLANES * h->win_len; int sel = h->S > 1 ? (int)si : -1;
                 if (ss.n_long) {
-                    if (h->minq) k3_scatter_long<true><<<(unsigned)((ss.n_long * 32 + 255) / 256), 256, 0, sm>>>(soa, u0, h->long_list.as<uint32_t>(), (uint32_t)ss.n_long, h->cnt_base, h->win_len, cnt, h->minq, sel);
-                    else k3_scatter_long<false><<<(unsigned)((ss.n_long * 32 + 255) / 256), 256, 0, sm>>>(soa, u0, h->long_list.as<uint32_t>(), (uint32_t)ss.n_long, h->cnt_base, h->win_len, cnt, 0, sel);
+                    if (h->minq) BD_LAUNCH((unsigned)((ss.n_long * 32 + 255) / 256), 256, 0, sm, k3_scatter_long<true>)(soa, u0, h->long_list.as<uint32_t>(), (uint32_t)ss.n_long, h->cnt_base, h->win_len, cnt, h->minq, sel);
+                    else BD_LAUNCH((unsigned)((ss.n_long * 32 + 255) / 256), 256, 0, sm, k3_scatter_long<false>)(soa, u0, h->long_list.as<uint32_t>(), (uint32_t)ss.n_long, h->cnt_base, h->win_len, cnt, 0, sel);
                     CK(cudaGetLastError()); st.gpu_launches++;
                 }
                 if (h->k3_pre) {       // experiment, see kernels.cuh
-                    if (h->minq) k3_gather<true, true><<<(unsigned)n_tiles, 256, 0, sm>>>(soa, u0, tiles_base, h->cnt_base, h->win_len, h->tile_first.as<uint32_t>(), h->tile_lo.as<uint32_t>(), cnt, h->minq, sel);
-                    else k3_gather<false, true><<<(unsigned)n_tiles, 256, 0, sm>>>(soa, u0, tiles_base, h->cnt_base, h->win_len, h->tile_first.as<uint32_t>(), h->tile_lo.as<uint32_t>(), cnt, 0, sel);
-                } else if (h->minq) k3_gather<true, false><<<(unsigned)n_tiles, 256, 0, sm>>>(soa, u0, tiles_base, h->cnt_base, h->win_len, h->tile_first.as<uint32_t>(), h->tile_lo.as<uint32_t>(), cnt, h->minq, sel);
-                else k3_gather<false, false><<<(unsigned)n_tiles, 256, 0, sm>>>(soa, u0, tiles_base, h->cnt_base, h->win_len, h->tile_first.as<uint32_t>(), h->tile_lo.as<uint32_t>(), cnt, 0, sel);
+                    if (h->minq) BD_LAUNCH((unsigned)n_tiles, 256, 0, sm, k3_gather<true, true>)(soa, u0, tiles_base, h->cnt_base, h->win_len, h->tile_first.as<uint32_t>(), h->tile_lo.as<uint32_t>(), cnt, h->minq, sel);
+                    else BD_LAUNCH((unsigned)n_tiles, 256, 0, sm, k3_gather<false, true>)(soa, u0, tiles_base, h->cnt_base, h->win_len, h->tile_first.as<uint32_t>(), h->tile_lo.as<uint32_t>(), cnt, 0, sel);
+                } else if (h->minq) BD_LAUNCH((unsigned)n_tiles, 256, 0, sm, k3_gather<true, false>)(soa, u0, tiles_base, h->cnt_base, h->win_len, h->tile_first.as<uint32_t>(), h->tile_lo.as<uint32_t>(), cnt, h->minq, sel);
+                else BD_LAUNCH((unsigned)n_tiles, 256, 0, sm, k3_gather<false, false>)(soa, u0, tiles_base, h->cnt_base, h->win_len, h->tile_first.as<uint32_t>(), h->tile_lo.as<uint32_t>(), cnt, 0, sel);
                 CK(cudaGetLastError()); st.gpu_launches++;
             }
         }
@@ -891,7 +896,7 @@ int run_pipeline(bdepth* h, RunMode mode, RunOut* ro, Emitter* em = nullptr) {
                           h->tile_lo.as<uint32_t>(), idx_tiles_base, idx_n_tiles, h->long_list.as<uint32_t>(), (uint32_t)ss.n_long, 0,
                           (int*)h->m_ctl.p, (unsigned long long*)((uint8_t*)h->m_ctl.p + 16)};
             const unsigned mg = (unsigned)((R + 127) / 128);
-            km_hash<<<mg, 128, 0, sm>>>(mp); km_link<<<mg, 128, 0, sm>>>(mp); km_fix<<<mg, 128, 0, sm>>>(mp);
+            BD_LAUNCH(mg, 128, 0, sm, km_hash)(mp); BD_LAUNCH(mg, 128, 0, sm, km_link)(mp); BD_LAUNCH(mg, 128, 0, sm, km_fix)(mp);
             CK(cudaGetLastError()); st.gpu_launches += 3;
             CK(cudaEventRecord(em1, sm));
             struct { int err[4]; unsigned long long stat[3]; } ctl;
@@ -1116,7 +1121,7 @@ int bdepth_run_resident(bdepth_t* h) {
     cudaStream_t sm = h->s_main;
     CK(cudaMemsetAsync(h->misc.p, 0, 8, sm));
     uint64_t a = std::max(h->own_lo, h->cnt_base) - h->cnt_base, b = std::min(h->own_hi, h->cnt_base + h->win_len) - h->cnt_base;
-    if (b > a) { k_count_covered<<<2048, 256, 0, sm>>>(h->counts.as<uint32_t>(), h->win_len, a, b, (unsigned long long*)h->misc.p, N_PLANES * (int)h->S); CK(cudaGetLastError()); h->st.gpu_launches++; }
+    if (b > a) { BD_LAUNCH(COUNT_GRID, 256, 0, sm, k_count_covered)(h->counts.as<uint32_t>(), h->win_len, a, b, (unsigned long long*)h->misc.p, N_PLANES * (int)h->S); CK(cudaGetLastError()); h->st.gpu_launches++; }
     unsigned long long cov = 0; CK(cudaMemcpyAsync(&cov, h->misc.p, 8, cudaMemcpyDeviceToHost, sm)); CK(cudaStreamSynchronize(sm));
     h->st.covered_positions = cov;
     h->st.ms_total_device = h->st.ms_h2d + h->st.ms_inflate + h->st.ms_scan + h->st.ms_coverage + h->st.ms_exchange;
@@ -1137,7 +1142,7 @@ int bdepth_run_base(bdepth_t* h, bdepth_tile_cb cb, void* user) {
     // covered positions (rows of default `depth base`), over the range this rank owns
     CK(cudaMemsetAsync(h->misc.p, 0, 8, sm));
     { uint64_t ca = std::max(h->own_lo, h->cnt_base) - h->cnt_base, cb2 = std::min(h->own_hi, h->cnt_base + h->win_len) - h->cnt_base;
-      if (cb2 > ca) { k_count_covered<<<2048, 256, 0, sm>>>(h->counts.as<uint32_t>(), h->win_len, ca, cb2, (unsigned long long*)h->misc.p, N_PLANES * (int)h->S); CK(cudaGetLastError()); h->st.gpu_launches++; } }
+      if (cb2 > ca) { BD_LAUNCH(COUNT_GRID, 256, 0, sm, k_count_covered)(h->counts.as<uint32_t>(), h->win_len, ca, cb2, (unsigned long long*)h->misc.p, N_PLANES * (int)h->S); CK(cudaGetLastError()); h->st.gpu_launches++; } }
     unsigned long long cov = 0; CK(cudaMemcpyAsync(&cov, h->misc.p, 8, cudaMemcpyDeviceToHost, sm));
     CK(cudaEventRecord(e0, sm));
     if (h->world > 1) {   // multi-GPU: ranks deliver disjoint, ordered pieces: clip the not-yet-delivered ranges to the owned range
@@ -1164,7 +1169,7 @@ int bdepth_run_base_text(bdepth_t* h, const bdepth_text_opts* o, bdepth_text_cb 
     CK(cudaEventRecord(e0, sm));
     CK(cudaMemsetAsync(h->misc.p, 0, 8, sm));
     { uint64_t ca = std::max(h->own_lo, h->cnt_base) - h->cnt_base, cb2 = std::min(h->own_hi, h->cnt_base + h->win_len) - h->cnt_base;
-      if (cb2 > ca) { k_count_covered<<<2048, 256, 0, sm>>>(h->counts.as<uint32_t>(), h->win_len, ca, cb2, (unsigned long long*)h->misc.p, N_PLANES * (int)h->S); CK(cudaGetLastError()); h->st.gpu_launches++; } }
+      if (cb2 > ca) { BD_LAUNCH(COUNT_GRID, 256, 0, sm, k_count_covered)(h->counts.as<uint32_t>(), h->win_len, ca, cb2, (unsigned long long*)h->misc.p, N_PLANES * (int)h->S); CK(cudaGetLastError()); h->st.gpu_launches++; } }
     unsigned long long cov = 0; CK(cudaMemcpyAsync(&cov, h->misc.p, 8, cudaMemcpyDeviceToHost, sm));
     TextParams tp; memset(&tp, 0, sizeof tp);
     tp.min_cov = o->min_cov; tp.max_cov = o->max_cov; tp.annotate = o->annotate ? 1 : 0; tp.with_sample = h->combined ? 0 : 1;
@@ -1217,13 +1222,13 @@ int bdepth_run_base_text(bdepth_t* h, const bdepth_text_opts* o, bdepth_text_cb 
         const uint32_t* cnt = p.in_window ? h->counts.as<uint32_t>() : h->text_zero.as<uint32_t>();
         uint64_t wl = p.in_window ? h->win_len : 0, idx0 = p.in_window ? p.a - h->cnt_base : 0;
         unsigned long long* tot_d = (unsigned long long*)((uint8_t*)h->text_offs.p + (size_t)(max_piece / TEXT_TILE + 2) * 8);
-        k_text_len<<<n_tiles, 256, 0, sm>>>(tp, cnt, wl, idx0, pos0, n, h->text_tiles.as<uint32_t>());
-        k_text_scan<<<1, 1024, 0, sm>>>(h->text_tiles.as<uint32_t>(), n_tiles, (unsigned long long*)h->text_offs.p, tot_d);
+        BD_LAUNCH(n_tiles, 256, 0, sm, k_text_len)(tp, cnt, wl, idx0, pos0, n, h->text_tiles.as<uint32_t>());
+        BD_LAUNCH(1, 1024, 0, sm, k_text_scan)(h->text_tiles.as<uint32_t>(), n_tiles, (unsigned long long*)h->text_offs.p, tot_d);
         unsigned long long tot = 0; CK(cudaMemcpyAsync(&tot, tot_d, 8, cudaMemcpyDeviceToHost, sm));
         CK(cudaStreamSynchronize(sm));
         if (tot > TEXT_BUF) return fail(h, BDEPTH_ERR_ARG, "internal: text chunk larger than its buffer");
         if (tot) {
-            k_text_write<<<n_tiles, 256, 0, sm>>>(tp, cnt, wl, idx0, pos0, n, (const unsigned long long*)h->text_offs.p, h->text[slot].as<char>());
+            BD_LAUNCH(n_tiles, 256, 0, sm, k_text_write)(tp, cnt, wl, idx0, pos0, n, (const unsigned long long*)h->text_offs.p, h->text[slot].as<char>());
             CK(cudaGetLastError());
             CK(cudaMemcpyAsync((char*)h->pinned + (size_t)slot * TEXT_BUF, h->text[slot].p, tot, cudaMemcpyDeviceToHost, sm));
         }
@@ -1304,7 +1309,7 @@ static int run_segments(bdepth* h, const std::vector<SegDef>& segs, const uint32
     cudaMemsetAsync(dbases.p, 0, NS * nn * 4, sm); cudaMemsetAsync(dcov.p, 0, NS * nn * 4 * nt1, sm);
     if (n) {
         for (size_t si = 0; si < NS; si++) {
-            k_segment_stats<<<(unsigned)((n * 32 + 255) / 256), 256, 0, sm>>>(h->counts.as<uint32_t>() + (uint64_t)si * N_PLANES * h->win_len, h->win_len, da.as<uint64_t>(), dac.as<uint64_t>(), db.as<uint64_t>(), (uint32_t)n, dthr.as<uint32_t>(), (uint32_t)n_thr, dbases.as<uint32_t>() + si * n, dcov.as<uint32_t>() + si * n * nt1);
+            BD_LAUNCH((unsigned)((n * 32 + 255) / 256), 256, 0, sm, k_segment_stats)(h->counts.as<uint32_t>() + (uint64_t)si * N_PLANES * h->win_len, h->win_len, da.as<uint64_t>(), dac.as<uint64_t>(), db.as<uint64_t>(), (uint32_t)n, dthr.as<uint32_t>(), (uint32_t)n_thr, dbases.as<uint32_t>() + si * n, dcov.as<uint32_t>() + si * n * nt1);
             h->st.gpu_launches++;
         }
         if (h->world > 1 && h->comm) {   // per-segment partial sums are additive over ranks

@@ -20,7 +20,7 @@
 //   per-base counters  sambamba/depth.d:495-556 (writeColumn), base.d:186 (nt16 -> nt5)
 //   region/window      sambamba/depth.d:661-698 (countRead), :760-845 (push), :847-876
 #pragma once
-#include <cuda_runtime.h>
+#include "launch.cuh"
 #include <stdint.h>
 #include "inflate_core.cuh"
 #include "filter.cuh"
@@ -51,7 +51,7 @@ constexpr int K1_WARPS = 13;
 constexpr int K1_SMEM = K1_WARPS * SMEM_BYTES_PER_WARP;         // 229,632 B
 __global__ void __launch_bounds__(K1_WARPS * 32, 1) k1_inflate(const uint32_t* __restrict__ comp, const BlockDesc* __restrict__ blocks,
                                                                uint32_t n_blocks, uint8_t* __restrict__ u, int* __restrict__ status) {
-    extern __shared__ uint32_t smem[];
+    BD_DYN_SMEM(uint32_t, smem);
     uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t b = (blockIdx.x * K1_WARPS + warp) * 32u + lane;
     uint32_t scratch[96];
@@ -75,7 +75,7 @@ constexpr int K1S_WARPS = 4;
 constexpr int K1S_SMEM = K1S_WARPS * SMEM_BYTES_PER_WARP;       // 70,656 B
 __global__ void __launch_bounds__(K1S_WARPS * 32, 3) k1_inflate_small(const uint32_t* __restrict__ comp, const BlockDesc* __restrict__ blocks,
                                                                       uint32_t n_blocks, uint8_t* __restrict__ u, int* __restrict__ status) {
-    extern __shared__ uint32_t smem[];
+    BD_DYN_SMEM(uint32_t, smem);
     uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t b = (blockIdx.x * K1S_WARPS + warp) * 32u + lane;
     uint32_t scratch[96];
@@ -231,7 +231,7 @@ __device__ __forceinline__ bool cig_qcons(uint32_t op) { return op == 0 || op ==
 __device__ __forceinline__ bool cig_match(uint32_t op) { return op == 0 || op == 7 || op == 8; }
 
 // out of line: the default predicate's path through k2_decode keeps its registers
-__device__ __noinline__ bool filter_eval_cold(const FilterProg* fp, const uint8_t* rec, uint32_t rec_size) { return filter_eval(*fp, rec, rec_size); }
+__device__ BD_NOINLINE bool filter_eval_cold(const FilterProg* fp, const uint8_t* rec, uint32_t rec_size) { return filter_eval(*fp, rec, rec_size); }
 
 template <bool FILTER>      // FILTER: a compiled -F query decides (its own instantiation, so that the default predicate's kernel keeps its register count)
 __global__ void k2_decode(ScanParams sp, const int64_t* __restrict__ chunk_start, uint32_t n_chunks, const uint32_t* __restrict__ slot_base,

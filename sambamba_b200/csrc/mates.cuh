@@ -386,7 +386,7 @@ BD_HD void mate_fix_one(const MateParams& p, uint32_t r) {
     mate_fix_group(p, idx, n, r);
 }
 
-#if defined(__CUDACC__)
+#if defined(__CUDACC__) || defined(BDEPTH_EMULATE_SHIM)
 __global__ void km_hash(MateParams p) { uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; if (r < p.R) mate_hash_one(p, r); }
 __global__ void km_link(MateParams p) { uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; if (r < p.R) mate_link_one(p, r); }
 __global__ void km_fix(MateParams p) { uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; if (r < p.R) mate_fix_one(p, r); }

@@ -13,9 +13,31 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
 
+EMULATE = os.environ.get("BDEPTH_EMULATE") == "1"
+
+
+def pytest_collection_modifyitems(config, items):
+    """BDEPTH_EMULATE=1 (TEST INFRASTRUCTURE): run the `gpu` tests on the CPU against tests/emul/libbdepth_emul.so, the
+    same pipeline and kernels compiled with g++ over a CUDA-on-CPU emulation (tests/emul/cuda_shim.hpp).  Multi-GPU tests
+    (NCCL) and the full-size ones stay out; nothing of this ever touches the product library."""
+    if not EMULATE:
+        return
+    skip = pytest.mark.skip(reason="not under CPU emulation (NCCL / full size / timing)")
+    for it in items:
+        if "test_gpu_multi" in it.nodeid or "fullsize" in it.nodeid or "experiments" in it.nodeid:
+            it.add_marker(skip)
+
+
 @pytest.fixture(scope="session", autouse=True)
 def _build_everything():
     """Build the oracle, the generator, the emulation harness and (cross-compile) libbdepth.so once."""
     import __graft_entry__ as g
     g.build(quiet=True)
+    if EMULATE:
+        import helpers
+        import sambamba_b200._lib as L
+        emul = os.path.join(ROOT, "tests", "emul")
+        L.lib_path = lambda: os.path.join(emul, "libbdepth_emul.so")
+        L._lib = None                      # build() has loaded the product library: drop the cached handle
+        helpers.CLI = os.path.join(emul, "sambamba-depth-emul")
     yield

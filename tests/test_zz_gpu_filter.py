@@ -16,7 +16,7 @@ pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600),
 
 
 def test_cli_filters_match_oracle_on_prefiltered_input(tmp_path):
-    p = tef.make_bam(str(tmp_path / "f.bam"), seed=5, n=3000)
+    p = tef.make_bam(str(tmp_path / "f.bam"), seed=5, n=3000, empty_seq=False)
     u = helpers.oracle_inflate(p)
     _, recs = tef.parse_all(u)
     full = os.environ.get("BDEPTH_FULLSIZE") == "1"
