@@ -24,7 +24,7 @@ def pytest_collection_modifyitems(config, items):
         return
     skip = pytest.mark.skip(reason="not under CPU emulation (NCCL / full size / timing)")
     for it in items:
-        if "test_gpu_multi" in it.nodeid or "fullsize" in it.nodeid or "experiments" in it.nodeid:
+        if "test_gpu_multi" in it.nodeid or "fullsize" in it.nodeid:
             it.add_marker(skip)
 
 

@@ -1,0 +1,24 @@
+"""The `gpu` tests of the CLI, of `-m` and of `-F`, run on the CPU against tests/emul/libbdepth_emul.so: the same host
+pipeline (bdepth.cu) and kernels compiled with g++ over a CUDA-on-CPU emulation (tests/emul/cuda_shim.hpp: a fiber per
+thread, rendezvous for warp collectives and __syncthreads).  TEST INFRASTRUCTURE: it shows that launch plumbing written
+without access to a GPU is logically right; it is no substitute for the hardware run (memory model, alignment, PTX paths,
+speed) and no part of the product.  The other gpu suites pass under it as well (parity, edge cases, sparse staging,
+kernel variants: about 15 minutes, run them with BDEPTH_EMULATE=1 python -m pytest tests -m gpu --runxfail)."""
+import os
+import subprocess
+import sys
+
+from helpers import ROOT
+
+SUITES = ["tests/test_gpu_cli.py", "tests/test_zz_gpu_mates.py", "tests/test_zz_gpu_filter.py"]
+
+
+def test_gpu_suites_pass_under_cpu_emulation():
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "tests", "emul")], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    env = dict(os.environ, BDEPTH_EMULATE="1")
+    procs = [(s, subprocess.Popen([sys.executable, "-m", "pytest", s, "-q", "-m", "gpu", "--runxfail", "-p", "no:cacheprovider", "-x"], cwd=ROOT, env=env,
+                                  stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)) for s in SUITES]
+    for s, p in procs:
+        out, _ = p.communicate(timeout=1500)
+        assert p.returncode == 0, (s, out[-3000:])
+        assert " passed" in out and "failed" not in out and "skipped" not in out, (s, out[-600:])

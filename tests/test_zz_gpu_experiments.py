@@ -9,16 +9,18 @@ import pytest
 import helpers
 from helpers import GOLDEN
 
+N_READS = 12000 if os.environ.get("BDEPTH_EMULATE") == "1" else 120000
+
 pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600), pytest.mark.xfail(strict=False, reason="first hardware run pending")]
 
 
 def test_small_cta_inflate_gives_identical_output(tmp_path):
-    p = helpers.gen_bam(str(tmp_path / "t.bam"), "-r", "chrA:900000", "-r", "chrB:600000", "-n", 120000, "-s", 4, "-t", 4, "--stored-every", 7)
+    p = helpers.gen_bam(str(tmp_path / "t.bam"), "-r", "chrA:900000", "-r", "chrB:600000", "-n", N_READS, "-s", 4, "-t", 4, "--stored-every", 7)
     _same_output_with(tmp_path, p, dict(BDEPTH_K1_STREAM_WARPS="4"))
 
 
 def test_k3_prefetch_gives_identical_output(tmp_path):
-    p = helpers.gen_bam(str(tmp_path / "t.bam"), "-r", "chrA:900000", "-r", "chrB:600000", "-n", 120000, "-s", 5, "-t", 4)
+    p = helpers.gen_bam(str(tmp_path / "t.bam"), "-r", "chrA:900000", "-r", "chrB:600000", "-n", N_READS, "-s", 5, "-t", 4)
     _same_output_with(tmp_path, p, dict(BDEPTH_K3_PREFETCH="1"), extra=[["base", "-q", "25", p], ["base", "-c", "0", os.path.join(GOLDEN, "issue225.bam")]])
 
 
