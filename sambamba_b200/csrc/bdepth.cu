@@ -102,6 +102,13 @@ NcclApi& nccl() {
     static NcclApi api; static bool tried = false;
     if (tried) return api;
     tried = true;
+#ifdef BDEPTH_EMULATE_SHIM      // test build only (launch.cuh): ranks are threads, the collectives are rendezvous between them
+    api.GetUniqueId = [](NcclUid* u) { return emu_ncclGetUniqueId(u->b); };
+    api.CommInitRank = [](NcclComm* c, int w, NcclUid u, int r) { return emu_ncclCommInitRank(c, w, u.b, r); };
+    api.CommDestroy = emu_ncclCommDestroy; api.AllGather = emu_ncclAllGather; api.AllReduce = emu_ncclAllReduce; api.Send = emu_ncclSend; api.Recv = emu_ncclRecv;
+    api.GroupStart = emu_ncclGroupStart; api.GroupEnd = emu_ncclGroupEnd; api.GetErrorString = emu_ncclGetErrorString; api.ok = true;
+    return api;
+#endif
     void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
     if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
     if (!lib) { api.err = std::string("cannot load libnccl.so.2: ") + dlerror(); return api; }
@@ -670,8 +677,7 @@ int run_pipeline(bdepth* h, RunMode mode, RunOut* ro, Emitter* em = nullptr) {
                 CK(cudaEventRecord(h->k1_ev[j], ks));
                 // Sub-batches: a lane needs ~60 ms for its block however empty the GPU is, so the scan / coverage /
                 // delivery of the blocks that arrived first runs while the later chunks are still being inflated.
-                // (one rank only: with several ranks the batch is scanned as a whole, the flow that was validated on 2 GPUs)
-                if (mode == RUN_FULL && h->world == 1 && !fix) subs.push_back(Sub{c0, c1, (int)j, (int)j}); else { if (subs.empty()) subs.push_back(Sub{b, b1, 0, (int)j}); subs[0].ev_hi = (int)j; }
+                if (mode == RUN_FULL && !fix) subs.push_back(Sub{c0, c1, (int)j, (int)j}); else { if (subs.empty()) subs.push_back(Sub{b, b1, 0, (int)j}); subs[0].ev_hi = (int)j; }
                 c0 = c1;
             }
         }

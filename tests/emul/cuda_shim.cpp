@@ -80,3 +80,64 @@ void run_grid(dim3 grid, dim3 block, size_t smem, const std::function<void()>& b
 }
 
 }  // namespace emu
+
+// ------------------------------------------------------------------------------------------------ NCCL stand-in
+#include <condition_variable>
+#include <map>
+#include <mutex>
+#include <string>
+#include <thread>
+namespace {
+struct Group {
+    int world = 0; std::mutex mu; std::condition_variable cv; int waiting = 0; unsigned long gen = 0;
+    std::vector<const void*> pub; std::vector<size_t> pub_n;                       // per rank: published buffer of the running collective
+    std::map<std::pair<int, int>, std::vector<std::vector<uint8_t>>> mail;         // (src, dst) -> queued messages
+    void barrier() { std::unique_lock<std::mutex> l(mu); unsigned long g = gen; if (++waiting == world) { waiting = 0; gen++; cv.notify_all(); } else cv.wait(l, [&] { return gen != g; }); }
+};
+struct Comm { Group* g; int rank; };
+std::mutex g_reg_mu; std::map<std::string, Group*> g_groups; unsigned long g_uid_counter = 0;
+size_t dsize(int dtype) { return dtype == 3 ? 4 : dtype == 5 ? 8 : 1; }           // ncclUint32 = 3, ncclUint64 = 5 (the two the library uses)
+struct PendingOp { bool send; const void* sbuf; void* rbuf; size_t bytes; int peer; Comm* c; };
+thread_local std::vector<PendingOp> t_ops; thread_local int t_group_depth = 0;
+int flush_ops() {
+    if (t_ops.empty()) return 0;
+    Group* g = t_ops[0].c->g; int me = t_ops[0].c->rank;
+    { std::lock_guard<std::mutex> l(g->mu); for (auto& o : t_ops) if (o.send) g->mail[{me, o.peer}].emplace_back((const uint8_t*)o.sbuf, (const uint8_t*)o.sbuf + o.bytes); }
+    for (auto& o : t_ops) if (!o.send) {        // blocking receive: wait until the peer has posted
+        std::unique_lock<std::mutex> l(g->mu);
+        for (;;) { auto it = g->mail.find({o.peer, me}); if (it != g->mail.end() && !it->second.empty()) { auto msg = std::move(it->second.front()); it->second.erase(it->second.begin()); l.unlock(); if (msg.size() != o.bytes) return 5; memcpy(o.rbuf, msg.data(), o.bytes); break; } l.unlock(); std::this_thread::yield(); l.lock(); }
+    }
+    t_ops.clear();
+    return 0;
+}
+}  // namespace
+int emu_ncclGetUniqueId(void* uid128) { std::lock_guard<std::mutex> l(g_reg_mu); memset(uid128, 0, 128); unsigned long v = ++g_uid_counter; memcpy(uid128, "EMUNCCL", 8); memcpy((char*)uid128 + 8, &v, sizeof v); return 0; }
+int emu_ncclCommInitRank(void** comm, int world, const void* uid128, int rank) {
+    Group* g;
+    { std::lock_guard<std::mutex> l(g_reg_mu); std::string key((const char*)uid128, 128); auto it = g_groups.find(key); if (it == g_groups.end()) { g = new Group(); g->world = world; g->pub.assign(world, nullptr); g->pub_n.assign(world, 0); g_groups[key] = g; } else g = it->second; }
+    if (g->world != world || rank < 0 || rank >= world) return 4;
+    *comm = new Comm{g, rank};
+    g->barrier();                    // ncclCommInitRank is collective
+    return 0;
+}
+int emu_ncclCommDestroy(void* comm) { delete (Comm*)comm; return 0; }
+int emu_ncclAllGather(const void* send, void* recv, size_t count, int dtype, void* comm, cudaStream_t) {
+    Comm* c = (Comm*)comm; Group* g = c->g; size_t nb = count * dsize(dtype);
+    g->pub[c->rank] = send; g->barrier();
+    std::vector<uint8_t> tmp(nb * g->world); for (int r = 0; r < g->world; r++) memcpy(tmp.data() + r * nb, g->pub[r], nb);
+    g->barrier(); memcpy(recv, tmp.data(), tmp.size()); g->barrier();
+    return 0;
+}
+int emu_ncclAllReduce(const void* send, void* recv, size_t count, int dtype, int, void* comm, cudaStream_t) {
+    Comm* c = (Comm*)comm; Group* g = c->g;
+    g->pub[c->rank] = send; g->barrier();
+    std::vector<uint8_t> tmp(count * dsize(dtype), 0);
+    for (int r = 0; r < g->world; r++) { if (dtype == 3) { const uint32_t* s = (const uint32_t*)g->pub[r]; uint32_t* d = (uint32_t*)tmp.data(); for (size_t i = 0; i < count; i++) d[i] += s[i]; } else { const uint64_t* s = (const uint64_t*)g->pub[r]; uint64_t* d = (uint64_t*)tmp.data(); for (size_t i = 0; i < count; i++) d[i] += s[i]; } }
+    g->barrier(); memcpy(recv, tmp.data(), tmp.size()); g->barrier();
+    return 0;
+}
+int emu_ncclSend(const void* send, size_t count, int dtype, int peer, void* comm, cudaStream_t) { t_ops.push_back({true, send, nullptr, count * dsize(dtype), peer, (Comm*)comm}); return t_group_depth ? 0 : flush_ops(); }
+int emu_ncclRecv(void* recv, size_t count, int dtype, int peer, void* comm, cudaStream_t) { t_ops.push_back({false, nullptr, recv, count * dsize(dtype), peer, (Comm*)comm}); return t_group_depth ? 0 : flush_ops(); }
+int emu_ncclGroupStart() { t_group_depth++; return 0; }
+int emu_ncclGroupEnd() { if (--t_group_depth == 0) return flush_ops(); return 0; }
+const char* emu_ncclGetErrorString(int e) { return e ? "emulated NCCL error" : "no error"; }

@@ -104,7 +104,7 @@ enum { cudaStreamNonBlocking = 1, cudaEventDisableTiming = 2, cudaHostAllocMappe
 static inline const char* cudaGetErrorString(cudaError_t e) { return e ? "emulated CUDA error" : "no error"; }
 static inline const char* cudaGetErrorName(cudaError_t e) { return e ? "cudaErrorEmulated" : "cudaSuccess"; }
 static inline cudaError_t cudaGetLastError() { return cudaSuccess; }
-static inline cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }
+static inline cudaError_t cudaGetDeviceCount(int* n) { *n = 8; return cudaSuccess; }       // eight pretend devices: ranks are threads (NCCL stand-in below)
 static inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
 static inline cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
 static inline cudaError_t cudaMemGetInfo(size_t* f, size_t* t) { *f = (size_t)32 << 30; *t = (size_t)64 << 30; return cudaSuccess; }
@@ -130,3 +130,18 @@ static inline cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t) { e->t = 
 static inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
 static inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t a, cudaEvent_t b) { *ms = (float)(b->t - a->t); return cudaSuccess; }
 template <class F> static inline cudaError_t cudaFuncSetAttribute(F, int, int) { return cudaSuccess; }
+
+// ------------------------------------------------------------------------------------------------ NCCL stand-in
+// Ranks are THREADS of one process under emulation (the tests start one thread per rank; ctypes releases the GIL).  The
+// collectives the library uses (all-gather, all-reduce sum, grouped send/recv) are rendezvous between those threads,
+// matched by the 128-byte unique id.  Calls are blocking, which satisfies any stream ordering.
+int emu_ncclGetUniqueId(void* uid128);
+int emu_ncclCommInitRank(void** comm, int world, const void* uid128, int rank);
+int emu_ncclCommDestroy(void* comm);
+int emu_ncclAllGather(const void* send, void* recv, size_t count, int dtype, void* comm, cudaStream_t);
+int emu_ncclAllReduce(const void* send, void* recv, size_t count, int dtype, int op, void* comm, cudaStream_t);
+int emu_ncclSend(const void* send, size_t count, int dtype, int peer, void* comm, cudaStream_t);
+int emu_ncclRecv(void* recv, size_t count, int dtype, int peer, void* comm, cudaStream_t);
+int emu_ncclGroupStart();
+int emu_ncclGroupEnd();
+const char* emu_ncclGetErrorString(int);

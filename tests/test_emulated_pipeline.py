@@ -1,4 +1,4 @@
-"""The `gpu` tests of the CLI, of `-m` and of `-F`, run on the CPU against tests/emul/libbdepth_emul.so: the same host
+"""The `gpu` tests of the CLI, of `-m`, of `-F` and of the multi-rank sharding (ranks as threads over an NCCL stand-in), run on the CPU against tests/emul/libbdepth_emul.so: the same host
 pipeline (bdepth.cu) and kernels compiled with g++ over a CUDA-on-CPU emulation (tests/emul/cuda_shim.hpp: a fiber per
 thread, rendezvous for warp collectives and __syncthreads).  TEST INFRASTRUCTURE: it shows that launch plumbing written
 without access to a GPU is logically right; it is no substitute for the hardware run (memory model, alignment, PTX paths,
@@ -10,7 +10,7 @@ import sys
 
 from helpers import ROOT
 
-SUITES = ["tests/test_gpu_cli.py", "tests/test_zz_gpu_mates.py", "tests/test_zz_gpu_filter.py"]
+SUITES = ["tests/test_gpu_cli.py", "tests/test_zz_gpu_mates.py", "tests/test_zz_gpu_filter.py", "tests/test_gpu_multi.py"]
 
 
 def test_gpu_suites_pass_under_cpu_emulation():

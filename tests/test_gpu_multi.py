@@ -20,12 +20,14 @@ def _n_gpus():
         return 0
 
 
-def _rank_main(rank, world, path, uid, mode, q):
+def _rank_main(rank, world, path, uid, mode, q, tuning=None):
     try:
         sys.path.insert(0, helpers.ROOT)
         import sambamba_b200 as sb
         with sb.BDepth(path, device=rank) as b:
             b.set_shard(rank, world, uid)
+            if tuning:
+                b.set_tuning(*tuning)
             if mode == "base":
                 got = b.run_base()
                 st = b.stats()
@@ -38,12 +40,27 @@ def _rank_main(rank, world, path, uid, mode, q):
         q.put((rank, "err", 0, 0, repr(e), None))
 
 
-def _run(world, path, mode):
+def _run(world, path, mode, tuning=None):
     import sambamba_b200 as sb
     uid = sb.nccl_unique_id()
+    if os.environ.get("BDEPTH_EMULATE") == "1":
+        # CPU emulation of the pipeline (tests/emul): ranks are threads of this process, NCCL is a rendezvous between them
+        import queue
+        import threading
+        q = queue.Queue()
+        ts = [threading.Thread(target=_rank_main, args=(r, world, path, uid, mode, q, tuning)) for r in range(world)]
+        for t in ts:
+            t.start()
+        res = [q.get(timeout=1500) for _ in range(world)]
+        for t in ts:
+            t.join(timeout=60)
+        res.sort(key=lambda r: r[0])
+        for r in res:
+            assert r[1] == "ok", r
+        return res
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    ps = [ctx.Process(target=_rank_main, args=(r, world, path, uid, mode, q)) for r in range(world)]
+    ps = [ctx.Process(target=_rank_main, args=(r, world, path, uid, mode, q, tuning)) for r in range(world)]
     for p in ps:
         p.start()
     res = [q.get(timeout=300) for _ in range(world)]
@@ -58,6 +75,8 @@ def _run(world, path, mode):
 @pytest.fixture(scope="module")
 def bam(tmp_path_factory):
     d = tmp_path_factory.mktemp("multi")
+    if os.environ.get("BDEPTH_EMULATE") == "1":       # same shape, a tenth of the size (the CPU emulation is slow)
+        return helpers.gen_bam(str(d / "m.bam"), "-r", "chrA:200000", "-r", "chrB:700", "-r", "chrC:150000", "-n", 30000, "-s", 11, "-t", 8)
     return helpers.gen_bam(str(d / "m.bam"), "-r", "chrA:2000000", "-r", "chrB:700", "-r", "chrC:1500000", "-n", 300000, "-s", 11, "-t", 8)
 
 
@@ -80,6 +99,21 @@ def test_sharded_base_equals_oracle(bam, world):
     assert np.array_equal(got, want)
     assert sum(r[5]["covered_positions"] for r in res) == int((want.sum(axis=0) > 0).sum())
     assert any(r[5]["halo_bytes_sent"] > 0 for r in res), "reads straddling a shard boundary must be exchanged"
+
+
+@pytest.mark.parametrize("world,tuning", [(2, (1 << 20, 3)), (4, (1 << 20, 1)), (3, (0, 2))])
+def test_sharded_with_small_batches_and_sub_batches(bam, world, tuning):
+    """Several batches per rank and several sub-batches per batch (the shard limit then falls inside or before a sub-batch)."""
+    if _n_gpus() < world:
+        pytest.skip(f"needs {world} GPUs")
+    want, ost = helpers.oracle_counts(bam)
+    res = _run(world, bam, "base", tuning)
+    got = np.zeros_like(want)
+    for rank, _, lo, hi, arr, st in res:
+        got[:, lo:hi] = arr
+    assert sum(r[5]["n_records"] for r in res) == ost.n_records
+    assert any(r[5]["n_batches"] > 1 for r in res) or tuning[0] == 0
+    assert np.array_equal(got, want)
 
 
 def test_sharded_windows_equal_single_gpu(bam):
