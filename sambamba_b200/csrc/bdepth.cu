@@ -504,11 +504,13 @@ int run_pipeline(bdepth* h, RunMode mode, RunOut* ro, Emitter* em = nullptr) {
     bdepth_stats& st = h->st; uint32_t launches0 = 0;
     st = bdepth_stats{}; st.gpu_launches = launches0;
     const bool sparse = mode == RUN_FULL && plan_sparse(h);
-    // -m pairs reads of one name wherever they sit in the shard: the whole shard is one batch (and one sub-batch), so
-    // that every record of the SoA and the bytes behind it are resident when the mate kernels run
+    // -m pairs reads of one name wherever they sit in the shard.  A batch is scanned as a whole (no sub-batches), and every
+    // batch after the first re-reads the end of the previous one as "ghost" records -- from the earliest record that can
+    // still meet a mate (mates.cuh) -- so that a pair cut by a batch boundary is seen complete by the batch that closes it.
     const bool fix = mode == RUN_FULL && h->fix_mates;
     if (fix && h->world > 1) return fail(h, BDEPTH_ERR_ARG, "fix-mate-overlaps is not available with several ranks yet");
-    const uint64_t eff_batch_u = fix ? (UINT64_MAX >> 2) : h->batch_u;
+    const uint64_t eff_batch_u = h->batch_u;
+    size_t ghost_b = 0; int64_t ghost_entry = 0; uint64_t ghost_below_abs = 0, prev_s_last = 0, covered_from = 0;      // -m: where the next batch's stream begins
     const std::vector<HostBlock>& B = sparse ? h->vblocks : h->blocks;
     const size_t blk_lo = sparse ? 0 : h->blk_lo, blk_hi = sparse ? B.size() : h->blk_hi;
     const size_t nref = h->hdr.ref_len.size();
@@ -628,11 +630,17 @@ int run_pipeline(bdepth* h, RunMode mode, RunOut* ro, Emitter* em = nullptr) {
     };
     while (b < blk_hi) {
         // ---- batch extent
-        size_t b1 = b; uint64_t ub = 0;
-        while (b1 < blk_hi && (b1 == b || ub + B[b1].isize <= eff_batch_u)) { ub += B[b1].isize; b1++; }
-        const size_t nb = b1 - b; const bool last_batch = b1 == blk_hi;
+        size_t b1 = b; uint64_t ub_new = 0;
+        while (b1 < blk_hi && (b1 == b || ub_new + B[b1].isize <= eff_batch_u)) { ub_new += B[b1].isize; b1++; }
+        const bool last_batch = b1 == blk_hi;
+        st.n_batches++; st.n_blocks += b1 - b; st.inflated_bytes += ub_new;
+        const size_t new_b = b;                                                          // first block that has not been scanned yet
+        const size_t stream_b = (fix && batch_no > 0) ? std::min(ghost_b, b) : b;          // -m: the batch's stream begins with re-read blocks
+        {   // from here to the end of the sub-batch loop `b` is the first block of the batch's stream
+        const size_t b = stream_b;
+        const size_t nb = b1 - b;
         const uint64_t batch_u0 = B[b].uoff;               // absolute inflated offset of the batch start
-        st.n_batches++; st.n_blocks += nb; st.inflated_bytes += ub;
+        const uint64_t ub = B[b1 - 1].uoff + B[b1 - 1].isize - batch_u0;
         // ---- compressed bytes on the device: H2D runs on the copy stream into one of two buffers, so the copy of
         // batch i+1 overlaps the kernels of batch i
         const uint32_t* d_comp;
@@ -640,7 +648,11 @@ int run_pipeline(bdepth* h, RunMode mode, RunOut* ro, Emitter* em = nullptr) {
         CK(cudaEventRecord(e0, sm));
         if (h->staged) d_comp = h->comp.as<uint32_t>();
         else {
-            if (batch_no == 0) { int rcp = issue_h2d(0, b, b1); if (rcp) return rcp; }
+            if (fix) {       // no prefetch: where a batch begins is only known when the previous one has been scanned
+                uint64_t need = 8; if (sparse) for (size_t i = b; i < b1; i++) need += B[i].bsize; else need = B[b1 - 1].coff + B[b1 - 1].bsize - (B[b].coff & ~3ull);
+                CK(h->comp2[batch_no & 1].ensure(need + 256));
+                int rcp = issue_h2d(batch_no, b, b1); if (rcp) return rcp;
+            } else if (batch_no == 0) { int rcp = issue_h2d(0, b, b1); if (rcp) return rcp; }
             d_comp = h->comp2[batch_no & 1].as<uint32_t>();
         }
         // ---- descriptors
@@ -648,7 +660,8 @@ int run_pipeline(bdepth* h, RunMode mode, RunOut* ro, Emitter* em = nullptr) {
         for (size_t i = 0; i < nb; i++) {
             const HostBlock& hb = B[b + i];
             uint64_t dev_off = h->staged ? hb.coff - h->staged_file_off : dco[batch_no & 1][i];
-            d[i] = BlockDesc{dev_off + hb.cdata_off, hb.uoff - batch_u0, hb.csize, hb.isize}; csum += hb.csize; st.file_bytes += hb.bsize;
+            d[i] = BlockDesc{dev_off + hb.cdata_off, hb.uoff - batch_u0, hb.csize, hb.isize};
+            if (b + i >= new_b) { csum += hb.csize; st.file_bytes += hb.bsize; }
         }
         st.cdata_bytes += csum;
         CK(h->descs.ensure(nb * sizeof(BlockDesc))); CK(h->status.ensure(nb * sizeof(int))); CK(h->ubuf.ensure(CARRY_MAX + ub + 256));
@@ -681,7 +694,7 @@ int run_pipeline(bdepth* h, RunMode mode, RunOut* ro, Emitter* em = nullptr) {
                 c0 = c1;
             }
         }
-        if (!h->staged && b1 < blk_hi) { int rcp = issue_h2d(batch_no + 1, b1, batch_end(b1)); if (rcp) return rcp; }
+        if (!h->staged && !fix && b1 < blk_hi) { int rcp = issue_h2d(batch_no + 1, b1, batch_end(b1)); if (rcp) return rcp; }
         const size_t mb = b, mb1 = b1; const uint64_t m_u0abs = batch_u0; uint8_t* const m_u0 = u0; const bool m_last = last_batch;
         for (size_t sbi = 0; sbi < subs.size(); sbi++) {
         const size_t b = subs[sbi].s0, b1 = subs[sbi].s1, nb = b1 - b;                  // from here on: the sub-batch
@@ -714,7 +727,8 @@ int run_pipeline(bdepth* h, RunMode mode, RunOut* ro, Emitter* em = nullptr) {
         UP(h->chunk_start.p, cstart.data(), (nb + 1) * 8);
         UP(h->slot_base.p, sbase.data(), (nb + 1) * 4);
         CK(cudaMemsetAsync(h->entry.p, ENTRY_NONE_BYTE, nb * 8, sm));
-        int64_t anchor = seg0 ? (int64_t)h->seg_entry[b] : first_batch ? h->entry0 : -(int64_t)carry_len;
+        // (-m: a stream that begins exactly where a region-query chunk begins starts at that chunk's first record)
+        int64_t anchor = (fix && batch_no > 0) ? ((seg0 && ghost_entry < (int64_t)h->seg_entry[b]) ? (int64_t)h->seg_entry[b] : ghost_entry) : seg0 ? (int64_t)h->seg_entry[b] : first_batch ? h->entry0 : -(int64_t)carry_len;
         UP(h->entry.p, &anchor, 8);
         CK(cudaMemsetAsync(h->misc.p, 0, 64, sm));
         // records that START at or after the shard limit belong to the next rank
@@ -808,18 +822,21 @@ int run_pipeline(bdepth* h, RunMode mode, RunOut* ro, Emitter* em = nullptr) {
         size_t Rc = R ? R : 1;
         CK(h->soa_start.ensure(Rc * 8)); CK(h->soa_span.ensure(Rc * 4)); CK(h->soa_meta.ensure(Rc * 4)); CK(h->soa_off.ensure(Rc * 8)); CK(h->soa_ncl.ensure(Rc * 4)); CK(h->soa_lseq.ensure(Rc * 4)); CK(h->long_list.ensure(Rc * 4));
         RecordSoA soa{h->soa_start.as<uint64_t>(), h->soa_span.as<uint32_t>(), h->soa_meta.as<uint32_t>(), h->soa_off.as<int64_t>(), h->soa_ncl.as<uint32_t>(), h->soa_lseq.as<int32_t>()};
-        ScanStats zs{0, 0, 0, 0, ~0ull, 0, 0, ~0ull};
+        ScanStats zs{0, 0, 0, 0, ~0ull, 0, 0, ~0ull, 0};
+        const int64_t ghost_below = (fix && batch_no > 0) ? (int64_t)ghost_below_abs - (int64_t)batch_u0 : INT64_MIN;
         UP(h->scan_stats.p, &zs, sizeof zs);
         if (mode == RUN_SCAN_ONLY && !h->ref_has.p) { CK(h->ref_has.ensure((nref / 32 + 2) * 4)); CK(cudaMemsetAsync(h->ref_has.p, 0, (nref / 32 + 2) * 4, sm)); }
-        if (d_fprog)
-            BD_LAUNCH((unsigned)((nb * 32 + 255) / 256), 256, 0, sm, k2_decode<true>)(sp, h->chunk_start.as<int64_t>(), (uint32_t)nb, h->slot_base.as<uint32_t>(), h->slots.as<uint16_t>(), h->count.as<uint32_t>(), h->rec_base.as<uint32_t>(), soa, h->mapq_gt, h->flag_reject, h->scan_stats.as<ScanStats>(), h->long_list.as<uint32_t>(), h->ref_has.as<uint32_t>(), rgt, d_fprog);
-        else
-            BD_LAUNCH((unsigned)((nb * 32 + 255) / 256), 256, 0, sm, k2_decode<false>)(sp, h->chunk_start.as<int64_t>(), (uint32_t)nb, h->slot_base.as<uint32_t>(), h->slots.as<uint16_t>(), h->count.as<uint32_t>(), h->rec_base.as<uint32_t>(), soa, h->mapq_gt, h->flag_reject, h->scan_stats.as<ScanStats>(), h->long_list.as<uint32_t>(), h->ref_has.as<uint32_t>(), rgt, d_fprog);
+#define K2_DECODE(F, G) BD_LAUNCH((unsigned)((nb * 32 + 255) / 256), 256, 0, sm, k2_decode<F, G>)(sp, h->chunk_start.as<int64_t>(), (uint32_t)nb, h->slot_base.as<uint32_t>(), h->slots.as<uint16_t>(), h->count.as<uint32_t>(), h->rec_base.as<uint32_t>(), soa, h->mapq_gt, h->flag_reject, h->scan_stats.as<ScanStats>(), h->long_list.as<uint32_t>(), h->ref_has.as<uint32_t>(), rgt, d_fprog, ghost_below)
+        if (fix) { if (d_fprog) K2_DECODE(true, true); else K2_DECODE(false, true); }
+        else if (d_fprog) K2_DECODE(true, false);
+        else K2_DECODE(false, false);
+#undef K2_DECODE
         CK(cudaGetLastError()); st.gpu_launches++;
         DOWN(ssp, ScanStats, h->scan_stats.p, sizeof(ScanStats));
         CK(cudaEventRecord(e3, sm));
         CK(cudaStreamSynchronize(sm));
         const ScanStats ss = *ssp;
+        st.n_records -= ss.n_ghost;          // re-read records of the previous batch were counted there
         if (ss.rg_err != ~0ull) return fail(h, BDEPTH_ERR_FORMAT, "error in read #%llu of the batch: its read group is not present in the header", ss.rg_err);
         st.n_records_pass += ss.n_pass; st.n_cigar_ops += ss.n_cigar; st.seq_bytes += ss.seq_bytes; st.long_reads += ss.n_long;
         if (ss.n_pass) { shard_min = std::min<uint64_t>(shard_min, ss.min_start); shard_max = std::max<uint64_t>(shard_max, ss.max_end); }
@@ -881,8 +898,14 @@ int run_pipeline(bdepth* h, RunMode mode, RunOut* ro, Emitter* em = nullptr) {
             }
         }
         // ---- -m: take the worse mate of every overlapping pair out again (mates.cuh)
-        if (fix && ss.n_pass) {
-            if (!last_batch || !last_sub || subs.size() != 1 || batch_no != 0) return fail(h, BDEPTH_ERR_ARG, "internal: fix-mate-overlaps needs the shard in one batch");
+        if (fix) {      // where the next batch's stream begins if nothing is open: the first record this batch did not consume
+            const uint64_t tail_abs = batch_u0 + (uint64_t)tail; size_t lo = 0, hi = B.size(); while (lo + 1 < hi) { size_t m2 = (lo + hi) / 2; if (B[m2].uoff <= tail_abs) lo = m2; else hi = m2; }
+            ghost_b = lo; ghost_entry = (int64_t)(tail_abs - B[lo].uoff); ghost_below_abs = tail_abs;
+        }
+        if (fix && R && (ss.n_pass || ss.n_ghost)) {
+            if (subs.size() != 1) return fail(h, BDEPTH_ERR_ARG, "internal: fix-mate-overlaps scans a batch as a whole");
+            uint64_t s_last = 0;       // start of the batch's last record: nothing that follows starts before it
+            CK(cudaMemcpyAsync(&s_last, soa.start + (R - 1), 8, cudaMemcpyDeviceToHost, sm)); CK(cudaStreamSynchronize(sm));
             cudaEvent_t em0 = h->ev[20], em1 = h->ev[21];
             CK(cudaEventRecord(em0, sm));
             CK(h->m_hash.ensure(Rc * 8)); CK(h->m_flag.ensure(Rc * 4)); CK(h->m_ctl.ensure(64));
@@ -892,40 +915,49 @@ int run_pipeline(bdepth* h, RunMode mode, RunOut* ro, Emitter* em = nullptr) {
             const uint32_t n_flt = (uint32_t)h->regions.size();
             CK(h->m_flt.ensure(fl.size() * 8 + 16));
             if (n_flt) CK(cudaMemcpyAsync(h->m_flt.p, fl.data(), fl.size() * 8, cudaMemcpyHostToDevice, sm));
-            CK(cudaMemsetAsync(h->m_ctl.p, 0, 64, sm));
+            CK(cudaMemsetAsync(h->m_ctl.p, 0, 64, sm)); CK(cudaMemsetAsync((uint8_t*)h->m_ctl.p + 48, 0xFF, 16, sm));       // err, stat; open_off = open_start = none
             const bool segm = h->seg.on && h->seg.n;
             MateParams mp{soa.start, soa.span, soa.meta, soa.off, soa.ncl, soa.lseq, u0, (uint32_t)R, h->m_hash.as<uint64_t>(), h->m_flag.as<uint32_t>(),
                           h->m_flt.as<uint64_t>(), h->m_flt.as<uint64_t>() + n_flt, n_flt, h->counts.as<uint32_t>(), h->cnt_base, h->win_len, h->S, h->minq,
                           segm ? h->seg.s.as<uint64_t>() : nullptr, segm ? h->seg.e.as<uint64_t>() : nullptr, segm ? h->seg.pmax.as<uint64_t>() : nullptr, segm ? h->seg.id.as<uint32_t>() : nullptr,
                           segm ? h->seg.n : 0u, segm ? h->seg.reads.as<uint32_t>() : nullptr, segm ? h->seg.mbases.as<uint32_t>() : nullptr, h->S,
                           segm && h->seg.has_u ? h->seg.ustart.as<uint64_t>() : nullptr, segm && h->seg.has_u && h->seg.has_min ? h->seg.minstart.as<uint64_t>() : nullptr, segm && h->seg.has_u ? h->seg.ext_max : 0ull,
-                          h->tile_lo.as<uint32_t>(), idx_tiles_base, idx_n_tiles, h->long_list.as<uint32_t>(), (uint32_t)ss.n_long, 0,
+                          h->tile_lo.as<uint32_t>(), idx_tiles_base, idx_n_tiles, h->long_list.as<uint32_t>(), (uint32_t)ss.n_long,
+                          (uint32_t)ss.n_ghost, s_last, prev_s_last, covered_from, last_batch ? 1 : 0, (unsigned long long*)((uint8_t*)h->m_ctl.p + 48), (unsigned long long*)((uint8_t*)h->m_ctl.p + 56), 0,
                           (int*)h->m_ctl.p, (unsigned long long*)((uint8_t*)h->m_ctl.p + 16)};
             const unsigned mg = (unsigned)((R + 127) / 128);
             BD_LAUNCH(mg, 128, 0, sm, km_hash)(mp); BD_LAUNCH(mg, 128, 0, sm, km_link)(mp); BD_LAUNCH(mg, 128, 0, sm, km_fix)(mp);
+            if (!last_batch) { BD_LAUNCH(mg, 128, 0, sm, km_cover)(mp); st.gpu_launches++; }
             CK(cudaGetLastError()); st.gpu_launches += 3;
             CK(cudaEventRecord(em1, sm));
-            struct { int err[4]; unsigned long long stat[3]; } ctl;
+            struct { int err[4]; unsigned long long stat[3]; unsigned long long pad; unsigned long long open_off, open_start; } ctl;
             CK(cudaMemcpyAsync(&ctl, h->m_ctl.p, sizeof ctl, cudaMemcpyDeviceToHost, sm));
             CK(cudaStreamSynchronize(sm));
             if (ctl.err[0] == MATE_ERR_TOO_MANY) return fail(h, BDEPTH_ERR_ARG, "fix-mate-overlaps: more than %d overlapping reads share one name (record #%d of the batch)", MATE_MAX_MEMBERS, ctl.err[1]);
-            st.mate_pairs = ctl.stat[0]; st.mate_pair_columns = ctl.stat[1]; st.mate_groups = ctl.stat[2];
-            { float t = 0; CK(cudaEventElapsedTime(&t, em0, em1)); st.ms_mates = t; }
+            if (ctl.err[0] == MATE_ERR_CROSS) return fail(h, BDEPTH_ERR_ARG, "fix-mate-overlaps: four or more overlapping reads of one name next to a batch boundary (record #%d of the batch): not reproduced there, use larger batches", ctl.err[1]);
+            st.mate_pairs += ctl.stat[0]; st.mate_pair_columns += ctl.stat[1]; st.mate_groups += ctl.stat[2];
+            if (!last_batch && ctl.open_off != ~0ull && batch_u0 + (ctl.open_off - 4) < ghost_below_abs) {      // something is still open: re-read from its first record
+                const uint64_t g_abs = batch_u0 + (ctl.open_off - 4); size_t lo = 0, hi = B.size(); while (lo + 1 < hi) { size_t m2 = (lo + hi) / 2; if (B[m2].uoff <= g_abs) lo = m2; else hi = m2; }
+                ghost_b = lo; ghost_entry = (int64_t)(g_abs - B[lo].uoff);
+            }
+            prev_s_last = s_last; covered_from = ctl.open_start;
+            { float t = 0; CK(cudaEventElapsedTime(&t, em0, em1)); st.ms_mates += t; }
         }
         CK(cudaEventRecord(e4, sm));
-        if (em && mode == RUN_FULL && h->world == 1 && !last_batch && ss.n_pass) { int rce = em->advance(ss.max_start / TILE_POS * TILE_POS, e4); if (rce) return rce; }
+        if (em && mode == RUN_FULL && h->world == 1 && !fix && !last_batch && ss.n_pass) { int rce = em->advance(ss.max_start / TILE_POS * TILE_POS, e4); if (rce) return rce; }
         // ---- carry the incomplete tail record to the front of the next batch
         uint64_t new_carry = (uint64_t)((int64_t)ub - tail);
-        if (!last_batch && last_sub && new_carry) {      // inside a batch the tail already sits right below the next sub-batch
+        if (!last_batch && last_sub && new_carry && !fix) {      // inside a batch the tail already sits right below the next sub-batch; -m re-reads it with the next batch
             if (new_carry > CARRY_MAX) return fail(h, BDEPTH_ERR_FORMAT, "BAM record larger than %zu bytes", CARRY_MAX);
             CK(cudaMemcpyAsync(m_u0 - new_carry, u0 + tail, new_carry, cudaMemcpyDeviceToDevice, sm));
         }
         CK(cudaStreamSynchronize(sm));
         { float t; if (!h->staged && last_sub) { CK(cudaEventElapsedTime(&t, h->ev[18 + (batch_no & 1)], h->ev[14 + (batch_no & 1)])); ms_h2d += t; } if (last_sub) { CK(cudaEventElapsedTime(&t, e1, e2)); ms_k1 += t; } CK(cudaEventElapsedTime(&t, e2, e3)); ms_k2 += t; CK(cudaEventElapsedTime(&t, e3, e4)); ms_k3 += t; }
-        carry_len = last_batch ? 0 : new_carry; first_batch = false;
+        carry_len = (last_batch || fix) ? 0 : new_carry; first_batch = false;
         hs.used = 0;      // synchronised above: the scratch is free again
         }   // sub-batches
-        b = mb1; batch_no++;
+        }   // stream scope
+        b = b1; batch_no++;
     }
     st.ms_h2d = ms_h2d; st.ms_inflate = ms_k1; st.ms_scan = ms_k2; st.ms_coverage = ms_k3;
     st.positions = mode == RUN_FULL ? h->hdr.total_len : 0;
@@ -1102,7 +1134,7 @@ long bdepth_plan_region_chunks(const char* bam_path, const bdepth_region* region
     return (long)cs.size();
 }
 int bdepth_set_tuning(bdepth_t* h, uint64_t batch_inflated_bytes, uint64_t chunk_blocks) {
-    if (batch_inflated_bytes) h->batch_u = std::max<uint64_t>(batch_inflated_bytes, 1 << 20);
+    if (batch_inflated_bytes) h->batch_u = std::max<uint64_t>(batch_inflated_bytes, 1 << 16);
     if (chunk_blocks) h->chunk_blocks = chunk_blocks;
     h->staged = false;
     return 0;

@@ -36,7 +36,8 @@
 namespace bdk {
 
 constexpr int MATE_MAX_MEMBERS = 8;
-enum MateErr : int { MATE_OK = 0, MATE_ERR_TOO_MANY = 1 };
+enum MateErr : int { MATE_OK = 0, MATE_ERR_TOO_MANY = 1, MATE_ERR_CROSS = 2 };
+constexpr uint32_t MATE_NCL_GHOST = 1u << 31;      // RecordSoA.ncl bit of a re-read record of the previous batch (kernels.cuh NCL_GHOST)
 enum MateFlag : uint32_t { MF_INSTREAM = 1u, MF_HAS_PRED = 2u, MF_HAS_SUCC = 4u };
 
 struct MateParams {
@@ -61,6 +62,15 @@ struct MateParams {
     // K3's read index, for the one question that needs the other reads of a column (mate_follows): per 1024-position
     // tile the first passing short read overlapping it, and the list of long reads
     const uint32_t* tile_lo; uint64_t tiles_base; uint32_t n_tiles; const uint32_t* long_list; uint32_t n_long;
+    // Several batches.  The first n_ghost rows are records of the previous batch, re-read (pass bit clear, ncl bit 31 set if
+    // they pass the filter) because they can still meet a mate: a component (chain of overlapping same-hash reads) is
+    // fixed in the batch in which it closes -- its reach does not go beyond s_last, the start of the batch's last record
+    // (later records start there or further right) -- and a component made of ghosts only that had already closed in the
+    // previous batch (reach <= prev_s_last) is left alone.  What has to be re-read next time -- the leaders of open
+    // components and every read that ends after s_last -- lowers *open_off (offset relative to u).
+    // km_cover then adds every read that reaches into the columns of something open, so that the next batch knows all
+    // reads of those columns (covered_from = the previous batch's *open_start; mate_follows needs them).
+    uint32_t n_ghost; uint64_t s_last, prev_s_last, covered_from; int last_batch; unsigned long long* open_off; unsigned long long* open_start;
     int force_general;           // tests: send pairs through the state-machine path as well
     int* err;                    // err[0] = MateErr, err[1] = record index
     unsigned long long* stat;    // [0] pairs, [1] (pair, column) fixes, [2] components with more than two members
@@ -71,11 +81,13 @@ BD_HD void m_add(uint32_t* p, uint32_t v) { atomicAdd(p, v); }
 BD_HD void m_or(uint32_t* p, uint32_t v) { atomicOr(p, v); }
 BD_HD void m_stat(unsigned long long* p, unsigned long long v) { atomicAdd(p, v); }
 BD_HD void m_err(const MateParams& p, int code, uint32_t r) { if (atomicMax(p.err, code) < code) p.err[1] = (int)r; }
+BD_HD void m_min(unsigned long long* p, unsigned long long v) { atomicMin(p, v); }
 #else
 BD_HD void m_add(uint32_t* p, uint32_t v) { *p += v; }
 BD_HD void m_or(uint32_t* p, uint32_t v) { *p |= v; }
 BD_HD void m_stat(unsigned long long* p, unsigned long long v) { *p += v; }
 BD_HD void m_err(const MateParams& p, int code, uint32_t r) { if (p.err[0] < code) { p.err[0] = code; p.err[1] = (int)r; } }
+BD_HD void m_min(unsigned long long* p, unsigned long long v) { if (v < *p) *p = v; }
 #endif
 
 BD_HD uint32_t m_ld32(const uint8_t* q) { return (uint32_t)q[0] | ((uint32_t)q[1] << 8) | ((uint32_t)q[2] << 16) | ((uint32_t)q[3] << 24); }
@@ -90,7 +102,7 @@ struct MRead {
 BD_HD void m_load(const MateParams& p, uint32_t r, MRead& m) {
     m.s = p.start[r]; m.span = p.span[r]; m.e = m.s + m.span;
     uint32_t mt = p.meta[r]; m.mapq = (mt >> 8) & 0xFFu; m.sample = (mt >> 2) & 63u;
-    uint32_t ncl = p.ncl[r]; m.n_cigar = ncl >> 8; m.l_name = ncl & 0xFFu;
+    uint32_t ncl = p.ncl[r]; m.n_cigar = (ncl >> 8) & 0xFFFFu; m.l_name = ncl & 0xFFu;
     int32_t ls = p.lseq[r]; m.lseq = ls > 0 ? (uint32_t)ls : 0u;
     const uint8_t* rec = p.u + p.off[r];
     m.name = rec + 32; m.cg = m.name + m.l_name; m.seq = m.cg + 4u * m.n_cigar; m.qual = m.seq + (m.lseq + 1) / 2;
@@ -143,7 +155,7 @@ BD_HD void m_count(const MateParams& p, uint32_t* planes, int plane, uint64_t g,
 // ---------------------------------------------------------------------------------------- km_hash
 BD_HD void mate_hash_one(const MateParams& p, uint32_t r) {
     uint32_t fl = 0; uint64_t h = 0;
-    if (p.meta[r] & 1u) {
+    if ((p.meta[r] & 1u) || (p.ncl[r] & MATE_NCL_GHOST)) {
         bool in = true;
         if (p.n_flt) {      // first merged region that ends after the read starts; the read is kept iff it reaches it
             uint64_t s = p.start[r], e = s + p.span[r];
@@ -169,6 +181,7 @@ BD_HD void mate_link_one(const MateParams& p, uint32_t r) {
     for (uint32_t k = r + 1; k < p.R && p.start[k] < e; k++)
         if (p.mhash[k] == h && (p.mflag[k] & MF_INSTREAM)) { m_or(&p.mflag[k], MF_HAS_PRED); any = true; }
     if (any) m_or(&p.mflag[r], MF_HAS_SUCC);
+    if (!p.last_batch && e > p.s_last) { m_min(p.open_off, (unsigned long long)p.off[r]); m_min(p.open_start, p.start[r]); }      // a later batch may bring its mate
 }
 
 // ---------------------------------------------------------------------------------------- km_fix
@@ -251,7 +264,11 @@ BD_HD void mate_fix_pair(const MateParams& p, const MRead& A, const MRead& B) {
 // Is a read with a larger name hash present in column g?  Then a read of hash h is not the last entry of the column's
 // hash-sorted array (depth.d:380-384 treats the last entry differently).  Same search as k3_gather: the short reads from
 // the tile's first overlapping one up to the last that starts at or before g, plus the long reads.
-BD_HD bool mate_follows(const MateParams& p, uint64_t h, uint64_t g) {
+BD_HD bool mate_follows(const MateParams& p, uint64_t h, uint64_t g, uint32_t who) {
+    // the re-read records hold every read that reaches column covered_from or beyond (km_cover); left of it the column is not fully known
+    if (p.n_ghost && g < p.covered_from) { m_err(p, MATE_ERR_CROSS, who); return true; }
+    for (uint32_t k = 0; k < p.n_ghost && p.start[k] <= g; k++)           // re-read records are not in K3's index
+        if ((p.mflag[k] & MF_INSTREAM) && p.start[k] + p.span[k] > g && p.mhash[k] > h) return true;
     if (g >= p.tiles_base) {
         uint64_t t = (g - p.tiles_base) >> 10;
         if (t < p.n_tiles) {
@@ -306,7 +323,7 @@ BD_HD void mate_fix_group(const MateParams& p, const uint32_t* idx, int n, uint3
             if (st[a]) {
                 // Alone again: `past` -- unless it is the very last entry of the column's sorted array and its predecessor has
                 // the same hash; then the reference leaves it as it is (depth.d:380-384).
-                if (!(np >= 2 && st[a] != 3 && !mate_follows(p, p.mhash[idx[a]], g))) st[a] = 3;
+                if (!(np >= 2 && st[a] != 3 && !mate_follows(p, p.mhash[idx[a]], g, leader))) st[a] = 3;
             }
             i += 1;
         }
@@ -377,6 +394,8 @@ BD_HD void mate_fix_one(const MateParams& p, uint32_t r) {
         idx[n++] = k;
         uint64_t e = p.start[k] + p.span[k]; if (e > reach) reach = e;
     }
+    if (!p.last_batch && reach > p.s_last) { m_min(p.open_off, (unsigned long long)p.off[r]); m_min(p.open_start, p.start[r]); return; }      // still open: the batch that closes it fixes it
+    if (p.n_ghost && idx[n - 1] < p.n_ghost && reach <= p.prev_s_last) return;                                   // only re-read records, closed before: already fixed
     if (n == 2 && !p.force_general && !p.seg_u) {
         MRead A, B; m_load(p, idx[0], A); m_load(p, idx[1], B);
         if (m_same_name(A, B)) mate_fix_pair(p, A, B);
@@ -386,7 +405,13 @@ BD_HD void mate_fix_one(const MateParams& p, uint32_t r) {
     mate_fix_group(p, idx, n, r);
 }
 
+// every read that reaches into the columns of an open component has to be re-read with it (after km_link and km_fix)
+BD_HD void mate_cover_one(const MateParams& p, uint32_t r) {
+    if ((p.mflag[r] & MF_INSTREAM) && p.start[r] + p.span[r] > *p.open_start) m_min(p.open_off, (unsigned long long)p.off[r]);
+}
+
 #if defined(__CUDACC__) || defined(BDEPTH_EMULATE_SHIM)
+__global__ void km_cover(MateParams p) { uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; if (r < p.R) mate_cover_one(p, r); }
 __global__ void km_hash(MateParams p) { uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; if (r < p.R) mate_hash_one(p, r); }
 __global__ void km_link(MateParams p) { uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; if (r < p.R) mate_link_one(p, r); }
 __global__ void km_fix(MateParams p) { uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; if (r < p.R) mate_fix_one(p, r); }

@@ -117,3 +117,45 @@ def test_window_mode(pairs, tmp_path):
     for w, o in ((100, 50), (100, 30), (90, 80), (64, 63)):
         check_same(["window", "-w", str(w), "--overlap", str(o), "-m", "-T", "2", "-T", "5", q])
     check_same(["window", "-w", "1000", "--overlap", "300", "-m", "-T", "3", p])
+
+
+def test_several_batches(pairs, tmp_path):
+    """-m across batch boundaries: 1 MB batches cut the pair stream many times; the counters, the pair statistics and the
+    region / window tables must equal the one-batch run and the oracle."""
+    import sambamba_b200 as sb
+    import test_emul_mates as tem
+    p = pairs[0]
+    want, npc = helpers.oracle_counts_fix_mates(p)
+    regs = [(0, 100, 900), (0, 1000, 1200), (0, 1200, 1207), (1, 10, 20), (2, 5, 40000)]
+    with sb.BDepth(p) as b:
+        b.set_fix_mates(True)
+        one = b.run_base()
+        st1 = b.stats()
+        r1 = b.run_regions(regs, [3, 10])
+        w1 = b.run_windows(700, 300, [2])
+        b.set_tuning(1 << 20, 0)
+        many = b.run_base()
+        st = b.stats()
+        assert st["n_batches"] >= 4 and st1["n_batches"] == 1
+        assert np.array_equal(one, want) and np.array_equal(many, want)
+        assert st["mate_pair_columns"] == npc == st1["mate_pair_columns"] and st["mate_pairs"] == st1["mate_pairs"] and st["n_records"] == st1["n_records"]
+        assert b.run_regions(regs, [3, 10]) == r1
+        assert b.run_windows(700, 300, [2]) == w1
+        for batch in (1 << 16, 200000, 3 << 16):      # down to one BGZF block per batch: a boundary every 64 KB
+            b.set_tuning(batch, 0)
+            assert np.array_equal(b.run_base(), want), batch
+            stb = b.stats()
+            assert stb["mate_pair_columns"] == npc and stb["n_records"] == st1["n_records"]
+        b.set_tuning(1 << 16, 0)
+        assert b.run_regions(regs, [3, 10]) == r1
+    # names with three and more reads, dense, in small batches
+    q = tem.make_pairs_bam(str(tmp_path / "tri.bam"), 91, n_frag=4000, refs=(("c1", 6000), ("c2", 2500)), triples=0.3)
+    want, npc = helpers.oracle_counts_fix_mates(q)
+    with sb.BDepth(q) as b:
+        b.set_fix_mates(True)
+        for batch in (1 << 20, 1 << 16):
+            b.set_tuning(batch, 0)
+            got = b.run_base()
+            st = b.stats()
+            assert st["n_batches"] >= 2 and st["mate_groups"] > 50
+            assert np.array_equal(got, want), batch
