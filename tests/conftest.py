@@ -19,14 +19,11 @@ EMULATE = os.environ.get("BDEPTH_EMULATE") == "1"
 def pytest_collection_modifyitems(config, items):
     """BDEPTH_EMULATE=1 (TEST INFRASTRUCTURE): run the `gpu` tests on the CPU against tests/emul/libbdepth_emul.so, the
     same pipeline and kernels compiled with g++ over a CUDA-on-CPU emulation (tests/emul/cuda_shim.hpp).  The multi-GPU
-    tests run with ranks as threads over an NCCL stand-in; the full-size ones stay out.  Nothing of this ever touches the
-    product library."""
+    tests run with ranks as threads over an NCCL stand-in; the full-size test runs its own logic on a small file.  Nothing
+    of this ever touches the product library."""
     if not EMULATE:
         return
-    skip = pytest.mark.skip(reason="not under CPU emulation (full size)")
-    for it in items:
-        if "fullsize" in it.nodeid:
-            it.add_marker(skip)
+    del items      # every gpu test has an emulation-sized variant of its input (see the tests)
 
 
 @pytest.fixture(scope="session", autouse=True)
