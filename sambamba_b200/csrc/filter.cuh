@@ -35,6 +35,8 @@ enum FilterOpCode : uint8_t {
     FO_NAME,           // push read_name <cmp> pool[s_off, s_len)                 StringFieldFilter("read_name")
     FO_STRAND,         // push strand <cmp> pool[s_off]                           StringFieldFilter("strand")
     FO_STRTAG,         // push string/char tag <cmp> pool[...]                    StringTagFilter
+    FO_SEQ,            // push cmp(sequence, pool[...]) <cmp> 0                   StringFieldFilter("sequence")
+    FO_CIGAR,          // push cigarString() <cmp> pool[...]                      StringFieldFilter("cigar")
     FO_AND, FO_OR, FO_NOT
 };
 enum FilterCmp : uint8_t { FC_GT = 0, FC_LT, FC_GE, FC_LE, FC_EQ, FC_NE };
@@ -134,6 +136,27 @@ BD_HD bool filter_eval(const FilterProg& fp, const uint8_t* rec, uint32_t rec_si
             break; }
         case FO_NAME: r = f_cmp<int>(o.cmp, f_strcmp(rec + 32, l_name ? l_name - 1 : 0, fp.pool + o.s_off, o.s_len), 0); break;
         case FO_STRAND: r = f_cmp<int>(o.cmp, (flag & 0x10u) ? '-' : '+', (int)(uint8_t)fp.pool[o.s_off]); break;
+        case FO_SEQ: {      // std.algorithm.cmp over the decoded bases (read.d:364-383: "=ACMGRSVTWYHKDBN"), then length
+            const uint8_t* seq = rec + 32 + l_name + 4u * n_cigar; int c = 0; uint32_t k = 0;
+            for (; k < lq && k < o.s_len && seq + (k >> 1) < end; k++) {
+                uint8_t b = seq[k >> 1], nib = (k & 1) ? (b & 15u) : (b >> 4); char ch = "=ACMGRSVTWYHKDBN"[nib], want = fp.pool[o.s_off + k];
+                if (ch != want) { c = (uint8_t)ch < (uint8_t)want ? -1 : 1; break; }
+            }
+            if (!c && !(k < lq && k < o.s_len)) c = lq == o.s_len ? 0 : (lq < o.s_len ? -1 : 1);
+            r = f_cmp<int>(o.cmp, c, 0); break; }
+        case FO_CIGAR: {    // cigarString() (read.d:265-276): decimal length + "MIDNSHP=X????????"[op] per operation, compared as a D string
+            const uint8_t* cg = rec + 32 + l_name; uint32_t pos = 0; int c = 0;
+            for (uint32_t i = 0; i < n_cigar && !c && cg + 4 * i + 4 <= end; i++) {
+                uint32_t raw = f_ld32(cg + 4 * i), len = raw >> 4; char buf[11]; int nd = 0;
+                do { buf[nd++] = (char)('0' + len % 10u); len /= 10u; } while (len);
+                for (int d = nd; d >= 0 && !c; d--) {
+                    char ch = d ? buf[d - 1] : "MIDNSHP=X????????"[raw & 15u];
+                    if (pos >= o.s_len) c = 1;                                  // the literal is a proper prefix of the CIGAR text
+                    else { char want = fp.pool[o.s_off + pos]; if (ch != want) c = (uint8_t)ch < (uint8_t)want ? -1 : 1; pos++; }
+                }
+            }
+            if (!c && pos < o.s_len) c = -1;                                    // the CIGAR text is a proper prefix of the literal
+            r = f_cmp<int>(o.cmp, c, 0); break; }
         case FO_AND: { bool b = (stack >> (sp - 1)) & 1, a = (stack >> (sp - 2)) & 1; sp -= 2; r = a && b; break; }
         case FO_OR: { bool b = (stack >> (sp - 1)) & 1, a = (stack >> (sp - 2)) & 1; sp -= 2; r = a || b; break; }
         case FO_NOT: { bool a = (stack >> (sp - 1)) & 1; sp -= 1; r = !a; break; }

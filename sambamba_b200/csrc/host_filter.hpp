@@ -5,9 +5,9 @@
 // the current position (no word boundaries: "notpaired" is `not` `paired`), binding powers: comparison 110,
 // `not` 100 (prefix), `and` 80, `or` 60, brackets.  Supported nodes: the 13 flag conditions, the integer fields
 // (incl. avg_base_quality), [XX] tags against integers / strings / null, read_name and strand against strings,
-// ref_name / mate_ref_name == / != 'name' (folded into ref_id comparisons).  Refused with a message (never
-// evaluated differently): regular expressions (=~), sequence / cigar string comparisons, ordering comparisons of
-// reference names.  Unlike the reference, tokens left over after a complete expression are an error.
+// sequence and cigar against strings, ref_name / mate_ref_name == / != 'name' (folded into ref_id comparisons).
+// Refused with a message (never evaluated differently): regular expressions (=~), ordering comparisons of reference
+// names.  Unlike the reference, tokens left over after a complete expression are an error.
 #pragma once
 #include <stdint.h>
 #include <string.h>
@@ -171,6 +171,7 @@ struct FilterCompiler {
                 if (id == -2) { o.op = FO_CONST; o.imm = o.cmp == FC_NE; return push(p, o); }
                 o.op = FO_INTFIELD; o.a = a.s == "ref_name" ? FF_REF_ID : FF_MATE_REF_ID; o.imm = id; return push(p, o);
             }
+            if (a.s == "sequence" || a.s == "cigar") { o.op = a.s == "sequence" ? FO_SEQ : FO_CIGAR; if (!pool(p, b.s, o, used)) return false; return push(p, o); }
             err = "comparisons of `" + a.s + "` are not available in the GPU engine yet"; return false; }
         default: err = "filter string must represent a condition"; return false;
         }

@@ -22,7 +22,7 @@ def em():
 
 
 class Rec:
-    __slots__ = ("ref", "pos", "mapq", "flag", "lseq", "mref", "mpos", "tlen", "name", "qual", "tags", "off", "size")
+    __slots__ = ("ref", "pos", "mapq", "flag", "lseq", "mref", "mpos", "tlen", "name", "qual", "tags", "off", "size", "cigar", "seq")
 
 
 def parse_all(u):
@@ -37,6 +37,9 @@ def parse_all(u):
         r.ref, r.pos, bmn, fnc, r.lseq, r.mref, r.mpos, r.tlen = struct.unpack_from("<iiIIiiii", b, o + 4)
         ln, r.mapq, r.flag, nc = bmn & 0xFF, (bmn >> 8) & 0xFF, fnc >> 16, fnc & 0xFFFF
         r.name = b[o + 36:o + 36 + ln - 1]
+        r.cigar = b"".join(b"%d%c" % (c >> 4, b"MIDNSHP=X????????"[c & 15]) for c in struct.unpack_from("<%dI" % nc, b, o + 36 + ln))
+        s0 = o + 36 + ln + 4 * nc
+        r.seq = bytes(b"=ACMGRSVTWYHKDBN"[(b[s0 + (k >> 1)] & 15) if k & 1 else (b[s0 + (k >> 1)] >> 4)] for k in range(max(r.lseq, 0)))
         q0 = o + 36 + ln + 4 * nc + (r.lseq + 1) // 2
         r.qual = b[q0:q0 + r.lseq]
         r.tags = {}
@@ -154,14 +157,19 @@ QUERIES = [
     ("strand != '+' and ref_name == 'c2'", lambda r: bool(r.flag & 0x10) and r.ref == 1),
     ("ref_name == 'weird name' or ref_name == 'nope'", lambda r: r.ref == 2),
     ("ref_name != 'nope' and mate_ref_name == '*'", lambda r: r.mref == -1),
+    ("cigar == '35M'", lambda r: r.cigar == b"35M"),
+    ("cigar > '20M' and cigar <= '35M'", lambda r: b"20M" < r.cigar <= b"35M"),
+    ("cigar != '10M' and cigar < '3'", lambda r: r.cigar != b"10M" and r.cigar < b"3"),
+    ("sequence >= 'G'", lambda r: r.seq >= b"G"),
+    ("sequence < 'ACGT' or sequence == ''", lambda r: r.seq < b"ACGT" or r.seq == b""),
     ("notpaired", lambda r: not r.flag & 1),
     ("duplicate  and\tnot\nfailed_quality_control", lambda r: bool(r.flag & 0x400) and not r.flag & 0x200),
     ("((mapping_quality > 10))", lambda r: r.mapq > 10),
     ("mapping_quality > -1 and position > +5", lambda r: r.pos > 5),
 ]
 
-BAD = ["", "mapping_quality", "mapping_quality >", "paired and", "(paired", "paired)", "paired unmapped", "read_name =~ /^r/", "[RG] =~ /x/", "sequence == 'ACGT'",
-       "cigar == '50M'", "ref_name > 'c1'", "mapping_quality == 'x'", "read_name == 5", "position == null", "5 > 3", "not 5", "paired and 5", "frobnicate", "[NMX] == 1",
+BAD = ["", "mapping_quality", "mapping_quality >", "paired and", "(paired", "paired)", "paired unmapped", "read_name =~ /^r/", "[RG] =~ /x/", "sequence =~ /ACGT/",
+       "cigar == 50", "ref_name > 'c1'", "mapping_quality == 'x'", "read_name == 5", "position == null", "5 > 3", "not 5", "paired and 5", "frobnicate", "[NMX] == 1",
        "mapping_quality > 5 > 3"]
 
 
