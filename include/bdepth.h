@@ -117,6 +117,12 @@ typedef struct {
 int  bdepth_device_count(void);
 /* Open a BAM by path (mmap) -- also looks for <path>.bai / <path minus ext>.bai. */
 int  bdepth_open(const char* bam_path, int device, bdepth_t** out);
+/* The same, but the BGZF members of the file are framed only as far as the header needs.  A region query (regions set,
+ * usable .bai) then touches nothing but the header and the members inside its BAI chunks, as the reference's
+ * RandomAccessManager does (randomaccessmanager.d:316-338) -- bdepth_open reads the 18-byte header and the footer of every
+ * member of the file up front, which for a cold multi-100-GB file is most of the cost of a small query.  Any run that
+ * needs the whole file frames the rest when it starts (framing errors are then reported by that run). */
+int  bdepth_open_lazy(const char* bam_path, int device, bdepth_t** out);
 /* Open a BAM image held in host memory (pinned memory gives full-rate H2D).  bai may be NULL. */
 int  bdepth_open_memory(const void* bam, size_t bam_len, const void* bai, size_t bai_len, int device, bdepth_t** out);
 void bdepth_close(bdepth_t* h);

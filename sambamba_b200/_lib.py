@@ -69,6 +69,7 @@ def load_library():
     vp = C.c_void_p
     L.bdepth_device_count.restype = C.c_int
     L.bdepth_open.argtypes = [C.c_char_p, C.c_int, C.POINTER(vp)]
+    L.bdepth_open_lazy.argtypes = [C.c_char_p, C.c_int, C.POINTER(vp)]
     L.bdepth_open_memory.argtypes = [vp, C.c_size_t, vp, C.c_size_t, C.c_int, C.POINTER(vp)]
     L.bdepth_close.argtypes = [vp]
     L.bdepth_close.restype = None
@@ -115,7 +116,7 @@ def load_library():
 
 
 EXPORTED_SYMBOLS = [
-    "bdepth_device_count", "bdepth_open", "bdepth_open_memory", "bdepth_close", "bdepth_last_error", "bdepth_n_ref",
+    "bdepth_device_count", "bdepth_open", "bdepth_open_lazy", "bdepth_open_memory", "bdepth_close", "bdepth_last_error", "bdepth_n_ref",
     "bdepth_ref_name", "bdepth_ref_length", "bdepth_header_text", "bdepth_is_coordinate_sorted", "bdepth_has_index",
     "bdepth_n_samples", "bdepth_sample_name", "bdepth_set_filter", "bdepth_set_filter_query", "bdepth_set_min_baseq", "bdepth_set_fix_mates", "bdepth_set_combined", "bdepth_set_regions",
     "bdepth_set_shard", "bdepth_nccl_unique_id", "bdepth_plan_shards", "bdepth_plan_region_chunks", "bdepth_set_tuning", "bdepth_stage", "bdepth_run_resident", "bdepth_run_base", "bdepth_run_base_text",
@@ -156,7 +157,7 @@ def plan_region_chunks(path, regions):
 class BDepth:
     """Thin object wrapper over the C ABI (mirrors what the CLI host does)."""
 
-    def __init__(self, path=None, device=0, memory=None, bai=None):
+    def __init__(self, path=None, device=0, memory=None, bai=None, lazy=False):
         self.L = load_library()
         self.h = C.c_void_p()
         if memory is not None:
@@ -165,7 +166,7 @@ class BDepth:
             bp = bai.ctypes.data_as(C.c_void_p) if bai is not None else None
             rc = self.L.bdepth_open_memory(mp, memory.size, bp, 0 if bai is None else bai.size, device, C.byref(self.h))
         else:
-            rc = self.L.bdepth_open(os.fsencode(path), device, C.byref(self.h))
+            rc = (self.L.bdepth_open_lazy if lazy else self.L.bdepth_open)(os.fsencode(path), device, C.byref(self.h))
         if rc:
             raise BDepthError(rc, self.L.bdepth_last_error(None).decode())
 

@@ -134,6 +134,9 @@ struct bdepth {
     // ---- input
     const uint8_t* file = nullptr; size_t file_len = 0; bool mapped = false; int fd = -1;
     std::vector<HostBlock> blocks; uint64_t total_u = 0;
+    // lazy open (bdepth_open_lazy): `blocks` is a prefix of the file's BGZF members (enough for the header) until somebody
+    // needs them all; a region query never does (plan_sparse frames the members of its BAI chunks on its own)
+    bool lazy = false, framed_all = true; size_t framed_off = 0;
     BamHeader hdr; BaiIndex bai; bool has_index = false;
     int device = 0;
     // ---- config
@@ -240,9 +243,20 @@ int inflate_blocks_to_host(bdepth* h, size_t b0, size_t b1, std::vector<uint8_t>
     return 0;
 }
 
-int finish_open(bdepth* h) {
-    std::string e = index_bgzf(h->file, h->file_len, h->blocks, &h->total_u);
+// frame up to `more` further BGZF members (all of them: SIZE_MAX)
+int frame_more(bdepth* h, size_t more) {
+    if (h->framed_all) return 0;
+    bool eof = false;
+    std::string e = frame_bgzf(h->file, h->file_len, &h->framed_off, &h->total_u, more, UINT64_MAX, h->blocks, &eof);
     if (!e.empty()) return fail(h, BDEPTH_ERR_FORMAT, "%s", e.c_str());
+    if (eof) h->framed_all = true;
+    return 0;
+}
+int ensure_all_blocks(bdepth* h) { return frame_more(h, SIZE_MAX); }
+
+int finish_open(bdepth* h) {
+    h->blocks.clear(); h->total_u = 0; h->framed_off = 0; h->framed_all = false;
+    { int rcf = frame_more(h, h->lazy ? 4 : SIZE_MAX); if (rcf) return rcf; }
     if (h->blocks.empty()) return fail(h, BDEPTH_ERR_FORMAT, "Invalid file format: expected BAM\\1");
     int rc = init_device(h); if (rc) return rc;
     // header: inflate a growing prefix of blocks on the GPU until it parses
@@ -252,6 +266,7 @@ int finish_open(bdepth* h) {
         std::string perr; int pr = parse_bam_header(u.data(), u.size(), h->hdr, perr);
         if (pr == 0) break;
         if (pr < 0) return fail(h, BDEPTH_ERR_FORMAT, "%s", perr.c_str());
+        if (nb == h->blocks.size() && !h->framed_all) { rc = frame_more(h, nb * 3); if (rc) return rc; }
         if (nb == h->blocks.size()) return fail(h, BDEPTH_ERR_FORMAT, "truncated BAM header");
         nb = std::min(h->blocks.size(), nb * 4);
     }
@@ -278,6 +293,7 @@ uint64_t shard_cut_voffset(const std::vector<uint64_t>& vos, uint64_t file_len, 
 // Resolve the block range / entry / limit of this rank's shard.
 int prepare_shard(bdepth* h) {
     if (h->shard_ready) return 0;
+    { int rcf = ensure_all_blocks(h); if (rcf) return rcf; }
     const auto& B = h->blocks;
     auto block_of_u = [&](uint64_t u) { size_t lo = 0, hi = B.size(); while (lo + 1 < hi) { size_t m = (lo + hi) / 2; if (B[m].uoff <= u) lo = m; else hi = m; } return lo; };
     auto block_of_c = [&](uint64_t c) { size_t lo = 0, hi = B.size(); while (lo + 1 < hi) { size_t m = (lo + hi) / 2; if (B[m].coff <= c) lo = m; else hi = m; } return lo; };
@@ -439,45 +455,59 @@ int exchange_boundaries(bdepth* h, uint64_t shard_min, uint64_t shard_max) {
 static bool plan_sparse(bdepth* h) {
     h->sparse_on = false;
     if (h->regions.empty() || !h->sparse_ok || h->world != 1 || h->staged || !h->bai.valid || h->bai.bins.size() != h->hdr.ref_len.size()) return false;
-    const auto& B = h->blocks; if (B.empty()) return false;
+    const auto& P = h->blocks; if (P.empty()) return false;          // the framed prefix of the file: at least the header's members
+    uint64_t vo_first;
     {   // a credible index starts where the records start (a dummy or foreign .bai is accepted by the reference, which only
         // checks that one exists, depth.d:1166 -- it must not make reads disappear here)
         uint64_t mn = UINT64_MAX; for (uint64_t v : h->bai.min_chunk_beg) mn = std::min(mn, v);
-        size_t lo = 0, hi = B.size(); while (lo + 1 < hi) { size_t m = (lo + hi) / 2; if (B[m].uoff <= h->hdr.first_rec_off) lo = m; else hi = m; }
-        uint64_t vo_first = (B[lo].coff << 16) | (h->hdr.first_rec_off - B[lo].uoff);
-        if (h->hdr.first_rec_off - B[lo].uoff >= B[lo].isize && lo + 1 < B.size()) vo_first = B[lo + 1].coff << 16;
+        size_t lo = 0, hi = P.size(); while (lo + 1 < hi) { size_t m = (lo + hi) / 2; if (P[m].uoff <= h->hdr.first_rec_off) lo = m; else hi = m; }
+        vo_first = (P[lo].coff << 16) | (h->hdr.first_rec_off - P[lo].uoff);
+        if (h->hdr.first_rec_off - P[lo].uoff >= P[lo].isize) vo_first = (P[lo].coff + P[lo].bsize) << 16;      // the first record begins the next member
         if (mn != vo_first) { h->sparse_ok = false; return false; }
     }
     std::vector<HostRegion> rg; rg.reserve(h->regions.size());
     for (auto& g : h->regions) rg.push_back(HostRegion{g.ref_id, g.start, g.end});
     std::vector<BaiChunk> cs = region_chunks(h->bai, rg);
-    auto block_at = [&](uint64_t coff) -> long { size_t lo = 0, hi = B.size(); while (lo + 1 < hi) { size_t m = (lo + hi) / 2; if (B[m].coff <= coff) lo = m; else hi = m; } return B[lo].coff == coff ? (long)lo : -1; };
-    struct Seg { size_t b0, b1; uint32_t entry, limit; };      // blocks [b0, b1], entry inside b0, limit inside b1
+    // Frame the members the chunks touch straight from the file (sorted by offset; no need for the whole file's table).
+    std::vector<HostBlock> L; bool file_end = false; uint64_t end_coff = 0;      // end_coff: offset after the last member once the end has been seen
+    auto frame_to = [&](uint64_t from, uint64_t to) -> bool {       // make sure every member starting in [from, to] is in L; from must be a member start
+        if (from >= h->file_len) return true;
+        size_t off = (size_t)from; uint64_t dummy = 0; bool eof = false;
+        if (!L.empty() && L.back().coff >= from) { if (L.back().coff >= to) return true; off = (size_t)(L.back().coff + L.back().bsize); }
+        else if (!L.empty() && L.back().coff + L.back().bsize > from) return false;       // begins inside a member framed before: not a member start
+        std::vector<HostBlock> add; std::string e = frame_bgzf(h->file, h->file_len, &off, &dummy, SIZE_MAX, to, add, &eof);
+        if (!e.empty()) return false;
+        if (eof) { file_end = true; end_coff = off; }
+        L.insert(L.end(), add.begin(), add.end());
+        return true;
+    };
+    auto block_at = [&](uint64_t coff) -> long { if (L.empty()) return -1; size_t lo = 0, hi = L.size(); while (lo + 1 < hi) { size_t m = (lo + hi) / 2; if (L[m].coff <= coff) lo = m; else hi = m; } return L[lo].coff == coff ? (long)lo : -1; };
+    struct Seg { size_t b0, b1; uint32_t entry, limit; };      // members L[b0..b1], entry inside b0, limit inside b1
     std::vector<Seg> segs;
     for (const BaiChunk& c : cs) {
+        if (c.beg < vo_first) { h->sparse_ok = false; return false; }                        // the header's members are never part of a chunk
+        if (!frame_to(c.beg >> 16, c.end >> 16)) { h->sparse_ok = false; return false; }      // the index does not describe this file
         long kb = block_at(c.beg >> 16), ke = block_at(c.end >> 16);
         uint32_t wb = (uint32_t)(c.beg & 0xFFFF), we = (uint32_t)(c.end & 0xFFFF);
-        if (kb < 0) { h->sparse_ok = false; return false; }                                   // the index does not describe this file
-        if (ke < 0) { if ((c.end >> 16) >= h->file_len || (c.end >> 16) >= B.back().coff + B.back().bsize) { ke = (long)B.size() - 1; we = B.back().isize; } else { h->sparse_ok = false; return false; } }
-        if (wb >= B[kb].isize) { kb++; wb = 0; if ((size_t)kb >= B.size()) continue; }      // "end of block" == start of the next one
-        if (we == 0) { if (ke == 0) continue; ke--; we = B[ke].isize; }
-        if (we > B[ke].isize) { h->sparse_ok = false; return false; }
+        if (kb < 0) { if (file_end && (c.beg >> 16) >= end_coff) continue; h->sparse_ok = false; return false; }
+        if (ke < 0) { if (file_end && (c.end >> 16) >= end_coff) { ke = (long)L.size() - 1; we = L.back().isize; } else { h->sparse_ok = false; return false; } }
+        if (wb >= L[kb].isize) { kb++; wb = 0; if ((size_t)kb >= L.size()) continue; }      // "end of block" == start of the next one
+        if (we == 0) { if (ke == 0) continue; ke--; we = L[ke].isize; }
+        if (we > L[ke].isize) { h->sparse_ok = false; return false; }
         if (ke < kb || (ke == kb && we <= wb)) continue;
-        // the header blocks are never part of a segment; a chunk cannot begin before the first record
-        if (B[kb].uoff + wb < h->hdr.first_rec_off) { h->sparse_ok = false; return false; }
         if (!segs.empty() && (size_t)kb <= segs.back().b1) {         // touches the previous segment's last block: one segment
             if ((size_t)ke > segs.back().b1 || ((size_t)ke == segs.back().b1 && we > segs.back().limit)) { segs.back().b1 = (size_t)ke; segs.back().limit = we; }
             continue;
         }
         segs.push_back(Seg{(size_t)kb, (size_t)ke, wb, we});
     }
-    size_t nsel = 0; for (auto& sg : segs) nsel += sg.b1 - sg.b0 + 1;
-    if (nsel * 10 > B.size() * 9) return false;                      // nearly the whole file: the plain path is simpler
+    uint64_t sel_bytes = 0; size_t nsel = 0; for (auto& sg : segs) for (size_t k = sg.b0; k <= sg.b1; k++) { sel_bytes += L[k].bsize; nsel++; }
+    if (sel_bytes * 10 > (uint64_t)h->file_len * 9) return false;      // nearly the whole file: the plain path is simpler
     h->vblocks.clear(); h->seg_entry.clear(); h->seg_limit.clear();
     h->vblocks.reserve(nsel); h->seg_entry.reserve(nsel); h->seg_limit.reserve(nsel);
     uint64_t vu = 0;
     for (auto& sg : segs) for (size_t k = sg.b0; k <= sg.b1; k++) {
-        HostBlock hb = B[k]; hb.uoff = vu; vu += hb.isize;
+        HostBlock hb = L[k]; hb.uoff = vu; vu += hb.isize;
         h->vblocks.push_back(hb); h->seg_entry.push_back(k == sg.b0 ? (int32_t)sg.entry : -1); h->seg_limit.push_back(k == sg.b1 ? sg.limit : UINT32_MAX);
     }
     h->sparse_on = true;
@@ -499,11 +529,11 @@ __global__ void k_fill_u32(uint32_t* p, uint32_t v, uint64_t n) { uint64_t i = (
 // The pipeline: leaves the per-position counters of the whole shard in h->counts (RUN_FULL).
 int run_pipeline(bdepth* h, RunMode mode, RunOut* ro, Emitter* em = nullptr) {
     int rc = init_device(h); if (rc) return rc;
-    rc = prepare_shard(h); if (rc) return rc;
     auto t_host0 = std::chrono::steady_clock::now();
     bdepth_stats& st = h->st; uint32_t launches0 = 0;
     st = bdepth_stats{}; st.gpu_launches = launches0;
     const bool sparse = mode == RUN_FULL && plan_sparse(h);
+    if (!sparse) { rc = prepare_shard(h); if (rc) return rc; }      // the plain path needs the whole file's member table (a lazily opened handle frames it now)
     // -m pairs reads of one name wherever they sit in the shard.  A batch is scanned as a whole (no sub-batches), and every
     // batch after the first re-reads the end of the previous one as "ghost" records -- from the earliest record that can
     // still meet a mate (mates.cuh) -- so that a pair cut by a batch boundary is seen complete by the batch that closes it.
@@ -1002,9 +1032,12 @@ static int open_common(bdepth* h, bdepth_t** out) {
     *out = h; return 0;
 }
 
-int bdepth_open(const char* bam_path, int device, bdepth_t** out) {
+static int open_path(const char* bam_path, int device, bool lazy, bdepth_t** out);
+int bdepth_open(const char* bam_path, int device, bdepth_t** out) { return open_path(bam_path, device, false, out); }
+int bdepth_open_lazy(const char* bam_path, int device, bdepth_t** out) { return open_path(bam_path, device, true, out); }
+static int open_path(const char* bam_path, int device, bool lazy, bdepth_t** out) {
     if (!bam_path || !out) return fail(nullptr, BDEPTH_ERR_ARG, "null argument");
-    bdepth* h = new bdepth(); h->device = device;
+    bdepth* h = new bdepth(); h->device = device; h->lazy = lazy;
     h->fd = open(bam_path, O_RDONLY);
     if (h->fd < 0) { delete h; return fail(nullptr, BDEPTH_ERR_IO, "Cannot open file `%s' in mode `rb' (No such file or directory)", bam_path); }
     struct stat sb; if (fstat(h->fd, &sb) != 0 || sb.st_size == 0) { close(h->fd); delete h; return fail(nullptr, BDEPTH_ERR_IO, "cannot stat `%s' or file is empty", bam_path); }

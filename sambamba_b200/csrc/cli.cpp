@@ -265,7 +265,9 @@ int main(int argc, char** argv) {
     const std::string bam_path = a.v[1];
     if (c.mode == 2) { c.window_mode = true; }
 
-    int rc = bdepth_open(bam_path.c_str(), 0, &c.h);
+    // with -L only the header and the BGZF members inside the regions' BAI chunks are looked at (a run that turns out to
+    // need the whole file frames the rest itself)
+    int rc = has_bed ? bdepth_open_lazy(bam_path.c_str(), 0, &c.h) : bdepth_open(bam_path.c_str(), 0, &c.h);
     if (rc) return die(bdepth_last_error(nullptr));
     if (!bdepth_is_coordinate_sorted(c.h)) return die("All files must be coordinate-sorted");
     if (!bdepth_has_index(c.h)) return die("All files must be indexed");

@@ -29,11 +29,16 @@ static inline uint64_t h_rd64(const uint8_t* p) { return (uint64_t)h_rd32(p) | (
 
 // Walk the BGZF members of [file, file+len).  Stops at the first block with ISIZE == 0 (EOF
 // marker), as BgzfInputStream.fillNextBlock does (inputstream.d:393).  Returns "" or an error.
-static inline std::string index_bgzf(const uint8_t* file, size_t len, std::vector<HostBlock>& out, uint64_t* total_u) {
-    size_t off = 0; uint64_t uoff = 0;
+// frame_bgzf is the resumable form: it starts at *off_io / *uoff_io, appends at most max_blocks members that begin at or
+// before stop_coff, leaves the position after the last one in *off_io / *uoff_io and sets *eof when the file (or the EOF
+// marker) has been reached.  Region queries frame only the members inside their BAI chunks with it.
+static inline std::string frame_bgzf(const uint8_t* file, size_t len, size_t* off_io, uint64_t* uoff_io, size_t max_blocks, uint64_t stop_coff, std::vector<HostBlock>& out, bool* eof) {
+    size_t off = *off_io; uint64_t uoff = *uoff_io; size_t n_new = 0;
     char msg[256];
-    while (off < len) {
-        if (len - off < 4) break;
+    *eof = false;
+    while (true) {
+        if (off >= len || len - off < 4) { *eof = true; break; }
+        if (n_new >= max_blocks || (uint64_t)off > stop_coff) break;
         const uint8_t* p = file + off;
         if (!(p[0] == 0x1f && p[1] == 0x8b && p[2] == 0x08 && p[3] == 0x04)) { snprintf(msg, sizeof msg, "Error reading BGZF block starting from offset %zu: wrong BGZF magic", off); return msg; }
         if (len - off < 12) { snprintf(msg, sizeof msg, "Error reading BGZF block starting from offset %zu: stream error", off); return msg; }
@@ -56,13 +61,19 @@ static inline std::string index_bgzf(const uint8_t* file, size_t len, std::vecto
         size_t total = (size_t)bsize + 1;
         if (len - off < total) { snprintf(msg, sizeof msg, "Error reading BGZF block starting from offset %zu: stream error: not enough data in stream", off); return msg; }
         uint32_t isize = h_rd32(p + total - 4);
-        if (isize == 0) break;
+        if (isize == 0) { *eof = true; break; }
         if (isize > 65536) { snprintf(msg, sizeof msg, "Error reading BGZF block starting from offset %zu: input size is more than 65536", off); return msg; }
         out.push_back(HostBlock{(uint64_t)off, 12 + xlen, (uint32_t)cdata, isize, (uint32_t)total, uoff});
-        uoff += isize; off += total;
+        uoff += isize; off += total; n_new++;
     }
-    *total_u = uoff;
+    *off_io = off; *uoff_io = uoff;
     return "";
+}
+static inline std::string index_bgzf(const uint8_t* file, size_t len, std::vector<HostBlock>& out, uint64_t* total_u) {
+    size_t off = 0; uint64_t uoff = 0; bool eof = false;
+    std::string e = frame_bgzf(file, len, &off, &uoff, SIZE_MAX, UINT64_MAX, out, &eof);
+    *total_u = uoff;
+    return e;
 }
 
 struct BamHeader {

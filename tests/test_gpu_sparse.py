@@ -78,3 +78,38 @@ def test_foreign_index_falls_back_to_the_whole_file(big, tmp_path):
     with sb.BDepth(p) as b:
         got = b.run_base(window=(wa, wb))
     assert np.array_equal(got, want)
+
+
+def test_lazy_open_frames_only_what_a_region_query_needs(big, tmp_path):
+    """bdepth_open_lazy: a region query must not depend on BGZF members outside its BAI chunks.  A copy of the file whose
+    LAST data member is damaged cannot be opened eagerly, but answers a query on its first reference when opened lazily --
+    and reports the damage as soon as a run needs the whole file."""
+    import sambamba_b200 as sb
+    raw = bytearray(open(big, "rb").read())
+    # walk the members to the last data block and break its magic
+    off, last = 0, None
+    while off + 18 <= len(raw):
+        bsize = (raw[off + 16] | (raw[off + 17] << 8)) + 1
+        isize = int.from_bytes(raw[off + bsize - 4:off + bsize], "little")
+        if isize == 0:
+            break
+        last = off
+        off += bsize
+    raw[last] = 0x00
+    bad = str(tmp_path / "bad.bam")
+    open(bad, "wb").write(raw)
+    open(bad + ".bai", "wb").write(open(big + ".bai", "rb").read())
+    with pytest.raises(sb.BDepthError) as ei:
+        sb.BDepth(bad)
+    assert "wrong BGZF magic" in str(ei.value)
+    want, _ = helpers.oracle_counts(big, window=(1000, 40000))
+    with sb.BDepth(bad, lazy=True) as b:
+        assert np.array_equal(b.run_base(window=(1000, 40000)), want)
+        rows = b.run_regions([(0, 5000, 9000), (0, 200000, 201000)], [1, 10])
+        with pytest.raises(sb.BDepthError) as ei:
+            b.run_base(collect=False)              # the whole file: the rest is framed now
+        assert "wrong BGZF magic" in str(ei.value)
+    with sb.BDepth(big, lazy=True) as b, sb.BDepth(big) as e:
+        assert b.run_regions([(0, 5000, 9000), (0, 200000, 201000)], [1, 10]) == rows == e.run_regions([(0, 5000, 9000), (0, 200000, 201000)], [1, 10])
+        got = b.run_base(collect=False)            # lazily opened handles do whole-file runs too
+        assert b.stats()["n_blocks"] == e.stats()["n_blocks"] or e.run_base(collect=False) is None and b.stats()["n_blocks"] == e.stats()["n_blocks"]
