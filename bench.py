@@ -297,6 +297,25 @@ def main():
         if i >= n_w:
             e2e_t.append(dt)
     e2e_stats = h.stats()
+    # ---- rows of `depth base` formatted on the GPU ("text formatting timed as its own line"): the same pass,
+    # delivered as the text PerBasePrinter would print instead of counter planes (single GPU only; host wall clock)
+    text = None
+    if world == 1:
+        tt, tbytes = [], 0
+        for i in range(2):
+            box = {"n": 0}
+
+            def text_sink(_u, _p, n, box=box):
+                box["n"] += n
+                return 0
+            t0 = time.perf_counter()
+            h._ck(h.L.bdepth_run_base_text(h.h, C.byref(sb._lib.TextOpts(1.0, 1e50, 0)), sb._lib.TEXT_CB(text_sink), None))
+            dt = time.perf_counter() - t0
+            if i:
+                tt.append(dt)
+                tbytes = box["n"]
+        text = {"ms_per_step": 1e3 * sum(tt) / len(tt), "text_bytes": tbytes, "text_gb_per_s": tbytes / 1e9 / (sum(tt) / len(tt)), "bam_gb_per_s": file_bytes / 1e9 / (sum(tt) / len(tt)),
+                "path": "bdepth_run_base_text: H2D + kernels + k_text_len/scan/write + D2H of the row text (default `depth base`, min coverage 1)"}
     h.close()
     e2e_s = sum(e2e_t) / len(e2e_t)
     h2d_total = file_bytes
@@ -319,6 +338,7 @@ def main():
                 "device_ms": {k: e2e_stats[k] for k in ("ms_h2d", "ms_inflate", "ms_scan", "ms_coverage", "ms_d2h", "ms_span_device")},
                 "path": "bdepth_open_memory(pinned host BAM image) + bdepth_run_base -> 7 x u32 counters in pinned host memory", "host_input": host_kind, "chunk_blocks": chunk_blocks or "default (6656)",
                 "variants": {k: os.environ[k] for k in ("BDEPTH_K1_STREAM_WARPS", "BDEPTH_K3_PREFETCH") if k in os.environ}},
+        "text_rows": text,
         "gpu_launches": int(total_launches),
         "roofline": {"kernel": "k1_inflate (lane-per-BGZF-block DEFLATE)", "bound": "hbm", "achieved": k1_bytes / 1e9 / (k1_ms / 1e3), "peak": peak, "unit": "GB/s",
                      "frac": k1_bytes / 1e9 / (k1_ms / 1e3) / peak, "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH if (a.gpus == 1 and a.reads_per_unit == READS_PER_UNIT) else None,
