@@ -146,9 +146,10 @@ int bdepth_set_filter(bdepth_t* h, int mapq_gt, uint32_t flag_reject_mask);
 /* -F / --filter (depth.d:1121, createFilterFromQuery filtering.d:40-51): a query in sambamba's filter language
  * (queryparser.d), compiled to a small postfix program that the record scan evaluates per read.  "" keeps every
  * read.  Supported: flag conditions, integer fields incl. avg_base_quality, [XX] tags against integers, strings and
- * null, read_name / strand / sequence / cigar string comparisons, ref_name / mate_ref_name == / !=, and / or / not /
- * brackets.  BDEPTH_ERR_ARG (with the message) for syntax errors and for what is not supported: regular expressions
- * (=~), ordering comparisons of reference names. */
+ * null, read_name / strand / sequence / cigar string comparisons, ref_name / mate_ref_name == / !=, `=~ /regex/flags` on
+ * read_name, sequence, cigar and string tags (patterns without back-references / look-around, at most 64 NFA states), and /
+ * or / not / brackets.  BDEPTH_ERR_ARG (with the message) for syntax errors and for what is not supported: regular
+ * expressions outside that subset or on reference names, ordering comparisons of reference names. */
 int bdepth_set_filter_query(bdepth_t* h, const char* query);
 int bdepth_set_min_baseq(bdepth_t* h, uint32_t min_base_quality);
 /* -m / --fix-mate-overlaps (depth.d:1133; detectOverlappingMates :319-388, selectBetterMate :391-399, the -m branches

@@ -7,7 +7,7 @@
 // D binding that would replace this file is in sambamba_b200/d/bdepth.d and INTEGRATION.md.
 //
 // Not supported through the GPU path yet (rejected with a message, never silently wrong):
-//   -F with regular expressions ; several BAM files ; more than 64 samples without --combined.
+//   -F with back-references / look-around in regular expressions ; several BAM files ; more than 64 samples without --combined.
 #include <math.h>
 #include <stdint.h>
 #include <stdio.h>

@@ -11,6 +11,7 @@
 // __host__ __device__ and free of warp intrinsics: tests/emul/emul_filter.cpp runs the same code on the CPU.
 #pragma once
 #include <stdint.h>
+#include "regex.cuh"
 #ifndef BD_HD
 #if defined(__CUDACC__)
 #define BD_HD __host__ __device__ __forceinline__
@@ -37,13 +38,16 @@ enum FilterOpCode : uint8_t {
     FO_STRTAG,         // push string/char tag <cmp> pool[...]                    StringTagFilter
     FO_SEQ,            // push cmp(sequence, pool[...]) <cmp> 0                   StringFieldFilter("sequence")
     FO_CIGAR,          // push cigarString() <cmp> pool[...]                      StringFieldFilter("cigar")
+    FO_REGEX,          // push subject[a] contains a match of rx[s_off]          RegexpFieldFilter / RegexpTagFilter
     FO_AND, FO_OR, FO_NOT
 };
+enum FilterSubject : uint8_t { FS_NAME = 0, FS_TAG, FS_SEQ, FS_CIGAR };
+constexpr int FILTER_MAX_RX = 2;
 enum FilterCmp : uint8_t { FC_GT = 0, FC_LT, FC_GE, FC_LE, FC_EQ, FC_NE };
 enum FilterField : uint8_t { FF_REF_ID = 0, FF_POSITION, FF_MAPQ, FF_SEQ_LEN, FF_MATE_REF_ID, FF_MATE_POSITION, FF_TLEN };
 
 struct FilterOp { uint8_t op, cmp, a, pad; uint16_t tag; uint8_t s_off, s_len; int64_t imm; };      // 16 bytes
-struct FilterProg { uint32_t n; uint32_t pad; FilterOp ops[FILTER_MAX_OPS]; char pool[FILTER_POOL]; };
+struct FilterProg { uint32_t n; uint32_t n_rx; FilterOp ops[FILTER_MAX_OPS]; char pool[FILTER_POOL]; RegexProg rx[FILTER_MAX_RX]; };
 
 template <class T> BD_HD bool f_cmp(uint8_t c, T a, T b) {
     switch (c) { case FC_GT: return a > b; case FC_LT: return a < b; case FC_GE: return a >= b; case FC_LE: return a <= b; case FC_EQ: return a == b; default: return a != b; }
@@ -157,6 +161,16 @@ BD_HD bool filter_eval(const FilterProg& fp, const uint8_t* rec, uint32_t rec_si
             }
             if (!c && pos < o.s_len) c = -1;                                    // the CIGAR text is a proper prefix of the literal
             r = f_cmp<int>(o.cmp, c, 0); break; }
+        case FO_REGEX: {
+            const RegexProg& rx = fp.rx[o.s_off];
+            if (o.a == FS_NAME) { RxBytes g{rec + 32, l_name ? l_name - 1 : 0u, 0u}; r = rx_search(rx, g); }
+            else if (o.a == FS_SEQ) { RxSeq g{rec + 32 + l_name + 4u * n_cigar, lq, 0u}; r = rx_search(rx, g); }
+            else if (o.a == FS_CIGAR) { RxCigar g; g.cg = rec + 32 + l_name; g.n_ops = n_cigar; g.op_i = 0; g.nd = 0; g.started = false; r = rx_search(rx, g); }
+            else {      // a string tag (RegexpTagFilter: anything else is no match)
+                uint8_t ty = 0; const uint8_t* v = aux <= end ? f_find_tag(aux, end, o.tag, &ty) : nullptr;
+                if (v && (ty == 'Z' || ty == 'H')) { const uint8_t* q = v; while (q < end && *q) q++; RxBytes g{v, (uint32_t)(q - v), 0u}; r = rx_search(rx, g); } else r = false;
+            }
+            break; }
         case FO_AND: { bool b = (stack >> (sp - 1)) & 1, a = (stack >> (sp - 2)) & 1; sp -= 2; r = a && b; break; }
         case FO_OR: { bool b = (stack >> (sp - 1)) & 1, a = (stack >> (sp - 2)) & 1; sp -= 2; r = a || b; break; }
         case FO_NOT: { bool a = (stack >> (sp - 1)) & 1; sp -= 1; r = !a; break; }

@@ -5,15 +5,17 @@
 // the current position (no word boundaries: "notpaired" is `not` `paired`), binding powers: comparison 110,
 // `not` 100 (prefix), `and` 80, `or` 60, brackets.  Supported nodes: the 13 flag conditions, the integer fields
 // (incl. avg_base_quality), [XX] tags against integers / strings / null, read_name and strand against strings,
-// sequence and cigar against strings, ref_name / mate_ref_name == / != 'name' (folded into ref_id comparisons).
-// Refused with a message (never evaluated differently): regular expressions (=~), ordering comparisons of reference
-// names.  Unlike the reference, tokens left over after a complete expression are an error.
+// sequence and cigar against strings, ref_name / mate_ref_name == / != 'name' (folded into ref_id comparisons), and
+// `=~ /regex/` on read_name, sequence, cigar and string tags (host_regex.hpp: the subset listed in regex.cuh).
+// Refused with a message (never evaluated differently): regular expressions outside that subset or on reference names,
+// ordering comparisons of reference names.  Unlike the reference, tokens left over after a complete expression are an error.
 #pragma once
 #include <stdint.h>
 #include <string.h>
 #include <string>
 #include <vector>
 #include "filter.cuh"
+#include "host_regex.hpp"
 
 namespace bdk {
 
@@ -100,7 +102,7 @@ struct FilterCompiler {
         case K_TAG: return add(Node{K_TAG, t.text.substr(1, 2)});
         case K_INT: { Node n{K_INT, t.text}; n.v = strtoll(t.text.c_str(), nullptr, 10); return add(n); }
         case K_STR: { std::string s; for (size_t i = 1; i + 1 < t.text.size(); i++) { if (t.text[i] == '\\' && i + 2 < t.text.size() && t.text[i + 1] == '\'') { s += '\''; i++; } else s += t.text[i]; } return add(Node{K_STR, s}); }
-        case K_REGEX: err = "regular expressions in filters are not available in the GPU engine yet"; return -1;
+        case K_REGEX: return add(Node{K_REGEX, t.text});
         case K_NOT: { int a = parse(100); if (a < 0) return -1; if (!nodes[a].cond) { err = "`not` needs a condition, got '" + nodes[a].s + "'"; return -1; } Node n{K_NOT, "not"}; n.a = a; n.cond = true; return add(n); }
         case K_OPEN: { int a = parse(0); if (a < 0) return -1; if (tok.k != K_CLOSE) { err = "unexpected character at position " + std::to_string(tok.pos); return -1; } if (!next()) return -1; return a; }
         default: err = "parsing error: unexpected '" + (t.k == K_END ? std::string("end of filter") : t.text) + "'"; return -1;
@@ -112,7 +114,12 @@ struct FilterCompiler {
             if (!nodes[left].cond || !nodes[r].cond) { err = "`" + op.text + "` needs two conditions"; return -1; }
             Node n{op.k, op.text}; n.a = left; n.b = r; n.cond = true; return add(n);
         }
-        if (op.k == K_MATCH) { err = "regular expressions in filters are not available in the GPU engine yet"; return -1; }
+        if (op.k == K_MATCH) {
+            int r = parse(110); if (r < 0) return -1;
+            if (nodes[r].k != K_REGEX) { err = "expected regular expression, not '" + nodes[r].s + "'"; return -1; }
+            if (nodes[left].k != K_SFIELD && nodes[left].k != K_TAG) { err = "expected string field or tag name, not '" + nodes[left].s + "'"; return -1; }
+            Node n{K_MATCH, "=~"}; n.a = left; n.b = r; n.cond = true; return add(n);
+        }
         if (op.k == K_CMP) {
             int r = parse(110); if (r < 0) return -1;
             const Node& a = nodes[left]; const Node& b = nodes[r];
@@ -143,6 +150,19 @@ struct FilterCompiler {
             if (n.s == "chimeric") { o.op = FO_CHIMERIC; return push(p, o); }
             for (auto& f : F) if (n.s == f.nm) { o.op = FO_FLAG; o.imm = f.bit; return push(p, o); }
             err = "unknown flag '" + n.s + "'"; return false; }
+        case K_MATCH: {
+            const Node a = nodes[n.a], b = nodes[n.b];
+            size_t d = b.s.size() - 1; while (d > 0 && b.s[d] != '/') d--;
+            if (p.n_rx >= (uint32_t)FILTER_MAX_RX) { err = "more than two regular expressions in a filter are not available in the GPU engine"; return false; }
+            RegexCompiler rc; std::string e = rc.compile(b.s.substr(1, d - 1), b.s.substr(d + 1), p.rx[p.n_rx]);
+            if (!e.empty()) { err = e; return false; }
+            o.op = FO_REGEX; o.s_off = (uint8_t)p.n_rx++;
+            if (a.k == K_TAG) { o.a = FS_TAG; o.tag = (uint16_t)((uint8_t)a.s[0] | ((uint8_t)a.s[1] << 8)); }
+            else if (a.s == "read_name") o.a = FS_NAME;
+            else if (a.s == "sequence") o.a = FS_SEQ;
+            else if (a.s == "cigar") o.a = FS_CIGAR;
+            else { err = "regular expressions on `" + a.s + "` are not available in the GPU engine yet (compare ref_id instead)"; return false; }
+            return push(p, o); }
         case K_NOT: if (!emit(n.a, p, used)) return false; o.op = FO_NOT; return push(p, o);
         case K_AND: case K_OR: if (!emit(n.a, p, used) || !emit(n.b, p, used)) return false; o.op = n.k == K_AND ? FO_AND : FO_OR; return push(p, o);
         case K_CMP: {

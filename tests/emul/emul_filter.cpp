@@ -20,3 +20,10 @@ extern "C" size_t emul_filter_prog_size() { return sizeof(FilterProg); }
 extern "C" void emul_filter_eval(const FilterProg* p, const uint8_t* u, const uint64_t* offs, const uint32_t* sizes, uint64_t n, uint8_t* out) {
     for (uint64_t i = 0; i < n; i++) out[i] = filter_eval(*p, u + offs[i], sizes[i]) ? 1 : 0;
 }
+// one regular expression against one subject: 1 / 0, or -1 when the pattern is outside the supported subset
+extern "C" int emul_regex_search(const char* pattern, const char* options, const uint8_t* subject, uint32_t n) {
+    RegexProg p; RegexCompiler rc;
+    if (!rc.compile(pattern, options, p).empty()) return -1;
+    RxBytes g{subject, n, 0u};
+    return rx_search(p, g) ? 1 : 0;
+}

@@ -5,7 +5,9 @@ stating what each query means.  No GPU needed."""
 import ctypes as C
 import os
 import random
+import re
 import struct
+import warnings
 
 import numpy as np
 import pytest
@@ -162,13 +164,25 @@ QUERIES = [
     ("cigar != '10M' and cigar < '3'", lambda r: r.cigar != b"10M" and r.cigar < b"3"),
     ("sequence >= 'G'", lambda r: r.seq >= b"G"),
     ("sequence < 'ACGT' or sequence == ''", lambda r: r.seq < b"ACGT" or r.seq == b""),
+    ("read_name =~ /^read/", lambda r: re.search(rb"^read", r.name) is not None),
+    ("read_name =~ /^(read|zz)[0-3]?[05]$/", lambda r: re.search(rb"^(read|zz)[0-3]?[05]$", r.name) is not None),
+    ("read_name =~ /a.?\\d{2}/ and not read_name =~ /9$/", lambda r: re.search(rb"a.?\d{2}", r.name) is not None and re.search(rb"9$", r.name) is None),
+    ("read_name =~ /FRAG|^R\\d+$/i", lambda r: re.search(rb"FRAG|^R\d+$", r.name, re.I) is not None),
+    ("[RG] =~ /^g(rp)?\\d*$/", lambda r: stag(r, "RG") is not None and re.search(rb"^g(rp)?\d*$", stag(r, "RG")) is not None),
+    ("[NM] =~ /x/", lambda r: stag(r, "NM") is not None and b"x" in stag(r, "NM")),
+    ("cigar =~ /^(20|35)M$/", lambda r: re.search(rb"^(20|35)M$", r.cigar) is not None),
+    ("cigar =~ /\\b\\d0M/ or cigar =~ /^$/", lambda r: re.search(rb"\b\d0M", r.cigar) is not None or r.cigar == b""),
+    ("sequence =~ /^[ACGT]{20,35}$/", lambda r: re.search(rb"^[ACGT]{20,35}$", r.seq) is not None),
+    ("sequence =~ /(ACG){2,}|T{5}|^$/", lambda r: re.search(rb"(ACG){2,}|T{5}|^$", r.seq) is not None),
+    ("sequence =~ /G[^G]+?GG\\w*C$/", lambda r: re.search(rb"G[^G]+?GG\w*C$", r.seq) is not None),
     ("notpaired", lambda r: not r.flag & 1),
     ("duplicate  and\tnot\nfailed_quality_control", lambda r: bool(r.flag & 0x400) and not r.flag & 0x200),
     ("((mapping_quality > 10))", lambda r: r.mapq > 10),
     ("mapping_quality > -1 and position > +5", lambda r: r.pos > 5),
 ]
 
-BAD = ["", "mapping_quality", "mapping_quality >", "paired and", "(paired", "paired)", "paired unmapped", "read_name =~ /^r/", "[RG] =~ /x/", "sequence =~ /ACGT/",
+BAD = ["", "mapping_quality", "mapping_quality >", "paired and", "(paired", "paired)", "paired unmapped", "read_name =~ /(a)\\1/", "[RG] =~ /(?=x)/", "sequence =~ /\\p{L}/", "ref_name =~ /^c/", "read_name =~ /a/x", "read_name =~ /[a-z&&[^b]]/", "read_name =~ 'x'", "read_name =~ /(a/",
+       "read_name =~ /a{3,2}/", "read_name =~ /*a/", "read_name =~ /(a|b|c|d|e|f|g|h|i|j|k|l|m|n|o|p|q|r|s|t|u|v|w|x){3}/",
        "cigar == 50", "ref_name > 'c1'", "mapping_quality == 'x'", "read_name == 5", "position == null", "5 > 3", "not 5", "paired and 5", "frobnicate", "[NMX] == 1",
        "mapping_quality > 5 > 3"]
 
@@ -217,3 +231,62 @@ def test_prefiltered_input_method(tmp_path):
         rc1, out1, _ = helpers.oracle_cli(mode + [p])
         rc2, out2, _ = helpers.oracle_cli(mode + ["-F", "", sub])
         assert rc1 == 0 and rc2 == 0 and out1 == out2 and len(out1) > 60, mode
+
+
+def test_regex_engine_against_python_re(em):
+    """Random patterns over a small alphabet (literals, classes, escapes, groups, alternation, all quantifier forms, anchors,
+    word boundaries) on random subjects: the NFA simulation of regex.cuh must agree with Python's `re.search`."""
+    rnd = random.Random(7)
+
+    def atom(d):
+        k = rnd.random()
+        if k < 0.35:
+            return rnd.choice("abcAB01_-")
+        if k < 0.45:
+            return "."
+        if k < 0.6:
+            return rnd.choice([r"\d", r"\w", r"\s", r"\D", r"\W", r"\-", r"\.", r"\x41"])
+        if k < 0.75:
+            body = "".join(rnd.choice(["a", "b", "c", "0-1", "a-c", "A-B", r"\d", "_", "-"]) for _ in range(rnd.randint(1, 3)))
+            return "[" + ("^" if rnd.random() < 0.3 else "") + body.lstrip("-") + "x]"
+        if k < 0.85 and d < 2:
+            return "(" + ("?:" if rnd.random() < 0.4 else "") + alt(d + 1) + ")"
+        return rnd.choice(["^", "$", r"\b", r"\B"]) if rnd.random() < 0.5 else rnd.choice("abc")
+
+    def rep(d):
+        a = atom(d)
+        if a in ("^", "$", r"\b", r"\B"):
+            return a
+        k = rnd.random()
+        q = "" if k < 0.55 else rnd.choice(["*", "+", "?", "{2}", "{1,2}", "{0,1}", "{2,}", "*?", "+?"])
+        return a + q
+
+    def cat(d):
+        return "".join(rep(d) for _ in range(rnd.randint(1, 3)))
+
+    def alt(d):
+        return "|".join(cat(d) for _ in range(rnd.choice([1, 1, 1, 2, 3])))
+
+    n_checked = n_refused = n_true = 0
+    for _ in range(3000):
+        pat = alt(0)
+        flags = "i" if rnd.random() < 0.2 else ""
+        try:
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                want_re = re.compile(pat.encode(), re.I if flags else 0)
+        except re.error:
+            continue
+        for _ in range(4):
+            subj = "".join(rnd.choice("abcAB01_- x") for _ in range(rnd.randint(0, 9))).encode()
+            if not subj and "\\B" in pat:
+                continue                  # Python (before 3.14) never matches \B on an empty subject; ECMAScript-style engines, D's included, do
+            got = em.emul_regex_search(pat.encode(), flags.encode(), subj, len(subj))
+            if got < 0:
+                n_refused += 1
+                break
+            want = 1 if want_re.search(subj) else 0
+            assert got == want, (pat, flags, subj, got, want)
+            n_checked += 1
+            n_true += want
+    assert n_checked > 6000 and n_refused < 0.2 * 3000 and 0.15 < n_true / n_checked < 0.9, (n_checked, n_refused, n_true)
