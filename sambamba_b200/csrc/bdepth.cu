@@ -77,6 +77,7 @@ constexpr unsigned COUNT_GRID = 2048;
 constexpr size_t CARRY_MAX = 64ull << 20;
 constexpr size_t EMIT_CHUNK = 4ull << 20;     // positions per D2H chunk
 constexpr uint32_t SHARD_EXTRA_BLOCKS = 8;
+constexpr uint32_t MATE_ZONE_BLOCKS = 64;       // -m on several ranks: blocks read behind the shard so that pairs cut by the boundary are seen whole
 
 enum RunMode { RUN_FULL = 0, RUN_INFLATE_ONLY = 1, RUN_SCAN_ONLY = 2 };
 
@@ -160,6 +161,7 @@ struct bdepth {
     // ---- shard (resolved lazily)
     bool shard_ready = false;
     size_t blk_lo = 0, blk_hi = 0; int64_t entry0 = 0; uint64_t limit_abs_u = 0;
+    uint64_t own_lo_abs_u = 0;            // -m on several ranks: the stream begins before the shard does (zone of the previous rank); own records start here
     // Sparse staging for region queries: only the BGZF blocks inside the BAI chunk list of the
     // regions are copied, inflated and scanned.  vblocks = those blocks with uoff re-based to a compact stream;
     // a segment is one merged chunk: it starts at a record (seg_entry = offset inside its first block) and ends at
@@ -316,9 +318,30 @@ int prepare_shard(bdepth* h) {
     }
     if (start_u >= h->total_u) { h->blk_lo = h->blk_hi = B.size(); h->entry0 = 0; h->limit_abs_u = h->total_u; h->shard_ready = true; return 0; }
     h->blk_lo = block_of_u(start_u); h->entry0 = (int64_t)(start_u - B[h->blk_lo].uoff);
-    h->limit_abs_u = end_u;
+    h->limit_abs_u = end_u; h->own_lo_abs_u = start_u;
     if (end_u >= h->total_u) h->blk_hi = B.size();
-    else h->blk_hi = std::min(B.size(), block_of_u(end_u) + 1 + SHARD_EXTRA_BLOCKS);
+    else h->blk_hi = std::min(B.size(), block_of_u(end_u) + 1 + (h->fix_mates ? MATE_ZONE_BLOCKS : SHARD_EXTRA_BLOCKS));
+    if (h->fix_mates && h->world > 1 && h->rank > 0) {
+        // The zone before the shard.  The BAI linear index holds, per 16 kbp window, the first record that overlaps the window:
+        // starting at the entry of the window of the shard's first read includes every read that overlaps any column at or
+        // after that window's start, i.e. every read the rank's own components and their columns can involve.
+        std::vector<uint8_t> u; int rc = inflate_blocks_to_host(h, h->blk_lo, std::min(B.size(), h->blk_lo + 2), u); if (rc) return rc;
+        const uint64_t o = (uint64_t)h->entry0;
+        if (o + 12 <= u.size()) {
+            int32_t ref = (int32_t)h_rd32(u.data() + o + 4), pos = (int32_t)h_rd32(u.data() + o + 8);
+            if (ref >= 0 && (size_t)ref < h->bai.ioffsets.size() && pos >= 0) {
+                const auto& lin = h->bai.ioffsets[ref]; size_t w = (size_t)pos >> 14;
+                uint64_t vo = w < lin.size() ? lin[w] : 0;
+                if (vo) {
+                    size_t b = block_of_c(vo >> 16);
+                    if (B[b].coff != (vo >> 16)) return fail(h, BDEPTH_ERR_FORMAT, "fix-mate-overlaps on several ranks: the linear index does not match the file");
+                    uint64_t zu = B[b].uoff + (vo & 0xFFFF);
+                    if (zu < h->hdr.first_rec_off) zu = h->hdr.first_rec_off;
+                    if (zu < start_u) { h->blk_lo = block_of_u(zu); h->entry0 = (int64_t)(zu - B[h->blk_lo].uoff); }
+                }
+            }
+        }
+    }
     h->shard_ready = true;
     return 0;
 }
@@ -538,7 +561,7 @@ int run_pipeline(bdepth* h, RunMode mode, RunOut* ro, Emitter* em = nullptr) {
     // batch after the first re-reads the end of the previous one as "ghost" records -- from the earliest record that can
     // still meet a mate (mates.cuh) -- so that a pair cut by a batch boundary is seen complete by the batch that closes it.
     const bool fix = mode == RUN_FULL && h->fix_mates;
-    if (fix && h->world > 1) return fail(h, BDEPTH_ERR_ARG, "fix-mate-overlaps is not available with several ranks yet");
+    if (fix && h->world > 1 && !h->comm) return fail(h, BDEPTH_ERR_ARG, "fix-mate-overlaps on several ranks needs the boundary exchange (bdepth_set_shard with a NCCL id)");
     const uint64_t eff_batch_u = h->batch_u;
     size_t ghost_b = 0; int64_t ghost_entry = 0; uint64_t ghost_below_abs = 0, prev_s_last = 0, covered_from = 0;      // -m: where the next batch's stream begins
     const std::vector<HostBlock>& B = sparse ? h->vblocks : h->blocks;
@@ -828,7 +851,7 @@ int run_pipeline(bdepth* h, RunMode mode, RunOut* ro, Emitter* em = nullptr) {
         tail = cur < (int64_t)ub ? cur : (int64_t)ub;     // first byte not consumed by a complete record
         // ---- shard limit: drop records starting at/after u_limit (host trims counts; offsets are sorted)
         std::vector<uint32_t> rbase(nb + 1); uint64_t R = 0;
-        bool limited = u_limit < (int64_t)ub;
+        bool limited = u_limit < (int64_t)ub && !fix;        // (-m keeps the records behind the limit: they are marked as the next rank's by k2_decode)
         std::vector<uint16_t> tmp_slots;
         for (size_t i = 0; i < nb; i++) {
             if (limited && cnt[i]) {
@@ -852,11 +875,13 @@ int run_pipeline(bdepth* h, RunMode mode, RunOut* ro, Emitter* em = nullptr) {
         size_t Rc = R ? R : 1;
         CK(h->soa_start.ensure(Rc * 8)); CK(h->soa_span.ensure(Rc * 4)); CK(h->soa_meta.ensure(Rc * 4)); CK(h->soa_off.ensure(Rc * 8)); CK(h->soa_ncl.ensure(Rc * 4)); CK(h->soa_lseq.ensure(Rc * 4)); CK(h->long_list.ensure(Rc * 4));
         RecordSoA soa{h->soa_start.as<uint64_t>(), h->soa_span.as<uint32_t>(), h->soa_meta.as<uint32_t>(), h->soa_off.as<int64_t>(), h->soa_ncl.as<uint32_t>(), h->soa_lseq.as<int32_t>()};
-        ScanStats zs{0, 0, 0, 0, ~0ull, 0, 0, ~0ull, 0};
+        ScanStats zs{0, 0, 0, 0, ~0ull, 0, 0, ~0ull, 0, 0};
         const int64_t ghost_below = (fix && batch_no > 0) ? (int64_t)ghost_below_abs - (int64_t)batch_u0 : INT64_MIN;
+        const int64_t own_lo = (fix && h->world > 1) ? (int64_t)h->own_lo_abs_u - (int64_t)batch_u0 : INT64_MIN;           // -m on several ranks: records outside belong to the neighbours
+        const int64_t own_hi = (fix && h->world > 1 && h->limit_abs_u < h->total_u) ? (int64_t)h->limit_abs_u - (int64_t)batch_u0 : INT64_MAX;
         UP(h->scan_stats.p, &zs, sizeof zs);
         if (mode == RUN_SCAN_ONLY && !h->ref_has.p) { CK(h->ref_has.ensure((nref / 32 + 2) * 4)); CK(cudaMemsetAsync(h->ref_has.p, 0, (nref / 32 + 2) * 4, sm)); }
-#define K2_DECODE(F, G) BD_LAUNCH((unsigned)((nb * 32 + 255) / 256), 256, 0, sm, k2_decode<F, G>)(sp, h->chunk_start.as<int64_t>(), (uint32_t)nb, h->slot_base.as<uint32_t>(), h->slots.as<uint16_t>(), h->count.as<uint32_t>(), h->rec_base.as<uint32_t>(), soa, h->mapq_gt, h->flag_reject, h->scan_stats.as<ScanStats>(), h->long_list.as<uint32_t>(), h->ref_has.as<uint32_t>(), rgt, d_fprog, ghost_below)
+#define K2_DECODE(F, G) BD_LAUNCH((unsigned)((nb * 32 + 255) / 256), 256, 0, sm, k2_decode<F, G>)(sp, h->chunk_start.as<int64_t>(), (uint32_t)nb, h->slot_base.as<uint32_t>(), h->slots.as<uint16_t>(), h->count.as<uint32_t>(), h->rec_base.as<uint32_t>(), soa, h->mapq_gt, h->flag_reject, h->scan_stats.as<ScanStats>(), h->long_list.as<uint32_t>(), h->ref_has.as<uint32_t>(), rgt, d_fprog, ghost_below, own_lo, own_hi)
         if (fix) { if (d_fprog) K2_DECODE(true, true); else K2_DECODE(false, true); }
         else if (d_fprog) K2_DECODE(true, false);
         else K2_DECODE(false, false);
@@ -866,7 +891,7 @@ int run_pipeline(bdepth* h, RunMode mode, RunOut* ro, Emitter* em = nullptr) {
         CK(cudaEventRecord(e3, sm));
         CK(cudaStreamSynchronize(sm));
         const ScanStats ss = *ssp;
-        st.n_records -= ss.n_ghost;          // re-read records of the previous batch were counted there
+        st.n_records -= ss.n_ghost + ss.n_ghost_right;          // re-read records of the previous batch / of the neighbours' zones are counted there
         if (ss.rg_err != ~0ull) return fail(h, BDEPTH_ERR_FORMAT, "error in read #%llu of the batch: its read group is not present in the header", ss.rg_err);
         st.n_records_pass += ss.n_pass; st.n_cigar_ops += ss.n_cigar; st.seq_bytes += ss.seq_bytes; st.long_reads += ss.n_long;
         if (ss.n_pass) { shard_min = std::min<uint64_t>(shard_min, ss.min_start); shard_max = std::max<uint64_t>(shard_max, ss.max_end); }
@@ -932,7 +957,7 @@ int run_pipeline(bdepth* h, RunMode mode, RunOut* ro, Emitter* em = nullptr) {
             const uint64_t tail_abs = batch_u0 + (uint64_t)tail; size_t lo = 0, hi = B.size(); while (lo + 1 < hi) { size_t m2 = (lo + hi) / 2; if (B[m2].uoff <= tail_abs) lo = m2; else hi = m2; }
             ghost_b = lo; ghost_entry = (int64_t)(tail_abs - B[lo].uoff); ghost_below_abs = tail_abs;
         }
-        if (fix && R && (ss.n_pass || ss.n_ghost)) {
+        if (fix && R && (ss.n_pass || ss.n_ghost || ss.n_ghost_right)) {
             if (subs.size() != 1) return fail(h, BDEPTH_ERR_ARG, "internal: fix-mate-overlaps scans a batch as a whole");
             uint64_t s_last = 0;       // start of the batch's last record: nothing that follows starts before it
             CK(cudaMemcpyAsync(&s_last, soa.start + (R - 1), 8, cudaMemcpyDeviceToHost, sm)); CK(cudaStreamSynchronize(sm));
@@ -953,14 +978,15 @@ int run_pipeline(bdepth* h, RunMode mode, RunOut* ro, Emitter* em = nullptr) {
                           segm ? h->seg.n : 0u, segm ? h->seg.reads.as<uint32_t>() : nullptr, segm ? h->seg.mbases.as<uint32_t>() : nullptr, h->S,
                           segm && h->seg.has_u ? h->seg.ustart.as<uint64_t>() : nullptr, segm && h->seg.has_u && h->seg.has_min ? h->seg.minstart.as<uint64_t>() : nullptr, segm && h->seg.has_u ? h->seg.ext_max : 0ull,
                           h->tile_lo.as<uint32_t>(), idx_tiles_base, idx_n_tiles, h->long_list.as<uint32_t>(), (uint32_t)ss.n_long,
-                          (uint32_t)ss.n_ghost, s_last, prev_s_last, covered_from, last_batch ? 1 : 0, (unsigned long long*)((uint8_t*)h->m_ctl.p + 48), (unsigned long long*)((uint8_t*)h->m_ctl.p + 56), 0,
+                          (uint32_t)ss.n_ghost, s_last, prev_s_last, covered_from, last_batch ? 1 : 0, (unsigned long long*)((uint8_t*)h->m_ctl.p + 48), (unsigned long long*)((uint8_t*)h->m_ctl.p + 56),
+                          (last_batch && blk_hi < B.size()) ? 1 : 0, (unsigned long long*)((uint8_t*)h->m_ctl.p + 40), (uint32_t)ss.n_ghost_right, ghost_below == INT64_MIN ? INT64_MIN : ghost_below + 4, 0,
                           (int*)h->m_ctl.p, (unsigned long long*)((uint8_t*)h->m_ctl.p + 16)};
             const unsigned mg = (unsigned)((R + 127) / 128);
             BD_LAUNCH(mg, 128, 0, sm, km_hash)(mp); BD_LAUNCH(mg, 128, 0, sm, km_link)(mp); BD_LAUNCH(mg, 128, 0, sm, km_fix)(mp);
             if (!last_batch) { BD_LAUNCH(mg, 128, 0, sm, km_cover)(mp); st.gpu_launches++; }
             CK(cudaGetLastError()); st.gpu_launches += 3;
             CK(cudaEventRecord(em1, sm));
-            struct { int err[4]; unsigned long long stat[3]; unsigned long long pad; unsigned long long open_off, open_start; } ctl;
+            struct { int err[4]; unsigned long long stat[3]; unsigned long long fix_max_end; unsigned long long open_off, open_start; } ctl;
             CK(cudaMemcpyAsync(&ctl, h->m_ctl.p, sizeof ctl, cudaMemcpyDeviceToHost, sm));
             CK(cudaStreamSynchronize(sm));
             if (ctl.err[0] == MATE_ERR_TOO_MANY) return fail(h, BDEPTH_ERR_ARG, "fix-mate-overlaps: more than %d overlapping reads share one name (record #%d of the batch)", MATE_MAX_MEMBERS, ctl.err[1]);
@@ -970,6 +996,8 @@ int run_pipeline(bdepth* h, RunMode mode, RunOut* ro, Emitter* em = nullptr) {
                 const uint64_t g_abs = batch_u0 + (ctl.open_off - 4); size_t lo = 0, hi = B.size(); while (lo + 1 < hi) { size_t m2 = (lo + hi) / 2; if (B[m2].uoff <= g_abs) lo = m2; else hi = m2; }
                 ghost_b = lo; ghost_entry = (int64_t)(g_abs - B[lo].uoff);
             }
+            if (ctl.err[0] == MATE_ERR_ZONE) return fail(h, BDEPTH_ERR_ARG, "fix-mate-overlaps on several ranks: overlapping reads of one name reach more than %u BGZF blocks past a shard boundary (record #%d of the batch)", MATE_ZONE_BLOCKS, ctl.err[1]);
+            if (ctl.fix_max_end > shard_max && shard_min != UINT64_MAX) shard_max = ctl.fix_max_end;      // the halo exchange carries the corrections to their owners
             prev_s_last = s_last; covered_from = ctl.open_start;
             { float t = 0; CK(cudaEventElapsedTime(&t, em0, em1)); st.ms_mates += t; }
         }
@@ -1108,7 +1136,7 @@ int bdepth_set_filter_query(bdepth_t* h, const char* query) {
     return 0;
 }
 int bdepth_set_combined(bdepth_t* h, int combined) { h->combined = combined != 0; return 0; }
-int bdepth_set_fix_mates(bdepth_t* h, int on) { h->fix_mates = on != 0; return 0; }
+int bdepth_set_fix_mates(bdepth_t* h, int on) { if (h->fix_mates != (on != 0)) h->shard_ready = false; h->fix_mates = on != 0; return 0; }      // (with -m a shard is read with zones around it)
 int bdepth_set_min_baseq(bdepth_t* h, uint32_t q) { h->minq = q > 255 ? 255 : q; return 0; }
 int bdepth_set_regions(bdepth_t* h, const bdepth_region* r, size_t n) { normalize_regions(h, r, n, h->regions); return 0; }
 int bdepth_set_shard(bdepth_t* h, int rank, int world, const void* nccl_unique_id) {
@@ -1389,6 +1417,7 @@ static int run_segments(bdepth* h, const std::vector<SegDef>& segs, const uint32
             if (n_thr) N.AllReduce(dcov.p, dcov.p, NS * n * n_thr, NCCL_UINT32, NCCL_SUM, h->comm, sm);
             N.AllReduce(S.reads.p, S.reads.p, NS * n, NCCL_UINT32, NCCL_SUM, h->comm, sm);
             if (has_min) N.AllReduce(S.bases_reads.p, S.bases_reads.p, NS * n, NCCL_UINT32, NCCL_SUM, h->comm, sm);
+            if (h->fix_mates) N.AllReduce(S.mbases.p, S.mbases.p, NS * n, NCCL_UINT32, NCCL_SUM, h->comm, sm);
         }
         cudaMemcpyAsync(bases.data(), dbases.p, NS * n * 4, cudaMemcpyDeviceToHost, sm);
         if (n_thr) cudaMemcpyAsync(cov.data(), dcov.p, NS * n * n_thr * 4, cudaMemcpyDeviceToHost, sm);

@@ -194,9 +194,11 @@ struct RecordSoA {
 };
 struct ScanStats {      // device-side accumulators
     unsigned long long n_pass, n_cigar, seq_bytes, max_end, min_start, n_long, max_start, rg_err;   // rg_err: 1 + index of the first read with an unknown RG
-    unsigned long long n_ghost;     // -m across batches: records re-read from the previous batch (k2_decode<.., true>)
+    unsigned long long n_ghost;     // -m: records before the batch's own ones (re-read from the previous batch / the previous rank's zone), k2_decode<.., true>
+    unsigned long long n_ghost_right;   // -m on several ranks: records at or after the shard limit (the next rank's zone)
 };
-constexpr uint32_t NCL_GHOST = 1u << 31;      // RecordSoA.ncl: a re-read record of the previous batch that passes the filter (its pass bit is clear)
+constexpr uint32_t NCL_GHOST = 1u << 31;      // RecordSoA.ncl: a record that is only re-read for the mate kernels and passes the filter (its pass bit is clear)
+constexpr uint32_t NCL_FOREIGN = 1u << 30;    // ... and belongs to another rank's shard (-m on several ranks: the zones left and right of the shard)
 // @RG ID -> sample table (depth.d:1170-1181); ids are NUL-terminated, concatenated.  n_rg == 0 disables the scan.
 struct RgTable { const uint8_t* ids; const uint32_t* offs; const uint8_t* sample_of; uint32_t n_rg; };
 
@@ -236,15 +238,16 @@ __device__ __forceinline__ bool cig_match(uint32_t op) { return op == 0 || op ==
 __device__ BD_NOINLINE bool filter_eval_cold(const FilterProg* fp, const uint8_t* rec, uint32_t rec_size) { return filter_eval(*fp, rec, rec_size); }
 
 // FILTER: a compiled -F query decides (its own instantiation, so that the default predicate's kernel keeps its register count).
-// GHOST (-m across batches, mates.cuh): records that start below ghost_below were counted by the previous batch and are
-// re-read only so that the mate kernels see them: their pass bit stays clear (K3, the per-read reducers and the
-// statistics ignore them), NCL_GHOST marks the ones that pass the filter.
+// GHOST (-m across batches and ranks, mates.cuh): records that start below ghost_below were counted by the previous batch,
+// records outside [own_lo, own_hi) belong to a neighbouring rank's shard; both are read only so that the mate kernels see
+// them: their pass bit stays clear (K3, the per-read reducers and the statistics ignore them), NCL_GHOST marks the ones
+// that pass the filter, NCL_FOREIGN the ones of another rank.
 template <bool FILTER, bool GHOST>
 __global__ void k2_decode(ScanParams sp, const int64_t* __restrict__ chunk_start, uint32_t n_chunks, const uint32_t* __restrict__ slot_base,
                           const uint16_t* __restrict__ slots, const uint32_t* __restrict__ count, const uint32_t* __restrict__ rec_base,
                           RecordSoA soa, int mapq_gt, uint32_t flag_reject, ScanStats* __restrict__ st, uint32_t* __restrict__ long_list,
                           uint32_t* __restrict__ ref_has_reads, RgTable rg, const FilterProg* __restrict__ fprog /* compiled -F query, or nullptr: mapq_gt / flag_reject */,
-                          int64_t ghost_below) {
+                          int64_t ghost_below, int64_t own_lo, int64_t own_hi) {
     uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= n_chunks) return;
     uint32_t n = count[warp];
@@ -253,7 +256,7 @@ __global__ void k2_decode(ScanParams sp, const int64_t* __restrict__ chunk_start
     uint32_t rb = rec_base[warp];
     unsigned long long loc_pass = 0, loc_cig = 0, loc_seq = 0, loc_maxend = 0, loc_minstart = ~0ull, loc_maxstart = 0;
     uint32_t has_word = 0xFFFFFFFFu, has_bits = 0;      // per-lane pending "reference has reads" bits (one atomic per warp, not per read)
-    unsigned long long loc_ghost = 0;
+    unsigned long long loc_ghost = 0, loc_ghost_r = 0;
     for (uint32_t k = lane; k < n; k += 32) {
         int64_t o = ((k == 0 || c0 > 0) ? c0 : 0) + sl[k];
         const uint8_t* p = sp.u + o + 4;
@@ -288,7 +291,10 @@ __global__ void k2_decode(ScanParams sp, const int64_t* __restrict__ chunk_start
             sample = (uint32_t)sid & 63u;
         }
         uint32_t ghost_bit = 0;
-        if (GHOST && o < ghost_below) { loc_ghost++; if (pass) ghost_bit = NCL_GHOST; pass = false; is_long = false; }
+        if (GHOST) {
+            const bool foreign = o < own_lo || o >= own_hi;
+            if (foreign || o < ghost_below) { if (o >= own_hi) loc_ghost_r++; else loc_ghost++; if (pass) ghost_bit = NCL_GHOST | (foreign ? NCL_FOREIGN : 0u); pass = false; is_long = false; }
+        }
         soa.start[r] = start; soa.span[r] = span_eff;
         soa.meta[r] = (flag << 16) | (mapq << 8) | (sample << 2) | (pass ? 1u : 0u) | (is_long ? 2u : 0u);
         soa.off[r] = o + 4; soa.ncl[r] = (n_cigar << 8) | l_name | ghost_bit; soa.lseq[r] = l_seq;
@@ -304,6 +310,7 @@ __global__ void k2_decode(ScanParams sp, const int64_t* __restrict__ chunk_start
         }
     }
     if (GHOST && loc_ghost) atomicAdd(&st->n_ghost, loc_ghost);       // per lane: only a batch's first blocks hold ghosts
+    if (GHOST && loc_ghost_r) atomicAdd(&st->n_ghost_right, loc_ghost_r);
     {   // flush the has-reads bits: in the common case the whole warp saw one bitmap word -> one atomic
         uint32_t w0 = __shfl_sync(0xFFFFFFFFu, has_word, 0);
         bool same = __all_sync(0xFFFFFFFFu, has_word == w0 || has_bits == 0);

@@ -36,7 +36,8 @@
 namespace bdk {
 
 constexpr int MATE_MAX_MEMBERS = 8;
-enum MateErr : int { MATE_OK = 0, MATE_ERR_TOO_MANY = 1, MATE_ERR_CROSS = 2 };
+enum MateErr : int { MATE_OK = 0, MATE_ERR_TOO_MANY = 1, MATE_ERR_CROSS = 2, MATE_ERR_ZONE = 3 };
+constexpr uint32_t MATE_NCL_FOREIGN = 1u << 30;    // ... of another rank's shard (kernels.cuh NCL_FOREIGN): seen, never the leader of a component this rank fixes
 constexpr uint32_t MATE_NCL_GHOST = 1u << 31;      // RecordSoA.ncl bit of a re-read record of the previous batch (kernels.cuh NCL_GHOST)
 enum MateFlag : uint32_t { MF_INSTREAM = 1u, MF_HAS_PRED = 2u, MF_HAS_SUCC = 4u };
 
@@ -71,6 +72,12 @@ struct MateParams {
     // km_cover then adds every read that reaches into the columns of something open, so that the next batch knows all
     // reads of those columns (covered_from = the previous batch's *open_start; mate_follows needs them).
     uint32_t n_ghost; uint64_t s_last, prev_s_last, covered_from; int last_batch; unsigned long long* open_off; unsigned long long* open_start;
+    // Several ranks: a rank's stream is [zone of the previous shard | its shard | zone of the next shard]; a component is
+    // fixed by the rank that owns its leader.  stream_cut: the stream ends before the file does (a component of an own
+    // leader that is still open there is refused); *fix_max_end collects how far the fixed components reach (the halo
+    // exchange must carry the counters up to there).
+    int stream_cut; unsigned long long* fix_max_end; uint32_t n_right;      // n_right: the last rows are the next rank's zone
+    int64_t old_below;           // records whose off lies below were part of the previous batch too (INT64_MIN in the first batch)
     int force_general;           // tests: send pairs through the state-machine path as well
     int* err;                    // err[0] = MateErr, err[1] = record index
     unsigned long long* stat;    // [0] pairs, [1] (pair, column) fixes, [2] components with more than two members
@@ -82,12 +89,14 @@ BD_HD void m_or(uint32_t* p, uint32_t v) { atomicOr(p, v); }
 BD_HD void m_stat(unsigned long long* p, unsigned long long v) { atomicAdd(p, v); }
 BD_HD void m_err(const MateParams& p, int code, uint32_t r) { if (atomicMax(p.err, code) < code) p.err[1] = (int)r; }
 BD_HD void m_min(unsigned long long* p, unsigned long long v) { atomicMin(p, v); }
+BD_HD void m_max(unsigned long long* p, unsigned long long v) { atomicMax(p, v); }
 #else
 BD_HD void m_add(uint32_t* p, uint32_t v) { *p += v; }
 BD_HD void m_or(uint32_t* p, uint32_t v) { *p |= v; }
 BD_HD void m_stat(unsigned long long* p, unsigned long long v) { *p += v; }
 BD_HD void m_err(const MateParams& p, int code, uint32_t r) { if (p.err[0] < code) { p.err[0] = code; p.err[1] = (int)r; } }
 BD_HD void m_min(unsigned long long* p, unsigned long long v) { if (v < *p) *p = v; }
+BD_HD void m_max(unsigned long long* p, unsigned long long v) { if (v > *p) *p = v; }
 #endif
 
 BD_HD uint32_t m_ld32(const uint8_t* q) { return (uint32_t)q[0] | ((uint32_t)q[1] << 8) | ((uint32_t)q[2] << 16) | ((uint32_t)q[3] << 24); }
@@ -269,6 +278,8 @@ BD_HD bool mate_follows(const MateParams& p, uint64_t h, uint64_t g, uint32_t wh
     if (p.n_ghost && g < p.covered_from) { m_err(p, MATE_ERR_CROSS, who); return true; }
     for (uint32_t k = 0; k < p.n_ghost && p.start[k] <= g; k++)           // re-read records are not in K3's index
         if ((p.mflag[k] & MF_INSTREAM) && p.start[k] + p.span[k] > g && p.mhash[k] > h) return true;
+    for (uint32_t k = p.R - p.n_right; k < p.R && p.start[k] <= g; k++)   // nor are the records of the next rank's zone
+        if ((p.mflag[k] & MF_INSTREAM) && p.start[k] + p.span[k] > g && p.mhash[k] > h) return true;
     if (g >= p.tiles_base) {
         uint64_t t = (g - p.tiles_base) >> 10;
         if (t < p.n_tiles) {
@@ -395,7 +406,10 @@ BD_HD void mate_fix_one(const MateParams& p, uint32_t r) {
         uint64_t e = p.start[k] + p.span[k]; if (e > reach) reach = e;
     }
     if (!p.last_batch && reach > p.s_last) { m_min(p.open_off, (unsigned long long)p.off[r]); m_min(p.open_start, p.start[r]); return; }      // still open: the batch that closes it fixes it
-    if (p.n_ghost && idx[n - 1] < p.n_ghost && reach <= p.prev_s_last) return;                                   // only re-read records, closed before: already fixed
+    if (p.ncl[r] & MATE_NCL_FOREIGN) return;                                                                    // another rank owns the leader
+    if (p.stream_cut && reach > p.s_last) { m_err(p, MATE_ERR_ZONE, r); return; }                               // runs out of the zone read behind the shard
+    if (p.fix_max_end) m_max(p.fix_max_end, reach);
+    if (p.off[idx[n - 1]] < p.old_below && reach <= p.prev_s_last) return;                                       // only records the previous batch has seen, closed there: already fixed
     if (n == 2 && !p.force_general && !p.seg_u) {
         MRead A, B; m_load(p, idx[0], A); m_load(p, idx[1], B);
         if (m_same_name(A, B)) mate_fix_pair(p, A, B);

@@ -29,7 +29,7 @@ extern "C" int emul_mates(const uint8_t* u, uint32_t R, const uint64_t* start, c
     MateParams p{start, span, meta, off, ncl, lseq, u, R, mhash.data(), mflag.data(), flt_s, flt_e, n_flt, counts, cnt_base, win_len, S, minq,
                  seg_s, seg_e, seg_pmax, seg_id, n_seg, seg_reads, seg_mbases, n_samples_out, seg_u, seg_qmin, seg_ext_max,
                  tile_lo.data(), tiles_base, n_tiles, long_list.data(), (uint32_t)long_list.size(),
-                 0u, ~0ull, 0ull, 0ull, 1, nullptr, nullptr, force_general, err2, stat3};      // one batch: no ghosts, everything closes
+                 0u, ~0ull, 0ull, 0ull, 1, nullptr, nullptr, 0, nullptr, 0u, INT64_MIN, force_general, err2, stat3};      // one batch, one rank: no ghosts, everything closes
     std::vector<uint32_t> ord(R); std::iota(ord.begin(), ord.end(), 0u);
     if (order == 1) std::reverse(ord.begin(), ord.end());
     if (order == 2) { uint64_t s = 88172645463325252ull; for (uint32_t i = R; i > 1; i--) { s ^= s << 13; s ^= s >> 7; s ^= s << 17; std::swap(ord[i - 1], ord[s % i]); } }

@@ -28,11 +28,17 @@ def _rank_main(rank, world, path, uid, mode, q, tuning=None):
             b.set_shard(rank, world, uid)
             if tuning:
                 b.set_tuning(*tuning)
+            if mode.endswith("-m"):
+                b.set_fix_mates(True)
+                mode = mode[:-2]
             if mode == "base":
                 got = b.run_base()
                 st = b.stats()
                 lo, hi = st["own_lo"], st["own_hi"]
                 q.put((rank, "ok", lo, hi, got[:, lo:hi].copy(), st))
+            elif mode == "regions":
+                rows = b.run_regions([(0, 100, 9000), (0, 9000, 9100), (0, 60000, 140000), (2, 5, 100000)], [2, 8])
+                q.put((rank, "ok", 0, 0, rows, b.stats()))
             else:
                 rows = b.run_windows(1000, 0, [1, 10])
                 q.put((rank, "ok", 0, 0, rows, b.stats()))
@@ -125,3 +131,45 @@ def test_sharded_windows_equal_single_gpu(bam):
     res = _run(2, bam, "windows")
     for r in res:
         assert r[4] == want      # the statistics are all-reduced, so every rank holds the full table
+
+
+@pytest.fixture(scope="module")
+def pairs_bam(tmp_path_factory):
+    d = tmp_path_factory.mktemp("multim")
+    small = os.environ.get("BDEPTH_EMULATE") == "1"
+    return helpers.gen_bam(str(d / "mp.bam"), "-r", "chrA:%d" % (200000 if small else 2000000), "-r", "chrB:700", "-r", "chrC:%d" % (150000 if small else 1500000),
+                           "-n", 30000 if small else 300000, "--pairs", 7, "-s", 12, "-t", 8)
+
+
+@pytest.mark.xfail(strict=False, reason="first hardware run pending (-m on several ranks was written without a GPU; it passes under the CPU emulation)")
+@pytest.mark.parametrize("world,tuning", [(2, None), (4, None), (8, None), (3, (1 << 20, 0)), (2, (1 << 16, 0))])
+def test_fix_mates_on_several_ranks(pairs_bam, world, tuning):
+    """-m with shards: every rank reads a zone of its neighbours' records around its shard, a pair cut by a shard boundary is
+    fixed by the rank that owns its first mate and the correction travels with the halo exchange."""
+    if _n_gpus() < world:
+        pytest.skip(f"needs {world} GPUs")
+    want, npc = helpers.oracle_counts_fix_mates(pairs_bam)
+    res = _run(world, pairs_bam, "base-m", tuning)
+    got = np.zeros_like(want)
+    for rank, _, lo, hi, arr, st in res:
+        got[:, lo:hi] = arr
+    assert np.array_equal(got, want)
+    assert sum(r[5]["mate_pair_columns"] for r in res) == npc and npc > 10000
+    _, ost = helpers.oracle_counts(pairs_bam)
+    assert sum(r[5]["n_records"] for r in res) == ost.n_records
+
+
+@pytest.mark.xfail(strict=False, reason="first hardware run pending (-m on several ranks)")
+def test_fix_mates_windows_and_regions_on_several_ranks(pairs_bam):
+    if _n_gpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    import sambamba_b200 as sb
+    with sb.BDepth(pairs_bam) as b:
+        b.set_fix_mates(True)
+        want_w = b.run_windows(1000, 0, [1, 10])
+        want_r = b.run_regions([(0, 100, 9000), (0, 9000, 9100), (0, 60000, 140000), (2, 5, 100000)], [2, 8])
+    for world in (2, 3):
+        for r in _run(world, pairs_bam, "windows-m"):
+            assert r[4] == want_w
+        for r in _run(world, pairs_bam, "regions-m"):
+            assert r[4] == want_r
