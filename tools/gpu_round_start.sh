@@ -36,3 +36,8 @@ PY
 # 5. launch list of one staged pass (cold-cache, serialised: compare shares, not absolutes)
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline > $OUT/ncu_bench.log 2>&1
 tail -3 $OUT/pytest_gpu.log; cat $OUT/bench_n1.json | head -c 600; echo; grep -o '"e2e": {"value": [0-9.]*' $OUT/bench_n1*.json; grep -o '"k3_coverage": [0-9.]*' $OUT/bench_n1.json $OUT/bench_n1_k3pre.json
+
+# Second call, on two GPUs (the sharded path: sub-batches per rank and -m across shard boundaries have only run under the
+# CPU emulation so far):
+#   /usr/local/graft/bin/gpurun --gpus 2 --timeout 1500 -- 'python -m pytest tests/test_gpu_multi.py -m gpu -q -rxX -p no:cacheprovider > gpurun_out/round_start_multi.log 2>&1; \
+#     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 3 --warmup 3 > gpurun_out/bench_n2.json 2> gpurun_out/bench_n2.err'
