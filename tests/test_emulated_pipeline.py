@@ -10,15 +10,17 @@ import sys
 
 from helpers import ROOT
 
-SUITES = ["tests/test_gpu_cli.py", "tests/test_zz_gpu_mates.py", "tests/test_zz_gpu_filter.py", "tests/test_gpu_multi.py"]
+# (suite, -k expression): the -m suite is split in two so that the four processes take about the same time
+SUITES = [("tests/test_gpu_cli.py", None), ("tests/test_zz_gpu_mates.py", "several_batches or window_mode"),
+          ("tests/test_zz_gpu_mates.py", "not several_batches and not window_mode"), ("tests/test_zz_gpu_filter.py", None), ("tests/test_gpu_multi.py", None)]
 
 
 def test_gpu_suites_pass_under_cpu_emulation():
     subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "tests", "emul")], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
     env = dict(os.environ, BDEPTH_EMULATE="1")
-    procs = [(s, subprocess.Popen([sys.executable, "-m", "pytest", s, "-q", "-m", "gpu", "--runxfail", "-p", "no:cacheprovider", "-x"], cwd=ROOT, env=env,
-                                  stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)) for s in SUITES]
+    procs = [((s, k), subprocess.Popen([sys.executable, "-m", "pytest", s, "-q", "-m", "gpu", "--runxfail", "-p", "no:cacheprovider", "-x"] + (["-k", k] if k else []), cwd=ROOT, env=env,
+                                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)) for s, k in SUITES]
     for s, p in procs:
         out, _ = p.communicate(timeout=1500)
         assert p.returncode == 0, (s, out[-3000:])
-        assert " passed" in out and "failed" not in out and "skipped" not in out, (s, out[-600:])
+        assert " passed" in out and "failed" not in out and "skipped" not in out, (s, out[-600:])      # (deselected by -k is fine)
