@@ -337,7 +337,7 @@ def main():
                 "ms_per_step": e2e_s * 1e3, "covered_mbases_per_s": covered / 1e6 / e2e_s, "first_call_incl_open_ms": cold_s * 1e3,
                 "device_ms": {k: e2e_stats[k] for k in ("ms_h2d", "ms_inflate", "ms_scan", "ms_coverage", "ms_d2h", "ms_span_device")},
                 "path": "bdepth_open_memory(pinned host BAM image) + bdepth_run_base -> 7 x u32 counters in pinned host memory", "host_input": host_kind, "chunk_blocks": chunk_blocks or "default (6656)",
-                "variants": {k: os.environ[k] for k in ("BDEPTH_K1_STREAM_WARPS", "BDEPTH_K3_PREFETCH") if k in os.environ}},
+                "variants": {k: os.environ[k] for k in ("BDEPTH_K1_STREAM_WARPS", "BDEPTH_K1_LIT3", "BDEPTH_K3_PREFETCH") if k in os.environ}},
         "text_rows": text,
         "gpu_launches": int(total_launches),
         "roofline": {"kernel": "k1_inflate (lane-per-BGZF-block DEFLATE)", "bound": "hbm", "achieved": k1_bytes / 1e9 / (k1_ms / 1e3), "peak": peak, "unit": "GB/s",

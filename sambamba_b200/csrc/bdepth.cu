@@ -151,6 +151,7 @@ struct bdepth {
     bool fix_mates = false;               // -m: overlapping mates count once per column (mates.cuh)
     bool k1_small = false;                // BDEPTH_K1_STREAM_WARPS=4: streaming K1 sub-launches in 4-warp CTAs (experiment)
     bool k3_pre = false;                  // BDEPTH_K3_PREFETCH=1: k3_gather with lane-parallel record prefetch (experiment)
+    bool k1_lit3 = false;                 // BDEPTH_K1_LIT3=1: K1 with up to three literals per iteration (experiment)
     bool has_fprog = false; FilterProg fprog; DevBuf fprog_d;      // -F: compiled query (filter.cuh); otherwise mapq_gt / flag_reject
     DevBuf m_hash, m_flag, m_flt, m_ctl;
     uint32_t S = 1;                       // counter sets in the current run (samples, or 1)
@@ -219,6 +220,8 @@ int init_device(bdepth* h) {
     CK(cudaFuncSetAttribute(k1_inflate, cudaFuncAttributeMaxDynamicSharedMemorySize, K1_SMEM));
     { const char* e = getenv("BDEPTH_K1_STREAM_WARPS"); h->k1_small = e && atoi(e) == K1S_WARPS; }      // experiment, see kernels.cuh
     { const char* e = getenv("BDEPTH_K3_PREFETCH"); h->k3_pre = e && atoi(e) == 1; }
+    { const char* e = getenv("BDEPTH_K1_LIT3"); h->k1_lit3 = e && atoi(e) == 1; }
+    if (h->k1_lit3) CK(cudaFuncSetAttribute(k1_inflate_lit3, cudaFuncAttributeMaxDynamicSharedMemorySize, K1_SMEM));
     if (h->k1_small) { CK(cudaFuncSetAttribute(k1_inflate_small, cudaFuncAttributeMaxDynamicSharedMemorySize, K1S_SMEM)); CK(cudaFuncSetAttribute(k1_inflate_small, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)); }
     return 0;
 }
@@ -727,7 +730,8 @@ int run_pipeline(bdepth* h, RunMode mode, RunOut* ro, Emitter* em = nullptr) {
         // ---- K1: when the input is streaming in, one sub-launch per H2D chunk, spread over a few streams so that
         // they run side by side (a lone sub-launch cannot fill the GPU: every lane owns a whole BGZF block)
         if (h->staged) {
-            BD_LAUNCH((unsigned)((nb + 32 * K1_WARPS - 1) / (32 * K1_WARPS)), 32 * K1_WARPS, K1_SMEM, sm, k1_inflate)(d_comp, h->descs.as<BlockDesc>(), (uint32_t)nb, u0, h->status.as<int>());
+            if (h->k1_lit3) BD_LAUNCH((unsigned)((nb + 32 * K1_WARPS - 1) / (32 * K1_WARPS)), 32 * K1_WARPS, K1_SMEM, sm, k1_inflate_lit3)(d_comp, h->descs.as<BlockDesc>(), (uint32_t)nb, u0, h->status.as<int>());
+            else BD_LAUNCH((unsigned)((nb + 32 * K1_WARPS - 1) / (32 * K1_WARPS)), 32 * K1_WARPS, K1_SMEM, sm, k1_inflate)(d_comp, h->descs.as<BlockDesc>(), (uint32_t)nb, u0, h->status.as<int>());
             CK(cudaGetLastError()); st.gpu_launches++;
             subs.push_back(Sub{b, b1, 0, -1});
         } else {
@@ -736,7 +740,8 @@ int run_pipeline(bdepth* h, RunMode mode, RunOut* ro, Emitter* em = nullptr) {
                 size_t c1 = h->chunk_end[slot][j]; cudaStream_t ks = h->s_k1[j & 15];
                 CK(cudaStreamWaitEvent(ks, e1, 0)); CK(cudaStreamWaitEvent(ks, h->chunk_ev[slot][j], 0));
                 uint32_t n = (uint32_t)(c1 - c0);
-                if (h->k1_small) BD_LAUNCH((n + 32 * K1S_WARPS - 1) / (32 * K1S_WARPS), 32 * K1S_WARPS, K1S_SMEM, ks, k1_inflate_small)(d_comp, h->descs.as<BlockDesc>() + (c0 - b), n, u0, h->status.as<int>() + (c0 - b));
+                if (h->k1_lit3) BD_LAUNCH((n + 32 * K1_WARPS - 1) / (32 * K1_WARPS), 32 * K1_WARPS, K1_SMEM, ks, k1_inflate_lit3)(d_comp, h->descs.as<BlockDesc>() + (c0 - b), n, u0, h->status.as<int>() + (c0 - b));
+                else if (h->k1_small) BD_LAUNCH((n + 32 * K1S_WARPS - 1) / (32 * K1S_WARPS), 32 * K1S_WARPS, K1S_SMEM, ks, k1_inflate_small)(d_comp, h->descs.as<BlockDesc>() + (c0 - b), n, u0, h->status.as<int>() + (c0 - b));
                 else BD_LAUNCH((n + 32 * K1_WARPS - 1) / (32 * K1_WARPS), 32 * K1_WARPS, K1_SMEM, ks, k1_inflate)(d_comp, h->descs.as<BlockDesc>() + (c0 - b), n, u0, h->status.as<int>() + (c0 - b));
                 CK(cudaGetLastError()); st.gpu_launches++;
                 if (h->k1_ev.size() <= j) { cudaEvent_t ne; CK(cudaEventCreateWithFlags(&ne, cudaEventDisableTiming)); h->k1_ev.push_back(ne); }

@@ -506,7 +506,10 @@ BD_HD_COLD HdrResult next_block(Tab t, BitReader br, uint8_t* lens, uint32_t* li
 // output bytes go to absolute stream offsets [a0, a0+isize) of `out`.  On the device ALL 32 lanes
 // of the warp must call this together; lanes without a block pass active = false.
 // scratch: 320 bytes for code lengths + 64 bytes for the limit hand-over, 4-byte aligned.
-template <class Tab, class Out>
+// LIT3 (EXPERIMENT, kernels.cuh k1_inflate_lit3): after two literals take a third one in the same iteration when the bits
+// that are left hold its whole code.  Host emulation on the bench workload: a third literal is available in 40 % of the
+// iterations (about a fifth fewer iterations) for one more decode_sym_at per iteration.
+template <class Tab, class Out, bool LIT3 = false>
 BD_HD int inflate_block(const Tab& t, const uint32_t* words, uint64_t byte_off, uint32_t nbytes, const Out& out, uint64_t a0, uint32_t isize, uint32_t* scratch /* 384 B */, bool active = true) {
     unsigned mask = BD_BALLOT(0xFFFFFFFFu, active);
     if (!active) return INF_OK;
@@ -545,7 +548,13 @@ BD_HD int inflate_block(const Tab& t, const uint32_t* words, uint64_t byte_off, 
                     // next symbol too (>= 18 valid bits remain after a refill and one code) and take it in the same
                     // iteration if it is a literal.  Anything else stays in the reservoir for the next iteration.
                     int L2; int s2 = decode_sym_at<Tab, 0>(t, ll, (uint32_t)br.bb, L2);
-                    if (s2 >= 0 && s2 < 256) { br.drop(L2); lit2 = (uint32_t)s2; n_lit = 2; }
+                    if (s2 >= 0 && s2 < 256) {
+                        br.drop(L2); lit2 = (uint32_t)s2; n_lit = 2;
+                        if (LIT3 && pos + 3 <= isize) {      // the reservoir is zero above its bc valid bits: a code is whole iff its length fits
+                            int L3; int s3 = decode_sym_at<Tab, 0>(t, ll, (uint32_t)br.bb, L3);
+                            if (s3 >= 0 && s3 < 256 && L3 <= br.bc) { br.drop(L3); lit2 |= (uint32_t)s3 << 8; n_lit = 3; }
+                        }
+                    }
                 }
             } else if (state == ST_STORED) {
                 br.refill(); sym = (int)br.get(8); have_sym = true;

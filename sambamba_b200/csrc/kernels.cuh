@@ -88,6 +88,22 @@ __global__ void __launch_bounds__(K1S_WARPS * 32, 3) k1_inflate_small(const uint
     if (active) status[b] = rc;
 }
 
+// EXPERIMENT (off by default, BDEPTH_K1_LIT3=1): k1_inflate with up to three literals per iteration (inflate_core.cuh LIT3).
+__global__ void __launch_bounds__(K1_WARPS * 32, 1) k1_inflate_lit3(const uint32_t* __restrict__ comp, const BlockDesc* __restrict__ blocks,
+                                                                    uint32_t n_blocks, uint8_t* __restrict__ u, int* __restrict__ status) {
+    BD_DYN_SMEM(uint32_t, smem);
+    uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t b = (blockIdx.x * K1_WARPS + warp) * 32u + lane;
+    uint32_t scratch[96];
+    const bool active = b < n_blocks;
+    BlockDesc d = active ? blocks[b] : BlockDesc{0, 0, 0, 0};
+    uint32_t* wbase = smem + warp * (SMEM_BYTES_PER_WARP / 4);
+    SmemTab tab{wbase + lane, (uint32_t)__cvta_generic_to_shared(wbase + T_WORDS * 32) + lane * 16, (uint32_t)__cvta_generic_to_shared(wbase + T_FAR * 32 + lane)};
+    ByteOut out{u};
+    int rc = inflate_block<SmemTab, ByteOut, true>(tab, comp, d.coff, d.csize, out, d.uoff, d.isize, scratch, active);
+    if (active) status[b] = rc;
+}
+
 // ------------------------------------------------------------------------------------- K2
 // Unaligned little-endian loads from the inflated stream: two aligned 32-bit loads + funnel shift (records are
 // byte-aligned; four byte loads per field made k2_decode LSU-queue bound: profiles/r1_k2_k3_ncu_full_summary.txt).

@@ -12,6 +12,8 @@ using namespace bdk;
 
 extern "C" void emul_stats(unsigned long long* o) { memcpy(o, &g_inflate_stats, sizeof(g_inflate_stats)); memset(&g_inflate_stats, 0, sizeof(g_inflate_stats)); }
 
+static bool g_lit3 = false;
+extern "C" void emul_set_lit3(int on) { g_lit3 = on != 0; }       // the three-literal variant of the lane logic (k1_inflate_lit3)
 extern "C" long emul_inflate_file(const char* path, uint8_t* dst, uint64_t cap, int* first_err) {
     FILE* f = fopen(path, "rb"); if (!f) return -1;
     fseek(f, 0, SEEK_END); long n = ftell(f); fseek(f, 0, SEEK_SET);
@@ -31,7 +33,7 @@ extern "C" long emul_inflate_file(const char* path, uint8_t* dst, uint64_t cap, 
         if (uoff + isize > cap) return -2;
         memset(tab, 0xAB, sizeof tab);
         FlatTab ft{tab}; ByteOut out{dst};
-        int rc = inflate_block(ft, words.data(), off + 12 + xlen, cdata, out, uoff, isize, lens);
+        int rc = g_lit3 ? inflate_block<FlatTab, ByteOut, true>(ft, words.data(), off + 12 + xlen, cdata, out, uoff, isize, lens) : inflate_block(ft, words.data(), off + 12 + xlen, cdata, out, uoff, isize, lens);
         if (rc) { *first_err = rc; return -(100 + rc); }
         uoff += isize; off += total;
     }
@@ -43,5 +45,5 @@ extern "C" int emul_inflate_raw(const uint8_t* src, uint32_t n, uint8_t* dst, ui
     memcpy((uint8_t*)words.data() + byte_off, src, n);
     uint32_t tab[T_WORDS]; uint32_t lens[96]; memset(tab, 0xCD, sizeof tab);
     FlatTab ft{tab}; ByteOut out{dst};
-    return inflate_block(ft, words.data(), byte_off, n, out, out_off, isize, lens);
+    return g_lit3 ? inflate_block<FlatTab, ByteOut, true>(ft, words.data(), byte_off, n, out, out_off, isize, lens) : inflate_block(ft, words.data(), byte_off, n, out, out_off, isize, lens);
 }

@@ -13,12 +13,15 @@ import helpers
 from helpers import GOLDEN, ROOT
 
 
-@pytest.fixture(scope="module")
-def em():
+@pytest.fixture(scope="module", params=[0, 1], ids=["two-literals", "three-literals"])
+def em(request):
+    """Both variants of the lane logic: the default one and the one behind k1_inflate_lit3 (BDEPTH_K1_LIT3=1)."""
     L = C.CDLL(os.path.join(ROOT, "tests", "emul", "libemul.so"))
     L.emul_inflate_file.restype = C.c_long
     L.emul_inflate_raw.restype = C.c_int
-    return L
+    L.emul_set_lit3(request.param)
+    yield L
+    L.emul_set_lit3(0)
 
 
 @pytest.fixture(scope="module")

@@ -13,6 +13,7 @@ timeout 300 python __graft_entry__.py smoke > $OUT/smoke.log 2>&1
 timeout 900 python bench.py --steps 5 --warmup 3 > $OUT/bench_n1.json 2> $OUT/bench_n1.err
 # 3. K1 experiment: 4-warp CTAs for the streaming sub-launches (kernels.cuh k1_inflate_small); compare e2e.ms_per_step
 BDEPTH_K1_STREAM_WARPS=4 timeout 900 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > $OUT/bench_n1_k1small.json 2> $OUT/bench_n1_k1small.err
+BDEPTH_K1_LIT3=1 timeout 900 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > $OUT/bench_n1_k1lit3.json 2> $OUT/bench_n1_k1lit3.err             # compare stage_ms.k1_inflate
 BDEPTH_K3_PREFETCH=1 timeout 900 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > $OUT/bench_n1_k3pre.json 2> $OUT/bench_n1_k3pre.err      # compare stage_ms.k3_coverage
 for cb in 1664 3328 13312; do       # H2D chunk / sub-batch size sweep (default 6656 blocks), with and without the 4-warp CTAs
   BDEPTH_BENCH_CHUNK_BLOCKS=$cb timeout 600 python bench.py --steps 3 --warmup 2 --no-cpu-baseline > $OUT/bench_n1_cb$cb.json 2> $OUT/bench_n1_cb$cb.err
@@ -35,7 +36,7 @@ with sb.BDepth(p) as b:
 PY
 # 5. launch list of one staged pass (cold-cache, serialised: compare shares, not absolutes)
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline > $OUT/ncu_bench.log 2>&1
-tail -3 $OUT/pytest_gpu.log; cat $OUT/bench_n1.json | head -c 600; echo; grep -o '"e2e": {"value": [0-9.]*' $OUT/bench_n1*.json; grep -o '"k3_coverage": [0-9.]*' $OUT/bench_n1.json $OUT/bench_n1_k3pre.json
+tail -3 $OUT/pytest_gpu.log; cat $OUT/bench_n1.json | head -c 600; echo; grep -o '"e2e": {"value": [0-9.]*' $OUT/bench_n1*.json; grep -o '"k3_coverage": [0-9.]*' $OUT/bench_n1.json $OUT/bench_n1_k3pre.json; grep -o '"k1_inflate": [0-9.]*' $OUT/bench_n1.json $OUT/bench_n1_k1lit3.json
 
 # Second call, on two GPUs (the sharded path: sub-batches per rank and -m across shard boundaries have only run under the
 # CPU emulation so far):
