@@ -15,6 +15,14 @@ SUITES = [("tests/test_gpu_cli.py", None), ("tests/test_zz_gpu_mates.py", "sever
           ("tests/test_zz_gpu_mates.py", "not several_batches and not window_mode"), ("tests/test_zz_gpu_filter.py", None), ("tests/test_gpu_multi.py", None)]
 
 
+def test_the_emulation_itself():
+    """Known-answer kernels for every collective the library uses (ballot with shrinking masks, shuffles, reductions,
+    __syncthreads with threads that left, static / dynamic shared memory, atomics): tests/emul/shim_selftest.cpp."""
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "tests", "emul"), "shim_selftest"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    r = subprocess.run([os.path.join(ROOT, "tests", "emul", "shim_selftest")], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.strip() == "ok", r.stdout + r.stderr
+
+
 def test_gpu_suites_pass_under_cpu_emulation():
     subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "tests", "emul")], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
     env = dict(os.environ, BDEPTH_EMULATE="1")
