@@ -200,8 +200,9 @@ int bdepth_run_windows(bdepth_t* h, uint32_t window, uint32_t overlap, const uin
 int bdepth_run_regions(bdepth_t* h, const bdepth_region* regions, size_t n, const uint32_t* thresholds, size_t n_thresholds, bdepth_stat_cb cb, void* user);
 
 /* `depth base` with the row text produced on the GPU: the rows PerBasePrinter would print
- * (depth.d:534-555, zero rows :452-487) for one sample or --combined, delivered in order as text chunks.
- * Returns BDEPTH_ERR_ARG for multi-sample per-sample output (use bdepth_run_base and format on the host). */
+ * (depth.d:534-555, zero rows :452-487), delivered in order as text chunks: one row per position for one sample or
+ * --combined, one row per sample and position otherwise (a sample whose COV is out of bounds ends the position, as
+ * writeColumn's early return does). */
 typedef struct { double min_cov, max_cov; int annotate; } bdepth_text_opts;
 typedef int (*bdepth_text_cb)(void* user, const char* text, size_t len);
 int bdepth_run_base_text(bdepth_t* h, const bdepth_text_opts* opts, bdepth_text_cb cb, void* user);

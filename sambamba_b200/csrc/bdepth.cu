@@ -156,7 +156,7 @@ struct bdepth {
     DevBuf m_hash, m_flag, m_flt, m_ctl;
     uint32_t S = 1;                       // counter sets in the current run (samples, or 1)
     DevBuf rg_ids, rg_offs, rg_samp;
-    DevBuf text[2], text_tiles, text_offs, text_zero;
+    DevBuf text[2], text_tiles, text_offs, text_zero, text_samp;
     uint64_t batch_u = 6ull << 30;
     uint64_t chunk_blocks = 13 * 32 * 16;              // BGZF blocks per H2D chunk = per K1 sub-launch = per sub-batch: 6656 blocks = 16 K1 CTAs, ~260 MB compressed
     // ---- shard (resolved lazily)
@@ -1104,7 +1104,7 @@ void bdepth_close(bdepth_t* h) {
     DevBuf* bufs[] = {&h->comp, &h->descs, &h->status, &h->ubuf, &h->chunk_start, &h->entry, &h->exitb, &h->count, &h->slot_base, &h->slots, &h->rec_base, &h->walk_list, &h->soa_start, &h->soa_span, &h->soa_meta, &h->soa_off, &h->soa_ncl, &h->soa_lseq, &h->long_list, &h->tile_first, &h->tile_lo, &h->counts, &h->ref_len_d, &h->ref_lin0_d, &h->scan_stats, &h->ref_has, &h->misc};
     for (DevBuf* b : bufs) b->release();
     h->rg_ids.release(); h->rg_offs.release(); h->rg_samp.release();
-    h->text[0].release(); h->text[1].release(); h->text_tiles.release(); h->text_offs.release(); h->text_zero.release();
+    h->text[0].release(); h->text[1].release(); h->text_tiles.release(); h->text_offs.release(); h->text_zero.release(); h->text_samp.release();
     h->seg.s.release(); h->seg.e.release(); h->seg.pmax.release(); h->seg.id.release(); h->seg.reads.release(); h->seg.minstart.release(); h->seg.bases_reads.release(); h->seg.mbases.release(); h->seg.ustart.release();
     h->m_hash.release(); h->m_flag.release(); h->m_flt.release(); h->m_ctl.release(); h->fprog_d.release();
     if (h->comm) { nccl().CommDestroy(h->comm); h->comm = nullptr; }
@@ -1266,8 +1266,8 @@ int bdepth_run_base(bdepth_t* h, bdepth_tile_cb cb, void* user) {
 // ---- base mode with GPU-side text
 int bdepth_run_base_text(bdepth_t* h, const bdepth_text_opts* o, bdepth_text_cb cb, void* user) {
     if (!o) return fail(h, BDEPTH_ERR_ARG, "null options");
-    if (!h->combined && h->hdr.sample_names.size() > 1) return fail(h, BDEPTH_ERR_ARG, "GPU text formatting handles one sample or --combined; use bdepth_run_base for per-sample rows");
     int rc = run_pipeline(h, RUN_FULL, nullptr); if (rc) return rc;
+    const bool ms = h->S > 1;             // one row per sample and position (k_text_len_ms / k_text_write_ms)
     cudaStream_t sm = h->s_main;
     cudaEvent_t e0 = h->ev[5], e1 = h->ev[6];
     CK(cudaEventRecord(e0, sm));
@@ -1280,6 +1280,19 @@ int bdepth_run_base_text(bdepth_t* h, const bdepth_text_opts* o, bdepth_text_cb 
     const std::string& sn = h->hdr.sample_names[0];
     if (sn.size() > 255) return fail(h, BDEPTH_ERR_ARG, "sample name too long");
     tp.sample_len = (uint32_t)sn.size(); memcpy(tp.sample, sn.data(), sn.size());
+    TextParamsMS tpm; memset(&tpm, 0, sizeof tpm); size_t max_sample = sn.size();
+    if (ms) {
+        std::vector<char> names; std::vector<uint32_t> offs;
+        for (uint32_t si = 0; si < h->S; si++) { const std::string& x = h->hdr.sample_names[si]; offs.push_back((uint32_t)names.size()); names.insert(names.end(), x.begin(), x.end()); max_sample = std::max(max_sample, x.size()); }
+        offs.push_back((uint32_t)names.size());
+        const size_t off_bytes = (names.size() + 15) & ~size_t(15);
+        CK(h->text_samp.ensure(off_bytes + offs.size() * 4 + 16));
+        if (!names.empty()) CK(cudaMemcpyAsync(h->text_samp.p, names.data(), names.size(), cudaMemcpyHostToDevice, sm));
+        CK(cudaMemcpyAsync((uint8_t*)h->text_samp.p + off_bytes, offs.data(), offs.size() * 4, cudaMemcpyHostToDevice, sm));
+        CK(cudaStreamSynchronize(sm));
+        tpm.min_cov = o->min_cov; tpm.max_cov = o->max_cov; tpm.annotate = o->annotate ? 1 : 0; tpm.S = h->S;
+        tpm.samp = h->text_samp.as<char>(); tpm.samp_off = (const uint32_t*)((uint8_t*)h->text_samp.p + off_bytes);
+    }
     constexpr size_t TEXT_BUF = 128ull << 20;
     rc = ensure_pinned(h, std::max<size_t>(2 * TEXT_BUF, 2 * EMIT_CHUNK * N_PLANES * 4)); if (rc) return rc;
     CK(h->text[0].ensure(TEXT_BUF)); CK(h->text[1].ensure(TEXT_BUF));
@@ -1296,7 +1309,7 @@ int bdepth_run_base_text(bdepth_t* h, const bdepth_text_opts* o, bdepth_text_cb 
             uint64_t e = std::min(b, h->hdr.ref_lin0[ref] + h->hdr.ref_len[ref]);
             bool inw = a >= h->cnt_base && a < h->cnt_base + h->win_len;
             if (inw) e = std::min(e, h->cnt_base + h->win_len); else if (a < h->cnt_base) e = std::min(e, h->cnt_base);
-            size_t max_row = h->hdr.ref_names[ref].size() + sn.size() + 96;
+            size_t max_row = (h->hdr.ref_names[ref].size() + max_sample + 96) * (ms ? h->S : 1);
             uint64_t cp = std::max<uint64_t>(TEXT_TILE, (TEXT_BUF / max_row) / TEXT_TILE * TEXT_TILE);
             e = std::min(e, a + cp);
             if (inw || o->min_cov <= 0) pieces.push_back({(uint32_t)ref, a, e, inw});      // zero rows only exist when min_cov == 0
@@ -1322,17 +1335,20 @@ int bdepth_run_base_text(bdepth_t* h, const bdepth_text_opts* o, bdepth_text_cb 
         const std::string& nm = h->hdr.ref_names[p.ref];
         if (nm.size() > 255) return fail(h, BDEPTH_ERR_ARG, "reference name too long");
         tp.name_len = (uint32_t)nm.size(); memcpy(tp.name, nm.data(), nm.size());
+        tpm.name_len = tp.name_len; memcpy(tpm.name, nm.data(), nm.size()); tpm.sample_stride = p.in_window ? (uint64_t)N_PLANES * h->win_len : 0;
         uint32_t n = (uint32_t)(p.b - p.a), n_tiles = (n + TEXT_TILE - 1) / TEXT_TILE, pos0 = (uint32_t)(p.a - h->hdr.ref_lin0[p.ref]);
         const uint32_t* cnt = p.in_window ? h->counts.as<uint32_t>() : h->text_zero.as<uint32_t>();
         uint64_t wl = p.in_window ? h->win_len : 0, idx0 = p.in_window ? p.a - h->cnt_base : 0;
         unsigned long long* tot_d = (unsigned long long*)((uint8_t*)h->text_offs.p + (size_t)(max_piece / TEXT_TILE + 2) * 8);
-        BD_LAUNCH(n_tiles, 256, 0, sm, k_text_len)(tp, cnt, wl, idx0, pos0, n, h->text_tiles.as<uint32_t>());
+        if (ms) BD_LAUNCH(n_tiles, 256, 0, sm, k_text_len_ms)(tpm, cnt, wl, idx0, pos0, n, h->text_tiles.as<uint32_t>());
+        else BD_LAUNCH(n_tiles, 256, 0, sm, k_text_len)(tp, cnt, wl, idx0, pos0, n, h->text_tiles.as<uint32_t>());
         BD_LAUNCH(1, 1024, 0, sm, k_text_scan)(h->text_tiles.as<uint32_t>(), n_tiles, (unsigned long long*)h->text_offs.p, tot_d);
         unsigned long long tot = 0; CK(cudaMemcpyAsync(&tot, tot_d, 8, cudaMemcpyDeviceToHost, sm));
         CK(cudaStreamSynchronize(sm));
         if (tot > TEXT_BUF) return fail(h, BDEPTH_ERR_ARG, "internal: text chunk larger than its buffer");
         if (tot) {
-            BD_LAUNCH(n_tiles, 256, 0, sm, k_text_write)(tp, cnt, wl, idx0, pos0, n, (const unsigned long long*)h->text_offs.p, h->text[slot].as<char>());
+            if (ms) BD_LAUNCH(n_tiles, 256, 0, sm, k_text_write_ms)(tpm, cnt, wl, idx0, pos0, n, (const unsigned long long*)h->text_offs.p, h->text[slot].as<char>());
+            else BD_LAUNCH(n_tiles, 256, 0, sm, k_text_write)(tp, cnt, wl, idx0, pos0, n, (const unsigned long long*)h->text_offs.p, h->text[slot].as<char>());
             CK(cudaGetLastError());
             CK(cudaMemcpyAsync((char*)h->pinned + (size_t)slot * TEXT_BUF, h->text[slot].p, tot, cudaMemcpyDeviceToHost, sm));
         }

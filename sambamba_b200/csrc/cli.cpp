@@ -299,8 +299,9 @@ int main(int argc, char** argv) {
     }
     if (c.mode == 0) {
         if (has_bed) { if (regs.empty()) { c.out.flush(); bdepth_close(c.h); return 0; } bdepth_set_regions(c.h, regs.data(), regs.size()); }
-        // rows are formatted on the GPU when there is a single counter set; per-sample rows are formatted here
-        if (c.combined || c.samples.size() == 1) { bdepth_text_opts to{c.min_cov, c.max_cov, c.annotate ? 1 : 0}; rc = bdepth_run_base_text(c.h, &to, text_cb, &c); }
+        // rows are formatted on the GPU (one counter set, or one row per sample and position); base_tile_cb is the host-side
+        // formatter a caller of bdepth_run_base would use
+        if (c.combined || c.samples.size() <= 64) { bdepth_text_opts to{c.min_cov, c.max_cov, c.annotate ? 1 : 0}; rc = bdepth_run_base_text(c.h, &to, text_cb, &c); }
         else rc = bdepth_run_base(c.h, base_tile_cb, &c);
     } else if (c.mode == 1) {
         rc = bdepth_run_regions(c.h, regs.data(), regs.size(), c.thr.data(), c.thr.size(), stat_cb, &c);

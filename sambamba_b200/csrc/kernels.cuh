@@ -735,4 +735,64 @@ __global__ void __launch_bounds__(256) k_text_write(TextParams tp, const uint32_
     }
 }
 
+// ---- the same for several samples: every position prints one row per sample, in sample order, and the first sample whose
+// COV is out of bounds ends the position (writeColumn returns instead of continuing, depth.d:540-541 -- SURVEY quirk 2);
+// a position without any read prints nothing when min_cov > 0 and one zero row per sample otherwise (depth.d:452-487).
+struct TextParamsMS {
+    double min_cov, max_cov; int annotate; uint32_t name_len; char name[256];
+    uint32_t S; const char* samp; const uint32_t* samp_off;      // sample names concatenated, S + 1 offsets
+    uint64_t sample_stride;                                       // elements between the counter sets of two samples (0: all read the same planes)
+};
+// length of the rows of one position; writes them when p != nullptr
+__device__ __forceinline__ uint32_t text_rows_ms(const TextParamsMS& tp, const uint32_t* __restrict__ counts, uint64_t win_len, uint64_t idx, uint32_t pos, char* p) {
+    uint32_t any = 0;
+    for (uint32_t s = 0; s < tp.S; s++) for (int pl = 0; pl < N_PLANES; pl++) any |= counts[(uint64_t)s * tp.sample_stride + (uint64_t)pl * win_len + idx];
+    if (!any && tp.min_cov > 0) return 0;
+    uint32_t len = 0;
+    for (uint32_t s = 0; s < tp.S; s++) {
+        uint32_t v[N_PLANES], total = 0;
+#pragma unroll
+        for (int pl = 0; pl < N_PLANES; pl++) { v[pl] = counts[(uint64_t)s * tp.sample_stride + (uint64_t)pl * win_len + idx]; total += v[pl]; }
+        const bool ok = (double)total >= tp.min_cov && (double)total <= tp.max_cov;
+        if (!ok && !tp.annotate) break;
+        const uint32_t sl = tp.samp_off[s + 1] - tp.samp_off[s];
+        uint32_t rl = tp.name_len + 1 + dec_digits(pos) + 1 + dec_digits(total) + 1 + dec_digits(v[0]) + 1 + dec_digits(v[1]) + 1 + dec_digits(v[2]) + 1 + dec_digits(v[3]) + 1 + dec_digits(v[5]) + 1 + dec_digits(v[6]) + 1 + sl + (tp.annotate ? 2 : 0) + 1;
+        if (p) {
+            char* q = p + len;
+            for (uint32_t k = 0; k < tp.name_len; k++) *q++ = tp.name[k];
+            *q++ = '\t'; q = put_dec(q, pos); *q++ = '\t'; q = put_dec(q, total);
+            *q++ = '\t'; q = put_dec(q, v[0]); *q++ = '\t'; q = put_dec(q, v[1]); *q++ = '\t'; q = put_dec(q, v[2]); *q++ = '\t'; q = put_dec(q, v[3]);
+            *q++ = '\t'; q = put_dec(q, v[5]); *q++ = '\t'; q = put_dec(q, v[6]);
+            *q++ = '\t'; for (uint32_t k = 0; k < sl; k++) *q++ = tp.samp[tp.samp_off[s] + k];
+            if (tp.annotate) { *q++ = '\t'; *q++ = !any ? (tp.min_cov > 0 ? 'n' : 'y') : (ok ? 'y' : 'n'); }
+            *q++ = '\n';
+        }
+        len += rl;
+    }
+    return len;
+}
+__global__ void __launch_bounds__(256) k_text_len_ms(TextParamsMS tp, const uint32_t* __restrict__ counts, uint64_t win_len, uint64_t idx0, uint32_t pos0, uint32_t n, uint32_t* __restrict__ tile_sum) {
+    __shared__ uint32_t wsum[8];
+    uint32_t base = blockIdx.x * TEXT_TILE, s = 0;
+    for (int k = 0; k < 4; k++) { uint32_t i = base + threadIdx.x * 4 + k; if (i < n) s += text_rows_ms(tp, counts, win_len, idx0 + i, pos0 + i, nullptr); }
+    for (int sh = 16; sh; sh >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, sh);
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) { uint32_t t = 0; for (int w = 0; w < 8; w++) t += wsum[w]; tile_sum[blockIdx.x] = t; }
+}
+__global__ void __launch_bounds__(256) k_text_write_ms(TextParamsMS tp, const uint32_t* __restrict__ counts, uint64_t win_len, uint64_t idx0, uint32_t pos0, uint32_t n,
+                                                       const unsigned long long* __restrict__ tile_off, char* __restrict__ out) {
+    __shared__ uint32_t wsum[8];
+    uint32_t base = blockIdx.x * TEXT_TILE, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t len[4], mine = 0;
+    for (int k = 0; k < 4; k++) { uint32_t i = base + threadIdx.x * 4 + k; len[k] = i < n ? text_rows_ms(tp, counts, win_len, idx0 + i, pos0 + i, nullptr) : 0; mine += len[k]; }
+    uint32_t incl = mine;
+    for (int sh = 1; sh < 32; sh <<= 1) { uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, sh); if (lane >= (uint32_t)sh) incl += t; }
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    uint32_t woff = 0; for (uint32_t w = 0; w < warp; w++) woff += wsum[w];
+    char* p = out + tile_off[blockIdx.x] + woff + (incl - mine);
+    for (int k = 0; k < 4; k++) { if (!len[k]) continue; uint32_t i = base + threadIdx.x * 4 + k; text_rows_ms(tp, counts, win_len, idx0 + i, pos0 + i, p); p += len[k]; }
+}
+
 }  // namespace bdk
