@@ -156,7 +156,8 @@ struct bdepth {
     DevBuf m_hash, m_flag, m_flt, m_ctl;
     uint32_t S = 1;                       // counter sets in the current run (samples, or 1)
     DevBuf rg_ids, rg_offs, rg_samp;
-    DevBuf text[2], text_tiles, text_offs, text_zero, text_samp;
+    DevBuf text[2], text_tiles, text_offs, text_zero, text_samp, present;
+    bool want_presence = false;           // -a with -q and a positive minimum coverage: mark the positions reads cover (k_presence)
     uint64_t batch_u = 6ull << 30;
     uint64_t chunk_blocks = 13 * 32 * 16;              // BGZF blocks per H2D chunk = per K1 sub-launch = per sub-batch: 6656 blocks = 16 K1 CTAs, ~260 MB compressed
     // ---- shard (resolved lazily)
@@ -596,6 +597,7 @@ int run_pipeline(bdepth* h, RunMode mode, RunOut* ro, Emitter* em = nullptr) {
         if (need > h->counts.cap && need > free_b + h->counts.cap) return fail(h, BDEPTH_ERR_CUDA, "counter window needs %zu bytes of HBM, %zu free", need, free_b);
         CK(h->counts.ensure(need));
         CK(cudaMemsetAsync(h->counts.p, 0, need, sm));
+        if (h->want_presence) { CK(h->present.ensure((h->win_len / 32 + 2) * 4)); CK(cudaMemsetAsync(h->present.p, 0, (h->win_len / 32 + 2) * 4, sm)); }
         CK(h->ref_has.ensure((nref / 32 + 2) * 4)); CK(cudaMemsetAsync(h->ref_has.p, 0, (nref / 32 + 2) * 4, sm));
     }
     CK(h->scan_stats.ensure(sizeof(ScanStats)));
@@ -940,6 +942,7 @@ int run_pipeline(bdepth* h, RunMode mode, RunOut* ro, Emitter* em = nullptr) {
             CK(h->tile_first.ensure((n_tiles + 2) * 4)); CK(h->tile_lo.ensure((n_tiles + 2) * 4));
             BD_LAUNCH((unsigned)((n_tiles + 2 + 255) / 256), 256, 0, sm, k_fill_u32)(h->tile_first.as<uint32_t>(), (uint32_t)R, n_tiles + 2);
             CK(cudaMemsetAsync(h->tile_lo.p, 0xFF, (n_tiles + 2) * 4, sm));
+            if (h->want_presence) { BD_LAUNCH((unsigned)((R + 255) / 256), 256, 0, sm, k_presence)(soa, (uint32_t)R, h->cnt_base, h->win_len, h->present.as<uint32_t>()); st.gpu_launches++; }
             BD_LAUNCH((unsigned)((R + 255) / 256), 256, 0, sm, k3_tile_index)(soa, (uint32_t)R, tiles_base, (uint32_t)n_tiles, h->tile_first.as<uint32_t>(), h->tile_lo.as<uint32_t>());
             CK(cudaGetLastError()); st.gpu_launches += 2;
             for (uint32_t si = 0; si < h->S; si++) {      // one counter set per sample (one pass when combined / single sample)
@@ -1104,7 +1107,7 @@ void bdepth_close(bdepth_t* h) {
     DevBuf* bufs[] = {&h->comp, &h->descs, &h->status, &h->ubuf, &h->chunk_start, &h->entry, &h->exitb, &h->count, &h->slot_base, &h->slots, &h->rec_base, &h->walk_list, &h->soa_start, &h->soa_span, &h->soa_meta, &h->soa_off, &h->soa_ncl, &h->soa_lseq, &h->long_list, &h->tile_first, &h->tile_lo, &h->counts, &h->ref_len_d, &h->ref_lin0_d, &h->scan_stats, &h->ref_has, &h->misc};
     for (DevBuf* b : bufs) b->release();
     h->rg_ids.release(); h->rg_offs.release(); h->rg_samp.release();
-    h->text[0].release(); h->text[1].release(); h->text_tiles.release(); h->text_offs.release(); h->text_zero.release(); h->text_samp.release();
+    h->text[0].release(); h->text[1].release(); h->text_tiles.release(); h->text_offs.release(); h->text_zero.release(); h->text_samp.release(); h->present.release();
     h->seg.s.release(); h->seg.e.release(); h->seg.pmax.release(); h->seg.id.release(); h->seg.reads.release(); h->seg.minstart.release(); h->seg.bases_reads.release(); h->seg.mbases.release(); h->seg.ustart.release();
     h->m_hash.release(); h->m_flag.release(); h->m_flt.release(); h->m_ctl.release(); h->fprog_d.release();
     if (h->comm) { nccl().CommDestroy(h->comm); h->comm = nullptr; }
@@ -1266,8 +1269,12 @@ int bdepth_run_base(bdepth_t* h, bdepth_tile_cb cb, void* user) {
 // ---- base mode with GPU-side text
 int bdepth_run_base_text(bdepth_t* h, const bdepth_text_opts* o, bdepth_text_cb cb, void* user) {
     if (!o) return fail(h, BDEPTH_ERR_ARG, "null options");
-    int rc = run_pipeline(h, RUN_FULL, nullptr); if (rc) return rc;
+    // a position that reads cover but whose every base fails -q still has a column: with -a and a positive minimum coverage
+    // the reference prints it (flag n); the counters cannot tell it from an empty position, a bitmap can (one rank only)
+    h->want_presence = o->annotate && h->minq > 0 && o->min_cov > 0 && h->world == 1;
+    int rc = run_pipeline(h, RUN_FULL, nullptr); h->want_presence = false; if (rc) return rc;
     const bool ms = h->S > 1;             // one row per sample and position (k_text_len_ms / k_text_write_ms)
+    const bool presence = o->annotate && h->minq > 0 && o->min_cov > 0 && h->world == 1;
     cudaStream_t sm = h->s_main;
     cudaEvent_t e0 = h->ev[5], e1 = h->ev[6];
     CK(cudaEventRecord(e0, sm));
@@ -1336,6 +1343,7 @@ int bdepth_run_base_text(bdepth_t* h, const bdepth_text_opts* o, bdepth_text_cb 
         if (nm.size() > 255) return fail(h, BDEPTH_ERR_ARG, "reference name too long");
         tp.name_len = (uint32_t)nm.size(); memcpy(tp.name, nm.data(), nm.size());
         tpm.name_len = tp.name_len; memcpy(tpm.name, nm.data(), nm.size()); tpm.sample_stride = p.in_window ? (uint64_t)N_PLANES * h->win_len : 0;
+        tp.present = tpm.present = (presence && p.in_window) ? h->present.as<uint32_t>() : nullptr;      // indexed like the counters (idx0 is window-relative)
         uint32_t n = (uint32_t)(p.b - p.a), n_tiles = (n + TEXT_TILE - 1) / TEXT_TILE, pos0 = (uint32_t)(p.a - h->hdr.ref_lin0[p.ref]);
         const uint32_t* cnt = p.in_window ? h->counts.as<uint32_t>() : h->text_zero.as<uint32_t>();
         uint64_t wl = p.in_window ? h->win_len : 0, idx0 = p.in_window ? p.a - h->cnt_base : 0;

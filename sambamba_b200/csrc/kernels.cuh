@@ -658,7 +658,25 @@ struct TextParams {
     int annotate, with_sample;
     uint32_t name_len, sample_len;
     char name[256], sample[256];
+    const uint32_t* present;      // optional bitmap (window-relative): a read covers the position even if -q left no counted base (k_presence)
 };
+// With -a, -q and a positive minimum coverage the reference still prints a row (flag n) for a position that reads cover but
+// whose every base fails -q: the column exists, its counters are zero (depth.d:534-555).  The counters alone cannot tell
+// that from "no read here", so such runs also mark the covered positions: one bit per position, thread per passing read.
+__global__ void k_presence(RecordSoA soa, uint32_t R, uint64_t cnt_base, uint64_t win_len, uint32_t* __restrict__ present) {
+    uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R || !(soa.meta[r] & 1u)) return;
+    uint64_t a = soa.start[r], b = a + soa.span[r];
+    if (a < cnt_base) a = cnt_base;
+    if (b > cnt_base + win_len) b = cnt_base + win_len;
+    if (a >= b) return;
+    a -= cnt_base; b -= cnt_base;
+    for (uint64_t w = a >> 5; w <= (b - 1) >> 5; w++) {
+        uint32_t lo = w == (a >> 5) ? (uint32_t)(a & 31) : 0u, hi = w == ((b - 1) >> 5) ? (uint32_t)((b - 1) & 31) : 31u;
+        uint32_t m = (hi == 31 ? 0xFFFFFFFFu : ((1u << (hi + 1)) - 1u)) & ~((1u << lo) - 1u);
+        atomicOr(&present[w], m);
+    }
+}
 __device__ __forceinline__ uint32_t dec_digits(uint32_t v) {
     return v < 10u ? 1u : v < 100u ? 2u : v < 1000u ? 3u : v < 10000u ? 4u : v < 100000u ? 5u : v < 1000000u ? 6u : v < 10000000u ? 7u : v < 100000000u ? 8u : v < 1000000000u ? 9u : 10u;
 }
@@ -675,7 +693,7 @@ __device__ __forceinline__ uint32_t text_row(const TextParams& tp, const uint32_
     bool ok = (double)total >= tp.min_cov && (double)total <= tp.max_cov;
     *okp = ok;
     if (!ok && !tp.annotate) return 0;
-    if (total == 0 && tp.min_cov > 0) return 0;          // no column at all: nothing is written when min_cov > 0 (depth.d:568-572)
+    if (total == 0 && tp.min_cov > 0 && !(tp.present && tp.annotate && ((tp.present[idx >> 5] >> (idx & 31)) & 1u))) return 0;          // no column at all: nothing is written when min_cov > 0 (depth.d:568-572)
     uint32_t len = tp.name_len + 1 + dec_digits(pos) + 1 + dec_digits(total);
     len += 1 + dec_digits(v[0]) + 1 + dec_digits(v[1]) + 1 + dec_digits(v[2]) + 1 + dec_digits(v[3]) + 1 + dec_digits(v[5]) + 1 + dec_digits(v[6]);
     if (tp.with_sample) len += 1 + tp.sample_len;
@@ -742,11 +760,13 @@ struct TextParamsMS {
     double min_cov, max_cov; int annotate; uint32_t name_len; char name[256];
     uint32_t S; const char* samp; const uint32_t* samp_off;      // sample names concatenated, S + 1 offsets
     uint64_t sample_stride;                                       // elements between the counter sets of two samples (0: all read the same planes)
+    const uint32_t* present;                                      // as in TextParams
 };
 // length of the rows of one position; writes them when p != nullptr
 __device__ __forceinline__ uint32_t text_rows_ms(const TextParamsMS& tp, const uint32_t* __restrict__ counts, uint64_t win_len, uint64_t idx, uint32_t pos, char* p) {
     uint32_t any = 0;
     for (uint32_t s = 0; s < tp.S; s++) for (int pl = 0; pl < N_PLANES; pl++) any |= counts[(uint64_t)s * tp.sample_stride + (uint64_t)pl * win_len + idx];
+    if (!any && tp.present && ((tp.present[idx >> 5] >> (idx & 31)) & 1u)) any = 1;      // the column exists although -q left nothing to count
     if (!any && tp.min_cov > 0) return 0;
     uint32_t len = 0;
     for (uint32_t s = 0; s < tp.S; s++) {

@@ -96,3 +96,17 @@ def test_errors_and_usage(tiny):
     assert rc == 1 and err.startswith(b"sambamba-depth: ")
     rc, out, err = helpers.run_cli(["window", p])
     assert rc == 1 and b"positive window size must be specified" in err
+
+
+def test_annotated_rows_of_positions_whose_bases_all_fail_q(tiny, tmp_path):
+    """-a with -q and a positive minimum coverage: a position that reads cover but whose every base is below -q still has a
+    column; the reference prints it with flag n (depth.d:534-555).  The counters are zero there: a presence bitmap
+    (k_presence) tells it from a position without reads."""
+    p, _, sbed = tiny
+    for args in (["base", "-a", "-q", "38", "-c", "1", p], ["base", "-a", "-q", "41", "-c", "3", "-L", "ctgA:1-3000", p], ["base", "-a", "-q", "39", "-c", "2", "--combined", p],
+                 ["base", "-a", "-q", "40", "-c", "1", "-L", sbed, p]):
+        out, _ = check_same(args)
+        assert b"\t0\t0\t0\t0\t0\t0\t0\t" in out          # rows with COV 0 are there
+    import test_emul_mates as tem
+    ms = tem.make_pairs_bam(str(tmp_path / "ms.bam"), 3, rg=[("g1", "S1"), ("g2", "S2")])
+    check_same(["base", "-a", "-q", "38", "-c", "2", ms])
