@@ -481,7 +481,7 @@ int exchange_boundaries(bdepth* h, uint64_t shard_min, uint64_t shard_max) {
 // regions, no usable index, several ranks, input staged as a whole) or would not save anything.
 static bool plan_sparse(bdepth* h) {
     h->sparse_on = false;
-    if (h->regions.empty() || !h->sparse_ok || h->world != 1 || h->staged || !h->bai.valid || h->bai.bins.size() != h->hdr.ref_len.size()) return false;
+    if (h->regions.empty() || !h->sparse_ok || (h->world != 1 && h->fix_mates) || h->staged || !h->bai.valid || h->bai.bins.size() != h->hdr.ref_len.size()) return false;
     const auto& P = h->blocks; if (P.empty()) return false;          // the framed prefix of the file: at least the header's members
     uint64_t vo_first;
     {   // a credible index starts where the records start (a dummy or foreign .bai is accepted by the reference, which only
@@ -530,6 +530,11 @@ static bool plan_sparse(bdepth* h) {
     }
     uint64_t sel_bytes = 0; size_t nsel = 0; for (auto& sg : segs) for (size_t k = sg.b0; k <= sg.b1; k++) { sel_bytes += L[k].bsize; nsel++; }
     if (sel_bytes * 10 > (uint64_t)h->file_len * 9) return false;      // nearly the whole file: the plain path is simpler
+    if (h->world > 1) {      // several ranks: consecutive segments (each begins and ends at a record) by compressed bytes; file order = coordinate order, so
+        std::vector<Seg> mine; uint64_t cum = 0;                        // the ranks' reads still lie in consecutive coordinate ranges and the boundary exchange applies as it is
+        for (auto& sg : segs) { uint64_t bytes = 0; for (size_t k = sg.b0; k <= sg.b1; k++) bytes += L[k].bsize; int owner = sel_bytes ? (int)std::min<uint64_t>((uint64_t)h->world - 1, (cum + bytes / 2) * (uint64_t)h->world / sel_bytes) : 0; if (owner == h->rank) mine.push_back(sg); cum += bytes; }
+        segs.swap(mine); nsel = 0; for (auto& sg : segs) nsel += sg.b1 - sg.b0 + 1;
+    }
     h->vblocks.clear(); h->seg_entry.clear(); h->seg_limit.clear();
     h->vblocks.reserve(nsel); h->seg_entry.reserve(nsel); h->seg_limit.reserve(nsel);
     uint64_t vu = 0;
