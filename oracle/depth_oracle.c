@@ -508,7 +508,7 @@ static int src_next(ReadSrc *s, PRead *out) {
     const Bgzf *z = &s->b->z;
     while (s->off + 4 <= z->ulen) {
         uint32_t bs = rd32(z->u + s->off);
-        if (s->off + 4 + (size_t)bs > z->ulen) break;      /* truncated tail: stop like a short read */
+        if (s->off + 4 + (size_t)bs > z->ulen) { fail("not enough data in stream"); s->err = 1; return 0; }   /* the stream ends inside a record: readExact throws, readrange.d:169 (fewer than 4 stray bytes end it quietly, :139-149) */
         const uint8_t *rec = z->u + s->off + 4; s->off += 4 + (size_t)bs;
         PRead r; if (parse_record(s->b, rec, bs, &r)) { s->err = 1; return 0; }
         if (s->sel) {

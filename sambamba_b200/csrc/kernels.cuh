@@ -212,6 +212,7 @@ struct ScanStats {      // device-side accumulators
     unsigned long long n_pass, n_cigar, seq_bytes, max_end, min_start, n_long, max_start, rg_err;   // rg_err: 1 + index of the first read with an unknown RG
     unsigned long long n_ghost;     // -m: records before the batch's own ones (re-read from the previous batch / the previous rank's zone), k2_decode<.., true>
     unsigned long long n_ghost_right;   // -m on several ranks: records at or after the shard limit (the next rank's zone)
+    unsigned long long bad_rec;     // 1 + index of the first record whose name + CIGAR + sequence + qualities do not fit its block_size (~0: none)
 };
 constexpr uint32_t NCL_GHOST = 1u << 31;      // RecordSoA.ncl: a record that is only re-read for the mate kernels and passes the filter (its pass bit is clear)
 constexpr uint32_t NCL_FOREIGN = 1u << 30;    // ... and belongs to another rank's shard (-m on several ranks: the zones left and right of the shard)
@@ -286,6 +287,12 @@ __global__ void k2_decode(ScanParams sp, const int64_t* __restrict__ chunk_start
         uint32_t l_name = bmn & 0xFF, mapq = (bmn >> 8) & 0xFF, flag = fnc >> 16, n_cigar = fnc & 0xFFFF;
         const uint8_t* cg = p + 32 + l_name;
         uint64_t span = 0;
+        {   // a record whose fields overrun its block_size (corrupt file) must not send anybody reading past it: the reference
+            // slices without bounds checks there (release build), this engine refuses the file (bdepth.cu reports bad_rec)
+            const uint32_t bs = __funnelshift_r(__ldg(pw - 1), h0, psh);
+            const uint64_t need = 32ull + l_name + 4ull * n_cigar + (l_seq > 0 ? ((uint64_t)(uint32_t)l_seq + 1) / 2 + (uint32_t)l_seq : 0ull);
+            if (l_seq < 0 || need > bs) { atomicMin(&st->bad_rec, (unsigned long long)(rb + k) + 1); n_cigar = 0; l_seq = 0; ref = -1; }
+        }
         for (uint32_t i = 0; i < n_cigar; i++) { uint32_t c = ldu32(cg + 4 * i); if (cig_rcons(c & 15)) span += c >> 4; }
         bool placed = ref >= 0 && ref < sp.n_ref && pos >= 0;
         bool pass = placed && !(flag & 4u) && span > 0;

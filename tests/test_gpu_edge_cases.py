@@ -187,3 +187,59 @@ def test_overlapping_windows_first_reference_without_reads(tmp_path):
     p2 = helpers.write_bam(str(tmp_path / "w0.bam"), [("e0", 3000), ("c1", 5000), ("c2", 5000), ("e3", 2500)], reads0 + reads)
     for args in (["window", "-w", "400", "--overlap", "100", "-T", "3", p2], ["window", "-w", "330", "--overlap", "300", "-T", "2", "-q", "15", p2]):
         cli_same(args)
+
+
+@pytest.mark.xfail(strict=False, reason="first hardware run pending (passes under the CPU emulation)")
+def test_corrupt_and_truncated_files_are_refused(tmp_path):
+    """Malformed input must end in an error message, never in a hang, a fault or quietly shortened output: a truncated last
+    record (readExact throws in the reference, readrange.d:169), a damaged DEFLATE stream (zlib error, block.d:127-216), a
+    record whose fields overrun its block_size (the release build of the reference slices past it unchecked; this engine
+    refuses), a cut file.  Each case runs in its own process (the CLI), so a device fault could not hide behind a later test."""
+    import struct
+    import numpy as np
+    src = helpers.gen_bam(str(tmp_path / "src.bam"), "-r", "chrA:100000", "-r", "chrC:50000", "-n", 8000, "-s", 3, "-t", 2)
+    u = helpers.oracle_inflate(src)
+    first, _ = helpers.header_first_record_offset(u)
+    recs = helpers.parse_records(u, first)
+    o = recs[len(recs) // 2][0]
+    body = bytearray(u.tobytes())
+
+    def body_with(fn):
+        v = bytearray(body)
+        fn(v)
+        return helpers.write_bgzf(str(tmp_path / "c.bam"), bytes(v), 2)
+
+    cases = [
+        ("block_size 0", lambda v: struct.pack_into("<i", v, o, 0)),
+        ("block_size beyond the file", lambda v: struct.pack_into("<i", v, o, 0x7FFFFFF0)),
+        ("n_cigar_op overruns the record", lambda v: struct.pack_into("<H", v, o + 16, 65535)),
+        ("l_seq overruns the record", lambda v: struct.pack_into("<i", v, o + 20, 0x7FFFFFF0)),
+        ("negative l_seq", lambda v: struct.pack_into("<i", v, o + 20, -3)),
+    ]
+    for what, fn in cases:
+        for args in (["base"], ["base", "-q", "20"], ["window", "-w", "1000"]):
+            rc, out, err = helpers.run_cli(args + [body_with(fn)])
+            assert rc != 0 and err.strip(), (what, args, rc, err[:200])
+    p = helpers.write_bgzf(str(tmp_path / "cut.bam"), bytes(body[:len(body) - 17]), 2)      # the stream ends inside the last record
+    rc, out, err = helpers.run_cli(["base", p])
+    assert rc != 0 and b"not enough data" in err, err[:200]
+    rc2, _, err2 = helpers.oracle_cli(["base", p])
+    assert rc2 != 0 and b"not enough data" in err2, err2[:200]
+    p = helpers.write_bgzf(str(tmp_path / "cut2.bam"), bytes(body[:recs[-1][0] + 2]), 2)     # two stray bytes after the last record: a quiet end (readrange.d:139-149)
+    rc, out, err = helpers.run_cli(["base", p])
+    assert rc == 0, err[:200]
+    raw = open(src, "rb").read()
+    bad = tmp_path / "deflate.bam"
+    flipped = 0
+    for pos in range(len(raw) // 2, len(raw) // 2 + 4000, 97):        # somewhere in there a flip breaks a Huffman stream
+        data = bytearray(raw)
+        data[pos] ^= 0x55
+        bad.write_bytes(bytes(data))
+        rc, out, err = helpers.run_cli(["base", str(bad)])
+        assert rc == 0 or err.strip(), (pos, rc)
+        flipped += rc != 0
+    assert flipped, "no flip was detected"
+    for cut in (len(raw) // 2, 100, 10):
+        bad.write_bytes(raw[:cut])
+        rc, out, err = helpers.run_cli(["base", str(bad)])
+        assert rc != 0 and err.strip(), (cut, rc)
