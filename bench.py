@@ -140,6 +140,8 @@ def cpu_baseline(path, threads, sample_bytes):
     t0 = time.time()
     r = subprocess.run(cmd, capture_output=True, text=True)
     dt = time.time() - t0
+    if r.returncode != 0:
+        raise RuntimeError(f"the CPU baseline failed (exit {r.returncode}): {r.stderr[-300:]}")
     st = {}
     for line in r.stderr.splitlines():
         if line.startswith("{"):

@@ -142,3 +142,21 @@ def test_region_chunk_plan_covers_every_overlapping_record(tmp_path):
             assert k >= 0 and chunks[k][0] <= vo < chunks[k][1], (q, r)
     small = sb.plan_region_chunks(p, [(0, 1000, 1200)])
     assert sum((e >> 16) - (b >> 16) for b, e in small) < 0.05 * (total_span >> 16)
+
+
+def test_bench_reference_arm_prints_its_line(tmp_path):
+    """`bench.py --impl reference` (the CPU arm the driver times beside the GPU one) on a small workload: one JSON line with
+    the contract's keys, measured on a bounded sample that ends mid-stream (the oracle tolerates the cut only there)."""
+    import json
+    import subprocess
+    import sys
+    env = dict(os.environ, BDEPTH_BENCH_DIR=str(tmp_path))
+    r = subprocess.run([sys.executable, os.path.join(helpers.ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                        "--reads-per-unit", "60000", "--cpu-sample-mb", "2"], capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0, r.stderr[-400:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["value"] > 0 and line["unit"] == "GB/s" and line["gpu_launches"] == 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1 and "covered positions" in line["cpu_baseline"]["sample"]
+    assert line["e2e"] == {"value": line["value"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    sample_mb = float(line["cpu_baseline"]["sample"].split()[1])
+    assert 0 < sample_mb <= 2.2, line["cpu_baseline"]["sample"]
