@@ -22,6 +22,7 @@ import argparse
 import ctypes as C
 import json
 import os
+import shutil
 import subprocess
 import sys
 import threading
@@ -33,7 +34,28 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 READS_PER_UNIT = 12888833
 UNIT_LEN = 64444167
-NCU_TRAFFIC_BYTES_PER_LAUNCH = 50975621000  # dram__bytes_read.sum + dram__bytes_write.sum of k1_inflate on this workload (profiles/r1_k1_v8_two_literal_ncu_full_summary.txt)
+
+
+def ncu_traffic(kernel_key):
+    """roofline.traffic = dram__bytes_read.sum + dram__bytes_write.sum per launch of the kernel, parsed from the ncu
+    summary profiles/CURRENT.json names for it (the capture of the shipped build; tools/ncu_summary.py wrote it)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "CURRENT.json")) as f:
+            ent = json.load(f)[kernel_key]
+        tot, inside = 0.0, False
+        with open(os.path.join(ROOT, ent["summary"])) as f:
+            for line in f:
+                if line.startswith("== kernel:"):
+                    inside = ent["kernel_match"] in line
+                elif inside and ("dram__bytes_read.sum" in line or "dram__bytes_write.sum" in line):
+                    unit = line.split("[")[1].split("]")[0].lower()
+                    v = float(line.rsplit("=", 1)[1].replace(",", ""))
+                    tot += v * {"gbyte": 1e9, "mbyte": 1e6, "kbyte": 1e3, "byte": 1.0, "tbyte": 1e12}[unit]
+                elif inside and line.startswith("== hottest"):
+                    break
+        return (int(tot) if tot else None), ent["summary"]
+    except Exception as e:                                    # no capture of this build yet: say so instead of quoting a stale one
+        return None, f"none ({type(e).__name__})"
 
 
 def peaks():
@@ -50,9 +72,9 @@ def workload_path(n_units, reads_per_unit):
     return os.path.join(d, f"synth_chr20x{n_units}_{reads_per_unit}.bam")
 
 
-def ensure_workload(n_units, reads_per_unit):
+def ensure_workload(n_units, reads_per_unit, load=True):
     import __graft_entry__ as g
-    g.build(quiet=True)
+    g.build(quiet=True, load=load)          # load=False (reference arm): the product library is never mapped into that process
     path = workload_path(n_units, reads_per_unit)
     if os.path.exists(path) and os.path.exists(path + ".bai"):
         return path
@@ -136,7 +158,7 @@ def cpu_baseline(path, threads, sample_bytes):
     column sweep and per-base printer), on a bounded prefix of the same BAM.  kind = "port": the reference is D
     and cannot be compiled in this image."""
     exe = os.path.join(ROOT, "oracle", "_build", "depth_oracle")
-    cmd = [exe, "--inflate-threads", str(threads), "--max-file-bytes", str(sample_bytes), "--stats", "depth", "base", path, "-o", "/dev/null"]
+    cmd = [exe, "--inflate-threads", str(threads)] + (["--max-file-bytes", str(sample_bytes)] if sample_bytes else []) + ["--stats", "depth", "base", path, "-o", "/dev/null"]
     t0 = time.time()
     r = subprocess.run(cmd, capture_output=True, text=True)
     dt = time.time() - t0
@@ -146,10 +168,66 @@ def cpu_baseline(path, threads, sample_bytes):
     for line in r.stderr.splitlines():
         if line.startswith("{"):
             st = json.loads(line)
-    nbytes = st.get("file_bytes", sample_bytes)
+    nbytes = st.get("file_bytes", sample_bytes or os.path.getsize(path))
     return {"value": nbytes / 1e9 / dt, "unit": "GB/s", "cores": threads, "kind": "port",
-            "sample": f"first {nbytes / 1e6:.0f} MB of the BAM ({st.get('columns', 0)} covered positions): inflate {st.get('t_inflate', 0):.2f} s on {threads} threads + serial pileup sweep/print {st.get('t_sweep', 0):.2f} s; wall {dt:.2f} s",
+            "sample": f"{'first ' if sample_bytes else 'all '}{nbytes / 1e6:.0f} MB of the BAM ({st.get('columns', 0)} covered positions): inflate {st.get('t_inflate', 0):.2f} s on {threads} threads + serial pileup sweep/print {st.get('t_sweep', 0):.2f} s; wall {dt:.2f} s",
             "covered_mbases_per_s": st.get("columns", 0) / 1e6 / dt}, dt, nbytes, st
+
+
+CK_A, CK_B = 0x9E3779B97F4A7C15, 0xC2B2AE3D27D4EB4F
+
+
+def plane_checksums(planes, lin_start):
+    """Order-sensitive checksum of a [7, n] block of counters whose first column is linear position lin_start: the sum over
+    planes p and positions g of count * ((g * CK_A + (p + 1) * CK_B) | 1) modulo 2^64, the plain sum, and the number of
+    covered positions.  All three add over disjoint tiles, so ranks (and tiles) can be summed in any order."""
+    import numpy as np
+    n = planes.shape[1]
+    g = np.arange(lin_start, lin_start + n, dtype=np.uint64) * np.uint64(CK_A)
+    ck, tot = 0, 0
+    with np.errstate(over="ignore"):
+        for p in range(7):
+            c = planes[p].astype(np.uint64)
+            w = (g + np.uint64(((p + 1) * CK_B) & 0xFFFFFFFFFFFFFFFF)) | np.uint64(1)
+            ck = (ck + int((c * w).sum(dtype=np.uint64))) & 0xFFFFFFFFFFFFFFFF
+            tot += int(c.sum(dtype=np.uint64))
+    covered = int(np.count_nonzero(planes.sum(axis=0, dtype=np.uint64)))
+    return ck, tot, covered
+
+
+def checksum_run(h, lin0):
+    """One more (untimed) bdepth_run_base whose tile callback folds every delivered tile into the checksums."""
+    import numpy as np
+    import sambamba_b200._lib as L
+    acc = [0, 0, 0, 0]
+
+    def cb(_user, tp):
+        t = tp.contents
+        src = np.ctypeslib.as_array(t.counts, shape=(6 * t.stride + t.len,))
+        planes = np.stack([src[p * t.stride:p * t.stride + t.len] for p in range(7)])
+        ck, tot, cov = plane_checksums(planes, int(lin0[t.ref_id]) + t.start)
+        acc[0] = (acc[0] + ck) & 0xFFFFFFFFFFFFFFFF
+        acc[1] += tot
+        acc[2] += cov
+        acc[3] += t.len
+        return 0
+    h._ck(h.L.bdepth_run_base(h.h, L.TILE_CB(cb), None))
+    return acc
+
+
+def oracle_checksums(path, threads):
+    """The same three numbers from the CPU oracle's closed-form counters over the whole genome (test infrastructure; the
+    only use of oracle/ in our arm is this check AFTER the timed region)."""
+    import helpers
+    want, st = helpers.oracle_counts(path, threads=threads)
+    ck = tot = cov = 0
+    step = 1 << 24
+    for a0 in range(0, want.shape[1], step):
+        c, t, v = plane_checksums(want[:, a0:a0 + step], a0)
+        ck = (ck + c) & 0xFFFFFFFFFFFFFFFF
+        tot += t
+        cov += v
+    return [ck, tot, cov, want.shape[1]], st
 
 
 def main():
@@ -161,6 +239,8 @@ def main():
     ap.add_argument("--reads-per-unit", type=int, default=READS_PER_UNIT, help="smaller values are for smoke tests only")
     ap.add_argument("--cpu-sample-mb", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-full-file", action="store_true", help="reference arm: skip the one whole-file run of the port")
+    ap.add_argument("--no-verify", action="store_true", help="development only: skip the bit-exact check of the counters after the timed region")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -175,16 +255,35 @@ def main():
     if a.impl == "reference":
         if rank != 0:
             return 0
-        path = ensure_workload(n_units, a.reads_per_unit)
+        path = ensure_workload(n_units, a.reads_per_unit, load=False)
         threads = os.cpu_count() or 1
+        probe = {"sambamba": shutil.which(os.environ.get("BDEPTH_SAMBAMBA", "sambamba")), "ldc2": shutil.which("ldc2")}
         times, nb = [], 0
-        for i in range(a.warmup + a.steps):
-            cb, dt, nb, st = cpu_baseline(path, threads, a.cpu_sample_mb << 20)
-            if i >= a.warmup:
-                times.append(dt)
-        dt = sum(times) / len(times)
+        if probe["sambamba"]:
+            # the real thing: `sambamba depth base -t $(nproc)` over the whole file; without -t it is serial (depth.d:1081,1154)
+            nb = os.path.getsize(path)
+            for i in range(a.warmup + a.steps):
+                t0 = time.time()
+                r = subprocess.run([probe["sambamba"], "depth", "base", "-t", str(threads), path, "-o", "/dev/null"], capture_output=True, text=True)
+                if r.returncode != 0:
+                    raise RuntimeError(f"sambamba failed (exit {r.returncode}): {r.stderr[-300:]}")
+                if i >= a.warmup:
+                    times.append(time.time() - t0)
+            dt = sum(times) / len(times)
+            cb = {"value": nb / 1e9 / dt, "unit": "GB/s", "cores": threads, "kind": "sambamba", "sample": f"whole file ({nb / 1e6:.0f} MB), {probe['sambamba']} depth base -t {threads}"}
+        else:
+            for i in range(a.warmup + a.steps):
+                cb, dt, nb, st = cpu_baseline(path, threads, a.cpu_sample_mb << 20)
+                if i >= a.warmup:
+                    times.append(dt)
+            dt = sum(times) / len(times)
+            if n_units == 1 and not a.no_full_file:
+                # the bounded sample is a prefix; time the port over the WHOLE file once as well, so that the per-step number is not an extrapolation
+                full, fdt, fnb, fst = cpu_baseline(path, threads, 0)
+                cb["full_file"] = {"value": fnb / 1e9 / fdt, "unit": "GB/s", "seconds": fdt, "bytes": fnb, "covered_positions": fst.get("columns", 0)}
         v = nb / 1e9 / dt
         cb["value"] = v
+        cb["probe"] = probe
         print(json.dumps({"impl": "reference", "metric": "bam_gb_per_s_depth_base", "value": v, "unit": "GB/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
                           "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
                           "config": config, "cpu_baseline": cb, "e2e": {"value": v, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -318,6 +417,24 @@ def main():
                 tbytes = box["n"]
         text = {"ms_per_step": 1e3 * sum(tt) / len(tt), "text_bytes": tbytes, "text_gb_per_s": tbytes / 1e9 / (sum(tt) / len(tt)), "bam_gb_per_s": file_bytes / 1e9 / (sum(tt) / len(tt)),
                 "path": "bdepth_run_base_text: H2D + kernels + k_text_len/scan/write + D2H of the row text (default `depth base`, min coverage 1)"}
+    # ---- verification AFTER the timed regions: the counters this very session delivers (every rank's owned tiles) against the
+    # CPU oracle over the whole input -- order-sensitive checksum, total count, covered positions, positions delivered
+    verify = None
+    if not a.no_verify:
+        lin0 = np.concatenate([[0], np.cumsum([l for _, l in h.refs])]).astype(np.int64)
+        mine = checksum_run(h, lin0)
+        if dist is not None:
+            allv = [None] * world
+            dist.all_gather_object(allv, mine)
+        else:
+            allv = [mine]
+        if rank == 0:
+            got = [sum(v[0] for v in allv) & 0xFFFFFFFFFFFFFFFF, sum(v[1] for v in allv), sum(v[2] for v in allv), sum(v[3] for v in allv)]
+            t0 = time.perf_counter()
+            want, ost = oracle_checksums(path, min(64, os.cpu_count() or 8))
+            verify = {"ok": got == want and got[2] == int(covered), "checksum": f"{got[0]:016x}", "oracle_checksum": f"{want[0]:016x}", "counts_total": got[1], "oracle_counts_total": want[1],
+                      "covered_positions": got[2], "oracle_covered_positions": want[2], "positions_delivered": got[3], "oracle_seconds": time.perf_counter() - t0,
+                      "what": "sum over planes p, positions g of count*((g*A+(p+1)*B)|1) mod 2^64 over every rank's delivered tiles vs the CPU oracle's closed-form counters of the whole file"}
     h.close()
     e2e_s = sum(e2e_t) / len(e2e_t)
     h2d_total = file_bytes
@@ -328,6 +445,7 @@ def main():
             dist.destroy_process_group()
         return 0
     peak, peak_src = peaks()
+    traffic, traffic_src = ncu_traffic("roofline")
     value = file_bytes / 1e9 / (ms_step / 1e3)
     out = {
         "metric": "bam_gb_per_s_depth_base", "value": value, "unit": "GB/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
@@ -343,10 +461,11 @@ def main():
         "text_rows": text,
         "gpu_launches": int(total_launches),
         "roofline": {"kernel": "k1_inflate (lane-per-BGZF-block DEFLATE)", "bound": "hbm", "achieved": k1_bytes / 1e9 / (k1_ms / 1e3), "peak": peak, "unit": "GB/s",
-                     "frac": k1_bytes / 1e9 / (k1_ms / 1e3) / peak, "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH if (a.gpus == 1 and a.reads_per_unit == READS_PER_UNIT) else None,
+                     "frac": k1_bytes / 1e9 / (k1_ms / 1e3) / peak, "traffic": traffic if (a.gpus == 1 and a.reads_per_unit == READS_PER_UNIT) else None, "traffic_source": traffic_src,
                      "algorithmic_bytes_per_launch": int(k1_bytes / max(1, k1_launches_per_step)), "launches_per_step": k1_launches_per_step,
                      "peak_source": peak_src, "note": "C + U per launch (SURVEY 8d) / CUDA-event duration of the launch on the library stream; DEFLATE decoding is instruction-latency bound, not HBM bound"},
         "clocks": clocks,
+        "verified": (verify["ok"] if verify else None), "verification": verify,
     }
     if not a.no_cpu_baseline:
         cb, _, _, _ = cpu_baseline(path, os.cpu_count() or 1, a.cpu_sample_mb << 20)
@@ -354,6 +473,9 @@ def main():
     print(json.dumps(out))
     if dist is not None:
         dist.destroy_process_group()
+    if verify is not None and not verify["ok"]:
+        sys.stderr.write("bench.py: VERIFICATION FAILED: the counters differ from the CPU oracle's\n")
+        return 3
     return 0
 
 

@@ -31,6 +31,7 @@
 #include <stdarg.h>
 #include <math.h>
 #include <pthread.h>
+#include <stdatomic.h>
 #include <zlib.h>
 
 /* ------------------------------------------------------------------ utils */
@@ -1075,6 +1076,38 @@ error:
  */
 typedef struct { uint64_t n_records, n_pass, n_blocks, ulen, clen, covered, min_lin, max_lin; double t_inflate, t_scan; } ScatterStats;
 
+/* One passing read of the closed form: scatter its CIGAR into the window (the body of the per-read loop; the record
+ * walk that finds the reads is serial, the scatter runs on worker threads with relaxed atomic increments). */
+typedef struct { const uint8_t *rec; uint64_t base, rlen; } ScatterRead;
+typedef struct { const ScatterRead *rd; size_t n; _Atomic size_t *next; uint32_t *counts; uint64_t win_a, L; int min_bq; int atomic; } ScatterJob;
+static void scatter_one(const ScatterJob *j, const ScatterRead *r) {
+    const uint8_t *rec = r->rec; int32_t pos = (int32_t)rd32(rec + 4); uint32_t bmn = rd32(rec + 8), fnc = rd32(rec + 12);
+    uint32_t l_name = bmn & 0xFF, n_cigar = fnc & 0xFFFF; int32_t l_seq = (int32_t)rd32(rec + 16);
+    const uint8_t *cig = rec + 32 + l_name, *seq = cig + 4 * (size_t)n_cigar, *qual = seq + ((size_t)l_seq + 1) / 2;
+    uint64_t base = r->base, rlen = r->rlen, p = (uint64_t)(uint32_t)pos, L = j->L, win_a = j->win_a; uint32_t q = 0; uint32_t *counts = j->counts;
+    for (uint32_t i = 0; i < n_cigar; i++) {
+        uint32_t c = rd32(cig + 4 * i), len = op_len(c), op = c & 0xF;
+        if (op_match(c)) {
+            for (uint32_t k = 0; k < len; k++, p++, q++) {
+                if (p >= rlen || q >= (uint32_t)l_seq) continue;       /* clip at reference end (documented deviation for invalid input) */
+                if (qual[q] < j->min_bq) continue;
+                uint64_t g = base + p; if (g < win_a || g - win_a >= L) continue;
+                uint8_t b = seq[q >> 1]; b = (q & 1) ? (b & 0xF) : (b >> 4);
+                uint32_t *c32 = &counts[(uint64_t)NT16_TO_NT5[b] * L + (g - win_a)];
+                if (j->atomic) __atomic_fetch_add(c32, 1u, __ATOMIC_RELAXED); else ++*c32;
+            }
+        } else if (op_rcons(c)) {
+            int plane = (op == 2) ? 5 : 6;
+            for (uint32_t k = 0; k < len; k++, p++) if (p < rlen) { uint64_t g = base + p; if (g >= win_a && g - win_a < L) { uint32_t *c32 = &counts[(uint64_t)plane * L + (g - win_a)]; if (j->atomic) __atomic_fetch_add(c32, 1u, __ATOMIC_RELAXED); else ++*c32; } }
+        } else if (op_qcons(c)) q += len;
+    }
+}
+static void *scatter_worker(void *arg) {
+    ScatterJob *j = arg;
+    for (;;) { size_t a = atomic_fetch_add(j->next, 4096), b = a + 4096 < j->n ? a + 4096 : j->n; if (a >= j->n) break; for (size_t i = a; i < b; i++) scatter_one(j, &j->rd[i]); }
+    return NULL;
+}
+
 int oracle_base_counts(const char *bam_path, int mapq_gt, unsigned flag_reject, int min_bq, int nthreads, size_t max_file_bytes,
                        uint32_t *counts /* [7][win_len], may be NULL to just scan */, uint64_t win_a /* first linear position of the window */, uint64_t win_len, ScatterStats *st) {
     Bam B; memset(&B, 0, sizeof B);
@@ -1086,35 +1119,29 @@ int oracle_base_counts(const char *bam_path, int mapq_gt, unsigned flag_reject, 
     for (int i = 0; i < B.n_ref; i++) { ref_off[i] = total; total += B.refs[i].length; } ref_off[B.n_ref] = total;
     uint64_t nrec = 0, npass = 0; size_t off = B.first_rec; const uint8_t *u = B.z.u;
     uint64_t L = win_len, min_lin = UINT64_MAX, max_lin = 0;
+    ScatterRead *rd = NULL; size_t nrd = 0, cap = 0;
     while (off + 4 <= B.z.ulen) {
         uint32_t bs = rd32(u + off); if (off + 4 + (size_t)bs > B.z.ulen) break;
         const uint8_t *rec = u + off + 4; off += 4 + (size_t)bs; nrec++;
         int32_t ref_id = (int32_t)rd32(rec), pos = (int32_t)rd32(rec + 4); uint32_t bmn = rd32(rec + 8), fnc = rd32(rec + 12);
-        uint32_t l_name = bmn & 0xFF, mapq = (bmn >> 8) & 0xFF, flag = fnc >> 16, n_cigar = fnc & 0xFFFF; int32_t l_seq = (int32_t)rd32(rec + 16);
+        uint32_t l_name = bmn & 0xFF, mapq = (bmn >> 8) & 0xFF, flag = fnc >> 16, n_cigar = fnc & 0xFFFF;
         if (!((int)mapq > mapq_gt) || (flag & flag_reject) || (flag & 0x4) || ref_id < 0 || ref_id >= B.n_ref) continue;
-        const uint8_t *cig = rec + 32 + l_name, *seq = cig + 4 * (size_t)n_cigar, *qual = seq + ((size_t)l_seq + 1) / 2;
+        const uint8_t *cig = rec + 32 + l_name;
         uint64_t span = 0; for (uint32_t i = 0; i < n_cigar; i++) { uint32_t c = rd32(cig + 4 * i); if (op_rcons(c)) span += op_len(c); }
         if (!span) continue;
         npass++;
         { uint64_t g0 = ref_off[ref_id] + (uint32_t)pos, g1 = g0 + span; if (g0 < min_lin) min_lin = g0; if (g1 > max_lin) max_lin = g1; }
         if (!counts) continue;
-        uint64_t base = ref_off[ref_id], rlen = B.refs[ref_id].length; uint64_t p = (uint64_t)(uint32_t)pos; uint32_t q = 0;
-        for (uint32_t i = 0; i < n_cigar; i++) {
-            uint32_t c = rd32(cig + 4 * i), len = op_len(c), op = c & 0xF;
-            if (op_match(c)) {
-                for (uint32_t k = 0; k < len; k++, p++, q++) {
-                    if (p >= rlen || q >= (uint32_t)l_seq) continue;       /* clip at reference end (documented deviation for invalid input) */
-                    if (qual[q] < min_bq) continue;
-                    uint64_t g = base + p; if (g < win_a || g - win_a >= L) continue;
-                    uint8_t b = seq[q >> 1]; b = (q & 1) ? (b & 0xF) : (b >> 4);
-                    counts[(uint64_t)NT16_TO_NT5[b] * L + (g - win_a)]++;
-                }
-            } else if (op_rcons(c)) {
-                int plane = (op == 2) ? 5 : 6;
-                for (uint32_t k = 0; k < len; k++, p++) if (p < rlen) { uint64_t g = base + p; if (g >= win_a && g - win_a < L) counts[(uint64_t)plane * L + (g - win_a)]++; }
-            } else if (op_qcons(c)) q += len;
-        }
+        if (nrd == cap) { cap = cap ? cap * 2 : (1u << 16); rd = realloc(rd, cap * sizeof *rd); }
+        rd[nrd].rec = rec; rd[nrd].base = ref_off[ref_id]; rd[nrd].rlen = B.refs[ref_id].length; nrd++;
     }
+    if (counts && nrd) {
+        _Atomic size_t next = 0; int nt = nthreads > 1 ? nthreads : 1;
+        ScatterJob job = { rd, nrd, &next, counts, win_a, L, min_bq, nt > 1 };
+        if (nt == 1) scatter_worker(&job);
+        else { pthread_t *th = calloc(nt, sizeof *th); for (int t = 0; t < nt; t++) pthread_create(&th[t], NULL, scatter_worker, &job); for (int t = 0; t < nt; t++) pthread_join(th[t], NULL); free(th); }
+    }
+    free(rd);
     if (st) {
         st->n_records = nrec; st->n_pass = npass; st->n_blocks = B.z.n_blocks; st->ulen = B.z.ulen; st->clen = B.z.file_len; st->t_inflate = t1 - t0; st->t_scan = now_s() - t1; st->covered = 0;
         st->min_lin = min_lin; st->max_lin = max_lin;

@@ -444,7 +444,9 @@ int exchange_boundaries(bdepth* h, uint64_t shard_min, uint64_t shard_max) {
     std::vector<uint64_t> soff, roff;
     for (auto& x : sends) {   // pack the 7 planes of the slice contiguously
         uint64_t n = x.hi - x.lo; soff.push_back(off);
-        CK(cudaMemcpy2DAsync(sp + off, n * 4, h->counts.as<uint32_t>() + (x.lo - h->cnt_base), h->win_len * 4, n * 4, NP, cudaMemcpyDeviceToDevice, sm));
+        // one copy per plane: a pitched 2D copy would need a source pitch of win_len * 4 bytes, which exceeds cudaDeviceProp::memPitch
+        // (2^31 - 1) as soon as the references total more than ~536 Mbp -- and with several ranks the window is the whole genome
+        for (int pl = 0; pl < NP; pl++) CK(cudaMemcpyAsync(sp + off + (uint64_t)pl * n, h->counts.as<uint32_t>() + (uint64_t)pl * h->win_len + (x.lo - h->cnt_base), n * 4, cudaMemcpyDeviceToDevice, sm));
         off += n * NP;
     }
     for (auto& x : recvs) { roff.push_back(off); off += (x.hi - x.lo) * NP; }
@@ -640,6 +642,7 @@ int run_pipeline(bdepth* h, RunMode mode, RunOut* ro, Emitter* em = nullptr) {
 
     float ms_h2d = 0, ms_k1 = 0, ms_k2 = 0, ms_k3 = 0;
     uint64_t carry_len = 0; bool first_batch = true;
+    bool sparse_bad = false;         // a region chunk's record chain did not end at the chunk end (several ranks: decided together after the batches)
     uint64_t shard_min = UINT64_MAX, shard_max = 0;
     CK(cudaEventRecord(h->ev[10], sm));
     size_t b = blk_lo;
@@ -846,9 +849,11 @@ int run_pipeline(bdepth* h, RunMode mode, RunOut* ro, Emitter* em = nullptr) {
                 cur = ext[i];
                 if (sparse && h->seg_limit[b + i] != UINT32_MAX) {      // last block of a chunk: the chain must end exactly at the chunk end
                     if (ext[i] != (i ? cstart[i] : 0) + (int64_t)h->seg_limit[b + i]) {
-                        // the index does not describe this file (the reference only checks that one exists): plain pass instead
-                        h->sparse_ok = false; CK(cudaDeviceSynchronize());
-                        return run_pipeline(h, mode, ro, em);
+                        // the index does not describe this file (the reference only checks that one exists): plain pass instead.
+                        // On several ranks that decision has to be taken by all of them together (below, after the batches):
+                        // a rank falling back on its own would leave the union of the ranks' records no partition of the file.
+                        if (h->world == 1) { h->sparse_ok = false; CK(cudaDeviceSynchronize()); return run_pipeline(h, mode, ro, em); }
+                        sparse_bad = true; break;
                     }
                     cur = INT64_MAX / 2;                                  // nothing follows until the next chunk begins
                     continue;
@@ -859,6 +864,7 @@ int run_pipeline(bdepth* h, RunMode mode, RunOut* ro, Emitter* em = nullptr) {
                 }
             }
         }
+        if (sparse_bad) break;
         if (walk_err) return fail(h, BDEPTH_ERR_FORMAT, "corrupt BAM record chain (block_size < 32)");
         tail = cur < (int64_t)ub ? cur : (int64_t)ub;     // first byte not consumed by a complete record
         // ---- shard limit: drop records starting at/after u_limit (host trims counts; offsets are sorted)
@@ -916,7 +922,7 @@ int run_pipeline(bdepth* h, RunMode mode, RunOut* ro, Emitter* em = nullptr) {
                 CK(cudaMemcpy(hsp.data(), soa.span, n * 4, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(hm.data(), soa.meta, n * 4, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(hn.data(), soa.ncl, n * 4, cudaMemcpyDeviceToHost));
                 for (uint64_t i = 0; i < n; i++) {
                     uint64_t k = ro->scan_n + i; int32_t rid = -1, p = -1;
-                    if (hs[i] != 0xFFFFFFFFFFFFFFFEull) { size_t lo = 0, hi = nref; while (lo + 1 < hi) { size_t m = (lo + hi) / 2; if (h->hdr.ref_lin0[m] <= hs[i]) lo = m; else hi = m; } while (lo + 1 < nref && h->hdr.ref_lin0[lo + 1] <= hs[i] && h->hdr.ref_len[lo] == 0) lo++; rid = (int32_t)lo; p = (int32_t)(hs[i] - h->hdr.ref_lin0[lo]); }
+                    if (hs[i] != START_UNPLACED) { size_t lo = 0, hi = nref; while (lo + 1 < hi) { size_t m = (lo + hi) / 2; if (h->hdr.ref_lin0[m] <= hs[i]) lo = m; else hi = m; } while (lo + 1 < nref && h->hdr.ref_lin0[lo + 1] <= hs[i] && h->hdr.ref_len[lo] == 0) lo++; rid = (int32_t)lo; p = (int32_t)(hs[i] - h->hdr.ref_lin0[lo]); }
                     if (ro->ref_id) ro->ref_id[k] = rid; if (ro->pos) ro->pos[k] = p; if (ro->span) ro->span[k] = hsp[i];
                     if (ro->flag) ro->flag[k] = (uint16_t)(hm[i] >> 16); if (ro->mapq) ro->mapq[k] = (uint8_t)(hm[i] >> 8); if (ro->n_cigar) ro->n_cigar[k] = (uint16_t)(hn[i] >> 8);
                     if (ro->rec_off) ro->rec_off[k] = batch_u0 + ho[i] - 4;       // absolute offset of the block_size field
@@ -1030,8 +1036,19 @@ int run_pipeline(bdepth* h, RunMode mode, RunOut* ro, Emitter* em = nullptr) {
         carry_len = (last_batch || fix) ? 0 : new_carry; first_batch = false;
         hs.used = 0;      // synchronised above: the scratch is free again
         }   // sub-batches
+        if (sparse_bad) break;
         }   // stream scope
         b = b1; batch_no++;
+    }
+    if (sparse && h->world > 1) {      // did the region chunks end where the index says, on EVERY rank?
+        if (h->comm) {
+            uint32_t flag = sparse_bad ? 1u : 0u;
+            CK(cudaMemcpyAsync(h->misc.p, &flag, 4, cudaMemcpyHostToDevice, sm));
+            NK(nccl().AllReduce(h->misc.p, h->misc.p, 1, NCCL_UINT32, NCCL_SUM, h->comm, sm));
+            CK(cudaMemcpyAsync(&flag, h->misc.p, 4, cudaMemcpyDeviceToHost, sm)); CK(cudaStreamSynchronize(sm));
+            sparse_bad = flag != 0;
+        } else if (sparse_bad) return fail(h, BDEPTH_ERR_FORMAT, "the index does not describe this file (a region chunk does not end at a record); several ranks without a NCCL id cannot fall back together");
+        if (sparse_bad) { h->sparse_ok = false; CK(cudaDeviceSynchronize()); return run_pipeline(h, mode, ro, em); }
     }
     st.ms_h2d = ms_h2d; st.ms_inflate = ms_k1; st.ms_scan = ms_k2; st.ms_coverage = ms_k3;
     st.positions = mode == RUN_FULL ? h->hdr.total_len : 0;
@@ -1428,10 +1445,9 @@ static int run_segments(bdepth* h, const std::vector<SegDef>& segs, const uint32
     cudaEvent_t e0 = h->ev[5], e1 = h->ev[6];
     CK(cudaEventRecord(e0, sm));
     // per-segment sums over the counters (original order)
-    DevBuf da, dac, db, dthr, dbases, dcov;
-    auto cleanup = [&]() { da.release(); dac.release(); db.release(); dthr.release(); dbases.release(); dcov.release(); };
-    cudaError_t ce;
-    if ((ce = da.ensure(nn * 8)) || (ce = dac.ensure(nn * 8)) || (ce = db.ensure(nn * 8)) || (ce = dthr.ensure(64)) || (ce = dbases.ensure(NS * nn * 4)) || (ce = dcov.ensure(NS * nn * 4 * nt1))) { cleanup(); return fail(h, BDEPTH_ERR_CUDA, "out of device memory (%s)", cudaGetErrorString(ce)); }
+    struct Scratch { DevBuf da, dac, db, dthr, dbases, dcov; ~Scratch() { da.release(); dac.release(); db.release(); dthr.release(); dbases.release(); dcov.release(); } } scr;      // released on every return path
+    DevBuf &da = scr.da, &dac = scr.dac, &db = scr.db, &dthr = scr.dthr, &dbases = scr.dbases, &dcov = scr.dcov;
+    CK(da.ensure(nn * 8)); CK(dac.ensure(nn * 8)); CK(db.ensure(nn * 8)); CK(dthr.ensure(64)); CK(dbases.ensure(NS * nn * 4)); CK(dcov.ensure(NS * nn * 4 * nt1));
     std::vector<uint64_t> acv(n); std::vector<uint32_t> qbases, mbases;
     for (size_t i = 0; i < n; i++) {
         uint64_t lo = std::max(h->cnt_base, h->own_lo), hi = std::min(h->cnt_base + h->win_len, h->own_hi); if (hi < lo) hi = lo;
@@ -1440,36 +1456,34 @@ static int run_segments(bdepth* h, const std::vector<SegDef>& segs, const uint32
         uint64_t wa = std::min(std::max(a[i], lo), hi), wb = std::min(std::max(b[i], lo), hi), wc = std::min(std::max(acov, lo), hi);
         a[i] = wa - h->cnt_base; b[i] = wb - h->cnt_base; acv[i] = wc - h->cnt_base;
     }
-    if (n) { cudaMemcpyAsync(da.p, a.data(), n * 8, cudaMemcpyHostToDevice, sm); cudaMemcpyAsync(dac.p, acv.data(), n * 8, cudaMemcpyHostToDevice, sm); cudaMemcpyAsync(db.p, b.data(), n * 8, cudaMemcpyHostToDevice, sm); }
-    if (n_thr) cudaMemcpyAsync(dthr.p, thr, n_thr * 4, cudaMemcpyHostToDevice, sm);
-    cudaMemsetAsync(dbases.p, 0, NS * nn * 4, sm); cudaMemsetAsync(dcov.p, 0, NS * nn * 4 * nt1, sm);
+    if (n) { CK(cudaMemcpyAsync(da.p, a.data(), n * 8, cudaMemcpyHostToDevice, sm)); CK(cudaMemcpyAsync(dac.p, acv.data(), n * 8, cudaMemcpyHostToDevice, sm)); CK(cudaMemcpyAsync(db.p, b.data(), n * 8, cudaMemcpyHostToDevice, sm)); }
+    if (n_thr) CK(cudaMemcpyAsync(dthr.p, thr, n_thr * 4, cudaMemcpyHostToDevice, sm));
+    CK(cudaMemsetAsync(dbases.p, 0, NS * nn * 4, sm)); CK(cudaMemsetAsync(dcov.p, 0, NS * nn * 4 * nt1, sm));
     if (n) {
         for (size_t si = 0; si < NS; si++) {
             BD_LAUNCH((unsigned)((n * 32 + 255) / 256), 256, 0, sm, k_segment_stats)(h->counts.as<uint32_t>() + (uint64_t)si * N_PLANES * h->win_len, h->win_len, da.as<uint64_t>(), dac.as<uint64_t>(), db.as<uint64_t>(), (uint32_t)n, dthr.as<uint32_t>(), (uint32_t)n_thr, dbases.as<uint32_t>() + si * n, dcov.as<uint32_t>() + si * n * nt1);
-            h->st.gpu_launches++;
+            CK(cudaGetLastError()); h->st.gpu_launches++;
         }
-        if (h->world > 1 && h->comm) {   // per-segment partial sums are additive over ranks
+        if (h->world > 1 && h->comm) {   // per-segment partial sums are additive over ranks; a failed collective is an error, never a partial sum handed out as the result
             NcclApi& N = nccl();
-            N.AllReduce(dbases.p, dbases.p, NS * n, NCCL_UINT32, NCCL_SUM, h->comm, sm);
-            if (n_thr) N.AllReduce(dcov.p, dcov.p, NS * n * n_thr, NCCL_UINT32, NCCL_SUM, h->comm, sm);
-            N.AllReduce(S.reads.p, S.reads.p, NS * n, NCCL_UINT32, NCCL_SUM, h->comm, sm);
-            if (has_min) N.AllReduce(S.bases_reads.p, S.bases_reads.p, NS * n, NCCL_UINT32, NCCL_SUM, h->comm, sm);
-            if (h->fix_mates) N.AllReduce(S.mbases.p, S.mbases.p, NS * n, NCCL_UINT32, NCCL_SUM, h->comm, sm);
+            NK(N.AllReduce(dbases.p, dbases.p, NS * n, NCCL_UINT32, NCCL_SUM, h->comm, sm));
+            if (n_thr) NK(N.AllReduce(dcov.p, dcov.p, NS * n * n_thr, NCCL_UINT32, NCCL_SUM, h->comm, sm));
+            NK(N.AllReduce(S.reads.p, S.reads.p, NS * n, NCCL_UINT32, NCCL_SUM, h->comm, sm));
+            if (has_min) NK(N.AllReduce(S.bases_reads.p, S.bases_reads.p, NS * n, NCCL_UINT32, NCCL_SUM, h->comm, sm));
+            if (h->fix_mates) NK(N.AllReduce(S.mbases.p, S.mbases.p, NS * n, NCCL_UINT32, NCCL_SUM, h->comm, sm));
         }
-        cudaMemcpyAsync(bases.data(), dbases.p, NS * n * 4, cudaMemcpyDeviceToHost, sm);
-        if (n_thr) cudaMemcpyAsync(cov.data(), dcov.p, NS * n * n_thr * 4, cudaMemcpyDeviceToHost, sm);
-        cudaMemcpyAsync(reads.data(), S.reads.p, NS * n * 4, cudaMemcpyDeviceToHost, sm);
-        if (has_min) { qbases.resize(NS * n); cudaMemcpyAsync(qbases.data(), S.bases_reads.p, NS * n * 4, cudaMemcpyDeviceToHost, sm); }
-        if (h->fix_mates) { mbases.resize(NS * n); cudaMemcpyAsync(mbases.data(), S.mbases.p, NS * n * 4, cudaMemcpyDeviceToHost, sm); }      // -m: what n_bases has on top of the base planes (mates.cuh)
+        CK(cudaMemcpyAsync(bases.data(), dbases.p, NS * n * 4, cudaMemcpyDeviceToHost, sm));
+        if (n_thr) CK(cudaMemcpyAsync(cov.data(), dcov.p, NS * n * n_thr * 4, cudaMemcpyDeviceToHost, sm));
+        CK(cudaMemcpyAsync(reads.data(), S.reads.p, NS * n * 4, cudaMemcpyDeviceToHost, sm));
+        if (has_min) { qbases.resize(NS * n); CK(cudaMemcpyAsync(qbases.data(), S.bases_reads.p, NS * n * 4, cudaMemcpyDeviceToHost, sm)); }
+        if (h->fix_mates) { mbases.resize(NS * n); CK(cudaMemcpyAsync(mbases.data(), S.mbases.p, NS * n * 4, cudaMemcpyDeviceToHost, sm)); }      // -m: what n_bases has on top of the base planes (mates.cuh)
     }
-    cudaEventRecord(e1, sm);
-    ce = cudaStreamSynchronize(sm);
-    if (ce == cudaSuccess) ce = cudaGetLastError();
-    cleanup();
-    if (ce != cudaSuccess) return fail(h, BDEPTH_ERR_CUDA, "CUDA error in segment statistics: %s", cudaGetErrorString(ce));
+    CK(cudaEventRecord(e1, sm));
+    CK(cudaStreamSynchronize(sm));
+    CK(cudaGetLastError());
     if (!qbases.empty()) for (size_t si = 0; si < NS; si++) for (size_t i = 0; i < n; i++) if (segs[i].min_read_start) bases[si * n + i] = qbases[si * n + i];
     if (!mbases.empty()) for (size_t k = 0; k < NS * n; k++) bases[k] += mbases[k];
-    float t = 0; cudaEventElapsedTime(&t, e0, e1); h->st.ms_reduce = t;
+    float t = 0; CK(cudaEventElapsedTime(&t, e0, e1)); h->st.ms_reduce = t;
     h->st.ms_total_device = h->st.ms_h2d + h->st.ms_inflate + h->st.ms_scan + h->st.ms_coverage + h->st.ms_reduce;
     return 0;
 }

@@ -214,6 +214,7 @@ struct ScanStats {      // device-side accumulators
     unsigned long long n_ghost_right;   // -m on several ranks: records at or after the shard limit (the next rank's zone)
     unsigned long long bad_rec;     // 1 + index of the first record whose name + CIGAR + sequence + qualities do not fit its block_size (~0: none)
 };
+constexpr uint64_t START_UNPLACED = 0xFFFFFFFFFFFFFFFEull;      // RecordSoA.start of a record without a position on a known reference
 constexpr uint32_t NCL_GHOST = 1u << 31;      // RecordSoA.ncl: a record that is only re-read for the mate kernels and passes the filter (its pass bit is clear)
 constexpr uint32_t NCL_FOREIGN = 1u << 30;    // ... and belongs to another rank's shard (-m on several ranks: the zones left and right of the shard)
 // @RG ID -> sample table (depth.d:1170-1181); ids are NUL-terminated, concatenated.  n_rg == 0 disables the scan.
@@ -297,7 +298,7 @@ __global__ void k2_decode(ScanParams sp, const int64_t* __restrict__ chunk_start
         bool placed = ref >= 0 && ref < sp.n_ref && pos >= 0;
         bool pass = placed && !(flag & 4u) && span > 0;
         if (pass) { if (FILTER) pass = filter_eval_cold(fprog, p, ldu32(sp.u + o)); else pass = ((int)mapq > mapq_gt) && !(flag & flag_reject); }
-        uint64_t start = placed ? sp.ref_lin0[ref] + (uint64_t)pos : 0xFFFFFFFFFFFFFFFEull;
+        uint64_t start = placed ? sp.ref_lin0[ref] + (uint64_t)pos : START_UNPLACED;
         uint32_t span_eff = 0;
         if (pass) {
             uint64_t room = (uint32_t)pos < sp.ref_len[ref] ? (uint64_t)sp.ref_len[ref] - (uint32_t)pos : 0;
@@ -364,13 +365,18 @@ __global__ void k3_tile_index(RecordSoA soa, uint32_t R, uint64_t win_base, uint
     uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= R) return;
     uint64_t s = soa.start[r];
+    // A record that is not placed (pos = -1 on a reference, or a reference id the header does not have) can sit anywhere
+    // in a sorted file; its start is the sentinel, which is not monotone: it takes no part in the index, and the placed
+    // record behind it looks back past it.
+    if (s == START_UNPLACED) return;
     // boundaries: tiles whose start lies in (prev_start, s] get first = r
     // tile_first[t] = min{ r : start[r] >= tile_start(t) }.  Record r is that minimum for all t with
     // start[r-1] < tile_start(t) <= start[r].
     int64_t t_hi = s >= win_base ? (int64_t)((s - win_base) / TILE_POS) : -1;                        // last tile with tile_start <= s
     int64_t t_lo;
-    if (r == 0) t_lo = 0;
-    else { uint64_t ps = soa.start[r - 1]; t_lo = ps >= win_base ? (int64_t)((ps - win_base) / TILE_POS) + 1 : 0; }
+    uint32_t q = r; while (q > 0 && soa.start[q - 1] == START_UNPLACED) q--;
+    if (q == 0) t_lo = 0;
+    else { uint64_t ps = soa.start[q - 1]; t_lo = ps >= win_base ? (int64_t)((ps - win_base) / TILE_POS) + 1 : 0; }
     if (t_hi > (int64_t)n_tiles) t_hi = n_tiles;
     for (int64_t t = t_lo; t <= t_hi; t++) tile_first[t] = r;
     uint32_t m = soa.meta[r];
@@ -431,9 +437,10 @@ __global__ void __launch_bounds__(256) k3_gather(RecordSoA soa, const uint8_t* _
             ov = (mt & 3u) == 1u && (sample_sel < 0 || (int)((mt >> 2) & 63u) == sample_sel) && s < w1 && s + sp > w0;
             if (PRE && ov) { off_l = soa.off[r]; ncl_l = soa.ncl[r]; lseq_l = (uint32_t)max(soa.lseq[r], 0); c0_l = ldu32(u + off_l + 32 + (ncl_l & 0xFF)); }
         }
-        // reads are sorted by start: once the first lane of a group starts at or past w1, we are done
-        uint64_t s_first = __shfl_sync(0xFFFFFFFFu, s, 0);
-        if (s_first >= w1) break;
+        // reads are sorted by start: once the first PLACED read of a group starts at or past w1, we are done (an
+        // unplaced record in the middle of the file carries the sentinel start and says nothing about the ones behind it)
+        unsigned placed_m = __ballot_sync(0xFFFFFFFFu, r < hi && s != START_UNPLACED);
+        if (placed_m) { uint64_t s_first = __shfl_sync(0xFFFFFFFFu, s, __ffs(placed_m) - 1); if (s_first >= w1) break; }
         unsigned m = __ballot_sync(0xFFFFFFFFu, ov);
         while (m) {
             int bsel = __ffs(m) - 1; m &= m - 1;

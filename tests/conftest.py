@@ -16,14 +16,10 @@ def pytest_configure(config):
 EMULATE = os.environ.get("BDEPTH_EMULATE") == "1"
 
 
-def pytest_collection_modifyitems(config, items):
-    """BDEPTH_EMULATE=1 (TEST INFRASTRUCTURE): run the `gpu` tests on the CPU against tests/emul/libbdepth_emul.so, the
-    same pipeline and kernels compiled with g++ over a CUDA-on-CPU emulation (tests/emul/cuda_shim.hpp).  The multi-GPU
-    tests run with ranks as threads over an NCCL stand-in; the full-size test runs its own logic on a small file.  Nothing
-    of this ever touches the product library."""
-    if not EMULATE:
-        return
-    del items      # every gpu test has an emulation-sized variant of its input (see the tests)
+# BDEPTH_EMULATE=1 (TEST INFRASTRUCTURE): the `gpu` tests run on the CPU against tests/emul/libbdepth_emul.so, the same pipeline
+# and kernels compiled with g++ over a CUDA-on-CPU emulation (tests/emul/cuda_shim.hpp).  The multi-GPU tests run with ranks
+# as threads over an NCCL stand-in; every gpu test has an emulation-sized variant of its input.  Nothing of this ever touches
+# the product library.
 
 
 @pytest.fixture(scope="session", autouse=True)

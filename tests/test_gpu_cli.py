@@ -98,7 +98,6 @@ def test_errors_and_usage(tiny):
     assert rc == 1 and b"positive window size must be specified" in err
 
 
-@pytest.mark.xfail(strict=False, reason="first hardware run pending (k_presence was written without a GPU; it passes under the CPU emulation)")
 def test_annotated_rows_of_positions_whose_bases_all_fail_q(tiny, tmp_path):
     """-a with -q and a positive minimum coverage: a position that reads cover but whose every base is below -q still has a
     column; the reference prints it with flag n (depth.d:534-555).  The counters are zero there: a presence bitmap

@@ -189,7 +189,6 @@ def test_overlapping_windows_first_reference_without_reads(tmp_path):
         cli_same(args)
 
 
-@pytest.mark.xfail(strict=False, reason="first hardware run pending (passes under the CPU emulation)")
 def test_corrupt_and_truncated_files_are_refused(tmp_path):
     """Malformed input must end in an error message, never in a hang, a fault or quietly shortened output: a truncated last
     record (readExact throws in the reference, readrange.d:169), a damaged DEFLATE stream (zlib error, block.d:127-216), a

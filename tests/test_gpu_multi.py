@@ -119,7 +119,6 @@ def test_sharded_base_equals_oracle(bam, world):
     assert any(r[5]["halo_bytes_sent"] > 0 for r in res), "reads straddling a shard boundary must be exchanged"
 
 
-@pytest.mark.xfail(strict=False, reason="first hardware run pending (sub-batches on several ranks; passes under the CPU emulation)")
 @pytest.mark.parametrize("world,tuning", [(2, (1 << 20, 3)), (4, (1 << 20, 1)), (3, (0, 2))])
 def test_sharded_with_small_batches_and_sub_batches(bam, world, tuning):
     """Several batches per rank and several sub-batches per batch (the shard limit then falls inside or before a sub-batch)."""
@@ -154,7 +153,6 @@ def pairs_bam(tmp_path_factory):
                            "-n", 30000 if small else 300000, "--pairs", 7, "-s", 12, "-t", 8)
 
 
-@pytest.mark.xfail(strict=False, reason="first hardware run pending (-m on several ranks was written without a GPU; it passes under the CPU emulation)")
 @pytest.mark.parametrize("world,tuning", [(2, None), (4, None), (8, None), (3, (1 << 20, 0)), (2, (1 << 16, 0))])
 def test_fix_mates_on_several_ranks(pairs_bam, world, tuning):
     """-m with shards: every rank reads a zone of its neighbours' records around its shard, a pair cut by a shard boundary is
@@ -172,7 +170,6 @@ def test_fix_mates_on_several_ranks(pairs_bam, world, tuning):
     assert sum(r[5]["n_records"] for r in res) == ost.n_records
 
 
-@pytest.mark.xfail(strict=False, reason="first hardware run pending (-m on several ranks)")
 def test_fix_mates_windows_and_regions_on_several_ranks(pairs_bam):
     if _n_gpus() < 2:
         pytest.skip("needs 2 GPUs")
@@ -188,7 +185,6 @@ def test_fix_mates_windows_and_regions_on_several_ranks(pairs_bam):
             assert r[4] == want_r
 
 
-@pytest.mark.xfail(strict=False, reason="first hardware run pending (region chunks divided among ranks; passes under the CPU emulation)")
 @pytest.mark.parametrize("world", [2, 3])
 def test_scattered_regions_divide_their_chunks_among_ranks(bam, world):
     """BASELINE configs[4] (`depth region -L exome.bed` on several GPUs): only the BAI chunks of the regions are staged, and

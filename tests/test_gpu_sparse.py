@@ -80,7 +80,6 @@ def test_foreign_index_falls_back_to_the_whole_file(big, tmp_path):
     assert np.array_equal(got, want)
 
 
-@pytest.mark.xfail(strict=False, reason="first hardware run pending (host logic only; it passes under the CPU emulation)")
 def test_lazy_open_frames_only_what_a_region_query_needs(big, tmp_path):
     """bdepth_open_lazy: a region query must not depend on BGZF members outside its BAI chunks.  A copy of the file whose
     LAST data member is damaged cannot be opened eagerly, but answers a query on its first reference when opened lazily --

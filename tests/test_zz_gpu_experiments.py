@@ -12,7 +12,7 @@ from helpers import GOLDEN
 
 N_READS = 12000 if os.environ.get("BDEPTH_EMULATE") == "1" else 120000
 
-pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600), pytest.mark.xfail(strict=False, reason="first hardware run pending")]
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600)]
 
 
 def test_small_cta_inflate_gives_identical_output(tmp_path):

@@ -11,8 +11,7 @@ import pytest
 import helpers
 import test_emul_filter as tef
 
-pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600),
-              pytest.mark.xfail(strict=False, reason="first hardware run pending (GPU budget of the round was spent before -F was wired in)")]
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600)]
 
 
 def test_cli_filters_match_oracle_on_prefiltered_input(tmp_path):

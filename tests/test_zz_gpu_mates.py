@@ -13,8 +13,7 @@ import pytest
 import helpers
 from helpers import GOLDEN
 
-pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600),
-              pytest.mark.xfail(strict=False, reason="first hardware run pending (GPU budget of the round was spent before -m was wired in)")]
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600)]
 
 
 def G(f):
