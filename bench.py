@@ -31,6 +31,9 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
+if os.environ.get("BDEPTH_EMULATE") == "1":        # TEST INFRASTRUCTURE (tests/test_bench_cpu.py): the bench logic on the CPU over the CUDA-on-CPU emulation of the library; never a benchmark
+    import sambamba_b200._lib as _L
+    _L.lib_path = lambda: os.path.join(ROOT, "tests", "emul", "libbdepth_emul.so")
 
 READS_PER_UNIT = 12888833
 UNIT_LEN = 64444167
@@ -88,6 +91,59 @@ def ensure_workload(n_units, reads_per_unit, load=True):
     os.replace(tmp + ".bai", path + ".bai")
     os.replace(tmp, path)
     return path
+
+
+GRCH38 = [248956422, 242193529, 198295559, 190214555, 181538259, 170805979, 159345973, 145138636, 138394717, 133797422, 135086622, 133275309, 114364328,
+          107043718, 101991189, 90338345, 83257441, 80373285, 58617616, 64444167, 46709983, 50818468, 156040895, 57227415]
+WGS_SCALE = int(os.environ.get("BDEPTH_BENCH_WGS_SCALE", "10"))       # every chromosome at 1 / WGS_SCALE of its GRCh38 length, still 30x
+WGS_READS = 620000000
+
+
+def wgs_refs(scale=None):
+    scale = scale or WGS_SCALE
+    return [((f"chr{i + 1}" if i < 22 else ("chrX" if i == 22 else "chrY")), GRCH38[i] // scale) for i in range(24)]
+
+
+def ensure_wgs(load=True):
+    """BASELINE configs[2..4] input: the 24 GRCh38 primary chromosomes, 30x of 150 bp reads, seed 30 -- at 1 / WGS_SCALE
+    linear scale: a full-size one is 108 GB of BAM, more than the box's 79 GB disk and ~10 minutes of generation per bench run.
+    Every per-position ratio (reads per tile, bytes per position, blocks per Mbp) is that of the full genome; 62 M reads,
+    10.8 GB of BAM, 18 GB inflated = three 6 GiB HBM batches, so the carry / tile-window / prefetch paths are all in the timing."""
+    import __graft_entry__ as g
+    g.build(quiet=True, load=load)
+    d = os.environ.get("BDEPTH_BENCH_DIR", "/tmp/bdepth_bench")
+    os.makedirs(d, exist_ok=True)
+    n = WGS_READS // WGS_SCALE
+    path = os.path.join(d, f"synth_wgs_div{WGS_SCALE}_{n}.bam")
+    if os.path.exists(path) and os.path.exists(path + ".bai"):
+        return path
+    tmp = path + f".tmp{os.getpid()}"
+    cmd = [os.path.join(ROOT, "tools", "_build", "bamgen"), "-o", tmp, "-n", str(n), "-s", "30", "-t", str(min(64, os.cpu_count() or 8))]
+    for name, ln in wgs_refs():
+        cmd += ["-r", f"{name}:{ln}"]
+    subprocess.check_call(cmd, stderr=subprocess.DEVNULL)
+    os.replace(tmp + ".bai", path + ".bai")
+    os.replace(tmp, path)
+    return path
+
+
+def exome_bed(refs, n_total, seed=50):
+    """sorted, non-overlapping intervals, lengths ~ lognormal (median 150, clipped 50..2000), spread over the
+    references in proportion to their length.  Returns an [n, 3] uint32 array (ref_id, start, end)."""
+    import numpy as np
+    rs = np.random.RandomState(seed)
+    total = sum(l for _, l in refs)
+    out = []
+    for ri, (_, L) in enumerate(refs):
+        k = max(1, int(round(n_total * L / total)))
+        lens = np.clip(np.exp(rs.normal(np.log(150.0), 0.6, k)), 50, 2000).astype(np.int64)
+        slack = L - int(lens.sum()) - k
+        if slack <= 0:
+            k = max(1, int(L // 4000)); lens = lens[:k]; slack = L - int(lens.sum()) - k
+        gaps = np.diff(np.concatenate([[0], np.sort(rs.randint(0, slack + 1, k))])) + 1          # >= 1 between consecutive intervals
+        starts = np.cumsum(gaps + np.concatenate([[0], lens[:-1]]))
+        out.append(np.stack([np.full(k, ri, np.int64), starts, starts + lens], axis=1))
+    return np.concatenate(out).astype(np.uint32)
 
 
 class ClockSampler:
@@ -230,12 +286,254 @@ def oracle_checksums(path, threads):
     return [ck, tot, cov, want.shape[1]], st
 
 
+def setup_dist(world, local_rank):
+    if world <= 1:
+        return None
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    return dist
+
+
+def run_wgs_config(a, rank, world, local_rank):
+    """BASELINE configs[2] (`depth window -w 1000`, 1 GPU), [3] (`depth base` sharded over 2/4/8 GPUs, one file: strong scaling) and
+    [4] (`depth region -L exome.bed`, 8 GPUs) on the GRCh38-shaped 30x BAM.  Same JSON contract as the headline config."""
+    import numpy as np
+    refs = wgs_refs()
+    lin0 = np.concatenate([[0], np.cumsum([l for _, l in refs])]).astype(np.int64)
+    n_bed = max(1000, 200000 // WGS_SCALE)
+    mode = {"window": "depth window -w 1000", "wgs-shard": "depth base", "exome": f"depth region -L exome.bed ({n_bed} intervals)"}[a.config]
+    workload = (f"synthetic 30x whole-genome BAM, GRCh38 primary chromosomes at 1/{WGS_SCALE} length (BASELINE configs[{ {'window': 2, 'wgs-shard': 3, 'exome': 4}[a.config] }] shape): "
+                f"24 references, {sum(l for _, l in refs):,} bp, {WGS_READS // WGS_SCALE:,} x 150 bp reads, seed 30, zlib-6 BGZF; `{mode}`, default filter"
+                + (f"; BED: {n_bed} sorted intervals (200,000 x 1/{WGS_SCALE}: the interval density of the full-size case), lognormal lengths, seed 50" if a.config == "exome" else ""))
+    config = {"workload": workload, "mode": mode, "filter": "mapping_quality > 0 and not duplicate and not failed_quality_control",
+              "parallelism": f"bgzf-shard x{a.gpus} (one file, strong scaling)" if a.gpus > 1 else "single GPU", "l2": "inputs >> L2 (10.8 GB compressed, 18 GB inflated, three 6 GiB HBM batches)"}
+    metric = {"window": "bam_gb_per_s_depth_window", "wgs-shard": "bam_gb_per_s_depth_base", "exome": "bam_gb_per_s_depth_region"}[a.config]
+    bed = exome_bed(refs, n_bed) if a.config == "exome" else None
+
+    # ------------------------------------------------------------------ reference arm (CPU port, bounded sample of the same command)
+    if a.impl == "reference":
+        if rank != 0:
+            return 0
+        path = ensure_wgs(load=False)
+        threads = os.cpu_count() or 1
+        exe = os.path.join(ROOT, "oracle", "_build", "depth_oracle")
+        sample = a.cpu_sample_mb << 20
+        extra = []
+        if a.config == "exome":
+            bp = path + f".exome{n_bed}.bed"
+            with open(bp, "w") as f:
+                f.write("".join(f"{refs[r][0]}\t{s}\t{e}\n" for r, s, e in bed.tolist()))
+            extra = ["-L", bp]
+        sub = {"window": ["depth", "window", "-w", "1000"], "wgs-shard": ["depth", "base"], "exome": ["depth", "region"] + extra}[a.config]
+        times = []
+        for i in range(a.warmup + a.steps):
+            t0 = time.time()
+            r = subprocess.run([exe, "--inflate-threads", str(threads), "--max-file-bytes", str(sample), "--stats"] + sub + [path, "-o", "/dev/null"], capture_output=True, text=True)
+            if r.returncode != 0:
+                raise RuntimeError(f"the CPU baseline failed (exit {r.returncode}): {r.stderr[-300:]}")
+            if i >= a.warmup:
+                times.append(time.time() - t0)
+        dt = sum(times) / len(times)
+        nb = min(sample, os.path.getsize(path))
+        v = nb / 1e9 / dt
+        cb = {"value": v, "unit": "GB/s", "cores": threads, "kind": "port", "sample": f"first {nb / 1e6:.0f} MB of the BAM, `{mode}` by the oracle port: zlib inflate on {threads} threads + serial sweep; wall {dt:.2f} s",
+              "probe": {"sambamba": shutil.which("sambamba"), "ldc2": shutil.which("ldc2")}}
+        print(json.dumps({"impl": "reference", "metric": metric, "value": v, "unit": "GB/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": dt * 1e3,
+                          "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32", "data": "synthetic", "config": config, "cpu_baseline": cb,
+                          "e2e": {"value": v, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
+        return 0
+
+    # ------------------------------------------------------------------ our arm
+    import sambamba_b200 as sb
+    dist = setup_dist(world, local_rank)
+    if rank == 0:
+        path = ensure_wgs()
+    if dist is not None:
+        dist.barrier()
+    path = ensure_wgs()
+    file_bytes = os.path.getsize(path)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    def reduce(x, op):
+        if dist is None:
+            return x
+        import torch
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=getattr(dist.ReduceOp, op))
+        return float(t.item())
+
+    def fresh_uid():
+        if dist is None:
+            return None
+        obj = [sb.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(obj, src=0)
+        return obj[0]
+
+    def one_pass(h, collect=False):
+        if a.config == "window":
+            return h.run_windows(1000, 0, (1, 10, 30) if collect else (), collect="arrays" if collect else False)
+        if a.config == "exome":
+            return h.run_regions(bed, (1, 10, 30) if collect else (), collect="arrays" if collect else False)
+        return h.run_base(collect=False)
+
+    # ---- value: the (shard of the) compressed file resident in HBM
+    b = sb.BDepth(path, device=local_rank, lazy=(a.config == "exome"))
+    if world > 1:
+        b.set_shard(rank, world, fresh_uid())
+    if a.config != "exome":
+        b.stage()            # a region query stages only its BAI chunks, per run: that is its "resident" form too (sparse staging excludes bdepth_stage)
+    for _ in range(a.warmup):
+        barrier()
+        one_pass(b) if a.config != "wgs-shard" else b.run_resident()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    span, k1, k2, k3, ex, red, launches = [], [], [], [], [], [], 0
+    barrier()
+    for _ in range(a.steps):
+        barrier()
+        t0 = time.perf_counter()
+        one_pass(b) if a.config != "wgs-shard" else b.run_resident()
+        wall = (time.perf_counter() - t0) * 1e3
+        st = b.stats()
+        dev = st["ms_span_device"] + st["ms_reduce"] if a.config != "exome" else wall        # exome: H2D of the selected blocks is part of every run
+        span.append(reduce(dev, "MAX"))
+        k1.append(st["ms_inflate"]); k2.append(st["ms_scan"]); k3.append(st["ms_coverage"]); ex.append(st["ms_exchange"]); red.append(st["ms_reduce"])
+        launches += st["gpu_launches"]
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    st = b.stats()
+    ms_step = sum(span) / len(span)
+    k1_ms = sum(k1) / len(k1)
+    k1_bytes = st["cdata_bytes"] + st["inflated_bytes"]
+    n_batches = st["n_batches"]
+    staged_bytes = reduce(st["file_bytes"], "SUM")
+    covered = reduce(st["covered_positions"], "SUM") if a.config == "wgs-shard" else None
+    total_launches = reduce(launches, "SUM")
+    b.close()
+
+    # ---- e2e: pinned host BAM image in, results in host memory out, everything inside the timed region
+    try:
+        img, keep = pinned_file(path)
+        host_kind = "pinned"
+    except Exception:
+        img, keep, host_kind = np.fromfile(path, dtype=np.uint8), None, "pageable (cudaHostAlloc of the whole image failed)"
+    bai = np.fromfile(path + ".bai", dtype=np.uint8)
+    h = sb.BDepth(memory=img, bai=bai, device=local_rank)
+    if world > 1:
+        h.set_shard(rank, world, fresh_uid())
+    e2e_t, d2h_bytes, h2d_bytes = [], 0, 0
+    n_w = max(1, min(a.warmup, 3))
+    for i in range(n_w + a.steps):
+        barrier()
+        t0 = time.perf_counter()
+        one_pass(h)
+        dt = reduce(time.perf_counter() - t0, "MAX")
+        s2 = h.stats()
+        h2d_bytes = reduce(s2["file_bytes"], "SUM")
+        d2h_bytes = reduce((s2["own_hi"] - s2["own_lo"]) * 28, "SUM") if a.config == "wgs-shard" else None
+        if i >= n_w:
+            e2e_t.append(dt)
+    e2e_stats = h.stats()
+    e2e_s = sum(e2e_t) / len(e2e_t)
+
+    # ---- verification after the timed regions, against the CPU oracle's closed forms over the whole file
+    verify = None
+    if not a.no_verify:
+        if a.config == "wgs-shard":
+            mine = checksum_run(h, lin0)
+            allv = [None] * world
+            if dist is not None:
+                dist.all_gather_object(allv, mine)
+            else:
+                allv = [mine]
+            if rank == 0:
+                got = [sum(v[0] for v in allv) & 0xFFFFFFFFFFFFFFFF, sum(v[1] for v in allv), sum(v[2] for v in allv), sum(v[3] for v in allv)]
+                t0 = time.perf_counter()
+                want, ost = oracle_checksums(path, min(64, os.cpu_count() or 8))
+                verify = {"ok": got == want and got[2] == int(covered), "checksum": f"{got[0]:016x}", "oracle_checksum": f"{want[0]:016x}", "counts_total": got[1], "oracle_counts_total": want[1],
+                          "covered_positions": got[2], "oracle_covered_positions": want[2], "positions_delivered": got[3], "oracle_seconds": time.perf_counter() - t0,
+                          "what": "order-sensitive checksum of every rank's delivered counter tiles vs the CPU oracle's closed-form counters of the whole file"}
+        else:
+            rows = one_pass(h, collect=True)           # every rank holds the all-reduced table; rank 0 checks it
+            if rank == 0:
+                import helpers
+                t0 = time.perf_counter()
+                if a.config == "window":
+                    sa = np.concatenate([lin0[r] + np.arange(0, (L // 1000) * 1000, 1000, dtype=np.int64) for r, (_, L) in enumerate(refs)]).astype(np.uint64)
+                    sb_ = sa + np.uint64(1000)
+                else:
+                    sa = (lin0[bed[:, 0].astype(np.int64)] + bed[:, 1].astype(np.int64)).astype(np.uint64)
+                    sb_ = (lin0[bed[:, 0].astype(np.int64)] + bed[:, 2].astype(np.int64)).astype(np.uint64)
+                wr, wb, wc = helpers.oracle_segment_stats(path, sa, sb_, (1, 10, 30), threads=min(64, os.cpu_count() or 8))
+                same_rows = len(rows["n_reads"]) == len(sa) and np.array_equal(lin0[rows["ref_id"]] + rows["start"], sa.astype(np.int64))
+                ok_r = same_rows and np.array_equal(rows["n_reads"], wr)
+                ok_b = same_rows and np.array_equal(rows["n_bases"], wb)
+                ok_c = same_rows and np.array_equal(rows["cov_ge"].T, wc)
+                verify = {"ok": bool(ok_r and ok_b and ok_c), "rows": int(len(sa)), "n_reads_equal": bool(ok_r), "n_bases_equal": bool(ok_b), "cov_ge_1_10_30_equal": bool(ok_c),
+                          "sum_n_reads": int(rows["n_reads"].sum()), "sum_n_bases": int(rows["n_bases"].astype(np.uint64).sum()), "oracle_seconds": time.perf_counter() - t0,
+                          "what": "readCount, n_bases and the positions with COV >= 1 / 10 / 30 of every row vs the CPU oracle's closed form (oracle_segment_stats, itself checked against the faithful sweep in tests/test_oracle_golden.py)"}
+    h.close()
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return 0
+    peak, peak_src = peaks()
+    traffic, traffic_src = ncu_traffic("roofline")
+    value = file_bytes / 1e9 / (ms_step / 1e3)
+    out = {
+        "metric": metric, "value": value, "unit": "GB/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "u32", "data": "synthetic", "config": config,
+        "covered_mbases_per_s": (covered / 1e6 / (ms_step / 1e3)) if covered is not None else None,
+        "stage_ms": {"k1_inflate": k1_ms, "k2_scan": sum(k2) / len(k2), "k3_coverage": sum(k3) / len(k3), "nccl_exchange": sum(ex) / len(ex), "reduce": sum(red) / len(red), "hbm_batches": n_batches},
+        "staged_bytes_per_step": int(staged_bytes),
+        "e2e": {"value": file_bytes / 1e9 / e2e_s, "unit": "GB/s", "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(d2h_bytes) if d2h_bytes is not None else "result table only",
+                "ms_per_step": e2e_s * 1e3, "device_ms": {k: e2e_stats[k] for k in ("ms_h2d", "ms_inflate", "ms_scan", "ms_coverage", "ms_reduce", "ms_d2h", "ms_span_device")},
+                "path": "bdepth_open_memory(pinned host BAM image) + " + {"window": "bdepth_run_windows", "wgs-shard": "bdepth_run_base", "exome": "bdepth_run_regions"}[a.config], "host_input": host_kind},
+        "gpu_launches": int(total_launches),
+        "roofline": {"kernel": "K1 two-phase inflate (k1_huff + k1_lz)", "bound": "hbm", "achieved": k1_bytes / 1e9 / (k1_ms / 1e3) if k1_ms else None, "peak": peak, "unit": "GB/s",
+                     "frac": (k1_bytes / 1e9 / (k1_ms / 1e3) / peak) if k1_ms else None, "traffic": None, "traffic_source": "per-launch capture exists for the chr20 workload only (" + str(traffic_src) + ")",
+                     "algorithmic_bytes_per_launch": int(k1_bytes / max(1, n_batches)), "launches_per_step": n_batches, "peak_source": peak_src,
+                     "note": "C + U of this rank's shard / CUDA-event time of its K1 launches"},
+        "clocks": clocks, "verified": (verify["ok"] if verify else None), "verification": verify,
+    }
+    if not a.no_cpu_baseline:
+        exe = os.path.join(ROOT, "oracle", "_build", "depth_oracle")
+        sample = a.cpu_sample_mb << 20
+        sub = {"window": ["depth", "window", "-w", "1000"], "wgs-shard": ["depth", "base"], "exome": None}[a.config]
+        if sub is not None:
+            threads = os.cpu_count() or 1
+            t0 = time.time()
+            r = subprocess.run([exe, "--inflate-threads", str(threads), "--max-file-bytes", str(sample), "--stats"] + sub + [path, "-o", "/dev/null"], capture_output=True, text=True)
+            dt = time.time() - t0
+            if r.returncode != 0:
+                raise RuntimeError(f"the CPU baseline failed (exit {r.returncode}): {r.stderr[-300:]}")
+            out["cpu_baseline"] = {"value": min(sample, file_bytes) / 1e9 / dt, "unit": "GB/s", "cores": threads, "kind": "port",
+                                   "sample": f"first {min(sample, file_bytes) / 1e6:.0f} MB of the BAM, `{mode}` by the oracle port; wall {dt:.2f} s"}
+        else:
+            out["cpu_baseline"] = {"value": None, "unit": "GB/s", "cores": os.cpu_count(), "kind": "port", "sample": "see `bench.py --impl reference --config exome` (needs the BED file on disk)"}
+    print(json.dumps(out))
+    if dist is not None:
+        dist.destroy_process_group()
+    if verify is not None and not verify["ok"]:
+        sys.stderr.write("bench.py: VERIFICATION FAILED\n")
+        return 3
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="chr20", choices=["chr20", "window", "wgs-shard", "exome"],
+                    help="chr20: BASELINE configs[1] (headline; N > 1: N chromosomes, weak scaling).  window / wgs-shard / exome: configs[2] / [3] / [4] on the GRCh38-shaped 30x BAM")
     ap.add_argument("--reads-per-unit", type=int, default=READS_PER_UNIT, help="smaller values are for smoke tests only")
     ap.add_argument("--cpu-sample-mb", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -245,6 +543,8 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if a.config != "chr20":
+        return run_wgs_config(a, rank, world, local_rank)
     n_units = max(1, a.gpus)
     workload = (f"synthetic 30x chr20 BAM (BASELINE configs[1]): {n_units} x 64,444,167 bp, {a.reads_per_unit * n_units} x 150 bp reads, seed 20, "
                 "zlib-6 BGZF 0xFF00 blocks; `depth base`, default filter")

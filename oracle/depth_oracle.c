@@ -1079,15 +1079,27 @@ typedef struct { uint64_t n_records, n_pass, n_blocks, ulen, clen, covered, min_
 /* One passing read of the closed form: scatter its CIGAR into the window (the body of the per-read loop; the record
  * walk that finds the reads is serial, the scatter runs on worker threads with relaxed atomic increments). */
 typedef struct { const uint8_t *rec; uint64_t base, rlen; } ScatterRead;
-typedef struct { const ScatterRead *rd; size_t n; _Atomic size_t *next; uint32_t *counts; uint64_t win_a, L; int min_bq; int atomic; } ScatterJob;
+typedef struct { const ScatterRead *rd; size_t n; _Atomic size_t *next; uint32_t *counts; uint64_t win_a, L; int min_bq; int atomic;
+                 uint64_t n_seg; const uint64_t *seg_a, *seg_b; uint32_t *seg_reads; } ScatterJob;       /* optional: countRead per sorted, disjoint segment */
 static void scatter_one(const ScatterJob *j, const ScatterRead *r) {
     const uint8_t *rec = r->rec; int32_t pos = (int32_t)rd32(rec + 4); uint32_t bmn = rd32(rec + 8), fnc = rd32(rec + 12);
     uint32_t l_name = bmn & 0xFF, n_cigar = fnc & 0xFFFF; int32_t l_seq = (int32_t)rd32(rec + 16);
     const uint8_t *cig = rec + 32 + l_name, *seq = cig + 4 * (size_t)n_cigar, *qual = seq + ((size_t)l_seq + 1) / 2;
     uint64_t base = r->base, rlen = r->rlen, p = (uint64_t)(uint32_t)pos, L = j->L, win_a = j->win_a; uint32_t q = 0; uint32_t *counts = j->counts;
+    int64_t last_seg = -1;
     for (uint32_t i = 0; i < n_cigar; i++) {
         uint32_t c = rd32(cig + 4 * i), len = op_len(c), op = c & 0xF;
         if (op_match(c)) {
+            if (j->n_seg) {       /* countRead (depth.d:661-669) in closed form: the read counts once in every segment in which it has a base with quality >= -q */
+                uint64_t g0 = base + p, g1 = g0 + len; if (g1 > base + rlen) g1 = base + rlen;
+                uint64_t lo = 0, hi = j->n_seg; while (lo < hi) { uint64_t m = (lo + hi) / 2; if (j->seg_b[m] <= g0) lo = m + 1; else hi = m; }
+                for (uint64_t sgi = lo; sgi < j->n_seg && j->seg_a[sgi] < g1; sgi++) {
+                    if ((int64_t)sgi <= last_seg) continue;
+                    uint64_t xa = j->seg_a[sgi] > g0 ? j->seg_a[sgi] : g0, xb = j->seg_b[sgi] < g1 ? j->seg_b[sgi] : g1; int hit = 0;
+                    for (uint64_t g = xa; g < xb && !hit; g++) { uint32_t qq = q + (uint32_t)(g - g0); if (qq < (uint32_t)l_seq && qual[qq] >= j->min_bq) hit = 1; }
+                    if (hit) { __atomic_fetch_add(&j->seg_reads[sgi], 1u, __ATOMIC_RELAXED); last_seg = (int64_t)sgi; }
+                }
+            }
             for (uint32_t k = 0; k < len; k++, p++, q++) {
                 if (p >= rlen || q >= (uint32_t)l_seq) continue;       /* clip at reference end (documented deviation for invalid input) */
                 if (qual[q] < j->min_bq) continue;
@@ -1108,8 +1120,9 @@ static void *scatter_worker(void *arg) {
     return NULL;
 }
 
-int oracle_base_counts(const char *bam_path, int mapq_gt, unsigned flag_reject, int min_bq, int nthreads, size_t max_file_bytes,
-                       uint32_t *counts /* [7][win_len], may be NULL to just scan */, uint64_t win_a /* first linear position of the window */, uint64_t win_len, ScatterStats *st) {
+int oracle_bam_info(const char *bam_path, int *n_ref, uint64_t *total_len, uint64_t *ulen, uint64_t *n_blocks);
+static int base_counts_impl(const char *bam_path, int mapq_gt, unsigned flag_reject, int min_bq, int nthreads, size_t max_file_bytes,
+                            uint32_t *counts, uint64_t win_a, uint64_t win_len, ScatterStats *st, uint64_t n_seg, const uint64_t *seg_a, const uint64_t *seg_b, uint32_t *seg_reads) {
     Bam B; memset(&B, 0, sizeof B);
     double t0 = now_s();
     if (bgzf_load(&B.z, bam_path, nthreads, max_file_bytes)) return -1;
@@ -1137,7 +1150,7 @@ int oracle_base_counts(const char *bam_path, int mapq_gt, unsigned flag_reject, 
     }
     if (counts && nrd) {
         _Atomic size_t next = 0; int nt = nthreads > 1 ? nthreads : 1;
-        ScatterJob job = { rd, nrd, &next, counts, win_a, L, min_bq, nt > 1 };
+        ScatterJob job = { rd, nrd, &next, counts, win_a, L, min_bq, nt > 1, n_seg, seg_a, seg_b, seg_reads };
         if (nt == 1) scatter_worker(&job);
         else { pthread_t *th = calloc(nt, sizeof *th); for (int t = 0; t < nt; t++) pthread_create(&th[t], NULL, scatter_worker, &job); for (int t = 0; t < nt; t++) pthread_join(th[t], NULL); free(th); }
     }
@@ -1149,6 +1162,51 @@ int oracle_base_counts(const char *bam_path, int mapq_gt, unsigned flag_reject, 
     }
     free(ref_off); bgzf_free(&B.z);
     return 0;
+}
+
+int oracle_base_counts(const char *bam_path, int mapq_gt, unsigned flag_reject, int min_bq, int nthreads, size_t max_file_bytes,
+                       uint32_t *counts /* [7][win_len], may be NULL to just scan */, uint64_t win_a /* first linear position of the window */, uint64_t win_len, ScatterStats *st) {
+    return base_counts_impl(bam_path, mapq_gt, flag_reject, min_bq, nthreads, max_file_bytes, counts, win_a, win_len, st, 0, NULL, NULL, NULL);
+}
+
+/* Region / window statistics in closed form (PerSampleRegionData, depth.d:609-635, as printRegionStats :847-876 uses them), for
+ * segments [seg_a[i], seg_b[i]) in linear coordinates, sorted and disjoint (BED regions, or the tiling windows of `depth window`
+ * without --overlap): n_reads = reads with at least one M/=/X base of quality >= -q inside (countRead :661-669), n_bases = sum of
+ * the A,C,G,T,N counters, cov[t][i] = positions whose COV (all seven counters) reaches thr[t].  Checked against the faithful
+ * sweep's region and window output in tests/test_oracle_golden.py; used by bench.py to verify full-size window / region runs,
+ * where the serial sweep would take minutes.  One sample, no -m.  Test infrastructure only. */
+typedef struct { const uint32_t *counts; uint64_t L; uint64_t n_seg; const uint64_t *a, *b; uint32_t n_thr; const uint32_t *thr; uint32_t *bases, *cov; _Atomic uint64_t *next; } SegSumJob;
+static void *seg_sum_worker(void *arg) {
+    SegSumJob *j = arg;
+    for (;;) {
+        uint64_t i0 = atomic_fetch_add(j->next, 256), i1 = i0 + 256 < j->n_seg ? i0 + 256 : j->n_seg; if (i0 >= j->n_seg) break;
+        for (uint64_t i = i0; i < i1; i++) {
+            uint64_t nb = 0;
+            for (uint64_t g = j->a[i]; g < j->b[i] && g < j->L; g++) {
+                uint32_t s5 = 0, s7 = 0; for (int k = 0; k < 7; k++) { uint32_t v = j->counts[(uint64_t)k * j->L + g]; s7 += v; if (k < 5) s5 += v; }
+                nb += s5;
+                for (uint32_t t = 0; t < j->n_thr; t++) if (s7 >= j->thr[t] && s7) j->cov[(uint64_t)t * j->n_seg + i]++;
+            }
+            j->bases[i] = (uint32_t)nb;
+        }
+    }
+    return NULL;
+}
+int oracle_segment_stats(const char *bam_path, int mapq_gt, unsigned flag_reject, int min_bq, int nthreads, uint64_t n_seg, const uint64_t *seg_a, const uint64_t *seg_b,
+                         uint32_t n_thr, const uint32_t *thr, uint32_t *out_reads, uint32_t *out_bases, uint32_t *out_cov /* [n_thr][n_seg] */) {
+    int n_ref; uint64_t total, ulen, nblk;
+    if (oracle_bam_info(bam_path, &n_ref, &total, &ulen, &nblk)) return -1;
+    uint32_t *counts = calloc((size_t)7 * (total ? total : 1), 4); if (!counts) { snprintf(g_err, sizeof g_err, "out of memory for %llu positions", (unsigned long long)total); return -1; }
+    memset(out_reads, 0, n_seg * 4); memset(out_bases, 0, n_seg * 4); if (n_thr) memset(out_cov, 0, (size_t)n_thr * n_seg * 4);
+    int rc = base_counts_impl(bam_path, mapq_gt, flag_reject, min_bq, nthreads, 0, counts, 0, total, NULL, n_seg, seg_a, seg_b, out_reads);
+    if (!rc && n_seg) {
+        _Atomic uint64_t next = 0; int nt = nthreads > 1 ? nthreads : 1;
+        SegSumJob job = { counts, total, n_seg, seg_a, seg_b, n_thr, thr, out_bases, out_cov, &next };
+        if (nt == 1) seg_sum_worker(&job);
+        else { pthread_t *th = calloc(nt, sizeof *th); for (int t = 0; t < nt; t++) pthread_create(&th[t], NULL, seg_sum_worker, &job); for (int t = 0; t < nt; t++) pthread_join(th[t], NULL); free(th); }
+    }
+    free(counts);
+    return rc;
 }
 
 /* --------------------------------------------- closed form for -m (fix-mate-overlaps), base mode

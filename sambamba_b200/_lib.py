@@ -300,9 +300,33 @@ class BDepth:
         self._ck(self.L.bdepth_run_base_text(self.h, C.byref(opts), TEXT_CB(cb), None))
         return b"".join(parts)
 
-    def _run_stats(self, fn):
-        rows = []
+    def _run_stats(self, fn, collect=True):
+        """collect=True: list of rows; "arrays": numpy columns (large runs); False: no callback at all (timing)."""
+        if collect is False:
+            self._ck(fn(C.cast(None, STAT_CB)))
+            return None
         nthr = self._nthr
+        if collect == "arrays":
+            cap = [1 << 16]
+            cols = {"ref_id": np.zeros(cap[0], np.int32), "start": np.zeros(cap[0], np.uint32), "end": np.zeros(cap[0], np.uint32), "n_reads": np.zeros(cap[0], np.uint32),
+                    "n_bases": np.zeros(cap[0], np.uint32), "cov_ge": np.zeros((cap[0], max(1, nthr)), np.uint32), "sample_id": np.zeros(cap[0], np.int32)}
+            n = [0]
+
+            def cba(_user, sp, idx):
+                s = sp.contents
+                i = n[0]
+                if i == cap[0]:
+                    cap[0] *= 2
+                    for k in cols:
+                        cols[k] = np.concatenate([cols[k], np.zeros_like(cols[k])])
+                cols["ref_id"][i] = s.ref_id; cols["start"][i] = s.start; cols["end"][i] = s.end; cols["n_reads"][i] = s.n_reads; cols["n_bases"][i] = s.n_bases; cols["sample_id"][i] = s.sample_id
+                for t in range(nthr):
+                    cols["cov_ge"][i, t] = s.cov_ge[t]
+                n[0] = i + 1
+                return 0
+            self._ck(fn(STAT_CB(cba)))
+            return {k: v[:n[0]] for k, v in cols.items()}
+        rows = []
 
         def cb(_user, sp, idx):
             s = sp.contents
@@ -311,16 +335,20 @@ class BDepth:
         self._ck(fn(STAT_CB(cb)))
         return rows
 
-    def run_windows(self, window, overlap=0, thresholds=()):
+    def run_windows(self, window, overlap=0, thresholds=(), collect=True):
         thr = (C.c_uint32 * max(1, len(thresholds)))(*thresholds)
         self._nthr = len(thresholds)
-        return self._run_stats(lambda cb: self.L.bdepth_run_windows(self.h, window, overlap, thr, len(thresholds), cb, None))
+        return self._run_stats(lambda cb: self.L.bdepth_run_windows(self.h, window, overlap, thr, len(thresholds), cb, None), collect)
 
-    def run_regions(self, regions, thresholds=()):
+    def run_regions(self, regions, thresholds=(), collect=True):
         thr = (C.c_uint32 * max(1, len(thresholds)))(*thresholds)
-        arr = (Region * max(1, len(regions)))(*[Region(*r) for r in regions])
+        if isinstance(regions, np.ndarray):          # [n, 3] uint32 (ref_id, start, end): no per-region Python objects
+            flat = np.ascontiguousarray(regions, np.uint32)
+            arr = C.cast(flat.ctypes.data_as(C.c_void_p), C.POINTER(Region)); n = len(flat); self._keep_regions = flat
+        else:
+            arr = (Region * max(1, len(regions)))(*[Region(*r) for r in regions]); n = len(regions)
         self._nthr = len(thresholds)
-        return self._run_stats(lambda cb: self.L.bdepth_run_regions(self.h, arr, len(regions), thr, len(thresholds), cb, None))
+        return self._run_stats(lambda cb: self.L.bdepth_run_regions(self.h, arr, n, thr, len(thresholds), cb, None), collect)
 
     def inflate(self):
         n = self._ck(self.L.bdepth_inflate_to_host(self.h, None, 0))

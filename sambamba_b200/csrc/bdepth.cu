@@ -149,9 +149,10 @@ struct bdepth {
     bool bai_window_ok = true;            // cleared when the linear index turns out not to describe the file
     bool combined = false;                // --combined: one counter set for all samples
     bool fix_mates = false;               // -m: overlapping mates count once per column (mates.cuh)
-    bool k1_small = false;                // BDEPTH_K1_STREAM_WARPS=4: streaming K1 sub-launches in 4-warp CTAs (experiment)
-    bool k3_pre = false;                  // BDEPTH_K3_PREFETCH=1: k3_gather with lane-parallel record prefetch (experiment)
-    bool k1_lit3 = false;                 // BDEPTH_K1_LIT3=1: K1 with up to three literals per iteration (experiment)
+    int k1h_variant = 0;                  // BDEPTH_K1H_VARIANT: which instantiation of k1_huff runs (0: limits in registers, 4 CTAs/SM)
+    bool k1_onephase = false;             // BDEPTH_K1_ONEPHASE=1: the round-1 one-phase K1 for every block (A/B against the two-phase inflater)
+    bool k3_pre = false;                  // BDEPTH_K3_PREFETCH=0: k3_gather without the lane-parallel record prefetch
+    bool k3_tile = true;                  // BDEPTH_K3=gather: the round-1 per-position gather kernel instead of k3_tile
     bool has_fprog = false; FilterProg fprog; DevBuf fprog_d;      // -F: compiled query (filter.cuh); otherwise mapq_gt / flag_reject
     DevBuf m_hash, m_flag, m_flt, m_ctl;
     uint32_t S = 1;                       // counter sets in the current run (samples, or 1)
@@ -163,7 +164,8 @@ struct bdepth {
     // ---- shard (resolved lazily)
     bool shard_ready = false;
     size_t blk_lo = 0, blk_hi = 0; int64_t entry0 = 0; uint64_t limit_abs_u = 0;
-    uint64_t own_lo_abs_u = 0;            // -m on several ranks: the stream begins before the shard does (zone of the previous rank); own records start here
+    uint64_t zone_lin_lo = UINT64_MAX;    // several ranks: linear coordinate of the 16 kbp window in which this rank's first record begins (its counter window starts there)
+    uint64_t own_lo_abs_u = 0;            // several ranks: the stream begins before the shard does (zone of the previous rank); own records start here
     // Sparse staging for region queries: only the BGZF blocks inside the BAI chunk list of the
     // regions are copied, inflated and scanned.  vblocks = those blocks with uoff re-based to a compact stream;
     // a segment is one merged chunk: it starts at a record (seg_entry = offset inside its first block) and ends at
@@ -180,6 +182,7 @@ struct bdepth {
     std::vector<cudaEvent_t> chunk_ev[2], k1_ev;      // per H2D chunk (per slot) / per K1 sub-launch
     std::vector<size_t> chunk_end[2];                  // block index (exclusive) covered by each H2D chunk of a slot
     bool staged = false; uint64_t staged_file_off = 0;
+    DevBuf tok, lits, aux, segi, littab;              // two-phase K1: match tokens, packed literals, per-block counts, segment starts, literal tables
     DevBuf comp, descs, status, ubuf, chunk_start, entry, exitb, count, slot_base, slots, rec_base, walk_list;
     DevBuf soa_start, soa_span, soa_meta, soa_off, soa_ncl, soa_lseq, long_list, tile_first, tile_lo, counts, ref_len_d, ref_lin0_d, scan_stats, ref_has, misc;
     uint64_t cnt_base = 0, win_len = 0;
@@ -219,11 +222,14 @@ int init_device(bdepth* h) {
     CK(cudaSetDevice(h->device));
     if (!h->s_main) { CK(cudaStreamCreateWithFlags(&h->s_main, cudaStreamNonBlocking)); CK(cudaStreamCreateWithFlags(&h->s_copy, cudaStreamNonBlocking)); CK(cudaStreamCreateWithFlags(&h->s_d2h, cudaStreamNonBlocking)); for (auto& ks : h->s_k1) CK(cudaStreamCreateWithFlags(&ks, cudaStreamNonBlocking)); for (auto& e2 : h->ev) CK(cudaEventCreate(&e2)); }
     CK(cudaFuncSetAttribute(k1_inflate, cudaFuncAttributeMaxDynamicSharedMemorySize, K1_SMEM));
-    { const char* e = getenv("BDEPTH_K1_STREAM_WARPS"); h->k1_small = e && atoi(e) == K1S_WARPS; }      // experiment, see kernels.cuh
-    { const char* e = getenv("BDEPTH_K3_PREFETCH"); h->k3_pre = e && atoi(e) == 1; }
-    { const char* e = getenv("BDEPTH_K1_LIT3"); h->k1_lit3 = e && atoi(e) == 1; }
-    if (h->k1_lit3) CK(cudaFuncSetAttribute(k1_inflate_lit3, cudaFuncAttributeMaxDynamicSharedMemorySize, K1_SMEM));
-    if (h->k1_small) { CK(cudaFuncSetAttribute(k1_inflate_small, cudaFuncAttributeMaxDynamicSharedMemorySize, K1S_SMEM)); CK(cudaFuncSetAttribute(k1_inflate_small, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)); }
+    CK(cudaFuncSetAttribute(k1_fallback, cudaFuncAttributeMaxDynamicSharedMemorySize, K1_SMEM));
+    CK(cudaFuncSetAttribute(k1_huff<false, 4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)); CK(cudaFuncSetAttribute(k1_huff<false, 6>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CK(cudaFuncSetAttribute(k1_huff<true, 5>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)); CK(cudaFuncSetAttribute(k1_huff<true, 4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    { const char* e = getenv("BDEPTH_K1H_VARIANT"); h->k1h_variant = e ? atoi(e) : 0; }      // A/B of the phase-1 instantiations (kernels.cuh)
+    { const char* e = getenv("BDEPTH_K3"); h->k3_tile = !(e && !strcmp(e, "gather")); }
+    CK(cudaFuncSetAttribute(k3_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K3T_SMEM)); CK(cudaFuncSetAttribute(k3_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K3T_SMEM));
+    { const char* e = getenv("BDEPTH_K1_ONEPHASE"); h->k1_onephase = e && atoi(e) == 1; }
+    { const char* e = getenv("BDEPTH_K3_PREFETCH"); h->k3_pre = !e || atoi(e) != 0; }      // default since round 2: measured 10.4 -> 8.4 ms on chr20 (profiles/k3_history.md)
     return 0;
 }
 
@@ -325,7 +331,8 @@ int prepare_shard(bdepth* h) {
     h->limit_abs_u = end_u; h->own_lo_abs_u = start_u;
     if (end_u >= h->total_u) h->blk_hi = B.size();
     else h->blk_hi = std::min(B.size(), block_of_u(end_u) + 1 + (h->fix_mates ? MATE_ZONE_BLOCKS : SHARD_EXTRA_BLOCKS));
-    if (h->fix_mates && h->world > 1 && h->rank > 0) {
+    h->zone_lin_lo = UINT64_MAX;
+    if (h->world > 1 && h->rank > 0) {      // (with -m: the same zone, read for the mate kernels; without: its reads are counted where they reach into this rank's positions)
         // The zone before the shard.  The BAI linear index holds, per 16 kbp window, the first record that overlaps the window:
         // starting at the entry of the window of the shard's first read includes every read that overlaps any column at or
         // after that window's start, i.e. every read the rank's own components and their columns can involve.
@@ -342,6 +349,7 @@ int prepare_shard(bdepth* h) {
                     uint64_t zu = B[b].uoff + (vo & 0xFFFF);
                     if (zu < h->hdr.first_rec_off) zu = h->hdr.first_rec_off;
                     if (zu < start_u) { h->blk_lo = block_of_u(zu); h->entry0 = (int64_t)(zu - B[h->blk_lo].uoff); }
+                    h->zone_lin_lo = h->hdr.ref_lin0[ref] + ((uint64_t)w << 14);      // this rank's own positions begin at or after the first record's position, i.e. inside this window
                 }
             }
         }
@@ -358,6 +366,7 @@ struct Emitter {
     bdepth* h; bdepth_tile_cb cb; void* user;
     struct Range { uint64_t a, b; };
     std::vector<Range> ranges; size_t ri = 0; uint64_t pos = 0; bool started = false;
+    uint64_t lo_clip = 0, hi_clip = UINT64_MAX;      // several ranks: only the positions this rank owns are delivered
     struct Slot { uint64_t a = 0, b = 0; } slot[2];
     int head = 0, inflight = 0;
     uint64_t d2h_bytes = 0;
@@ -397,10 +406,11 @@ struct Emitter {
         if (!started) { started = true; if (!ranges.empty()) pos = ranges[0].a; }
         while (ri < ranges.size()) {
             const Range& r = ranges[ri];
-            uint64_t a = std::max(pos, r.a);
-            if (a >= r.b) { ri++; if (ri < ranges.size()) pos = ranges[ri].a; continue; }
+            const uint64_t rb = std::min(r.b, hi_clip);
+            uint64_t a = std::max(std::max(pos, r.a), lo_clip);
+            if (a >= rb) { if (r.b > hi_clip) break; ri++; if (ri < ranges.size()) pos = ranges[ri].a; continue; }      // (nothing beyond hi_clip is this rank's)
             if (a >= limit) break;
-            uint64_t b = std::min(std::min(r.b, limit), a + (uint64_t)chunk());
+            uint64_t b = std::min(std::min(rb, limit), a + (uint64_t)chunk());
             if (inflight == 2) { int rc = deliver_oldest(); if (rc) return rc; }
             int rc = issue(head, a, b); if (rc) return rc;
             head ^= 1; inflight++; pos = b;
@@ -419,7 +429,7 @@ __global__ void k_add_u32(uint32_t* __restrict__ dst, const uint32_t* __restrict
 // read starts at or before p; every rank sends the part of its counters that lies in a later rank's range
 // (7 planes, packed) with ncclSend/ncclRecv inside one group, and the owner adds it.  One all-gather of
 // (min_start, max_end) per rank tells everybody the ranges.  Also reduces the per-reference "has reads" bits.
-int exchange_boundaries(bdepth* h, uint64_t shard_min, uint64_t shard_max) {
+int exchange_boundaries(bdepth* h, uint64_t shard_min, uint64_t shard_max, bool with_counters) {
     NcclApi& N = nccl(); cudaStream_t sm = h->s_main; const int W = h->world, me = h->rank;
     cudaEvent_t e0 = h->ev[12], e1 = h->ev[13];
     CK(cudaEventRecord(e0, sm));
@@ -431,12 +441,16 @@ int exchange_boundaries(bdepth* h, uint64_t shard_min, uint64_t shard_max) {
     CK(cudaMemcpyAsync(all.data(), dall.p, 16 * (size_t)W, cudaMemcpyDeviceToHost, sm));
     CK(cudaStreamSynchronize(sm));
     auto nonempty = [&](int r) { return all[2 * r] != UINT64_MAX; };
-    auto own_lo = [&](int r) -> uint64_t { for (int q = 0; q < r; q++) if (nonempty(q)) return all[2 * r]; return 0; };   // first non-empty rank owns from 0
+    auto own_lo = [&](int r) -> uint64_t { return r == 0 ? 0 : all[2 * r]; };      // rank 0 owns from 0 (whether it has reads or not): every rank knows where its own positions begin before it has heard of the others
     auto own_hi = [&](int r) -> uint64_t { for (int q = r + 1; q < W; q++) if (nonempty(q)) return all[2 * q]; return h->hdr.total_len; };
     struct Xfer { int peer; uint64_t lo, hi; };
     std::vector<Xfer> sends, recvs;
+    // with_counters == false (plain shards without -m): every rank has counted the reads of the previous ranks' zone itself, so its own
+    // positions are complete and only the table of boundaries is exchanged
+    if (with_counters) {
     if (nonempty(me)) for (int j = me + 1; j < W; j++) if (nonempty(j) && all[2 * j] < shard_max) { uint64_t lo = std::max(all[2 * j], shard_min), hi = std::min(shard_max, own_hi(j)); if (lo < hi) sends.push_back({j, lo, hi}); }
     if (nonempty(me)) for (int i = 0; i < me; i++) if (nonempty(i) && all[2 * i + 1] > all[2 * me]) { uint64_t lo = std::max(all[2 * me], all[2 * i]), hi = std::min(all[2 * i + 1], own_hi(me)); if (lo < hi) recvs.push_back({i, lo, hi}); }
+    }
     uint64_t tot = 0; for (auto& x : sends) tot += x.hi - x.lo; uint64_t sent = tot; for (auto& x : recvs) tot += x.hi - x.lo;
     const int NP = N_PLANES * (int)h->S;      // all counter planes of all samples
     DevBuf stage; CK(stage.ensure((size_t)std::max<uint64_t>(tot, 1) * NP * 4));
@@ -474,7 +488,7 @@ int exchange_boundaries(bdepth* h, uint64_t shard_min, uint64_t shard_max) {
     CK(cudaEventRecord(e1, sm)); CK(cudaStreamSynchronize(sm));
     float t = 0; CK(cudaEventElapsedTime(&t, e0, e1)); h->st.ms_exchange = t; h->st.halo_bytes_sent = sent * NP * 4;
     // ownership: an empty rank owns nothing
-    if (nonempty(me)) { h->own_lo = own_lo(me); h->own_hi = own_hi(me); } else { h->own_lo = h->own_hi = 0; }
+    if (nonempty(me) || me == 0) { h->own_lo = own_lo(me); h->own_hi = own_hi(me); } else { h->own_lo = h->own_hi = 0; }
     dpair.release(); dall.release(); stage.release(); bits.release();
     return 0;
 }
@@ -584,7 +598,21 @@ int run_pipeline(bdepth* h, RunMode mode, RunOut* ro, Emitter* em = nullptr) {
     // span of the linear genome is allocated; without one the whole genome is (87 GB for GRCh38, fits 180 GB HBM).
     if (mode == RUN_FULL) {
         uint64_t lo = 0, hi = h->hdr.total_len;
-        if (h->bai.valid && h->bai_window_ok && h->bai.ioffsets.size() == nref && h->world == 1) {
+        if (h->bai.valid && h->bai_window_ok && h->bai.ioffsets.size() == nref && h->world > 1 && !sparse && !fix && blk_hi > blk_lo) {
+            // a shard: from the window in which its first record begins (its own positions begin there or later) to the end of the last
+            // 16 kbp window that any read before the shard's end overlaps (the linear index holds, per window, the first such read)
+            const uint64_t vo_end = blk_hi < B.size() ? (B[blk_hi].coff << 16) : (h->file_len << 16);
+            lo = h->rank == 0 ? UINT64_MAX : h->zone_lin_lo; hi = 0;
+            for (size_t r = 0; r < nref; r++) {
+                const auto& v = h->bai.ioffsets[r];
+                for (size_t k = 0; k < v.size(); k++) if (v[k] && v[k] < vo_end) {
+                    const uint64_t a = h->hdr.ref_lin0[r] + std::min<uint64_t>((uint64_t)k << 14, h->hdr.ref_len[r]), e = h->hdr.ref_lin0[r] + std::min<uint64_t>((uint64_t)(k + 1) << 14, h->hdr.ref_len[r]);
+                    if (h->rank == 0) lo = std::min(lo, a);
+                    if (e > hi) hi = e;
+                }
+            }
+            if (lo == UINT64_MAX || lo >= hi) { lo = 0; hi = h->hdr.total_len; }
+        } else if (h->bai.valid && h->bai_window_ok && h->bai.ioffsets.size() == nref && h->world == 1) {
             lo = UINT64_MAX; hi = 0;
             for (size_t r = 0; r < nref; r++) {
                 const auto& v = h->bai.ioffsets[r]; if (v.empty()) continue;
@@ -722,15 +750,17 @@ int run_pipeline(bdepth* h, RunMode mode, RunOut* ro, Emitter* em = nullptr) {
             d_comp = h->comp2[batch_no & 1].as<uint32_t>();
         }
         // ---- descriptors
-        std::vector<BlockDesc> d(nb); uint64_t csum = 0;
+        std::vector<BlockDesc> d(nb); uint64_t csum = 0, tok_words = 0;
         for (size_t i = 0; i < nb; i++) {
             const HostBlock& hb = B[b + i];
             uint64_t dev_off = h->staged ? hb.coff - h->staged_file_off : dco[batch_no & 1][i];
-            d[i] = BlockDesc{dev_off + hb.cdata_off, hb.uoff - batch_u0, hb.csize, hb.isize};
+            d[i] = BlockDesc{dev_off + hb.cdata_off, hb.uoff - batch_u0, hb.csize, hb.isize, tok_words};
+            tok_words += tok_cap_of(hb.isize);
             if (b + i >= new_b) { csum += hb.csize; st.file_bytes += hb.bsize; }
         }
         st.cdata_bytes += csum;
         CK(h->descs.ensure(nb * sizeof(BlockDesc))); CK(h->status.ensure(nb * sizeof(int))); CK(h->ubuf.ensure(CARRY_MAX + ub + 256));
+        if (!h->k1_onephase) { CK(h->tok.ensure(tok_words * 4 + 64)); CK(h->lits.ensure(ub + 16 * nb + 64)); CK(h->aux.ensure(nb * sizeof(BlockAux))); CK(h->segi.ensure(nb * MAX_SEG * 4)); CK(h->littab.ensure(nb * (size_t)MAX_SEG * 256)); }
         CK(hs.ensure(nb * (sizeof(BlockDesc) + 192) + 16384)); hs.used = 0;      // nothing is in flight here: every sub-batch ends synchronised
         UP(h->descs.p, d.data(), nb * sizeof(BlockDesc));
         uint8_t* u0 = h->ubuf.as<uint8_t>() + CARRY_MAX;     // offset 0 of this batch's inflated bytes
@@ -739,10 +769,27 @@ int run_pipeline(bdepth* h, RunMode mode, RunOut* ro, Emitter* em = nullptr) {
         std::vector<Sub> subs;
         // ---- K1: when the input is streaming in, one sub-launch per H2D chunk, spread over a few streams so that
         // they run side by side (a lone sub-launch cannot fill the GPU: every lane owns a whole BGZF block)
+        // K1 of blocks [c0, c0 + n) of the batch on stream ks: the two-phase inflater (k1_huff, k1_lz) and the exact one-phase kernel
+        // for whatever phase 1 handed back (normally nothing: it returns at once); BDEPTH_K1_ONEPHASE=1 runs the round-1 kernel alone (A/B)
+        auto launch_k1 = [&](cudaStream_t ks, size_t c0, uint32_t n) -> int {
+            const BlockDesc* dd = h->descs.as<BlockDesc>() + (c0 - b); int* stp = h->status.as<int>() + (c0 - b);
+            if (h->k1_onephase) {
+                BD_LAUNCH((n + 32 * K1_WARPS - 1) / (32 * K1_WARPS), 32 * K1_WARPS, K1_SMEM, ks, k1_inflate)(d_comp, dd, n, u0, stp);
+                CK(cudaGetLastError()); st.gpu_launches++;
+                return 0;
+            }
+            BlockAux* ax = h->aux.as<BlockAux>() + (c0 - b); uint32_t* sgi = h->segi.as<uint32_t>() + (c0 - b) * MAX_SEG; uint8_t* ltb = h->littab.as<uint8_t>() + (c0 - b) * (size_t)MAX_SEG * 256;
+            const unsigned hg = (n + 32 * K1H_WARPS - 1) / (32 * K1H_WARPS); const uint32_t blk0 = (uint32_t)(c0 - b);
+#define K1H(LIMS, MINB) BD_LAUNCH(hg, 32 * K1H_WARPS, k1h_smem<LIMS>(), ks, k1_huff<LIMS, MINB>)(d_comp, dd, n, blk0, stp, h->tok.as<uint32_t>(), h->lits.as<uint8_t>(), ax, sgi, ltb)
+            switch (h->k1h_variant) { case 1: K1H(false, 6); break; case 2: K1H(true, 5); break; case 3: K1H(true, 4); break; default: K1H(false, 4); }
+#undef K1H
+            BD_LAUNCH((n + K1L_WARPS - 1) / K1L_WARPS, 32 * K1L_WARPS, 0, ks, k1_lz)(dd, n, blk0, u0, stp, h->tok.as<uint32_t>(), h->lits.as<uint8_t>(), ax, sgi, ltb);
+            BD_LAUNCH((n + 32 * K1_WARPS - 1) / (32 * K1_WARPS), 32 * K1_WARPS, K1_SMEM, ks, k1_fallback)(d_comp, dd, n, u0, stp);
+            CK(cudaGetLastError()); st.gpu_launches += 3;
+            return 0;
+        };
         if (h->staged) {
-            if (h->k1_lit3) BD_LAUNCH((unsigned)((nb + 32 * K1_WARPS - 1) / (32 * K1_WARPS)), 32 * K1_WARPS, K1_SMEM, sm, k1_inflate_lit3)(d_comp, h->descs.as<BlockDesc>(), (uint32_t)nb, u0, h->status.as<int>());
-            else BD_LAUNCH((unsigned)((nb + 32 * K1_WARPS - 1) / (32 * K1_WARPS)), 32 * K1_WARPS, K1_SMEM, sm, k1_inflate)(d_comp, h->descs.as<BlockDesc>(), (uint32_t)nb, u0, h->status.as<int>());
-            CK(cudaGetLastError()); st.gpu_launches++;
+            { int rck = launch_k1(sm, b, (uint32_t)nb); if (rck) return rck; }
             subs.push_back(Sub{b, b1, 0, -1});
         } else {
             int slot = (int)(batch_no & 1); size_t c0 = b;
@@ -750,10 +797,7 @@ int run_pipeline(bdepth* h, RunMode mode, RunOut* ro, Emitter* em = nullptr) {
                 size_t c1 = h->chunk_end[slot][j]; cudaStream_t ks = h->s_k1[j & 15];
                 CK(cudaStreamWaitEvent(ks, e1, 0)); CK(cudaStreamWaitEvent(ks, h->chunk_ev[slot][j], 0));
                 uint32_t n = (uint32_t)(c1 - c0);
-                if (h->k1_lit3) BD_LAUNCH((n + 32 * K1_WARPS - 1) / (32 * K1_WARPS), 32 * K1_WARPS, K1_SMEM, ks, k1_inflate_lit3)(d_comp, h->descs.as<BlockDesc>() + (c0 - b), n, u0, h->status.as<int>() + (c0 - b));
-                else if (h->k1_small) BD_LAUNCH((n + 32 * K1S_WARPS - 1) / (32 * K1S_WARPS), 32 * K1S_WARPS, K1S_SMEM, ks, k1_inflate_small)(d_comp, h->descs.as<BlockDesc>() + (c0 - b), n, u0, h->status.as<int>() + (c0 - b));
-                else BD_LAUNCH((n + 32 * K1_WARPS - 1) / (32 * K1_WARPS), 32 * K1_WARPS, K1_SMEM, ks, k1_inflate)(d_comp, h->descs.as<BlockDesc>() + (c0 - b), n, u0, h->status.as<int>() + (c0 - b));
-                CK(cudaGetLastError()); st.gpu_launches++;
+                { int rck = launch_k1(ks, c0, n); if (rck) return rck; }
                 if (h->k1_ev.size() <= j) { cudaEvent_t ne; CK(cudaEventCreateWithFlags(&ne, cudaEventDisableTiming)); h->k1_ev.push_back(ne); }
                 CK(cudaEventRecord(h->k1_ev[j], ks));
                 // Sub-batches: a lane needs ~60 ms for its block however empty the GPU is, so the scan / coverage /
@@ -893,13 +937,14 @@ int run_pipeline(bdepth* h, RunMode mode, RunOut* ro, Emitter* em = nullptr) {
         size_t Rc = R ? R : 1;
         CK(h->soa_start.ensure(Rc * 8)); CK(h->soa_span.ensure(Rc * 4)); CK(h->soa_meta.ensure(Rc * 4)); CK(h->soa_off.ensure(Rc * 8)); CK(h->soa_ncl.ensure(Rc * 4)); CK(h->soa_lseq.ensure(Rc * 4)); CK(h->long_list.ensure(Rc * 4));
         RecordSoA soa{h->soa_start.as<uint64_t>(), h->soa_span.as<uint32_t>(), h->soa_meta.as<uint32_t>(), h->soa_off.as<int64_t>(), h->soa_ncl.as<uint32_t>(), h->soa_lseq.as<int32_t>()};
-        ScanStats zs{0, 0, 0, 0, ~0ull, 0, 0, ~0ull, 0, 0, ~0ull};
+        ScanStats zs{0, 0, 0, 0, ~0ull, 0, 0, ~0ull, 0, 0, ~0ull, 0, ~0ull};
         const int64_t ghost_below = (fix && batch_no > 0) ? (int64_t)ghost_below_abs - (int64_t)batch_u0 : INT64_MIN;
         const int64_t own_lo = (fix && h->world > 1) ? (int64_t)h->own_lo_abs_u - (int64_t)batch_u0 : INT64_MIN;           // -m on several ranks: records outside belong to the neighbours
         const int64_t own_hi = (fix && h->world > 1 && h->limit_abs_u < h->total_u) ? (int64_t)h->limit_abs_u - (int64_t)batch_u0 : INT64_MAX;
+        const int64_t zone_below = (!fix && !sparse && h->world > 1) ? (int64_t)h->own_lo_abs_u - (int64_t)batch_u0 : INT64_MIN;       // records of the previous ranks' zone
         UP(h->scan_stats.p, &zs, sizeof zs);
         if (mode == RUN_SCAN_ONLY && !h->ref_has.p) { CK(h->ref_has.ensure((nref / 32 + 2) * 4)); CK(cudaMemsetAsync(h->ref_has.p, 0, (nref / 32 + 2) * 4, sm)); }
-#define K2_DECODE(F, G) BD_LAUNCH((unsigned)((nb * 32 + 255) / 256), 256, 0, sm, k2_decode<F, G>)(sp, h->chunk_start.as<int64_t>(), (uint32_t)nb, h->slot_base.as<uint32_t>(), h->slots.as<uint16_t>(), h->count.as<uint32_t>(), h->rec_base.as<uint32_t>(), soa, h->mapq_gt, h->flag_reject, h->scan_stats.as<ScanStats>(), h->long_list.as<uint32_t>(), h->ref_has.as<uint32_t>(), rgt, d_fprog, ghost_below, own_lo, own_hi)
+#define K2_DECODE(F, G) BD_LAUNCH((unsigned)((nb * 32 + 255) / 256), 256, 0, sm, k2_decode<F, G>)(sp, h->chunk_start.as<int64_t>(), (uint32_t)nb, h->slot_base.as<uint32_t>(), h->slots.as<uint16_t>(), h->count.as<uint32_t>(), h->rec_base.as<uint32_t>(), soa, h->mapq_gt, h->flag_reject, h->scan_stats.as<ScanStats>(), h->long_list.as<uint32_t>(), h->ref_has.as<uint32_t>(), rgt, d_fprog, ghost_below, own_lo, own_hi, zone_below)
         if (fix) { if (d_fprog) K2_DECODE(true, true); else K2_DECODE(false, true); }
         else if (d_fprog) K2_DECODE(true, false);
         else K2_DECODE(false, false);
@@ -938,8 +983,9 @@ int run_pipeline(bdepth* h, RunMode mode, RunOut* ro, Emitter* em = nullptr) {
         }
         uint64_t idx_tiles_base = 0; uint32_t idx_n_tiles = 0;      // K3's per-tile read index of this sub-batch (the mate kernels look reads up through it)
         // ---- K3
-        if (mode == RUN_FULL && ss.n_pass) {
-            uint64_t gmin = ss.min_start, gmax = ss.max_end;
+        if (mode == RUN_FULL && (ss.n_pass || ss.n_zone_pass)) {
+            uint64_t gmin = std::min<uint64_t>(ss.min_start, ss.min_start_all), gmax = ss.max_end;
+            if (ss.n_zone_pass && gmin < h->cnt_base) gmin = h->cnt_base;      // a zone read may begin before the window; only what reaches this rank's positions matters
             if (gmin < h->cnt_base || gmax > h->cnt_base + h->win_len) {
                 // the index does not describe this file (the reference only checks that one exists, depth.d:1166):
                 // start over with the whole genome as the counter window
@@ -964,7 +1010,10 @@ int run_pipeline(bdepth* h, RunMode mode, RunOut* ro, Emitter* em = nullptr) {
                     else BD_LAUNCH((unsigned)((ss.n_long * 32 + 255) / 256), 256, 0, sm, k3_scatter_long<false>)(soa, u0, h->long_list.as<uint32_t>(), (uint32_t)ss.n_long, h->cnt_base, h->win_len, cnt, 0, sel);
                     CK(cudaGetLastError()); st.gpu_launches++;
                 }
-                if (h->k3_pre) {       // experiment, see kernels.cuh
+                if (h->k3_tile) {      // CTA per tile, shared-memory counters, records staged by cp.async.bulk
+                    if (h->minq) BD_LAUNCH((unsigned)n_tiles, 256, K3T_SMEM, sm, k3_tile<true>)(soa, u0, (int64_t)ub, (uint32_t)R, tiles_base, h->cnt_base, h->win_len, h->tile_first.as<uint32_t>(), h->tile_lo.as<uint32_t>(), cnt, h->minq, sel);
+                    else BD_LAUNCH((unsigned)n_tiles, 256, K3T_SMEM, sm, k3_tile<false>)(soa, u0, (int64_t)ub, (uint32_t)R, tiles_base, h->cnt_base, h->win_len, h->tile_first.as<uint32_t>(), h->tile_lo.as<uint32_t>(), cnt, 0, sel);
+                } else if (h->k3_pre) {       // round-1 gather kernel with lane-parallel record prefetch (BDEPTH_K3=gather)
                     if (h->minq) BD_LAUNCH((unsigned)n_tiles, 256, 0, sm, k3_gather<true, true>)(soa, u0, tiles_base, h->cnt_base, h->win_len, h->tile_first.as<uint32_t>(), h->tile_lo.as<uint32_t>(), cnt, h->minq, sel);
                     else BD_LAUNCH((unsigned)n_tiles, 256, 0, sm, k3_gather<false, true>)(soa, u0, tiles_base, h->cnt_base, h->win_len, h->tile_first.as<uint32_t>(), h->tile_lo.as<uint32_t>(), cnt, 0, sel);
                 } else if (h->minq) BD_LAUNCH((unsigned)n_tiles, 256, 0, sm, k3_gather<true, false>)(soa, u0, tiles_base, h->cnt_base, h->win_len, h->tile_first.as<uint32_t>(), h->tile_lo.as<uint32_t>(), cnt, h->minq, sel);
@@ -1022,7 +1071,12 @@ int run_pipeline(bdepth* h, RunMode mode, RunOut* ro, Emitter* em = nullptr) {
             { float t = 0; CK(cudaEventElapsedTime(&t, em0, em1)); st.ms_mates += t; }
         }
         CK(cudaEventRecord(e4, sm));
-        if (em && mode == RUN_FULL && h->world == 1 && !fix && !last_batch && ss.n_pass) { int rce = em->advance(ss.max_start / TILE_POS * TILE_POS, e4); if (rce) return rce; }
+        // Progressive delivery: positions below the start of the sub-batch's last own read are final (the file is coordinate sorted).  Several ranks
+        // (plain shards): a rank's own positions begin at its first passing read -- known once such a read has been seen -- and the reads of the
+        // previous ranks that reach into them come first in its stream (the zone), so the same holds; where its positions end it learns at the end.
+        const bool zone_mode = h->world > 1 && h->comm && !fix && !sparse;
+        if (em && zone_mode && h->rank > 0 && shard_min != UINT64_MAX) em->lo_clip = shard_min;
+        if (em && mode == RUN_FULL && (h->world == 1 || (zone_mode && (h->rank == 0 || shard_min != UINT64_MAX))) && !fix && !last_batch && ss.n_pass) { int rce = em->advance(ss.max_start / TILE_POS * TILE_POS, e4); if (rce) return rce; }
         // ---- carry the incomplete tail record to the front of the next batch
         uint64_t new_carry = (uint64_t)((int64_t)ub - tail);
         // the file ends inside a record: readExact throws "not enough data in stream" (readrange.d:169); fewer than 4 left-over bytes end the stream quietly (:139-149)
@@ -1054,7 +1108,7 @@ int run_pipeline(bdepth* h, RunMode mode, RunOut* ro, Emitter* em = nullptr) {
     st.positions = mode == RUN_FULL ? h->hdr.total_len : 0;
     h->own_lo = 0; h->own_hi = h->hdr.total_len;
     if (mode == RUN_FULL) {
-        if (h->world > 1 && h->comm) { rc = exchange_boundaries(h, shard_min, shard_max); if (rc) return rc; }
+        if (h->world > 1 && h->comm) { rc = exchange_boundaries(h, shard_min, shard_max, sparse || fix); if (rc) return rc; }      // plain shards: the boundary table only (every rank counted its zone)
         h->ref_has_host.assign(nref / 32 + 2, 0);
         CK(cudaMemcpyAsync(h->ref_has_host.data(), h->ref_has.p, (nref / 32 + 2) * 4, cudaMemcpyDeviceToHost, sm));
     }
@@ -1128,7 +1182,7 @@ int bdepth_open_memory(const void* bam, size_t bam_len, const void* bai, size_t 
 void bdepth_close(bdepth_t* h) {
     if (!h) return;
     cudaSetDevice(h->device);
-    h->anchors_idx.release(); h->anchors_val.release(); h->chunk_limit.release();
+    h->anchors_idx.release(); h->anchors_val.release(); h->chunk_limit.release(); h->tok.release(); h->lits.release(); h->aux.release(); h->segi.release(); h->littab.release();
     DevBuf* bufs[] = {&h->comp, &h->descs, &h->status, &h->ubuf, &h->chunk_start, &h->entry, &h->exitb, &h->count, &h->slot_base, &h->slots, &h->rec_base, &h->walk_list, &h->soa_start, &h->soa_span, &h->soa_meta, &h->soa_off, &h->soa_ncl, &h->soa_lseq, &h->long_list, &h->tile_first, &h->tile_lo, &h->counts, &h->ref_len_d, &h->ref_lin0_d, &h->scan_stats, &h->ref_has, &h->misc};
     for (DevBuf* b : bufs) b->release();
     h->rg_ids.release(); h->rg_offs.release(); h->rg_samp.release();
@@ -1277,11 +1331,7 @@ int bdepth_run_base(bdepth_t* h, bdepth_tile_cb cb, void* user) {
       if (cb2 > ca) { BD_LAUNCH(COUNT_GRID, 256, 0, sm, k_count_covered)(h->counts.as<uint32_t>(), h->win_len, ca, cb2, (unsigned long long*)h->misc.p, N_PLANES * (int)h->S); CK(cudaGetLastError()); h->st.gpu_launches++; } }
     unsigned long long cov = 0; CK(cudaMemcpyAsync(&cov, h->misc.p, 8, cudaMemcpyDeviceToHost, sm));
     CK(cudaEventRecord(e0, sm));
-    if (h->world > 1) {   // multi-GPU: ranks deliver disjoint, ordered pieces: clip the not-yet-delivered ranges to the owned range
-        std::vector<Emitter::Range> clipped;
-        for (auto& r : em.ranges) { uint64_t a = std::max(r.a, h->own_lo), b = std::min(r.b, h->own_hi); if (a < b) clipped.push_back({a, b}); }
-        em.ranges = clipped; em.ri = 0; em.started = false;
-    }
+    if (h->world > 1) { em.lo_clip = h->own_lo; em.hi_clip = h->own_hi; }      // multi-GPU: ranks deliver disjoint, ordered pieces (what was delivered on the way lies inside)
     rc = em.advance(UINT64_MAX, e0); if (rc) { em.finish(); return rc; }
     rc = em.finish(); if (rc) return rc;
     CK(cudaEventRecord(e1, h->s_d2h)); CK(cudaStreamSynchronize(h->s_d2h)); CK(cudaStreamSynchronize(sm));

@@ -206,6 +206,8 @@ struct BitReader {
     void refill() { if (bc <= 32) { bb |= (uint64_t)nw << bc; bc += 32; nw = *++wp; } }
     bool overrun() const { return wp > wend + 3; }
 #endif
+    BD_HD uint32_t lo32() const { return (uint32_t)bb; }
+    BD_HD void align_byte() { drop(bc & 7); }
     BD_HD uint32_t peek(int n) const { return (uint32_t)bb & ((1u << n) - 1u); }
     BD_HD void drop(int n) { bb >>= n; bc -= n; }
     BD_HD uint32_t get(int n) { uint32_t v = peek(n); drop(n); return v; }
@@ -323,7 +325,8 @@ BD_HD int decode_sym(const Tab& t, const HuffPk& lim, BitReader& br) {
 
 // Read the dynamic-block header and produce lens[] (RFC 1951 3.2.7).  lens must hold 320 bytes.
 // The 19-symbol code-length code lives entirely in registers.
-BD_HD int read_dynamic_lens(BitReader& br, uint8_t* lens, int& nlen, int& ndist) {
+template <class BR>
+BD_HD int read_dynamic_lens(BR& br, uint8_t* lens, int& nlen, int& ndist) {
     br.refill();
     nlen = (int)br.get(5) + 257;
     ndist = (int)br.get(5) + 1;
@@ -355,7 +358,7 @@ BD_HD int read_dynamic_lens(BitReader& br, uint8_t* lens, int& nlen, int& ndist)
     int n = 0, total = nlen + ndist;
     while (n < total) {
         br.refill();
-        uint32_t rev7 = bitrev32((uint32_t)br.bb) >> 25;
+        uint32_t rev7 = bitrev32(br.lo32()) >> 25;
         int L = 1;
 #pragma unroll
         for (int j = 1; j <= 6; j++) L += (rev7 >= lim[j]) ? 1 : 0;
@@ -402,8 +405,10 @@ enum { ST_HDR = 0, ST_SYM = 1, ST_STORED = 2, ST_DONE = 3 };
 // the lanes still decoding: it is both the reconvergence point and the next iteration's mask.
 #if defined(__CUDA_ARCH__)
 #define BD_BALLOT(mask, pred) __ballot_sync((mask), (pred))
+#define BD_SYNCWARP(mask) __syncwarp(mask)
 #else
 #define BD_BALLOT(mask, pred) ((pred) ? 1u : 0u)
+#define BD_SYNCWARP(mask) ((void)0)
 #endif
 
 // Output assembly state: `cur` holds the bytes of the word being filled (absolute alignment).

@@ -23,6 +23,7 @@
 #include "launch.cuh"
 #include <stdint.h>
 #include "inflate_core.cuh"
+#include "inflate2_core.cuh"
 #include "filter.cuh"
 
 namespace bdk {
@@ -41,7 +42,14 @@ struct BlockDesc {
     uint64_t uoff;      // byte offset of the output inside the inflated buffer
     uint32_t csize;
     uint32_t isize;
+    uint64_t tok_off;   // first word of the block's token area (two-phase K1; capacity tok_cap_of(isize) words)
 };
+// Token area per block: a match is at least 3 bytes, so isize / 3 tokens is the worst case; BAM data needs about isize / 9.
+// A block that needs more than isize / 4 takes the one-phase fallback instead of everybody paying for the worst case.
+BD_HD uint32_t tok_cap_of(uint32_t isize) { return isize / 4u + 16u; }
+struct BlockAux { uint32_t n_tok, n_seg, n_lit, pad; };      // what phase 1 found in the block
+// Literal area of block i of a batch (16-byte aligned, >= isize bytes, disjoint from its neighbours'): derived from the output offset.
+BD_HD uint64_t lit_off_of(uint64_t uoff, uint64_t block_index) { return (uoff & ~15ull) + 16ull * block_index; }
 
 // One CTA of 13 warps per SM: 13 x 17,664 B = 229,632 B of dynamic shared memory (the per-CTA 1 KB system
 // reservation is paid once, which is what lets a 13th warp fit).  148 x 13 x 32 = 61,568 BGZF blocks in flight:
@@ -56,7 +64,7 @@ __global__ void __launch_bounds__(K1_WARPS * 32, 1) k1_inflate(const uint32_t* _
     uint32_t b = (blockIdx.x * K1_WARPS + warp) * 32u + lane;
     uint32_t scratch[96];
     const bool active = b < n_blocks;
-    BlockDesc d = active ? blocks[b] : BlockDesc{0, 0, 0, 0};
+    BlockDesc d = active ? blocks[b] : BlockDesc{0, 0, 0, 0, 0};
     uint32_t* wbase = smem + warp * (SMEM_BYTES_PER_WARP / 4);
     SmemTab tab{wbase + lane, (uint32_t)__cvta_generic_to_shared(wbase + T_WORDS * 32) + lane * 16, (uint32_t)__cvta_generic_to_shared(wbase + T_FAR * 32 + lane)};
     ByteOut out{u};
@@ -64,43 +72,185 @@ __global__ void __launch_bounds__(K1_WARPS * 32, 1) k1_inflate(const uint32_t* _
     if (active) status[b] = rc;
 }
 
-// EXPERIMENT (off by default, BDEPTH_K1_STREAM_WARPS=4): the same lane logic in 4-warp CTAs, three of which fit one SM
-// (3 x 70,656 B of shared memory).  When the input is streaming in, a K1 sub-launch of one H2D chunk is 208 warps:
-// as 16 CTAs of 13 warps it fills 16 SMs to the brim and every lane runs at the full-SM pace (~50 ms per block)
-// while 130 SMs idle; as 52 CTAs of 4 warps the block scheduler spreads it over 52 SMs with one warp per
-// scheduler, where a lane runs at close to its lone pace (26.7 ms), and SMs only fill up as later chunks arrive.
-// Same total throughput once the GPU is full (12 instead of 13 warps per SM), shorter drain after the last byte.
-// Never measured: DESIGN.md section 10.
-constexpr int K1S_WARPS = 4;
-constexpr int K1S_SMEM = K1S_WARPS * SMEM_BYTES_PER_WARP;       // 70,656 B
-__global__ void __launch_bounds__(K1S_WARPS * 32, 3) k1_inflate_small(const uint32_t* __restrict__ comp, const BlockDesc* __restrict__ blocks,
-                                                                      uint32_t n_blocks, uint8_t* __restrict__ u, int* __restrict__ status) {
+
+// ------------------------------------------------------------------------------------- K1, two phases (inflate2_core.cuh)
+// Phase 1: one lane per BGZF block, Huffman decoding only.  256 (+64) B of shared memory per lane and no output window:
+// 4-warp CTAs, several per SM; the block scheduler spreads a chromosome's 450 CTAs evenly.
+constexpr int K1H_WARPS = 4;
+template <bool LIMS> constexpr int k1h_smem() { return K1H_WARPS * (H_SMEM_BYTES_PER_WARP + (LIMS ? H_LIM_BYTES_PER_WARP : 0)); }      // 32 KB / 40 KB
+// LIMS / MINB: where the Huffman limits live and how many CTAs per SM the register allocation aims at -- the variants
+// measured against each other in profiles/k1_history.md.  blk0: index of blocks[0] in the batch (literal areas are per batch).
+template <bool LIMS, int MINB>
+__global__ void __launch_bounds__(K1H_WARPS * 32, MINB) k1_huff(const uint32_t* __restrict__ comp, const BlockDesc* __restrict__ blocks, uint32_t n_blocks, uint32_t blk0,
+                                                                int* __restrict__ status, uint32_t* __restrict__ tok, uint8_t* __restrict__ lits, BlockAux* __restrict__ aux,
+                                                                uint32_t* __restrict__ seg_info, uint8_t* __restrict__ lit_tab) {
     BD_DYN_SMEM(uint32_t, smem);
     uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t b = (blockIdx.x * K1S_WARPS + warp) * 32u + lane;
+    uint32_t b = (blockIdx.x * K1H_WARPS + warp) * 32u + lane;
     uint32_t scratch[96];
     const bool active = b < n_blocks;
-    BlockDesc d = active ? blocks[b] : BlockDesc{0, 0, 0, 0};
-    uint32_t* wbase = smem + warp * (SMEM_BYTES_PER_WARP / 4);
-    SmemTab tab{wbase + lane, (uint32_t)__cvta_generic_to_shared(wbase + T_WORDS * 32) + lane * 16, (uint32_t)__cvta_generic_to_shared(wbase + T_FAR * 32 + lane)};
-    ByteOut out{u};
-    int rc = inflate_block(tab, comp, d.coff, d.csize, out, d.uoff, d.isize, scratch, active);
-    if (active) status[b] = rc;
+    BlockDesc d = active ? blocks[b] : BlockDesc{0, 0, 0, 0, 0};
+    constexpr int PER_WARP = (H_SMEM_BYTES_PER_WARP + (LIMS ? H_LIM_BYTES_PER_WARP : 0)) / 4;
+    uint32_t* wbase = smem + warp * PER_WARP;
+    uint32_t* limb = wbase + H_WORDS * 32 + (32 * RING_BYTES_PER_LANE) / 4;
+    SmemTab2 tab{wbase + lane, limb + lane * 4, (uint32_t)__cvta_generic_to_shared(wbase + H_WORDS * 32) + lane * 16};
+    HuffOut ho{tok + d.tok_off, tok_cap_of(d.isize), lits + lit_off_of(d.uoff, (uint64_t)blk0 + b), lit_tab + (size_t)b * (MAX_SEG * 256), seg_info + (size_t)b * MAX_SEG};
+    uint32_t n_tok = 0, n_seg = 0, n_lit = 0;
+    int rc = huff_phase<SmemTab2, LIMS>(tab, comp, d.coff, d.csize, d.isize, scratch, ho, n_tok, n_seg, n_lit, active);
+    if (active) { status[b] = rc; aux[b] = BlockAux{n_tok, n_seg, n_lit, 0u}; }
 }
 
-// EXPERIMENT (off by default, BDEPTH_K1_LIT3=1): k1_inflate with up to three literals per iteration (inflate_core.cuh LIT3).
-__global__ void __launch_bounds__(K1_WARPS * 32, 1) k1_inflate_lit3(const uint32_t* __restrict__ comp, const BlockDesc* __restrict__ blocks,
-                                                                    uint32_t n_blocks, uint8_t* __restrict__ u, int* __restrict__ status) {
+// Phase 2: one warp per BGZF block, 32 tokens at a time.  A warp scan of (literals + length) and of (literals) gives every
+// token its place in the output and in the packed literal stream.  (1) the group's literals: lanes stride over the packed
+// ranks (coalesced), find their token by a binary search over the 32 prefix sums in shared memory, translate through the
+// deflate block's rank -> byte table (shared memory) and store.  (2) the matches: lane = token; a source byte that lies
+// inside the group's own output range is resolved through the group's tokens (pointer jumping: a byte of match j is the
+// byte `distance_j` before it, repeated until the position is a literal or lies before the group), so all copies of a
+// group read only finished bytes and need no order among themselves; groups are separated by __syncwarp.  Distances
+// and sizes are validated here; a violation ends the block with the error zlib would report.
+// little-endian 32-bit load at any byte address (shared or global)
+__device__ __forceinline__ uint32_t ld_u32_any(const uint8_t* p) {
+    uintptr_t a = reinterpret_cast<uintptr_t>(p); const uint32_t* w = reinterpret_cast<const uint32_t*>(a & ~uintptr_t(3));
+    return __funnelshift_r(w[0], w[1], (uint32_t)(a & 3) * 8);
+}
+constexpr int K1L_WARPS = 8;
+#ifndef BDEPTH_EMULATE_SHIM
+__device__ __forceinline__ uint32_t warp_max_u32(uint32_t v) { return __reduce_max_sync(0xFFFFFFFFu, v); }
+#else
+static inline uint32_t warp_max_u32(uint32_t v) { return ~__reduce_min_sync(0xFFFFFFFFu, ~v); }
+static inline bool emu_k1lz_warp() { static const bool on = getenv("BDEPTH_EMU_K1LZ_WARP") && atoi(getenv("BDEPTH_EMU_K1LZ_WARP")) == 1; return on; }
+#endif
+__global__ void __launch_bounds__(K1L_WARPS * 32) k1_lz(const BlockDesc* __restrict__ blocks, uint32_t n_blocks, uint32_t blk0, uint8_t* __restrict__ u, int* __restrict__ status,
+                                                        const uint32_t* __restrict__ tok, const uint8_t* __restrict__ lits, const BlockAux* __restrict__ aux,
+                                                        const uint32_t* __restrict__ seg_info, const uint8_t* __restrict__ lit_tab) {
+    __shared__ uint32_t s_tab[K1L_WARPS][64];
+    __shared__ uint32_t s_il[K1L_WARPS][33], s_dl[K1L_WARPS][33];      // (one slot of slack: the stepping loop looks one token ahead)
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t b = blockIdx.x * K1L_WARPS + warp;
+    if (b >= n_blocks || status[b] != INF_OK) return;            // warp-uniform
+    const BlockDesc d = blocks[b]; const BlockAux ax = aux[b];
+    uint8_t* const ub = u + d.uoff;
+    const uint8_t* const lt = lits + lit_off_of(d.uoff, (uint64_t)blk0 + b);
+    const uint32_t* const sgi = seg_info + (size_t)b * MAX_SEG;
+    const uint8_t* const ltab = lit_tab + (size_t)b * (MAX_SEG * 256);
+#ifdef BDEPTH_EMULATE_SHIM
+    // TEST BUILD ONLY: a warp collective costs 32 fiber switches under the CPU emulation, which makes this kernel ~30x slower than
+    // the rest of the emulated pipeline.  The big emulated suites therefore run the serial restatement of phase 2 (one fiber per
+    // block); tests/test_emul_inflate.py runs the warp code below on every fixture with BDEPTH_EMU_K1LZ_WARP=1.
+    if (!emu_k1lz_warp()) {
+        if (lane == 0) { int rcs = lz_phase_serial(ub, d.isize, tok + d.tok_off, ax.n_tok, lt, ax.n_lit, ltab, sgi, ax.n_seg); if (rcs) status[b] = rcs; }
+        return;
+    }
+#endif
+    const uint8_t* const tb = reinterpret_cast<const uint8_t*>(s_tab[warp]);
+    // current deflate block (segment) of the literal stream: literals [seg_lo, seg_hi)
+    uint32_t sg = 0, seg_hi = ax.n_seg > 1 ? (sgi[1] & 0x7FFFFFFFu) : 0xFFFFFFFFu; bool seg_raw = ax.n_seg == 0 || (sgi[0] & SEG_RAW);
+    if (!seg_raw) { const uint32_t* tg = reinterpret_cast<const uint32_t*>(ltab); s_tab[warp][lane] = tg[lane]; s_tab[warp][lane + 32] = tg[lane + 32]; }
+    __syncwarp();
+    const uint32_t* tk = tok + d.tok_off;
+    uint32_t base = 0, lbase = 0;           // output position / literal index at which the group begins
+    int err = INF_OK;
+    for (uint32_t g = 0; g < ax.n_tok; g += 32) {
+        const uint32_t t = g + lane < ax.n_tok ? tk[g + lane] : TOK_NOMATCH;
+        const uint32_t lit = t & 0xFFu, len = (t >> 31) ? 0u : ((t >> 8) & 0xFFu) + 3u, dist = ((t >> 16) & 0x7FFFu) + 1u;
+        uint32_t incl = lit + len, il = lit;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, o), w = __shfl_up_sync(0xFFFFFFFFu, il, o); if ((int)lane >= o) { incl += v; il += w; } }
+        const uint32_t tot = __shfl_sync(0xFFFFFFFFu, incl, 31), totl = __shfl_sync(0xFFFFFFFFu, il, 31);
+        const uint32_t dlit = base + incl - len - lit, dst = dlit + lit;
+        {   // what zlib checks while it copies: "invalid distance too far back", output larger than ISIZE
+            const bool far = len && dist > dst;
+            if (__ballot_sync(0xFFFFFFFFu, far)) { err = INF_ERR_DIST; break; }
+            if (base + tot > d.isize || lbase + totl > ax.n_lit) { err = INF_ERR_OVERRUN; break; }
+        }
+        // ---- (1) literals of the group.  Lanes stride over the packed ranks four at a time (one unaligned word per lane and round:
+        // a group's ~130 literals are one round); the token a literal belongs to is found by a binary search over the 32
+        // inclusive counts in shared memory for the first of the four and by stepping for the others; rank -> byte through the
+        // deflate block's table in shared memory; byte stores (runs are a few bytes at arbitrary alignment).
+        if (totl) {
+            while (sg + 1 < ax.n_seg && lbase >= seg_hi) {        // the group begins in a later deflate block: its table
+                sg++; seg_hi = sg + 1 < ax.n_seg ? (sgi[sg + 1] & 0x7FFFFFFFu) : 0xFFFFFFFFu; seg_raw = (sgi[sg] & SEG_RAW) != 0;
+                __syncwarp();
+                if (!seg_raw) { const uint32_t* tg = reinterpret_cast<const uint32_t*>(ltab + sg * 256u); s_tab[warp][lane] = tg[lane]; s_tab[warp][lane + 32] = tg[lane + 32]; }
+                __syncwarp();
+            }
+            const bool one_seg = lbase + totl <= seg_hi;
+            s_il[warp][lane] = il; s_dl[warp][lane] = dlit;
+            __syncwarp();
+            for (uint32_t j0 = 4 * lane; j0 < totl; j0 += 128) {
+                const uint32_t w = ld_u32_any(lt + lbase + j0);
+                int lo = 0, hi = 31;                              // the first token whose inclusive literal count exceeds j0
+                while (lo < hi) { int mid = (lo + hi) >> 1; if (s_il[warp][mid] > j0) hi = mid; else lo = mid + 1; }
+                uint32_t tend = s_il[warp][lo], tbeg = lo ? s_il[warp][lo - 1] : 0u, tdst = s_dl[warp][lo];
+#pragma unroll
+                for (uint32_t bq = 0; bq < 4; bq++) {
+                    const uint32_t j = j0 + bq;
+                    if (j >= totl) break;
+                    while (j >= tend) { lo++; tbeg = tend; tend = s_il[warp][lo]; tdst = s_dl[warp][lo]; }      // (tokens without literals are stepped over)
+                    const uint32_t r = (w >> (8 * bq)) & 0xFFu;
+                    uint32_t v;
+                    if (one_seg) v = seg_raw ? r : (uint32_t)tb[r];
+                    else {                                        // the group straddles deflate blocks (at most MAX_SEG - 1 groups per block): table from global memory
+                        uint32_t s2 = sg; while (s2 + 1 < ax.n_seg && lbase + j >= (sgi[s2 + 1] & 0x7FFFFFFFu)) s2++;
+                        v = (sgi[s2] & SEG_RAW) ? r : (uint32_t)ltab[s2 * 256u + r];
+                    }
+                    ub[tdst + (j - tbeg)] = (uint8_t)v;
+                }
+            }
+            __syncwarp();
+        }
+        // ---- (2) matches of the group, in rounds.  Everything before the first match that has not been copied yet is final
+        // (all earlier matches, all literals of the group), so a match whose source bytes -- those it does not produce itself --
+        // end at or before that position can go now; the first pending match always can.  A lane copies its match front to back,
+        // four bytes at a time when the distance is at least four (then the four source bytes lie before the four it writes), byte
+        // by byte otherwise, so a match that overlaps its own source (distance < length) needs no special case.  Dependent
+        // matches (a record header copied from the previous record, which was itself copied) take another round.
+        {
+            const uint32_t need = len ? ((dst - dist + len < dst) ? dst - dist + len : dst) : 0u;       // end of the source bytes other lanes (or earlier groups) produce
+            uint8_t* dp = ub + dst; const uint8_t* sp = dp - dist;
+            unsigned pending = __ballot_sync(0xFFFFFFFFu, len != 0);
+            while (pending) {
+                const uint32_t ready = __shfl_sync(0xFFFFFFFFu, dst, __ffs(pending) - 1);
+                const bool go = ((pending >> lane) & 1u) && need <= ready;
+                const uint32_t ml = warp_max_u32(go ? len : 0u);
+                for (uint32_t k = 0; k < ml; k += 4) {
+                    if (!go || k >= len) continue;
+                    const uint32_t n = len - k < 4u ? len - k : 4u;
+                    if (dist >= 4) {
+                        const uint32_t w = ld_u32_any(sp + k);
+                        dp[k] = (uint8_t)w;
+                        if (n > 1) dp[k + 1] = (uint8_t)(w >> 8);
+                        if (n > 2) dp[k + 2] = (uint8_t)(w >> 16);
+                        if (n > 3) dp[k + 3] = (uint8_t)(w >> 24);
+                    } else for (uint32_t q = 0; q < n; q++) dp[k + q] = sp[k + q];
+                }
+                pending &= ~__ballot_sync(0xFFFFFFFFu, go);
+                __syncwarp();
+            }
+        }
+        base += tot; lbase += totl;
+    }
+    if (!err && (base != d.isize || lbase != ax.n_lit)) err = INF_ERR_SHORT;
+    if (err && lane == 0) status[b] = err;
+}
+
+// The exact one-phase decoder for the blocks phase 1 marked INF_FALLBACK (more than MAX_SEG deflate blocks, more tokens
+// than the token area holds).  Launched after every two-phase inflate; a warp without such a block returns at once.
+__global__ void __launch_bounds__(K1_WARPS * 32, 1) k1_fallback(const uint32_t* __restrict__ comp, const BlockDesc* __restrict__ blocks,
+                                                                uint32_t n_blocks, uint8_t* __restrict__ u, int* __restrict__ status) {
     BD_DYN_SMEM(uint32_t, smem);
     uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t b = (blockIdx.x * K1_WARPS + warp) * 32u + lane;
     uint32_t scratch[96];
-    const bool active = b < n_blocks;
-    BlockDesc d = active ? blocks[b] : BlockDesc{0, 0, 0, 0};
+    const bool active = b < n_blocks && status[b] == INF_FALLBACK;
+#ifndef BDEPTH_EMULATE_SHIM
+    if (!__any_sync(0xFFFFFFFFu, active)) return;
+#endif
+    BlockDesc d = active ? blocks[b] : BlockDesc{0, 0, 0, 0, 0};
     uint32_t* wbase = smem + warp * (SMEM_BYTES_PER_WARP / 4);
     SmemTab tab{wbase + lane, (uint32_t)__cvta_generic_to_shared(wbase + T_WORDS * 32) + lane * 16, (uint32_t)__cvta_generic_to_shared(wbase + T_FAR * 32 + lane)};
     ByteOut out{u};
-    int rc = inflate_block<SmemTab, ByteOut, true>(tab, comp, d.coff, d.csize, out, d.uoff, d.isize, scratch, active);
+    int rc = inflate_block(tab, comp, d.coff, d.csize, out, d.uoff, d.isize, scratch, active);
     if (active) status[b] = rc;
 }
 
@@ -213,6 +363,7 @@ struct ScanStats {      // device-side accumulators
     unsigned long long n_ghost;     // -m: records before the batch's own ones (re-read from the previous batch / the previous rank's zone), k2_decode<.., true>
     unsigned long long n_ghost_right;   // -m on several ranks: records at or after the shard limit (the next rank's zone)
     unsigned long long bad_rec;     // 1 + index of the first record whose name + CIGAR + sequence + qualities do not fit its block_size (~0: none)
+    unsigned long long n_zone_pass, min_start_all;      // several ranks without -m: passing reads of the previous ranks' zone; smallest start over own and zone reads
 };
 constexpr uint64_t START_UNPLACED = 0xFFFFFFFFFFFFFFFEull;      // RecordSoA.start of a record without a position on a known reference
 constexpr uint32_t NCL_GHOST = 1u << 31;      // RecordSoA.ncl: a record that is only re-read for the mate kernels and passes the filter (its pass bit is clear)
@@ -265,7 +416,8 @@ __global__ void k2_decode(ScanParams sp, const int64_t* __restrict__ chunk_start
                           const uint16_t* __restrict__ slots, const uint32_t* __restrict__ count, const uint32_t* __restrict__ rec_base,
                           RecordSoA soa, int mapq_gt, uint32_t flag_reject, ScanStats* __restrict__ st, uint32_t* __restrict__ long_list,
                           uint32_t* __restrict__ ref_has_reads, RgTable rg, const FilterProg* __restrict__ fprog /* compiled -F query, or nullptr: mapq_gt / flag_reject */,
-                          int64_t ghost_below, int64_t own_lo, int64_t own_hi) {
+                          int64_t ghost_below, int64_t own_lo, int64_t own_hi, int64_t zone_below /* several ranks without -m: records below this offset
+                          belong to the previous ranks' shards and are read only because they reach into this rank's positions: counted by K3, kept out of the statistics */) {
     uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= n_chunks) return;
     uint32_t n = count[warp];
@@ -274,7 +426,7 @@ __global__ void k2_decode(ScanParams sp, const int64_t* __restrict__ chunk_start
     uint32_t rb = rec_base[warp];
     unsigned long long loc_pass = 0, loc_cig = 0, loc_seq = 0, loc_maxend = 0, loc_minstart = ~0ull, loc_maxstart = 0;
     uint32_t has_word = 0xFFFFFFFFu, has_bits = 0;      // per-lane pending "reference has reads" bits (one atomic per warp, not per read)
-    unsigned long long loc_ghost = 0, loc_ghost_r = 0;
+    unsigned long long loc_ghost = 0, loc_ghost_r = 0, loc_zone = 0, loc_minall = ~0ull;
     for (uint32_t k = lane; k < n; k += 32) {
         int64_t o = ((k == 0 || c0 > 0) ? c0 : 0) + sl[k];
         const uint8_t* p = sp.u + o + 4;
@@ -319,11 +471,18 @@ __global__ void k2_decode(ScanParams sp, const int64_t* __restrict__ chunk_start
             const bool foreign = o < own_lo || o >= own_hi;
             if (foreign || o < ghost_below) { if (o >= own_hi) loc_ghost_r++; else loc_ghost++; if (pass) ghost_bit = NCL_GHOST | (foreign ? NCL_FOREIGN : 0u); pass = false; is_long = false; }
         }
+        const bool zone = !GHOST && o < zone_below;
+        if (zone) { loc_ghost++; if (pass) ghost_bit = NCL_FOREIGN; }
         soa.start[r] = start; soa.span[r] = span_eff;
         soa.meta[r] = (flag << 16) | (mapq << 8) | (sample << 2) | (pass ? 1u : 0u) | (is_long ? 2u : 0u);
         soa.off[r] = o + 4; soa.ncl[r] = (n_cigar << 8) | l_name | ghost_bit; soa.lseq[r] = l_seq;
-        loc_cig += n_cigar;
-        if (pass) {
+        if (!zone) loc_cig += n_cigar;
+        if (pass && zone) {      // a zone read: its extent bounds the tiles K3 has to visit; it is not one of this rank's reads otherwise
+            loc_zone++;
+            if (start < loc_minall) loc_minall = start;
+            if (start + span_eff > loc_maxend) loc_maxend = start + span_eff;
+            if (is_long) { uint32_t idx = (uint32_t)atomicAdd(&st->n_long, 1ull); long_list[idx] = r; }
+        } else if (pass) {
             loc_pass++; loc_seq += ((uint64_t)l_seq + 1) / 2;
             if (start + span_eff > loc_maxend) loc_maxend = start + span_eff;
             if (start < loc_minstart) loc_minstart = start;
@@ -333,7 +492,8 @@ __global__ void k2_decode(ScanParams sp, const int64_t* __restrict__ chunk_start
             if (is_long) { uint32_t idx = (uint32_t)atomicAdd(&st->n_long, 1ull); long_list[idx] = r; }
         }
     }
-    if (GHOST && loc_ghost) atomicAdd(&st->n_ghost, loc_ghost);       // per lane: only a batch's first blocks hold ghosts
+    if (loc_zone) { atomicAdd(&st->n_zone_pass, loc_zone); atomicMin(&st->min_start_all, loc_minall); }
+    if (loc_ghost) atomicAdd(&st->n_ghost, loc_ghost);       // per lane: only a batch's first blocks hold ghosts / zone records
     if (GHOST && loc_ghost_r) atomicAdd(&st->n_ghost_right, loc_ghost_r);
     {   // flush the has-reads bits: in the common case the whole warp saw one bitmap word -> one atomic
         uint32_t w0 = __shfl_sync(0xFFFFFFFFu, has_word, 0);
@@ -380,10 +540,12 @@ __global__ void k3_tile_index(RecordSoA soa, uint32_t R, uint64_t win_base, uint
     if (t_hi > (int64_t)n_tiles) t_hi = n_tiles;
     for (int64_t t = t_lo; t <= t_hi; t++) tile_first[t] = r;
     uint32_t m = soa.meta[r];
-    if ((m & 3u) == 1u && s >= win_base) {
+    if ((m & 3u) == 1u) {      // (a read of the previous rank's zone may begin before the first tile and still reach into it)
         uint64_t e = s + soa.span[r] - 1;
-        uint64_t ta = (s - win_base) / TILE_POS, tb = (e - win_base) / TILE_POS;
-        for (uint64_t t = ta; t <= tb && t < n_tiles; t++) atomicMin(&tile_lo[t], r);
+        if (e >= win_base) {
+            uint64_t ta = s >= win_base ? (s - win_base) / TILE_POS : 0, tb = (e - win_base) / TILE_POS;
+            for (uint64_t t = ta; t <= tb && t < n_tiles; t++) atomicMin(&tile_lo[t], r);
+        }
     }
 }
 
@@ -450,7 +612,7 @@ __global__ void __launch_bounds__(256) k3_gather(RecordSoA soa, const uint8_t* _
             int64_t off; uint32_t ncl, lseq;
             if (PRE) { off = __shfl_sync(0xFFFFFFFFu, off_l, bsel); ncl = __shfl_sync(0xFFFFFFFFu, ncl_l, bsel); lseq = __shfl_sync(0xFFFFFFFFu, lseq_l, bsel); }
             else { off = soa.off[rr]; ncl = soa.ncl[rr]; lseq = (uint32_t)max(soa.lseq[rr], 0); }
-            uint32_t n_cigar = ncl >> 8, l_name = ncl & 0xFF;
+            uint32_t n_cigar = (ncl >> 8) & 0xFFFFu, l_name = ncl & 0xFF;      // (bits 30-31 of ncl are the ghost / foreign marks)
             const uint8_t* rec = u + off;
             const uint8_t* cg = rec + 32 + l_name;
             const uint8_t* seq = cg + 4u * n_cigar;
@@ -528,6 +690,119 @@ __global__ void __launch_bounds__(256) k3_gather(RecordSoA soa, const uint8_t* _
     }
 }
 
+// ---- k3_tile: CTA per 1024-position tile, counters in shared memory, records staged by bulk async copy (TMA) ----------
+// The reads that can touch a tile are the records [tile_lo, tile_first[tile + 1]) of the sorted file, and they are
+// CONTIGUOUS in the inflated stream: one cp.async.bulk (UBLKCP, completion on an mbarrier) per chunk brings their bytes --
+// CIGARs, packed sequences, qualities -- into shared memory, instead of every warp chasing off -> CIGAR -> sequence
+// through dependent global loads per read (k3_gather: 190 instructions per read and 128-position window, long-scoreboard
+// bound).  A warp takes a record, walks its CIGAR (warp-uniform), lanes stride over the bases of an op clipped to the tile
+// and add into the 7 x 1024 shared-memory counters (ATOMS; the 32 lanes of a round hit 32 consecutive positions: no bank
+// conflicts).  One coalesced read-modify-write of the tile's counters at the end.  Reads longer than SPAN_SHORT stay with
+// k3_scatter_long.  A record that does not fit the stage on its own is read from global memory by the same code.
+constexpr uint32_t K3T_STAGE = 40 * 1024;                          // bytes of records staged per chunk
+constexpr uint32_t K3T_SMEM = N_PLANES * TILE_POS * 4 + K3T_STAGE + 64;      // 28,672 + 40,960 + 64 = 69,696 B -> 3 CTAs per SM
+#ifndef BDEPTH_EMULATE_SHIM
+__device__ __forceinline__ void mbar_init(uint32_t mbar_sa, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(mbar_sa), "r"(count) : "memory"); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_sa, const void* src, uint32_t bytes, uint32_t mbar_sa) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(mbar_sa), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" :: "r"(dst_sa), "l"(src), "r"(bytes), "r"(mbar_sa) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t mbar_sa, uint32_t parity) {
+    asm volatile("{\n.reg .pred p;\nWAIT_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}" :: "r"(mbar_sa), "r"(parity) : "memory");
+}
+#endif
+template <bool MINQ>
+__global__ void __launch_bounds__(256) k3_tile(RecordSoA soa, const uint8_t* __restrict__ u, int64_t u_end, uint32_t R, uint64_t tiles_base, uint64_t cnt_base, uint64_t win_len,
+                                               const uint32_t* __restrict__ tile_first, const uint32_t* __restrict__ tile_lo, uint32_t* __restrict__ counts, uint32_t minq, int sample_sel) {
+    BD_DYN_SMEM(uint8_t, smem_raw);
+    uint32_t* cnt = reinterpret_cast<uint32_t*>(smem_raw);                                  // [7][1024]
+    uint8_t* stage = smem_raw + N_PLANES * TILE_POS * 4;                                    // K3T_STAGE bytes, 16-byte aligned
+    __shared__ unsigned long long s_mbar; __shared__ uint32_t s_r1;
+    const uint32_t tile = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t lo = tile_lo[tile];
+    if (lo == 0xFFFFFFFFu) return;                        // no passing short read touches this tile
+    const uint32_t hi = tile_first[tile + 1];
+    const uint64_t t0 = tiles_base + (uint64_t)tile * TILE_POS;
+    for (uint32_t i = tid; i < N_PLANES * TILE_POS; i += 256) cnt[i] = 0;
+#ifndef BDEPTH_EMULATE_SHIM
+    const uint32_t mbar_sa = (uint32_t)__cvta_generic_to_shared(&s_mbar);
+    if (tid == 0) mbar_init(mbar_sa, 1);
+#endif
+    __syncthreads();
+    uint32_t parity = 0;
+    for (uint32_t r0 = lo; r0 < hi;) {
+        // ---- the chunk: records [r0, r1) whose bytes fit the stage (at least one record; a record larger than the stage is read in place)
+        const int64_t c0 = (int64_t)((reinterpret_cast<uintptr_t>(u) + (uintptr_t)(soa.off[r0] - 4)) & ~uintptr_t(15)) - (int64_t)reinterpret_cast<uintptr_t>(u);      // start of the chunk relative to u, at a 16-byte aligned ADDRESS
+        if (warp == 0) {
+            // largest r1 <= hi with end(r1 - 1) - c0 <= K3T_STAGE, end(r) = start of record r + 1 (or the end of the stream): binary search on the monotone offsets
+            uint32_t a = r0 + 1, b = hi;                               // r1 in [a, b]
+            while (a < b) { uint32_t m = (a + b + 1) >> 1; int64_t e = m < R ? soa.off[m] - 4 : u_end; if (e - c0 <= (int64_t)K3T_STAGE) a = m; else b = m - 1; }
+            if (lane == 0) s_r1 = a;
+        }
+        __syncthreads();
+        const uint32_t r1 = s_r1;
+        const int64_t c1 = r1 < R ? soa.off[r1] - 4 : u_end;
+        const bool staged = c1 - c0 <= (int64_t)K3T_STAGE;             // false only for a single oversized record
+        if (staged) {
+            const uint32_t bytes = (uint32_t)((c1 - c0 + 15) & ~int64_t(15));       // (the stream has >= 256 readable bytes behind its end)
+#ifndef BDEPTH_EMULATE_SHIM
+            if (tid == 0) bulk_g2s((uint32_t)__cvta_generic_to_shared(stage), u + c0, bytes, mbar_sa);
+            mbar_wait(mbar_sa, parity); parity ^= 1;
+#else
+            for (uint32_t i = tid; i < bytes; i += 256) stage[i] = u[c0 + i];
+            __syncthreads();
+#endif
+        }
+        const uint8_t* const rb = staged ? stage - c0 : u;             // record bytes: rb + off
+        for (uint32_t r = r0 + warp; r < r1; r += 8) {
+            const uint32_t mt = soa.meta[r];
+            if ((mt & 3u) != 1u || (sample_sel >= 0 && (int)((mt >> 2) & 63u) != sample_sel)) continue;
+            const uint64_t rs = soa.start[r]; const uint32_t rspan = soa.span[r];
+            if (rs >= t0 + TILE_POS || rs + rspan <= t0) continue;
+            const int64_t off = soa.off[r]; const uint32_t ncl = soa.ncl[r], lseq = (uint32_t)max(soa.lseq[r], 0);
+            const uint32_t n_cigar = (ncl >> 8) & 0xFFFFu, l_name = ncl & 0xFF;
+            const uint8_t* cg = rb + off + 32 + l_name; const uint8_t* seq = cg + 4u * n_cigar; const uint8_t* qual = seq + (lseq + 1) / 2;
+            // window of the read's reference offsets that fall into the tile: [w_lo, w_hi)
+            const uint32_t w_lo = rs < t0 ? (uint32_t)(t0 - rs) : 0u;
+            const uint32_t w_hi = (uint32_t)min((uint64_t)rspan, t0 + TILE_POS - rs);
+            const uint32_t pbase = (uint32_t)(rs - t0);                        // position in the tile of reference offset 0 (mod 2^32)
+            uint32_t rpos = 0, qpos = 0;
+            for (uint32_t i = 0; i < n_cigar && rpos < w_hi; i++) {
+                const uint32_t c = ld_u32_any(cg + 4 * i), len = c >> 4, op = c & 15;
+                if (cig_match(op)) {
+                    const uint32_t xa = rpos < w_lo ? w_lo - rpos : 0u, xb = min(len, w_hi - rpos);
+                    for (uint32_t x = xa + lane; x < xb; x += 32) {
+                        const uint32_t q = qpos + x;
+                        if (q >= lseq) break;
+                        if (MINQ) { if ((uint32_t)qual[q] < minq) continue; }
+                        const uint32_t b = seq[q >> 1], nib = (q & 1) ? (b & 15u) : (b >> 4);
+                        const uint32_t pl = (__popc(nib) == 1) ? (31 - __clz(nib)) : 4;        // nt16 -> nt5 (base.d:186)
+                        atomicAdd(&cnt[pl * TILE_POS + (pbase + rpos + x)], 1u);
+                    }
+                    rpos += len; qpos += len;
+                } else if (op == 2 || op == 3) {
+                    const uint32_t xa = rpos < w_lo ? w_lo - rpos : 0u, xb = min(len, w_hi - rpos);
+                    const uint32_t pl = op == 2 ? 5u : 6u;
+                    for (uint32_t x = xa + lane; x < xb; x += 32) atomicAdd(&cnt[pl * TILE_POS + (pbase + rpos + x)], 1u);
+                    rpos += len;
+                } else if (cig_qcons(op)) qpos += len;
+            }
+        }
+        __syncthreads();                                               // the stage is reused by the next chunk
+        r0 = r1;
+    }
+    // ---- add the tile's counters to the window (16-byte read-modify-writes; tiles are exclusive to their CTA)
+    const uint64_t idx0 = t0 - cnt_base;
+    if (idx0 + TILE_POS > win_len) return;
+    for (uint32_t i = tid; i < N_PLANES * TILE_POS / 4; i += 256) {
+        const uint4 v = reinterpret_cast<const uint4*>(cnt)[i];
+        if (!(v.x | v.y | v.z | v.w)) continue;
+        const uint32_t pl = i / (TILE_POS / 4), p4 = i % (TILE_POS / 4);
+        uint4* dst = reinterpret_cast<uint4*>(counts + (uint64_t)pl * win_len + idx0) + p4;
+        uint4 cur = *dst; cur.x += v.x; cur.y += v.y; cur.z += v.z; cur.w += v.w; *dst = cur;
+    }
+}
+
 // Long reads: one warp per read, lanes stride over the bases of each op, RED atomics.
 template <bool MINQ>
 __global__ void k3_scatter_long(RecordSoA soa, const uint8_t* __restrict__ u, const uint32_t* __restrict__ long_list, uint32_t n_long,
@@ -538,7 +813,7 @@ __global__ void k3_scatter_long(RecordSoA soa, const uint8_t* __restrict__ u, co
     if (sample_sel >= 0 && (int)((soa.meta[rr] >> 2) & 63u) != sample_sel) return;
     uint64_t rs = soa.start[rr]; uint32_t rspan = soa.span[rr];
     int64_t off = soa.off[rr]; uint32_t ncl = soa.ncl[rr]; uint32_t lseq = (uint32_t)max(soa.lseq[rr], 0);
-    uint32_t n_cigar = ncl >> 8, l_name = ncl & 0xFF;
+    uint32_t n_cigar = (ncl >> 8) & 0xFFFFu, l_name = ncl & 0xFF;      // (bits 30-31 of ncl are the ghost / foreign marks)
     const uint8_t* rec = u + off; const uint8_t* cg = rec + 32 + l_name; const uint8_t* seq = cg + 4u * n_cigar; const uint8_t* qual = seq + (lseq + 1) / 2;
     uint32_t rpos = 0, qpos = 0;
     for (uint32_t i = 0; i < n_cigar; i++) {
@@ -624,7 +899,7 @@ __global__ void k_read_segments(RecordSoA soa, const uint8_t* __restrict__ u, ui
                                 uint32_t* __restrict__ out_reads /* [n_samples][n_seg] */, uint32_t minq, uint32_t n_samples, uint32_t* __restrict__ out_bases_reads) {
     uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= R) return;
-    if (!(soa.meta[r] & 1u)) return;
+    if (!(soa.meta[r] & 1u) || (soa.ncl[r] & NCL_FOREIGN)) return;      // (a zone read is counted by the rank whose shard holds it)
     const uint32_t samp = n_samples > 1 ? ((soa.meta[r] >> 2) & 63u) : 0u;
     uint64_t rs = soa.start[r]; uint32_t rspan = soa.span[r]; uint64_t re = rs + rspan;
     // candidates: segments with seg_s < re ; walk down from the last such while pmax_end > rs
@@ -632,7 +907,7 @@ __global__ void k_read_segments(RecordSoA soa, const uint8_t* __restrict__ u, ui
     while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (seg_s[mid] < re) lo = mid + 1; else hi = mid; }
     if (lo == 0) return;
     int64_t off = soa.off[r]; uint32_t ncl = soa.ncl[r]; uint32_t lseq = (uint32_t)max(soa.lseq[r], 0);
-    uint32_t n_cigar = ncl >> 8, l_name = ncl & 0xFF;
+    uint32_t n_cigar = (ncl >> 8) & 0xFFFFu, l_name = ncl & 0xFF;      // (bits 30-31 of ncl are the ghost / foreign marks)
     const uint8_t* rec = u + off; const uint8_t* cg = rec + 32 + l_name; const uint8_t* qual = cg + 4u * n_cigar + (lseq + 1) / 2;
     for (int64_t k = (int64_t)lo - 1; k >= 0; k--) {
         if (pmax_end[k] <= rs) break;

@@ -32,7 +32,7 @@
 #define BD_NOINLINE __attribute__((noinline))
 #define __launch_bounds__(...)
 #define __restrict__
-#define __shared__ static
+#define __shared__ static thread_local      // (ranks are threads of one process under the emulation: every rank thread runs its own blocks)
 #define BD_HD inline
 #define BD_HD_COLD inline
 
@@ -77,6 +77,7 @@ static inline uint32_t __brev(uint32_t x) { x = ((x >> 1) & 0x55555555u) | ((x &
 static inline float __uint_as_float(uint32_t b) { float f; memcpy(&f, &b, 4); return f; }
 static inline size_t __cvta_generic_to_shared(const void* p) { return (size_t)(uintptr_t)p; }
 static inline void __syncthreads() { emu::syncthreads(); }
+static inline void __syncwarp(unsigned m = 0xFFFFFFFFu) { (void)emu::collective(m, 0, 0, 0); }
 static inline unsigned __ballot_sync(unsigned m, int p) { return (unsigned)emu::collective(m, p ? 1 : 0, 0, 0); }
 static inline int __all_sync(unsigned m, int p) { return (int)emu::collective(m, p ? 1 : 0, 6, 0); }
 static inline uint32_t __reduce_or_sync(unsigned m, uint32_t v) { return (uint32_t)emu::collective(m, v, 4, 0); }

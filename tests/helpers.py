@@ -30,6 +30,7 @@ def oracle():
         L.oracle_base_counts_fix_mates.argtypes = [C.c_char_p, C.c_int, C.c_uint, C.c_int, C.c_void_p, C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64)]
         L.oracle_bam_info.argtypes = [C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         L.oracle_last_error.restype = C.c_char_p
+        L.oracle_segment_stats.argtypes = [C.c_char_p, C.c_int, C.c_uint, C.c_int, C.c_int, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         _orc = L
     return _orc
 
@@ -69,6 +70,21 @@ def oracle_counts(path, mapq_gt=0, flag_reject=0x600, min_bq=0, threads=1, windo
     rc = L.oracle_base_counts(path.encode(), mapq_gt, flag_reject, min_bq, threads, 0, out.ctypes.data_as(C.c_void_p), a, max(1, b - a), C.byref(st))
     assert rc == 0, L.oracle_last_error()
     return out[:, :b - a], st
+
+
+def oracle_segment_stats(path, seg_a, seg_b, thresholds=(), mapq_gt=0, flag_reject=0x600, min_bq=0, threads=1):
+    """Closed-form region / window statistics for sorted, disjoint segments in linear coordinates:
+    (n_reads[n], n_bases[n], cov_ge[n_thr, n])."""
+    L = oracle()
+    a = np.ascontiguousarray(seg_a, np.uint64)
+    b = np.ascontiguousarray(seg_b, np.uint64)
+    n = len(a)
+    thr = np.ascontiguousarray(thresholds, np.uint32)
+    reads, bases, cov = np.zeros(max(1, n), np.uint32), np.zeros(max(1, n), np.uint32), np.zeros((max(1, len(thr)), max(1, n)), np.uint32)
+    rc = L.oracle_segment_stats(path.encode(), mapq_gt, flag_reject, min_bq, threads, n, a.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p), len(thr),
+                                thr.ctypes.data_as(C.c_void_p), reads.ctypes.data_as(C.c_void_p), bases.ctypes.data_as(C.c_void_p), cov.ctypes.data_as(C.c_void_p))
+    assert rc == 0, L.oracle_last_error()
+    return reads[:n], bases[:n], cov[:len(thr), :n]
 
 
 def oracle_counts_fix_mates(path, mapq_gt=0, flag_reject=0x600, min_bq=0, window=None):

@@ -160,3 +160,56 @@ def test_pileup_unittest_columns(tmp_path):
     for pos, r in rows.items():
         col = counts[:, pos]
         assert [int(col.sum()), col[0], col[1], col[2], col[3], col[5], col[6]] == r
+
+
+def _rows(out):
+    return [l.split("\t") for l in out.decode().splitlines() if l and not l.startswith("#")]
+
+
+def test_closed_form_segment_stats_equal_the_sweep(tmp_path):
+    """oracle_segment_stats (closed form: bench.py verifies full-size window / region runs with it) against the faithful sweep's
+    `depth window` and `depth region` output: readCount, meanCoverage (float32, %g) and the -T percentages, with and without -q."""
+    refs = [("chrA", 40000), ("chrB", 900), ("chrC", 25000)]
+    p = helpers.gen_bam(str(tmp_path / "s.bam"), "-r", "chrA:40000", "-r", "chrB:900", "-r", "chrC:25000", "-n", 9000, "-s", 5, "-t", 2)
+    lin0 = np.concatenate([[0], np.cumsum([l for _, l in refs])])
+    thr = [1, 5, 12]
+    for q in (0, 25):
+        qa = ["-q", str(q)] if q else []
+        # windows: every full 1000-bp window of every reference (all have reads)
+        rc, out, _ = helpers.oracle_cli(["window", "-w", "1000"] + sum((["-T", str(t)] for t in thr), []) + qa + [p])
+        assert rc == 0
+        rows = _rows(out)
+        name_to_i = {n: i for i, (n, _) in enumerate(refs)}
+        a = np.array([lin0[name_to_i[r[0]]] + int(r[1]) for r in rows], np.uint64)
+        b = np.array([lin0[name_to_i[r[0]]] + int(r[2]) for r in rows], np.uint64)
+        assert len(rows) == sum(l // 1000 for _, l in refs) and (np.diff(a.astype(np.int64)) > 0).all()
+        reads, bases, cov = helpers.oracle_segment_stats(p, a, b, thr, min_bq=q, threads=3)
+        for i, r in enumerate(rows):
+            ln = np.float32(int(b[i] - a[i]))
+            want = [str(int(reads[i])), "%g" % (np.float32(bases[i]) / ln)] + ["%g" % (np.float32(100) * np.float32(cov[t][i]) / ln) for t in range(len(thr))]
+            assert r[3:3 + 2 + len(thr)] == want, (q, i, r, want)
+        # regions from a BED file (sorted, disjoint)
+        rnd = np.random.RandomState(3)
+        bed = []
+        for ri, (n, l) in enumerate(refs):
+            x = 0
+            while True:
+                x += int(rnd.randint(1, 400))
+                e = x + int(rnd.randint(1, 700))
+                if e > l:
+                    break
+                bed.append((n, x, e))
+                x = e
+        bp = str(tmp_path / "r.bed")
+        open(bp, "w").write("".join(f"{n}\t{s}\t{e}\n" for n, s, e in bed))
+        rc, out, _ = helpers.oracle_cli(["region", "-L", bp] + sum((["-T", str(t)] for t in thr), []) + qa + [p])
+        assert rc == 0
+        rows = _rows(out)
+        assert len(rows) == len(bed)
+        a = np.array([lin0[name_to_i[n]] + s for n, s, e in bed], np.uint64)
+        b = np.array([lin0[name_to_i[n]] + e for n, s, e in bed], np.uint64)
+        reads, bases, cov = helpers.oracle_segment_stats(p, a, b, thr, min_bq=q, threads=2)
+        for i, r in enumerate(rows):
+            ln = np.float32(int(b[i] - a[i]))
+            want = [str(int(reads[i])), "%g" % (np.float32(bases[i]) / ln)] + ["%g" % (np.float32(100) * np.float32(cov[t][i]) / ln) for t in range(len(thr))]
+            assert r[3:3 + 2 + len(thr)] == want, (q, i, r, want)
