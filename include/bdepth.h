@@ -125,6 +125,11 @@ int  bdepth_open(const char* bam_path, int device, bdepth_t** out);
 int  bdepth_open_lazy(const char* bam_path, int device, bdepth_t** out);
 /* Open a BAM image held in host memory (pinned memory gives full-rate H2D).  bai may be NULL. */
 int  bdepth_open_memory(const void* bam, size_t bam_len, const void* bai, size_t bai_len, int device, bdepth_t** out);
+/* One more BAM whose reads are counted together with the handle's: new MultiBamReader(bam_filenames), depth.d:1162-1163,
+ * BioD/bio/std/hts/bam/multireader.d:244-268 (nWayUnion of the files' sorted streams).  The file needs the handle's reference
+ * dictionary; its @RG samples join the sample table (bdepth_n_samples / _sample_name afterwards).  bdepth_is_coordinate_sorted and
+ * bdepth_has_index then answer for all files.  Not with -m, not on several ranks.  Call before the first run. */
+int  bdepth_add_input(bdepth_t* h, const char* bam_path);
 void bdepth_close(bdepth_t* h);
 /* h == NULL returns the message of the last failed open on this thread. */
 const char* bdepth_last_error(const bdepth_t* h);

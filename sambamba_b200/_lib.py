@@ -71,6 +71,7 @@ def load_library():
     L.bdepth_open.argtypes = [C.c_char_p, C.c_int, C.POINTER(vp)]
     L.bdepth_open_lazy.argtypes = [C.c_char_p, C.c_int, C.POINTER(vp)]
     L.bdepth_open_memory.argtypes = [vp, C.c_size_t, vp, C.c_size_t, C.c_int, C.POINTER(vp)]
+    L.bdepth_add_input.argtypes = [vp, C.c_char_p]
     L.bdepth_close.argtypes = [vp]
     L.bdepth_close.restype = None
     L.bdepth_last_error.argtypes = [vp]
@@ -116,7 +117,7 @@ def load_library():
 
 
 EXPORTED_SYMBOLS = [
-    "bdepth_device_count", "bdepth_open", "bdepth_open_lazy", "bdepth_open_memory", "bdepth_close", "bdepth_last_error", "bdepth_n_ref",
+    "bdepth_device_count", "bdepth_open", "bdepth_open_lazy", "bdepth_open_memory", "bdepth_add_input", "bdepth_close", "bdepth_last_error", "bdepth_n_ref",
     "bdepth_ref_name", "bdepth_ref_length", "bdepth_header_text", "bdepth_is_coordinate_sorted", "bdepth_has_index",
     "bdepth_n_samples", "bdepth_sample_name", "bdepth_set_filter", "bdepth_set_filter_query", "bdepth_set_min_baseq", "bdepth_set_fix_mates", "bdepth_set_combined", "bdepth_set_regions",
     "bdepth_set_shard", "bdepth_nccl_unique_id", "bdepth_plan_shards", "bdepth_plan_region_chunks", "bdepth_set_tuning", "bdepth_stage", "bdepth_run_resident", "bdepth_run_base", "bdepth_run_base_text",
@@ -174,6 +175,9 @@ class BDepth:
         if rc < 0:
             raise BDepthError(rc, self.L.bdepth_last_error(self.h).decode())
         return rc
+
+    def add_input(self, path):
+        self._ck(self.L.bdepth_add_input(self.h, os.fsencode(path)))
 
     def close(self):
         if self.h:

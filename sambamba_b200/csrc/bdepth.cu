@@ -80,6 +80,7 @@ constexpr uint32_t SHARD_EXTRA_BLOCKS = 8;
 constexpr uint32_t MATE_ZONE_BLOCKS = 64;       // -m on several ranks: blocks read behind the shard so that pairs cut by the boundary are seen whole
 
 enum RunMode { RUN_FULL = 0, RUN_INFLATE_ONLY = 1, RUN_SCAN_ONLY = 2 };
+constexpr int RC_RETRY_WINDOW = 1;      // internal: a read lies outside the counter window a multi-input run was given
 
 // ---- NCCL, bound at run time (dlopen) so that single-GPU users need no NCCL at all and so that a host
 // process that already loaded NCCL (e.g. through torch) shares that one instance (same SONAME).
@@ -149,7 +150,7 @@ struct bdepth {
     bool bai_window_ok = true;            // cleared when the linear index turns out not to describe the file
     bool combined = false;                // --combined: one counter set for all samples
     bool fix_mates = false;               // -m: overlapping mates count once per column (mates.cuh)
-    int k1h_variant = 0;                  // BDEPTH_K1H_VARIANT: which instantiation of k1_huff runs (0: limits in registers, 4 CTAs/SM)
+    int k1h_variant = -1;                 // BDEPTH_K1H_VARIANT: which instantiation of k1_huff runs (-1: by launch size; 0: limits in registers, 4 CTAs/SM; 2: limits in shared memory, 5 CTAs/SM)
     bool k1_onephase = false;             // BDEPTH_K1_ONEPHASE=1: the round-1 one-phase K1 for every block (A/B against the two-phase inflater)
     bool k3_pre = false;                  // BDEPTH_K3_PREFETCH=0: k3_gather without the lane-parallel record prefetch
     bool k3_tile = true;                  // BDEPTH_K3=gather: the round-1 per-position gather kernel instead of k3_tile
@@ -191,6 +192,13 @@ struct bdepth {
     std::vector<uint32_t> ref_has_host;
     // ---- optional per-read segment counting (window / region front ends), device arrays
     struct SegSet { bool on = false; uint32_t n = 0; bool has_min = false, has_u = false; uint64_t ext_max = 0; DevBuf s, e, pmax, id, reads, minstart, bases_reads, mbases, ustart; } seg;
+    // ---- several BAM files (bdepth_add_input; MultiBamReader, multireader.d:218-268): the additional files are whole handles that
+    // only hold their input (file, BGZF members, header, index, shard / sparse plan); a run swaps them into this handle one after
+    // the other and accumulates into the same counters -- per-position counters and per-segment sums are additive over reads,
+    // and without -m nothing depends on the order in which the merged stream would have delivered them
+    std::vector<bdepth*> extra;
+    bool accum = false;                   // the run continues on the counters of the previous input
+    bool force_window = false;            // counter window fixed by the caller (union over the inputs)
     // ---- results
     bdepth_stats st{}; std::string err;
 };
@@ -225,7 +233,7 @@ int init_device(bdepth* h) {
     CK(cudaFuncSetAttribute(k1_fallback, cudaFuncAttributeMaxDynamicSharedMemorySize, K1_SMEM));
     CK(cudaFuncSetAttribute(k1_huff<false, 4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)); CK(cudaFuncSetAttribute(k1_huff<false, 6>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CK(cudaFuncSetAttribute(k1_huff<true, 5>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)); CK(cudaFuncSetAttribute(k1_huff<true, 4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    { const char* e = getenv("BDEPTH_K1H_VARIANT"); h->k1h_variant = e ? atoi(e) : 0; }      // A/B of the phase-1 instantiations (kernels.cuh)
+    { const char* e = getenv("BDEPTH_K1H_VARIANT"); h->k1h_variant = e ? atoi(e) : -1; }      // A/B of the phase-1 instantiations (kernels.cuh)
     { const char* e = getenv("BDEPTH_K3"); h->k3_tile = !(e && !strcmp(e, "gather")); }
     CK(cudaFuncSetAttribute(k3_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K3T_SMEM)); CK(cudaFuncSetAttribute(k3_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K3T_SMEM));
     { const char* e = getenv("BDEPTH_K1_ONEPHASE"); h->k1_onephase = e && atoi(e) == 1; }
@@ -596,8 +604,12 @@ int run_pipeline(bdepth* h, RunMode mode, RunOut* ro, Emitter* em = nullptr) {
 
     // ---- counter window (28 B/position).  With a BAI the linear index bounds where reads can lie, so only that
     // span of the linear genome is allocated; without one the whole genome is (87 GB for GRCh38, fits 180 GB HBM).
-    if (mode == RUN_FULL) {
+    if (mode == RUN_FULL && h->accum) {
+        // a further input of the same run: counters, window, sample planes stay as the first input left them
+    } else if (mode == RUN_FULL) {
         uint64_t lo = 0, hi = h->hdr.total_len;
+        if (h->force_window) { lo = h->cnt_base; hi = h->cnt_base + h->win_len; }
+        else
         if (h->bai.valid && h->bai_window_ok && h->bai.ioffsets.size() == nref && h->world > 1 && !sparse && !fix && blk_hi > blk_lo) {
             // a shard: from the window in which its first record begins (its own positions begin there or later) to the end of the last
             // 16 kbp window that any read before the shard's end overlaps (the linear index holds, per window, the first such read)
@@ -623,8 +635,10 @@ int run_pipeline(bdepth* h, RunMode mode, RunOut* ro, Emitter* em = nullptr) {
             }
             if (lo >= hi) { lo = 0; hi = h->hdr.total_len; }      // an index without linear entries says nothing
         }
-        h->cnt_base = lo / TILE_POS * TILE_POS;
-        h->win_len = ((hi - h->cnt_base + TILE_POS - 1) / TILE_POS + 1) * TILE_POS;
+        if (!h->force_window) {
+            h->cnt_base = lo / TILE_POS * TILE_POS;
+            h->win_len = ((hi - h->cnt_base + TILE_POS - 1) / TILE_POS + 1) * TILE_POS;
+        }
         h->S = (h->combined || h->hdr.sample_names.size() <= 1) ? 1u : (uint32_t)h->hdr.sample_names.size();
         if (h->S > 64) return fail(h, BDEPTH_ERR_ARG, "%u samples: per-sample output supports at most 64 (use --combined)", h->S);
         size_t need = (size_t)h->win_len * N_PLANES * 4 * h->S;
@@ -781,7 +795,10 @@ int run_pipeline(bdepth* h, RunMode mode, RunOut* ro, Emitter* em = nullptr) {
             BlockAux* ax = h->aux.as<BlockAux>() + (c0 - b); uint32_t* sgi = h->segi.as<uint32_t>() + (c0 - b) * MAX_SEG; uint8_t* ltb = h->littab.as<uint8_t>() + (c0 - b) * (size_t)MAX_SEG * 256;
             const unsigned hg = (n + 32 * K1H_WARPS - 1) / (32 * K1H_WARPS); const uint32_t blk0 = (uint32_t)(c0 - b);
 #define K1H(LIMS, MINB) BD_LAUNCH(hg, 32 * K1H_WARPS, k1h_smem<LIMS>(), ks, k1_huff<LIMS, MINB>)(d_comp, dd, n, blk0, stp, h->tok.as<uint32_t>(), h->lits.as<uint8_t>(), ax, sgi, ltb)
-            switch (h->k1h_variant) { case 1: K1H(false, 6); break; case 2: K1H(true, 5); break; case 3: K1H(true, 4); break; default: K1H(false, 4); }
+            // which instantiation: limits in registers at 4 CTAs per SM (16 warps) is the faster loop; when a launch has more warps than that
+            // holds at once, limits in shared memory at 5 CTAs (20 warps) wins by its occupancy (profiles/k1_history.md)
+            const int variant = h->k1h_variant >= 0 ? h->k1h_variant : (n > 148u * 16u * 32u ? 2 : 0);
+            switch (variant) { case 1: K1H(false, 6); break; case 2: K1H(true, 5); break; case 3: K1H(true, 4); break; default: K1H(false, 4); }
 #undef K1H
             BD_LAUNCH((n + K1L_WARPS - 1) / K1L_WARPS, 32 * K1L_WARPS, 0, ks, k1_lz)(dd, n, blk0, u0, stp, h->tok.as<uint32_t>(), h->lits.as<uint8_t>(), ax, sgi, ltb);
             BD_LAUNCH((n + 32 * K1_WARPS - 1) / (32 * K1_WARPS), 32 * K1_WARPS, K1_SMEM, ks, k1_fallback)(d_comp, dd, n, u0, stp);
@@ -991,6 +1008,7 @@ int run_pipeline(bdepth* h, RunMode mode, RunOut* ro, Emitter* em = nullptr) {
                 // start over with the whole genome as the counter window
                 if (!h->bai_window_ok) return fail(h, BDEPTH_ERR_FORMAT, "read extends past the end of the reference space");
                 h->bai_window_ok = false; CK(cudaDeviceSynchronize());
+                if (h->force_window || h->accum) return RC_RETRY_WINDOW;      // several inputs: the caller starts over with the whole genome as the window
                 return run_pipeline(h, mode, ro, em);
             }
             uint64_t t_lo = (gmin - h->cnt_base) / TILE_POS, t_hi = (gmax - h->cnt_base + TILE_POS - 1) / TILE_POS;
@@ -1120,6 +1138,71 @@ int run_pipeline(bdepth* h, RunMode mode, RunOut* ro, Emitter* em = nullptr) {
     return 0;
 }
 
+// ---- several inputs --------------------------------------------------------------------------------------------------------
+// Exchange the input of two handles: everything that describes the file and the plan made for it, nothing of the device state.
+void swap_inputs(bdepth* a, bdepth* b) {
+    std::swap(a->file, b->file); std::swap(a->file_len, b->file_len); std::swap(a->mapped, b->mapped); std::swap(a->fd, b->fd);
+    std::swap(a->blocks, b->blocks); std::swap(a->total_u, b->total_u); std::swap(a->lazy, b->lazy); std::swap(a->framed_all, b->framed_all); std::swap(a->framed_off, b->framed_off);
+    std::swap(a->hdr, b->hdr); std::swap(a->bai, b->bai); std::swap(a->has_index, b->has_index); std::swap(a->bai_window_ok, b->bai_window_ok);
+    std::swap(a->shard_ready, b->shard_ready); std::swap(a->blk_lo, b->blk_lo); std::swap(a->blk_hi, b->blk_hi); std::swap(a->entry0, b->entry0);
+    std::swap(a->limit_abs_u, b->limit_abs_u); std::swap(a->own_lo_abs_u, b->own_lo_abs_u); std::swap(a->zone_lin_lo, b->zone_lin_lo);
+    std::swap(a->sparse_ok, b->sparse_ok); std::swap(a->sparse_on, b->sparse_on); std::swap(a->vblocks, b->vblocks); std::swap(a->seg_entry, b->seg_entry); std::swap(a->seg_limit, b->seg_limit);
+}
+// where the linear index of the handle's current input says reads can lie (whole genome when it says nothing)
+void index_extent(const bdepth* h, uint64_t& lo, uint64_t& hi) {
+    const size_t nref = h->hdr.ref_len.size();
+    lo = 0; hi = h->hdr.total_len;
+    if (!(h->bai.valid && h->bai_window_ok && h->bai.ioffsets.size() == nref)) return;
+    uint64_t a = UINT64_MAX, b = 0;
+    for (size_t r = 0; r < nref; r++) {
+        const auto& v = h->bai.ioffsets[r]; if (v.empty()) continue;
+        size_t k = 0; while (k < v.size() && v[k] == 0) k++;
+        if (k == v.size()) continue;
+        a = std::min<uint64_t>(a, h->hdr.ref_lin0[r] + std::min<uint64_t>((uint64_t)k << 14, h->hdr.ref_len[r]));
+        b = std::max<uint64_t>(b, h->hdr.ref_lin0[r] + std::min<uint64_t>((uint64_t)v.size() << 14, h->hdr.ref_len[r]));
+    }
+    if (a < b) { lo = a; hi = b; }
+}
+void add_stats(bdepth_stats& t, const bdepth_stats& s) {
+    t.file_bytes += s.file_bytes; t.n_blocks += s.n_blocks; t.cdata_bytes += s.cdata_bytes; t.inflated_bytes += s.inflated_bytes; t.n_records += s.n_records; t.n_records_pass += s.n_records_pass;
+    t.n_cigar_ops += s.n_cigar_ops; t.seq_bytes += s.seq_bytes; t.long_reads += s.long_reads; t.chain_fixups += s.chain_fixups; t.gpu_launches += s.gpu_launches; t.n_batches += s.n_batches;
+    t.ms_h2d += s.ms_h2d; t.ms_inflate += s.ms_inflate; t.ms_scan += s.ms_scan; t.ms_coverage += s.ms_coverage; t.ms_span_device += s.ms_span_device; t.host_wall_ms += s.host_wall_ms;
+}
+// The pipeline over every input of the handle, into one set of counters (RUN_FULL).  One input: run_pipeline as it is.
+int run_all_inputs(bdepth* h, Emitter* em = nullptr) {
+    if (h->extra.empty()) return run_pipeline(h, RUN_FULL, nullptr, em);
+    if (h->fix_mates) return fail(h, BDEPTH_ERR_ARG, "fix-mate-overlaps with several BAM files: not available (mates are paired within one file's stream)");
+    if (h->world > 1) return fail(h, BDEPTH_ERR_ARG, "several BAM files on several ranks: not available");
+    h->staged = false;
+    for (int attempt = 0; attempt < 2; attempt++) {
+        // the counter window: the union of what the inputs' indices say (second attempt: an index lied -- the whole genome)
+        uint64_t lo = UINT64_MAX, hi = 0;
+        for (size_t i = 0; i <= h->extra.size(); i++) {
+            if (i) swap_inputs(h, h->extra[i - 1]);
+            uint64_t a, b; index_extent(h, a, b); if (attempt) { a = 0; b = h->hdr.total_len; }
+            lo = std::min(lo, a); hi = std::max(hi, b);
+            if (i) swap_inputs(h, h->extra[i - 1]);
+        }
+        h->cnt_base = lo / TILE_POS * TILE_POS; h->win_len = ((hi - h->cnt_base + TILE_POS - 1) / TILE_POS + 1) * TILE_POS;
+        h->force_window = true;
+        bdepth_stats total{}; int rc = 0;
+        for (size_t i = 0; i <= h->extra.size() && !rc; i++) {
+            if (i) swap_inputs(h, h->extra[i - 1]);
+            h->accum = i > 0;
+            rc = run_pipeline(h, RUN_FULL, nullptr, nullptr);       // (delivery starts when every input has been counted)
+            add_stats(total, h->st);
+            if (i) swap_inputs(h, h->extra[i - 1]);
+        }
+        h->accum = false; h->force_window = false;
+        if (rc == RC_RETRY_WINDOW) { if (attempt) return fail(h, BDEPTH_ERR_FORMAT, "read extends past the end of the reference space"); continue; }
+        if (rc) return rc;
+        total.positions = h->hdr.total_len; total.own_lo = h->own_lo; total.own_hi = h->own_hi;
+        h->st = total;
+        return 0;
+    }
+    return fail(h, BDEPTH_ERR_FORMAT, "internal: counter window");
+}
+
 // merged, sorted regions clipped to reference lengths
 void normalize_regions(const bdepth* h, const bdepth_region* r, size_t n, std::vector<bdepth_region>& out) {
     out.clear();
@@ -1179,8 +1262,41 @@ int bdepth_open_memory(const void* bam, size_t bam_len, const void* bai, size_t 
     return open_common(h, out);
 }
 
+// MultiBamReader(string[] filenames) (multireader.d:244-246, depth.d:1162-1163): one more coordinate-sorted, indexed BAM whose reads
+// are counted together with the handle's.  Its reference dictionary must be the handle's (the reference's SamHeaderMerger only
+// supports its "simple" strategy, multireader.d:225); its read groups join the sample table: a sample name keeps its number, new
+// names are appended in the order of the file's @RG lines (the reference numbers samples in the iteration order of a D
+// associative array, samheadermerger.d:202: not reproducible -- with --combined or one sample there is no order).
+int bdepth_add_input(bdepth_t* h, const char* bam_path) {
+    if (!h || !bam_path) return fail(h, BDEPTH_ERR_ARG, "null argument");
+    bdepth* x = nullptr;
+    int rc = open_path(bam_path, h->device, h->lazy, &x);
+    if (rc) { h->err = g_open_error; return rc; }
+    if (x->hdr.ref_names != h->hdr.ref_names || x->hdr.ref_len != h->hdr.ref_len) { bdepth_close(x); return fail(h, BDEPTH_ERR_ARG, "%s: its reference sequences differ from the first file's (only identical sequence dictionaries can be merged)", bam_path); }
+    // merged sample table, the same in every input's header
+    const bool first_has_rg = !h->hdr.rg_ids.empty(), this_has_rg = !x->hdr.rg_ids.empty();
+    std::vector<std::string> merged = first_has_rg ? h->hdr.sample_names : std::vector<std::string>();
+    std::vector<int> remap(x->hdr.sample_names.size(), 0);
+    if (this_has_rg) for (size_t i = 0; i < x->hdr.sample_names.size(); i++) {
+        int id = -1; for (size_t k = 0; k < merged.size(); k++) if (merged[k] == x->hdr.sample_names[i]) id = (int)k;
+        if (id < 0) { id = (int)merged.size(); merged.push_back(x->hdr.sample_names[i]); }
+        remap[i] = id;
+    }
+    if (merged.empty()) merged.push_back("*");
+    for (auto& sid : x->hdr.rg_sample) sid = remap[sid];
+    x->hdr.sample_names = merged; h->hdr.sample_names = merged;
+    for (bdepth* e : h->extra) e->hdr.sample_names = merged;
+    // the additional handle only holds its input from here on
+    x->comp.release(); x->descs.release(); x->status.release(); x->ubuf.release();
+    h->extra.push_back(x);
+    h->staged = false;
+    return 0;
+}
+
 void bdepth_close(bdepth_t* h) {
     if (!h) return;
+    for (bdepth* e : h->extra) bdepth_close(e);
+    h->extra.clear();
     cudaSetDevice(h->device);
     h->anchors_idx.release(); h->anchors_val.release(); h->chunk_limit.release(); h->tok.release(); h->lits.release(); h->aux.release(); h->segi.release(); h->littab.release();
     DevBuf* bufs[] = {&h->comp, &h->descs, &h->status, &h->ubuf, &h->chunk_start, &h->entry, &h->exitb, &h->count, &h->slot_base, &h->slots, &h->rec_base, &h->walk_list, &h->soa_start, &h->soa_span, &h->soa_meta, &h->soa_off, &h->soa_ncl, &h->soa_lseq, &h->long_list, &h->tile_first, &h->tile_lo, &h->counts, &h->ref_len_d, &h->ref_lin0_d, &h->scan_stats, &h->ref_has, &h->misc};
@@ -1205,8 +1321,8 @@ int bdepth_n_ref(const bdepth_t* h) { return (int)h->hdr.ref_len.size(); }
 const char* bdepth_ref_name(const bdepth_t* h, int i) { return (i >= 0 && (size_t)i < h->hdr.ref_names.size()) ? h->hdr.ref_names[i].c_str() : nullptr; }
 uint32_t bdepth_ref_length(const bdepth_t* h, int i) { return (i >= 0 && (size_t)i < h->hdr.ref_len.size()) ? h->hdr.ref_len[i] : 0; }
 const char* bdepth_header_text(const bdepth_t* h, size_t* len) { if (len) *len = h->hdr.text.size(); return h->hdr.text.c_str(); }
-int bdepth_is_coordinate_sorted(const bdepth_t* h) { return h->hdr.so_coordinate ? 1 : 0; }
-int bdepth_has_index(const bdepth_t* h) { return h->has_index ? 1 : 0; }
+int bdepth_is_coordinate_sorted(const bdepth_t* h) { for (const bdepth* e : h->extra) if (!e->hdr.so_coordinate) return 0; return h->hdr.so_coordinate ? 1 : 0; }      // "All files must be coordinate-sorted" (depth.d:1164)
+int bdepth_has_index(const bdepth_t* h) { for (const bdepth* e : h->extra) if (!e->has_index) return 0; return h->has_index ? 1 : 0; }
 int bdepth_n_samples(const bdepth_t* h) { return (int)h->hdr.sample_names.size(); }
 const char* bdepth_sample_name(const bdepth_t* h, int i) { return (i >= 0 && (size_t)i < h->hdr.sample_names.size()) ? h->hdr.sample_names[i].c_str() : nullptr; }
 
@@ -1303,7 +1419,7 @@ int bdepth_stage(bdepth_t* h) {
 }
 
 int bdepth_run_resident(bdepth_t* h) {
-    int rc = run_pipeline(h, RUN_FULL, nullptr); if (rc) return rc;
+    int rc = run_all_inputs(h); if (rc) return rc;
     cudaStream_t sm = h->s_main;
     CK(cudaMemsetAsync(h->misc.p, 0, 8, sm));
     uint64_t a = std::max(h->own_lo, h->cnt_base) - h->cnt_base, b = std::min(h->own_hi, h->cnt_base + h->win_len) - h->cnt_base;
@@ -1322,7 +1438,7 @@ int bdepth_run_base(bdepth_t* h, bdepth_tile_cb cb, void* user) {
     // ranges to deliver: whole genome, or the merged regions (sorted)
     if (h->regions.empty()) { if (h->hdr.total_len) em.ranges.push_back({0, h->hdr.total_len}); }
     else for (auto& g : h->regions) em.ranges.push_back({h->hdr.ref_lin0[g.ref_id] + g.start, h->hdr.ref_lin0[g.ref_id] + g.end});
-    rc = run_pipeline(h, RUN_FULL, nullptr, &em); if (rc) { em.finish(); return rc; }
+    rc = run_all_inputs(h, &em); if (rc) { em.finish(); return rc; }
     cudaStream_t sm = h->s_main;
     cudaEvent_t e0 = h->ev[5], e1 = h->ev[6];
     // covered positions (rows of default `depth base`), over the range this rank owns
@@ -1347,7 +1463,7 @@ int bdepth_run_base_text(bdepth_t* h, const bdepth_text_opts* o, bdepth_text_cb 
     // a position that reads cover but whose every base fails -q still has a column: with -a and a positive minimum coverage
     // the reference prints it (flag n); the counters cannot tell it from an empty position, a bitmap can (one rank only)
     h->want_presence = o->annotate && h->minq > 0 && o->min_cov > 0 && h->world == 1;
-    int rc = run_pipeline(h, RUN_FULL, nullptr); h->want_presence = false; if (rc) return rc;
+    int rc = run_all_inputs(h); h->want_presence = false; if (rc) return rc;
     const bool ms = h->S > 1;             // one row per sample and position (k_text_len_ms / k_text_write_ms)
     const bool presence = o->annotate && h->minq > 0 && o->min_cov > 0 && h->world == 1;
     cudaStream_t sm = h->s_main;
@@ -1488,7 +1604,7 @@ static int run_segments(bdepth* h, const std::vector<SegDef>& segs, const uint32
     CK(S.ustart.ensure(nn * 8)); if (n) CK(cudaMemcpy(S.ustart.p, us.data(), n * 8, cudaMemcpyHostToDevice));
     S.has_min = has_min; S.has_u = has_u; S.ext_max = ext_max;
     S.on = true; S.n = (uint32_t)n;
-    rc = run_pipeline(h, RUN_FULL, nullptr);
+    rc = run_all_inputs(h);
     S.on = false;
     if (rc) return rc;
     cudaStream_t sm = h->s_main;

@@ -7,7 +7,7 @@
 // D binding that would replace this file is in sambamba_b200/d/bdepth.d and INTEGRATION.md.
 //
 // Not supported through the GPU path yet (rejected with a message, never silently wrong):
-//   -F with back-references / look-around in regular expressions ; several BAM files ; more than 64 samples without --combined.
+//   -F with back-references / look-around in regular expressions ; several BAM files together with -m ; more than 64 samples without --combined.
 #include <math.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -261,7 +261,6 @@ int main(int argc, char** argv) {
     }
     int mapq_gt = 0; uint32_t flag_reject = 0x600;
     if (a.v.size() < 2) return die("no input BAM given");
-    if (a.v.size() > 2) return die("several BAM files: not available in the GPU engine yet");
     const std::string bam_path = a.v[1];
     if (c.mode == 2) { c.window_mode = true; }
 
@@ -269,6 +268,7 @@ int main(int argc, char** argv) {
     // need the whole file frames the rest itself)
     int rc = has_bed ? bdepth_open_lazy(bam_path.c_str(), 0, &c.h) : bdepth_open(bam_path.c_str(), 0, &c.h);
     if (rc) return die(bdepth_last_error(nullptr));
+    for (size_t fi = 2; fi < a.v.size(); fi++) if (bdepth_add_input(c.h, a.v[fi].c_str())) return die(bdepth_last_error(c.h));      // new MultiBamReader(bam_filenames), depth.d:1162-1163
     if (!bdepth_is_coordinate_sorted(c.h)) return die("All files must be coordinate-sorted");
     if (!bdepth_has_index(c.h)) return die("All files must be indexed");
     int nref = bdepth_n_ref(c.h);

@@ -45,6 +45,7 @@ int bdepth_device_count();
 int bdepth_open(const(char)* bam_path, int device, bdepth_t** h);
 int bdepth_open_lazy(const(char)* bam_path, int device, bdepth_t** h);   // region queries: frame only what the BAI chunks touch
 int bdepth_open_memory(const(void)* bam, size_t bam_len, const(void)* bai, size_t bai_len, int device, bdepth_t** h);
+int bdepth_add_input(bdepth_t* h, const(char)* bam_path);
 void bdepth_close(bdepth_t* h);
 const(char)* bdepth_last_error(const(bdepth_t)* h);
 

@@ -7,11 +7,11 @@ set -u
 OUT=gpurun_out/ab; mkdir -p $OUT
 python -c "import __graft_entry__ as g; g.build(quiet=True)" > $OUT/build.log 2>&1
 timeout 180 python __graft_entry__.py smoke > $OUT/smoke.log 2>&1; echo "smoke exit $?" >> $OUT/smoke.log
-BDEPTH_SKIP_FULLSIZE=1 timeout 1200 python -m pytest tests/test_gpu_parity.py tests/test_gpu_edge_cases.py tests/test_gpu_cli.py tests/test_gpu_sparse.py -m gpu -q -x -p no:cacheprovider --timeout 300 > $OUT/pytest.log 2>&1; echo "pytest exit $?" >> $OUT/pytest.log
+BDEPTH_SKIP_FULLSIZE=1 timeout 1200 python -m pytest tests/test_gpu_parity.py tests/test_gpu_edge_cases.py tests/test_gpu_cli.py tests/test_gpu_sparse.py tests/test_gpu_multibam.py -m gpu -q -x -p no:cacheprovider --timeout 300 > $OUT/pytest.log 2>&1; echo "pytest exit $?" >> $OUT/pytest.log
 timeout 600 python bench.py --steps 4 --warmup 3 --no-cpu-baseline > $OUT/bench_default.json 2> $OUT/bench_default.err
 BDEPTH_K3=gather timeout 600 python bench.py --steps 4 --warmup 3 --no-cpu-baseline --no-verify > $OUT/bench_k3gather.json 2> $OUT/bench_k3gather.err
-for v in 2 3; do BDEPTH_K1H_VARIANT=$v timeout 600 python bench.py --steps 4 --warmup 3 --no-cpu-baseline --no-verify > $OUT/bench_v$v.json 2> $OUT/bench_v$v.err; done
-for cb in 1664 3328; do BDEPTH_BENCH_CHUNK_BLOCKS=$cb timeout 600 python bench.py --steps 4 --warmup 3 --no-cpu-baseline --no-verify > $OUT/bench_cb$cb.json 2> $OUT/bench_cb$cb.err; done
+BDEPTH_K1H_VARIANT=2 timeout 600 python bench.py --steps 4 --warmup 3 --no-cpu-baseline --no-verify > $OUT/bench_v2.json 2> $OUT/bench_v2.err
+BDEPTH_BENCH_CHUNK_BLOCKS=13312 timeout 600 python bench.py --steps 4 --warmup 3 --no-cpu-baseline --no-verify > $OUT/bench_cb13312.json 2> $OUT/bench_cb13312.err
 timeout 900 python bench.py --config wgs-shard --steps 3 --warmup 2 --no-cpu-baseline > $OUT/wgs_default.json 2> $OUT/wgs_default.err
 BDEPTH_K1H_VARIANT=2 timeout 600 python bench.py --config wgs-shard --steps 3 --warmup 2 --no-cpu-baseline --no-verify > $OUT/wgs_v2.json 2> $OUT/wgs_v2.err
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file $OUT/launches.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-verify > $OUT/ncu_bench.log 2>&1
