@@ -527,6 +527,9 @@ def run_wgs_config(a, rank, world, local_rank):
 
 
 def main():
+    if os.environ.get("BDEPTH_BENCH_WATCHDOG"):        # development aid: dump every thread's Python stack and exit if the run takes longer than this many seconds
+        import faulthandler
+        faulthandler.dump_traceback_later(int(os.environ["BDEPTH_BENCH_WATCHDOG"]), exit=True)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)

@@ -181,7 +181,7 @@ def test_fix_mates_windows_and_regions_on_several_ranks(pairs_bam):
         b.set_fix_mates(True)
         want_w = b.run_windows(1000, 0, [1, 10])
         want_r = b.run_regions([(0, 100, 9000), (0, 9000, 9100), (0, 60000, 140000), (2, 5, 100000)], [2, 8])
-    for world in (2, 3):
+    for world in [w for w in (2, 3) if _n_gpus() >= w]:
         for r in _run(world, pairs_bam, "windows-m"):
             assert r[4] == want_w
         for r in _run(world, pairs_bam, "regions-m"):
