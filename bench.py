@@ -49,13 +49,13 @@ def ncu_traffic(kernel_key):
         with open(os.path.join(ROOT, ent["summary"])) as f:
             for line in f:
                 if line.startswith("== kernel:"):
-                    inside = ent["kernel_match"] in line
+                    inside = any(m in line for m in ent["kernel_match"])        # the K1 stage is two launches (k1_huff, k1_lz): their traffic adds
                 elif inside and ("dram__bytes_read.sum" in line or "dram__bytes_write.sum" in line):
                     unit = line.split("[")[1].split("]")[0].lower()
                     v = float(line.rsplit("=", 1)[1].replace(",", ""))
                     tot += v * {"gbyte": 1e9, "mbyte": 1e6, "kbyte": 1e3, "byte": 1.0, "tbyte": 1e12}[unit]
                 elif inside and line.startswith("== hottest"):
-                    break
+                    inside = False
         return (int(tot) if tot else None), ent["summary"]
     except Exception as e:                                    # no capture of this build yet: say so instead of quoting a stale one
         return None, f"none ({type(e).__name__})"
@@ -763,10 +763,10 @@ def main():
                 "variants": {k: os.environ[k] for k in ("BDEPTH_K1_STREAM_WARPS", "BDEPTH_K1_LIT3", "BDEPTH_K3_PREFETCH") if k in os.environ}},
         "text_rows": text,
         "gpu_launches": int(total_launches),
-        "roofline": {"kernel": "k1_inflate (lane-per-BGZF-block DEFLATE)", "bound": "hbm", "achieved": k1_bytes / 1e9 / (k1_ms / 1e3), "peak": peak, "unit": "GB/s",
+        "roofline": {"kernel": "K1 two-phase inflate: k1_huff (lane-per-BGZF-block Huffman phase) + k1_lz (warp-per-block LZ77 phase), timed together", "bound": "hbm", "achieved": k1_bytes / 1e9 / (k1_ms / 1e3), "peak": peak, "unit": "GB/s",
                      "frac": k1_bytes / 1e9 / (k1_ms / 1e3) / peak, "traffic": traffic if (a.gpus == 1 and a.reads_per_unit == READS_PER_UNIT) else None, "traffic_source": traffic_src,
                      "algorithmic_bytes_per_launch": int(k1_bytes / max(1, k1_launches_per_step)), "launches_per_step": k1_launches_per_step,
-                     "peak_source": peak_src, "note": "C + U per launch (SURVEY 8d) / CUDA-event duration of the launch on the library stream; DEFLATE decoding is instruction-latency bound, not HBM bound"},
+                     "peak_source": peak_src, "note": "C + U per pass (SURVEY 8d) / CUDA-event duration of the K1 launches (k1_huff + k1_lz + k1_fallback) on the library stream; phase 1 is instruction-latency bound, phase 2 issue bound, neither HBM bound"},
         "clocks": clocks,
         "verified": (verify["ok"] if verify else None), "verification": verify,
     }

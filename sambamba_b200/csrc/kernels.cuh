@@ -238,6 +238,99 @@ __global__ void __launch_bounds__(K1L_WARPS * 32) k1_lz(const BlockDesc* __restr
     if (err && lane == 0) status[b] = err;
 }
 
+// Phase 2, flattened: the same job as k1_lz with one output BYTE per lane and round instead of one token per lane.  After the two warp
+// scans every lane knows its token's range; a round covers 32 consecutive output positions: the tokens that begin inside the round
+// set a bit each (one warp OR), so a lane finds its token with a POPC instead of a search; a literal byte comes from the packed
+// stream through the rank -> byte table, a match byte from `distance` before it -- and if that position lies inside the group's own
+// range, it is resolved through the group's tokens (binary search over the 32 ends in shared memory, repeated until the position is
+// a literal or lies before the group: pointer jumping), so all bytes of a group are independent: no rounds of dependent copies,
+// 32 consecutive byte stores per round (one or two sectors).
+__global__ void __launch_bounds__(K1L_WARPS * 32) k1_lz_flat(const BlockDesc* __restrict__ blocks, uint32_t n_blocks, uint32_t blk0, uint8_t* __restrict__ u, int* __restrict__ status,
+                                                             const uint32_t* __restrict__ tok, const uint8_t* __restrict__ lits, const BlockAux* __restrict__ aux,
+                                                             const uint32_t* __restrict__ seg_info, const uint8_t* __restrict__ lit_tab) {
+    __shared__ uint32_t s_tab[K1L_WARPS][64];
+    __shared__ uint32_t s_end[K1L_WARPS][32], s_il[K1L_WARPS][32], s_dist[K1L_WARPS][32];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t b = blockIdx.x * K1L_WARPS + warp;
+    if (b >= n_blocks || status[b] != INF_OK) return;            // warp-uniform
+    const BlockDesc d = blocks[b]; const BlockAux ax = aux[b];
+    uint8_t* const ub = u + d.uoff;
+    const uint8_t* const lt = lits + lit_off_of(d.uoff, (uint64_t)blk0 + b);
+    const uint32_t* const sgi = seg_info + (size_t)b * MAX_SEG;
+    const uint8_t* const ltab = lit_tab + (size_t)b * (MAX_SEG * 256);
+    const uint8_t* const tb = reinterpret_cast<const uint8_t*>(s_tab[warp]);
+    uint32_t sg = 0, seg_hi = ax.n_seg > 1 ? (sgi[1] & 0x7FFFFFFFu) : 0xFFFFFFFFu; bool seg_raw = ax.n_seg == 0 || (sgi[0] & SEG_RAW);
+    if (!seg_raw) { const uint32_t* tg = reinterpret_cast<const uint32_t*>(ltab); s_tab[warp][lane] = tg[lane]; s_tab[warp][lane + 32] = tg[lane + 32]; }
+    __syncwarp();
+    const uint32_t* tk = tok + d.tok_off;
+    uint32_t base = 0, lbase = 0;
+    int err = INF_OK;
+    for (uint32_t g = 0; g < ax.n_tok; g += 32) {
+        const uint32_t t = g + lane < ax.n_tok ? tk[g + lane] : TOK_NOMATCH;
+        const uint32_t lit = t & 0xFFu, len = (t >> 31) ? 0u : ((t >> 8) & 0xFFu) + 3u, dist = ((t >> 16) & 0x7FFFu) + 1u;
+        uint32_t incl = lit + len, il = lit;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, o), w = __shfl_up_sync(0xFFFFFFFFu, il, o); if ((int)lane >= o) { incl += v; il += w; } }
+        const uint32_t tot = __shfl_sync(0xFFFFFFFFu, incl, 31), totl = __shfl_sync(0xFFFFFFFFu, il, 31);
+        const uint32_t tstart = incl - len - lit;                 // where the token's literals begin, relative to the group
+        {
+            const bool far = len && dist > base + tstart + lit;
+            if (__ballot_sync(0xFFFFFFFFu, far)) { err = INF_ERR_DIST; break; }
+            if (base + tot > d.isize || lbase + totl > ax.n_lit) { err = INF_ERR_OVERRUN; break; }
+        }
+        if (totl) {
+            while (sg + 1 < ax.n_seg && lbase >= seg_hi) {        // the group begins in a later deflate block: its table
+                sg++; seg_hi = sg + 1 < ax.n_seg ? (sgi[sg + 1] & 0x7FFFFFFFu) : 0xFFFFFFFFu; seg_raw = (sgi[sg] & SEG_RAW) != 0;
+                __syncwarp();
+                if (!seg_raw) { const uint32_t* tg = reinterpret_cast<const uint32_t*>(ltab + sg * 256u); s_tab[warp][lane] = tg[lane]; s_tab[warp][lane + 32] = tg[lane + 32]; }
+                __syncwarp();
+            }
+        }
+        const bool one_seg = lbase + totl <= seg_hi;
+        auto literal = [&](uint32_t li) -> uint32_t {           // the byte of literal li of the block
+            const uint32_t r = lt[li];
+            if (one_seg) return seg_raw ? r : (uint32_t)tb[r];
+            uint32_t s2 = sg; while (s2 + 1 < ax.n_seg && li >= (sgi[s2 + 1] & 0x7FFFFFFFu)) s2++;      // the group straddles deflate blocks: table from global memory
+            return (sgi[s2] & SEG_RAW) ? r : (uint32_t)ltab[s2 * 256u + r];
+        };
+        s_end[warp][lane] = incl; s_il[warp][lane] = il; s_dist[warp][lane] = dist;
+        __syncwarp();
+        const bool real = lit + len != 0;
+        for (uint32_t o0 = 0; o0 < tot; o0 += 32) {
+            // the tokens that begin inside this round, one bit each; the token the round begins in
+            const uint32_t mbits = __reduce_or_sync(0xFFFFFFFFu, (real && tstart >= o0 && tstart < o0 + 32) ? (1u << (tstart - o0)) : 0u);
+            const uint32_t first = (uint32_t)__popc(__ballot_sync(0xFFFFFFFFu, real && tstart <= o0)) - 1u;
+            const uint32_t o = o0 + lane;
+            if (o < tot) {
+                uint32_t i = first + (uint32_t)__popc(mbits & ((2u << lane) - 1u) & ~1u);
+                uint32_t ts = i ? s_end[warp][i - 1] : 0u, lb = i ? s_il[warp][i - 1] : 0u, li = s_il[warp][i] - lb, off = o - ts;
+                uint32_t v;
+                if (off < li) v = literal(lbase + lb + off);
+                else {
+                    uint32_t k = off - li, dd = s_dist[warp][i], ms = base + ts + li;
+                    uint32_t s = ms - dd + (dd <= k ? k % dd : k);             // inside its own match: period `dd`
+                    bool done = false; v = 0;
+                    while (s >= base) {                                        // the source lies in the group: through its tokens
+                        const uint32_t so = s - base;
+                        int lo = 0, hi = (int)i;                                // the first token whose end exceeds so (it is <= i)
+                        while (lo < hi) { int mid = (lo + hi) >> 1; if (s_end[warp][mid] > so) hi = mid; else lo = mid + 1; }
+                        ts = lo ? s_end[warp][lo - 1] : 0u; lb = lo ? s_il[warp][lo - 1] : 0u; li = s_il[warp][lo] - lb; off = so - ts;
+                        if (off < li) { v = literal(lbase + lb + off); done = true; break; }
+                        k = off - li; dd = s_dist[warp][lo]; ms = base + ts + li;
+                        s = ms - dd + (dd <= k ? k % dd : k);
+                    }
+                    if (!done) v = ub[s];
+                }
+                ub[base + o] = (uint8_t)v;
+            }
+        }
+        base += tot; lbase += totl;
+        __syncwarp();
+    }
+    if (!err && (base != d.isize || lbase != ax.n_lit)) err = INF_ERR_SHORT;
+    if (err && lane == 0) status[b] = err;
+}
+
 // The exact one-phase decoder for the blocks phase 1 marked INF_FALLBACK (more than MAX_SEG deflate blocks, more tokens
 // than the token area holds).  Launched after every two-phase inflate; a warp without such a block returns at once.
 __global__ void __launch_bounds__(K1_WARPS * 32, 1) k1_fallback(const uint32_t* __restrict__ comp, const BlockDesc* __restrict__ blocks,

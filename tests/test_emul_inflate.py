@@ -190,6 +190,9 @@ def test_phase_two_warp_code_under_the_emulation(tmp_path):
     import subprocess
     import sys
     mix = helpers.gen_bam(str(tmp_path / "mix.bam"), "--preset", "tiny", "-n", 6000, "--stored-every", 4, "-t", 2)
+    # long self-overlapping matches (distance 1..3, length 258), period-sized distances, identical records: what zlib makes of constant data
+    rep = [(0, 10 + (i // 7), 60, 0, [(120, 0)], "A" * 120, "q") for i in range(900)] + [(0, 400 + i, 60, 0, [(60, 0)], "ACG" * 20, "n%d" % (i % 3)) for i in range(600)]
+    runs = helpers.write_bam(str(tmp_path / "runs.bam"), [("c", 5000)], rep, quals=[[30] * len(r[5]) for r in rep], level=9)
     code = (
         "import sys, os, numpy as np\n"
         "sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
@@ -200,6 +203,7 @@ def test_phase_two_warp_code_under_the_emulation(tmp_path):
         "    with sb.BDepth(p) as b:\n"
         "        assert np.array_equal(b.inflate(), helpers.oracle_inflate(p)), p\n"
         "print('ok')\n") % (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "tests", "emul", "libbdepth_emul.so"))
-    files = [os.path.join(GOLDEN, f) for f in sorted(os.listdir(GOLDEN)) if f.endswith(".bam")] + [mix]
-    r = subprocess.run([sys.executable, "-c", code] + files, env=dict(os.environ, BDEPTH_EMU_K1LZ_WARP="1"), capture_output=True, text=True, timeout=900)
-    assert r.returncode == 0 and r.stdout.strip() == "ok", r.stderr[-2000:]
+    files = [os.path.join(GOLDEN, f) for f in sorted(os.listdir(GOLDEN)) if f.endswith(".bam")] + [mix, runs]
+    for variant in ({}, {"BDEPTH_K1LZ": "flat"}):        # k1_lz (lane = token, dependency rounds) and k1_lz_flat (lane = output byte, pointer jumping)
+        r = subprocess.run([sys.executable, "-c", code] + files, env=dict(os.environ, BDEPTH_EMU_K1LZ_WARP="1", **variant), capture_output=True, text=True, timeout=900)
+        assert r.returncode == 0 and r.stdout.strip() == "ok", (variant, r.stderr[-2000:])

@@ -1,7 +1,8 @@
 """Every selectable kernel variant must print what the default kernels print: the round-1 one-phase inflater for all blocks
 (BDEPTH_K1_ONEPHASE=1; by default it only takes the header blocks and what phase 1 hands back), the phase-1 instantiations of the
 two-phase inflater (BDEPTH_K1H_VARIANT: limits in registers / in shared memory, 4 / 5 / 6 CTAs per SM; by default chosen by launch
-size), round 1's k3_gather with and without its record prefetch (BDEPTH_K3=gather, BDEPTH_K3_PREFETCH=0; default: k3_tile)."""
+size), round 1's k3_gather with and without its record prefetch (BDEPTH_K3=gather, BDEPTH_K3_PREFETCH=0; default: k3_tile), the byte-flattened
+phase 2 (BDEPTH_K1LZ=flat)."""
 import os
 import subprocess
 
@@ -22,7 +23,7 @@ def bam(tmp_path_factory):
 
 
 @pytest.mark.parametrize("envadd", [dict(BDEPTH_K1_ONEPHASE="1"), dict(BDEPTH_K1H_VARIANT="0"), dict(BDEPTH_K1H_VARIANT="1"), dict(BDEPTH_K1H_VARIANT="2"),
-                                    dict(BDEPTH_K1H_VARIANT="3"), dict(BDEPTH_K3="gather"), dict(BDEPTH_K3="gather", BDEPTH_K3_PREFETCH="0")],
+                                    dict(BDEPTH_K1H_VARIANT="3"), dict(BDEPTH_K3="gather"), dict(BDEPTH_K3="gather", BDEPTH_K3_PREFETCH="0"), dict(BDEPTH_K1LZ="flat")],
                          ids=lambda e: ",".join(f"{k[7:]}={v}" for k, v in e.items()))
 def test_variant_gives_identical_output(bam, envadd):
     env = dict(os.environ, **envadd)
