@@ -221,6 +221,16 @@ int bdepth_ref_has_reads(const bdepth_t* h, int ref);
  * (used by the parity tests and the roofline bench; same kernels as the runs above) */
 /* Inflate the whole (shard of the) file on the GPU and copy the concatenated payload to dst. */
 int64_t bdepth_inflate_to_host(bdepth_t* h, void* dst, uint64_t cap);
+/* Build the BAI index of the opened BAM on the GPU -- what `sambamba index` writes: createIndex / IndexBuilder,
+ * BioD/bio/std/hts/bam/bai/indexing.d:56-366 (bins with their chunks as the reference cuts them -- a chunk ends where the bin of
+ * consecutive reads changes, chunks of one bin merge when they meet in one BGZF member --, the metadata pseudo-bin 37450, the linear
+ * index with its gaps filled, n_no_coor).  K1 inflate and the K2 record scan as in every run, then one thread per record
+ * (k_index_scan); the host assembles the per-bin lists from one entry per change of bin.  Bins are written in ascending order (the
+ * reference: iteration order of a D associative array); a file that is not coordinate sorted is refused as there (:259-271).
+ * Returns the size of the index in bytes (copied to dst when cap suffices; the first call builds, later calls only copy) or a negative
+ * error.  The handle adopts the index: bdepth_has_index turns 1, and sharding, counter windows and region queries work on input
+ * that came without a .bai (the reference refuses such input, depth.d:1166 -- the CLI still does unless --build-index is given). */
+int64_t bdepth_build_index(bdepth_t* h, void* dst, uint64_t cap);
 /* Scan records on the GPU; copy out up to cap rows of the columnar SoA (any pointer may be NULL). */
 int64_t bdepth_scan_to_host(bdepth_t* h, uint64_t cap, int32_t* ref_id, int32_t* pos, uint32_t* span, uint16_t* flag, uint8_t* mapq, uint16_t* n_cigar, uint64_t* rec_off);
 

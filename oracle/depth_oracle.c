@@ -1336,6 +1336,111 @@ int64_t oracle_inflate_file(const char *bam_path, uint8_t *dst, uint64_t cap) {
 }
 void oracle_get_stats(double *t_inflate, double *t_sweep, uint64_t *columns, uint64_t *file_bytes) { *t_inflate = g_stats.t_inflate; *t_sweep = g_stats.t_sweep; *columns = g_stats.columns; *file_bytes = g_stats.file_bytes; }
 
+
+/* ------------------------------------------------------------------ BAI builder (sambamba index)
+ * A restatement of IndexBuilder (BioD/bio/std/hts/bam/bai/indexing.d:56-351, createIndex :356-366) over the virtual offsets the
+ * reference's stream reports (BgzfInputStream: a position at the end of a member is the start of the next one, inputstream.d:430-452,
+ * :508-530; after the last member it is the offset of the EOF marker).  put() :290-333: reads are taken in file order; a read without
+ * reference or with position < 0 only counts in the metadata; the previous read's linear-index entries (:133-161) and, when the bin
+ * changes or a new reference begins, its chunk (:219-246: merged with the bin's last chunk when that one ends in the same member) are
+ * flushed when the next read arrives.  dumpCurrentReference :184-216 writes the bins, the metadata pseudo-bin 37450 and the linear
+ * index with its gaps filled from the left (:163-182).
+ * One deviation, stated: the reference writes a reference's bins in the iteration order of a D associative array (:188), which is not
+ * defined by anything but that runtime; this restatement writes them in ascending bin number.  A reader of the index cannot tell.
+ * Returns the size of the index (written to out when cap suffices), or -1 (oracle_last_error()).                                       */
+typedef struct { uint64_t beg, end; } BaiChunkO;
+typedef struct { uint32_t bin; BaiChunkO *c; size_t n, cap; } BaiBinO;
+typedef struct { uint8_t *p; size_t n, cap; } OutBuf;
+static void ob_put(OutBuf *o, const void *src, size_t len) { if (o->n + len > o->cap) { o->cap = (o->n + len) * 2 + 4096; o->p = realloc(o->p, o->cap); } memcpy(o->p + o->n, src, len); o->n += len; }
+static void ob_u32(OutBuf *o, uint32_t v) { uint8_t b[4] = { (uint8_t)v, (uint8_t)(v >> 8), (uint8_t)(v >> 16), (uint8_t)(v >> 24) }; ob_put(o, b, 4); }
+static void ob_u64(OutBuf *o, uint64_t v) { ob_u32(o, (uint32_t)v); ob_u32(o, (uint32_t)(v >> 32)); }
+static int bin_cmp(const void *a, const void *b) { const BaiBinO *x = a, *y = b; return x->bin < y->bin ? -1 : x->bin > y->bin; }
+static uint64_t voffset_of(const Bgzf *z, uint64_t u) {      /* virtualTell() at inflated offset u */
+    if (u >= z->ulen) { const BgzfBlock *l = &z->blocks[z->n_blocks - 1]; return (l->coff + l->bsize) << 16; }
+    size_t lo = 0, hi = z->n_blocks; while (lo + 1 < hi) { size_t m = (lo + hi) / 2; if (z->blocks[m].uoff <= u) lo = m; else hi = m; }
+    return (z->blocks[lo].coff << 16) | (u - z->blocks[lo].uoff);
+}
+#define BAI_LIN_N 32769           /* BAI_MAX_BIN_ID - BAI_MAX_NONLEAF_BIN_ID + 1, indexing.d:279 */
+static size_t lin_off(int32_t pos) { return pos < 0 ? 0 : (size_t)pos / 16384; }      /* toLinearIndexOffset :51-53 */
+typedef struct {
+    OutBuf out; uint64_t *lin; size_t lin_len;
+    int first_read; int32_t p_ref, p_pos, p_end; uint32_t p_bin; int p_unmapped; uint64_t p_svo, p_evo;      /* _prev_read */
+    uint64_t no_coord, beg_vo, end_vo, unmapped, mapped, cur_beg;
+    BaiBinO *bins; size_t n_bins, cap_bins;
+} BaiB;
+static void bb_update_linear(BaiB *b) {                      /* :133-161 */
+    size_t beg = lin_off(b->p_pos), end = b->p_unmapped ? beg : lin_off(b->p_pos + (b->p_end - b->p_pos) - 1);
+    for (size_t i = beg; i <= end && i < BAI_LIN_N; i++) if (b->lin[i] == 0) b->lin[i] = b->p_svo;
+    if (end + 1 > b->lin_len) b->lin_len = end + 1;
+}
+static void bb_update_chunks(BaiB *b) {                      /* :219-246 */
+    BaiBinO *bn = NULL;
+    for (size_t i = 0; i < b->n_bins; i++) if (b->bins[i].bin == b->p_bin) bn = &b->bins[i];
+    if (!bn) { BaiBinO nb = { b->p_bin, NULL, 0, 0 }; VEC_PUSH(b->bins, b->n_bins, b->cap_bins, nb); bn = &b->bins[b->n_bins - 1]; }
+    if (bn->n == 0 || (bn->c[bn->n - 1].end >> 16) != (b->cur_beg >> 16)) { BaiChunkO c = { b->cur_beg, b->p_evo }; VEC_PUSH(bn->c, bn->n, bn->cap, c); }
+    else bn->c[bn->n - 1].end = b->p_evo;
+    b->cur_beg = b->p_evo;
+}
+static void bb_dump_reference(BaiB *b) {                     /* :184-216 */
+    qsort(b->bins, b->n_bins, sizeof *b->bins, bin_cmp);
+    ob_u32(&b->out, (uint32_t)(b->n_bins + 1));
+    for (size_t i = 0; i < b->n_bins; i++) {
+        ob_u32(&b->out, b->bins[i].bin); ob_u32(&b->out, (uint32_t)b->bins[i].n);
+        for (size_t k = 0; k < b->bins[i].n; k++) { ob_u64(&b->out, b->bins[i].c[k].beg); ob_u64(&b->out, b->bins[i].c[k].end); }
+        free(b->bins[i].c);
+    }
+    ob_u32(&b->out, 37450); ob_u32(&b->out, 2); ob_u64(&b->out, b->beg_vo); ob_u64(&b->out, b->end_vo); ob_u64(&b->out, b->mapped); ob_u64(&b->out, b->unmapped);
+    ob_u32(&b->out, (uint32_t)b->lin_len);
+    uint64_t last = 0;
+    for (size_t i = 0; i < b->lin_len; i++) { uint64_t v = i < BAI_LIN_N ? b->lin[i] : 0; if (v == 0) v = last; else last = v; ob_u64(&b->out, v); }
+    memset(b->lin, 0, BAI_LIN_N * sizeof *b->lin); b->lin_len = 0; b->n_bins = 0;
+    b->cur_beg = b->p_evo; b->beg_vo = b->end_vo = b->cur_beg; b->unmapped = b->mapped = 0;
+}
+int64_t oracle_build_bai(const char *bam_path, uint8_t *out, uint64_t cap, int nthreads) {
+    Bam B; memset(&B, 0, sizeof B);
+    if (bgzf_load(&B.z, bam_path, nthreads, 0)) return -1;
+    if (bam_parse_header(&B, 0)) return -1;
+    BaiB b; memset(&b, 0, sizeof b); b.lin = calloc(BAI_LIN_N, sizeof *b.lin); b.first_read = 1; b.p_ref = -1; b.beg_vo = UINT64_MAX;
+    ob_put(&b.out, "BAI\1", 4); ob_u32(&b.out, (uint32_t)B.n_ref);
+    size_t off = B.first_rec; const uint8_t *u = B.z.u; int rc = 0;
+    while (off + 4 <= B.z.ulen) {
+        uint32_t bs = rd32(u + off); if (off + 4 + (size_t)bs > B.z.ulen) { rc = fail("not enough data in stream"); break; }
+        PRead r; if (parse_record(&B, u + off + 4, bs, &r)) { rc = -1; break; }
+        const uint64_t svo = voffset_of(&B.z, off), evo = voffset_of(&B.z, off + 4 + bs);
+        off += 4 + (size_t)bs;
+        const uint32_t bin = rd32(r.rec + 8) >> 16; const int unm = (r.flag & 0x4) != 0; const int32_t endp = r.pos + bases_covered(&r);
+        /* checkThatInputIsSorted :259-271 */
+        if (!b.first_read && r.ref_id != -1 && !(b.p_ref < r.ref_id) && !(r.ref_id == b.p_ref && r.pos >= b.p_pos)) { rc = fail("BAM file is not coordinate-sorted: read '%s' (%d:%d) must be after the previous read (%d:%d)", r.name, r.ref_id, r.pos, b.p_ref, b.p_pos); break; }
+        if (r.ref_id >= 0 && r.pos >= 0) {
+            if (b.first_read) {                              /* :301-311 */
+                b.first_read = 0; b.cur_beg = svo;
+                for (int i = 0; i < r.ref_id; i++) { ob_u32(&b.out, 0); ob_u32(&b.out, 0); }
+            } else {
+                if (r.ref_id > b.p_ref) {                    /* :316-323 */
+                    bb_update_linear(&b); bb_update_chunks(&b); bb_dump_reference(&b);
+                    for (int i = b.p_ref + 1; i < r.ref_id; i++) { ob_u32(&b.out, 0); ob_u32(&b.out, 0); }
+                } else if (r.ref_id == b.p_ref) {            /* :325-330 */
+                    bb_update_linear(&b);
+                    if (bin != b.p_bin) bb_update_chunks(&b);
+                }
+            }
+            b.p_ref = r.ref_id; b.p_pos = r.pos; b.p_end = endp; b.p_bin = bin; b.p_unmapped = unm; b.p_svo = svo; b.p_evo = evo;      /* updateLastReadInfo */
+        }
+        /* scope(exit) updateMetadata :117-131 */
+        if (r.ref_id == -1) b.no_coord++;
+        else { if (unm) b.unmapped++; else b.mapped++; if (b.beg_vo == UINT64_MAX) b.beg_vo = svo; b.end_vo = evo; }
+    }
+    if (!rc) {                                               /* finish :336-350 */
+        if (!b.first_read) { bb_update_linear(&b); bb_update_chunks(&b); bb_dump_reference(&b); }
+        for (int i = b.p_ref + 1; i < B.n_ref; i++) { ob_u32(&b.out, 0); ob_u32(&b.out, 0); }
+        ob_u64(&b.out, b.no_coord);
+    }
+    int64_t n = rc ? -1 : (int64_t)b.out.n;
+    if (!rc && out && cap >= b.out.n) memcpy(out, b.out.p, b.out.n);
+    free(b.out.p); free(b.lin); free(b.bins); bgzf_free(&B.z);
+    return n;
+}
+
 #ifdef ORACLE_MAIN
 int main(int argc, char **argv) {
     /* usage: depth_oracle [--inflate-threads N] [--max-file-bytes B] depth base|region|window ... ; prints timing to stderr with --stats */

@@ -112,6 +112,8 @@ def load_library():
     L.bdepth_inflate_to_host.restype = C.c_int64
     L.bdepth_scan_to_host.argtypes = [vp, C.c_uint64] + [vp] * 7
     L.bdepth_scan_to_host.restype = C.c_int64
+    L.bdepth_build_index.argtypes = [vp, vp, C.c_uint64]
+    L.bdepth_build_index.restype = C.c_int64
     _lib = L
     return L
 
@@ -121,7 +123,7 @@ EXPORTED_SYMBOLS = [
     "bdepth_ref_name", "bdepth_ref_length", "bdepth_header_text", "bdepth_is_coordinate_sorted", "bdepth_has_index",
     "bdepth_n_samples", "bdepth_sample_name", "bdepth_set_filter", "bdepth_set_filter_query", "bdepth_set_min_baseq", "bdepth_set_fix_mates", "bdepth_set_combined", "bdepth_set_regions",
     "bdepth_set_shard", "bdepth_nccl_unique_id", "bdepth_plan_shards", "bdepth_plan_region_chunks", "bdepth_set_tuning", "bdepth_stage", "bdepth_run_resident", "bdepth_run_base", "bdepth_run_base_text",
-    "bdepth_run_windows", "bdepth_run_regions", "bdepth_get_stats", "bdepth_ref_has_reads", "bdepth_inflate_to_host", "bdepth_scan_to_host",
+    "bdepth_run_windows", "bdepth_run_regions", "bdepth_get_stats", "bdepth_ref_has_reads", "bdepth_inflate_to_host", "bdepth_scan_to_host", "bdepth_build_index",
 ]
 
 
@@ -360,6 +362,14 @@ class BDepth:
         n2 = self._ck(self.L.bdepth_inflate_to_host(self.h, buf.ctypes.data_as(C.c_void_p), n))
         assert n2 == n
         return buf[:n]
+
+    def build_index(self):
+        """The BAI index of the file, built on the GPU (bytes); the handle adopts it."""
+        n = self._ck(self.L.bdepth_build_index(self.h, None, 0))
+        buf = np.zeros(max(1, n), np.uint8)
+        n2 = self._ck(self.L.bdepth_build_index(self.h, buf.ctypes.data_as(C.c_void_p), n))
+        assert n2 == n
+        return buf[:n].tobytes()
 
     def scan(self, cap):
         cols = dict(ref_id=np.zeros(cap, np.int32), pos=np.zeros(cap, np.int32), span=np.zeros(cap, np.uint32),

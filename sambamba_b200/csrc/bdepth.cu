@@ -17,6 +17,7 @@
 #include <unistd.h>
 #include <algorithm>
 #include <chrono>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -79,7 +80,7 @@ constexpr size_t EMIT_CHUNK = 4ull << 20;     // positions per D2H chunk
 constexpr uint32_t SHARD_EXTRA_BLOCKS = 8;
 constexpr uint32_t MATE_ZONE_BLOCKS = 64;       // -m on several ranks: blocks read behind the shard so that pairs cut by the boundary are seen whole
 
-enum RunMode { RUN_FULL = 0, RUN_INFLATE_ONLY = 1, RUN_SCAN_ONLY = 2 };
+enum RunMode { RUN_FULL = 0, RUN_INFLATE_ONLY = 1, RUN_SCAN_ONLY = 2, RUN_INDEX = 3 };
 constexpr int RC_RETRY_WINDOW = 1;      // internal: a read lies outside the counter window a multi-input run was given
 
 // ---- NCCL, bound at run time (dlopen) so that single-GPU users need no NCCL at all and so that a host
@@ -192,7 +193,10 @@ struct bdepth {
     HostScratch hs;
     std::vector<uint32_t> ref_has_host;
     // ---- optional per-read segment counting (window / region front ends), device arrays
-    struct SegSet { bool on = false; uint32_t n = 0; bool has_min = false, has_u = false; uint64_t ext_max = 0; DevBuf s, e, pmax, id, reads, minstart, bases_reads, mbases, ustart; } seg;
+    struct SegSet { bool on = false; uint32_t n = 0; bool has_min = false, has_u = false; uint64_t ext_max = 0; DevBuf s, e, pmax, id, reads, minstart, bases_reads, mbases, ustart, da, dac, db, dthr, dbases, dcov; } seg;
+    // ---- BAI builder (bdepth_build_index): device tables of k_index_scan, the runs / exceptions it handed out, the finished index
+    struct IndexSet { DevBuf lin, lin_len, lin_base, lin_cap, n_mapped, n_unmapped, carry, ctl, runs, excs; std::vector<uint32_t> base, cap; std::vector<IndexRun> h_runs; std::vector<IndexExc> h_excs; uint64_t n_lin = 0; } ix;
+    std::vector<uint8_t> built_bai;
     // ---- several BAM files (bdepth_add_input; MultiBamReader, multireader.d:218-268): the additional files are whole handles that
     // only hold their input (file, BGZF members, header, index, shard / sparse plan); a run swaps them into this handle one after
     // the other and accumulates into the same counters -- per-position counters and per-segment sums are additive over reads,
@@ -521,9 +525,14 @@ static bool plan_sparse(bdepth* h) {
     std::vector<HostRegion> rg; rg.reserve(h->regions.size());
     for (auto& g : h->regions) rg.push_back(HostRegion{g.ref_id, g.start, g.end});
     std::vector<BaiChunk> cs = region_chunks(h->bai, rg);
-    // Frame the members the chunks touch straight from the file (sorted by offset; no need for the whole file's table).
-    std::vector<HostBlock> L; bool file_end = false; uint64_t end_coff = 0;      // end_coff: offset after the last member once the end has been seen
+    // The members the chunks touch: the handle's table when it already covers the whole file (every open but the lazy one), else framed
+    // straight from the file as far as the chunks reach (sorted by offset; no need for the whole file's table).
+    const bool have_all = h->framed_all;
+    std::vector<HostBlock> Lown; const std::vector<HostBlock>& L = have_all ? P : Lown;
+    bool file_end = have_all; uint64_t end_coff = have_all ? P.back().coff + P.back().bsize : 0;      // end_coff: offset after the last member once the end has been seen
     auto frame_to = [&](uint64_t from, uint64_t to) -> bool {       // make sure every member starting in [from, to] is in L; from must be a member start
+        if (have_all) return true;
+        std::vector<HostBlock>& L = Lown;
         if (from >= h->file_len) return true;
         size_t off = (size_t)from; uint64_t dummy = 0; bool eof = false;
         if (!L.empty() && L.back().coff >= from) { if (L.back().coff >= to) return true; off = (size_t)(L.back().coff + L.back().bsize); }
@@ -688,6 +697,18 @@ int run_pipeline(bdepth* h, RunMode mode, RunOut* ro, Emitter* em = nullptr) {
     uint64_t carry_len = 0; bool first_batch = true;
     bool sparse_bad = false;         // a region chunk's record chain did not end at the chunk end (several ranks: decided together after the batches)
     uint64_t shard_min = UINT64_MAX, shard_max = 0;
+    if (mode == RUN_INDEX) {      // tables of k_index_scan: one linear-index row per reference (16 kbp windows up to one past the reference end), counters, carry
+        auto& X = h->ix; X.base.assign(nref + 1, 0); X.cap.assign(nref + 1, 0); uint64_t acc = 0;
+        for (size_t r = 0; r < nref; r++) { X.base[r] = (uint32_t)acc; X.cap[r] = (uint32_t)std::min<uint64_t>(32769, ((uint64_t)h->hdr.ref_len[r] >> 14) + 2); acc += X.cap[r]; if (acc > 0xFFFFFFF0ull) return fail(h, BDEPTH_ERR_ARG, "too many references for the linear index tables"); }
+        X.n_lin = acc; X.h_runs.clear(); X.h_excs.clear();
+        CK(X.lin.ensure((acc + 1) * 8)); CK(X.lin_len.ensure((nref + 1) * 4)); CK(X.lin_base.ensure((nref + 1) * 4)); CK(X.lin_cap.ensure((nref + 1) * 4));
+        CK(X.n_mapped.ensure((nref + 1) * 8)); CK(X.n_unmapped.ensure((nref + 1) * 8)); CK(X.carry.ensure(sizeof(IndexCarry))); CK(X.ctl.ensure(sizeof(IndexCtl)));
+        CK(cudaMemsetAsync(X.lin.p, 0xFF, (acc + 1) * 8, sm)); CK(cudaMemsetAsync(X.lin_len.p, 0, (nref + 1) * 4, sm)); CK(cudaMemsetAsync(X.n_mapped.p, 0, (nref + 1) * 8, sm)); CK(cudaMemsetAsync(X.n_unmapped.p, 0, (nref + 1) * 8, sm));
+        CK(cudaMemsetAsync(X.carry.p, 0, sizeof(IndexCarry), sm));
+        CK(cudaMemcpyAsync(X.lin_base.p, X.base.data(), (nref + 1) * 4, cudaMemcpyHostToDevice, sm)); CK(cudaMemcpyAsync(X.lin_cap.p, X.cap.data(), (nref + 1) * 4, cudaMemcpyHostToDevice, sm));
+        IndexCtl c0{0, 0, 0, ~0ull, ~0ull, 0, ~0ull, 0};
+        CK(cudaMemcpyAsync(X.ctl.p, &c0, sizeof c0, cudaMemcpyHostToDevice, sm)); CK(cudaStreamSynchronize(sm));
+    }
     CK(cudaEventRecord(h->ev[10], sm));
     size_t b = blk_lo;
     if (ro) { ro->inflate_len = 0; ro->scan_n = 0; }
@@ -822,7 +843,7 @@ int run_pipeline(bdepth* h, RunMode mode, RunOut* ro, Emitter* em = nullptr) {
                 CK(cudaEventRecord(h->k1_ev[j], ks));
                 // Sub-batches: a lane needs ~60 ms for its block however empty the GPU is, so the scan / coverage /
                 // delivery of the blocks that arrived first runs while the later chunks are still being inflated.
-                if (mode == RUN_FULL && !fix) subs.push_back(Sub{c0, c1, (int)j, (int)j}); else { if (subs.empty()) subs.push_back(Sub{b, b1, 0, (int)j}); subs[0].ev_hi = (int)j; }
+                if ((mode == RUN_FULL || mode == RUN_INDEX) && !fix) subs.push_back(Sub{c0, c1, (int)j, (int)j}); else { if (subs.empty()) subs.push_back(Sub{b, b1, 0, (int)j}); subs[0].ev_hi = (int)j; }
                 c0 = c1;
             }
         }
@@ -963,7 +984,7 @@ int run_pipeline(bdepth* h, RunMode mode, RunOut* ro, Emitter* em = nullptr) {
         const int64_t own_hi = (fix && h->world > 1 && h->limit_abs_u < h->total_u) ? (int64_t)h->limit_abs_u - (int64_t)batch_u0 : INT64_MAX;
         const int64_t zone_below = (!fix && !sparse && h->world > 1) ? (int64_t)h->own_lo_abs_u - (int64_t)batch_u0 : INT64_MIN;       // records of the previous ranks' zone
         UP(h->scan_stats.p, &zs, sizeof zs);
-        if (mode == RUN_SCAN_ONLY && !h->ref_has.p) { CK(h->ref_has.ensure((nref / 32 + 2) * 4)); CK(cudaMemsetAsync(h->ref_has.p, 0, (nref / 32 + 2) * 4, sm)); }
+        if ((mode == RUN_SCAN_ONLY || mode == RUN_INDEX) && !h->ref_has.p) { CK(h->ref_has.ensure((nref / 32 + 2) * 4)); CK(cudaMemsetAsync(h->ref_has.p, 0, (nref / 32 + 2) * 4, sm)); }
 #define K2_DECODE(F, G) BD_LAUNCH((unsigned)((nb * 32 + 255) / 256), 256, 0, sm, k2_decode<F, G>)(sp, h->chunk_start.as<int64_t>(), (uint32_t)nb, h->slot_base.as<uint32_t>(), h->slots.as<uint16_t>(), h->count.as<uint32_t>(), h->rec_base.as<uint32_t>(), soa, h->mapq_gt, h->flag_reject, h->scan_stats.as<ScanStats>(), h->long_list.as<uint32_t>(), h->ref_has.as<uint32_t>(), rgt, d_fprog, ghost_below, own_lo, own_hi, zone_below)
         if (fix) { if (d_fprog) K2_DECODE(true, true); else K2_DECODE(false, true); }
         else if (d_fprog) K2_DECODE(true, false);
@@ -995,6 +1016,24 @@ int run_pipeline(bdepth* h, RunMode mode, RunOut* ro, Emitter* em = nullptr) {
             }
             if (ro) ro->scan_n += R;
         }
+        // ---- BAI builder: the per-record part of IndexBuilder.put (bai/indexing.d:290-333) for this sub-batch's records
+        if (mode == RUN_INDEX && R) {
+            auto& X = h->ix;
+            CK(X.runs.ensure(R * sizeof(IndexRun))); CK(X.excs.ensure(R * sizeof(IndexExc)));
+            BD_LAUNCH((unsigned)((R + 255) / 256), 256, 0, sm, k_index_scan)(soa, u0, (uint32_t)R, (unsigned long long)batch_u0, (int)nref, X.lin_base.as<uint32_t>(), X.lin_cap.as<uint32_t>(), X.lin.as<unsigned long long>(), X.lin_len.as<uint32_t>(),
+                                                                               X.n_mapped.as<unsigned long long>(), X.n_unmapped.as<unsigned long long>(), X.carry.as<IndexCarry>(), X.runs.as<IndexRun>(), X.excs.as<IndexExc>(), X.ctl.as<IndexCtl>());
+            BD_LAUNCH(1, 32, 0, sm, k_index_carry)(soa, u0, (unsigned long long)batch_u0, X.carry.as<IndexCarry>(), X.ctl.as<IndexCtl>());
+            CK(cudaGetLastError()); st.gpu_launches += 2;
+            DOWN(icp, IndexCtl, X.ctl.p, sizeof(IndexCtl));
+            CK(cudaStreamSynchronize(sm));
+            const IndexCtl ic = *icp;
+            if (ic.bad_ref != ~0ull) return fail(h, BDEPTH_ERR_FORMAT, "record #%llu of the batch names a reference the header does not have", ic.bad_ref);
+            if (ic.unsorted != ~0ull) return fail(h, BDEPTH_ERR_FORMAT, "BAM file is not coordinate-sorted (record #%llu of the batch lies before the read in front of it)", ic.unsorted);
+            if (ic.past_end) return fail(h, BDEPTH_ERR_FORMAT, "%llu reads reach more than 16 kbp past the end of their reference: no index is built for such a file", ic.past_end);
+            if (ic.n_runs) { size_t o = X.h_runs.size(); X.h_runs.resize(o + ic.n_runs); CK(cudaMemcpy(X.h_runs.data() + o, X.runs.p, ic.n_runs * sizeof(IndexRun), cudaMemcpyDeviceToHost)); std::sort(X.h_runs.begin() + o, X.h_runs.end(), [](const IndexRun& a, const IndexRun& b) { return a.start_abs < b.start_abs; }); }
+            if (ic.n_exc) { size_t o = X.h_excs.size(); X.h_excs.resize(o + ic.n_exc); CK(cudaMemcpy(X.h_excs.data() + o, X.excs.p, ic.n_exc * sizeof(IndexExc), cudaMemcpyDeviceToHost)); std::sort(X.h_excs.begin() + o, X.h_excs.end(), [](const IndexExc& a, const IndexExc& b) { return a.start_abs < b.start_abs; }); }
+            CK(cudaMemsetAsync(X.ctl.p, 0, 16, sm));      // n_runs, n_exc
+        }
         // ---- per-read segment counting (countRead, depth.d:661-669) for the window / region front ends
         if (mode == RUN_FULL && h->seg.on && h->seg.n && ss.n_pass) {
             if (h->minq) BD_LAUNCH((unsigned)((R + 127) / 128), 128, 0, sm, k_read_segments<true>)(soa, u0, (uint32_t)R, h->seg.s.as<uint64_t>(), h->seg.e.as<uint64_t>(), h->seg.pmax.as<uint64_t>(), h->seg.id.as<uint32_t>(), h->seg.has_min ? h->seg.minstart.as<uint64_t>() : nullptr, h->seg.n, h->seg.reads.as<uint32_t>(), h->minq, h->S, h->seg.has_min ? h->seg.bases_reads.as<uint32_t>() : nullptr);
@@ -1003,9 +1042,11 @@ int run_pipeline(bdepth* h, RunMode mode, RunOut* ro, Emitter* em = nullptr) {
         }
         uint64_t idx_tiles_base = 0; uint32_t idx_n_tiles = 0;      // K3's per-tile read index of this sub-batch (the mate kernels look reads up through it)
         // ---- K3
-        if (mode == RUN_FULL && (ss.n_pass || ss.n_zone_pass)) {
-            uint64_t gmin = std::min<uint64_t>(ss.min_start, ss.min_start_all), gmax = ss.max_end;
-            if (ss.n_zone_pass && gmin < h->cnt_base) gmin = h->cnt_base;      // a zone read may begin before the window; only what reaches this rank's positions matters
+        uint64_t gmin = std::min<uint64_t>(ss.min_start, ss.min_start_all), gmax = ss.max_end;
+        if (ss.n_zone_pass && gmin < h->cnt_base) gmin = h->cnt_base;      // a zone read may begin before the window; only what reaches this rank's positions matters
+        // (a sub-batch of the zone's first blocks can hold nothing but reads that end before this rank's first position -- the linear index
+        // points at the first read that overlaps the 16 kbp window, the short reads behind it need not: nothing to count then)
+        if (mode == RUN_FULL && (ss.n_pass || ss.n_zone_pass) && gmax > gmin) {
             if (gmin < h->cnt_base || gmax > h->cnt_base + h->win_len) {
                 // the index does not describe this file (the reference only checks that one exists, depth.d:1166):
                 // start over with the whole genome as the counter window
@@ -1306,7 +1347,8 @@ void bdepth_close(bdepth_t* h) {
     for (DevBuf* b : bufs) b->release();
     h->rg_ids.release(); h->rg_offs.release(); h->rg_samp.release();
     h->text[0].release(); h->text[1].release(); h->text_tiles.release(); h->text_offs.release(); h->text_zero.release(); h->text_samp.release(); h->present.release();
-    h->seg.s.release(); h->seg.e.release(); h->seg.pmax.release(); h->seg.id.release(); h->seg.reads.release(); h->seg.minstart.release(); h->seg.bases_reads.release(); h->seg.mbases.release(); h->seg.ustart.release();
+    h->seg.s.release(); h->seg.e.release(); h->seg.pmax.release(); h->seg.id.release(); h->seg.reads.release(); h->seg.minstart.release(); h->seg.bases_reads.release(); h->seg.mbases.release(); h->seg.ustart.release(); h->seg.da.release(); h->seg.dac.release(); h->seg.db.release(); h->seg.dthr.release(); h->seg.dbases.release(); h->seg.dcov.release();
+    { auto& X = h->ix; X.lin.release(); X.lin_len.release(); X.lin_base.release(); X.lin_cap.release(); X.n_mapped.release(); X.n_unmapped.release(); X.carry.release(); X.ctl.release(); X.runs.release(); X.excs.release(); }
     h->m_hash.release(); h->m_flag.release(); h->m_flt.release(); h->m_ctl.release(); h->fprog_d.release();
     if (h->comm) { nccl().CommDestroy(h->comm); h->comm = nullptr; }
     if (h->pinned) cudaFreeHost(h->pinned);
@@ -1586,7 +1628,8 @@ static int run_segments(bdepth* h, const std::vector<SegDef>& segs, const uint32
     }
     // sorted view for the per-read kernel
     std::vector<uint32_t> order(n); for (size_t i = 0; i < n; i++) order[i] = (uint32_t)i;
-    std::sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return a[x] != a[y] ? a[x] < a[y] : x < y; });
+    if (!std::is_sorted(a.begin(), a.end()))      // windows and a sorted BED already are: 310 k windows would cost ~20 ms to sort again
+        std::sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return a[x] != a[y] ? a[x] < a[y] : x < y; });
     std::vector<uint64_t> ss(n), se(n), pm(n), ms(n), us(n); uint64_t mx = 0, ext_max = 0; bool has_min = false, has_u = false;
     for (size_t i = 0; i < n; i++) {
         ss[i] = a[order[i]]; se[i] = b[order[i]]; mx = std::max(mx, se[i]); pm[i] = mx;
@@ -1605,6 +1648,7 @@ static int run_segments(bdepth* h, const std::vector<SegDef>& segs, const uint32
     CK(cudaMemset(S.reads.p, 0, NS * nn * 4)); CK(cudaMemset(S.bases_reads.p, 0, NS * nn * 4)); CK(cudaMemset(S.mbases.p, 0, NS * nn * 4));
     if (n) CK(cudaMemcpy(S.minstart.p, ms.data(), n * 8, cudaMemcpyHostToDevice));
     CK(S.ustart.ensure(nn * 8)); if (n) CK(cudaMemcpy(S.ustart.p, us.data(), n * 8, cudaMemcpyHostToDevice));
+    CK(S.da.ensure(nn * 8)); CK(S.dac.ensure(nn * 8)); CK(S.db.ensure(nn * 8)); CK(S.dthr.ensure(64)); CK(S.dbases.ensure(NS * nn * 4)); CK(S.dcov.ensure(NS * nn * 4 * nt1));
     S.has_min = has_min; S.has_u = has_u; S.ext_max = ext_max;
     S.on = true; S.n = (uint32_t)n;
     rc = run_all_inputs(h);
@@ -1614,9 +1658,7 @@ static int run_segments(bdepth* h, const std::vector<SegDef>& segs, const uint32
     cudaEvent_t e0 = h->ev[5], e1 = h->ev[6];
     CK(cudaEventRecord(e0, sm));
     // per-segment sums over the counters (original order)
-    struct Scratch { DevBuf da, dac, db, dthr, dbases, dcov; ~Scratch() { da.release(); dac.release(); db.release(); dthr.release(); dbases.release(); dcov.release(); } } scr;      // released on every return path
-    DevBuf &da = scr.da, &dac = scr.dac, &db = scr.db, &dthr = scr.dthr, &dbases = scr.dbases, &dcov = scr.dcov;
-    CK(da.ensure(nn * 8)); CK(dac.ensure(nn * 8)); CK(db.ensure(nn * 8)); CK(dthr.ensure(64)); CK(dbases.ensure(NS * nn * 4)); CK(dcov.ensure(NS * nn * 4 * nt1));
+    DevBuf &da = S.da, &dac = S.dac, &db = S.db, &dthr = S.dthr, &dbases = S.dbases, &dcov = S.dcov;      // the handle's (sized before the pipeline ran, released with it): no allocation per call
     std::vector<uint64_t> acv(n); std::vector<uint32_t> qbases, mbases;
     for (size_t i = 0; i < n; i++) {
         uint64_t lo = std::max(h->cnt_base, h->own_lo), hi = std::min(h->cnt_base + h->win_len, h->own_hi); if (hi < lo) hi = lo;
@@ -1740,6 +1782,75 @@ int bdepth_run_regions(bdepth_t* h, const bdepth_region* regions, size_t n, cons
     if (!cb) return 0;
     for (size_t i = 0; i < n; i++) { rc = deliver_one(h, segs[i], i, n, n_thr, reads, bases, cov, false, cb, user, i); if (rc) return rc; }
     return 0;
+}
+
+// ---- BAI builder ------------------------------------------------------------------------------------------------------------------
+// The per-run part of IndexBuilder (bai/indexing.d): chunks from the runs (updateChunks :219-246), metadata (:117-131, :198-203), the
+// linear index with its gaps filled from the left (:163-182), empty references (:98-101), n_no_coor (:348).  Bins are written in
+// ascending order (the reference: iteration order of a D associative array, :188 -- not defined by anything but that runtime).
+static int assemble_bai(bdepth* h) {
+    auto& X = h->ix; const auto& B = h->blocks; const size_t nref = h->hdr.ref_len.size();
+    std::vector<unsigned long long> lin(X.n_lin + 1), nm(nref + 1), nu(nref + 1); std::vector<uint32_t> ll(nref + 1);
+    IndexCtl ctl; IndexCarry carry;
+    CK(cudaMemcpy(lin.data(), X.lin.p, (X.n_lin + 1) * 8, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(ll.data(), X.lin_len.p, (nref + 1) * 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(nm.data(), X.n_mapped.p, (nref + 1) * 8, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(nu.data(), X.n_unmapped.p, (nref + 1) * 8, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(&ctl, X.ctl.p, sizeof ctl, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(&carry, X.carry.p, sizeof carry, cudaMemcpyDeviceToHost));
+    const uint64_t end_coff = B.empty() ? 0 : B.back().coff + B.back().bsize;
+    auto vo = [&](uint64_t u) -> uint64_t {      // BgzfInputStream.virtualTell() at inflated offset u: the end of a member is the start of the next one
+        if (B.empty() || u >= h->total_u) return end_coff << 16;
+        size_t lo = 0, hi = B.size(); while (lo + 1 < hi) { size_t m = (lo + hi) / 2; if (B[m].uoff <= u) lo = m; else hi = m; }
+        return (B[lo].coff << 16) | (u - B[lo].uoff);
+    };
+    std::vector<uint8_t>& out = h->built_bai; out.clear();
+    auto p32 = [&](uint32_t v) { for (int i = 0; i < 4; i++) out.push_back((uint8_t)(v >> (8 * i))); };
+    auto p64 = [&](uint64_t v) { p32((uint32_t)v); p32((uint32_t)(v >> 32)); };
+    out.insert(out.end(), {'B', 'A', 'I', 1}); p32((uint32_t)nref);
+    const auto& R = X.h_runs; const auto& E = X.h_excs;
+    size_t next_ref = 0, e_i = 0;
+    for (size_t i0 = 0; i0 < R.size();) {
+        size_t i1 = i0; while (i1 < R.size() && R[i1].ref == R[i0].ref) i1++;
+        const size_t r = (size_t)R[i0].ref;
+        for (; next_ref < r; next_ref++) { p32(0); p32(0); }
+        std::map<uint32_t, std::vector<std::pair<uint64_t, uint64_t>>> bins;
+        for (size_t k = i0; k < i1; k++) {
+            const uint64_t beg = vo(R[k].prev_end_abs == ~0ull ? R[k].start_abs : R[k].prev_end_abs), end = vo(k + 1 < R.size() ? R[k + 1].prev_end_abs : carry.end_abs);
+            auto& cs = bins[R[k].bin];
+            if (cs.empty() || (cs.back().second >> 16) != (beg >> 16)) cs.push_back({beg, end}); else cs.back().second = end;
+        }
+        // metadata: reads with a reference but no position count where the stream stood (before the next reference's first valid read)
+        const uint64_t next_start = i1 < R.size() ? R[i1].start_abs : UINT64_MAX;
+        uint64_t mapped = nm[r], unmapped = nu[r], end_abs = i1 < R.size() ? R[i1].prev_end_abs : carry.end_abs;
+        for (; e_i < E.size() && E[e_i].start_abs < next_start; e_i++) { if (E[e_i].unmapped) unmapped++; else mapped++; if (E[e_i].end_abs > end_abs) end_abs = E[e_i].end_abs; }
+        const uint64_t beg_vo = i0 == 0 ? vo(ctl.first_placed_abs) : vo(R[i0].prev_end_abs);
+        p32((uint32_t)bins.size() + 1);
+        for (auto& kv : bins) { p32(kv.first); p32((uint32_t)kv.second.size()); for (auto& c : kv.second) { p64(c.first); p64(c.second); } }
+        p32(37450); p32(2); p64(beg_vo); p64(vo(end_abs)); p64(mapped); p64(unmapped);
+        p32(ll[r]);
+        uint64_t last = 0;
+        for (uint32_t w = 0; w < ll[r]; w++) { unsigned long long a = lin[X.base[r] + w]; uint64_t v = a == ~0ull ? 0 : vo(a); if (v == 0) v = last; else last = v; p64(v); }
+        next_ref = r + 1; i0 = i1;
+    }
+    for (; next_ref < nref; next_ref++) { p32(0); p32(0); }
+    p64(ctl.no_coord);
+    return 0;
+}
+
+int64_t bdepth_build_index(bdepth_t* h, void* dst, uint64_t cap) {
+    if (!h) return BDEPTH_ERR_ARG;
+    if (h->world > 1) return fail(h, BDEPTH_ERR_ARG, "the index is built by one rank (the shards of a run are cut from it)");
+    if (h->built_bai.empty()) {
+        const bool save_staged = h->staged; h->staged = false;
+        int rc = run_pipeline(h, RUN_INDEX, nullptr);
+        h->staged = save_staged;
+        if (rc) return rc;
+        rc = assemble_bai(h); if (rc) return rc;
+        h->ix.h_runs.clear(); h->ix.h_runs.shrink_to_fit(); h->ix.h_excs.clear();
+        // the handle adopts what it built: sharding, counter windows and region queries work on un-indexed input from here on
+        h->bai = BaiIndex{}; if (!parse_bai(h->built_bai.data(), h->built_bai.size(), h->bai)) return fail(h, BDEPTH_ERR_FORMAT, "internal: the built index does not parse");
+        h->has_index = true; h->sparse_ok = true; h->bai_window_ok = true; h->shard_ready = false;
+    }
+    if (dst && cap >= h->built_bai.size()) memcpy(dst, h->built_bai.data(), h->built_bai.size());
+    return (int64_t)h->built_bai.size();
 }
 
 int bdepth_ref_has_reads(const bdepth_t* h, int ref) {

@@ -207,10 +207,34 @@ static void region_header(Ctx& c, size_t n_before) {      // depth.d:643-659
     o.ch('\n'); o.flush(); fflush(o.f);
 }
 
+// `sambamba index input.bam [output.bai]` (index_main, sambamba/index.d:56-130) with the index built on the GPU (bdepth_build_index):
+// -t / -p are accepted, -c (check bins) and -F (FASTA) are not offered.  Errors as "sambamba-index: <msg>", exit code 1.
+static int index_main(Args& a) {
+    a.v.erase(a.v.begin() + 1);
+    std::vector<std::string> v;
+    opt_take(a, "nthreads", 't', true, &v); opt_take(a, "show-progress", 'p', false, nullptr);
+    if (a.v.size() != 2 && a.v.size() != 3) {
+        fprintf(stderr, "Usage: sambamba-index [OPTIONS] <input.bam> [output_file]\n\n\tCreates index for a BAM file\n\nOptions: -t, --nthreads=NTHREADS\n               accepted for compatibility (the index is built on the GPU)\n         -p, --show-progress\n               accepted for compatibility\n");
+        return 0;
+    }
+    const std::string in = a.v[1], out = a.v.size() > 2 ? a.v[2] : in + ".bai";
+    bdepth_t* h = nullptr;
+    if (bdepth_open(in.c_str(), 0, &h)) { fprintf(stderr, "sambamba-index: %s\n", bdepth_last_error(nullptr)); return 1; }
+    int64_t n = bdepth_build_index(h, nullptr, 0);
+    if (n < 0) { fprintf(stderr, "sambamba-index: %s\n", bdepth_last_error(h)); bdepth_close(h); return 1; }
+    std::vector<uint8_t> buf((size_t)n);
+    if (bdepth_build_index(h, buf.data(), (uint64_t)n) != n) { fprintf(stderr, "sambamba-index: %s\n", bdepth_last_error(h)); bdepth_close(h); return 1; }
+    bdepth_close(h);
+    FILE* f = fopen(out.c_str(), "wb");
+    if (!f || fwrite(buf.data(), 1, buf.size(), f) != buf.size() || fclose(f) != 0) { fprintf(stderr, "sambamba-index: Cannot open file `%s' in mode `wb'\n", out.c_str()); return 1; }
+    return 0;
+}
+
 int main(int argc, char** argv) {
     // accept both `sambamba-depth-b200 base ...` and `sambamba-depth-b200 depth base ...`
     Args a; for (int i = 0; i < argc; i++) a.v.push_back(argv[i]);
     if (a.v.size() > 1 && a.v[1] == "depth") a.v.erase(a.v.begin() + 1);
+    if (a.v.size() > 1 && a.v[1] == "index") return index_main(a);
     if (a.v.size() < 3) { usage(); return 0; }
     Ctx c;
     if (a.v[1] == "base") c.mode = 0; else if (a.v[1] == "region") c.mode = 1; else if (a.v[1] == "window") c.mode = 2; else { usage(); return 0; }
@@ -232,6 +256,7 @@ int main(int argc, char** argv) {
     if (opt_take(a, "annotate", 'a', false, nullptr) > 0) c.annotate = true;
     if (opt_take(a, "combined", 0, false, nullptr) > 0) c.combined = true;
     if (opt_take(a, "fix-mate-overlaps", 'm', false, nullptr) > 0) fix_mates = true;
+    const bool build_index = opt_take(a, "build-index", 0, false, nullptr) > 0;      // not a sambamba option: index un-indexed input on the GPU instead of refusing it
     c.out.f = out_fn.empty() ? stdout : fopen(out_fn.c_str(), "w+");
     if (!c.out.f) return die("Cannot open file `" + out_fn + "' in mode `w+'");
     if (c.mode != 2 && opt_take(a, "regions", 'L', true, &v) > 0) { bed_fn = v.back(); has_bed = true; } v.clear();
@@ -270,6 +295,7 @@ int main(int argc, char** argv) {
     if (rc) return die(bdepth_last_error(nullptr));
     for (size_t fi = 2; fi < a.v.size(); fi++) if (bdepth_add_input(c.h, a.v[fi].c_str())) return die(bdepth_last_error(c.h));      // new MultiBamReader(bam_filenames), depth.d:1162-1163
     if (!bdepth_is_coordinate_sorted(c.h)) return die("All files must be coordinate-sorted");
+    if (!bdepth_has_index(c.h) && build_index && a.v.size() == 2) { if (bdepth_build_index(c.h, nullptr, 0) < 0) return die(bdepth_last_error(c.h)); }
     if (!bdepth_has_index(c.h)) return die("All files must be indexed");
     int nref = bdepth_n_ref(c.h);
     for (int i = 0; i < nref; i++) c.ref_names.push_back(bdepth_ref_name(c.h, i));

@@ -950,6 +950,104 @@ __global__ void k3_scatter_long(RecordSoA soa, const uint8_t* __restrict__ u, co
     }
 }
 
+// ------------------------------------------------------------------------------------- BAI builder
+// What `sambamba index` computes over the record stream (IndexBuilder, BioD/bio/std/hts/bam/bai/indexing.d:56-351), split so that the
+// per-record part runs here, one thread per record of a sub-batch, and only the per-run part (one entry per change of bin) is left to the
+// host (bdepth.cu: assemble_bai):
+//   * linear index (:133-161): every read with a reference and a position >= 0 ("valid") offers its start to the 16 kbp windows it covers
+//     -- [pos, pos + basesCovered - 1], an unmapped read only its own window; the smallest start offset wins (= the first in file order);
+//     offsets here are positions in the inflated stream, the host turns them into virtual offsets;
+//   * chunks (:219-246, :325-330): a chunk ends where the bin of the valid reads changes (or a new reference begins): such a read emits a
+//     run entry with the end of the valid read before it (the reference's _current_chunk_beg);
+//   * metadata (:117-131): mapped / unmapped reads per reference, reads without reference; the rare reads that have a reference but no
+//     position take no part in the index yet count in the metadata of whatever reference is current: they go to the host as exceptions;
+//   * the sortedness check (:259-271) against the previous valid read.
+// The previous valid read of the sub-batch's first records is the carry (written by k_index_carry at the end of the previous sub-batch).
+struct IndexCarry { unsigned long long has, key, end_abs; int ref, pos; };
+struct IndexRun { unsigned long long start_abs, prev_end_abs; int ref; uint32_t bin; };       // prev_end_abs = ~0: no valid read before it
+struct IndexExc { unsigned long long start_abs, end_abs; int ref; uint32_t unmapped; };
+struct IndexCtl {
+    unsigned long long n_runs, n_exc, last_valid /* 1 + record index */, first_placed_abs, unsorted /* 1 + record index */, past_end, bad_ref, no_coord;
+};
+struct IndexRec { int ref, pos; uint32_t bin, unmapped; int64_t end_pos /* pos + basesCovered */; unsigned long long abs_s, abs_e; };
+
+__device__ __forceinline__ IndexRec index_rec(const RecordSoA& soa, const uint8_t* u, uint32_t r, unsigned long long batch_u0) {
+    const int64_t o = soa.off[r];                       // of refID; block_size sits 4 bytes below
+    const uint8_t* p = u + o;
+    IndexRec x;
+    x.ref = (int)ldu32(p); x.pos = (int)ldu32(p + 4);
+    const uint32_t bmn = ldu32(p + 8), fnc = ldu32(p + 12), bs = ldu32(p - 4);
+    x.bin = bmn >> 16; x.unmapped = (fnc >> 16) & 4u ? 1u : 0u;
+    const uint32_t l_name = bmn & 0xFF, n_cigar = fnc & 0xFFFF;
+    int64_t bc = 0;
+    if (!x.unmapped) { const uint8_t* cg = p + 32 + l_name; for (uint32_t i = 0; i < n_cigar; i++) { uint32_t c = ldu32(cg + 4 * i); if (cig_rcons(c & 15)) bc += c >> 4; } }      // basesCovered (read.d:255-262)
+    x.end_pos = (int64_t)x.pos + bc;
+    x.abs_s = batch_u0 + (unsigned long long)(o - 4); x.abs_e = x.abs_s + 4ull + bs;
+    return x;
+}
+
+__global__ void k_index_scan(RecordSoA soa, const uint8_t* __restrict__ u, uint32_t R, unsigned long long batch_u0, int n_ref,
+                             const uint32_t* __restrict__ lin_base, const uint32_t* __restrict__ lin_cap, unsigned long long* __restrict__ lin, uint32_t* __restrict__ lin_len,
+                             unsigned long long* __restrict__ n_mapped, unsigned long long* __restrict__ n_unmapped,
+                             const IndexCarry* __restrict__ carry, IndexRun* __restrict__ runs, IndexExc* __restrict__ excs, IndexCtl* __restrict__ ctl) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31;
+    const bool in = r < R;
+    IndexRec x{-1, -1, 0, 0, 0, 0, 0};
+    if (in) x = index_rec(soa, u, r, batch_u0);
+    const bool valid = in && x.ref >= 0 && x.pos >= 0, placed = in && x.ref != -1;
+    if (in && x.ref >= n_ref) { atomicMin(&ctl->bad_ref, (unsigned long long)r + 1); }
+    const bool ok_ref = x.ref < n_ref;
+    if (placed) {
+        // the valid read before this one: normally r - 1; reads without position are rare, a tail of unplaced reads never looks back
+        bool have = false; int pref = -1, ppos = -1; unsigned long long pkey = 0, pend = ~0ull;
+        for (int64_t q = (int64_t)r - 1; q >= 0; q--) {
+            IndexRec y = index_rec(soa, u, (uint32_t)q, batch_u0);
+            if (y.ref >= 0 && y.pos >= 0) { have = true; pref = y.ref; ppos = y.pos; pkey = ((unsigned long long)(uint32_t)y.ref << 32) | y.bin; pend = y.abs_e; break; }
+        }
+        if (!have && carry->has) { have = true; pref = carry->ref; ppos = carry->pos; pkey = carry->key; pend = carry->end_abs; }
+        if (have && !(pref < x.ref) && !(x.ref == pref && x.pos >= ppos)) atomicMin(&ctl->unsorted, (unsigned long long)r + 1);      // checkThatInputIsSorted
+        if (ctl->first_placed_abs > x.abs_s) atomicMin(&ctl->first_placed_abs, x.abs_s);
+        if (valid && ok_ref) {
+            const unsigned long long key = ((unsigned long long)(uint32_t)x.ref << 32) | x.bin;
+            if (!have || key != pkey) { unsigned long long i = atomicAdd(&ctl->n_runs, 1ull); runs[i] = IndexRun{x.abs_s, have ? pend : ~0ull, x.ref, x.bin}; }
+            const int64_t last = x.unmapped ? (int64_t)x.pos : x.end_pos - 1;
+            const uint32_t w0 = (uint32_t)x.pos >> 14, w1 = last < 0 ? 0u : (uint32_t)(last >> 14);
+            const uint32_t cap = lin_cap[x.ref]; unsigned long long* L = lin + lin_base[x.ref];
+            for (uint32_t w = w0; w <= w1; w++) {
+                if (w >= cap) { atomicAdd(&ctl->past_end, 1ull); break; }
+                if (L[w] > x.abs_s) atomicMin(&L[w], x.abs_s);
+            }
+            if (w1 + 1 <= cap && lin_len[x.ref] < w1 + 1) atomicMax(&lin_len[x.ref], w1 + 1);
+        } else if (!valid) {
+            unsigned long long i = atomicAdd(&ctl->n_exc, 1ull); excs[i] = IndexExc{x.abs_s, x.abs_e, x.ref, x.unmapped};
+        }
+    }
+    // metadata counters: one atomic per warp when the warp's reads share a reference (sorted input: nearly always)
+    const int cref = !in ? -2 : (valid && ok_ref) ? x.ref : (x.ref == -1 ? -1 : -2);      // -1: no reference; -2: counted elsewhere (exception) or nothing
+    const int cref0 = __shfl_sync(0xFFFFFFFFu, cref, 0);
+    const bool same = __all_sync(0xFFFFFFFFu, cref == cref0 || cref == -2);
+    if (same) {
+        const uint32_t bm = __ballot_sync(0xFFFFFFFFu, cref >= 0 && !x.unmapped), bu = __ballot_sync(0xFFFFFFFFu, cref >= 0 && x.unmapped), bn = __ballot_sync(0xFFFFFFFFu, cref == -1);
+        const uint32_t any = __ballot_sync(0xFFFFFFFFu, cref >= 0); const int rr = __shfl_sync(0xFFFFFFFFu, cref, any ? (31 - __clz(any)) : 0);
+        if (lane == 0) { if (bm) atomicAdd(&n_mapped[rr], (unsigned long long)__popc(bm)); if (bu) atomicAdd(&n_unmapped[rr], (unsigned long long)__popc(bu)); if (bn) atomicAdd(&ctl->no_coord, (unsigned long long)__popc(bn)); }
+    } else {
+        if (cref >= 0) { if (x.unmapped) atomicAdd(&n_unmapped[cref], 1ull); else atomicAdd(&n_mapped[cref], 1ull); }
+        else if (cref == -1) atomicAdd(&ctl->no_coord, 1ull);
+    }
+    const uint32_t bv = __ballot_sync(0xFFFFFFFFu, valid && ok_ref);
+    if (bv && lane == 31 - __clz(bv)) { if (ctl->last_valid < (unsigned long long)r + 1) atomicMax(&ctl->last_valid, (unsigned long long)r + 1); }
+}
+
+// the last valid read of the sub-batch becomes the carry of the next one
+__global__ void k_index_carry(RecordSoA soa, const uint8_t* __restrict__ u, unsigned long long batch_u0, IndexCarry* __restrict__ carry, IndexCtl* __restrict__ ctl) {
+    if (threadIdx.x || blockIdx.x) return;
+    if (ctl->last_valid) {
+        IndexRec y = index_rec(soa, u, (uint32_t)(ctl->last_valid - 1), batch_u0);
+        carry->has = 1; carry->key = ((unsigned long long)(uint32_t)y.ref << 32) | y.bin; carry->end_abs = y.abs_e; carry->ref = y.ref; carry->pos = y.pos;
+    }
+    ctl->last_valid = 0;
+}
+
 // ------------------------------------------------------------------------------------- reducers
 // number of positions in [a, b) (window-relative) whose 7 counters sum to > 0
 __global__ void k_count_covered(const uint32_t* __restrict__ counts, uint64_t win_len, uint64_t a, uint64_t b, unsigned long long* __restrict__ out, int n_planes) {

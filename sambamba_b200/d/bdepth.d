@@ -82,6 +82,8 @@ int bdepth_get_stats(const(bdepth_t)* h, bdepth_stats* s);
 int bdepth_ref_has_reads(const(bdepth_t)* h, int r);
 long bdepth_inflate_to_host(bdepth_t* h, void* dst, ulong cap);
 long bdepth_scan_to_host(bdepth_t* h, ulong cap, int* ref_id, int* pos, uint* span, ushort* flag, ubyte* mapq, ushort* n_cigar, ulong* rec_off);
+/// createIndex (bio/std/hts/bam/bai/indexing.d:356) on the GPU; the handle adopts the index
+long bdepth_build_index(bdepth_t* h, void* dst, ulong cap);
 
 /+ ---------------------------------------------------------------------------------------------------------
    Sketch of the sambamba-side patch (sambamba/depth.d).  The option parsing of depth_main (depth.d:1121-1152)

@@ -87,6 +87,50 @@ def oracle_segment_stats(path, seg_a, seg_b, thresholds=(), mapq_gt=0, flag_reje
     return reads[:n], bases[:n], cov[:len(thr), :n]
 
 
+def oracle_build_bai(path, threads=4):
+    """The BAI index as the reference's IndexBuilder computes it (oracle_build_bai in oracle/depth_oracle.c), bins ascending."""
+    import ctypes as C
+    o = oracle()
+    o.oracle_build_bai.restype = C.c_int64
+    o.oracle_build_bai.argtypes = [C.c_char_p, C.c_void_p, C.c_uint64, C.c_int]
+    n = o.oracle_build_bai(path.encode(), None, 0, threads)
+    if n < 0:
+        o.oracle_last_error.restype = C.c_char_p
+        raise RuntimeError(o.oracle_last_error().decode())
+    buf = (C.c_uint8 * n)()
+    assert o.oracle_build_bai(path.encode(), buf, n, threads) == n
+    return bytes(buf)
+
+
+def parse_bai(b):
+    """A .bai as ([(bins: {bin: [(beg, end)...]}, linear: [...])...], n_no_coor) -- independent of the order the bins were written in."""
+    import struct
+    assert b[:4] == b"BAI\x01"
+    n_ref, = struct.unpack_from("<i", b, 4)
+    o = 8
+    refs = []
+    for _ in range(n_ref):
+        n_bin, = struct.unpack_from("<i", b, o)
+        o += 4
+        bins = {}
+        for _ in range(n_bin):
+            bin_, n_chunk = struct.unpack_from("<Ii", b, o)
+            o += 8
+            assert bin_ not in bins
+            bins[bin_] = [struct.unpack_from("<QQ", b, o + 16 * k) for k in range(n_chunk)]
+            o += 16 * n_chunk
+        n_intv, = struct.unpack_from("<i", b, o)
+        o += 4
+        refs.append((bins, list(struct.unpack_from("<%dQ" % n_intv, b, o))))
+        o += 8 * n_intv
+    tail = None
+    if o + 8 <= len(b):
+        tail, = struct.unpack_from("<Q", b, o)
+        o += 8
+    assert o == len(b)
+    return refs, tail
+
+
 def oracle_counts_fix_mates(path, mapq_gt=0, flag_reject=0x600, min_bq=0, window=None):
     """Closed form for `-m` (base mode): counts[7, n] over the linear window and the number of (pair, column) fixes."""
     L = oracle()
@@ -164,9 +208,19 @@ def header_first_record_offset(u):
     return off, refs
 
 
-def write_bam(path, refs, reads, rg=None, block=0xFF00, level=6, quals=None, tags=None):
+def reg2bin(beg, end):
+    """The BAI bin of [beg, end) (SAM specification; BioD/bio/std/hts/bam/bai/bin.d:82-92)."""
+    end -= 1
+    for shift, base in ((14, 4681), (17, 585), (20, 73), (23, 9), (26, 1)):
+        if beg >> shift == end >> shift:
+            return base + (beg >> shift)
+    return 0
+
+
+def write_bam(path, refs, reads, rg=None, block=0xFF00, level=6, quals=None, tags=None, bins=None, index=True):
     """Minimal BAM + dummy BAI writer for hand-made reads: (ref, pos, mapq, flag, cigar[(len,op)], seq, name).
-    quals: optional list of per-read quality lists (default 30 everywhere); tags: optional per-read raw aux bytes."""
+    quals: optional list of per-read quality lists (default 30 everywhere); tags: optional per-read raw aux bytes;
+    bins: optional per-read bin fields (default 4680 everywhere; "auto": reg2bin of the alignment); index=False: no .bai."""
     import struct
     import zlib
     text = "@HD\tVN:1.6\tSO:coordinate\n" + "".join(f"@SQ\tSN:{n}\tLN:{l}\n" for n, l in refs)
@@ -181,7 +235,14 @@ def write_bam(path, refs, reads, rg=None, block=0xFF00, level=6, quals=None, tag
         packed = bytearray()
         for i in range(0, len(seq), 2):
             packed.append((code[seq[i]] << 4) | (code[seq[i + 1]] if i + 1 < len(seq) else 0))
-        rec = struct.pack("<iiIIiiii", ref, pos, (4680 << 16) | (mapq << 8) | len(nm), (flag << 16) | len(cigar), len(seq), -1, -1, 0)
+        if bins is None:
+            bin_ = 4680
+        elif bins == "auto":
+            span = 0 if flag & 4 else sum(l for l, op in cigar if op in (0, 2, 3, 7, 8))
+            bin_ = reg2bin(max(pos, 0), max(pos, 0) + max(span, 1))
+        else:
+            bin_ = bins[ri]
+        rec = struct.pack("<iiIIiiii", ref, pos, (bin_ << 16) | (mapq << 8) | len(nm), (flag << 16) | len(cigar), len(seq), -1, -1, 0)
         rec += nm + b"".join(struct.pack("<I", (l << 4) | op) for l, op in cigar) + bytes(packed) + (bytes(quals[ri]) if quals else bytes([30] * len(seq))) + (tags[ri] if tags else b"")
         body += struct.pack("<i", len(rec)) + rec
     with open(path, "wb") as f:
@@ -191,6 +252,8 @@ def write_bam(path, refs, reads, rg=None, block=0xFF00, level=6, quals=None, tag
             d = c.compress(chunk) + c.flush()
             f.write(b"\x1f\x8b\x08\x04\0\0\0\0\0\xff\x06\0BC\x02\0" + struct.pack("<H", len(d) + 25) + d + struct.pack("<II", zlib.crc32(chunk), len(chunk)))
         f.write(bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000"))
+    if not index:
+        return path
     with open(path + ".bai", "wb") as f:      # empty-but-valid index: depth only checks that it exists (depth.d:1166)
         f.write(b"BAI\1" + struct.pack("<i", len(refs)) + b"".join(struct.pack("<ii", 0, 0) for _ in refs) + struct.pack("<Q", 0))
     return path

@@ -1,4 +1,4 @@
-"""The `gpu` tests of the CLI, of `-m`, of `-F` and of the multi-rank sharding (ranks as threads over an NCCL stand-in), run on the CPU against tests/emul/libbdepth_emul.so: the same host
+"""The `gpu` tests of the CLI, of `-m`, of `-F`, of the BAI builder and of the multi-rank sharding (ranks as threads over an NCCL stand-in), run on the CPU against tests/emul/libbdepth_emul.so: the same host
 pipeline (bdepth.cu) and kernels compiled with g++ over a CUDA-on-CPU emulation (tests/emul/cuda_shim.hpp: a fiber per
 thread, rendezvous for warp collectives and __syncthreads).  TEST INFRASTRUCTURE: it shows that launch plumbing written
 without access to a GPU is logically right; it is no substitute for the hardware run (memory model, alignment, PTX paths,
@@ -12,7 +12,7 @@ from helpers import ROOT
 
 # (suite, -k expression): the -m suite is split in two so that the four processes take about the same time
 SUITES = [("tests/test_gpu_cli.py", None), ("tests/test_zz_gpu_mates.py", "several_batches or window_mode"),
-          ("tests/test_zz_gpu_mates.py", "not several_batches and not window_mode"), ("tests/test_zz_gpu_filter.py", None), ("tests/test_gpu_multi.py", None)]
+          ("tests/test_zz_gpu_mates.py", "not several_batches and not window_mode"), ("tests/test_zz_gpu_filter.py", None), ("tests/test_gpu_multi.py", None), ("tests/test_gpu_index.py", None)]
 
 
 def test_the_emulation_itself():

@@ -93,7 +93,7 @@ def _run(world, path, mode, tuning=None):
 @pytest.fixture(scope="module")
 def bam(tmp_path_factory):
     d = tmp_path_factory.mktemp("multi")
-    if os.environ.get("BDEPTH_EMULATE") == "1":       # same shape, a tenth of the size (the CPU emulation is slow)
+    if os.environ.get("BDEPTH_EMULATE") == "1" and os.environ.get("BDEPTH_EMU_MULTI_FULL") != "1":       # same shape, a tenth of the size (the CPU emulation is slow; BDEPTH_EMU_MULTI_FULL=1: the hardware's size)
         return helpers.gen_bam(str(d / "m.bam"), "-r", "chrA:200000", "-r", "chrB:700", "-r", "chrC:150000", "-n", 30000, "-s", 11, "-t", 8)
     return helpers.gen_bam(str(d / "m.bam"), "-r", "chrA:2000000", "-r", "chrB:700", "-r", "chrC:1500000", "-n", 300000, "-s", 11, "-t", 8)
 

@@ -213,3 +213,32 @@ def test_closed_form_segment_stats_equal_the_sweep(tmp_path):
             ln = np.float32(int(b[i] - a[i]))
             want = [str(int(reads[i])), "%g" % (np.float32(bases[i]) / ln)] + ["%g" % (np.float32(100) * np.float32(cov[t][i]) / ln) for t in range(len(thr))]
             assert r[3:3 + 2 + len(thr)] == want, (q, i, r, want)
+
+
+@pytest.mark.parametrize("name,bytewise", [("issue225.bam", True), ("issue_193.bam", True), ("issue_204.bam", True), ("mate_overlaps_1_3M_4M.bam", False)])
+def test_index_builder_reproduces_the_reference_bai_files(name, bytewise):
+    """oracle_build_bai (IndexBuilder, BioD/bio/std/hts/bam/bai/indexing.d) is pinned on the four .bai files the reference ships next
+    to its test BAMs -- sambamba's own indexer wrote them: bins, chunks, metadata pseudo-bins, linear index and n_no_coor are equal;
+    three files are equal byte for byte, the fourth differs only in the order of its bins (the reference: iteration order of a D
+    associative array; the oracle: ascending)."""
+    p = os.path.join(GOLDEN, name)
+    mine = helpers.oracle_build_bai(p, threads=2)
+    ref = open(p + ".bai", "rb").read()
+    assert helpers.parse_bai(mine) == helpers.parse_bai(ref)
+    assert len(mine) == len(ref) and (mine == ref) == bytewise
+
+
+def test_index_builder_edge_cases_by_hand(tmp_path):
+    """A hand-checked case: chunk ends where the bin changes, position-less reads only count, gaps of the linear index are filled."""
+    M = 0
+    seq = "ACGT" * 10
+    reads = [(0, 100, 60, 0, [(40, M)], seq, "a"), (0, 200, 60, 0, [(40, M)], seq, "b"), (0, 16380, 60, 0, [(40, M)], seq, "c"), (0, 50000, 60, 0, [(40, M)], seq, "d"),
+             (-1, -1, 0, 4, [], seq, "u")]
+    p = helpers.write_bam(str(tmp_path / "h.bam"), [("r0", 100000), ("r1", 500)], reads, bins="auto", index=False)
+    (refs, no_coor) = helpers.parse_bai(helpers.oracle_build_bai(p))
+    bins, lin = refs[0]
+    assert no_coor == 1 and refs[1] == ({}, [])
+    assert sorted(bins) == [585, 4681, 4684, 37450]      # a, b in leaf 4681; c crosses 16384 -> bin 585; d in leaf 4684
+    assert bins[37450][1] == (4, 0)
+    assert len(lin) == 4 and lin[0] == bins[4681][0][0] and lin[1] == bins[585][0][0] and lin[2] == lin[1] and lin[3] == bins[4684][0][0]      # window 2 is a gap: filled from the left
+    assert bins[4681][0][1] == bins[585][0][0] and bins[585][0][1] == bins[4684][0][0]          # chunks meet where the bin changes
