@@ -206,3 +206,32 @@ def test_scattered_regions_divide_their_chunks_among_ranks(bam, world):
     blocks = [r[5]["n_blocks"] for r in res]
     assert sum(blocks) <= one + world and sum(blocks) < total_blocks, (blocks, one, total_blocks)
     assert sum(1 for n in blocks if n) >= 2, blocks
+
+
+def test_zone_blocks_whose_reads_all_end_before_the_shard(tmp_path):
+    """The zone a rank re-reads begins at the first read that overlaps the 16 kbp window of its first own read (BAI linear index).  The
+    reads behind that one need not reach the window: here a read with a long skip overlaps it, and the next BGZF members hold only short
+    reads that end before it.  With one member per sub-batch such a sub-batch has nothing to count for this rank (hardware run of round 2:
+    this case ended in "read extends past the end of the reference space")."""
+    if _n_gpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    import random
+    rnd = random.Random(7)
+    M, N = 0, 3
+    def seq():
+        return "".join(rnd.choice("ACGT") for _ in range(40))
+    reads = [(0, p, 60, 0, [(40, M)], seq(), "a%d" % i) for i, p in enumerate(sorted(rnd.randrange(0, 13000) for _ in range(300)))]
+    reads.append((0, 14000, 60, 0, [(20, M), (2960, N), (20, M)], seq(), "skip"))
+    reads += [(0, p, 60, 0, [(40, M)], seq(), "b%d" % i) for i, p in enumerate(sorted(rnd.randrange(14000, 15000) for _ in range(200)))]
+    reads += [(0, p, 60, 0, [(40, M)], seq(), "c%d" % i) for i, p in enumerate(sorted(rnd.randrange(16400, 32000) for _ in range(100)))]
+    reads += [(0, p, 60, 0, [(40, M)], seq(), "d%d" % i) for i, p in enumerate(sorted(rnd.randrange(32700, 60000) for _ in range(500)))]
+    p = helpers.write_bam(str(tmp_path / "z.bam"), [("r0", 70000)], reads, block=4096, bins="auto", index=False)
+    open(p + ".bai", "wb").write(helpers.oracle_build_bai(p))
+    want, ost = helpers.oracle_counts(p)
+    res = _run(2, p, "base", (1 << 16, 1))
+    got = np.zeros_like(want)
+    for rank, _, lo, hi, arr, st in res:
+        got[:, lo:hi] = arr
+    assert res[1][2] > 16384 and res[1][5]["n_records"] > 0, "the second rank owns the positions from its first read on, inside the window the zone was read for"
+    assert sum(r[5]["n_records"] for r in res) == ost.n_records
+    assert np.array_equal(got, want)
