@@ -19,6 +19,7 @@ The file is 2.26 GB compressed / 3.76 GB inflated per chromosome unit, far large
 flush is needed between steps (config.l2: "inputs >> L2").
 """
 import argparse
+import datetime
 import ctypes as C
 import json
 import os
@@ -292,7 +293,7 @@ def setup_dist(world, local_rank):
     import torch
     import torch.distributed as dist
     torch.cuda.set_device(local_rank)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), timeout=datetime.timedelta(minutes=30))      # rank 0 checks the counters against the CPU oracle (minutes at N = 8) while the others wait in a collective
     return dist
 
 
@@ -600,7 +601,7 @@ def main():
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), timeout=datetime.timedelta(minutes=30))      # rank 0 checks the counters against the CPU oracle (minutes at N = 8) while the others wait in a collective
         if rank == 0:
             path = ensure_workload(n_units, a.reads_per_unit)
         dist.barrier()
