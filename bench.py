@@ -32,7 +32,7 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
-if os.environ.get("BDEPTH_EMULATE") == "1":        # TEST INFRASTRUCTURE (tests/test_bench_cpu.py): the bench logic on the CPU over the CUDA-on-CPU emulation of the library; never a benchmark
+if os.environ.get("BDEPTH_EMULATE") == "1":        # TEST INFRASTRUCTURE (run by hand: minutes even for a tiny workload): the bench logic on the CPU over the CUDA-on-CPU emulation of the library; never a benchmark
     import sambamba_b200._lib as _L
     _L.lib_path = lambda: os.path.join(ROOT, "tests", "emul", "libbdepth_emul.so")
 

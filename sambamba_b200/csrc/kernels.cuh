@@ -120,7 +120,7 @@ __device__ __forceinline__ uint32_t warp_max_u32(uint32_t v) { return __reduce_m
 static inline uint32_t warp_max_u32(uint32_t v) { return ~__reduce_min_sync(0xFFFFFFFFu, ~v); }
 static inline bool emu_k1lz_warp() { static const bool on = getenv("BDEPTH_EMU_K1LZ_WARP") && atoi(getenv("BDEPTH_EMU_K1LZ_WARP")) == 1; return on; }
 #endif
-__global__ void __launch_bounds__(K1L_WARPS * 32) k1_lz(const BlockDesc* __restrict__ blocks, uint32_t n_blocks, uint32_t blk0, uint8_t* __restrict__ u, int* __restrict__ status,
+__global__ void __launch_bounds__(K1L_WARPS * 32, 6) k1_lz(const BlockDesc* __restrict__ blocks, uint32_t n_blocks, uint32_t blk0, uint8_t* __restrict__ u, int* __restrict__ status,
                                                         const uint32_t* __restrict__ tok, const uint8_t* __restrict__ lits, const BlockAux* __restrict__ aux,
                                                         const uint32_t* __restrict__ seg_info, const uint8_t* __restrict__ lit_tab) {
     __shared__ uint32_t s_tab[K1L_WARPS][64];
@@ -179,18 +179,23 @@ __global__ void __launch_bounds__(K1L_WARPS * 32) k1_lz(const BlockDesc* __restr
             // round); the token a literal belongs to is found by a binary search over the 32 inclusive counts in shared memory for the
             // first of the four and by stepping for the others; rank -> byte through the deflate block's table in shared memory
             // (measured against a lane-per-token copy of the runs: 11.6 vs 12.9 ms, profiles/k1_history.md)
-            s_il[warp][lane] = il; s_dl[warp][lane] = dlit;
+            // Only the tokens that have literals enter the table (compacted by a ballot): every entry then covers at least one literal, so
+            // from one literal to the next the token changes by at most one entry -- one predicated step per byte instead of a loop over
+            // the match-only tokens in between (that loop was 13 % of the kernel's instructions at 7 of 32 lanes).
+            const unsigned has_l = __ballot_sync(0xFFFFFFFFu, lit != 0);
+            if (lit) { const uint32_t e = __popc(has_l & ((1u << lane) - 1u)); s_il[warp][e] = il; s_dl[warp][e] = dlit; }
+            const int n_ent = __popc(has_l);
             __syncwarp();
             for (uint32_t j0 = 4 * lane; j0 < totl; j0 += 128) {
                 const uint32_t w = ld_u32_any(lt + lbase + j0);
-                int lo = 0, hi = 31;                              // the first token whose inclusive literal count exceeds j0
+                int lo = 0, hi = n_ent - 1;                       // the first entry whose inclusive literal count exceeds j0 (the last one's is totl > j0)
                 while (lo < hi) { int mid = (lo + hi) >> 1; if (s_il[warp][mid] > j0) hi = mid; else lo = mid + 1; }
                 uint32_t tend = s_il[warp][lo], tbeg = lo ? s_il[warp][lo - 1] : 0u, tdst = s_dl[warp][lo];
 #pragma unroll
                 for (uint32_t bq = 0; bq < 4; bq++) {
                     const uint32_t j = j0 + bq;
                     if (j >= totl) break;
-                    while (j >= tend) { lo++; tbeg = tend; tend = s_il[warp][lo]; tdst = s_dl[warp][lo]; }      // (tokens without literals are stepped over)
+                    if (j >= tend) { lo++; tbeg = tend; tend = s_il[warp][lo]; tdst = s_dl[warp][lo]; }      // j == tend here, and the next entry has at least one literal
                     const uint32_t r = (w >> (8 * bq)) & 0xFFu;
                     uint32_t v;
                     if (one_seg) v = seg_raw ? r : (uint32_t)tb[r];
