@@ -668,6 +668,27 @@ def main():
     k1_ms = sum(k1) / len(k1)
     k1_bytes = st["cdata_bytes"] + st["inflated_bytes"]              # C + U of this rank's shard
     k1_launches_per_step = st["n_batches"]
+    # ---- A/B on the same resident handle (one GPU only; the library reads its switches at every run): kernels this build replaced,
+    # measured beside the shipped ones so that a change made without access to a GPU shows its effect in the line the driver records
+    ab = None
+    if world == 1:
+        ab = {"what": "stage times (ms) of 3 resident passes with one library switch each, same handle and input as `value`",
+              "shipped": {"k1_inflate": k1_ms, "k3_coverage": sum(k3) / len(k3), "ms_per_step": ms_step}}
+        for name, env in (("k1_lz_v12_literal_table", {"BDEPTH_K1LZ": "v12"}), ("k3_gather_round1", {"BDEPTH_K3": "gather"})):
+            try:
+                os.environ.update(env)
+                b.run_resident()
+                t = []
+                for _ in range(3):
+                    b.run_resident()
+                    s3 = b.stats()
+                    t.append((s3["ms_inflate"], s3["ms_coverage"], s3["ms_span_device"]))
+                ab[name] = {"env": env, "k1_inflate": sum(x[0] for x in t) / 3, "k3_coverage": sum(x[1] for x in t) / 3, "ms_per_step": sum(x[2] for x in t) / 3}
+            except Exception as e:                                  # an A/B leg must never take the bench line down
+                ab[name] = {"env": env, "error": repr(e)[:200]}
+            finally:
+                for k in env:
+                    os.environ.pop(k, None)
     b.close()
 
     # ---- e2e: host (pinned) buffers in, host (pinned) counters out, everything inside the timed region
@@ -761,7 +782,7 @@ def main():
                 "device_ms": {k: e2e_stats[k] for k in ("ms_h2d", "ms_inflate", "ms_scan", "ms_coverage", "ms_d2h", "ms_span_device")},
                 "path": "bdepth_open_memory(pinned host BAM image) + bdepth_run_base -> 7 x u32 counters in pinned host memory", "host_input": host_kind, "chunk_blocks": chunk_blocks or "default (6656)",
                 "variants": {k: os.environ[k] for k in ("BDEPTH_K1_STREAM_WARPS", "BDEPTH_K1_LIT3", "BDEPTH_K3_PREFETCH") if k in os.environ}},
-        "text_rows": text,
+        "text_rows": text, "ab": ab,
         "gpu_launches": int(total_launches),
         "roofline": {"kernel": "K1 two-phase inflate: k1_huff (lane-per-BGZF-block Huffman phase) + k1_lz (warp-per-block LZ77 phase), timed together", "bound": "hbm", "achieved": k1_bytes / 1e9 / (k1_ms / 1e3), "peak": peak, "unit": "GB/s",
                      "frac": k1_bytes / 1e9 / (k1_ms / 1e3) / peak, "traffic": traffic if (a.gpus == 1 and a.reads_per_unit == READS_PER_UNIT) else None, "traffic_source": traffic_src,

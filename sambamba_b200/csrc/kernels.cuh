@@ -120,6 +120,7 @@ __device__ __forceinline__ uint32_t warp_max_u32(uint32_t v) { return __reduce_m
 static inline uint32_t warp_max_u32(uint32_t v) { return ~__reduce_min_sync(0xFFFFFFFFu, ~v); }
 static inline bool emu_k1lz_warp() { static const bool on = getenv("BDEPTH_EMU_K1LZ_WARP") && atoi(getenv("BDEPTH_EMU_K1LZ_WARP")) == 1; return on; }
 #endif
+template <bool COMPACT>      // COMPACT = false: round 2's first literal stage (table of all 32 tokens, BDEPTH_K1LZ=v12), kept for the A/B bench.py prints
 __global__ void __launch_bounds__(K1L_WARPS * 32, 6) k1_lz(const BlockDesc* __restrict__ blocks, uint32_t n_blocks, uint32_t blk0, uint8_t* __restrict__ u, int* __restrict__ status,
                                                         const uint32_t* __restrict__ tok, const uint8_t* __restrict__ lits, const BlockAux* __restrict__ aux,
                                                         const uint32_t* __restrict__ seg_info, const uint8_t* __restrict__ lit_tab) {
@@ -182,9 +183,12 @@ __global__ void __launch_bounds__(K1L_WARPS * 32, 6) k1_lz(const BlockDesc* __re
             // Only the tokens that have literals enter the table (compacted by a ballot): every entry then covers at least one literal, so
             // from one literal to the next the token changes by at most one entry -- one predicated step per byte instead of a loop over
             // the match-only tokens in between (that loop was 13 % of the kernel's instructions at 7 of 32 lanes).
-            const unsigned has_l = __ballot_sync(0xFFFFFFFFu, lit != 0);
-            if (lit) { const uint32_t e = __popc(has_l & ((1u << lane) - 1u)); s_il[warp][e] = il; s_dl[warp][e] = dlit; }
-            const int n_ent = __popc(has_l);
+            int n_ent = 32;
+            if (COMPACT) {
+                const unsigned has_l = __ballot_sync(0xFFFFFFFFu, lit != 0);
+                if (lit) { const uint32_t e = __popc(has_l & ((1u << lane) - 1u)); s_il[warp][e] = il; s_dl[warp][e] = dlit; }
+                n_ent = __popc(has_l);
+            } else { s_il[warp][lane] = il; s_dl[warp][lane] = dlit; }
             __syncwarp();
             for (uint32_t j0 = 4 * lane; j0 < totl; j0 += 128) {
                 const uint32_t w = ld_u32_any(lt + lbase + j0);
@@ -195,7 +199,8 @@ __global__ void __launch_bounds__(K1L_WARPS * 32, 6) k1_lz(const BlockDesc* __re
                 for (uint32_t bq = 0; bq < 4; bq++) {
                     const uint32_t j = j0 + bq;
                     if (j >= totl) break;
-                    if (j >= tend) { lo++; tbeg = tend; tend = s_il[warp][lo]; tdst = s_dl[warp][lo]; }      // j == tend here, and the next entry has at least one literal
+                    if (COMPACT) { if (j >= tend) { lo++; tbeg = tend; tend = s_il[warp][lo]; tdst = s_dl[warp][lo]; } }      // j == tend here, and the next entry has at least one literal
+                    else while (j >= tend) { lo++; tbeg = tend; tend = s_il[warp][lo]; tdst = s_dl[warp][lo]; }            // (tokens without literals are stepped over)
                     const uint32_t r = (w >> (8 * bq)) & 0xFFu;
                     uint32_t v;
                     if (one_seg) v = seg_raw ? r : (uint32_t)tb[r];

@@ -204,6 +204,6 @@ def test_phase_two_warp_code_under_the_emulation(tmp_path):
         "        assert np.array_equal(b.inflate(), helpers.oracle_inflate(p)), p\n"
         "print('ok')\n") % (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "tests", "emul", "libbdepth_emul.so"))
     files = [os.path.join(GOLDEN, f) for f in sorted(os.listdir(GOLDEN)) if f.endswith(".bam")] + [mix, runs]
-    for variant in ({}, {"BDEPTH_K1LZ": "flat"}):        # k1_lz (lane = token, dependency rounds) and k1_lz_flat (lane = output byte, pointer jumping)
+    for variant in ({}, {"BDEPTH_K1LZ": "v12"}, {"BDEPTH_K1LZ": "flat"}):        # k1_lz (lane = token, dependency rounds; compacted and full literal table) and k1_lz_flat (lane = output byte, pointer jumping)
         r = subprocess.run([sys.executable, "-c", code] + files, env=dict(os.environ, BDEPTH_EMU_K1LZ_WARP="1", **variant), capture_output=True, text=True, timeout=900)
         assert r.returncode == 0 and r.stdout.strip() == "ok", (variant, r.stderr[-2000:])

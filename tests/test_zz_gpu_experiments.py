@@ -23,7 +23,7 @@ def bam(tmp_path_factory):
 
 
 @pytest.mark.parametrize("envadd", [dict(BDEPTH_K1_ONEPHASE="1"), dict(BDEPTH_K1H_VARIANT="0"), dict(BDEPTH_K1H_VARIANT="1"), dict(BDEPTH_K1H_VARIANT="2"),
-                                    dict(BDEPTH_K1H_VARIANT="3"), dict(BDEPTH_K3="gather"), dict(BDEPTH_K3="gather", BDEPTH_K3_PREFETCH="0"), dict(BDEPTH_K1LZ="flat")],
+                                    dict(BDEPTH_K1H_VARIANT="3"), dict(BDEPTH_K3="gather"), dict(BDEPTH_K3="gather", BDEPTH_K3_PREFETCH="0"), dict(BDEPTH_K1LZ="flat"), dict(BDEPTH_K1LZ="v12")],
                          ids=lambda e: ",".join(f"{k[7:]}={v}" for k, v in e.items()))
 def test_variant_gives_identical_output(bam, envadd):
     env = dict(os.environ, **envadd)
