@@ -34,6 +34,10 @@ def _rank_main(rank, world, path, uid, mode, q, tuning=None):
         sys.path.insert(0, helpers.ROOT)
         import sambamba_b200 as sb
         with sb.BDepth(path, device=rank) as b:
+            if mode.startswith("index+"):       # input without .bai: every rank builds the index itself, then the shards are cut from it
+                assert not b.has_index
+                b.build_index()
+                mode = mode[6:]
             b.set_shard(rank, world, uid)
             if tuning:
                 b.set_tuning(*tuning)
@@ -234,4 +238,20 @@ def test_zone_blocks_whose_reads_all_end_before_the_shard(tmp_path):
         got[:, lo:hi] = arr
     assert res[1][2] > 16384 and res[1][5]["n_records"] > 0, "the second rank owns the positions from its first read on, inside the window the zone was read for"
     assert sum(r[5]["n_records"] for r in res) == ost.n_records
+    assert np.array_equal(got, want)
+
+
+def test_unindexed_input_on_several_ranks(bam, tmp_path):
+    """A BAM without .bai: each rank builds the index on its GPU (bdepth_build_index), adopts it and takes its shard of the file."""
+    import shutil
+    if _n_gpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    p = str(tmp_path / "noidx.bam")
+    shutil.copy(bam, p)
+    want, ost = helpers.oracle_counts(bam)
+    res = _run(2, p, "index+base")
+    got = np.zeros_like(want)
+    for rank, _, lo, hi, arr, st in res:
+        got[:, lo:hi] = arr
+    assert sum(r[5]["n_records"] for r in res) == ost.n_records and res[1][2] > 0
     assert np.array_equal(got, want)
