@@ -1465,11 +1465,18 @@ int bdepth_stage(bdepth_t* h) {
     return 0;
 }
 
+// The part of the counter window this rank owns, window-relative: [a, b), empty when b <= a.  (A rank without a passing read of its own
+// owns nothing -- own_lo = own_hi = 0 -- while its window begins at its shard: the differences must not wrap.)
+static inline void owned_window(const bdepth* h, uint64_t& a, uint64_t& b) {
+    const uint64_t lo = std::max(h->own_lo, h->cnt_base), hi = std::min(h->own_hi, h->cnt_base + h->win_len);
+    if (hi > lo) { a = lo - h->cnt_base; b = hi - h->cnt_base; } else { a = b = 0; }
+}
+
 int bdepth_run_resident(bdepth_t* h) {
     int rc = run_all_inputs(h); if (rc) return rc;
     cudaStream_t sm = h->s_main;
     CK(cudaMemsetAsync(h->misc.p, 0, 8, sm));
-    uint64_t a = std::max(h->own_lo, h->cnt_base) - h->cnt_base, b = std::min(h->own_hi, h->cnt_base + h->win_len) - h->cnt_base;
+    uint64_t a, b; owned_window(h, a, b);
     if (b > a) { BD_LAUNCH(COUNT_GRID, 256, 0, sm, k_count_covered)(h->counts.as<uint32_t>(), h->win_len, a, b, (unsigned long long*)h->misc.p, N_PLANES * (int)h->S); CK(cudaGetLastError()); h->st.gpu_launches++; }
     unsigned long long cov = 0; CK(cudaMemcpyAsync(&cov, h->misc.p, 8, cudaMemcpyDeviceToHost, sm)); CK(cudaStreamSynchronize(sm));
     h->st.covered_positions = cov;
@@ -1490,7 +1497,7 @@ int bdepth_run_base(bdepth_t* h, bdepth_tile_cb cb, void* user) {
     cudaEvent_t e0 = h->ev[5], e1 = h->ev[6];
     // covered positions (rows of default `depth base`), over the range this rank owns
     CK(cudaMemsetAsync(h->misc.p, 0, 8, sm));
-    { uint64_t ca = std::max(h->own_lo, h->cnt_base) - h->cnt_base, cb2 = std::min(h->own_hi, h->cnt_base + h->win_len) - h->cnt_base;
+    { uint64_t ca, cb2; owned_window(h, ca, cb2);
       if (cb2 > ca) { BD_LAUNCH(COUNT_GRID, 256, 0, sm, k_count_covered)(h->counts.as<uint32_t>(), h->win_len, ca, cb2, (unsigned long long*)h->misc.p, N_PLANES * (int)h->S); CK(cudaGetLastError()); h->st.gpu_launches++; } }
     unsigned long long cov = 0; CK(cudaMemcpyAsync(&cov, h->misc.p, 8, cudaMemcpyDeviceToHost, sm));
     CK(cudaEventRecord(e0, sm));
@@ -1517,7 +1524,7 @@ int bdepth_run_base_text(bdepth_t* h, const bdepth_text_opts* o, bdepth_text_cb 
     cudaEvent_t e0 = h->ev[5], e1 = h->ev[6];
     CK(cudaEventRecord(e0, sm));
     CK(cudaMemsetAsync(h->misc.p, 0, 8, sm));
-    { uint64_t ca = std::max(h->own_lo, h->cnt_base) - h->cnt_base, cb2 = std::min(h->own_hi, h->cnt_base + h->win_len) - h->cnt_base;
+    { uint64_t ca, cb2; owned_window(h, ca, cb2);
       if (cb2 > ca) { BD_LAUNCH(COUNT_GRID, 256, 0, sm, k_count_covered)(h->counts.as<uint32_t>(), h->win_len, ca, cb2, (unsigned long long*)h->misc.p, N_PLANES * (int)h->S); CK(cudaGetLastError()); h->st.gpu_launches++; } }
     unsigned long long cov = 0; CK(cudaMemcpyAsync(&cov, h->misc.p, 8, cudaMemcpyDeviceToHost, sm));
     TextParams tp; memset(&tp, 0, sizeof tp);

@@ -139,3 +139,47 @@ def test_cli_index_subcommand(tmp_path):
     r2 = subprocess.run([helpers.CLI, "depth", "base", "--build-index", p], capture_output=True, text=True)
     want = subprocess.run([helpers.CLI, "depth", "base", src], capture_output=True, text=True)
     assert r2.returncode == 0 and r2.stdout == want.stdout and len(want.stdout) > 1000
+
+
+def _random_case(seed):
+    """A small random BAM: references with and without reads, position-less reads in front of a reference's reads, unmapped reads with a
+    position, empty / skipping / clipped CIGARs, right or arbitrary bin fields, unplaced reads at the end, BGZF members from 150 B to 64 KB."""
+    import random
+    rnd = random.Random(seed)
+    M, I, D, N, S = 0, 1, 2, 3, 4
+    refs = [("r%d" % i, rnd.choice([300, 5000, 40000, 200000])) for i in range(rnd.randint(1, 6))]
+    reads = []
+    for r, (_, ln) in enumerate(refs):
+        if rnd.random() < 0.25:
+            continue
+        pos = sorted(rnd.randrange(0, max(1, ln - 100)) for _ in range(rnd.randint(1, 400)))
+        if rnd.random() < 0.3:
+            pos = [-1] * rnd.randint(1, 3) + pos
+        for p in pos:
+            k = rnd.random()
+            cig = ([(40, M)] if k < 0.6 else [(10, M), (rnd.randint(1, 30000), N), (30, M)] if k < 0.7 else [(5, S), (20, M), (3, I), (12, M)] if k < 0.8
+                   else [(20, M), (rnd.randint(1, 50), D), (20, M)] if k < 0.9 else [] if k < 0.95 else [(rnd.randint(1, 100), M)])
+            if p >= 0 and p + sum(l for l, o in cig if o in (0, 2, 3)) > ln:
+                cig = [(min(40, max(1, ln - p)), M)]
+            reads.append((r, p, rnd.randint(0, 60), 4 if rnd.random() < 0.1 else 0, cig, "ACGT" * 10, "q%d" % len(reads)))
+    reads += [(-1, -1, 0, 4, [], "ACGT" * 10, "u%d" % i) for i in range(rnd.randint(0, 5))]
+    bins = "auto" if rnd.random() < 0.7 else [rnd.choice([4681, 4682, 585, 73, 0, 4690]) for _ in reads]
+    return refs, reads, bins, rnd.choice([0xFF00, 4096, 777, 150]), rnd.choice([None, (1 << 16, 1), (1 << 16, 2), (1 << 17, 3)])
+
+
+def test_random_files(tmp_path):
+    import sambamba_b200 as sb
+    for seed in range(40):
+        refs, reads, bins, block, tuning = _random_case(seed)
+        if not reads:
+            continue
+        p = helpers.write_bam(str(tmp_path / ("f%d.bam" % seed)), refs, reads, block=block, bins=bins, index=False)
+        try:
+            want = helpers.oracle_build_bai(p)
+        except RuntimeError:
+            want = None                      # (a position-less read behind reads of its reference: "not coordinate-sorted", indexing.d:259-271)
+        try:
+            got = _build(p, tuning)
+        except sb.BDepthError:
+            got = None
+        assert got == want, (seed, block, tuning)

@@ -255,3 +255,28 @@ def test_unindexed_input_on_several_ranks(bam, tmp_path):
         got[:, lo:hi] = arr
     assert sum(r[5]["n_records"] for r in res) == ost.n_records and res[1][2] > 0
     assert np.array_equal(got, want)
+
+
+def test_rank_without_a_passing_read_owns_nothing(tmp_path):
+    """The middle shard holds only reads the default filter drops (MAPQ 0): that rank owns no position -- own_lo = own_hi = 0 -- while its
+    counter window begins at its shard.  (Found by fuzzing under the emulation: the owned part of the window wrapped around and the
+    covered-positions kernel ran over it.)"""
+    if _n_gpus() < 3:
+        pytest.skip("needs 3 GPUs")
+    import random
+    rnd = random.Random(3)
+    def seq():
+        return "".join(rnd.choice("ACGT") for _ in range(40))
+    reads = [(0, p, 60, 0, [(40, 0)], seq(), "a%d" % i) for i, p in enumerate(sorted(rnd.randrange(0, 10000) for _ in range(150)))]
+    reads += [(0, p, 0, 0, [(40, 0)], seq(), "b%d" % i) for i, p in enumerate(sorted(rnd.randrange(20000, 150000) for _ in range(900)))]      # both cuts fall in here, several 16 kbp windows wide
+    reads += [(0, p, 60, 0, [(40, 0)], seq(), "c%d" % i) for i, p in enumerate(sorted(rnd.randrange(160000, 170000) for _ in range(150)))]
+    p = helpers.write_bam(str(tmp_path / "f.bam"), [("r0", 180000)], reads, block=4096, bins="auto", index=False)
+    open(p + ".bai", "wb").write(helpers.oracle_build_bai(p))
+    want, ost = helpers.oracle_counts(p)
+    res = _run(3, p, "base")
+    got = np.zeros_like(want)
+    for rank, _, lo, hi, arr, st in res:
+        got[:, lo:hi] = arr
+    assert (res[1][2], res[1][3]) == (0, 0) and res[1][5]["n_records"] > 0 and res[1][5]["n_records_pass"] == 0
+    assert sum(r[5]["n_records"] for r in res) == ost.n_records
+    assert np.array_equal(got, want)
