@@ -161,8 +161,9 @@ int bdepth_set_min_baseq(bdepth_t* h, uint32_t min_base_quality);
  * of writeColumn :521-530 and PerRegionPrinter.push :760-845): where two reads of one name (same sample) overlap,
  * every column counts only the better mate.  Available for bdepth_run_base / _run_base_text / _run_regions /
  * _run_windows / _run_resident; batches re-read the end of the previous batch and ranks a zone of their neighbours'
- * records, so that pairs cut by a batch or shard boundary are seen whole.  Names with three to eight overlapping
- * reads follow the reference's none/detected/fixed/past state machine; more than eight are refused (BDEPTH_ERR_ARG). */
+ * records, so that pairs cut by a batch or shard boundary are seen whole.  Names with three or more overlapping
+ * reads (a chain of any length) follow the reference's none/detected/fixed/past state machine; more than eight reads
+ * of one name over a single position are refused (BDEPTH_ERR_ARG). */
 int bdepth_set_fix_mates(bdepth_t* h, int on);
 /* --combined (depth.d:1131): one counter set for all samples.  Default: one per @RG sample (<= 64). */
 int bdepth_set_combined(bdepth_t* h, int combined);

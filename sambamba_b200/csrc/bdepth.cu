@@ -1122,7 +1122,7 @@ int run_pipeline(bdepth* h, RunMode mode, RunOut* ro, Emitter* em = nullptr) {
             struct { int err[4]; unsigned long long stat[3]; unsigned long long fix_max_end; unsigned long long open_off, open_start; } ctl;
             CK(cudaMemcpyAsync(&ctl, h->m_ctl.p, sizeof ctl, cudaMemcpyDeviceToHost, sm));
             CK(cudaStreamSynchronize(sm));
-            if (ctl.err[0] == MATE_ERR_TOO_MANY) return fail(h, BDEPTH_ERR_ARG, "fix-mate-overlaps: more than %d overlapping reads share one name (record #%d of the batch)", MATE_MAX_MEMBERS, ctl.err[1]);
+            if (ctl.err[0] == MATE_ERR_TOO_MANY) return fail(h, BDEPTH_ERR_ARG, "fix-mate-overlaps: more than %d reads of one name cover one position (record #%d of the batch)", MATE_MAX_MEMBERS, ctl.err[1]);
             if (ctl.err[0] == MATE_ERR_CROSS) return fail(h, BDEPTH_ERR_ARG, "fix-mate-overlaps: four or more overlapping reads of one name next to a batch boundary (record #%d of the batch): not reproduced there, use larger batches", ctl.err[1]);
             st.mate_pairs += ctl.stat[0]; st.mate_pair_columns += ctl.stat[1]; st.mate_groups += ctl.stat[2];
             if (!last_batch && ctl.open_off != ~0ull && batch_u0 + (ctl.open_off - 4) < ghost_below_abs) {      // something is still open: re-read from its first record

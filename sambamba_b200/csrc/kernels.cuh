@@ -1222,14 +1222,23 @@ __global__ void __launch_bounds__(256) k_text_len(TextParams tp, const uint32_t*
 }
 // exclusive scan of up to 1024*16 tile sums by one block (64-bit offsets)
 __global__ void __launch_bounds__(1024) k_text_scan(const uint32_t* __restrict__ tile_sum, uint32_t n_tiles, unsigned long long* __restrict__ tile_off, unsigned long long* __restrict__ total) {
-    __shared__ unsigned long long part[1024];
-    uint32_t per = (n_tiles + 1023) / 1024, lo = threadIdx.x * per, hi = min(n_tiles, lo + per);
+    __shared__ unsigned long long wtot[32];
+    const uint32_t per = (n_tiles + 1023) / 1024, lo = threadIdx.x * per, hi = min(n_tiles, lo + per), lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned long long s = 0;
     for (uint32_t i = lo; i < hi; i++) s += tile_sum[i];
-    part[threadIdx.x] = s; __syncthreads();
-    if (threadIdx.x == 0) { unsigned long long a = 0; for (int i = 0; i < 1024; i++) { unsigned long long t = part[i]; part[i] = a; a += t; } *total = a; }
+    // exclusive scan of the 1024 partial sums: a shuffle scan inside every warp, then one over the 32 warp totals
+    unsigned long long incl = s;
+    for (uint32_t sh = 1; sh < 32; sh <<= 1) { unsigned long long t = __shfl_up_sync(0xFFFFFFFFu, incl, sh); if (lane >= sh) incl += t; }
+    if (lane == 31) wtot[warp] = incl;
     __syncthreads();
-    unsigned long long a = part[threadIdx.x];
+    if (warp == 0) {
+        const unsigned long long w = wtot[lane]; unsigned long long wi = w;
+        for (uint32_t sh = 1; sh < 32; sh <<= 1) { unsigned long long t = __shfl_up_sync(0xFFFFFFFFu, wi, sh); if (lane >= sh) wi += t; }
+        wtot[lane] = wi - w;
+        if (lane == 31) *total = wi;
+    }
+    __syncthreads();
+    unsigned long long a = wtot[warp] + incl - s;
     for (uint32_t i = lo; i < hi; i++) { tile_off[i] = a; a += tile_sum[i]; }
 }
 // pass 2: write the rows

@@ -35,7 +35,7 @@
 
 namespace bdk {
 
-constexpr int MATE_MAX_MEMBERS = 8;
+constexpr int MATE_MAX_MEMBERS = 8;        // reads of one name hash present in ONE column (a component may have any number of members)
 enum MateErr : int { MATE_OK = 0, MATE_ERR_TOO_MANY = 1, MATE_ERR_CROSS = 2, MATE_ERR_ZONE = 3 };
 constexpr uint32_t MATE_NCL_FOREIGN = 1u << 30;    // ... of another rank's shard (kernels.cuh NCL_FOREIGN): seen, never the leader of a component this rank fixes
 constexpr uint32_t MATE_NCL_GHOST = 1u << 31;      // RecordSoA.ncl bit of a re-read record of the previous batch (kernels.cuh NCL_GHOST)
@@ -312,16 +312,30 @@ BD_HD bool mate_follows(const MateParams& p, uint64_t h, uint64_t g, uint32_t wh
 //   reducers   n_bases = A/C/G/T/N counters of the region's columns, n_reads = members with a counted base in it.
 // Nothing here needs reads outside the component: a member that started before a region is present in the region's
 // first column, so that column is the region's first visited one.
-BD_HD void mate_fix_group(const MateParams& p, const uint32_t* idx, int n, uint32_t leader) {
+//
+// The component may be any length (a chain of supplementary alignments, a name that many reads share): the walk keeps only the
+// members that are present in the current column -- slots are handed out when the column reaches a member's start and taken back
+// when it passes its end; `pres` lists the occupied slots in file order, which is the order the reference pairs neighbours in.  A
+// member that has ended is never looked at again (its state cannot matter any more), so nothing but the number of reads of one
+// name in ONE column is bounded (MATE_MAX_MEMBERS).
+BD_HD void mate_fix_group(const MateParams& p, uint32_t leader, uint64_t hi) {
     MRead M[MATE_MAX_MEMBERS]; MCur C[MATE_MAX_MEMBERS]; uint8_t st[MATE_MAX_MEMBERS];      // 0 none, 1 detected, 2 fixed, 3 past
-    uint64_t lo = ~0ull, hi = 0;
-    for (int k = 0; k < n; k++) { m_load(p, idx[k], M[k]); st[k] = 0; if (M[k].s < lo) lo = M[k].s; if (M[k].e > hi) hi = M[k].e; }
+    int pres[MATE_MAX_MEMBERS]; int np = 0; uint32_t used = 0;      // pres[0..np): the slots of the members present in column g, in file order
+    const uint64_t lo = p.start[leader], h = p.mhash[leader];
+    uint32_t next = leader;                                          // first record not yet looked at
     unsigned long long cols = 0;
     uint32_t seg_hi = 0;
     if (p.n_seg) { uint32_t l = 0, h2 = p.n_seg; while (l < h2) { uint32_t mid = (l + h2) >> 1; if (p.seg_s[mid] < hi + p.seg_ext_max) l = mid + 1; else h2 = mid; } seg_hi = l; }   // segments that are updated before the component ends
     for (uint64_t g = lo; g < hi; g++) {
-        int pres[MATE_MAX_MEMBERS], kind[MATE_MAX_MEMBERS]; uint32_t q[MATE_MAX_MEMBERS]; int np = 0;
-        for (int k = 0; k < n; k++) if (g >= M[k].s && g < M[k].e) { q[k] = 0; kind[k] = m_at(M[k], C[k], (uint32_t)(g - M[k].s), &q[k]); pres[np++] = k; }
+        { int w = 0; for (int i = 0; i < np; i++) { const int k = pres[i]; if (g < M[k].e) pres[w++] = k; else used &= ~(1u << k); } np = w; }      // members that ended
+        for (; next < p.R && p.start[next] <= g; next++) {                                                                              // members that begin here
+            if (p.mhash[next] != h || !(p.mflag[next] & MF_INSTREAM)) continue;
+            if (np == MATE_MAX_MEMBERS) { m_err(p, MATE_ERR_TOO_MANY, next); return; }
+            int k = 0; while ((used >> k) & 1u) k++;
+            used |= 1u << k; m_load(p, next, M[k]); C[k] = MCur(); st[k] = 0; pres[np++] = k;
+        }
+        int kind[MATE_MAX_MEMBERS]; uint32_t q[MATE_MAX_MEMBERS];
+        for (int i = 0; i < np; i++) { const int k = pres[i]; q[k] = 0; kind[k] = m_at(M[k], C[k], (uint32_t)(g - M[k].s), &q[k]); }
         int pa[MATE_MAX_MEMBERS / 2], pb[MATE_MAX_MEMBERS / 2], npairs = 0;
         for (int i = 0; i < np;) {
             if (i + 1 < np) {
@@ -334,7 +348,7 @@ BD_HD void mate_fix_group(const MateParams& p, const uint32_t* idx, int n, uint3
             if (st[a]) {
                 // Alone again: `past` -- unless it is the very last entry of the column's sorted array and its predecessor has
                 // the same hash; then the reference leaves it as it is (depth.d:380-384).
-                if (!(np >= 2 && st[a] != 3 && !mate_follows(p, p.mhash[idx[a]], g, leader))) st[a] = 3;
+                if (!(np >= 2 && st[a] != 3 && !mate_follows(p, h, g, leader))) st[a] = 3;
             }
             i += 1;
         }
@@ -396,27 +410,27 @@ BD_HD void mate_fix_group(const MateParams& p, const uint32_t* idx, int n, uint3
 
 BD_HD void mate_fix_one(const MateParams& p, uint32_t r) {
     if ((p.mflag[r] & (MF_INSTREAM | MF_HAS_PRED | MF_HAS_SUCC)) != (MF_INSTREAM | MF_HAS_SUCC)) return;
-    // the component: every same-hash read that starts before the running end of the members found so far
-    uint32_t idx[MATE_MAX_MEMBERS]; int n = 1; idx[0] = r;
+    // the component: every same-hash read that starts before the running end of the members found so far (any number of them)
+    uint32_t second = r, last = r; int n = 1;
     uint64_t reach = p.start[r] + p.span[r]; const uint64_t h = p.mhash[r];
     for (uint32_t k = r + 1; k < p.R && p.start[k] < reach; k++) {
         if (p.mhash[k] != h || !(p.mflag[k] & MF_INSTREAM)) continue;
-        if (n == MATE_MAX_MEMBERS) { m_err(p, MATE_ERR_TOO_MANY, r); return; }
-        idx[n++] = k;
+        if (n == 1) second = k;
+        last = k; n++;
         uint64_t e = p.start[k] + p.span[k]; if (e > reach) reach = e;
     }
     if (!p.last_batch && reach > p.s_last) { m_min(p.open_off, (unsigned long long)p.off[r]); m_min(p.open_start, p.start[r]); return; }      // still open: the batch that closes it fixes it
     if (p.ncl[r] & MATE_NCL_FOREIGN) return;                                                                    // another rank owns the leader
     if (p.stream_cut && reach > p.s_last) { m_err(p, MATE_ERR_ZONE, r); return; }                               // runs out of the zone read behind the shard
     if (p.fix_max_end) m_max(p.fix_max_end, reach);
-    if (p.off[idx[n - 1]] < p.old_below && reach <= p.prev_s_last) return;                                       // only records the previous batch has seen, closed there: already fixed
+    if (p.off[last] < p.old_below && reach <= p.prev_s_last) return;                                             // only records the previous batch has seen, closed there: already fixed
     if (n == 2 && !p.force_general && !p.seg_u) {
-        MRead A, B; m_load(p, idx[0], A); m_load(p, idx[1], B);
+        MRead A, B; m_load(p, r, A); m_load(p, second, B);
         if (m_same_name(A, B)) mate_fix_pair(p, A, B);
         return;
     }
     if (n < 2) return;
-    mate_fix_group(p, idx, n, r);
+    mate_fix_group(p, r, reach);
 }
 
 // every read that reaches into the columns of an open component has to be re-read with it (after km_link and km_fix)

@@ -227,7 +227,7 @@ def random_cigar(rnd, qlen, allow_n=True):
     return ops
 
 
-def make_pairs_bam(path, seed, n_frag=400, refs=(("c1", 4000), ("c2", 2500)), rg=None, triples=0.0, same_start=0.05):
+def make_pairs_bam(path, seed, n_frag=400, refs=(("c1", 4000), ("c2", 2500)), rg=None, triples=0.0, same_start=0.05, chains=0.0, pile=0):
     rnd = random.Random(seed)
     reads, quals, tags = [], [], []
     rgs = [r[0] for r in rg] if rg else None
@@ -259,6 +259,15 @@ def make_pairs_bam(path, seed, n_frag=400, refs=(("c1", 4000), ("c2", 2500)), rg
         if rnd.random() < triples:
             for _ in range(rnd.choice([1, 1, 2])):
                 one(ref, pos + rnd.randint(0, 120), name, 0x800 | 0x41, rgid)
+        if rnd.random() < chains:                  # a long chain of supplementary alignments of one name, a few of them present in any column
+            x = pos
+            for _ in range(rnd.randint(8, 30)):
+                x += rnd.randint(25, 60)
+                if x > refs[ref][1] - 250:
+                    break                          # (one() clamps positions at the reference end: the chain would pile up there)
+                one(ref, x, name, 0x800 | 0x41, rgid)
+    for j in range(pile):                          # `pile` reads of one name over one position
+        one(0, 1000 + j, "pile", 0x800 | 0x41, rgs[0] if rgs else None)
     order = sorted(range(len(reads)), key=lambda j: (reads[j][0], reads[j][1]))
     helpers.write_bam(path, list(refs), [reads[j] for j in order], rg=rg, quals=[quals[j] for j in order], tags=[tags[j] for j in order], block=rnd.choice([0xFF00, 3000]))
     return path
@@ -345,6 +354,49 @@ def test_groups_of_three_and_more(em, tmp_path):
         assert np.array_equal(planes6(c[0]), want6) and np.array_equal(c[0].sum(axis=0), want_cov), seed
         done += 1
     assert done == 20
+
+
+def test_long_chains_of_one_name(em, tmp_path):
+    """A component (chain of overlapping same-name reads) of any length: only the number of reads of one name in ONE column is bounded."""
+    for seed in range(300, 310):
+        p = make_pairs_bam(str(tmp_path / f"ch{seed}.bam"), seed, n_frag=60, triples=0.3, chains=0.3)
+        soa = Soa(p)
+        c = soa.plain_counts(1)
+        rc, stat, _, _, err = run_emul(em, soa, c, 1, order=seed % 3)
+        assert rc == 0, err
+        want_cov, want6 = sweep_base_counts(p, soa.refs)
+        assert stat[2] > 0
+        assert np.array_equal(planes6(c[0]), want6) and np.array_equal(c[0].sum(axis=0), want_cov), seed
+        closed, npc = helpers.oracle_counts_fix_mates(p)
+        assert np.array_equal(c[0], closed) and stat[1] == npc, seed
+    # region mode over the same kind of file
+    for seed in (311, 312, 313):
+        p = make_pairs_bam(str(tmp_path / f"chr{seed}.bam"), seed, n_frag=60, triples=0.3, chains=0.3)
+        rnd = random.Random(seed)
+        regs = []
+        for ref, ln in ((0, 4000), (1, 2500)):
+            x = rnd.randint(0, 60)
+            while x < ln - 50:
+                w = rnd.choice([1, 7, 30, 90, 200, 600])
+                regs.append((ref, x, min(x + w, ln)))
+                x += w + rnd.choice([0, 0, 1, 5, 40, 300])
+        st = check_regions(em, p, regs, [1, 4], rnd.choice([0, 20]), tmp_path)
+        assert st[2] > 0
+
+
+def test_more_reads_of_one_name_in_a_column_than_the_walk_holds(em, tmp_path):
+    """Eight reads of one name over one position are replayed; a ninth is refused (never silently different)."""
+    p = make_pairs_bam(str(tmp_path / "p8.bam"), 5, n_frag=20, pile=8)
+    soa = Soa(p)
+    c = soa.plain_counts(1)
+    rc, stat, _, _, err = run_emul(em, soa, c, 1)
+    assert rc == 0, err
+    want_cov, want6 = sweep_base_counts(p, soa.refs)
+    assert np.array_equal(planes6(c[0]), want6) and np.array_equal(c[0].sum(axis=0), want_cov)
+    p = make_pairs_bam(str(tmp_path / "p9.bam"), 5, n_frag=20, pile=9)
+    soa = Soa(p)
+    rc, stat, _, _, err = run_emul(em, soa, soa.plain_counts(1), 1)
+    assert err[0] == 1, (rc, err)
 
 
 def test_multi_sample_pairs(em, tmp_path):

@@ -158,3 +158,28 @@ def test_several_batches(pairs, tmp_path):
             st = b.stats()
             assert st["n_batches"] >= 2 and st["mate_groups"] > 50
             assert np.array_equal(got, want), batch
+
+
+def test_long_chains_of_one_name(tmp_path):
+    """A chain of overlapping reads of one name may be any length (the walk holds only the members of the current column); nine reads of a
+    name over one position are refused with a message.  Several batches: a chain cut by batch boundaries is fixed in the batch that closes it."""
+    import sambamba_b200 as sb
+    import test_emul_mates as tem
+    for seed in (300, 301):
+        p = tem.make_pairs_bam(str(tmp_path / f"ch{seed}.bam"), seed, n_frag=60, triples=0.3, chains=0.3)
+        check_same(["base", "-m", "-c", "0", "--combined", p])
+        check_same(["region", "-m", "-L", "c1:1-4000", "-T", "2", p])
+        check_same(["window", "-w", "100", "-m", "-T", "2", p])
+    q = tem.make_pairs_bam(str(tmp_path / "chb.bam"), 77, n_frag=1500, refs=(("c1", 60000), ("c2", 2500)), triples=0.2, chains=0.2)
+    want, npc = helpers.oracle_counts_fix_mates(q)
+    with sb.BDepth(q) as b:
+        b.set_fix_mates(True)
+        assert np.array_equal(b.run_base(), want)
+        b.set_tuning(1 << 16, 0)
+        got = b.run_base()
+        assert b.stats()["n_batches"] >= 2 and np.array_equal(got, want)
+    p9 = tem.make_pairs_bam(str(tmp_path / "p9.bam"), 5, n_frag=20, pile=9)
+    rc, out, err = helpers.run_cli(["depth", "base", "-m", p9])
+    assert rc == 1 and b"more than 8 reads of one name cover one position" in err, err
+    p8 = tem.make_pairs_bam(str(tmp_path / "p8.bam"), 5, n_frag=20, pile=8)
+    check_same(["base", "-m", "-c", "0", p8])
