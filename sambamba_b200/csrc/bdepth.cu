@@ -1764,12 +1764,13 @@ int bdepth_run_windows(bdepth_t* h, uint32_t window, uint32_t overlap, const uin
     for (size_t r = 0; r < nref; r++) {
         bool has = (h->ref_has_host[r >> 5] >> (r & 31)) & 1;
         uint32_t m = has ? n_full[r] : n_empty[r];
-        uint32_t shift = (!has && last_has >= 0 && (long)r == last_has + 1) ? n_full[last_has] * step : 0;
+        const bool carry = !has && last_has >= 0 && (long)r == last_has + 1;      // (also when that reference was shorter than a window: shift 0, the ring holds its only, partial, window)
+        const uint32_t shift = carry ? n_full[last_has] * step : 0;
         for (uint32_t k = 0; k < m; k++) {
             size_t i = first[r] + k;
             SegDef sd = segs[i];
-            if (shift) { sd = SegDef{(uint32_t)r, shift + k * step, shift + k * step + window}; i = first[last_has] + n_full[last_has] + k; }
-            rc = deliver_one(h, sd, i, segs.size(), n_thr, reads, bases, cov, shift != 0 && k >= nslot, cb, user, idx++); if (rc) return rc;
+            if (carry) { sd = SegDef{(uint32_t)r, shift + k * step, shift + k * step + window}; i = first[last_has] + n_full[last_has] + k; }
+            rc = deliver_one(h, sd, i, segs.size(), n_thr, reads, bases, cov, carry && k >= nslot, cb, user, idx++); if (rc) return rc;
         }
     }
     return 0;

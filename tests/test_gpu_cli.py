@@ -110,3 +110,16 @@ def test_annotated_rows_of_positions_whose_bases_all_fail_q(tiny, tmp_path):
     import test_emul_mates as tem
     ms = tem.make_pairs_bam(str(tmp_path / "ms.bam"), 3, rg=[("g1", "S1"), ("g2", "S2")])
     check_same(["base", "-a", "-q", "38", "-c", "2", ms])
+
+
+def test_window_longer_than_the_last_reference_with_reads(tmp_path):
+    """The first trailing reference without reads is printed before the window state is reset (depth.d:1070-1076): its first rows carry what
+    the ring still holds -- also when the last reference with reads was shorter than one window (no full window there: shift 0).  Found by
+    tools/fuzz_emul.py."""
+    p = helpers.write_bam(str(tmp_path / "short.bam"), [("r0", 1000), ("r1", 70000), ("r2", 500)],
+                          [(0, 328, 52, 145, [(2, 0)], "AC", "q0"), (0, 400, 30, 0, [(50, 0)], "A" * 50, "q1")])
+    for args in (["window", "-w", "100000", "--overlap", "98149", "-T", "2", p], ["window", "-w", "2000", p], ["window", "-w", "2000", "--overlap", "1500", "-T", "1", p],
+                 ["window", "-w", "1000", p], ["window", "-w", "1001", "-a", p], ["window", "-w", "999", "--overlap", "3", p]):
+        out, _ = check_same(args)
+    out, _ = check_same(["window", "-w", "100000", "--overlap", "98149", p])
+    assert b"r1\t0\t100000\t2\t0.00052" in out, out[:300]

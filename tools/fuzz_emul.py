@@ -35,6 +35,7 @@ import numpy as np      # noqa: E402
 
 import helpers          # noqa: E402
 
+LEGS = {}      # how many comparisons of each kind ran
 OPS = "MIDNSHP=X"
 REF_CONSUMING = (0, 2, 3, 7, 8)
 QUERY_CONSUMING = (0, 1, 4, 7, 8)
@@ -283,6 +284,45 @@ def max_same_name_overlap(reads):
     return worst
 
 
+def run_ranks(world, path, fix, tuning, minq, combined, regions, window):
+    """`world` ranks as threads over the emulation's NCCL stand-in (as tests/test_gpu_multi.py does): every rank's owned counters, region rows
+    and window rows."""
+    import queue
+    import threading
+    import sambamba_b200 as sb
+    uid = sb.nccl_unique_id()
+    q = queue.Queue()
+
+    def main(rank):
+        try:
+            with sb.BDepth(path, device=rank) as b:
+                b.set_shard(rank, world, uid)
+                if tuning:
+                    b.set_tuning(*tuning)
+                b.set_min_baseq(minq)
+                if fix:
+                    b.set_fix_mates(True)
+                if combined:
+                    b.set_combined(True)
+                got = b.run_base()
+                st = b.stats()
+                lo, hi = st["own_lo"], st["own_hi"]
+                rr = b.run_regions(regions, [1, 3]) if regions else None
+                ww = b.run_windows(window[0], window[1], [2]) if window else None
+                q.put((rank, "ok", lo, hi, np.asarray(got)[..., lo:hi].copy(), rr, ww))
+        except Exception as e:
+            q.put((rank, "err", 0, 0, repr(e)[:300], None, None))
+
+    ts = [threading.Thread(target=main, args=(r,)) for r in range(world)]
+    for t in ts:
+        t.start()
+    res = [q.get(timeout=900) for _ in range(world)]
+    for t in ts:
+        t.join(timeout=60)
+    res.sort(key=lambda r: r[0])
+    return res
+
+
 def one_case(seed, idx, keep):
     rng = random.Random(seed * 1000003 + idx)
     d = tempfile.mkdtemp(prefix="bdfuzz_")
@@ -314,6 +354,7 @@ def one_case(seed, idx, keep):
         for fix in ([False, True] if mates_ok else [False]):
             tuning = rng.choice([None, (1 << 20, 1), (1 << 20, 3), (0, 2), (1 << 16, 1)])
             minq = rng.choice([0, 0, 13, 30])
+            LEGS["counters"] = LEGS.get("counters", 0) + 1
             try:
                 with sb.BDepth(path) as b:
                     if tuning:
@@ -335,8 +376,65 @@ def one_case(seed, idx, keep):
             if g.shape != want_c.shape or not np.array_equal(g, want_c):
                 bad = np.argwhere(g != want_c)[:3].tolist() if g.shape == want_c.shape else "shape %s vs %s" % (g.shape, want_c.shape)
                 fail("counters fix=%s tuning=%s minq=%d" % (fix, tuning, minq), str(bad))
+        # ---- several ranks (threads): the owned counters tile the genome and equal the oracle's; region / window rows equal one rank's
+        if len(reads) >= 40 and rng.random() < 0.5:
+            world = rng.choice([2, 2, 3, 4])
+            fix = mates_ok and rng.random() < 0.4
+            tuning = rng.choice([None, None, (1 << 20, 1), (0, 2), (1 << 16, 1)])
+            minq = rng.choice([0, 0, 20])
+            regions = None
+            if rng.random() < 0.6:
+                regions = []
+                for _ in range(rng.choice([1, 3, 10])):
+                    r = rng.randrange(len(refs))
+                    a0 = rng.randrange(refs[r][1])
+                    regions.append((r, a0, min(refs[r][1], a0 + rng.choice([1, 50, 500, 5000]))))
+                regions.sort()
+            window = None
+            if rng.random() < 0.5:
+                w = rng.choice([x for x in (100, 640, 1000, 5000) if tot // x <= 2000] or [100000])
+                window = (w, rng.choice([0, 0, w // 2 if tot // max(1, w // 2) <= 3000 else 0]))
+            LEGS["ranks"] = LEGS.get("ranks", 0) + 1
+            what = "ranks world=%d fix=%s tuning=%s minq=%d regions=%s window=%s" % (world, fix, tuning, minq, regions, window)
+            try:
+                with sb.BDepth(path) as b:
+                    b.set_min_baseq(minq)
+                    if fix:
+                        b.set_fix_mates(True)
+                    if rg:
+                        b.set_combined(True)
+                    one_r = b.run_regions(regions, [1, 3]) if regions else None
+                    one_w = b.run_windows(window[0], window[1], [2]) if window else None
+                res = run_ranks(world, path, fix, tuning, minq, bool(rg), regions, window)
+                want_c = (helpers.oracle_counts_fix_mates(path, min_bq=minq) if fix else helpers.oracle_counts(path, min_bq=minq))[0]
+                got = np.zeros_like(want_c)
+                prev_hi, bad = 0, None
+                for rank, status, lo, hi, arr, rr, ww in res:
+                    if status != "ok":
+                        bad = "rank %d: %s" % (rank, arr)
+                        break
+                    if hi > lo:
+                        if lo != prev_hi:
+                            bad = "owned ranges do not tile: rank %d owns [%d, %d) after %d" % (rank, lo, hi, prev_hi)
+                            break
+                        got[:, lo:hi] = np.asarray(arr).reshape(-1, hi - lo)[:7]
+                        prev_hi = hi
+                    if rank == 0 and regions and rr != one_r:
+                        bad = "region rows differ from one rank's"
+                    if rank == 0 and window and ww != one_w:
+                        bad = "window rows differ from one rank's"
+                if bad is None and prev_hi != tot:
+                    bad = "owned ranges end at %d of %d" % (prev_hi, tot)
+                if bad is None and not np.array_equal(got, want_c):
+                    bad = "counters: " + str(np.argwhere(got != want_c)[:3].tolist())
+                if bad:
+                    fail(what, bad)
+            except Exception as e:
+                import traceback
+                fail(what, traceback.format_exc()[-600:])
         # ---- command lines
         for a in rand_commands(rng, path, refs, d, bool(rg), mates_ok):
+            LEGS["cli"] = LEGS.get("cli", 0) + 1
             rc1, o1, e1 = emul_cli(["depth"] + a)
             rc2, o2, e2 = helpers.oracle_cli(a)
             if rc1 != rc2 or o1 != o2:
@@ -387,7 +485,7 @@ def main():
             sys.stdout.flush()
         if a.seconds and time.time() - t0 > a.seconds:
             break
-    print("fuzz: %d cases, %d with mismatches, %.0f s" % (n, n_fail, time.time() - t0))
+    print("fuzz: %d cases, %d with mismatches, %.0f s; comparisons: %s" % (n, n_fail, time.time() - t0, LEGS))
     return 1 if n_fail else 0
 
 
