@@ -160,3 +160,40 @@ def test_bench_reference_arm_prints_its_line(tmp_path):
     assert line["e2e"] == {"value": line["value"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     sample_mb = float(line["cpu_baseline"]["sample"].split()[1])
     assert 0 < sample_mb <= 2.2, line["cpu_baseline"]["sample"]
+
+
+def test_bench_own_arm_control_flow_under_the_emulation(tmp_path):
+    """bench.py's own arm with the product library replaced by its CUDA-on-CPU emulation build (tests/run_bench_emul.py): warm-up, timed
+    passes, the A/B legs, e2e, text rows and the verification against the oracle all run and the line carries the contract's keys.
+    (What the numbers are is meaningless here; that the round-end launch cannot die of a Python error is the point.)"""
+    import json
+    import subprocess
+    import sys
+    env = dict(os.environ, BDEPTH_BENCH_DIR=str(tmp_path), BDEPTH_BENCH_UNIT_LEN="300000")
+    r = subprocess.run([sys.executable, os.path.join(helpers.ROOT, "tests", "run_bench_emul.py"), "--reads-per-unit", "15000", "--steps", "1", "--warmup", "1", "--cpu-sample-mb", "1"],
+                       capture_output=True, text=True, env=env, timeout=900)
+    assert r.returncode == 0, r.stderr[-600:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["verified"] is True and line["verification"]["checksum"] == line["verification"]["oracle_checksum"]
+    assert line["metric"] == "bam_gb_per_s_depth_base" and line["unit"] == "GB/s" and line["n_gpus"] == 1 and line["gpu_launches"] > 0
+    assert set(line["roofline"]) >= {"bound", "achieved", "peak", "unit", "frac", "traffic"} and line["cpu_baseline"]["kind"] == "port"
+    assert line["e2e"]["h2d_bytes_per_step"] > 0 and line["e2e"]["d2h_bytes_per_step"] == 300000 * 28
+    assert all("error" not in v for k, v in line["ab"].items() if isinstance(v, dict)), line["ab"]
+    assert line["text_rows"]["text_bytes"] > 0
+
+
+def test_bench_verification_deadline():
+    """The oracle leg runs under the launch's time budget: overrun -> None (the line is printed with "verified": null), errors propagate."""
+    import time
+    import bench
+    saved = bench.BENCH_BUDGET_S
+    try:
+        bench.BENCH_BUDGET_S = 0.0
+        t0 = time.time()
+        assert bench.with_deadline(lambda: time.sleep(30)) is None and time.time() - t0 < 10
+        bench.BENCH_BUDGET_S = 1e9
+        assert bench.with_deadline(lambda: 42) == 42
+        with pytest.raises(ZeroDivisionError):
+            bench.with_deadline(lambda: 1 // 0)
+    finally:
+        bench.BENCH_BUDGET_S = saved
