@@ -1069,12 +1069,41 @@ error:
  * (SURVEY 8a "closed form verified"): for every read passing the filter and
  * basesCovered()>0, walk the CIGAR from `pos`: M/=/X add to plane nt5(base) if
  * qual >= min_bq; D -> DEL; N -> REFSKIP.  Cross-checked against the sweep in
- * tests/test_oracle_golden.py.  A leading N op (quirk 1) is NOT modelled here.
+ * tests/test_oracle_golden.py.  A CIGAR that begins with N (quirk 1) is first turned
+ * into what the sweep's cursor makes of it (closed_form_lead_n below).
  *
  * counts layout: [7][total_len] planes A,C,G,T,N,DEL,REFSKIP over the
  * concatenation of all references (ref_off[i] = sum of lengths before i).
  */
 typedef struct { uint64_t n_records, n_pass, n_blocks, ulen, clen, covered, min_lin, max_lin; double t_inflate, t_scan; } ScatterStats;
+
+/* Quirk 1 in closed form.  pread_init_cursor (pileup.d:175-192) steps over leading N operations without consuming them, so the
+ * cursor walks the remaining operations that many columns early; past the last operation pread_increment (pileup.d:195-222) leaves
+ * cur_op at the last operation it looked at -- cigar[n-1] -- for the columns that remain (the read stays in the sweep for
+ * basesCovered() columns): base_process_current then counts a deletion if that operation is D and a reference skip if it does not
+ * consume both query and reference.  Equivalent CIGAR: the leading N operations removed, their total length appended as N (or D).
+ * If the last operation is M/=/X the sweep reads query offsets past l_seq there (pread_base's '=' / quality 0 stand in for the
+ * reference's unchecked reads): not a defined result, left as it is -- the product refuses such a read.  Returns 1 if rewritten.
+ * Checked against the faithful sweep in tests/test_oracle_golden.py. */
+static int closed_form_lead_n(uint8_t *cig, uint32_t n_cigar) {
+    uint32_t first = 0, k = 0; uint64_t nlead = 0; int found = 0;
+    for (; first < n_cigar; first++) {
+        uint32_t c = rd32(cig + 4 * first);
+        if (!op_rcons(c)) continue;
+        if ((c & 0xF) != 3) { found = 1; break; }
+        nlead += op_len(c); k++;
+    }
+    if (!k || !found) return 0;
+    uint32_t last = rd32(cig + 4 * (n_cigar - 1)) & 0xF;
+    if (last == 0 || last == 7 || last == 8) return 0;
+    uint32_t *tmp = malloc(4 * (size_t)n_cigar), w = 0;
+    for (uint32_t j = 0; j < n_cigar; j++) { uint32_t c = rd32(cig + 4 * j); if (j < first && (c & 0xF) == 3) continue; tmp[w++] = c; }
+    tmp[w++] = (uint32_t)(nlead << 4) | (last == 2 ? 2u : 3u);
+    while (w < n_cigar) tmp[w++] = 6u;                       /* 0P: consumes nothing */
+    for (uint32_t j = 0; j < n_cigar; j++) { uint32_t c = tmp[j]; cig[4 * j] = (uint8_t)c; cig[4 * j + 1] = (uint8_t)(c >> 8); cig[4 * j + 2] = (uint8_t)(c >> 16); cig[4 * j + 3] = (uint8_t)(c >> 24); }
+    free(tmp);
+    return 1;
+}
 
 /* One passing read of the closed form: scatter its CIGAR into the window (the body of the per-read loop; the record
  * walk that finds the reads is serial, the scatter runs on worker threads with relaxed atomic increments). */
@@ -1143,6 +1172,7 @@ static int base_counts_impl(const char *bam_path, int mapq_gt, unsigned flag_rej
         uint64_t span = 0; for (uint32_t i = 0; i < n_cigar; i++) { uint32_t c = rd32(cig + 4 * i); if (op_rcons(c)) span += op_len(c); }
         if (!span) continue;
         npass++;
+        closed_form_lead_n((uint8_t *)cig, n_cigar);          /* B.z.u is this call's own copy of the inflated stream */
         { uint64_t g0 = ref_off[ref_id] + (uint32_t)pos, g1 = g0 + span; if (g0 < min_lin) min_lin = g0; if (g1 > max_lin) max_lin = g1; }
         if (!counts) continue;
         if (nrd == cap) { cap = cap ? cap * 2 : (1u << 16); rd = realloc(rd, cap * sizeof *rd); }

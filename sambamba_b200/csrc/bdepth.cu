@@ -188,7 +188,7 @@ struct bdepth {
     bool staged = false; uint64_t staged_file_off = 0;
     DevBuf tok, lits, aux, segi, littab;              // two-phase K1: match tokens, packed literals, per-block counts, segment starts, literal tables
     DevBuf comp, descs, status, ubuf, chunk_start, entry, exitb, count, slot_base, slots, rec_base, walk_list;
-    DevBuf soa_start, soa_span, soa_meta, soa_off, soa_ncl, soa_lseq, long_list, tile_first, tile_lo, counts, ref_len_d, ref_lin0_d, scan_stats, ref_has, misc;
+    DevBuf soa_start, soa_span, soa_meta, soa_off, soa_ncl, soa_lseq, long_list, tile_first, tile_lo, counts, ref_len_d, ref_lin0_d, scan_stats, ref_has, ref_has_all, flt_d, misc;
     uint64_t cnt_base = 0, win_len = 0;
     void* pinned = nullptr; size_t pinned_cap = 0;
     HostScratch hs;
@@ -606,6 +606,7 @@ int run_pipeline(bdepth* h, RunMode mode, RunOut* ro, Emitter* em = nullptr) {
     // batch after the first re-reads the end of the previous one as "ghost" records -- from the earliest record that can
     // still meet a mate (mates.cuh) -- so that a pair cut by a batch boundary is seen complete by the batch that closes it.
     const bool fix = mode == RUN_FULL && h->fix_mates;
+    bool flt_uploaded = false;            // -L regions on the device for k_ref_seen (once per run)
     if (fix && h->world > 1 && !h->comm) return fail(h, BDEPTH_ERR_ARG, "fix-mate-overlaps on several ranks needs the boundary exchange (bdepth_set_shard with a NCCL id)");
     const uint64_t eff_batch_u = h->batch_u;
     size_t ghost_b = 0; int64_t ghost_entry = 0; uint64_t ghost_below_abs = 0, prev_s_last = 0, covered_from = 0;      // -m: where the next batch's stream begins
@@ -980,25 +981,49 @@ int run_pipeline(bdepth* h, RunMode mode, RunOut* ro, Emitter* em = nullptr) {
         size_t Rc = R ? R : 1;
         CK(h->soa_start.ensure(Rc * 8)); CK(h->soa_span.ensure(Rc * 4)); CK(h->soa_meta.ensure(Rc * 4)); CK(h->soa_off.ensure(Rc * 8)); CK(h->soa_ncl.ensure(Rc * 4)); CK(h->soa_lseq.ensure(Rc * 4)); CK(h->long_list.ensure(Rc * 4));
         RecordSoA soa{h->soa_start.as<uint64_t>(), h->soa_span.as<uint32_t>(), h->soa_meta.as<uint32_t>(), h->soa_off.as<int64_t>(), h->soa_ncl.as<uint32_t>(), h->soa_lseq.as<int32_t>()};
-        ScanStats zs{0, 0, 0, 0, ~0ull, 0, 0, ~0ull, 0, 0, ~0ull, 0, ~0ull};
+        ScanStats zs{0, 0, 0, 0, ~0ull, 0, 0, ~0ull, 0, 0, ~0ull, 0, ~0ull, ~0ull};
         const int64_t ghost_below = (fix && batch_no > 0) ? (int64_t)ghost_below_abs - (int64_t)batch_u0 : INT64_MIN;
         const int64_t own_lo = (fix && h->world > 1) ? (int64_t)h->own_lo_abs_u - (int64_t)batch_u0 : INT64_MIN;           // -m on several ranks: records outside belong to the neighbours
         const int64_t own_hi = (fix && h->world > 1 && h->limit_abs_u < h->total_u) ? (int64_t)h->limit_abs_u - (int64_t)batch_u0 : INT64_MAX;
         const int64_t zone_below = (!fix && !sparse && h->world > 1) ? (int64_t)h->own_lo_abs_u - (int64_t)batch_u0 : INT64_MIN;       // records of the previous ranks' zone
         UP(h->scan_stats.p, &zs, sizeof zs);
         if ((mode == RUN_SCAN_ONLY || mode == RUN_INDEX) && !h->ref_has.p) { CK(h->ref_has.ensure((nref / 32 + 2) * 4)); CK(cudaMemsetAsync(h->ref_has.p, 0, (nref / 32 + 2) * 4, sm)); }
-#define K2_DECODE(F, G) BD_LAUNCH((unsigned)((nb * 32 + 255) / 256), 256, 0, sm, k2_decode<F, G>)(sp, h->chunk_start.as<int64_t>(), (uint32_t)nb, h->slot_base.as<uint32_t>(), h->slots.as<uint16_t>(), h->count.as<uint32_t>(), h->rec_base.as<uint32_t>(), soa, h->mapq_gt, h->flag_reject, h->scan_stats.as<ScanStats>(), h->long_list.as<uint32_t>(), h->ref_has.as<uint32_t>(), rgt, d_fprog, ghost_below, own_lo, own_hi, zone_below)
+        // runs with -L regions: K2's every-passing-read bits go to a scratch word array, k_ref_seen marks the references of the reads that overlap a region
+        uint32_t* has_dst = h->ref_has.as<uint32_t>();
+        const uint32_t n_flt_k2 = mode == RUN_FULL ? (uint32_t)h->regions.size() : 0u;
+        if (n_flt_k2) {
+            if (!flt_uploaded) {
+                std::vector<uint64_t> fl; fl.reserve(2 * (size_t)n_flt_k2);
+                for (auto& g : h->regions) fl.push_back(h->hdr.ref_lin0[g.ref_id] + g.start);
+                for (auto& g : h->regions) fl.push_back(h->hdr.ref_lin0[g.ref_id] + g.end);
+                CK(h->flt_d.ensure(fl.size() * 8)); CK(cudaMemcpyAsync(h->flt_d.p, fl.data(), fl.size() * 8, cudaMemcpyHostToDevice, sm)); CK(cudaStreamSynchronize(sm));      // (fl is a local)
+                CK(h->ref_has_all.ensure((nref / 32 + 2) * 4)); CK(cudaMemsetAsync(h->ref_has_all.p, 0, (nref / 32 + 2) * 4, sm));
+                flt_uploaded = true;
+            }
+            has_dst = h->ref_has_all.as<uint32_t>();
+        }
+#define K2_DECODE(F, G) BD_LAUNCH((unsigned)((nb * 32 + 255) / 256), 256, 0, sm, k2_decode<F, G>)(sp, h->chunk_start.as<int64_t>(), (uint32_t)nb, h->slot_base.as<uint32_t>(), h->slots.as<uint16_t>(), h->count.as<uint32_t>(), h->rec_base.as<uint32_t>(), soa, h->mapq_gt, h->flag_reject, h->scan_stats.as<ScanStats>(), h->long_list.as<uint32_t>(), has_dst, rgt, d_fprog, ghost_below, own_lo, own_hi, zone_below)
         if (fix) { if (d_fprog) K2_DECODE(true, true); else K2_DECODE(false, true); }
         else if (d_fprog) K2_DECODE(true, false);
         else K2_DECODE(false, false);
 #undef K2_DECODE
         CK(cudaGetLastError()); st.gpu_launches++;
+        if (R && mode != RUN_INDEX && mode != RUN_SCAN_ONLY) {      // quirk 1: CIGARs that begin with N, rewritten to what the reference's cursor makes of them (the index and the raw scan see the file as it is)
+            BD_LAUNCH((unsigned)((R + 255) / 256), 256, 0, sm, k2_lead_n)(soa, u0, (uint32_t)R, h->scan_stats.as<ScanStats>(), h->seg.on ? 1 : 0, n_flt_k2 ? h->flt_d.as<uint64_t>() : nullptr, n_flt_k2 ? h->flt_d.as<uint64_t>() + n_flt_k2 : nullptr, n_flt_k2);
+            CK(cudaGetLastError()); st.gpu_launches++;
+        }
+        if (n_flt_k2 && R) {
+            BD_LAUNCH((unsigned)((R + 255) / 256), 256, 0, sm, k_ref_seen)(soa, (uint32_t)R, h->flt_d.as<uint64_t>(), h->flt_d.as<uint64_t>() + n_flt_k2, n_flt_k2, h->ref_lin0_d.as<uint64_t>(), (uint32_t)nref, h->ref_has.as<uint32_t>());
+            CK(cudaGetLastError()); st.gpu_launches++;
+        }
         DOWN(ssp, ScanStats, h->scan_stats.p, sizeof(ScanStats));
         CK(cudaEventRecord(e3, sm));
         CK(cudaStreamSynchronize(sm));
         const ScanStats ss = *ssp;
         st.n_records -= ss.n_ghost + ss.n_ghost_right;          // re-read records of the previous batch / of the neighbours' zones are counted there
         if (ss.bad_rec != ~0ull) return fail(h, BDEPTH_ERR_FORMAT, "corrupt BAM record (#%llu of the batch): its name, CIGAR, sequence and qualities do not fit its block_size", ss.bad_rec);
+        if (ss.lead_n != ~0ull) return fail(h, BDEPTH_ERR_FORMAT, "read #%llu of the batch: its CIGAR begins with N%s (pileup.d:180-189): there is no result to reproduce", ss.lead_n,
+                                             h->seg.on ? " -- the reference computes region / window statistics of such a read partly from its CIGAR as written and partly from a cursor that skips the leading N" : " and ends in a match -- the reference's pileup cursor runs past the read's sequence on such a read");
         if (ss.rg_err != ~0ull) return fail(h, BDEPTH_ERR_FORMAT, "error in read #%llu of the batch: its read group is not present in the header", ss.rg_err);
         st.n_records_pass += ss.n_pass; st.n_cigar_ops += ss.n_cigar; st.seq_bytes += ss.seq_bytes; st.long_reads += ss.n_long;
         if (ss.n_pass) { shard_min = std::min<uint64_t>(shard_min, ss.min_start); shard_max = std::max<uint64_t>(shard_max, ss.max_end); }
@@ -1345,7 +1370,7 @@ void bdepth_close(bdepth_t* h) {
     h->extra.clear();
     cudaSetDevice(h->device);
     h->anchors_idx.release(); h->anchors_val.release(); h->chunk_limit.release(); h->tok.release(); h->lits.release(); h->aux.release(); h->segi.release(); h->littab.release();
-    DevBuf* bufs[] = {&h->comp, &h->descs, &h->status, &h->ubuf, &h->chunk_start, &h->entry, &h->exitb, &h->count, &h->slot_base, &h->slots, &h->rec_base, &h->walk_list, &h->soa_start, &h->soa_span, &h->soa_meta, &h->soa_off, &h->soa_ncl, &h->soa_lseq, &h->long_list, &h->tile_first, &h->tile_lo, &h->counts, &h->ref_len_d, &h->ref_lin0_d, &h->scan_stats, &h->ref_has, &h->misc};
+    DevBuf* bufs[] = {&h->comp, &h->descs, &h->status, &h->ubuf, &h->chunk_start, &h->entry, &h->exitb, &h->count, &h->slot_base, &h->slots, &h->rec_base, &h->walk_list, &h->soa_start, &h->soa_span, &h->soa_meta, &h->soa_off, &h->soa_ncl, &h->soa_lseq, &h->long_list, &h->tile_first, &h->tile_lo, &h->counts, &h->ref_len_d, &h->ref_lin0_d, &h->scan_stats, &h->ref_has, &h->ref_has_all, &h->flt_d, &h->misc};
     for (DevBuf* b : bufs) b->release();
     h->rg_ids.release(); h->rg_offs.release(); h->rg_samp.release();
     h->text[0].release(); h->text[1].release(); h->text_tiles.release(); h->text_offs.release(); h->text_zero.release(); h->text_samp.release(); h->present.release();
@@ -1516,10 +1541,11 @@ int bdepth_run_base_text(bdepth_t* h, const bdepth_text_opts* o, bdepth_text_cb 
     if (!o) return fail(h, BDEPTH_ERR_ARG, "null options");
     // a position that reads cover but whose every base fails -q still has a column: with -a and a positive minimum coverage
     // the reference prints it (flag n); the counters cannot tell it from an empty position, a bitmap can (one rank only)
-    h->want_presence = o->annotate && h->minq > 0 && o->min_cov > 0 && h->world == 1;
+    // (with -m a column can be empty as well: a read left in state `detected` without a partner is skipped, depth.d:521-525)
+    const bool presence = o->annotate && (h->minq > 0 || h->fix_mates) && o->min_cov > 0 && h->world == 1;
+    h->want_presence = presence;
     int rc = run_all_inputs(h); h->want_presence = false; if (rc) return rc;
     const bool ms = h->S > 1;             // one row per sample and position (k_text_len_ms / k_text_write_ms)
-    const bool presence = o->annotate && h->minq > 0 && o->min_cov > 0 && h->world == 1;
     cudaStream_t sm = h->s_main;
     cudaEvent_t e0 = h->ev[5], e1 = h->ev[6];
     CK(cudaEventRecord(e0, sm));
@@ -1552,6 +1578,13 @@ int bdepth_run_base_text(bdepth_t* h, const bdepth_text_opts* o, bdepth_text_cb 
     // at the counter-window edges (outside it every counter is zero) and into chunks whose text fits the buffer
     struct Piece { uint32_t ref; uint64_t a, b; bool in_window; };
     std::vector<Piece> pieces;
+    // --min-coverage=0: the reference writes the empty rows of the references in front of the first one it sees reads on, of those behind the
+    // last one, and of the gaps of the ones it sees -- but when the sweep moves from one reference to a later one, only the tail of the
+    // former and the head of the latter are written (PerBasePrinter.push, depth.d:578-581): a reference in between, which has no column,
+    // gets no rows at all.  (No reference with reads: close() writes every one, :597-599.)
+    long first_seen = -1, last_seen = -1;
+    { const size_t nref = h->hdr.ref_len.size(); for (size_t r = 0; r < nref && !h->ref_has_host.empty(); r++) if ((h->ref_has_host[r >> 5] >> (r & 31)) & 1) { if (first_seen < 0) first_seen = (long)r; last_seen = (long)r; } }
+    auto ref_rows = [&](size_t ref) { return first_seen < 0 || (long)ref <= first_seen || (long)ref >= last_seen || ((h->ref_has_host[ref >> 5] >> (ref & 31)) & 1); };
     auto add_range = [&](uint64_t a, uint64_t b) {
         a = std::max(a, h->own_lo); b = std::min(b, h->own_hi);
         while (a < b) {
@@ -1564,7 +1597,7 @@ int bdepth_run_base_text(bdepth_t* h, const bdepth_text_opts* o, bdepth_text_cb 
             size_t max_row = (h->hdr.ref_names[ref].size() + max_sample + 96) * (ms ? h->S : 1);
             uint64_t cp = std::max<uint64_t>(TEXT_TILE, (TEXT_BUF / max_row) / TEXT_TILE * TEXT_TILE);
             e = std::min(e, a + cp);
-            if (inw || o->min_cov <= 0) pieces.push_back({(uint32_t)ref, a, e, inw});      // zero rows only exist when min_cov == 0
+            if ((inw || o->min_cov <= 0) && ref_rows(ref)) pieces.push_back({(uint32_t)ref, a, e, inw});      // zero rows only exist when min_cov == 0 (a skipped reference has no read, so no row of any kind)
             a = e;
         }
     };

@@ -471,6 +471,7 @@ struct ScanStats {      // device-side accumulators
     unsigned long long n_ghost_right;   // -m on several ranks: records at or after the shard limit (the next rank's zone)
     unsigned long long bad_rec;     // 1 + index of the first record whose name + CIGAR + sequence + qualities do not fit its block_size (~0: none)
     unsigned long long n_zone_pass, min_start_all;      // several ranks without -m: passing reads of the previous ranks' zone; smallest start over own and zone reads
+    unsigned long long lead_n;      // 1 + index of the first read whose CIGAR begins with N and cannot be reproduced (k2_lead_n; ~0: none)
 };
 constexpr uint64_t START_UNPLACED = 0xFFFFFFFFFFFFFFFEull;      // RecordSoA.start of a record without a position on a known reference
 constexpr uint32_t NCL_GHOST = 1u << 31;      // RecordSoA.ncl: a record that is only re-read for the mate kernels and passes the filter (its pass bit is clear)
@@ -1182,6 +1183,74 @@ __global__ void k_presence(RecordSoA soa, uint32_t R, uint64_t cnt_base, uint64_
         uint32_t m = (hi == 31 ? 0xFFFFFFFFu : ((1u << (hi + 1)) - 1u)) & ~((1u << lo) - 1u);
         atomicOr(&present[w], m);
     }
+}
+// Quirk 1: PileupRead's constructor looks for the first M/=/X/D operation and steps over N operations on the way WITHOUT
+// consuming them (pileup.d:180-189), while the read still occupies basesCovered() columns from its position.  The cursor therefore
+// runs through the rest of the CIGAR that many columns early and, once past the last operation, stays on the last one it examined --
+// cigar[$ - 1] -- for the columns that are left (incrementPosition leaves _cur_op alone when it finds nothing, :207-218): a D counts
+// deletions there, every operation that does not consume both query and reference (N, S, I, H, P) counts reference skips
+// (depth.d:507-513).  That is exactly the CIGAR with its leading N operations taken out and as many skipped (or deleted) columns
+// appended: this kernel rewrites such a CIGAR in the inflated stream, in place and in the same number of operations (thread per record,
+// after k2_decode -- the -F query has seen the original -- and before anything walks CIGARs), and every later kernel then computes what the
+// reference computes.  If the last operation is M/=/X the reference indexes the sequence and the qualities past their end for those
+// columns (release build: unchecked reads): there is nothing to reproduce, the run is refused.  Real aligners never write a leading N;
+// the cost for ordinary reads is one look at the first reference-consuming operation.
+// Region and window statistics mix the two views: readCount and meanCoverage go through countOverlappingBases, which walks the CIGAR
+// from the read's position as written (depth.d:671-698), the percentages through the shifted cursor -- with refuse_all such a read
+// ends the run whatever its last operation is.
+// (With -L only reads that overlap a region are in the reference's stream at all: flt_s / flt_e as in k_ref_seen; the others cannot end the run.)
+__global__ void k2_lead_n(RecordSoA soa, uint8_t* u, uint32_t R, ScanStats* __restrict__ st, int refuse_all, const uint64_t* __restrict__ flt_s, const uint64_t* __restrict__ flt_e, uint32_t n_flt) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    const uint32_t ncl = soa.ncl[r];
+    if (!((soa.meta[r] & 1u) || (ncl & (NCL_GHOST | NCL_FOREIGN)))) return;      // only reads that are counted (or re-read for the mate kernels)
+    const uint32_t n_cigar = (ncl >> 8) & 0xFFFFu, l_name = ncl & 0xFFu;
+    uint8_t* cg = u + soa.off[r] + 32 + l_name;
+    uint32_t first = 0, k = 0; uint64_t nlead = 0; bool found = false, zero = false;
+    for (; first < n_cigar; first++) {
+        const uint32_t c = ldu32(cg + 4 * first), op = c & 15u;
+        if (!cig_rcons(op)) continue;
+        if (op != 3u) { found = true; break; }
+        nlead += c >> 4; k++; zero |= (c >> 4) == 0;
+    }
+    if (!k || !found) return;            // the usual case; or nothing but N consumes the reference: the cursor never leaves the last operation and every column is a skip, as the CIGAR says
+    // ---- cold from here on
+    auto ld = [&](uint32_t j) { const uint8_t* q = cg + 4 * j; return (uint32_t)q[0] | ((uint32_t)q[1] << 8) | ((uint32_t)q[2] << 16) | ((uint32_t)q[3] << 24); };      // plain loads: these bytes are written below
+    auto st4 = [&](uint32_t j, uint32_t v) { uint8_t* q = cg + 4 * j; q[0] = (uint8_t)v; q[1] = (uint8_t)(v >> 8); q[2] = (uint8_t)(v >> 16); q[3] = (uint8_t)(v >> 24); };
+    const uint32_t last_op = ld(n_cigar - 1) & 15u;
+    if (refuse_all || last_op == 0u || last_op == 7u || last_op == 8u || zero || nlead >= (1ull << 28)) {
+        bool in_stream = true;
+        if (n_flt) {
+            const uint64_t s0 = soa.start[r], e0 = s0 + soa.span[r];
+            uint32_t lo = 0, hi = n_flt;
+            while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (flt_e[mid] <= s0) lo = mid + 1; else hi = mid; }
+            in_stream = lo < n_flt && flt_s[lo] < e0;
+        }
+        if (in_stream) atomicMin(&st->lead_n, (unsigned long long)r + 1);
+        return;
+    }
+    uint32_t w = 0;
+    for (uint32_t j = 0; j < n_cigar; j++) { const uint32_t c = ld(j); if (j < first && (c & 15u) == 3u) continue; st4(w++, c); }      // w <= j: a slot is read before it is overwritten
+    const uint32_t tail_op = last_op == 2u ? 2u : 3u;
+    for (uint32_t t = 0; t + 1 < k; t++) st4(w++, (1u << 4) | tail_op);                     // k operations went out, k come in: k - 1 of one column ...
+    st4(w, ((uint32_t)(nlead - (k - 1)) << 4) | tail_op);                                       // ... and the rest (every leading N had at least one column: nlead >= k)
+}
+
+// With -L the reference's pileup only ever sees the reads that overlap a region (getReadsOverlapping, randomaccessmanager.d:316-338): a
+// reference "has reads" -- is announced, gets its empty rows with --min-coverage=0 (depth.d:574-586), carries window state -- iff such a
+// read passes the filter.  K2 marks every passing read's reference; runs with regions mark through this kernel instead (thread per read;
+// flt_s / flt_e: the merged regions in linear coordinates, sorted and disjoint, as mates.cuh uses them).
+__global__ void k_ref_seen(RecordSoA soa, uint32_t R, const uint64_t* __restrict__ flt_s, const uint64_t* __restrict__ flt_e, uint32_t n_flt,
+                           const uint64_t* __restrict__ ref_lin0, uint32_t n_ref, uint32_t* __restrict__ ref_has_reads) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R || !(soa.meta[r] & 1u) || !n_ref) return;
+    const uint64_t s = soa.start[r], e = s + soa.span[r];
+    uint32_t lo = 0, hi = n_flt;                                   // first region that ends after the read starts; the read is in the stream iff it reaches it
+    while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (flt_e[mid] <= s) lo = mid + 1; else hi = mid; }
+    if (lo >= n_flt || flt_s[lo] >= e) return;
+    uint32_t a = 0, b = n_ref;                                     // the last reference that begins at or before s (an empty reference shares its successor's origin)
+    while (a + 1 < b) { const uint32_t mid = (a + b) >> 1; if (ref_lin0[mid] <= s) a = mid; else b = mid; }
+    atomicOr(&ref_has_reads[a >> 5], 1u << (a & 31));
 }
 __device__ __forceinline__ uint32_t dec_digits(uint32_t v) {
     return v < 10u ? 1u : v < 100u ? 2u : v < 1000u ? 3u : v < 10000u ? 4u : v < 100000u ? 5u : v < 1000000u ? 6u : v < 10000000u ? 7u : v < 100000000u ? 8u : v < 1000000000u ? 9u : 10u;

@@ -326,10 +326,22 @@ BD_HD void mate_fix_group(const MateParams& p, uint32_t leader, uint64_t hi) {
     unsigned long long cols = 0;
     uint32_t seg_hi = 0;
     if (p.n_seg) { uint32_t l = 0, h2 = p.n_seg; while (l < h2) { uint32_t mid = (l + h2) >> 1; if (p.seg_s[mid] < hi + p.seg_ext_max) l = mid + 1; else h2 = mid; } seg_hi = l; }   // segments that are updated before the component ends
+    // Per-base output with -L: PerBasePrinter.push hands a column to writeColumn -- and with it to detectOverlappingMates -- only when it
+    // lies in a region (depth.d:567-591), so the states do not move on the columns in between (a `detected` read that is alone there is
+    // still `detected` when the next region begins).  Region and window mode run the detection on every column (depth.d:760-770).
+    const bool gated = p.n_flt != 0 && p.n_seg == 0;
+    uint32_t fi = 0;
+    if (gated) { uint32_t l = 0, h2 = p.n_flt; while (l < h2) { uint32_t mid = (l + h2) >> 1; if (p.flt_e[mid] <= lo) l = mid + 1; else h2 = mid; } fi = l; }
     for (uint64_t g = lo; g < hi; g++) {
+        if (gated) {
+            while (fi < p.n_flt && p.flt_e[fi] <= g) fi++;
+            if (fi >= p.n_flt) break;                                   // no written column is left
+            if (p.flt_s[fi] > g) { g = (p.flt_s[fi] < hi ? p.flt_s[fi] : hi) - 1; continue; }      // on to the next region's first column
+        }
         { int w = 0; for (int i = 0; i < np; i++) { const int k = pres[i]; if (g < M[k].e) pres[w++] = k; else used &= ~(1u << k); } np = w; }      // members that ended
         for (; next < p.R && p.start[next] <= g; next++) {                                                                              // members that begin here
             if (p.mhash[next] != h || !(p.mflag[next] & MF_INSTREAM)) continue;
+            if (p.start[next] + p.span[next] <= g) continue;             // (began and ended between two regions: never seen by a written column)
             if (np == MATE_MAX_MEMBERS) { m_err(p, MATE_ERR_TOO_MANY, next); return; }
             int k = 0; while ((used >> k) & 1u) k++;
             used |= 1u << k; m_load(p, next, M[k]); C[k] = MCur(); st[k] = 0; pres[np++] = k;

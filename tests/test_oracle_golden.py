@@ -242,3 +242,56 @@ def test_index_builder_edge_cases_by_hand(tmp_path):
     assert bins[37450][1] == (4, 0)
     assert len(lin) == 4 and lin[0] == bins[4681][0][0] and lin[1] == bins[585][0][0] and lin[2] == lin[1] and lin[3] == bins[4684][0][0]      # window 2 is a gap: filled from the left
     assert bins[4681][0][1] == bins[585][0][0] and bins[585][0][1] == bins[4684][0][0]          # chunks meet where the bin changes
+
+
+LEAD_N_READS = [  # (pos, cigar, l_seq): CIGARs that begin with N and do NOT end in M/=/X (there the reference reads past the sequence)
+    (100, [(5, 3), (10, 0), (3, 4)], 13),                       # 5N10M3S
+    (140, [(2, 4), (4, 3), (6, 0), (2, 2), (5, 0), (4, 5)], 13),  # 2S4N6M2D5M4H
+    (200, [(3, 3), (2, 1), (2, 3), (8, 0), (3, 2)], 10),        # 3N2I2N8M3D: two leading N operations, the tail is counted as deletions
+    (260, [(7, 3), (4, 2), (6, 0), (20, 3), (5, 0), (1, 1)], 12),  # 7N4D6M20N5M1I: the first non-N operation is a D
+    (330, [(6, 3), (3, 4)], 3),                                 # 6N3S: nothing but N consumes the reference -- plain skips
+    (360, [(4, 3), (9, 0), (2, 6)], 9),                         # 4N9M2P
+]
+
+
+def _lead_n_bam(tmp_path, name="lead.bam"):
+    import random
+    rng = random.Random(5)
+    reads, quals = [], []
+    for i, (pos, cig, ls) in enumerate(LEAD_N_READS):
+        reads.append((0, pos, 30, 0, cig, "".join(rng.choice("ACGT") for _ in range(ls)), f"n{i}"))
+        quals.append([rng.choice([5, 30, 40]) for _ in range(ls)])
+    # ordinary neighbours so that columns hold more than one read
+    for pos in (95, 150, 210, 270, 335, 365):
+        reads.append((0, pos, 30, 0, [(30, 0)], "".join(rng.choice("ACGT") for _ in range(30)), f"m{pos}"))
+        quals.append([30] * 30)
+    order = sorted(range(len(reads)), key=lambda i: reads[i][1])
+    return helpers.write_bam(str(tmp_path / name), [("r0", 1000)], [reads[i] for i in order], quals=[quals[i] for i in order])
+
+
+def test_leading_n_closed_form_equals_the_sweep(tmp_path):
+    """Quirk 1 (pileup.d:180-189): the cursor steps over leading N operations without consuming them.  The faithful sweep restates the
+    constructor literally; the closed forms use the equivalent CIGAR (closed_form_lead_n) -- they must agree column by column, for the
+    per-base counters and for the region statistics, at two -q settings."""
+    p = _lead_n_bam(tmp_path)
+    for minq in (0, 20):
+        rc, out, err = helpers.oracle_cli(["base", "-c", "0", "-q", str(minq), p])
+        assert rc == 0, err
+        rows = {int(l.split(b"\t")[1]): [int(x) for x in l.split(b"\t")[2:9]] for l in out.splitlines()[1:]}
+        counts, _ = helpers.oracle_counts(p, min_bq=minq)
+        for pos, r in rows.items():
+            col = counts[:, pos]
+            assert [int(col.sum()), col[0], col[1], col[2], col[3], col[5], col[6]] == r, (minq, pos)
+        # the first read: 5N10M3S at 100 -- bases at 100..109 (not 105..114), then five skipped columns
+        assert rows[100][0] >= 1 and rows[112][6] >= 1
+    # region statistics through the sweep vs the closed form on disjoint segments
+    segs = [(90, 120), (120, 215), (215, 300), (320, 400)]
+    import numpy as np
+    bed = tmp_path / "s.bed"
+    bed.write_text("".join(f"r0\t{a}\t{b}\n" for a, b in segs))
+    for minq in (0, 20):
+        rc, out, err = helpers.oracle_cli(["region", "-L", str(bed), "-q", str(minq), "-T", "1", "-T", "2", p])
+        assert rc == 0, err
+        rr = _rows(out)
+        wr, wb, wc = helpers.oracle_segment_stats(p, np.array([a for a, _ in segs], dtype=np.uint64), np.array([b for _, b in segs], dtype=np.uint64), (1, 2), min_bq=minq)
+        assert [int(r[3]) for r in rr] == [int(x) for x in wr], (minq, rr, wr)
