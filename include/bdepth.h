@@ -215,7 +215,9 @@ int bdepth_run_base_text(bdepth_t* h, const bdepth_text_opts* opts, bdepth_text_
 
 int bdepth_get_stats(const bdepth_t* h, bdepth_stats* out);
 /* After a run: 1 if the reference has at least one read that produced a pileup column (the
- * condition under which depth.d:1225-1229 prints "Processing reference #k"). */
+ * condition under which depth.d:1225-1229 prints "Processing reference #k").  With regions set
+ * only reads that overlap a region count: the reference's stream holds no others
+ * (getReadsOverlapping, BioD/bio/std/hts/bam/randomaccessmanager.d:316-338). */
 int bdepth_ref_has_reads(const bdepth_t* h, int ref);
 
 /* ------------------------------------------------------------------ kernel-level entry points
