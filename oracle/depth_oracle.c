@@ -1172,7 +1172,9 @@ static int base_counts_impl(const char *bam_path, int mapq_gt, unsigned flag_rej
         uint64_t span = 0; for (uint32_t i = 0; i < n_cigar; i++) { uint32_t c = rd32(cig + 4 * i); if (op_rcons(c)) span += op_len(c); }
         if (!span) continue;
         npass++;
-        closed_form_lead_n((uint8_t *)cig, n_cigar);          /* B.z.u is this call's own copy of the inflated stream */
+        /* (B.z.u is this call's own copy of the inflated stream.)  Region / window statistics take readCount and meanCoverage from the CIGAR
+         * as written (countOverlappingBases, depth.d:671-698) and the percentages from the cursor: no closed form here, only the sweep knows */
+        if (closed_form_lead_n((uint8_t *)cig, n_cigar) && n_seg) { free(rd); free(ref_off); bgzf_free(&B.z); return fail("closed form of the region statistics: a CIGAR that begins with N is not modelled (use the sweep)"); }
         { uint64_t g0 = ref_off[ref_id] + (uint32_t)pos, g1 = g0 + span; if (g0 < min_lin) min_lin = g0; if (g1 > max_lin) max_lin = g1; }
         if (!counts) continue;
         if (nrd == cap) { cap = cap ? cap * 2 : (1u << 16); rd = realloc(rd, cap * sizeof *rd); }

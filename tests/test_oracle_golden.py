@@ -271,8 +271,8 @@ def _lead_n_bam(tmp_path, name="lead.bam"):
 
 def test_leading_n_closed_form_equals_the_sweep(tmp_path):
     """Quirk 1 (pileup.d:180-189): the cursor steps over leading N operations without consuming them.  The faithful sweep restates the
-    constructor literally; the closed forms use the equivalent CIGAR (closed_form_lead_n) -- they must agree column by column, for the
-    per-base counters and for the region statistics, at two -q settings."""
+    constructor literally; the per-base closed form uses the equivalent CIGAR (closed_form_lead_n) -- they must agree column by column, at
+    two -q settings."""
     p = _lead_n_bam(tmp_path)
     for minq in (0, 20):
         rc, out, err = helpers.oracle_cli(["base", "-c", "0", "-q", str(minq), p])
@@ -284,14 +284,8 @@ def test_leading_n_closed_form_equals_the_sweep(tmp_path):
             assert [int(col.sum()), col[0], col[1], col[2], col[3], col[5], col[6]] == r, (minq, pos)
         # the first read: 5N10M3S at 100 -- bases at 100..109 (not 105..114), then five skipped columns
         assert rows[100][0] >= 1 and rows[112][6] >= 1
-    # region statistics through the sweep vs the closed form on disjoint segments
-    segs = [(90, 120), (120, 215), (215, 300), (320, 400)]
+    # the closed form of the region statistics does not model such reads (the reference mixes the CIGAR as written with the shifted cursor
+    # there; the product refuses them in region / window mode): it says so instead of returning numbers
     import numpy as np
-    bed = tmp_path / "s.bed"
-    bed.write_text("".join(f"r0\t{a}\t{b}\n" for a, b in segs))
-    for minq in (0, 20):
-        rc, out, err = helpers.oracle_cli(["region", "-L", str(bed), "-q", str(minq), "-T", "1", "-T", "2", p])
-        assert rc == 0, err
-        rr = _rows(out)
-        wr, wb, wc = helpers.oracle_segment_stats(p, np.array([a for a, _ in segs], dtype=np.uint64), np.array([b for _, b in segs], dtype=np.uint64), (1, 2), min_bq=minq)
-        assert [int(r[3]) for r in rr] == [int(x) for x in wr], (minq, rr, wr)
+    with pytest.raises(Exception):
+        helpers.oracle_segment_stats(p, np.array([90], dtype=np.uint64), np.array([120], dtype=np.uint64), (1,))
