@@ -1208,7 +1208,7 @@ __global__ void k2_lead_n(RecordSoA soa, uint8_t* u, uint32_t R, ScanStats* __re
     uint8_t* cg = u + soa.off[r] + 32 + l_name;
     uint32_t first = 0, k = 0; uint64_t nlead = 0; bool found = false, zero = false;
     for (; first < n_cigar; first++) {
-        const uint32_t c = ldu32(cg + 4 * first), op = c & 15u;
+        const uint32_t c = ld_u32_any(cg + 4 * first), op = c & 15u;      // (plain loads throughout: this kernel writes CIGAR bytes, nothing here may go through the read-only path)
         if (!cig_rcons(op)) continue;
         if (op != 3u) { found = true; break; }
         nlead += c >> 4; k++; zero |= (c >> 4) == 0;

@@ -456,6 +456,37 @@ def one_case(seed, idx, keep):
             except Exception as e:
                 import traceback
                 fail(what, traceback.format_exc()[-600:])
+        # ---- several BAM files in one run: the records dealt out to two or three files (same header), every command line must print what
+        # the oracle prints for the one file (the N-way merge of coordinate-sorted files; no -m there: refused)
+        if len(reads) >= 5 and rng.random() < 0.3:
+            import struct
+            u = helpers.oracle_inflate(path)
+            first, _refs = helpers.header_first_record_offset(u)
+            raw = u.tobytes()
+            nf = rng.choice([2, 2, 3])
+            parts = [[raw[:first]] for _ in range(nf)]
+            o = first
+            while o + 4 <= len(raw):
+                bs = struct.unpack_from("<i", raw, o)[0]
+                parts[rng.randrange(nf)].append(raw[o:o + 4 + bs])
+                o += 4 + bs
+            files = []
+            for k in range(nf):
+                f = os.path.join(d, "part%d.bam" % k)
+                helpers.write_bgzf(f, b"".join(parts[k]), len(refs), block=rng.choice([300, 4000, 0xFF00]), level=rng.choice([1, 6]))
+                if os.path.exists(f + ".bai"):
+                    os.remove(f + ".bai")
+                rc, out, err = emul_cli(["index", f])
+                if rc != 0:
+                    fail("multi index rc", err.decode()[-300:])
+                files.append(f)
+            for a in rand_commands(rng, path, refs, d, bool(rg), False, base_only=lead_n)[:3]:
+                LEGS["multi"] = LEGS.get("multi", 0) + 1
+                rc1, o1, e1 = emul_cli(["depth"] + a[:-1] + files)
+                rc2, o2, e2 = helpers.oracle_cli(a)
+                if rc1 != rc2 or o1 != o2:
+                    k = next((i for i in range(min(len(o1), len(o2))) if o1[i] != o2[i]), min(len(o1), len(o2)))
+                    fail("multi %d files: " % nf + " ".join(a), "rc %d vs %d; first difference at byte %d: %r vs %r; stderr %r / %r" % (rc1, rc2, k, o1[max(0, k - 60):k + 60], o2[max(0, k - 60):k + 60], e1[-200:], e2[-200:]))
         # ---- command lines
         for a in rand_commands(rng, path, refs, d, bool(rg), mates_ok, base_only=lead_n):
             LEGS["cli"] = LEGS.get("cli", 0) + 1
