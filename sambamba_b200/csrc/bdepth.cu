@@ -162,6 +162,7 @@ struct bdepth {
     uint32_t S = 1;                       // counter sets in the current run (samples, or 1)
     DevBuf rg_ids, rg_offs, rg_samp;
     DevBuf text[2], text_tiles, text_offs, text_zero, text_samp, present;
+    int coll_pending = 0;                 // several ranks: collectives of the current run this rank has not joined yet (2: the sparse decision and the boundary table; 1: the boundary table) -- a rank that stops with an error joins them with a "failed" mark, so that the others stop too instead of waiting for it
     bool want_presence = false;           // -a with -q and a positive minimum coverage: mark the positions reads cover (k_presence)
     uint64_t batch_u = 6ull << 30;
     uint64_t chunk_blocks = 13 * 32 * 16;              // BGZF blocks per H2D chunk = per K1 sub-launch = per sub-batch: 6656 blocks = 16 K1 CTAs, ~260 MB compressed
@@ -444,6 +445,32 @@ __global__ void k_add_u32(uint32_t* __restrict__ dst, const uint32_t* __restrict
 // read starts at or before p; every rank sends the part of its counters that lies in a later rank's range
 // (7 planes, packed) with ncclSend/ncclRecv inside one group, and the owner adds it.  One all-gather of
 // (min_start, max_end) per rank tells everybody the ranges.  Also reduces the per-reference "has reads" bits.
+constexpr uint64_t PEER_FAILED = 0xFFFFFFFFFFFFFFFDull;      // in the boundary table instead of a rank's smallest start: that rank stopped with an error
+constexpr uint32_t SPARSE_PEER_FAILED = 1u << 16;            // the same in the sum of the sparse decision
+
+// A rank that stops with an error before the boundary table has been gathered still joins that all-gather (or, on a -L run, the decision
+// before it) and says so there: the other ranks then stop with an error of their own instead of waiting in the collective for ever (a
+// refusal such as "reads of one name reach too far past a shard boundary" concerns one rank only).  Best effort: errors in here are ignored.
+void abort_collectives(bdepth* h) {
+    const int p = h->coll_pending; h->coll_pending = 0;
+    if (!p || h->world <= 1 || !h->comm) return;
+    NcclApi& N = nccl(); cudaStream_t sm = h->s_main;
+    if (p == 2) {
+        uint32_t flag = SPARSE_PEER_FAILED;
+        if (h->misc.ensure(16) != cudaSuccess) return;
+        cudaMemcpyAsync(h->misc.p, &flag, 4, cudaMemcpyHostToDevice, sm);
+        N.AllReduce(h->misc.p, h->misc.p, 1, NCCL_UINT32, NCCL_SUM, h->comm, sm);
+        cudaStreamSynchronize(sm);
+        return;
+    }
+    DevBuf dpair, dall; if (dpair.ensure(16) != cudaSuccess || dall.ensure(16 * (size_t)h->world) != cudaSuccess) return;
+    uint64_t mine[2] = {PEER_FAILED, 0};
+    cudaMemcpyAsync(dpair.p, mine, 16, cudaMemcpyHostToDevice, sm);
+    N.AllGather(dpair.p, dall.p, 2, NCCL_UINT64, h->comm, sm);
+    cudaStreamSynchronize(sm);
+    dpair.release(); dall.release();
+}
+
 int exchange_boundaries(bdepth* h, uint64_t shard_min, uint64_t shard_max, bool with_counters) {
     NcclApi& N = nccl(); cudaStream_t sm = h->s_main; const int W = h->world, me = h->rank;
     cudaEvent_t e0 = h->ev[12], e1 = h->ev[13];
@@ -452,9 +479,11 @@ int exchange_boundaries(bdepth* h, uint64_t shard_min, uint64_t shard_max, bool 
     uint64_t mine[2] = {shard_min, shard_max};
     CK(cudaMemcpyAsync(dpair.p, mine, 16, cudaMemcpyHostToDevice, sm));
     NK(N.AllGather(dpair.p, dall.p, 2, NCCL_UINT64, h->comm, sm));
+    h->coll_pending = 0;
     std::vector<uint64_t> all(2 * (size_t)W);
     CK(cudaMemcpyAsync(all.data(), dall.p, 16 * (size_t)W, cudaMemcpyDeviceToHost, sm));
     CK(cudaStreamSynchronize(sm));
+    for (int r = 0; r < W; r++) if (all[2 * (size_t)r] == PEER_FAILED) return fail(h, BDEPTH_ERR_NCCL, "rank %d of the run stopped with an error (its own message says why): nothing was exchanged, no result", r);
     auto nonempty = [&](int r) { return all[2 * r] != UINT64_MAX; };
     auto own_lo = [&](int r) -> uint64_t { return r == 0 ? 0 : all[2 * r]; };      // rank 0 owns from 0 (whether it has reads or not): every rank knows where its own positions begin before it has heard of the others
     auto own_hi = [&](int r) -> uint64_t { for (int q = r + 1; q < W; q++) if (nonempty(q)) return all[2 * q]; return h->hdr.total_len; };
@@ -595,12 +624,20 @@ struct RunOut {                    // optional sinks for the kernel-level entry 
 __global__ void k_fill_u32(uint32_t* p, uint32_t v, uint64_t n) { uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; if (i < n) p[i] = v; }
 
 // The pipeline: leaves the per-position counters of the whole shard in h->counts (RUN_FULL).
+int run_pipeline_body(bdepth* h, RunMode mode, RunOut* ro, Emitter* em);
 int run_pipeline(bdepth* h, RunMode mode, RunOut* ro, Emitter* em = nullptr) {
+    const int rc = run_pipeline_body(h, mode, ro, em);
+    if (rc && rc != RC_RETRY_WINDOW) abort_collectives(h);      // (a nested run -- the restarts below -- has done that itself: nothing is pending then)
+    return rc;
+}
+int run_pipeline_body(bdepth* h, RunMode mode, RunOut* ro, Emitter* em) {
+    h->coll_pending = 0;
     int rc = init_device(h); if (rc) return rc;
     auto t_host0 = std::chrono::steady_clock::now();
     bdepth_stats& st = h->st; uint32_t launches0 = 0;
     st = bdepth_stats{}; st.gpu_launches = launches0;
     const bool sparse = mode == RUN_FULL && plan_sparse(h);
+    h->coll_pending = (mode == RUN_FULL && h->world > 1 && h->comm) ? (sparse ? 2 : 1) : 0;
     if (!sparse) { rc = prepare_shard(h); if (rc) return rc; }      // the plain path needs the whole file's member table (a lazily opened handle frames it now)
     // -m pairs reads of one name wherever they sit in the shard.  A batch is scanned as a whole (no sub-batches), and every
     // batch after the first re-reads the end of the previous one as "ghost" records -- from the earliest record that can
@@ -1188,7 +1225,9 @@ int run_pipeline(bdepth* h, RunMode mode, RunOut* ro, Emitter* em = nullptr) {
             uint32_t flag = sparse_bad ? 1u : 0u;
             CK(cudaMemcpyAsync(h->misc.p, &flag, 4, cudaMemcpyHostToDevice, sm));
             NK(nccl().AllReduce(h->misc.p, h->misc.p, 1, NCCL_UINT32, NCCL_SUM, h->comm, sm));
+            h->coll_pending = 1;
             CK(cudaMemcpyAsync(&flag, h->misc.p, 4, cudaMemcpyDeviceToHost, sm)); CK(cudaStreamSynchronize(sm));
+            if (flag >= SPARSE_PEER_FAILED) { h->coll_pending = 0; return fail(h, BDEPTH_ERR_NCCL, "another rank of the run stopped with an error (its own message says why): no result"); }
             sparse_bad = flag != 0;
         } else if (sparse_bad) return fail(h, BDEPTH_ERR_FORMAT, "the index does not describe this file (a region chunk does not end at a record); several ranks without a NCCL id cannot fall back together");
         if (sparse_bad) { h->sparse_ok = false; CK(cudaDeviceSynchronize()); return run_pipeline(h, mode, ro, em); }
