@@ -496,6 +496,30 @@ def one_case(seed, idx, keep):
                 if rc1 != rc2 or o1 != o2:
                     k = next((i for i in range(min(len(o1), len(o2))) if o1[i] != o2[i]), min(len(o1), len(o2)))
                     fail("multi %d files: " % nf + " ".join(a), "rc %d vs %d; first difference at byte %d: %r vs %r; stderr %r / %r" % (rc1, rc2, k, o1[max(0, k - 60):k + 60], o2[max(0, k - 60):k + 60], e1[-200:], e2[-200:]))
+        # ---- -F queries: the command line with a query on the whole file against the oracle with -F "" on the file reduced to the reads a
+        # Python statement of the query keeps (the oracle knows no queries; method checked in tests/test_emul_filter.py)
+        if len(reads) >= 5 and rng.random() < 0.3:
+            import test_emul_filter as tef
+            _, recs = tef.parse_all(helpers.oracle_inflate(path))
+            qk = rng.randint(0, 60)
+            sl = rng.choice([5, 40, 100])
+            cands = [("mapping_quality >= %d" % qk, lambda r: r.mapq >= qk),
+                     ("not (duplicate or failed_quality_control) and mapping_quality > %d" % (qk // 2), lambda r: not r.flag & 0x600 and r.mapq > qk // 2),
+                     ("paired and first_of_pair or mapping_quality < %d" % qk, lambda r: bool(r.flag & 1 and r.flag & 0x40) or r.mapq < qk),
+                     ("sequence_length >= %d and not secondary_alignment" % sl, lambda r: r.lseq >= sl and not r.flag & 0x100),
+                     ("reverse_strand and not supplementary", lambda r: bool(r.flag & 0x10) and not r.flag & 0x800),
+                     ("read_name =~ /^q[0-9]*[02468]$/", lambda r: len(r.name) >= 2 and r.name[:1] == b"q" and r.name[1:].isdigit() and r.name[-1:] in b"02468"),
+                     ("ref_id == 0 and position >= %d" % (refs[0][1] // 3), lambda r: r.ref == 0 and r.pos >= refs[0][1] // 3)]
+            qtxt, fn = rng.choice(cands)
+            sub = helpers.subset_bam(path, os.path.join(d, "sub.bam"), [bool(fn(r)) for r in recs])
+            for a in rand_commands(rng, path, refs, d, bool(rg), mates_ok, base_only=lead_n)[:3]:
+                a = [x for i, x in enumerate(a) if not (x == "-F" or (i and a[i - 1] == "-F"))]
+                LEGS["filter"] = LEGS.get("filter", 0) + 1
+                rc1, o1, e1 = emul_cli(["depth"] + a[:-1] + ["-F", qtxt, path])
+                rc2, o2, e2 = helpers.oracle_cli(a[:-1] + ["-F", "", sub])
+                if rc1 != rc2 or o1 != o2:
+                    k = next((i for i in range(min(len(o1), len(o2))) if o1[i] != o2[i]), min(len(o1), len(o2)))
+                    fail("filter -F '%s': " % qtxt + " ".join(a), "rc %d vs %d; first difference at byte %d: %r vs %r; stderr %r / %r" % (rc1, rc2, k, o1[max(0, k - 60):k + 60], o2[max(0, k - 60):k + 60], e1[-200:], e2[-200:]))
         # ---- command lines
         for a in rand_commands(rng, path, refs, d, bool(rg), mates_ok, base_only=lead_n):
             LEGS["cli"] = LEGS.get("cli", 0) + 1
