@@ -189,7 +189,7 @@ struct bdepth {
     bool staged = false; uint64_t staged_file_off = 0;
     DevBuf tok, lits, aux, segi, littab;              // two-phase K1: match tokens, packed literals, per-block counts, segment starts, literal tables
     DevBuf comp, descs, status, ubuf, chunk_start, entry, exitb, count, slot_base, slots, rec_base, walk_list;
-    DevBuf soa_start, soa_span, soa_meta, soa_off, soa_ncl, soa_lseq, long_list, tile_first, tile_lo, counts, ref_len_d, ref_lin0_d, scan_stats, ref_has, ref_has_all, flt_d, misc;
+    DevBuf soa_start, soa_span, soa_meta, soa_off, soa_ncl, soa_lseq, long_list, tile_first, tile_lo, counts, ref_len_d, ref_lin0_d, scan_stats, ref_has, ref_has_all, flt_d, lead_list, misc;
     uint64_t cnt_base = 0, win_len = 0;
     void* pinned = nullptr; size_t pinned_cap = 0;
     HostScratch hs;
@@ -1018,7 +1018,7 @@ int run_pipeline_body(bdepth* h, RunMode mode, RunOut* ro, Emitter* em) {
         size_t Rc = R ? R : 1;
         CK(h->soa_start.ensure(Rc * 8)); CK(h->soa_span.ensure(Rc * 4)); CK(h->soa_meta.ensure(Rc * 4)); CK(h->soa_off.ensure(Rc * 8)); CK(h->soa_ncl.ensure(Rc * 4)); CK(h->soa_lseq.ensure(Rc * 4)); CK(h->long_list.ensure(Rc * 4));
         RecordSoA soa{h->soa_start.as<uint64_t>(), h->soa_span.as<uint32_t>(), h->soa_meta.as<uint32_t>(), h->soa_off.as<int64_t>(), h->soa_ncl.as<uint32_t>(), h->soa_lseq.as<int32_t>()};
-        ScanStats zs{0, 0, 0, 0, ~0ull, 0, 0, ~0ull, 0, 0, ~0ull, 0, ~0ull, ~0ull};
+        ScanStats zs{0, 0, 0, 0, ~0ull, 0, 0, ~0ull, 0, 0, ~0ull, 0, ~0ull, ~0ull, 0};
         const int64_t ghost_below = (fix && batch_no > 0) ? (int64_t)ghost_below_abs - (int64_t)batch_u0 : INT64_MIN;
         const int64_t own_lo = (fix && h->world > 1) ? (int64_t)h->own_lo_abs_u - (int64_t)batch_u0 : INT64_MIN;           // -m on several ranks: records outside belong to the neighbours
         const int64_t own_hi = (fix && h->world > 1 && h->limit_abs_u < h->total_u) ? (int64_t)h->limit_abs_u - (int64_t)batch_u0 : INT64_MAX;
@@ -1046,8 +1046,16 @@ int run_pipeline_body(bdepth* h, RunMode mode, RunOut* ro, Emitter* em) {
 #undef K2_DECODE
         CK(cudaGetLastError()); st.gpu_launches++;
         if (R && mode != RUN_INDEX && mode != RUN_SCAN_ONLY) {      // quirk 1: CIGARs that begin with N, rewritten to what the reference's cursor makes of them (the index and the raw scan see the file as it is)
-            BD_LAUNCH((unsigned)((R + 255) / 256), 256, 0, sm, k2_lead_n)(soa, u0, (uint32_t)R, h->scan_stats.as<ScanStats>(), h->seg.on ? 1 : 0, n_flt_k2 ? h->flt_d.as<uint64_t>() : nullptr, n_flt_k2 ? h->flt_d.as<uint64_t>() + n_flt_k2 : nullptr, n_flt_k2);
-            CK(cudaGetLastError()); st.gpu_launches++;
+            // region mode proper (no window slots, no -m, one rank): the statistics of such a read are reproduced (kernels.cuh); otherwise refused
+            const bool lead_n_regions = h->seg.on && h->seg.n && !h->seg.has_u && !h->seg.has_min && !fix && h->world == 1;
+            LeadNSegs lsg{nullptr, nullptr, nullptr, nullptr, 0u, nullptr, nullptr, 1u, h->minq};
+            if (lead_n_regions) lsg = LeadNSegs{h->seg.s.as<uint64_t>(), h->seg.e.as<uint64_t>(), h->seg.pmax.as<uint64_t>(), h->seg.id.as<uint32_t>(), h->seg.n, h->seg.reads.as<uint32_t>(), h->seg.mbases.as<uint32_t>(),
+                                                (uint32_t)((h->combined || h->hdr.sample_names.size() <= 1) ? 1 : h->hdr.sample_names.size()), h->minq};
+            CK(h->lead_list.ensure(Rc * 4));
+            BD_LAUNCH((unsigned)((R + 255) / 256), 256, 0, sm, k2_lead_n_find)(soa, u0, (uint32_t)R, h->lead_list.as<uint32_t>(), h->scan_stats.as<ScanStats>());
+            BD_LAUNCH(32, 128, 0, sm, k2_lead_n_fix)(soa, u0, h->lead_list.as<uint32_t>(), h->scan_stats.as<ScanStats>(), (h->seg.on && !lead_n_regions) ? 1 : 0,
+                                                    n_flt_k2 ? h->flt_d.as<uint64_t>() : nullptr, n_flt_k2 ? h->flt_d.as<uint64_t>() + n_flt_k2 : nullptr, n_flt_k2, lsg);
+            CK(cudaGetLastError()); st.gpu_launches += 2;
         }
         if (n_flt_k2 && R) {
             BD_LAUNCH((unsigned)((R + 255) / 256), 256, 0, sm, k_ref_seen)(soa, (uint32_t)R, h->flt_d.as<uint64_t>(), h->flt_d.as<uint64_t>() + n_flt_k2, n_flt_k2, h->ref_lin0_d.as<uint64_t>(), (uint32_t)nref, h->ref_has.as<uint32_t>());
@@ -1409,7 +1417,7 @@ void bdepth_close(bdepth_t* h) {
     h->extra.clear();
     cudaSetDevice(h->device);
     h->anchors_idx.release(); h->anchors_val.release(); h->chunk_limit.release(); h->tok.release(); h->lits.release(); h->aux.release(); h->segi.release(); h->littab.release();
-    DevBuf* bufs[] = {&h->comp, &h->descs, &h->status, &h->ubuf, &h->chunk_start, &h->entry, &h->exitb, &h->count, &h->slot_base, &h->slots, &h->rec_base, &h->walk_list, &h->soa_start, &h->soa_span, &h->soa_meta, &h->soa_off, &h->soa_ncl, &h->soa_lseq, &h->long_list, &h->tile_first, &h->tile_lo, &h->counts, &h->ref_len_d, &h->ref_lin0_d, &h->scan_stats, &h->ref_has, &h->ref_has_all, &h->flt_d, &h->misc};
+    DevBuf* bufs[] = {&h->comp, &h->descs, &h->status, &h->ubuf, &h->chunk_start, &h->entry, &h->exitb, &h->count, &h->slot_base, &h->slots, &h->rec_base, &h->walk_list, &h->soa_start, &h->soa_span, &h->soa_meta, &h->soa_off, &h->soa_ncl, &h->soa_lseq, &h->long_list, &h->tile_first, &h->tile_lo, &h->counts, &h->ref_len_d, &h->ref_lin0_d, &h->scan_stats, &h->ref_has, &h->ref_has_all, &h->flt_d, &h->lead_list, &h->misc};
     for (DevBuf* b : bufs) b->release();
     h->rg_ids.release(); h->rg_offs.release(); h->rg_samp.release();
     h->text[0].release(); h->text[1].release(); h->text_tiles.release(); h->text_offs.release(); h->text_zero.release(); h->text_samp.release(); h->present.release();
@@ -1768,7 +1776,7 @@ static int run_segments(bdepth* h, const std::vector<SegDef>& segs, const uint32
         if (n_thr) CK(cudaMemcpyAsync(cov.data(), dcov.p, NS * n * n_thr * 4, cudaMemcpyDeviceToHost, sm));
         CK(cudaMemcpyAsync(reads.data(), S.reads.p, NS * n * 4, cudaMemcpyDeviceToHost, sm));
         if (has_min) { qbases.resize(NS * n); CK(cudaMemcpyAsync(qbases.data(), S.bases_reads.p, NS * n * 4, cudaMemcpyDeviceToHost, sm)); }
-        if (h->fix_mates) { mbases.resize(NS * n); CK(cudaMemcpyAsync(mbases.data(), S.mbases.p, NS * n * 4, cudaMemcpyDeviceToHost, sm)); }      // -m: what n_bases has on top of the base planes (mates.cuh)
+        if (h->fix_mates || h->world == 1) { mbases.resize(NS * n); CK(cudaMemcpyAsync(mbases.data(), S.mbases.p, NS * n * 4, cudaMemcpyDeviceToHost, sm)); }      // what n_bases has on top of the base planes: -m (mates.cuh), CIGARs that begin with N (k2_lead_n; zero otherwise)
     }
     CK(cudaEventRecord(e1, sm));
     CK(cudaStreamSynchronize(sm));

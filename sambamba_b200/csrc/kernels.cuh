@@ -471,7 +471,8 @@ struct ScanStats {      // device-side accumulators
     unsigned long long n_ghost_right;   // -m on several ranks: records at or after the shard limit (the next rank's zone)
     unsigned long long bad_rec;     // 1 + index of the first record whose name + CIGAR + sequence + qualities do not fit its block_size (~0: none)
     unsigned long long n_zone_pass, min_start_all;      // several ranks without -m: passing reads of the previous ranks' zone; smallest start over own and zone reads
-    unsigned long long lead_n;      // 1 + index of the first read whose CIGAR begins with N and cannot be reproduced (k2_lead_n; ~0: none)
+    unsigned long long lead_n;      // 1 + index of the first read whose CIGAR begins with N and cannot be reproduced (k2_lead_n_fix; ~0: none)
+    unsigned long long n_lead;      // reads whose first reference-consuming operation is N (k2_lead_n_find's list)
 };
 constexpr uint64_t START_UNPLACED = 0xFFFFFFFFFFFFFFFEull;      // RecordSoA.start of a record without a position on a known reference
 constexpr uint32_t NCL_GHOST = 1u << 31;      // RecordSoA.ncl: a record that is only re-read for the mate kernels and passes the filter (its pass bit is clear)
@@ -1190,50 +1191,100 @@ __global__ void k_presence(RecordSoA soa, uint32_t R, uint64_t cnt_base, uint64_
 // cigar[$ - 1] -- for the columns that are left (incrementPosition leaves _cur_op alone when it finds nothing, :207-218): a D counts
 // deletions there, every operation that does not consume both query and reference (N, S, I, H, P) counts reference skips
 // (depth.d:507-513).  That is exactly the CIGAR with its leading N operations taken out and as many skipped (or deleted) columns
-// appended: this kernel rewrites such a CIGAR in the inflated stream, in place and in the same number of operations (thread per record,
+// appended: k2_lead_n_find / k2_lead_n_fix rewrite such a CIGAR in the inflated stream, in place and in the same number of operations (
 // after k2_decode -- the -F query has seen the original -- and before anything walks CIGARs), and every later kernel then computes what the
 // reference computes.  If the last operation is M/=/X the reference indexes the sequence and the qualities past their end for those
 // columns (release build: unchecked reads): there is nothing to reproduce, the run is refused.  Real aligners never write a leading N;
 // the cost for ordinary reads is one look at the first reference-consuming operation.
 // Region and window statistics mix the two views: readCount and meanCoverage go through countOverlappingBases, which walks the CIGAR
-// from the read's position as written (depth.d:671-698), the percentages through the shifted cursor -- with refuse_all such a read
-// ends the run whatever its last operation is.
+// from the read's position as written (depth.d:671-698), the percentages through the shifted cursor.  Window mode, -m and several
+// ranks keep per-slot / per-pair / per-rank books of their own on top of that: with refuse_all such a read ends the run whatever
+// its last operation is.
 // (With -L only reads that overlap a region are in the reference's stream at all: flt_s / flt_e as in k_ref_seen; the others cannot end the run.)
-__global__ void k2_lead_n(RecordSoA soa, uint8_t* u, uint32_t R, ScanStats* __restrict__ st, int refuse_all, const uint64_t* __restrict__ flt_s, const uint64_t* __restrict__ flt_e, uint32_t n_flt) {
+// Region mode on one rank without -m (seg.n_seg != 0) is reproduced as well: the reducers take n_bases from the counter planes and the
+// read count from k_read_segments, both of which will see the rewritten CIGAR, so this kernel books the difference to the CIGAR as
+// written for every region the read overlaps -- (+ bases, + read) before the rewrite, (- bases, - read) after it -- into the arrays the
+// reducers add on top (seg_mbases, seg_reads: the ones the mate kernels use for the same purpose).
+struct LeadNSegs { const uint64_t* s; const uint64_t* e; const uint64_t* pmax; const uint32_t* id; uint32_t n_seg; uint32_t* reads; uint32_t* mbases; uint32_t n_samples; uint32_t minq; };
+__device__ BD_NOINLINE void lead_n_book(const LeadNSegs& sg, const RecordSoA& soa, const uint8_t* u, uint32_t r, uint32_t sign) {
+    const uint64_t rs = soa.start[r], re = rs + soa.span[r];
+    uint32_t lo = 0, hi = sg.n_seg;
+    while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (sg.s[mid] < re) lo = mid + 1; else hi = mid; }
+    const uint32_t ncl = soa.ncl[r], n_cigar = (ncl >> 8) & 0xFFFFu, l_name = ncl & 0xFFu, lseq = (uint32_t)max(soa.lseq[r], 0);
+    const uint8_t* cg = u + soa.off[r] + 32 + l_name; const uint8_t* qual = cg + 4u * n_cigar + (lseq + 1) / 2;
+    const uint32_t samp = sg.n_samples > 1 ? ((soa.meta[r] >> 2) & 63u) : 0u;
+    for (int64_t k = (int64_t)lo - 1; k >= 0; k--) {
+        if (sg.pmax[k] <= rs) break;
+        const uint64_t a = sg.s[k], b = sg.e[k];
+        if (b <= rs || a >= re) continue;
+        uint32_t rpos = 0, qpos = 0, nb = 0;                       // countOverlappingBases (depth.d:671-698) of the CIGAR as it stands in the stream
+        for (uint32_t i = 0; i < n_cigar; i++) {
+            const uint8_t* q4 = cg + 4 * i; const uint32_t c = (uint32_t)q4[0] | ((uint32_t)q4[1] << 8) | ((uint32_t)q4[2] << 16) | ((uint32_t)q4[3] << 24), len = c >> 4, op = c & 15u;
+            if (cig_match(op)) {
+                uint64_t ma = rs + rpos, mb = ma + len; if (mb > re) mb = re;
+                const uint64_t xa = ma > a ? ma : a, xb = mb < b ? mb : b;
+                for (uint64_t g = xa; g < xb; g++) { const uint32_t q = qpos + (uint32_t)(g - ma); if (q < lseq && qual[q] >= sg.minq) nb++; }
+                rpos += len; qpos += len;
+            } else if (op == 2u || op == 3u) rpos += len;
+            else if (cig_qcons(op)) qpos += len;
+        }
+        if (nb) { atomicAdd(&sg.mbases[(uint64_t)samp * sg.n_seg + sg.id[k]], sign * nb); atomicAdd(&sg.reads[(uint64_t)samp * sg.n_seg + sg.id[k]], sign); }
+    }
+}
+// Step 1, every record: does the first reference-consuming operation say N?  (the usual answer after one or two loads is no)
+__global__ void __launch_bounds__(256) k2_lead_n_find(RecordSoA soa, const uint8_t* u, uint32_t R, uint32_t* __restrict__ list, ScanStats* __restrict__ st) {
     const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= R) return;
     const uint32_t ncl = soa.ncl[r];
     if (!((soa.meta[r] & 1u) || (ncl & (NCL_GHOST | NCL_FOREIGN)))) return;      // only reads that are counted (or re-read for the mate kernels)
-    const uint32_t n_cigar = (ncl >> 8) & 0xFFFFu, l_name = ncl & 0xFFu;
-    uint8_t* cg = u + soa.off[r] + 32 + l_name;
-    uint32_t first = 0, k = 0; uint64_t nlead = 0; bool found = false, zero = false;
-    for (; first < n_cigar; first++) {
-        const uint32_t c = ld_u32_any(cg + 4 * first), op = c & 15u;      // (plain loads throughout: this kernel writes CIGAR bytes, nothing here may go through the read-only path)
+    const uint32_t n_cigar = (ncl >> 8) & 0xFFFFu;
+    const uint8_t* cg = u + soa.off[r] + 32 + (ncl & 0xFFu);
+    for (uint32_t i = 0; i < n_cigar; i++) {
+        const uint32_t op = ld_u32_any(cg + 4 * i) & 15u;       // (plain loads: step 2 writes CIGAR bytes)
         if (!cig_rcons(op)) continue;
-        if (op != 3u) { found = true; break; }
-        nlead += c >> 4; k++; zero |= (c >> 4) == 0;
-    }
-    if (!k || !found) return;            // the usual case; or nothing but N consumes the reference: the cursor never leaves the last operation and every column is a skip, as the CIGAR says
-    // ---- cold from here on
-    auto ld = [&](uint32_t j) { const uint8_t* q = cg + 4 * j; return (uint32_t)q[0] | ((uint32_t)q[1] << 8) | ((uint32_t)q[2] << 16) | ((uint32_t)q[3] << 24); };      // plain loads: these bytes are written below
-    auto st4 = [&](uint32_t j, uint32_t v) { uint8_t* q = cg + 4 * j; q[0] = (uint8_t)v; q[1] = (uint8_t)(v >> 8); q[2] = (uint8_t)(v >> 16); q[3] = (uint8_t)(v >> 24); };
-    const uint32_t last_op = ld(n_cigar - 1) & 15u;
-    if (refuse_all || last_op == 0u || last_op == 7u || last_op == 8u || zero || nlead >= (1ull << 28)) {
-        bool in_stream = true;
-        if (n_flt) {
-            const uint64_t s0 = soa.start[r], e0 = s0 + soa.span[r];
-            uint32_t lo = 0, hi = n_flt;
-            while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (flt_e[mid] <= s0) lo = mid + 1; else hi = mid; }
-            in_stream = lo < n_flt && flt_s[lo] < e0;
-        }
-        if (in_stream) atomicMin(&st->lead_n, (unsigned long long)r + 1);
+        if (op == 3u) list[(uint32_t)atomicAdd(&st->n_lead, 1ull)] = r;
         return;
     }
-    uint32_t w = 0;
-    for (uint32_t j = 0; j < n_cigar; j++) { const uint32_t c = ld(j); if (j < first && (c & 15u) == 3u) continue; st4(w++, c); }      // w <= j: a slot is read before it is overwritten
-    const uint32_t tail_op = last_op == 2u ? 2u : 3u;
-    for (uint32_t t = 0; t + 1 < k; t++) st4(w++, (1u << 4) | tail_op);                     // k operations went out, k come in: k - 1 of one column ...
-    st4(w, ((uint32_t)(nlead - (k - 1)) << 4) | tail_op);                                       // ... and the rest (every leading N had at least one column: nlead >= k)
+}
+// Step 2, the records step 1 listed (none, in any file an aligner wrote): a few blocks stride over the list.
+__global__ void __launch_bounds__(128) k2_lead_n_fix(RecordSoA soa, uint8_t* u, const uint32_t* __restrict__ list, ScanStats* __restrict__ st, int refuse_all,
+                                                     const uint64_t* __restrict__ flt_s, const uint64_t* __restrict__ flt_e, uint32_t n_flt, LeadNSegs sg) {
+    const unsigned long long n = st->n_lead;
+    for (unsigned long long li = blockIdx.x * blockDim.x + threadIdx.x; li < n; li += (unsigned long long)gridDim.x * blockDim.x) {
+        const uint32_t r = list[li];
+        const uint32_t ncl = soa.ncl[r], n_cigar = (ncl >> 8) & 0xFFFFu, l_name = ncl & 0xFFu;
+        uint8_t* cg = u + soa.off[r] + 32 + l_name;
+        auto ld = [&](uint32_t j) { const uint8_t* q = cg + 4 * j; return (uint32_t)q[0] | ((uint32_t)q[1] << 8) | ((uint32_t)q[2] << 16) | ((uint32_t)q[3] << 24); };
+        auto st4 = [&](uint32_t j, uint32_t v) { uint8_t* q = cg + 4 * j; q[0] = (uint8_t)v; q[1] = (uint8_t)(v >> 8); q[2] = (uint8_t)(v >> 16); q[3] = (uint8_t)(v >> 24); };
+        uint32_t first = 0, k = 0; uint64_t nlead = 0; bool found = false, zero = false;
+        for (; first < n_cigar; first++) {
+            const uint32_t c = ld(first), op = c & 15u;
+            if (!cig_rcons(op)) continue;
+            if (op != 3u) { found = true; break; }
+            nlead += c >> 4; k++; zero |= (c >> 4) == 0;
+        }
+        if (!k || !found) continue;          // nothing but N consumes the reference: the cursor never leaves the last operation and every column is a skip, as the CIGAR says
+        const uint32_t last_op = ld(n_cigar - 1) & 15u;
+        if (refuse_all || last_op == 0u || last_op == 7u || last_op == 8u || zero || nlead >= (1ull << 28)) {
+            bool in_stream = true;
+            if (n_flt) {
+                const uint64_t s0 = soa.start[r], e0 = s0 + soa.span[r];
+                uint32_t lo = 0, hi = n_flt;
+                while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (flt_e[mid] <= s0) lo = mid + 1; else hi = mid; }
+                in_stream = lo < n_flt && flt_s[lo] < e0;
+            }
+            if (in_stream) atomicMin(&st->lead_n, (unsigned long long)r + 1);
+            continue;
+        }
+        const bool book = sg.n_seg != 0 && (soa.meta[r] & 1u) && !(ncl & NCL_FOREIGN);
+        if (book) lead_n_book(sg, soa, u, r, 1u);
+        uint32_t w = 0;
+        for (uint32_t j = 0; j < n_cigar; j++) { const uint32_t c = ld(j); if (j < first && (c & 15u) == 3u) continue; st4(w++, c); }      // w <= j: a slot is read before it is overwritten
+        const uint32_t tail_op = last_op == 2u ? 2u : 3u;
+        for (uint32_t t = 0; t + 1 < k; t++) st4(w++, (1u << 4) | tail_op);                     // k operations went out, k come in: k - 1 of one column ...
+        st4(w, ((uint32_t)(nlead - (k - 1)) << 4) | tail_op);                                       // ... and the rest (every leading N had at least one column: nlead >= k)
+        if (book) lead_n_book(sg, soa, u, r, 0xFFFFFFFFu);
+    }
 }
 
 // With -L the reference's pileup only ever sees the reads that overlap a region (getReadsOverlapping, randomaccessmanager.d:316-338): a

@@ -167,9 +167,17 @@ def test_cigars_that_begin_with_n(tmp_path):
     for args in (["base", p], ["base", "-c", "0", p], ["base", "-q", "20", "-a", p], ["base", "-L", str(bed), p], ["base", "-F", "", "-q", "35", p],
                  ["base", "-m", p], ["base", "-m", "-q", "20", "-L", str(bed), p]):
         check_same(args)
-    # region / window statistics of such a read: the reference takes readCount and meanCoverage from the CIGAR as written (countOverlappingBases,
-    # depth.d:671-698) and the percentages from the shifted cursor -- refused with a message (reads without a leading N: as always)
-    for args in (["region", "-L", str(bed), "-T", "1", p], ["window", "-w", "50", p], ["region", "-m", "-L", str(bed), p]):
+    # region statistics of such a read: the reference takes readCount and meanCoverage from the CIGAR as written (countOverlappingBases,
+    # depth.d:671-698) and the percentages from the shifted cursor -- k2_lead_n books the difference (one rank, no -m)
+    obed = tmp_path / "o.bed"
+    obed.write_text("r0\t90\t120\tx\nr0\t100\t101\ty\nr0\t105\t300\tz\nr0\t265\t272\nr0\t290\t296\nr0\t330\t400\tw\nr0\t0\t1000\n")
+    for args in (["region", "-L", str(bed), "-T", "1", "-T", "2", p], ["region", "-L", str(bed), "-q", "20", "-T", "1", p], ["region", "-L", str(obed), "-T", "1", "-T", "3", p],
+                 ["region", "-L", str(obed), "-q", "35", "-a", "-c", "0.5", p], ["region", "-L", "r0:263-275", "-F", "", p]):
+        check_same(args)
+    for args in (["window", "-w", "50", p], ["window", "-w", "40", "-q", "20", "-T", "1", p]):       # windows that do not overlap are regions
+        check_same(args)
+    # overlapping windows and -m keep per-slot / per-pair books of their own on top of that: refused with a message (reads without a leading N: as always)
+    for args in (["window", "-w", "40", "--overlap", "10", p], ["region", "-m", "-L", str(bed), p]):
         rc, out, err = helpers.run_cli(["depth"] + args)
         assert rc != 0 and b"begins with N" in err, (args, err)
     check_same(["region", "-L", "r0:380-500", p])          # (sparse staging or not, the leading-N reads lie in front of this region ...
