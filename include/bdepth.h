@@ -48,7 +48,7 @@ typedef enum {
     BDEPTH_ERR_UNSORTED = -3,  /* header does not say SO:coordinate  (depth.d:1164)          */
     BDEPTH_ERR_NOINDEX = -4,   /* no .bai next to the file           (depth.d:1166)          */
     BDEPTH_ERR_CUDA = -5,      /* no device, CUDA error, out of device memory                */
-    BDEPTH_ERR_NCCL = -6,
+    BDEPTH_ERR_NCCL = -6,      /* a NCCL call failed -- or another rank of the run stopped with an error: every rank then returns this instead of waiting for it */
     BDEPTH_ERR_ARG = -7,       /* bad argument / unsupported combination                     */
     BDEPTH_ERR_CALLBACK = -8   /* a callback returned non-zero                               */
 } bdepth_status;
