@@ -12,7 +12,7 @@ from helpers import ROOT
 
 # (suite, -k expression): the -m suite is split in two so that the four processes take about the same time
 SUITES = [("tests/test_gpu_cli.py", None), ("tests/test_zz_gpu_mates.py", "several_batches or window_mode"),
-          ("tests/test_zz_gpu_mates.py", "not several_batches and not window_mode"), ("tests/test_zz_gpu_filter.py", None), ("tests/test_gpu_multi.py", None), ("tests/test_zzz_gpu_index.py", None)]
+          ("tests/test_zz_gpu_mates.py", "not several_batches and not window_mode"), ("tests/test_zz_gpu_filter.py", None), ("tests/test_gpu_multi.py", None), ("tests/test_zzz_gpu_index.py", None), ("tests/test_zzy_gpu_fuzz_regressions.py", None)]
 
 
 def test_the_emulation_itself():

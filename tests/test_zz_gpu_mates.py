@@ -183,54 +183,3 @@ def test_long_chains_of_one_name(tmp_path):
     assert rc == 1 and b"more than 8 reads of one name cover one position" in err, err
     p8 = tem.make_pairs_bam(str(tmp_path / "p8.bam"), 5, n_frag=20, pile=8)
     check_same(["base", "-m", "-c", "0", p8])
-
-
-def _rg(i):
-    return b"RGZg%d\x00" % i
-
-
-def test_states_move_only_on_written_columns_with_regions(tmp_path):
-    """`depth base -m -L`: writeColumn -- and detectOverlappingMates with it -- runs only on the columns of the regions (depth.d:567-591),
-    so a read that is `detected` in one region is still `detected` when the next region begins, whatever happened in between.
-    (a) it then pairs again and the pair counts once, not twice; (b) next to a read of the same name but another sample it is not
-    paired, stays `detected` and counts nothing (found by the differential fuzzer, seed 103 case 203)."""
-    refs = [("r0", 3000)]
-    rg = [("g0", "S0"), ("g1", "S1")]
-    long_cigar = [(10, 0), (500, 3), (10, 0)]
-    for third_sample, name in ((0, "same.bam"), (1, "other.bam")):
-        reads = [(0, 100, 42, 0x91, long_cigar, "ACGTACGTACGTACGTACGT", "x"),
-                 (0, 105, 35, 0x81, [(4, 0)], "ACGT", "x"),
-                 (0, 300, 24, 0x91, [(50, 0)], "ACGTA" * 10, "x"),
-                 (0, 320, 30, 0, [(2, 0)], "AC", "y")]
-        tags = [_rg(0), _rg(0), _rg(third_sample), _rg(0)]
-        p = helpers.write_bam(str(tmp_path / name), refs, reads, rg=rg, tags=tags)
-        bed = tmp_path / "two.bed"
-        bed.write_text("r0\t104\t108\nr0\t310\t400\n")
-        out = check_same(["base", "-m", "-L", str(bed), p])
-        rows = {(l.split(b"\t")[1], l.split(b"\t")[9]): l.split(b"\t") for l in out.splitlines()[1:]}
-        if third_sample == 0:
-            assert rows[(b"315", b"S0")][2] == b"1"                                  # the pair (long read on its N, third read on a base) counts once
-        else:
-            # the long read stays `detected`: nothing for its sample -- and a sample that fails the bounds ends the position (quirk 2), so the
-            # other sample's row appears only where read y lifts S0 to 1
-            assert (b"315", b"S0") not in rows and (b"315", b"S1") not in rows
-            assert rows[(b"320", b"S0")][2] == b"1" and rows[(b"320", b"S0")][8] == b"0" and rows[(b"320", b"S1")][2] == b"1"
-        check_same(["base", "-m", "-c", "0", "-L", str(bed), p])
-        check_same(["base", "-m", p])
-        check_same(["region", "-m", "-L", str(bed), p])
-
-
-def test_annotated_rows_of_columns_whose_reads_are_all_detected(tmp_path):
-    """-a -m: two reads of one name and different samples, each `detected` through a short third read of its own sample, are not a pair and stay
-    `detected`: their common columns exist but count nothing -- the reference prints them with flag n (found by the fuzzer, seed 102 case 166)."""
-    refs = [("r0", 1000)]
-    rg = [("g0", "S0"), ("g1", "S1")]
-    reads = [(0, 100, 30, 0, [(20, 0)], "ACGT" * 5, "x"), (0, 110, 30, 0, [(100, 0)], "ACGT" * 25, "x"),
-             (0, 120, 30, 0, [(100, 0)], "ACGT" * 25, "x"), (0, 125, 30, 0, [(3, 0)], "ACG", "x")]
-    p = helpers.write_bam(str(tmp_path / "det.bam"), refs, reads, rg=rg, tags=[_rg(0), _rg(0), _rg(1), _rg(1)])
-    out = check_same(["base", "-a", "-m", p])
-    rows = [l.split(b"\t") for l in out.splitlines()[1:]]
-    assert [r for r in rows if r[1] == b"150"] == [[b"r0", b"150", b"0", b"0", b"0", b"0", b"0", b"0", b"0", b"S0", b"n"], [b"r0", b"150", b"0", b"0", b"0", b"0", b"0", b"0", b"0", b"S1", b"n"]]
-    check_same(["base", "-m", p])
-    check_same(["base", "-a", "-m", "-c", "0", p])
-    check_same(["base", "-a", "-m", "-q", "10", "-L", "r0:100-300", p])
