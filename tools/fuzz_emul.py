@@ -37,6 +37,7 @@ import numpy as np      # noqa: E402
 import helpers          # noqa: E402
 
 LEGS = {}      # how many comparisons of each kind ran
+TEXTS = {}     # ranks leg: the row text every rank delivered (rank -> bytes)
 OPS = "MIDNSHP=X"
 REF_CONSUMING = (0, 2, 3, 7, 8)
 QUERY_CONSUMING = (0, 1, 4, 7, 8)
@@ -308,7 +309,7 @@ def max_same_name_overlap(reads):
     return worst
 
 
-def run_ranks(world, path, fix, tuning, minq, combined, regions, window):
+def run_ranks(world, path, fix, tuning, minq, combined, regions, window, text_cov=None):
     """`world` ranks as threads over the emulation's NCCL stand-in (as tests/test_gpu_multi.py does): every rank's owned counters, region rows
     and window rows."""
     import queue
@@ -333,6 +334,8 @@ def run_ranks(world, path, fix, tuning, minq, combined, regions, window):
                 lo, hi = st["own_lo"], st["own_hi"]
                 rr = b.run_regions(regions, [1, 3]) if regions else None
                 ww = b.run_windows(window[0], window[1], [2]) if window else None
+                if text_cov is not None:
+                    TEXTS[rank] = b.run_base_text(min_cov=text_cov)
                 q.put((rank, "ok", lo, hi, np.asarray(got)[..., lo:hi].copy(), rr, ww))
         except Exception as e:
             q.put((rank, "err", 0, 0, repr(e)[:300], None, None))
@@ -429,7 +432,10 @@ def one_case(seed, idx, keep):
                         b.set_combined(True)
                     one_r = b.run_regions(regions, [1, 3]) if regions else None
                     one_w = b.run_windows(window[0], window[1], [2]) if window else None
-                res = run_ranks(world, path, fix, tuning, minq, bool(rg), regions, window)
+                # ... and the rows of `depth base` every rank formats for its own positions, concatenated in rank order, are the one-process output
+                text_cov = rng.choice([None, 0.0, 1.0, 2.0])
+                TEXTS.clear()
+                res = run_ranks(world, path, fix, tuning, minq, bool(rg), regions, window, text_cov)
                 want_c = (helpers.oracle_counts_fix_mates(path, min_bq=minq) if fix else helpers.oracle_counts(path, min_bq=minq))[0]
                 got = np.zeros_like(want_c)
                 prev_hi, bad = 0, None
@@ -456,6 +462,15 @@ def one_case(seed, idx, keep):
                         bad = "region rows differ from one rank's"
                     if rank == 0 and window and ww != one_w:
                         bad = "window rows differ from one rank's"
+                if bad is None and text_cov is not None and res:
+                    a_ = ["base", "-c", "%g" % text_cov, "-q", str(minq)] + (["-m"] if fix else []) + (["--combined"] if rg else []) + [path]
+                    rc2, o2, e2 = helpers.oracle_cli(a_)
+                    got_t = b"".join(TEXTS.get(r_, b"") for r_ in range(world))
+                    want_t = o2.split(b"\n", 1)[1] if b"\n" in o2 else b""
+                    LEGS["ranks_text"] = LEGS.get("ranks_text", 0) + 1
+                    if rc2 != 0 or got_t != want_t:
+                        k = next((i for i in range(min(len(got_t), len(want_t))) if got_t[i] != want_t[i]), min(len(got_t), len(want_t)))
+                        bad = "row text of the ranks (-c %g): first difference at byte %d: %r vs %r" % (text_cov, k, got_t[max(0, k - 60):k + 60], want_t[max(0, k - 60):k + 60])
                 if bad is None and prev_hi != tot:
                     bad = "owned ranges end at %d of %d" % (prev_hi, tot)
                 if bad is None and not np.array_equal(got, want_c):
