@@ -1238,6 +1238,7 @@ __global__ void __launch_bounds__(256) k2_lead_n_find(RecordSoA soa, const uint8
     const uint32_t ncl = soa.ncl[r];
     if (!((soa.meta[r] & 1u) || (ncl & (NCL_GHOST | NCL_FOREIGN)))) return;      // only reads that are counted (or re-read for the mate kernels)
     const uint32_t n_cigar = (ncl >> 8) & 0xFFFFu;
+    if (n_cigar < 2) return;                                      // (an N in front of an M/=/X/D takes two operations: most reads are one M and never touch their CIGAR here)
     const uint8_t* cg = u + soa.off[r] + 32 + (ncl & 0xFFu);
     for (uint32_t i = 0; i < n_cigar; i++) {
         const uint32_t op = ld_u32_any(cg + 4 * i) & 15u;       // (plain loads: step 2 writes CIGAR bytes)
