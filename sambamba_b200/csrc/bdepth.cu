@@ -195,7 +195,7 @@ struct bdepth {
     HostScratch hs;
     std::vector<uint32_t> ref_has_host;
     // ---- optional per-read segment counting (window / region front ends), device arrays
-    struct SegSet { bool on = false; uint32_t n = 0; bool has_min = false, has_u = false; uint64_t ext_max = 0; DevBuf s, e, pmax, id, reads, minstart, bases_reads, mbases, ustart, da, dac, db, dthr, dbases, dcov; } seg;
+    struct SegSet { bool on = false; uint32_t n = 0; bool has_min = false, has_u = false; uint64_t ext_max = 0; DevBuf s, e, pmax, id, reads, minstart, bases_reads, mbases, ustart, da, dac, db, dthr, dbases, dcov, dscr; } seg;
     // ---- BAI builder (bdepth_build_index): device tables of k_index_scan, the runs / exceptions it handed out, the finished index
     struct IndexSet { DevBuf lin, lin_len, lin_base, lin_cap, n_mapped, n_unmapped, carry, ctl, runs, excs; std::vector<uint32_t> base, cap; std::vector<IndexRun> h_runs; std::vector<IndexExc> h_excs; uint64_t n_lin = 0; } ix;
     std::vector<uint8_t> built_bai;
@@ -1421,7 +1421,7 @@ void bdepth_close(bdepth_t* h) {
     for (DevBuf* b : bufs) b->release();
     h->rg_ids.release(); h->rg_offs.release(); h->rg_samp.release();
     h->text[0].release(); h->text[1].release(); h->text_tiles.release(); h->text_offs.release(); h->text_zero.release(); h->text_samp.release(); h->present.release();
-    h->seg.s.release(); h->seg.e.release(); h->seg.pmax.release(); h->seg.id.release(); h->seg.reads.release(); h->seg.minstart.release(); h->seg.bases_reads.release(); h->seg.mbases.release(); h->seg.ustart.release(); h->seg.da.release(); h->seg.dac.release(); h->seg.db.release(); h->seg.dthr.release(); h->seg.dbases.release(); h->seg.dcov.release();
+    h->seg.s.release(); h->seg.e.release(); h->seg.pmax.release(); h->seg.id.release(); h->seg.reads.release(); h->seg.minstart.release(); h->seg.bases_reads.release(); h->seg.mbases.release(); h->seg.ustart.release(); h->seg.dscr.release(); h->seg.da.release(); h->seg.dac.release(); h->seg.db.release(); h->seg.dthr.release(); h->seg.dbases.release(); h->seg.dcov.release();
     { auto& X = h->ix; X.lin.release(); X.lin_len.release(); X.lin_base.release(); X.lin_cap.release(); X.n_mapped.release(); X.n_unmapped.release(); X.carry.release(); X.ctl.release(); X.runs.release(); X.excs.release(); }
     h->m_hash.release(); h->m_flag.release(); h->m_flt.release(); h->m_ctl.release(); h->fprog_d.release();
     if (h->comm) { nccl().CommDestroy(h->comm); h->comm = nullptr; }
@@ -1702,7 +1702,6 @@ int bdepth_run_base_text(bdepth_t* h, const bdepth_text_opts* o, bdepth_text_cb 
 struct SegDef { uint32_t ref, start, end; uint32_t cov_ext = 0;  /* thresholds are counted from start - cov_ext */ uint32_t min_read_start = 0;  /* != 0: only reads starting at/after it count (quirk 6) */ };
 static int run_segments(bdepth* h, const std::vector<SegDef>& segs, const uint32_t* thr, size_t n_thr,
                         std::vector<uint32_t>& reads, std::vector<uint32_t>& bases, std::vector<uint32_t>& cov) {
-    if (n_thr > 16) return fail(h, BDEPTH_ERR_ARG, "at most 16 coverage thresholds are supported");
     int rc = init_device(h); if (rc) return rc;
     const size_t n = segs.size();
     const size_t NS = (h->combined || h->hdr.sample_names.size() <= 1) ? 1 : h->hdr.sample_names.size();   // layout: [sample][..]
@@ -1737,7 +1736,7 @@ static int run_segments(bdepth* h, const std::vector<SegDef>& segs, const uint32
     CK(cudaMemset(S.reads.p, 0, NS * nn * 4)); CK(cudaMemset(S.bases_reads.p, 0, NS * nn * 4)); CK(cudaMemset(S.mbases.p, 0, NS * nn * 4));
     if (n) CK(cudaMemcpy(S.minstart.p, ms.data(), n * 8, cudaMemcpyHostToDevice));
     CK(S.ustart.ensure(nn * 8)); if (n) CK(cudaMemcpy(S.ustart.p, us.data(), n * 8, cudaMemcpyHostToDevice));
-    CK(S.da.ensure(nn * 8)); CK(S.dac.ensure(nn * 8)); CK(S.db.ensure(nn * 8)); CK(S.dthr.ensure(64)); CK(S.dbases.ensure(NS * nn * 4)); CK(S.dcov.ensure(NS * nn * 4 * nt1));
+    CK(S.da.ensure(nn * 8)); CK(S.dac.ensure(nn * 8)); CK(S.db.ensure(nn * 8)); CK(S.dthr.ensure(std::max<size_t>(64, n_thr * 4))); if (n_thr > 16) CK(S.dscr.ensure(NS * nn * 4)); CK(S.dbases.ensure(NS * nn * 4)); CK(S.dcov.ensure(NS * nn * 4 * nt1));
     S.has_min = has_min; S.has_u = has_u; S.ext_max = ext_max;
     S.on = true; S.n = (uint32_t)n;
     rc = run_all_inputs(h);
@@ -1761,8 +1760,14 @@ static int run_segments(bdepth* h, const std::vector<SegDef>& segs, const uint32
     CK(cudaMemsetAsync(dbases.p, 0, NS * nn * 4, sm)); CK(cudaMemsetAsync(dcov.p, 0, NS * nn * 4 * nt1, sm));
     if (n) {
         for (size_t si = 0; si < NS; si++) {
-            BD_LAUNCH((unsigned)((n * 32 + 255) / 256), 256, 0, sm, k_segment_stats)(h->counts.as<uint32_t>() + (uint64_t)si * N_PLANES * h->win_len, h->win_len, da.as<uint64_t>(), dac.as<uint64_t>(), db.as<uint64_t>(), (uint32_t)n, dthr.as<uint32_t>(), (uint32_t)n_thr, dbases.as<uint32_t>() + si * n, dcov.as<uint32_t>() + si * n * nt1);
-            CK(cudaGetLastError()); h->st.gpu_launches++;
+            // the kernel keeps 16 threshold counters in registers: more thresholds (the reference has no limit) take further passes over the segments,
+            // whose base sums go to a scratch array (they were added by the first pass)
+            for (size_t t0 = 0; t0 < std::max<size_t>(n_thr, 1); t0 += 16) {
+                const uint32_t nt = n_thr ? (uint32_t)std::min<size_t>(16, n_thr - t0) : 0u;
+                BD_LAUNCH((unsigned)((n * 32 + 255) / 256), 256, 0, sm, k_segment_stats)(h->counts.as<uint32_t>() + (uint64_t)si * N_PLANES * h->win_len, h->win_len, da.as<uint64_t>(), dac.as<uint64_t>(), db.as<uint64_t>(), (uint32_t)n, dthr.as<uint32_t>() + t0, nt,
+                                                                                          (t0 ? S.dscr.as<uint32_t>() : dbases.as<uint32_t>()) + si * n, dcov.as<uint32_t>() + si * n * nt1 + t0 * n);
+                CK(cudaGetLastError()); h->st.gpu_launches++;
+            }
         }
         if (h->world > 1 && h->comm) {   // per-segment partial sums are additive over ranks; a failed collective is an error, never a partial sum handed out as the result
             NcclApi& N = nccl();

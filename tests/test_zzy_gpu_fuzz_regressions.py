@@ -145,3 +145,14 @@ def test_annotated_rows_of_columns_whose_reads_are_all_detected(tmp_path):
     check_same(["base", "-m", p])
     check_same(["base", "-a", "-m", "-c", "0", p])
     check_same(["base", "-a", "-m", "-q", "10", "-L", "r0:100-300", p])
+
+
+def test_more_than_sixteen_thresholds(tmp_path):
+    """-T may be given any number of times (depth.d has no limit); the reducer keeps 16 counters in registers and takes further passes."""
+    p = helpers.gen_bam(str(tmp_path / "t.bam"), "--preset", "tiny", "-n", 6000, "--pairs", 6, "-t", 2)
+    T = sum((["-T", str(t)] for t in list(range(0, 36)) + [60, 100]), [])
+    bed = tmp_path / "r.bed"
+    bed.write_text("ctgA\t100\t900\tgeneA\nctgA\t850\t1200\tgeneB\nctgC\t0\t52000\n")
+    for args in (["region", "-L", str(bed)], ["region", "-L", "ctgA:1-5000", "-q", "20"], ["window", "-w", "1000"], ["window", "-w", "700", "--overlap", "200"], ["region", "-m", "-L", str(bed)]):
+        out, _ = check_same(args + T + [p])
+        assert out.splitlines()[0].count(b"percentage") == 38

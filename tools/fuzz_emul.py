@@ -275,7 +275,7 @@ def rand_commands(rng, path, refs, d, has_rg, mates_ok, base_only=False):
                 a += ["-L", rand_bed(rng, refs, os.path.join(d, "b%d.bed" % len(cmds)))]
         elif mode == "region":
             a += ["-L", rand_region(rng, refs) if rng.random() < 0.4 else rand_bed(rng, refs, os.path.join(d, "b%d.bed" % len(cmds)))]
-            for _ in range(rng.choice([0, 1, 3])):
+            for _ in range(rng.choice([0, 1, 3, 3, 20])):
                 a += ["-T", str(rng.choice([0, 1, 2, 5, 10, 30]))]
         else:
             # (a reducer block per window costs ~2 ms under the emulation: keep the number of windows in the low thousands)
