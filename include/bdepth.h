@@ -167,7 +167,9 @@ int bdepth_set_min_baseq(bdepth_t* h, uint32_t min_base_quality);
 int bdepth_set_fix_mates(bdepth_t* h, int on);
 /* --combined (depth.d:1131): one counter set for all samples.  Default: one per @RG sample (<= 64). */
 int bdepth_set_combined(bdepth_t* h, int combined);
-/* Restrict runs to reads overlapping these regions (any order; merged internally).  n = 0 clears. */
+/* Restrict runs to reads overlapping these regions (any order; merged internally).  n = 0 clears.  Regions that hold no position
+ * (start >= end, or start behind the reference's end) are dropped; if none is left the restriction is cleared as with n = 0 -- a host that
+ * wants "nothing" for such a query (the reference prints its header only) does not run at all, as the CLI does. */
 int bdepth_set_regions(bdepth_t* h, const bdepth_region* regions, size_t n);
 /* Multi-GPU: this process handles shard `rank` of `world` (BGZF virtual-offset ranges cut at BAI
  * linear-index record starts).  nccl_unique_id (128 bytes, identical on all ranks, from

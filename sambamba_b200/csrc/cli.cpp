@@ -324,7 +324,14 @@ int main(int argc, char** argv) {
         }
     }
     if (c.mode == 0) {
-        if (has_bed) { if (regs.empty()) { c.out.flush(); bdepth_close(c.h); return 0; } bdepth_set_regions(c.h, regs.data(), regs.size()); }
+        if (has_bed) {
+            // no region at all, or none that holds a position (a region string the wrong way round, one that begins behind its reference's end):
+            // no read overlaps it, no row is required -- the header is all the reference prints (an empty region list would mean "everything" to the library)
+            bool any = false;
+            for (auto& g : regs) any |= g.start < g.end && g.start < bdepth_ref_length(c.h, (int)g.ref_id);
+            if (!any) { c.out.flush(); bdepth_close(c.h); return 0; }
+            bdepth_set_regions(c.h, regs.data(), regs.size());
+        }
         // rows are formatted on the GPU (one counter set, or one row per sample and position); base_tile_cb is the host-side
         // formatter a caller of bdepth_run_base would use
         if (c.combined || c.samples.size() <= 64) { bdepth_text_opts to{c.min_cov, c.max_cov, c.annotate ? 1 : 0}; rc = bdepth_run_base_text(c.h, &to, text_cb, &c); }

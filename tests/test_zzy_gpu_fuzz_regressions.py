@@ -156,3 +156,14 @@ def test_more_than_sixteen_thresholds(tmp_path):
     for args in (["region", "-L", str(bed)], ["region", "-L", "ctgA:1-5000", "-q", "20"], ["window", "-w", "1000"], ["window", "-w", "700", "--overlap", "200"], ["region", "-m", "-L", str(bed)]):
         out, _ = check_same(args + T + [p])
         assert out.splitlines()[0].count(b"percentage") == 38
+
+
+def test_region_strings_that_hold_no_position(tmp_path):
+    """`-L chr:200-100` or a region behind the reference's end: no read overlaps it and no row is required -- the reference prints its header
+    only; the CLI must not hand the library an empty region list (which means "everything")."""
+    p = helpers.gen_bam(str(tmp_path / "t.bam"), "--preset", "tiny", "-n", 3000, "-t", 2)
+    for args in (["base", "-L", "ctgA:200-100", p], ["base", "-c", "0", "-L", "ctgA:200-100", p], ["base", "-L", "ctgB:99999999", p], ["base", "-c", "0", "-a", "-L", "ctgA:99999999-999999999", p],
+                 ["region", "-L", "ctgA:200-100", p], ["region", "-L", "ctgB:99999999", "-T", "1", p], ["base", "-L", "ctgA:200-201", p]):
+        out, _ = check_same(args)
+        if args[0] == "base" and args[-2] != "ctgA:200-201":
+            assert out.count(b"\n") == 1
