@@ -223,6 +223,8 @@ def rand_region(rng, refs):
     if k < 0.3:
         return name
     a = rng.randrange(L)
+    if k < 0.36:                           # region strings that hold no position, or reach past the reference's end
+        return rng.choice(["%s:%d-%d" % (name, a + 2, a + 1), "%s:%d" % (name, L + 5), "%s:%d-%d" % (name, L + 1, L + 100), "%s:%d-%d" % (name, max(1, L - 5), L + 50), "%s:%d" % (name, a + 1)])
     b = min(L, a + rng.choice([1, 10, 100, 1000, 5000]))
     return "%s:%d-%d" % (name, a + 1, max(a + 1, b))
 
