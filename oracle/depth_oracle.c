@@ -924,7 +924,25 @@ static int opt_take(Args *a, const char *lng, char sht, int has_val, const char 
     }
     return found;
 }
-static void thr_cb(const char *v, void *ud) { Printer *p = ud; p->thr = realloc(p->thr, (p->n_thr + 1) * sizeof(uint32_t)); p->thr[p->n_thr++] = (uint32_t)strtoul(v, NULL, 10); }
+/* std.getopt converts option values with std.conv.to!T; its exceptions end depth_main with "sambamba-depth: <message>", exit code 1
+ * (depth.d:1236-1243).  Unsigned types: digits only (no sign), overflow is an error; double: what strtod consumes entirely. */
+static const char *g_conv_err = NULL; static char g_conv_buf[160];
+static int conv_unsigned(const char *s, unsigned long long maxv, const char *type, unsigned long long *out) {
+    if (!s || !*s) { snprintf(g_conv_buf, sizeof g_conv_buf, "Unexpected end of input when converting from type string to type %s", type); g_conv_err = g_conv_buf; return 0; }
+    unsigned long long v = 0;
+    for (const char *c = s; *c; c++) {
+        if (*c < '0' || *c > '9') { snprintf(g_conv_buf, sizeof g_conv_buf, "Unexpected '%c' when converting from type string to type %s", *c, type); g_conv_err = g_conv_buf; return 0; }
+        if (v > (maxv - (unsigned)(*c - '0')) / 10) { g_conv_err = "Conversion positive overflow"; return 0; }
+        v = v * 10 + (unsigned)(*c - '0');
+    }
+    *out = v; return 1;
+}
+static int conv_double(const char *s, double *out) {
+    char *end = NULL; if (!s || !*s || *s == ' ' || *s == '\t') { g_conv_err = "no digits seen"; return 0; }
+    double v = strtod(s, &end); if (end == s || *end) { g_conv_err = "no digits seen"; return 0; }
+    *out = v; return 1;
+}
+static void thr_cb(const char *v, void *ud) { Printer *p = ud; unsigned long long u = 0; if (!conv_unsigned(v, 0xFFFFFFFFull, "uint", &u)) return; p->thr = realloc(p->thr, (p->n_thr + 1) * sizeof(uint32_t)); p->thr[p->n_thr++] = (uint32_t)u; }
 
 typedef struct { int nthreads; size_t max_file_bytes; double t_inflate, t_sweep; uint64_t columns; uint64_t file_bytes; } RunStats;
 static RunStats g_stats;
@@ -944,9 +962,10 @@ int oracle_depth_main(int argc, char **argv_in, FILE *out_default, int inflate_t
     if (opt_take(&a, "filter", 'F', 1, &query, 0, NULL, NULL) < 0) BAIL("Missing value for argument -F.");
     opt_take(&a, "output-filename", 'o', 1, &out_fn, 0, NULL, NULL);
     v = NULL; if (opt_take(&a, "nthreads", 't', 1, &v, 0, NULL, NULL) > 0 && v && inflate_threads <= 0) inflate_threads = atoi(v);
-    v = NULL; if (opt_take(&a, "min-coverage", 'c', 1, &v, 0, NULL, NULL) > 0) P.min_cov = strtod(v, NULL);
-    v = NULL; if (opt_take(&a, "max-coverage", 'C', 1, &v, 0, NULL, NULL) > 0) P.max_cov = strtod(v, NULL);
-    v = NULL; if (opt_take(&a, "min-base-quality", 'q', 1, &v, 0, NULL, NULL) > 0) P.min_bq = atoi(v);
+    unsigned long long uv = 0; g_conv_err = NULL;
+    v = NULL; if (opt_take(&a, "min-coverage", 'c', 1, &v, 0, NULL, NULL) > 0 && !conv_double(v, &P.min_cov)) BAIL("%s", g_conv_err);
+    v = NULL; if (opt_take(&a, "max-coverage", 'C', 1, &v, 0, NULL, NULL) > 0 && !conv_double(v, &P.max_cov)) BAIL("%s", g_conv_err);
+    v = NULL; if (opt_take(&a, "min-base-quality", 'q', 1, &v, 0, NULL, NULL) > 0) { if (!conv_unsigned(v, 255, "ubyte", &uv)) BAIL("%s", g_conv_err); P.min_bq = (int)uv; }      /* ubyte min_base_quality, depth.d:280 */
     if (opt_take(&a, "annotate", 'a', 0, NULL, 0, NULL, NULL) > 0) P.annotate = 1;
     if (opt_take(&a, "combined", 0, 0, NULL, 0, NULL, NULL) > 0) P.combined = 1;
     if (opt_take(&a, "fix-mate-overlaps", 'm', 0, NULL, 0, NULL, NULL) > 0) P.fix_mates = 1;
@@ -963,11 +982,11 @@ int oracle_depth_main(int argc, char **argv_in, FILE *out_default, int inflate_t
         if (P.report_zero) P.min_cov = 0;
         if (P.min_cov == 0) P.report_zero = 1;
     } else if (P.mode == 1) {
-        opt_take(&a, "cov-threshold", 'T', 1, NULL, 1, thr_cb, &P);
+        opt_take(&a, "cov-threshold", 'T', 1, NULL, 1, thr_cb, &P); if (g_conv_err) BAIL("%s", g_conv_err);
     } else {
-        v = NULL; if (opt_take(&a, "window-size", 'w', 1, &v, 0, NULL, NULL) > 0) P.window_size = strtoull(v, NULL, 10);
-        v = NULL; if (opt_take(&a, "overlap", 0, 1, &v, 0, NULL, NULL) > 0) P.overlap = strtoull(v, NULL, 10);
-        opt_take(&a, "cov-threshold", 'T', 1, NULL, 1, thr_cb, &P);
+        v = NULL; if (opt_take(&a, "window-size", 'w', 1, &v, 0, NULL, NULL) > 0) { if (!conv_unsigned(v, 0xFFFFFFFFFFFFFFF0ull, "ulong", &uv)) BAIL("%s", g_conv_err); P.window_size = uv; }
+        v = NULL; if (opt_take(&a, "overlap", 0, 1, &v, 0, NULL, NULL) > 0) { if (!conv_unsigned(v, 0xFFFFFFFFFFFFFFF0ull, "ulong", &uv)) BAIL("%s", g_conv_err); P.overlap = uv; }
+        opt_take(&a, "cov-threshold", 'T', 1, NULL, 1, thr_cb, &P); if (g_conv_err) BAIL("%s", g_conv_err);
     }
     if (a.argc < 2) BAIL("no input BAM given");
     if (a.argc > 2) BAIL("oracle supports a single BAM file");   /* multi-BAM merge is out of scope */

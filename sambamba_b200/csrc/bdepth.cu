@@ -1808,7 +1808,9 @@ static int deliver_one(bdepth* h, const SegDef& sd, size_t i, size_t n, size_t n
 }
 
 int bdepth_run_windows(bdepth_t* h, uint32_t window, uint32_t overlap, const uint32_t* thr, size_t n_thr, bdepth_stat_cb cb, void* user) {
+    if (!h) return BDEPTH_ERR_ARG;
     if (window == 0) return fail(h, BDEPTH_ERR_ARG, "positive window size must be specified");
+    if (!(overlap < window)) return fail(h, BDEPTH_ERR_ARG, "specified overlap is larger than window size");      // (depth.d:959; a step of zero has no next window)
     // -m: a window is a segment with an update range (ring slots are updated before their window begins when the step does
     // not divide the window) and, for reference 0's first slots, without a first occurrence; mates.cuh replays both.
     const uint32_t step = window - overlap;

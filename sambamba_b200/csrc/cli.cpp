@@ -143,6 +143,25 @@ struct Ctx {
     int last_ref_announced = -2;
 };
 
+// std.getopt hands the option text to std.conv.to!T, whose exceptions end depth_main with "sambamba-depth: <message>" and exit code 1
+// (depth.d:1236-1243): a value that is no number of the option's type is an error, not a zero.
+static bool conv_unsigned(const std::string& s, unsigned long long maxv, const char* type, unsigned long long& out, std::string& err) {
+    if (s.empty()) { err = std::string("Unexpected end of input when converting from type string to type ") + type; return false; }
+    unsigned long long v = 0;
+    for (char ch : s) {
+        if (ch < '0' || ch > '9') { err = std::string("Unexpected '") + ch + "' when converting from type string to type " + type; return false; }
+        if (v > (maxv - (unsigned)(ch - '0')) / 10) { err = "Conversion positive overflow"; return false; }      // (maxv < 2^64 - 9 for every caller)
+        v = v * 10 + (unsigned)(ch - '0');
+    }
+    out = v; return true;
+}
+static bool conv_double(const std::string& s, double& out, std::string& err) {
+    if (s.empty()) { err = "Unexpected end of input when converting from type string to type double"; return false; }
+    char* end = nullptr; double v = strtod(s.c_str(), &end);
+    if (end == s.c_str() || *end || s[0] == ' ' || s[0] == '\t') { err = "no digits seen"; return false; }
+    out = v; return true;
+}
+
 static int base_tile_cb(void* user, const bdepth_tile* t) {
     Ctx& c = *(Ctx*)user; Out& o = c.out;
     const std::string& name = c.ref_names[t->ref_id];
@@ -246,12 +265,13 @@ int main(int argc, char** argv) {
     if (opt_take(a, "filter", 'F', true, &v) > 0) { query = v.back(); has_query = true; } v.clear();
     if (opt_take(a, "output-filename", 'o', true, &v) > 0) out_fn = v.back();
     v.clear();
-    opt_take(a, "nthreads", 't', true, &v); v.clear();                                      // accepted for compatibility
-    if (opt_take(a, "min-coverage", 'c', true, &v) > 0) c.min_cov = strtod(v.back().c_str(), nullptr);
+    opt_take(a, "nthreads", 't', true, &v); v.clear();                                      // accepted for compatibility (its value is not looked at)
+    std::string cerr_; unsigned long long uv = 0;
+    if (opt_take(a, "min-coverage", 'c', true, &v) > 0 && !conv_double(v.back(), c.min_cov, cerr_)) return die(cerr_);
     v.clear();
-    if (opt_take(a, "max-coverage", 'C', true, &v) > 0) c.max_cov = strtod(v.back().c_str(), nullptr);
+    if (opt_take(a, "max-coverage", 'C', true, &v) > 0 && !conv_double(v.back(), c.max_cov, cerr_)) return die(cerr_);
     v.clear();
-    if (opt_take(a, "min-base-quality", 'q', true, &v) > 0) min_bq = atoi(v.back().c_str());
+    if (opt_take(a, "min-base-quality", 'q', true, &v) > 0) { if (!conv_unsigned(v.back(), 255, "ubyte", uv, cerr_)) return die(cerr_); min_bq = (int)uv; }      // ubyte min_base_quality, depth.d:280
     v.clear();
     if (opt_take(a, "annotate", 'a', false, nullptr) > 0) c.annotate = true;
     if (opt_take(a, "combined", 0, false, nullptr) > 0) c.combined = true;
@@ -272,12 +292,12 @@ int main(int argc, char** argv) {
         c.out.ch('\n');
     } else {
         if (c.mode == 2) {
-            if (opt_take(a, "window-size", 'w', true, &v) > 0) window = (uint32_t)strtoull(v.back().c_str(), nullptr, 10);
+            if (opt_take(a, "window-size", 'w', true, &v) > 0) { if (!conv_unsigned(v.back(), 0xFFFFFFFFFFFFFFF0ull, "ulong", uv, cerr_)) return die(cerr_); if (uv > 0xFFFFFFFFull) return die("window sizes of 2^32 and more are not supported"); window = (uint32_t)uv; }
     v.clear();
-            if (opt_take(a, "overlap", 0, true, &v) > 0) overlap = (uint32_t)strtoull(v.back().c_str(), nullptr, 10);
+            if (opt_take(a, "overlap", 0, true, &v) > 0) { if (!conv_unsigned(v.back(), 0xFFFFFFFFFFFFFFF0ull, "ulong", uv, cerr_)) return die(cerr_); overlap = uv > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)uv; }
     v.clear();
         }
-        opt_take(a, "cov-threshold", 'T', true, &v); for (auto& s : v) c.thr.push_back((uint32_t)strtoul(s.c_str(), nullptr, 10));
+        opt_take(a, "cov-threshold", 'T', true, &v); for (auto& s : v) { if (!conv_unsigned(s, 0xFFFFFFFFull, "uint", uv, cerr_)) return die(cerr_); c.thr.push_back((uint32_t)uv); }
     v.clear();
         if (c.mode == 2) {
             if (!(window > 0)) return die("positive window size must be specified");

@@ -167,3 +167,21 @@ def test_region_strings_that_hold_no_position(tmp_path):
         out, _ = check_same(args)
         if args[0] == "base" and args[-2] != "ctgA:200-201":
             assert out.count(b"\n") == 1
+
+
+def test_option_values_that_are_no_numbers(tmp_path):
+    """std.getopt converts with std.conv.to!T and depth_main turns the exception into "sambamba-depth: <message>", exit code 1, nothing on
+    stdout (depth.d:1236-1243; ubyte min_base_quality :280): -q 256 is an error, not a wrap-around; the ABI refuses a window step of zero."""
+    p = helpers.gen_bam(str(tmp_path / "t.bam"), "--preset", "tiny", "-n", 2000, "-t", 2)
+    for args in (["base", "-q", "256"], ["base", "-q", "-1"], ["base", "-q", "abc"], ["base", "-c", "x"], ["window", "-w", "-5"], ["window", "-w", "10", "--overlap", "3x"],
+                 ["region", "-L", "ctgA", "-T", "-1"], ["region", "-L", "ctgA", "-T", "4294967296"], ["window", "-w", "100", "-T", "3", "-T", "x"]):
+        rc, out, err = helpers.run_cli(["depth"] + args + [p])
+        rc2, out2, err2 = helpers.oracle_cli(args + [p])
+        assert rc == 1 and rc2 == 1 and out == b"" and out2 == b"" and err.startswith(b"sambamba-depth: ") and err == err2, (args, err, err2)
+    for args in (["base", "-q", "255"], ["base", "-c", "1e1", "-C", "inf"], ["region", "-L", "ctgA", "-T", "7"]):
+        check_same(args + [p])
+    import sambamba_b200 as sb
+    with sb.BDepth(p) as b:
+        for w, o in ((10, 10), (10, 11), (0, 0)):
+            with pytest.raises(sb.BDepthError):
+                b.run_windows(w, o, [])
